@@ -1,0 +1,255 @@
+/*
+ * mhb.h -- C ABI of libmhb (megahit_b200): the B200-native SdBG-construction hot path of MEGAHIT.
+ *
+ * Plain pointers and sizes only; no C++ or torch types.  Status: 0 = ok, non-zero = error
+ * (mhb_last_error() returns the message).  There is NO CPU fallback: every compute entry point fails
+ * with MHB_ERR_CUDA when no CUDA device / kernel image is available.
+ *
+ * Reference interfaces replaced (paths relative to voutcn/megahit v1.2.9 src/):
+ *   mhb_count_*     <- KmerCounter (sorting/kmer_counter.{h,cpp}) driven by main_kmer_count
+ *                      (main_sdbg_build.cpp:35-86) through BaseSequenceSortingEngine::Run
+ *                      (sorting/base_engine.cpp:143-211)
+ *   mhb_sort_*      <- SelectSortingFunc / kmlib::kmsort (sorting/kmsort_selector.cpp:61-64,
+ *                      kmlib/kmsort.h:43-122): sort fixed-width uint32 records by their leading words
+ *   mhb_s2s_*       <- SeqToSdbg (sorting/seq_to_sdbg.{h,cpp}) driven by main_seq2sdbg
+ *                      (main_sdbg_build.cpp:158-224)
+ *   *_run           <- the `megahit_core count` / `megahit_core seq2sdbg` sub-commands themselves
+ *                      (main.cpp:82-86), same option names and on-disk formats
+ *
+ * Layers:
+ *   1. device level  -- raw device pointers + a cudaStream_t (as void*); the caller (PyTorch, or the
+ *                       host pipeline below) owns all memory.  Used by tests, bench.py and the
+ *                       multi-GPU driver (megahit_b200/multigpu.py).
+ *   2. host level    -- host buffers in, host buffers out (H2D/D2H inside).
+ *   3. file level    -- reads/writes the reference's on-disk formats; what `megahit_core` calls.
+ */
+#ifndef MHB_H
+#define MHB_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MHB_OK 0
+#define MHB_ERR_ARG 1
+#define MHB_ERR_CUDA 2
+#define MHB_ERR_IO 3
+#define MHB_ERR_NOMEM 4
+
+#define MHB_NUM_BUCKETS 65536 /* sorting/base_engine.h: kNumBuckets (8-base prefix) */
+#define MHB_MAX_MUL 65535     /* sdbg/sdbg_def.h:12 kMaxMul */
+#define MHB_MAX_K 255         /* sdbg/sdbg_def.h:20 kMaxK */
+#define MHB_SENTINEL_OFFSET 0xFFFFFFFFu /* kmer_counter.h:49 */
+
+const char *mhb_last_error(void);
+const char *mhb_version(void);
+/* number of visible CUDA devices (0 when none); never fails */
+int mhb_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Geometry helpers (pure host arithmetic, callable without a GPU)
+ * ------------------------------------------------------------------------------------------- */
+/* words per `count` sort record on the device: the canonical (k+1)-mer left-aligned, then zero bits,
+ * then prev<<3|next in the low 6 bits of the last word (the reference carries a 64-bit read_info
+ * payload instead, kmer_counter.cpp:240-249; we re-derive read positions in mhb_count_mark_mercy). */
+uint32_t mhb_count_record_words(uint32_t k);
+/* words per edge in `.edges` files: ceil((2(k+1)+16)/32)  (kmer_counter.cpp:79-80) */
+uint32_t mhb_words_per_edge(uint32_t k);
+/* words per seq2sdbg sort record: ceil((2k+20)/32)  (seq_to_sdbg.cpp:510-512) */
+uint32_t mhb_s2s_record_words(uint32_t k);
+/* byte positions (0 = least significant byte of the last word) the LSD radix sort visits, ascending;
+ * returns the count, at most 4*words. */
+uint32_t mhb_count_sort_bytes(uint32_t k, uint8_t *bytes);
+uint32_t mhb_s2s_sort_bytes(uint32_t k, uint8_t *bytes);
+/* bytes of scratch mhb_sort_records needs for n records */
+size_t mhb_sort_workspace_bytes(uint64_t n, uint32_t words);
+
+/* ---------------------------------------------------------------------------------------------
+ * 1. Device level.  All pointers are device pointers unless marked host.  `stream` is a cudaStream_t.
+ * ------------------------------------------------------------------------------------------- */
+
+/* A read library resident on the device in `.bin` layout (sequence_package.h:224-240): per read a
+ * u32 length followed by ceil(len/16) words, forward (file) orientation.  The device code applies the
+ * reversal that KmerCounter::Initialize does at load time (kmer_counter.cpp:61,72).
+ * fixed_len > 0: every read has that length, record r starts at word r*(1+ceil(fixed_len/16));
+ * rec_off/edge_off may then be NULL.  Otherwise rec_off[n_reads+1] gives each record's first word and
+ * edge_off[n_reads+1] the exclusive prefix sum of max(0, len-k).
+ * `bin` must be 16-byte aligned and its allocation padded to a multiple of 16 bytes. */
+typedef struct {
+  const uint32_t *bin;
+  uint64_t bin_words;
+  uint64_t n_reads;
+  uint32_t fixed_len;
+  const uint64_t *rec_off;
+  const uint64_t *edge_off;
+} mhb_dev_reads;
+
+/* A1-A3: canonical (k+1)-mer extraction (kmer_counter.cpp:114-252).  Writes n_edges records of
+ * mhb_count_record_words(k) words to `records` and adds the 256-bin histogram of record byte
+ * `hist_byte` into hist256 (uint64[256], caller-zeroed; pass NULL to skip). */
+int mhb_count_extract(void *stream, const mhb_dev_reads *reads, uint32_t k, uint32_t *records,
+                      uint64_t n_edges, uint64_t *hist256, int hist_byte);
+
+/* A4: stable LSD radix sort of n records of `words` uint32 each, ascending on the given byte
+ * positions (least significant first).  `first_hist` = histogram of bytes[0] if the caller already has
+ * it (from mhb_count_extract / mhb_s2s_extract), else NULL.  Result is left in `a` if *result_in_b == 0
+ * else in `b`.  ws = workspace of mhb_sort_workspace_bytes() bytes. */
+int mhb_sort_records(void *stream, uint32_t *a, uint32_t *b, uint64_t n, uint32_t words,
+                     const uint8_t *bytes, uint32_t n_bytes, const uint64_t *first_hist, void *ws,
+                     size_t ws_bytes, int *result_in_b);
+
+/* A5/A6: run-length count over sorted records, solid filter, edge packing
+ * (kmer_counter.cpp:254-381, PackEdge :32-52).
+ *   edges_out   capacity_edges * mhb_words_per_edge(k) words, ascending solid edges
+ *   aux_out     capacity_edges bytes: bit0 = no incoming, bit1 = no outgoing (for solid edges)
+ *   mul_hist    uint64[65536], caller-zeroed: multiplicity histogram of ALL distinct edges
+ *   n_solid_out device uint64 (caller-zeroed)
+ *   scratch     mhb_count_solid_scratch_bytes(n) bytes
+ * If the number of solid edges exceeds capacity_edges the surplus is not written; *n_solid_out still
+ * reports the true count so the caller can retry. */
+size_t mhb_count_solid_scratch_bytes(uint64_t n);
+int mhb_count_solid(void *stream, const uint32_t *sorted_records, uint64_t n, uint32_t k, int32_t m,
+                    uint32_t *edges_out, uint8_t *aux_out, uint64_t capacity_edges, uint64_t *mul_hist,
+                    uint64_t *n_solid_out, void *scratch, size_t scratch_bytes);
+
+/* A5 (mercy bookkeeping, kmer_counter.cpp:307-367): for every read, first_0_out / last_0_in exactly as
+ * KmerCounter leaves them.  tips = hash set built by mhb_tipset_build from the solid edges whose aux
+ * flags are non-zero. */
+size_t mhb_tipset_bytes(uint64_t n_tip_edges, uint32_t k);
+int mhb_tipset_build(void *stream, const uint32_t *edges, const uint8_t *aux, uint64_t n_solid, uint32_t k,
+                     void *tipset, size_t tipset_bytes, uint64_t n_tip_edges);
+int mhb_count_mark_mercy(void *stream, const mhb_dev_reads *reads, uint32_t k, const void *tipset,
+                         size_t tipset_bytes, uint32_t *first_0_out, uint32_t *last_0_in);
+/* number of solid edges with aux != 0 (device reduction; result to host) */
+int mhb_count_tip_edges(void *stream, const uint8_t *aux, uint64_t n_solid, uint64_t *n_tip_host);
+
+/* Sequences in package orientation for seq2sdbg: word-aligned 2-bit packing.
+ * fixed_len > 0: sequence s starts at word s*ceil(fixed_len/16); seq_off/len/item_off may be NULL.
+ * Otherwise word_off[n+1], len[n], item_off[n+1] (exclusive prefix of 2*(len-k+2) for len >= k+1, else 0). */
+typedef struct {
+  const uint32_t *words;
+  uint64_t n_words;
+  uint64_t n_seqs;
+  uint32_t fixed_len;
+  const uint64_t *word_off;
+  const uint32_t *len;
+  const uint64_t *item_off;
+  const uint16_t *mult; /* per sequence */
+} mhb_dev_seqs;
+
+/* A8/A9 (seq_to_sdbg.cpp:530-700): all sort items of both strands. */
+int mhb_s2s_extract(void *stream, const mhb_dev_seqs *seqs, uint32_t k, uint32_t *records, uint64_t n_items,
+                    uint64_t *hist256, int hist_byte);
+
+/* A10 (seq_to_sdbg.cpp:702-789 + sdbg_writer.cpp:25-58): SdBG item stream from sorted records.
+ *   bytes_out     capacity_bytes; the variable-length item stream in sorted (= bucket) order
+ *   bucket_table  uint64[65536*4] device: per bucket {byte offset, #items, #tips, #large_mul};
+ *   totals        uint64[16] device: [0]=bytes [1]=items [2]=tips [3]=large_mul [4..12]=w counts [13]=ones in last
+ *   scratch       mhb_s2s_emit_scratch_bytes(n) */
+size_t mhb_s2s_emit_scratch_bytes(uint64_t n);
+int mhb_s2s_emit(void *stream, const uint32_t *sorted_records, uint64_t n, uint32_t k, uint8_t *bytes_out,
+                 uint64_t capacity_bytes, uint64_t *bucket_table, uint64_t *totals, void *scratch,
+                 size_t scratch_bytes);
+
+/* ---------------------------------------------------------------------------------------------
+ * 2. Host level (buffers in host memory; device 0 unless mhb_set_device was called)
+ * ------------------------------------------------------------------------------------------- */
+int mhb_set_device(int device);
+
+typedef struct {
+  uint32_t k;
+  int32_t m;                /* solid threshold (-m / --min_kmer_frequency) */
+  const uint32_t *bin;      /* host `.bin` image */
+  uint64_t bin_words;
+  uint64_t n_reads;
+  int want_mercy;           /* compute first_0_out/last_0_in + candidate ids */
+} mhb_count_args;
+
+typedef struct {
+  uint64_t n_edge_records;  /* (k+1)-mer occurrences processed */
+  uint64_t n_solid;
+  uint32_t words_per_edge;
+  uint32_t *edges;          /* malloc'ed, n_solid * words_per_edge; free with mhb_free */
+  uint64_t n_cand;
+  uint64_t *cand_ids;       /* malloc'ed ascending read ids (kmer_counter.cpp:390-401) */
+  uint64_t n_has_tips;
+  int64_t counting[MHB_MAX_MUL + 1]; /* edge_counter.h:44-52 */
+  double t_h2d_ms, t_extract_ms, t_sort_ms, t_count_ms, t_mercy_ms, t_d2h_ms, t_total_ms;
+  uint32_t n_sort_passes;
+  double sort_pass_ms[64];
+} mhb_count_result;
+
+int mhb_count_host(const mhb_count_args *args, mhb_count_result *res);
+
+typedef struct {
+  uint32_t k;
+  const uint32_t *words;    /* host package-orientation sequences, word aligned */
+  const uint64_t *word_off; /* n_seqs + 1 */
+  const uint32_t *len;      /* n_seqs */
+  const uint16_t *mult;     /* n_seqs */
+  uint64_t n_seqs;
+} mhb_s2s_args;
+
+typedef struct {
+  uint64_t n_records;
+  uint64_t n_items, n_tips, n_large_mul, n_bytes;
+  uint32_t words_per_tip_label;
+  uint8_t *bytes;                                /* malloc'ed item stream, bucket order */
+  uint64_t bucket_table[MHB_NUM_BUCKETS * 4];    /* {byte offset, items, tips, large_mul} */
+  uint64_t w_count[9];
+  uint64_t ones_in_last;
+  double t_total_ms, t_extract_ms, t_sort_ms, t_emit_ms;
+} mhb_s2s_result;
+
+int mhb_s2s_host(const mhb_s2s_args *args, mhb_s2s_result *res);
+
+void mhb_free(void *p);
+/* drop the cached device arena (host-level entry points keep it between calls) */
+int mhb_release(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * 3. File level: the sub-commands.  Option names/meaning as main_sdbg_build.cpp:42-57 and :164-189.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  uint32_t k;
+  int32_t m;
+  double host_mem;
+  int32_t num_cpu_threads;
+  const char *read_lib_file;
+  const char *output_prefix;
+  int32_t mem_flag;
+} mhb_count_opts;
+
+typedef struct {
+  double host_mem;
+  uint32_t k;
+  uint32_t k_from;
+  int32_t num_cpu_threads;
+  const char *contig;
+  const char *bubble;
+  const char *addi_contig;
+  const char *local_contig;
+  const char *input_prefix;
+  const char *output_prefix;
+  int32_t need_mercy;
+  int32_t mem_flag;
+} mhb_seq2sdbg_opts;
+
+int mhb_count_run(const mhb_count_opts *opts);
+int mhb_seq2sdbg_run(const mhb_seq2sdbg_opts *opts);
+
+/* ---------------------------------------------------------------------------------------------
+ * Self-test hooks (host): build ONE sort record with the same __host__ __device__ code the kernels
+ * run, so CPU-only tests can compare the bit arithmetic with the oracle.  Not a compute path.
+ * ------------------------------------------------------------------------------------------- */
+int mhb_selftest_count_record(const uint32_t *read_words, uint32_t nwords, uint32_t L, uint32_t k, uint32_t q,
+                              uint32_t *rec_out, uint32_t *strand_out);
+int mhb_selftest_s2s_record(const uint32_t *seq_words, uint32_t nwords, uint32_t L, uint32_t k, uint32_t strand,
+                            uint32_t offset, uint32_t mult, uint32_t *rec_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MHB_H */

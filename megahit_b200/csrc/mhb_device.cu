@@ -1,0 +1,427 @@
+// mhb_device.cu -- device-level C ABI (see include/mhb.h, layer 1): kernel launches on caller-owned
+// device memory.  Built for sm_100a only; there is no host fallback.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "mhb.h"
+#include "mhb_count.cuh"
+#include "mhb_internal.h"
+#include "mhb_s2s.cuh"
+#include "mhb_sort.cuh"
+
+using namespace mhb;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+int mhb_set_error(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+extern "C" const char *mhb_last_error(void) { return g_err; }
+extern "C" const char *mhb_version(void) { return "megahit_b200 0.1 (sm_100a; formats of megahit v1.2.9)"; }
+extern "C" int mhb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+extern "C" void mhb_free(void *p) { free(p); }
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return mhb_set_error(MHB_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,      \
+                           cudaGetErrorString(e_));                                                \
+  } while (0)
+#define CK_LAUNCH() CK(cudaGetLastError())
+
+// ------------------------------------------------------------------------------------------------
+// geometry
+// ------------------------------------------------------------------------------------------------
+extern "C" uint32_t mhb_count_record_words(uint32_t k) { return count_record_words(k); }
+extern "C" uint32_t mhb_words_per_edge(uint32_t k) { return words_per_edge(k); }
+extern "C" uint32_t mhb_s2s_record_words(uint32_t k) { return s2s_record_words(k); }
+
+extern "C" uint32_t mhb_count_sort_bytes(uint32_t k, uint8_t *bytes) {
+  // key = top 2(k+1) bits of the record: every byte that holds at least one key bit
+  const u32 wr = count_record_words(k), total_bits = 32 * wr, key_bits = 2 * (k + 1);
+  const u32 lo = (total_bits - key_bits) / 8;
+  u32 n = 0;
+  for (u32 b = lo; b < 4 * wr; ++b) bytes[n++] = (uint8_t)b;
+  return n;
+}
+extern "C" uint32_t mhb_s2s_sort_bytes(uint32_t k, uint8_t *bytes) {
+  // whole record is the key (no payload): low 20 flag bits + the k-mer bits; all-zero bytes in
+  // between are skipped
+  const u32 w = s2s_record_words(k), total_bits = 32 * w, key_bits = 2 * k;
+  const u32 lo = (total_bits - key_bits) / 8;
+  u32 n = 0;
+  for (u32 b = 0; b < 4 * w; ++b)
+    if (b < 3 || b >= lo) bytes[n++] = (uint8_t)b;
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch helpers
+// ------------------------------------------------------------------------------------------------
+#define MHB_FOR_W(M) M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12) M(13) M(14) M(15) M(16)
+#define MHB_FOR_WR(M) MHB_FOR_W(M) M(17)
+
+static int g_sm_count = 0;
+static int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+static ReadsView make_reads_view(const mhb_dev_reads *r) {
+  ReadsView v;
+  v.bin = r->bin;
+  v.bin_words = r->bin_words;
+  v.n_reads = r->n_reads;
+  v.fixed_len = r->fixed_len;
+  v.fixed_stride = r->fixed_len ? 1 + div_ceil(r->fixed_len, 16) : 0;
+  v.rec_off = r->rec_off;
+  v.edge_off = r->edge_off;
+  return v;
+}
+
+static int check_reads(const mhb_dev_reads *r, uint32_t k) {
+  if (!r || k < 1 || k > MHB_MAX_K) return mhb_set_error(MHB_ERR_ARG, "bad reads/k (k=%u)", k);
+  if (r->n_reads && !r->bin) return mhb_set_error(MHB_ERR_ARG, "reads->bin is NULL");
+  if (((uintptr_t)r->bin & 15) != 0) return mhb_set_error(MHB_ERR_ARG, "reads->bin must be 16-byte aligned");
+  if (!r->fixed_len && r->n_reads && (!r->rec_off || !r->edge_off))
+    return mhb_set_error(MHB_ERR_ARG, "variable-length reads need rec_off and edge_off");
+  return MHB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// count: extract
+// ------------------------------------------------------------------------------------------------
+extern "C" int mhb_count_extract(void *stream, const mhb_dev_reads *reads, uint32_t k, uint32_t *records,
+                                 uint64_t n_edges, uint64_t *hist256, int hist_byte) {
+  if (int rc = check_reads(reads, k)) return rc;
+  if (reads->n_reads == 0 || n_edges == 0) return MHB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const ReadsView rv = make_reads_view(reads);
+  const u32 W = count_key_words(k), WR = count_record_words(k);
+  const u64 n_batches = (rv.n_reads + kReadsPerBatch - 1) / kReadsPerBatch;
+  const int grid = (int)(n_batches < (u64)(sm_count() * 8) ? n_batches : (u64)(sm_count() * 8));
+#define M(WW)                                                                                              \
+  if (W == WW && WR == WW)                                                                                 \
+    k_count_extract<WW, WW><<<grid, kExtractThreads, 0, st>>>(rv, k, records, hist256, hist_byte);         \
+  else if (W == WW && WR == WW + 1)                                                                        \
+    k_count_extract<WW, WW + 1><<<grid, kExtractThreads, 0, st>>>(rv, k, records, hist256, hist_byte);     \
+  else
+  MHB_FOR_W(M) return mhb_set_error(MHB_ERR_ARG, "unsupported k=%u", k);
+#undef M
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sort
+// ------------------------------------------------------------------------------------------------
+template <int WR>
+static u64 sort_tiles(u64 n) {
+  return (n + SortCfg<WR>::TILE - 1) / SortCfg<WR>::TILE;
+}
+static u64 sort_num_tiles(u64 n, u32 words) {
+#define M(WW) \
+  if (words == WW) return sort_tiles<WW>(n);
+  MHB_FOR_WR(M)
+#undef M
+  return 0;
+}
+static constexpr size_t kSortHeadBytes = (size_t)(72 + 1) * 256 * 8 /*hist*/ + 256 * 8 /*bin_base*/ + 128 * 4;
+
+extern "C" size_t mhb_sort_workspace_bytes(uint64_t n, uint32_t words) {
+  return kSortHeadBytes + sort_num_tiles(n, words) * 256 * 8 + 256;
+}
+
+template <int WR>
+static int launch_radix_pass(cudaStream_t st, const u32 *in, u32 *out, u64 n, int byte_idx, const u64 *bin_base,
+                             u64 *lookback, u32 *tile_counter, u64 *next_hist, int next_byte, u32 epoch) {
+  using C = SortCfg<WR>;
+  static int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    CK(cudaFuncSetAttribute(k_radix_pass<WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_radix_pass<WR>, C::THREADS, C::SMEM));
+    if (blocks_per_sm < 1) return mhb_set_error(MHB_ERR_CUDA, "radix pass kernel (WR=%d) does not fit an SM", WR);
+  }
+  const u64 tiles = sort_tiles<WR>(n);
+  u64 grid = (u64)blocks_per_sm * sm_count();
+  if (grid > tiles) grid = tiles;
+  k_radix_pass<WR><<<(int)grid, C::THREADS, C::SMEM, st>>>(in, out, n, (u32)tiles, byte_idx, bin_base, lookback,
+                                                            tile_counter, next_hist, next_byte, epoch);
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
+int mhb_sort_records_impl(void *stream, uint32_t *a, uint32_t *b, uint64_t n, uint32_t words, const uint8_t *bytes,
+                          uint32_t n_bytes, const uint64_t *first_hist, void *ws, size_t ws_bytes, int *result_in_b,
+                          double *pass_ms_host) {
+  if (words < 1 || words > 17 || n_bytes > 72 || !result_in_b)
+    return mhb_set_error(MHB_ERR_ARG, "bad sort geometry (words=%u n_bytes=%u)", words, n_bytes);
+  *result_in_b = 0;
+  if (n == 0 || n_bytes == 0) return MHB_OK;
+  if (ws_bytes < mhb_sort_workspace_bytes(n, words)) return mhb_set_error(MHB_ERR_ARG, "sort workspace too small");
+  if (n >= (1ull << 53)) return mhb_set_error(MHB_ERR_ARG, "too many records");
+  cudaStream_t st = (cudaStream_t)stream;
+  u64 *hist = (u64 *)ws;                   // [n_bytes+1][256]
+  u64 *bin_base = hist + (72 + 1) * 256;   // [256]
+  u32 *tile_counter = (u32 *)(bin_base + 256);  // [128]
+  u64 *lookback = (u64 *)((char *)ws + kSortHeadBytes);
+  CK(cudaMemsetAsync(ws, 0, mhb_sort_workspace_bytes(n, words), st));
+  if (first_hist) {
+    CK(cudaMemcpyAsync(hist, first_hist, 256 * 8, cudaMemcpyDeviceToDevice, st));
+  } else {
+#define M(WW) \
+  if (words == WW) k_hist_byte<WW><<<sm_count() * 4, 256, 0, st>>>(a, n, bytes[0], hist);
+    MHB_FOR_WR(M)
+#undef M
+    CK_LAUNCH();
+  }
+  cudaEvent_t ev[74];
+  if (pass_ms_host) {
+    for (u32 p = 0; p <= n_bytes; ++p) CK(cudaEventCreate(&ev[p]));
+    CK(cudaEventRecord(ev[0], st));
+  }
+  u32 *in = a, *out = b;
+  for (u32 p = 0; p < n_bytes; ++p) {
+    k_hist_scan256<<<1, 256, 0, st>>>(hist + (u64)p * 256, bin_base);
+    CK_LAUNCH();
+    u64 *next_hist = p + 1 < n_bytes ? hist + (u64)(p + 1) * 256 : nullptr;
+    const int next_byte = p + 1 < n_bytes ? bytes[p + 1] : 0;
+    int rc = MHB_ERR_ARG;
+#define M(WW) \
+  if (words == WW) rc = launch_radix_pass<WW>(st, in, out, n, bytes[p], bin_base, lookback, tile_counter + p, next_hist, next_byte, p + 1);
+    MHB_FOR_WR(M)
+#undef M
+    if (rc) return rc;
+    if (pass_ms_host) CK(cudaEventRecord(ev[p + 1], st));
+    u32 *t = in;
+    in = out;
+    out = t;
+  }
+  *result_in_b = (in == b) ? 1 : 0;
+  if (pass_ms_host) {
+    CK(cudaStreamSynchronize(st));
+    for (u32 p = 0; p < n_bytes; ++p) {
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, ev[p], ev[p + 1]));
+      pass_ms_host[p] = ms;
+    }
+    for (u32 p = 0; p <= n_bytes; ++p) cudaEventDestroy(ev[p]);
+  }
+  return MHB_OK;
+}
+
+extern "C" int mhb_sort_records(void *stream, uint32_t *a, uint32_t *b, uint64_t n, uint32_t words,
+                                const uint8_t *bytes, uint32_t n_bytes, const uint64_t *first_hist, void *ws,
+                                size_t ws_bytes, int *result_in_b) {
+  return mhb_sort_records_impl(stream, a, b, n, words, bytes, n_bytes, first_hist, ws, ws_bytes, result_in_b, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// count: solid edges
+// ------------------------------------------------------------------------------------------------
+extern "C" int mhb_count_solid(void *stream, const uint32_t *sorted_records, uint64_t n, uint32_t k, int32_t m,
+                               uint32_t *edges_out, uint8_t *aux_out, uint64_t capacity_edges, uint64_t *mul_hist,
+                               uint64_t *n_solid_out, void *scratch, size_t scratch_bytes) {
+  if (k < 1 || k > MHB_MAX_K || !mul_hist || !n_solid_out) return mhb_set_error(MHB_ERR_ARG, "bad args");
+  if (n == 0) return MHB_OK;
+  const u64 nblk = (n + kCompactTile - 1) / kCompactTile;
+  const size_t need = mhb_count_solid_scratch_bytes(n);
+  if (scratch_bytes < need) return mhb_set_error(MHB_ERR_ARG, "count scratch too small (%zu < %zu)", scratch_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  u32 *info = (u32 *)scratch;
+  u64 *btot = (u64 *)((char *)scratch + (((size_t)n * 4 + 63) & ~(size_t)63));
+  const u32 WR = count_record_words(k);
+  const u64 gmark = (n + 255) / 256;
+#define M(WW) \
+  if (WR == WW) k_count_mark<WW><<<(unsigned)gmark, 256, 0, st>>>(sorted_records, n, m, info, mul_hist);
+  MHB_FOR_WR(M)
+#undef M
+  CK_LAUNCH();
+  k_solid_block_totals<<<(unsigned)nblk, kCompactThreads, 0, st>>>(info, n, btot);
+  CK_LAUNCH();
+  k_scan_u64<<<1, 1024, 0, st>>>(btot, nblk, n_solid_out);
+  CK_LAUNCH();
+#define M(WW)                                                                                                       \
+  if (WR == WW)                                                                                                     \
+    k_count_emit<WW><<<(unsigned)nblk, kCompactThreads, 0, st>>>(sorted_records, info, n, k, btot, edges_out, aux_out, \
+                                                                 capacity_edges);
+  MHB_FOR_WR(M)
+#undef M
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
+extern "C" size_t mhb_count_solid_scratch_bytes(uint64_t n) {
+  const u64 nblk = (n + kCompactTile - 1) / kCompactTile;
+  return (((size_t)n * 4 + 63) & ~(size_t)63) + (size_t)nblk * 8 + 128;
+}
+
+// ------------------------------------------------------------------------------------------------
+// count: mercy bookkeeping
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t mhb_tipset_bytes(uint64_t n_tip_edges, uint32_t k) {
+  return 16 + tipset_capacity(n_tip_edges) * (size_t)(count_key_words(k) + 1) * 4;
+}
+
+extern "C" int mhb_count_tip_edges(void *stream, const uint8_t *aux, uint64_t n_solid, uint64_t *n_tip_host) {
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long *d = nullptr;
+  *n_tip_host = 0;
+  if (n_solid == 0) return MHB_OK;
+  CK(cudaMallocAsync((void **)&d, 8, st));
+  CK(cudaMemsetAsync(d, 0, 8, st));
+  k_count_tips<<<sm_count() * 4, 256, 0, st>>>(aux, n_solid, d);
+  CK_LAUNCH();
+  CK(cudaMemcpyAsync(n_tip_host, d, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaFreeAsync(d, st));
+  return MHB_OK;
+}
+
+extern "C" int mhb_tipset_build(void *stream, const uint32_t *edges, const uint8_t *aux, uint64_t n_solid, uint32_t k,
+                                void *tipset, size_t tipset_bytes, uint64_t n_tip_edges) {
+  if (tipset_bytes < mhb_tipset_bytes(n_tip_edges, k)) return mhb_set_error(MHB_ERR_ARG, "tipset too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const u64 cap = tipset_capacity(n_tip_edges);
+  CK(cudaMemsetAsync(tipset, 0, mhb_tipset_bytes(n_tip_edges, k), st));
+  CK(cudaMemcpyAsync(tipset, &cap, 8, cudaMemcpyHostToDevice, st));
+  if (n_solid == 0) return MHB_OK;
+  u32 *table = (u32 *)((char *)tipset + 16);
+  const u32 W = count_key_words(k);
+  const u64 g = (n_solid + 255) / 256;
+#define M(WW) \
+  if (W == WW) k_tipset_insert<WW><<<(unsigned)g, 256, 0, st>>>(edges, aux, n_solid, k, table, cap);
+  MHB_FOR_W(M)
+#undef M
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
+extern "C" int mhb_count_mark_mercy(void *stream, const mhb_dev_reads *reads, uint32_t k, const void *tipset,
+                                    size_t tipset_bytes, uint32_t *first_0_out, uint32_t *last_0_in) {
+  if (int rc = check_reads(reads, k)) return rc;
+  if (reads->n_reads == 0) return MHB_OK;
+  if (tipset_bytes < 16 + 1024 * 8) return mhb_set_error(MHB_ERR_ARG, "bad tipset");
+  cudaStream_t st = (cudaStream_t)stream;
+  const ReadsView rv = make_reads_view(reads);
+  const u32 W = count_key_words(k), WR = count_record_words(k);
+  const u64 cap = (tipset_bytes - 16) / ((size_t)(W + 1) * 4);
+  if (cap & (cap - 1)) return mhb_set_error(MHB_ERR_ARG, "tipset capacity %llu is not a power of two", (unsigned long long)cap);
+  const u32 *table = (const u32 *)((const char *)tipset + 16);
+  const u64 n_batches = (rv.n_reads + kReadsPerBatch - 1) / kReadsPerBatch;
+  const int grid = (int)(n_batches < (u64)(sm_count() * 8) ? n_batches : (u64)(sm_count() * 8));
+#define M(WW)                                                                                                  \
+  if (W == WW && WR == WW)                                                                                     \
+    k_mark_mercy<WW, WW><<<grid, kExtractThreads, 0, st>>>(rv, k, table, cap, first_0_out, last_0_in);         \
+  else if (W == WW && WR == WW + 1)                                                                            \
+    k_mark_mercy<WW, WW + 1><<<grid, kExtractThreads, 0, st>>>(rv, k, table, cap, first_0_out, last_0_in);     \
+  else
+  MHB_FOR_W(M) return mhb_set_error(MHB_ERR_ARG, "unsupported k=%u", k);
+#undef M
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// seq2sdbg
+// ------------------------------------------------------------------------------------------------
+static SeqsView make_seqs_view(const mhb_dev_seqs *s) {
+  SeqsView v;
+  v.words = s->words;
+  v.n_words = s->n_words;
+  v.n_seqs = s->n_seqs;
+  v.fixed_len = s->fixed_len;
+  v.word_off = s->word_off;
+  v.len = s->len;
+  v.item_off = s->item_off;
+  v.mult = s->mult;
+  return v;
+}
+
+extern "C" int mhb_s2s_extract(void *stream, const mhb_dev_seqs *seqs, uint32_t k, uint32_t *records,
+                               uint64_t n_items, uint64_t *hist256, int hist_byte) {
+  if (!seqs || k < 9 || k > MHB_MAX_K) return mhb_set_error(MHB_ERR_ARG, "kmer size must be >= 9 and <= 255");
+  if (n_items == 0) return MHB_OK;
+  if (!seqs->mult) return mhb_set_error(MHB_ERR_ARG, "seqs->mult is NULL");
+  if (!seqs->fixed_len && (!seqs->word_off || !seqs->len || !seqs->item_off))
+    return mhb_set_error(MHB_ERR_ARG, "variable-length sequences need word_off, len and item_off");
+  if (seqs->fixed_len && seqs->fixed_len < k + 1) return mhb_set_error(MHB_ERR_ARG, "fixed_len < k+1");
+  cudaStream_t st = (cudaStream_t)stream;
+  const SeqsView sv = make_seqs_view(seqs);
+  const u32 W = s2s_record_words(k);
+  u64 g = (n_items + 255) / 256;
+  if (g > (u64)sm_count() * 32) g = (u64)sm_count() * 32;
+#define M(WW) \
+  if (W == WW) k_s2s_extract<WW><<<(unsigned)g, 256, 0, st>>>(sv, k, records, n_items, hist256, hist_byte);
+  MHB_FOR_WR(M)
+#undef M
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
+extern "C" size_t mhb_s2s_emit_scratch_bytes(uint64_t n) {
+  const u64 nblk = (n + kEmitThreads - 1) / kEmitThreads;
+  return (size_t)nblk * 4 * 8 + (size_t)MHB_NUM_BUCKETS * 4 * 8 + 256;
+}
+
+extern "C" int mhb_s2s_emit(void *stream, const uint32_t *sorted_records, uint64_t n, uint32_t k, uint8_t *bytes_out,
+                            uint64_t capacity_bytes, uint64_t *bucket_table, uint64_t *totals, void *scratch,
+                            size_t scratch_bytes) {
+  if (k < 9 || k > MHB_MAX_K || !bucket_table || !totals) return mhb_set_error(MHB_ERR_ARG, "bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(totals, 0, 16 * 8, st));
+  CK(cudaMemsetAsync(bucket_table, 0, (size_t)MHB_NUM_BUCKETS * 4 * 8, st));
+  if (n == 0) return MHB_OK;
+  if (scratch_bytes < mhb_s2s_emit_scratch_bytes(n)) return mhb_set_error(MHB_ERR_ARG, "emit scratch too small");
+  const u64 nblk = (n + kEmitThreads - 1) / kEmitThreads;
+  u64 *bucket_start = (u64 *)scratch;
+  u64 *btot = bucket_start + (size_t)MHB_NUM_BUCKETS * 4;
+  CK(cudaMemsetAsync(bucket_start, 0xFF, (size_t)MHB_NUM_BUCKETS * 4 * 8, st));
+  const u32 W = s2s_record_words(k);
+#define M(WW) \
+  if (W == WW) k_s2s_size<WW><<<(unsigned)nblk, kEmitThreads, 0, st>>>(sorted_records, n, k, btot);
+  MHB_FOR_WR(M)
+#undef M
+  CK_LAUNCH();
+  for (int q = 0; q < 4; ++q) {
+    k_scan_u64<<<1, 1024, 0, st>>>(btot + (u64)q * nblk, nblk, totals + q);
+    CK_LAUNCH();
+  }
+#define M(WW)                                                                                                    \
+  if (W == WW)                                                                                                   \
+    k_s2s_write<WW><<<(unsigned)nblk, kEmitThreads, 0, st>>>(sorted_records, n, k, btot, bytes_out, capacity_bytes, \
+                                                            bucket_start, totals);
+  MHB_FOR_WR(M)
+#undef M
+  CK_LAUNCH();
+  k_bucket_finalize<<<64, 256, 0, st>>>(bucket_start, totals, bucket_table);
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
+extern "C" int mhb_set_device(int device) {
+  CK(cudaSetDevice(device));
+  g_sm_count = 0;
+  return MHB_OK;
+}

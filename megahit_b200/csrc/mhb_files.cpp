@@ -1,0 +1,595 @@
+// mhb_files.cpp -- file-level C ABI (include/mhb.h, layer 3): the `count` and `seq2sdbg` sub-commands on
+// the reference's on-disk formats.  Host-side IO only; all sorting/counting/emission runs on the GPU
+// through mhb_count_host / mhb_s2s_host.
+//
+// Formats follow voutcn/megahit v1.2.9 (paths relative to src/):
+//   read library   sequence/io/sequence_lib.cpp:93-118, sequence/sequence_package.h:224-240
+//   edges          sequence/io/edge/edge_io_meta.h:25-70, edge_writer.h:68-111, edge_reader.h:40-138
+//   candidates     sorting/kmer_counter.cpp:383-401 ; counting: sorting/edge_counter.h:44-52
+//   contigs        sequence/io/contig/contig_reader.h:52-119
+//   SdBG           sdbg/sdbg_writer.cpp:25-79, sdbg/sdbg_meta.cpp:12-61
+#include <omp.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+
+#include <algorithm>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "mhb.h"
+#include "mhb_bits.cuh"
+#include "mhb_internal.h"
+
+using namespace mhb;
+
+namespace {
+
+#define XINFO(...)                                                         \
+  do {                                                                     \
+    fprintf(stderr, "INFO  %-30s: %4d - ", "megahit_b200", __LINE__);      \
+    fprintf(stderr, __VA_ARGS__);                                          \
+  } while (0)
+
+double now_s() {
+  timeval tv;
+  gettimeofday(&tv, nullptr);
+  return tv.tv_sec + tv.tv_usec * 1e-6;
+}
+
+bool read_file(const std::string &path, std::vector<uint32_t> *out, bool must_exist = true) {
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) {
+    if (must_exist) mhb_set_error(MHB_ERR_IO, "cannot open %s", path.c_str());
+    return false;
+  }
+  fseek(f, 0, SEEK_END);
+  const long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  out->resize(((size_t)sz + 3) / 4 + 4, 0);  // padded so the image can be handed to the device as is
+  const size_t got = sz ? fread(out->data(), 1, (size_t)sz, f) : 0;
+  fclose(f);
+  if (got != (size_t)sz) {
+    mhb_set_error(MHB_ERR_IO, "short read on %s", path.c_str());
+    return false;
+  }
+  out->resize(((size_t)sz + 3) / 4);
+  return true;
+}
+
+// host container mirroring what SeqPackage holds for seq2sdbg: word-aligned package-orientation sequences
+struct HostSeqs {
+  std::vector<uint32_t> words;
+  std::vector<uint64_t> word_off{0};
+  std::vector<uint32_t> len;
+  std::vector<uint16_t> mult;
+  size_t size() const { return len.size(); }
+  void append_packed(const uint32_t *w, uint32_t L, uint16_t m) {  // already left-aligned, tail bits may be dirty
+    const uint32_t nw = div_ceil(L, 16);
+    const size_t at = words.size();
+    words.insert(words.end(), w, w + nw);
+    if (L % 16) words[at + nw - 1] &= top_mask(2 * (L % 16));
+    word_off.push_back(words.size());
+    len.push_back(L);
+    mult.push_back(m);
+  }
+  void append_ascii(const char *s, uint32_t L, bool reverse, uint16_t m) {  // sequence_package.h:245-273
+    static const struct Map {
+      uint8_t v[256];
+      Map() {
+        memset(v, 0, sizeof(v));
+        const char *a = "ACGTNacgtn", *b = "0123201232";
+        for (int i = 0; i < 10; ++i) v[(int)a[i]] = b[i] - '0';
+      }
+    } map;
+    const uint32_t nw = div_ceil(L, 16);
+    const size_t at = words.size();
+    words.resize(at + nw, 0);
+    for (uint32_t i = 0; i < L; ++i) {
+      const uint8_t c = map.v[(uint8_t)s[reverse ? L - 1 - i : i]];
+      words[at + (i >> 4)] |= (uint32_t)c << (30 - 2 * (i & 15));
+    }
+    word_off.push_back(words.size());
+    len.push_back(L);
+    mult.push_back(m);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// edges
+// ------------------------------------------------------------------------------------------------
+struct EdgeMeta {
+  uint32_t kmer_size = 0, words_per_edge = 0, num_files = 0, num_buckets = 0;
+  int64_t num_edges = 0;
+  int is_sorted = 1;
+  struct B {
+    int file_id;
+    int64_t off, cnt;
+  };
+  std::vector<B> buckets;
+};
+
+bool scan_field(std::istream &is, const char *name, long long *v) {  // utils.h ScanField
+  std::string s;
+  if (!(is >> s) || s != name || !(is >> *v)) {
+    mhb_set_error(MHB_ERR_IO, "Invalid format. Expect field %s", name);
+    return false;
+  }
+  return true;
+}
+
+int read_edge_meta(const std::string &prefix, EdgeMeta *m) {
+  std::ifstream is(prefix + ".edges.info");
+  if (!is) return mhb_set_error(MHB_ERR_IO, "cannot open %s.edges.info", prefix.c_str());
+  long long v[6];
+  const char *names[6] = {"kmer_size", "words_per_edge", "num_files", "num_buckets", "num_edges", "is_sorted"};
+  for (int i = 0; i < 6; ++i)
+    if (!scan_field(is, names[i], &v[i])) return MHB_ERR_IO;
+  m->kmer_size = (uint32_t)v[0];
+  m->words_per_edge = (uint32_t)v[1];
+  m->num_files = (uint32_t)v[2];
+  m->num_buckets = (uint32_t)v[3];
+  m->num_edges = v[4];
+  m->is_sorted = (int)v[5];
+  m->buckets.resize(m->num_buckets);
+  for (uint32_t i = 0; i < m->num_buckets; ++i) {
+    long long id;
+    is >> id >> m->buckets[i].file_id >> m->buckets[i].off >> m->buckets[i].cnt;
+    if (!is || id != (long long)i) return mhb_set_error(MHB_ERR_IO, "Invalid format: bucket id not matched!");
+    if (m->buckets[i].file_id >= (int)m->num_files)
+      return mhb_set_error(MHB_ERR_IO, "Record ID %d is greater than number of files %u", m->buckets[i].file_id, m->num_files);
+  }
+  return MHB_OK;
+}
+
+// All edges in reader order (edge_reader.h:40-138): bucket order when sorted, file order otherwise.
+int read_all_edges(const std::string &prefix, EdgeMeta *meta, std::vector<uint32_t> *edges) {
+  if (int rc = read_edge_meta(prefix, meta)) return rc;
+  const uint32_t W = meta->words_per_edge;
+  std::vector<std::vector<uint32_t>> files(meta->num_files);
+  for (uint32_t i = 0; i < meta->num_files; ++i)
+    if (!read_file(prefix + ".edges." + std::to_string(i), &files[i])) return MHB_ERR_IO;
+  edges->clear();
+  if (!meta->is_sorted) {
+    if (files.empty() || files[0].size() < (size_t)meta->num_edges * W) return mhb_set_error(MHB_ERR_IO, "%s.edges.0 is truncated", prefix.c_str());
+    edges->assign(files[0].begin(), files[0].begin() + (size_t)meta->num_edges * W);
+    return MHB_OK;
+  }
+  edges->reserve((size_t)meta->num_edges * W);
+  for (const auto &b : meta->buckets) {
+    if (b.file_id < 0 || b.cnt == 0) continue;
+    const auto &f = files[b.file_id];
+    if ((size_t)(b.off + b.cnt) * W > f.size()) return mhb_set_error(MHB_ERR_IO, "%s.edges.%d is truncated", prefix.c_str(), b.file_id);
+    edges->insert(edges->end(), f.begin() + (size_t)b.off * W, f.begin() + (size_t)(b.off + b.cnt) * W);
+  }
+  return MHB_OK;
+}
+
+int write_edges(const std::string &prefix, uint32_t k, const uint32_t *edges, uint64_t n) {
+  const uint32_t W = words_per_edge(k);
+  FILE *f = fopen((prefix + ".edges.0").c_str(), "wb");
+  if (!f) return mhb_set_error(MHB_ERR_IO, "cannot open %s.edges.0 for writing", prefix.c_str());
+  if (n && fwrite(edges, 4 * (size_t)W, n, f) != n) {
+    fclose(f);
+    return mhb_set_error(MHB_ERR_IO, "write to %s.edges.0 failed", prefix.c_str());
+  }
+  fclose(f);
+  std::vector<int64_t> cnt(MHB_NUM_BUCKETS, 0), off(MHB_NUM_BUCKETS, 0);
+  for (uint64_t i = 0; i < n; ++i) cnt[edges[i * W] >> 16]++;
+  int64_t acc = 0;
+  for (int b = 0; b < MHB_NUM_BUCKETS; ++b) {
+    off[b] = acc;
+    acc += cnt[b];
+  }
+  FILE *g = fopen((prefix + ".edges.info").c_str(), "w");
+  if (!g) return mhb_set_error(MHB_ERR_IO, "cannot open %s.edges.info for writing", prefix.c_str());
+  fprintf(g, "kmer_size %u\nwords_per_edge %u\nnum_files 1\nnum_buckets %d\nnum_edges %lld\nis_sorted 1\n", k, W,
+          MHB_NUM_BUCKETS, (long long)n);
+  for (int b = 0; b < MHB_NUM_BUCKETS; ++b) {
+    if (cnt[b]) fprintf(g, "%d 0 %lld %lld\n", b, (long long)off[b], (long long)cnt[b]);
+    else fprintf(g, "%d -1 0 0\n", b);
+  }
+  fclose(g);
+  return MHB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mercy edges (seq_to_sdbg.cpp:100-357) -- host side, OpenMP over candidate reads.
+// Operates on base arrays for clarity; candidate reads are few (~0.2 % of reads).
+// ------------------------------------------------------------------------------------------------
+struct EdgeIndex {
+  const uint32_t *e;
+  int64_t n;
+  uint32_t wpe;
+  std::vector<int64_t> lut;  // [first,last] per 12-mer prefix, -1 = empty
+  uint32_t base(int64_t id, uint32_t i) const { return base_at(e + (size_t)id * wpe, i); }
+  void build() {  // InitLookupTable :100-127
+    lut.assign(2u << 24, -1);
+    if (n == 0) return;
+    uint32_t cur = e[0] >> 8;
+    lut[2 * (size_t)cur] = 0;
+    for (int64_t i = 1; i < n; ++i) {
+      const uint32_t p = e[(size_t)i * wpe] >> 8;
+      if (p > cur) {
+        lut[2 * (size_t)cur + 1] = i - 1;
+        cur = p;
+        lut[2 * (size_t)cur] = i;
+      }
+    }
+    lut[2 * (size_t)cur + 1] = n - 1;
+  }
+  int64_t search(const uint8_t *km, uint32_t ksz) const {  // BinarySearchKmer :132-161
+    uint32_t prefix = 0;
+    for (uint32_t i = 0; i < 12; ++i) prefix = (prefix << 2) | (i < ksz ? km[i] : 0u);
+    int64_t l = lut[2 * (size_t)prefix];
+    if (l == -1) return -1;
+    int64_t r = lut[2 * (size_t)prefix + 1];
+    while (l <= r) {
+      const int64_t mid = (l + r) / 2;
+      int cmp = 0;
+      for (uint32_t i = 0; i < ksz; ++i) {
+        const uint32_t eb = base(mid, i);
+        if (km[i] != eb) {
+          cmp = km[i] < eb ? -1 : 1;
+          break;
+        }
+      }
+      if (cmp > 0) l = mid + 1;
+      else if (cmp < 0) r = mid - 1;
+      else return mid;
+    }
+    return -1;
+  }
+};
+
+int cmp_bases(const uint8_t *x, const uint8_t *y, uint32_t n) {
+  for (uint32_t i = 0; i < n; ++i)
+    if (x[i] != y[i]) return x[i] < y[i] ? -1 : 1;
+  return 0;
+}
+
+// cand: `.cand` image (u32 len + words per read, package orientation).  Appends (k+1)-mers with mult 1.
+int gen_mercy_edges(const std::vector<uint32_t> &edges, uint32_t wpe, const std::vector<uint32_t> &cand, uint32_t k,
+                    int n_threads, HostSeqs *out, int64_t *n_reads_out, int64_t *n_mercy_out) {
+  EdgeIndex ix{edges.data(), (int64_t)(edges.size() / wpe), wpe, {}};
+  ix.build();
+  std::vector<size_t> starts;
+  for (size_t pos = 0; pos < cand.size();) {
+    starts.push_back(pos);
+    pos += 1 + div_ceil(cand[pos], 16);
+  }
+  const int64_t nr = (int64_t)starts.size();
+  std::vector<std::vector<uint32_t>> per_read(nr);  // mercy edges of each read, WM words each
+  const uint32_t WM = div_ceil(k + 1, 16);
+#pragma omp parallel for schedule(dynamic, 64) num_threads(n_threads > 0 ? n_threads : 1)
+  for (int64_t r = 0; r < nr; ++r) {
+    const uint32_t L = cand[starts[r]];
+    const uint32_t *w = cand.data() + starts[r] + 1;
+    if (L < k + 2) continue;  // :206-208
+    std::vector<uint8_t> has_in(L + 2, 0), has_out(L + 2, 0), km(k + 2), rv(k + 2);
+    for (uint32_t i = 0; i < k; ++i) {
+      km[i] = (uint8_t)base_at(w, i);
+      rv[i] = (uint8_t)(3u - base_at(w, k - 1 - i));
+    }
+    km[k] = rv[k] = 0;
+    for (uint32_t i = 0; i + k <= L; ++i) {  // :224-307
+      if (!has_in[i]) {
+        if (ix.search(rv.data(), k) != -1) {
+          has_in[i] = 1;
+        } else {
+          rv[k] = 3;
+          memmove(&km[1], &km[0], k);
+          for (uint32_t c = 0; c < 4; ++c) {
+            km[0] = (uint8_t)c;
+            if (cmp_bases(km.data(), rv.data(), k + 1) > 0) break;
+            if (ix.search(km.data(), k + 1) != -1) {
+              has_in[i] = 1;
+              break;
+            }
+          }
+          rv[k] = 0;
+          memmove(&km[0], &km[1], k);
+          km[k] = 0;
+        }
+      }
+      const int64_t edge_id = ix.search(km.data(), k);
+      if (edge_id != -1) {
+        has_out[i] = 1;
+        if (i + k < L && ix.base(edge_id, k) == base_at(w, i + k)) has_in[i + 1] = 1;
+      } else {
+        km[k] = 3;
+        const uint32_t next_char = i + k < L ? 3u - base_at(w, i + k) : 0u;
+        memmove(&rv[1], &rv[0], k);
+        rv[0] = (uint8_t)next_char;
+        if (cmp_bases(rv.data(), km.data(), k + 1) <= 0 && ix.search(rv.data(), k + 1) != -1) {
+          has_out[i] = 1;
+          has_in[i + 1] = 1;
+        } else {
+          for (uint32_t c = 0; c < 4; ++c) {
+            if (c == next_char) continue;
+            rv[0] = (uint8_t)c;
+            if (cmp_bases(rv.data(), km.data(), k + 1) > 0) break;
+            if (ix.search(rv.data(), k + 1) != -1) {
+              has_out[i] = 1;
+              break;
+            }
+          }
+        }
+        km[k] = 0;
+        memmove(&rv[0], &rv[1], k);
+        rv[k] = 0;
+      }
+      if (i + k < L) {
+        const uint32_t nc = base_at(w, i + k);
+        memmove(&km[0], &km[1], k - 1);
+        km[k - 1] = (uint8_t)nc;
+        memmove(&rv[1], &rv[0], k - 1);
+        rv[0] = (uint8_t)(3u - nc);
+      }
+    }
+    int last_no_out = -1;  // :310-352
+    for (uint32_t i = 0; i + k <= L; ++i) {
+      switch (has_in[i] | (has_out[i] << 1)) {
+        case 1:
+          last_no_out = (int)i;
+          break;
+        case 2:
+          if (last_no_out >= 0) {
+            for (uint32_t j = (uint32_t)last_no_out; j < i; ++j) {
+              const size_t at = per_read[r].size();
+              per_read[r].resize(at + WM, 0);
+              for (uint32_t x = 0; x < k + 1; ++x)
+                per_read[r][at + (x >> 4)] |= base_at(w, j + x) << (30 - 2 * (x & 15));
+            }
+          }
+          last_no_out = -1;
+          break;
+        case 3:
+          last_no_out = -1;
+          break;
+        default:
+          break;
+      }
+    }
+  }
+  int64_t n_mercy = 0;
+  for (int64_t r = 0; r < nr; ++r) {
+    for (size_t at = 0; at < per_read[r].size(); at += WM) {
+      out->append_packed(per_read[r].data() + at, k + 1, 1);
+      ++n_mercy;
+    }
+  }
+  *n_reads_out = nr;
+  *n_mercy_out = n_mercy;
+  return MHB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// contigs (contig_reader.h:52-119): FASTA with "flag=F multi=M len=N" comments
+// ------------------------------------------------------------------------------------------------
+int read_contigs(const std::string &path, uint32_t min_len, uint32_t k_from, uint32_t k_to, bool reverse,
+                 HostSeqs *out, int64_t *n_read) {
+  *n_read = 0;
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) return MHB_OK;  // the reference opens a missing file as an empty stream
+  const bool extend_loop = k_from < k_to;
+  std::string header, seq, line;
+  char *buf = nullptr;
+  size_t cap = 0;
+  ssize_t got;
+  bool have = false;
+  auto flush = [&]() {
+    if (!have) return;
+    have = false;
+    if (seq.size() < min_len) return;
+    const size_t sp = header.find_first_of(" \t");
+    const std::string comment = sp == std::string::npos ? "" : header.substr(header.find_first_not_of(" \t", sp));
+    const unsigned flag = comment.size() > 5 ? (unsigned)(comment[5] - '0') : 0u;
+    const double m = comment.size() > 13 ? atof(comment.c_str() + 13) : 0.0;
+    const uint16_t mult = (uint16_t)(int32_t)(m + .5);
+    if (extend_loop && (flag & 2u)) {  // contig_flag::kLoop, contig_reader.h:73-86
+      if (seq.size() < k_to + 1u) return;
+      std::string ss(seq);
+      for (uint32_t i = k_from; i < k_to; ++i) ss.push_back(ss[i]);
+      out->append_ascii(ss.data(), (uint32_t)ss.size(), reverse, mult);
+    } else {
+      out->append_ascii(seq.data(), (uint32_t)seq.size(), reverse, mult);
+    }
+    ++*n_read;
+  };
+  while ((got = getline(&buf, &cap, f)) >= 0) {
+    while (got > 0 && (buf[got - 1] == '\n' || buf[got - 1] == '\r')) --got;
+    if (got > 0 && buf[0] == '>') {
+      flush();
+      header.assign(buf + 1, got - 1);
+      seq.clear();
+      have = true;
+    } else if (have) {
+      seq.append(buf, got);
+    }
+  }
+  flush();
+  free(buf);
+  fclose(f);
+  return MHB_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// count
+// ================================================================================================
+extern "C" int mhb_count_run(const mhb_count_opts *o) {
+  if (!o || !o->read_lib_file || !o->read_lib_file[0]) return mhb_set_error(MHB_ERR_ARG, "No read library configuration file!");
+  if (o->host_mem == 0) return mhb_set_error(MHB_ERR_ARG, "Please specify the host memory!");
+  const std::string lib = o->read_lib_file, prefix = o->output_prefix ? o->output_prefix : "out";
+  const double t0 = now_s();
+  long long total_bases = 0, n_reads = 0;
+  {
+    std::ifstream is(lib + ".lib_info");
+    if (!(is >> total_bases >> n_reads)) return mhb_set_error(MHB_ERR_IO, "cannot read %s.lib_info", lib.c_str());
+  }
+  std::vector<uint32_t> bin;
+  if (!read_file(lib + ".bin", &bin)) return MHB_ERR_IO;
+  XINFO("%lld reads, %lld bases; k = %u, m = %d\n", n_reads, total_bases, o->k, o->m);
+
+  mhb_count_args a;
+  memset(&a, 0, sizeof(a));
+  a.k = o->k;
+  a.m = o->m;
+  a.bin = bin.data();
+  a.bin_words = bin.size();
+  a.n_reads = (uint64_t)n_reads;
+  a.want_mercy = 1;
+  std::vector<char> resbuf(sizeof(mhb_count_result));
+  mhb_count_result *res = reinterpret_cast<mhb_count_result *>(resbuf.data());
+  if (int rc = mhb_count_host(&a, res)) return rc;
+  XINFO("GPU count: %llu edge records, h2d %.2f ms, extract %.2f ms, sort %.2f ms (%u passes), count %.2f ms, mercy %.2f ms, d2h %.2f ms\n",
+        (unsigned long long)res->n_edge_records, res->t_h2d_ms, res->t_extract_ms, res->t_sort_ms, res->n_sort_passes,
+        res->t_count_ms, res->t_mercy_ms, res->t_d2h_ms);
+
+  int rc = write_edges(prefix, o->k, res->edges, res->n_solid);
+  if (!rc) {  // kmer_counter.cpp:383-401: candidate reads, in the reversed orientation KmerCounter holds them
+    FILE *f = fopen((prefix + ".cand").c_str(), "wb");
+    if (!f) rc = mhb_set_error(MHB_ERR_IO, "cannot open %s.cand", prefix.c_str());
+    else {
+      uint64_t r = 0;
+      size_t pos = 0;
+      std::vector<uint32_t> rec;
+      for (uint64_t c = 0; c < res->n_cand; ++c) {
+        while (r < res->cand_ids[c]) {
+          pos += 1 + div_ceil(bin[pos], 16);
+          ++r;
+        }
+        const uint32_t L = bin[pos], nw = div_ceil(L, 16);
+        rec.assign(nw + 1, 0);
+        rec[0] = L;
+        for (uint32_t i = 0; i < L; ++i)  // sequence_package.h:284-295 (reverse, no complement)
+          rec[1 + (i >> 4)] |= base_at(&bin[pos + 1], L - 1 - i) << (30 - 2 * (i & 15));
+        fwrite(rec.data(), 4, nw + 1, f);
+      }
+      fclose(f);
+    }
+  }
+  if (!rc) {
+    FILE *f = fopen((prefix + ".counting").c_str(), "w");
+    if (!f) rc = mhb_set_error(MHB_ERR_IO, "cannot open %s.counting", prefix.c_str());
+    else {
+      for (int i = 1; i <= MHB_MAX_MUL; ++i) fprintf(f, "%d %lld\n", i, (long long)res->counting[i]);
+      fclose(f);
+    }
+  }
+  XINFO("Total number of candidate reads: %llu (%llu)\n", (unsigned long long)res->n_cand, (unsigned long long)res->n_has_tips);
+  XINFO("Total number of solid edges: %llu\n", (unsigned long long)res->n_solid);
+  XINFO("count done. Time elapsed: %.4f\n", now_s() - t0);
+  mhb_free(res->edges);
+  mhb_free(res->cand_ids);
+  return rc;
+}
+
+// ================================================================================================
+// seq2sdbg
+// ================================================================================================
+extern "C" int mhb_seq2sdbg_run(const mhb_seq2sdbg_opts *o) {
+  auto S = [](const char *s) { return std::string(s ? s : ""); };
+  if (!o) return mhb_set_error(MHB_ERR_ARG, "null options");
+  const std::string input = S(o->input_prefix), contig = S(o->contig), bubble = S(o->bubble), addi = S(o->addi_contig),
+                    local = S(o->local_contig), prefix = S(o->output_prefix);
+  if (input.empty() && contig.empty() && addi.empty()) return mhb_set_error(MHB_ERR_ARG, "No input files!");
+  if (o->k < 9) return mhb_set_error(MHB_ERR_ARG, "kmer size must be >= 9!");
+  if (o->host_mem == 0) return mhb_set_error(MHB_ERR_ARG, "Please specify the host memory!");
+  const uint32_t k = o->k;
+  const double t0 = now_s();
+  const int n_threads = o->num_cpu_threads > 0 ? o->num_cpu_threads : omp_get_max_threads();
+
+  HostSeqs seqs;
+  if (!input.empty()) {  // seq_to_sdbg.cpp:424-434
+    EdgeMeta meta;
+    std::vector<uint32_t> edges;
+    if (int rc = read_all_edges(input, &meta, &edges)) return rc;
+    if (meta.kmer_size != k) return mhb_set_error(MHB_ERR_ARG, "edges were built for k=%u, not %u", meta.kmer_size, k);
+    const uint32_t W = meta.words_per_edge;
+    const size_t n = edges.size() / W;
+    seqs.words.reserve(n * div_ceil(k + 1, 16) * 5 / 4);
+    for (size_t i = 0; i < n; ++i) seqs.append_packed(&edges[i * W], k + 1, (uint16_t)(edges[i * W + W - 1] & 0xFFFF));
+    XINFO("Read %zu edges.\n", n);
+    if (o->need_mercy) {  // :436-450
+      const double t1 = now_s();
+      std::vector<uint32_t> cand;
+      if (!meta.is_sorted) return mhb_set_error(MHB_ERR_ARG, "--need_mercy needs sorted edges");
+      read_file(input + ".cand", &cand, false);
+      int64_t nr = 0, nm = 0;
+      if (int rc = gen_mercy_edges(edges, W, cand, k, std::max(1, n_threads - 1), &seqs, &nr, &nm)) return rc;
+      XINFO("Number of reads: %lld, Number of mercy edges: %lld\n", (long long)nr, (long long)nm);
+      XINFO("Adding mercy Done. Time elapsed: %.4f\n", now_s() - t1);
+    }
+  }
+  int64_t nr = 0;
+  if (!contig.empty()) {  // :452-476
+    if (int rc = read_contigs(contig, k + 1, o->k_from, k, true, &seqs, &nr)) return rc;
+    XINFO("Read %lld contigs from %s.\n", (long long)nr, contig.c_str());
+    if (int rc = read_contigs(bubble, k + 1, 0, 0, true, &seqs, &nr)) return rc;
+    XINFO("Read %lld contigs from %s.\n", (long long)nr, bubble.c_str());
+  }
+  if (!addi.empty()) {
+    if (int rc = read_contigs(addi, k + 1, 0, 0, true, &seqs, &nr)) return rc;
+    XINFO("Read %lld contigs from %s.\n", (long long)nr, addi.c_str());
+  }
+  if (!local.empty()) {
+    if (int rc = read_contigs(local, k + 1, 0, 0, true, &seqs, &nr)) return rc;
+    XINFO("Read %lld contigs from %s.\n", (long long)nr, local.c_str());
+  }
+
+  mhb_s2s_args a;
+  memset(&a, 0, sizeof(a));
+  a.k = k;
+  if (seqs.words.empty()) seqs.words.push_back(0);
+  a.words = seqs.words.data();
+  a.word_off = seqs.word_off.data();
+  a.len = seqs.len.data();
+  a.mult = seqs.mult.data();
+  a.n_seqs = seqs.size();
+  std::vector<char> resbuf(sizeof(mhb_s2s_result));
+  mhb_s2s_result *res = reinterpret_cast<mhb_s2s_result *>(resbuf.data());
+  if (int rc = mhb_s2s_host(&a, res)) return rc;
+  XINFO("GPU seq2sdbg: %llu sort items, extract %.2f ms, sort %.2f ms, emit %.2f ms\n", (unsigned long long)res->n_records,
+        res->t_extract_ms, res->t_sort_ms, res->t_emit_ms);
+
+  // sdbg_writer.cpp:25-79 + sdbg_meta.cpp:44-61: one file, buckets in id order
+  int rc = MHB_OK;
+  FILE *f = fopen((prefix + ".sdbg.0").c_str(), "wb");
+  if (!f) rc = mhb_set_error(MHB_ERR_IO, "cannot open %s.sdbg.0", prefix.c_str());
+  else {
+    if (res->n_bytes && fwrite(res->bytes, 1, res->n_bytes, f) != res->n_bytes) rc = mhb_set_error(MHB_ERR_IO, "write failed");
+    fclose(f);
+  }
+  if (!rc) {
+    FILE *g = fopen((prefix + ".sdbg_info").c_str(), "w");
+    if (!g) rc = mhb_set_error(MHB_ERR_IO, "cannot open %s.sdbg_info", prefix.c_str());
+    else {
+      fprintf(g, "k %u\nwords_per_tip_label %u\nnum_buckets %d\nnum_files %d\n", k, res->words_per_tip_label, MHB_NUM_BUCKETS,
+              res->n_items ? 1 : 0);
+      int empty = 0;
+      for (int b = 0; b < MHB_NUM_BUCKETS; ++b) {
+        const uint64_t *t = res->bucket_table + 4 * (size_t)b;
+        if (t[1]) fprintf(g, "%d 0 %llu %llu %llu %llu\n", b, (unsigned long long)t[0], (unsigned long long)t[1],
+                          (unsigned long long)t[2], (unsigned long long)t[3]);
+        else ++empty;
+      }
+      for (int i = 0; i < empty; ++i) fprintf(g, "18446744073709551615 18446744073709551615 0 0 0 0\n");
+      fclose(g);
+    }
+  }
+  XINFO("Number of $ A C G T A- C- G- T-:\n");
+  XINFO("");
+  for (int i = 0; i < 9; ++i) fprintf(stderr, "%llu ", (unsigned long long)res->w_count[i]);
+  fprintf(stderr, "\n");
+  XINFO("Total number of edges: %llu\n", (unsigned long long)res->n_items);
+  XINFO("Total number of ONEs: %llu\n", (unsigned long long)res->ones_in_last);
+  XINFO("Total number of $v edges: %llu\n", (unsigned long long)res->n_tips);
+  XINFO("seq2sdbg done. Time elapsed: %.4f\n", now_s() - t0);
+  mhb_free(res->bytes);
+  return rc;
+}

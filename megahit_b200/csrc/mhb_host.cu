@@ -1,0 +1,442 @@
+// mhb_host.cu -- host-level C ABI (include/mhb.h, layer 2): host buffers in, host buffers out.
+// Orchestrates the device-level entry points on one GPU with a grow-only device arena that is kept
+// between calls (so repeated steps do not pay cudaMalloc).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "mhb.h"
+#include "mhb_bits.cuh"
+#include "mhb_internal.h"
+
+using namespace mhb;
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return mhb_set_error(MHB_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,      \
+                           cudaGetErrorString(e_));                                                \
+  } while (0)
+#define CKR(call)           \
+  do {                      \
+    int rc_ = (call);       \
+    if (rc_) return rc_;    \
+  } while (0)
+
+namespace {
+
+struct Arena {
+  char *base = nullptr;
+  size_t cap = 0, used = 0;
+  int reserve(size_t bytes) {
+    used = 0;
+    if (bytes <= cap) return MHB_OK;
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc((void **)&base, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return mhb_set_error(MHB_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    cap = bytes;
+    return MHB_OK;
+  }
+  template <class T>
+  T *take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    char *p = base + used;
+    used += bytes;
+    return reinterpret_cast<T *>(p);
+  }
+  static size_t pad(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+};
+Arena g_arena;
+
+struct Timer {
+  cudaEvent_t a, b;
+  cudaStream_t st;
+  explicit Timer(cudaStream_t s) : st(s) {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+  }
+  ~Timer() {
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  }
+  void start() { cudaEventRecord(a, st); }
+  double stop() {
+    cudaEventRecord(b, st);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+  }
+};
+
+// Index a `.bin` image (sequence_package.h:224-240).  Fixed-length libraries need no side arrays.
+struct BinIndex {
+  uint32_t fixed_len = 0;
+  std::vector<uint64_t> rec_off, edge_off;
+  uint64_t n_edges = 0;
+};
+
+int index_bin(const uint32_t *bin, uint64_t bin_words, uint64_t n_reads, uint32_t k, BinIndex *ix) {
+  ix->fixed_len = 0;
+  ix->n_edges = 0;
+  if (n_reads == 0) return MHB_OK;
+  if (bin_words == 0) return mhb_set_error(MHB_ERR_ARG, "empty .bin image for %llu reads", (unsigned long long)n_reads);
+  const uint32_t L0 = bin[0];
+  const uint64_t stride = 1 + div_ceil(L0, 16);
+  bool fixed = L0 > 0 && bin_words == n_reads * stride;
+  if (fixed) {
+    for (uint64_t r = 0; r < n_reads; ++r) {
+      if (bin[r * stride] != L0) {
+        fixed = false;
+        break;
+      }
+    }
+  }
+  if (fixed) {
+    ix->fixed_len = L0;
+    ix->n_edges = L0 >= k + 1 ? n_reads * (uint64_t)(L0 - k) : 0;
+    if (L0 < k + 1) ix->fixed_len = L0;  // kernels skip short reads themselves
+    return MHB_OK;
+  }
+  ix->rec_off.resize(n_reads + 1);
+  ix->edge_off.resize(n_reads + 1);
+  uint64_t pos = 0, e = 0;
+  for (uint64_t r = 0; r < n_reads; ++r) {
+    if (pos >= bin_words) return mhb_set_error(MHB_ERR_ARG, ".bin image truncated at read %llu", (unsigned long long)r);
+    const uint32_t L = bin[pos];
+    ix->rec_off[r] = pos;
+    ix->edge_off[r] = e;
+    if (L >= k + 1) e += L - k;
+    pos += 1 + div_ceil(L, 16);
+  }
+  if (pos > bin_words) return mhb_set_error(MHB_ERR_ARG, ".bin image truncated");
+  ix->rec_off[n_reads] = pos;
+  ix->edge_off[n_reads] = e;
+  ix->n_edges = e;
+  return MHB_OK;
+}
+
+}  // namespace
+
+extern "C" int mhb_release(void) {
+  if (g_arena.base) cudaFree(g_arena.base);
+  g_arena = Arena();
+  return MHB_OK;
+}
+
+// ================================================================================================
+// count
+// ================================================================================================
+extern "C" int mhb_count_host(const mhb_count_args *args, mhb_count_result *res) {
+  if (!args || !res) return mhb_set_error(MHB_ERR_ARG, "null args");
+  memset(res, 0, sizeof(*res));
+  const uint32_t k = args->k;
+  if (k < 1 || k > MHB_MAX_K) return mhb_set_error(MHB_ERR_ARG, "kmer size %u out of range", k);
+  if (mhb_device_count() == 0) return mhb_set_error(MHB_ERR_CUDA, "no CUDA device: libmhb has no CPU path");
+  res->words_per_edge = words_per_edge(k);
+
+  BinIndex ix;
+  CKR(index_bin(args->bin, args->bin_words, args->n_reads, k, &ix));
+  const uint64_t n = ix.n_edges, n_reads = args->n_reads;
+  res->n_edge_records = n;
+
+  cudaStream_t st = 0;
+  Timer t_all(st), t(st);
+  t_all.start();
+
+  const uint32_t WR = count_record_words(k), WE = words_per_edge(k);
+  uint8_t sort_bytes[72];
+  const uint32_t n_sort = mhb_count_sort_bytes(k, sort_bytes);
+  const int32_t m = args->m;
+  const uint64_t cap_edges = n / (uint64_t)std::max(1, m) + 1;
+
+  const size_t bin_bytes = (args->bin_words * 4 + 15) & ~(size_t)15;
+  const size_t ws_bytes = mhb_sort_workspace_bytes(n, WR);
+  const size_t scratch_bytes = mhb_count_solid_scratch_bytes(n);
+  size_t need = Arena::pad(bin_bytes + 16) + 2 * Arena::pad((size_t)n * WR * 4 + 16) + Arena::pad(ws_bytes) +
+                Arena::pad(scratch_bytes) + Arena::pad((size_t)cap_edges * WE * 4) + Arena::pad(cap_edges) +
+                Arena::pad(65536 * 8) + Arena::pad(256 * 8) + 4096;
+  if (!ix.fixed_len) need += 2 * Arena::pad((n_reads + 1) * 8);
+  if (args->want_mercy) need += 2 * Arena::pad((size_t)(n_reads + 1) * 4);
+  CKR(g_arena.reserve(need));
+
+  uint32_t *d_bin = g_arena.take<uint32_t>(bin_bytes / 4 + 4);
+  uint32_t *d_a = g_arena.take<uint32_t>((size_t)n * WR + 4);
+  uint32_t *d_b = g_arena.take<uint32_t>((size_t)n * WR + 4);
+  char *d_ws = g_arena.take<char>(ws_bytes);
+  char *d_scratch = g_arena.take<char>(scratch_bytes);
+  uint32_t *d_edges = g_arena.take<uint32_t>((size_t)cap_edges * WE);
+  uint8_t *d_aux = g_arena.take<uint8_t>(cap_edges);
+  uint64_t *d_mul_hist = g_arena.take<uint64_t>(65536);
+  uint64_t *d_hist0 = g_arena.take<uint64_t>(256);
+  uint64_t *d_nsolid = g_arena.take<uint64_t>(8);
+  uint64_t *d_rec_off = nullptr, *d_edge_off = nullptr;
+  uint32_t *d_first = nullptr, *d_last = nullptr;
+  if (!ix.fixed_len) {
+    d_rec_off = g_arena.take<uint64_t>(n_reads + 1);
+    d_edge_off = g_arena.take<uint64_t>(n_reads + 1);
+  }
+  if (args->want_mercy) {
+    d_first = g_arena.take<uint32_t>(n_reads + 1);
+    d_last = g_arena.take<uint32_t>(n_reads + 1);
+  }
+
+  // ---- H2D ----
+  t.start();
+  if (args->bin_words) CK(cudaMemcpyAsync(d_bin, args->bin, args->bin_words * 4, cudaMemcpyHostToDevice, st));
+  if (!ix.fixed_len && n_reads) {
+    CK(cudaMemcpyAsync(d_rec_off, ix.rec_off.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_edge_off, ix.edge_off.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaMemsetAsync(d_mul_hist, 0, 65536 * 8, st));
+  CK(cudaMemsetAsync(d_hist0, 0, 256 * 8, st));
+  CK(cudaMemsetAsync(d_nsolid, 0, 64, st));
+  res->t_h2d_ms = t.stop();
+
+  mhb_dev_reads reads;
+  reads.bin = d_bin;
+  reads.bin_words = args->bin_words;
+  reads.n_reads = n_reads;
+  reads.fixed_len = ix.fixed_len;
+  reads.rec_off = d_rec_off;
+  reads.edge_off = d_edge_off;
+
+  // ---- extract ----
+  t.start();
+  CKR(mhb_count_extract(st, &reads, k, d_a, n, d_hist0, sort_bytes[0]));
+  res->t_extract_ms = t.stop();
+
+  // ---- sort ----
+  t.start();
+  int in_b = 0;
+  res->n_sort_passes = n ? n_sort : 0;
+  CKR(mhb_sort_records_impl(st, d_a, d_b, n, WR, sort_bytes, n_sort, d_hist0, d_ws, ws_bytes, &in_b, res->sort_pass_ms));
+  res->t_sort_ms = t.stop();
+  const uint32_t *d_sorted = in_b ? d_b : d_a;
+
+  // ---- count ----
+  t.start();
+  CKR(mhb_count_solid(st, d_sorted, n, k, m, d_edges, d_aux, cap_edges, d_mul_hist, d_nsolid, d_scratch, scratch_bytes));
+  uint64_t n_solid = 0;
+  CK(cudaMemcpyAsync(&n_solid, d_nsolid, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  res->t_count_ms = t.stop();
+  if (n_solid > cap_edges) return mhb_set_error(MHB_ERR_NOMEM, "internal: solid edges exceed capacity");
+  res->n_solid = n_solid;
+
+  // ---- mercy bookkeeping ----
+  std::vector<uint32_t> h_first, h_last;
+  if (args->want_mercy && n_reads) {
+    t.start();
+    uint64_t n_tip = 0;
+    CKR(mhb_count_tip_edges(st, d_aux, n_solid, &n_tip));
+    const size_t ts_bytes = mhb_tipset_bytes(n_tip, k);
+    // the sort workspace and the unused ping-pong buffer are free now: put the tip set there if it fits
+    char *d_tips = nullptr;
+    uint32_t *d_free = in_b ? d_a : d_b;
+    bool own = false;
+    if (ts_bytes <= (size_t)n * WR * 4) d_tips = (char *)d_free;
+    else {
+      CK(cudaMalloc((void **)&d_tips, ts_bytes));
+      own = true;
+    }
+    int rc = mhb_tipset_build(st, d_edges, d_aux, n_solid, k, d_tips, ts_bytes, n_tip);
+    if (!rc) rc = mhb_count_mark_mercy(st, &reads, k, d_tips, ts_bytes, d_first, d_last);
+    h_first.resize(n_reads);
+    h_last.resize(n_reads);
+    if (!rc) {
+      cudaMemcpyAsync(h_first.data(), d_first, n_reads * 4, cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(h_last.data(), d_last, n_reads * 4, cudaMemcpyDeviceToHost, st);
+      if (cudaStreamSynchronize(st) != cudaSuccess) rc = mhb_set_error(MHB_ERR_CUDA, "mercy marking failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (own) cudaFree(d_tips);
+    if (rc) return rc;
+    res->t_mercy_ms = t.stop();
+  }
+
+  // ---- D2H ----
+  t.start();
+  res->edges = (uint32_t *)malloc(std::max<size_t>(1, (size_t)n_solid * WE * 4));
+  if (!res->edges) return mhb_set_error(MHB_ERR_NOMEM, "host malloc failed");
+  if (n_solid) CK(cudaMemcpyAsync(res->edges, d_edges, (size_t)n_solid * WE * 4, cudaMemcpyDeviceToHost, st));
+  std::vector<uint64_t> h_hist(65536);
+  CK(cudaMemcpyAsync(h_hist.data(), d_mul_hist, 65536 * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  res->t_d2h_ms = t.stop();
+  for (int i = 0; i <= MHB_MAX_MUL; ++i) res->counting[i] = (int64_t)h_hist[i];
+
+  if (args->want_mercy) {  // kmer_counter.cpp:390-401
+    std::vector<uint64_t> ids;
+    for (uint64_t r = 0; r < n_reads; ++r) {
+      const uint32_t f = h_first[r], l = h_last[r];
+      if (f != MHB_SENTINEL_OFFSET && l != MHB_SENTINEL_OFFSET) {
+        ++res->n_has_tips;
+        if (l > f) ids.push_back(r);
+      }
+    }
+    res->n_cand = ids.size();
+    res->cand_ids = (uint64_t *)malloc(std::max<size_t>(1, ids.size() * 8));
+    if (!ids.empty()) memcpy(res->cand_ids, ids.data(), ids.size() * 8);
+  }
+  res->t_total_ms = t_all.stop();
+  return MHB_OK;
+}
+
+// ================================================================================================
+// seq2sdbg
+// ================================================================================================
+extern "C" int mhb_s2s_host(const mhb_s2s_args *args, mhb_s2s_result *res) {
+  if (!args || !res) return mhb_set_error(MHB_ERR_ARG, "null args");
+  memset(res, 0, sizeof(*res));
+  const uint32_t k = args->k;
+  if (k < 9 || k > MHB_MAX_K) return mhb_set_error(MHB_ERR_ARG, "kmer size must be >= 9!");
+  if (mhb_device_count() == 0) return mhb_set_error(MHB_ERR_CUDA, "no CUDA device: libmhb has no CPU path");
+  res->words_per_tip_label = words_per_tip_label(k);
+  const uint64_t ns = args->n_seqs;
+
+  // item offsets; detect the fixed-length, gap-free layout (edges only)
+  std::vector<uint64_t> item_off(ns + 1);
+  uint64_t n_items = 0;
+  bool fixed = ns > 0;
+  const uint32_t L0 = ns ? args->len[0] : 0;
+  for (uint64_t s = 0; s < ns; ++s) {
+    item_off[s] = n_items;
+    const uint32_t L = args->len[s];
+    if (L >= k + 1) n_items += 2ull * (L - k + 2);
+    if (L != L0 || args->word_off[s] != s * (uint64_t)div_ceil(L0, 16)) fixed = false;
+  }
+  item_off[ns] = n_items;
+  if (L0 < k + 1) fixed = false;
+  const uint64_t n_words = ns ? args->word_off[ns] : 0;
+  res->n_records = n_items;
+
+  cudaStream_t st = 0;
+  Timer t_all(st), t(st);
+  t_all.start();
+  const uint32_t W = s2s_record_words(k);
+  uint8_t sort_bytes[72];
+  const uint32_t n_sort = mhb_s2s_sort_bytes(k, sort_bytes);
+  const size_t ws_bytes = mhb_sort_workspace_bytes(n_items, W);
+  const size_t scratch_bytes = mhb_s2s_emit_scratch_bytes(n_items);
+  // worst case bytes per sort item: 2 + 2 + 4*WPT (every item a large-multiplicity tip)
+  const uint64_t cap_bytes = n_items * (4ull + 4ull * res->words_per_tip_label) + 16;
+  size_t need = Arena::pad(n_words * 4 + 64) + Arena::pad((ns + 1) * 8) * 2 + Arena::pad((ns + 1) * 4) +
+                Arena::pad((ns + 1) * 2) + 2 * Arena::pad((size_t)n_items * W * 4 + 16) + Arena::pad(ws_bytes) +
+                Arena::pad(scratch_bytes) + Arena::pad(cap_bytes) + Arena::pad((size_t)MHB_NUM_BUCKETS * 4 * 8) +
+                Arena::pad(256 * 8) + Arena::pad(16 * 8) + 4096;
+  CKR(g_arena.reserve(need));
+  uint32_t *d_words = g_arena.take<uint32_t>(n_words + 16);
+  uint64_t *d_word_off = g_arena.take<uint64_t>(ns + 1);
+  uint64_t *d_item_off = g_arena.take<uint64_t>(ns + 1);
+  uint32_t *d_len = g_arena.take<uint32_t>(ns + 1);
+  uint16_t *d_mult = g_arena.take<uint16_t>(ns + 1);
+  uint32_t *d_a = g_arena.take<uint32_t>((size_t)n_items * W + 4);
+  uint32_t *d_b = g_arena.take<uint32_t>((size_t)n_items * W + 4);
+  char *d_ws = g_arena.take<char>(ws_bytes);
+  char *d_scratch = g_arena.take<char>(scratch_bytes);
+  uint8_t *d_bytes = g_arena.take<uint8_t>(cap_bytes);
+  uint64_t *d_table = g_arena.take<uint64_t>((size_t)MHB_NUM_BUCKETS * 4);
+  uint64_t *d_hist0 = g_arena.take<uint64_t>(256);
+  uint64_t *d_totals = g_arena.take<uint64_t>(16);
+
+  if (ns) {
+    CK(cudaMemcpyAsync(d_words, args->words, n_words * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_word_off, args->word_off, (ns + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_item_off, item_off.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_len, args->len, ns * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_mult, args->mult, ns * 2, cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaMemsetAsync(d_hist0, 0, 256 * 8, st));
+
+  mhb_dev_seqs seqs;
+  seqs.words = d_words;
+  seqs.n_words = n_words;
+  seqs.n_seqs = ns;
+  seqs.fixed_len = fixed ? L0 : 0;
+  seqs.word_off = d_word_off;
+  seqs.len = d_len;
+  seqs.item_off = d_item_off;
+  seqs.mult = d_mult;
+
+  t.start();
+  CKR(mhb_s2s_extract(st, &seqs, k, d_a, n_items, d_hist0, sort_bytes[0]));
+  res->t_extract_ms = t.stop();
+  t.start();
+  int in_b = 0;
+  CKR(mhb_sort_records_impl(st, d_a, d_b, n_items, W, sort_bytes, n_sort, d_hist0, d_ws, ws_bytes, &in_b, nullptr));
+  res->t_sort_ms = t.stop();
+  t.start();
+  CKR(mhb_s2s_emit(st, in_b ? d_b : d_a, n_items, k, d_bytes, cap_bytes, d_table, d_totals, d_scratch, scratch_bytes));
+  uint64_t totals[16];
+  CK(cudaMemcpyAsync(totals, d_totals, sizeof(totals), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(res->bucket_table, d_table, sizeof(res->bucket_table), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  res->t_emit_ms = t.stop();
+  res->n_bytes = totals[0];
+  res->n_items = totals[1];
+  res->n_tips = totals[2];
+  res->n_large_mul = totals[3];
+  for (int i = 0; i < 9; ++i) res->w_count[i] = totals[4 + i];
+  res->ones_in_last = totals[13];
+  if (res->n_bytes > cap_bytes) return mhb_set_error(MHB_ERR_NOMEM, "internal: SdBG byte stream exceeds capacity");
+  res->bytes = (uint8_t *)malloc(std::max<size_t>(1, res->n_bytes));
+  if (!res->bytes) return mhb_set_error(MHB_ERR_NOMEM, "host malloc failed");
+  if (res->n_bytes) CK(cudaMemcpy(res->bytes, d_bytes, res->n_bytes, cudaMemcpyDeviceToHost));
+  res->t_total_ms = t_all.stop();
+  return MHB_OK;
+}
+
+// ================================================================================================
+// Self-test hooks: run the SAME record builders the kernels use (mhb_kernels.cuh, __host__ __device__)
+// on the host, so that `pytest -m "not gpu"` can check the bit arithmetic against the oracle without a
+// GPU.  They build one record at a time and are not a compute path.
+// ================================================================================================
+#include "mhb_kernels.cuh"
+
+extern "C" int mhb_selftest_count_record(const uint32_t *read_words, uint32_t nwords, uint32_t L, uint32_t k, uint32_t q,
+                                         uint32_t *rec_out, uint32_t *strand_out) {
+  const uint32_t W = count_key_words(k), WR = count_record_words(k);
+  if (k < 1 || k > MHB_MAX_K || L < k + 1 || q + k + 1 > L) return mhb_set_error(MHB_ERR_ARG, "bad selftest args");
+#define M(WW)                                                                       \
+  if (W == WW && WR == WW) {                                                        \
+    uint32_t r[WW];                                                                 \
+    make_count_record<WW, WW>(read_words, nwords, L, k, q, r, *strand_out);         \
+    memcpy(rec_out, r, sizeof(r));                                                  \
+    return MHB_OK;                                                                  \
+  }                                                                                 \
+  if (W == WW && WR == WW + 1) {                                                    \
+    uint32_t r[WW + 1];                                                             \
+    make_count_record<WW, WW + 1>(read_words, nwords, L, k, q, r, *strand_out);     \
+    memcpy(rec_out, r, sizeof(r));                                                  \
+    return MHB_OK;                                                                  \
+  }
+  M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12) M(13) M(14) M(15) M(16)
+#undef M
+  return mhb_set_error(MHB_ERR_ARG, "unsupported k");
+}
+
+extern "C" int mhb_selftest_s2s_record(const uint32_t *seq_words, uint32_t nwords, uint32_t L, uint32_t k, uint32_t strand,
+                                       uint32_t offset, uint32_t mult, uint32_t *rec_out) {
+  const uint32_t W = s2s_record_words(k);
+  if (k < 9 || k > MHB_MAX_K || L < k + 1 || offset > L - k + 1) return mhb_set_error(MHB_ERR_ARG, "bad selftest args");
+#define M(WW)                                                                \
+  if (W == WW) {                                                             \
+    uint32_t r[WW];                                                          \
+    make_s2s_record<WW>(seq_words, nwords, L, k, strand, offset, mult, r);   \
+    memcpy(rec_out, r, sizeof(r));                                           \
+    return MHB_OK;                                                           \
+  }
+  M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12) M(13) M(14) M(15) M(16) M(17)
+#undef M
+  return mhb_set_error(MHB_ERR_ARG, "unsupported k");
+}

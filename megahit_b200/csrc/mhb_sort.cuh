@@ -1,0 +1,195 @@
+// mhb_sort.cuh -- on-device LSD radix sort of fixed-width records (8-bit digits, one sweep per digit).
+//
+// Replaces kmlib::kmsort (voutcn/megahit src/kmlib/kmsort.h:43-122, an in-place MSD byte radix +
+// insertion sort run per 16-bit bucket on the CPU) with a stable LSD sort over whole-array passes:
+// same total order on the key (kmsort_selector.cpp:18-27), ties left in input order.
+//
+// One pass = one persistent kernel: every CTA repeatedly claims the next tile (atomic ticket, so tiles
+// start in order), ranks its records by digit with warp match + shared-memory counters, publishes the
+// tile's per-digit counts and resolves its global offsets by decoupled look-back over earlier tiles,
+// reorders the tile in shared memory so that every digit's records are contiguous, and scatters them
+// with coalesced stores.  While the records are in registers the pass also accumulates the histogram
+// of the NEXT pass's digit, so the input is never read just to count.
+#pragma once
+#include "mhb_kernels.cuh"
+
+namespace mhb {
+
+// look-back descriptor: [63:62] status (0 invalid, 1 partial, 2 inclusive) [61:54] epoch [53:0] value
+static constexpr u64 kLbPartial = 1ull << 62, kLbInclusive = 2ull << 62, kLbStatusMask = 3ull << 62;
+static constexpr u64 kLbValueMask = (1ull << 54) - 1;
+__host__ __device__ inline u64 lb_epoch(u32 e) { return (u64)(e & 255u) << 54; }
+
+template <int WR>
+struct SortCfg {
+  // tile = THREADS * IPT records; sized so that two CTAs fit in one SM's shared memory
+  static constexpr int THREADS = 384;
+  static constexpr int IPT = WR <= 2 ? 18 : (WR <= 3 ? 12 : (WR <= 4 ? 10 : (WR <= 6 ? 6 : (WR <= 9 ? 4 : 2))));
+  static constexpr int TILE = THREADS * IPT;
+  static constexpr int NW = THREADS / 32;
+  static constexpr size_t SMEM = (size_t)(NW * 256 + 256 + 256 + 8) * 4 + 256 * 8 + (size_t)TILE * WR * 4;
+};
+
+// exclusive scan of a 256-bin histogram (one block of 256 threads)
+__global__ void k_hist_scan256(const u64 *hist, u64 *bin_base) {
+  __shared__ u64 s[256];
+  const u32 t = threadIdx.x;
+  s[t] = hist[t];
+  __syncthreads();
+  for (int d = 1; d < 256; d <<= 1) {
+    u64 v = t >= (u32)d ? s[t - d] : 0;
+    __syncthreads();
+    s[t] += v;
+    __syncthreads();
+  }
+  bin_base[t] = s[t] - hist[t];
+}
+
+// standalone digit histogram (only needed when the producer of the records did not provide one)
+template <int WR>
+__global__ void k_hist_byte(const u32 *in, u64 n, int byte_idx, u64 *hist) {
+  __shared__ u32 s_h[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_h[i] = 0;
+  __syncthreads();
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    u32 r[WR];
+    ld_rec<WR>(in, i, r);
+    atomicAdd(&s_h[rec_byte<WR>(r, byte_idx)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    if (s_h[i]) atomicAdd((unsigned long long *)&hist[i], (unsigned long long)s_h[i]);
+}
+
+template <int WR>
+__global__ void __launch_bounds__(SortCfg<WR>::THREADS)
+    k_radix_pass(const u32 *__restrict__ in, u32 *__restrict__ out, u64 n, u32 num_tiles, int byte_idx,
+                 const u64 *__restrict__ bin_base, u64 *lookback, u32 *tile_counter, u64 *next_hist,
+                 int next_byte, u32 epoch) {
+  using C = SortCfg<WR>;
+  constexpr int THREADS = C::THREADS, IPT = C::IPT, TILE = C::TILE, NW = C::NW;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u64 *s_glob = reinterpret_cast<u64 *>(smem_raw);          // 256: global offset - local bin start
+  u32 *s_warp_hist = reinterpret_cast<u32 *>(s_glob + 256);  // NW*256
+  u32 *s_bin_start = s_warp_hist + NW * 256;                 // 256
+  u32 *s_next = s_bin_start + 256;                           // 256
+  u32 *s_misc = s_next + 256;                                // 8 (ticket + scan scratch is separate)
+  u32 *s_recs = s_misc + 8;                                  // TILE*WR (16-byte aligned)
+  __shared__ u32 s_scan[THREADS / 32 + 1];
+
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 lt_mask = lanemask_lt();
+  const u64 ep = lb_epoch(epoch);
+
+  for (int i = tid; i < 256; i += THREADS) s_next[i] = 0;
+
+  while (true) {
+    if (tid == 0) s_misc[0] = atomicAdd(tile_counter, 1u);
+    for (int i = tid; i < NW * 256; i += THREADS) s_warp_hist[i] = 0;
+    __syncthreads();
+    const u32 tile = s_misc[0];
+    if (tile >= num_tiles) break;
+    const u64 tile_base = (u64)tile * TILE;
+    const u32 valid = (u32)((n - tile_base) < (u64)TILE ? (n - tile_base) : (u64)TILE);
+
+    // ---- load (warp-striped: slot i of lane l = warp chunk[i*32 + l]) ----
+    u32 r[IPT][WR];
+    const u64 warp_base = tile_base + (u64)warp * 32 * IPT;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const u64 idx = warp_base + (u64)i * 32 + lane;
+      if (idx < n) {
+        ld_rec<WR>(in, idx, r[i]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < WR; ++j) r[i][j] = 0xFFFFFFFFu;  // padding sorts to the very end of the tile
+      }
+    }
+
+    // ---- rank inside the warp: match on the digit, leader bumps the warp's counter ----
+    u32 rk[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const u32 d = rec_byte<WR>(r[i], byte_idx);
+      const u32 peers = __match_any_sync(0xffffffffu, d);
+      const u32 leader = __ffs(peers) - 1;
+      u32 old = 0;
+      if (lane == leader) {
+        old = s_warp_hist[warp * 256 + d];
+        s_warp_hist[warp * 256 + d] = old + __popc(peers);
+      }
+      __syncwarp();
+      old = __shfl_sync(0xffffffffu, old, leader);
+      rk[i] = old + __popc(peers & lt_mask);
+    }
+    __syncthreads();
+
+    // ---- per digit: prefix over warps, tile total, local start, global offset (look-back) ----
+    u32 total = 0;
+    if (tid < 256) {
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const u32 c = s_warp_hist[w * 256 + tid];
+        s_warp_hist[w * 256 + tid] = total;
+        total += c;
+      }
+    }
+    u32 tile_total;
+    const u32 excl = block_excl_scan<THREADS>(total, s_scan, tile_total);
+    if (tid < 256) {
+      s_bin_start[tid] = excl;
+      // padding records all carry digit 255 and are not real: exclude them from what we publish
+      const u64 pub = (u64)total - ((tid == 255) ? (u64)(TILE - valid) : 0ull);
+      u64 *my = lookback + (u64)tile * 256 + tid;
+      u64 prefix = 0;
+      if (tile == 0) {
+        st_relaxed(my, kLbInclusive | ep | pub);
+      } else {
+        st_relaxed(my, kLbPartial | ep | pub);
+        for (u32 p = tile; p-- > 0;) {
+          const u64 *pp = lookback + (u64)p * 256 + tid;
+          u64 v;
+          do {
+            v = ld_relaxed(pp);
+          } while ((v & kLbStatusMask) == 0 || (v & lb_epoch(255)) != ep);
+          prefix += v & kLbValueMask;
+          if ((v & kLbStatusMask) == kLbInclusive) break;
+        }
+        st_relaxed(my, kLbInclusive | ep | (prefix + pub));
+      }
+      s_glob[tid] = bin_base[tid] + prefix - (u64)excl;
+    }
+    __syncthreads();
+
+    // ---- reorder in shared memory: every digit's records become contiguous, input order kept ----
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const u32 d = rec_byte<WR>(r[i], byte_idx);
+      const u32 pos = s_bin_start[d] + s_warp_hist[warp * 256 + d] + rk[i];
+      st_rec<WR>(s_recs, pos, r[i]);
+    }
+    __syncthreads();
+
+    // ---- coalesced scatter + next digit's histogram ----
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const u32 p = (u32)i * THREADS + tid;
+      if (p < valid) {
+        u32 q[WR];
+        ld_rec<WR>(s_recs, p, q);
+        const u32 d = rec_byte<WR>(q, byte_idx);
+        st_rec<WR>(out, s_glob[d] + p, q);
+        if (next_hist) atomicAdd(&s_next[rec_byte<WR>(q, next_byte)], 1u);
+      }
+    }
+    __syncthreads();
+  }
+
+  if (next_hist) {
+    __syncthreads();
+    for (int i = tid; i < 256; i += THREADS)
+      if (s_next[i]) atomicAdd((unsigned long long *)&next_hist[i], (unsigned long long)s_next[i]);
+  }
+}
+
+}  // namespace mhb

@@ -1,0 +1,158 @@
+"""Device-level stages on torch tensors (PyTorch = device memory + streams; the kernels are libmhb's).
+
+`CountPlan` / `S2sPlan` pre-allocate every buffer a stage needs so that a timed step launches kernels
+only; all launches go to torch's current stream, so `torch.cuda.Event` timing sees them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def sort_records(a: torch.Tensor, b: torch.Tensor, n: int, words: int, sort_bytes, first_hist=None, ws=None):
+    """LSD radix sort of n records (int32 tensors a, b of >= n*words elements).  Returns the tensor
+    holding the result."""
+    L = lib.load()
+    need = L.mhb_sort_workspace_bytes(n, words)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=a.device)
+    bytes_arr = (C.c_uint8 * len(sort_bytes))(*sort_bytes)
+    in_b = C.c_int(0)
+    lib._check(L.mhb_sort_records(_stream(), _ptr(a), _ptr(b), n, words, bytes_arr, len(sort_bytes), _ptr(first_hist),
+                                  _ptr(ws), ws.numel(), C.byref(in_b)))
+    return b if in_b.value else a
+
+
+class CountPlan:
+    """`count` (extract -> sort -> solid edges [-> mercy bookkeeping]) for a fixed-length read library
+    resident on the device."""
+
+    def __init__(self, n_reads: int, read_len: int, k: int, m: int, device, want_mercy: bool = True):
+        L = lib.load()
+        self.L, self.k, self.m, self.n_reads, self.read_len, self.device = L, k, m, n_reads, read_len, device
+        self.want_mercy = want_mercy
+        self.n = n_reads * (read_len - k) if read_len >= k + 1 else 0
+        self.WR, self.WE = lib.count_record_words(k), lib.words_per_edge(k)
+        self.sort_bytes = lib.count_sort_bytes(k)
+        n = self.n
+        i32 = dict(dtype=torch.int32, device=device)
+        self.a = torch.empty(n * self.WR + 4, **i32)
+        self.b = torch.empty(n * self.WR + 4, **i32)
+        self.ws = torch.empty(L.mhb_sort_workspace_bytes(n, self.WR), dtype=torch.uint8, device=device)
+        self.scratch = torch.empty(L.mhb_count_solid_scratch_bytes(n), dtype=torch.uint8, device=device)
+        self.cap_edges = n // max(1, m) + 1
+        self.edges = torch.empty(self.cap_edges * self.WE, **i32)
+        self.aux = torch.empty(self.cap_edges, dtype=torch.uint8, device=device)
+        self.mul_hist = torch.zeros(65536, dtype=torch.int64, device=device)
+        self.hist0 = torch.zeros(256, dtype=torch.int64, device=device)
+        self.n_solid_dev = torch.zeros(8, dtype=torch.int64, device=device)
+        self.first = torch.empty(n_reads + 1, **i32) if want_mercy else None
+        self.last = torch.empty(n_reads + 1, **i32) if want_mercy else None
+        self.tipset = None
+        self.events = {}
+
+    def _reads(self, bin_dev: torch.Tensor) -> lib.DevReads:
+        return lib.DevReads(bin_dev.data_ptr(), bin_dev.numel(), self.n_reads, self.read_len, None, None)
+
+    def _mark(self, name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.events.setdefault(name, []).append(ev)
+
+    def extract(self, bin_dev):
+        self.hist0.zero_()
+        lib._check(self.L.mhb_count_extract(_stream(), C.byref(self._reads(bin_dev)), self.k, _ptr(self.a), self.n,
+                                            _ptr(self.hist0), self.sort_bytes[0]))
+
+    def sort(self):
+        self.sorted = sort_records(self.a, self.b, self.n, self.WR, self.sort_bytes, self.hist0, self.ws)
+        return self.sorted
+
+    def count(self):
+        self.mul_hist.zero_()
+        self.n_solid_dev.zero_()
+        lib._check(self.L.mhb_count_solid(_stream(), _ptr(self.sorted), self.n, self.k, self.m, _ptr(self.edges),
+                                          _ptr(self.aux), self.cap_edges, _ptr(self.mul_hist), _ptr(self.n_solid_dev),
+                                          _ptr(self.scratch), self.scratch.numel()))
+
+    def mercy(self, bin_dev):
+        n_solid = int(self.n_solid_dev[0].item())
+        n_tip = C.c_uint64(0)
+        lib._check(self.L.mhb_count_tip_edges(_stream(), _ptr(self.aux), n_solid, C.byref(n_tip)))
+        need = self.L.mhb_tipset_bytes(n_tip.value, self.k)
+        if self.tipset is None or self.tipset.numel() < need:
+            self.tipset = torch.empty(need, dtype=torch.uint8, device=self.device)
+        lib._check(self.L.mhb_tipset_build(_stream(), _ptr(self.edges), _ptr(self.aux), n_solid, self.k,
+                                           _ptr(self.tipset), need, n_tip.value))
+        lib._check(self.L.mhb_count_mark_mercy(_stream(), C.byref(self._reads(bin_dev)), self.k, _ptr(self.tipset),
+                                               need, _ptr(self.first), _ptr(self.last)))
+        return n_solid, n_tip.value
+
+    def run(self, bin_dev: torch.Tensor, timed: bool = False):
+        """One pass of the count stage over the resident library.  Returns n_solid (host int)."""
+        if timed:
+            self._mark("t0")
+        self.extract(bin_dev)
+        if timed:
+            self._mark("extract")
+        self.sort()
+        if timed:
+            self._mark("sort")
+        self.count()
+        if timed:
+            self._mark("count")
+        if self.want_mercy:
+            n_solid, _ = self.mercy(bin_dev)
+        else:
+            n_solid = int(self.n_solid_dev[0].item())
+        if timed:
+            self._mark("mercy")
+        return n_solid
+
+    def edges_host(self, n_solid: int) -> np.ndarray:
+        return self.edges[: n_solid * self.WE].cpu().numpy().view(np.uint32).reshape(-1, self.WE)
+
+
+class S2sPlan:
+    """`seq2sdbg` for fixed-length sequences ((k+1)-mer edges) resident on the device."""
+
+    def __init__(self, n_seqs: int, seq_len: int, k: int, device):
+        L = lib.load()
+        self.L, self.k, self.n_seqs, self.seq_len, self.device = L, k, n_seqs, seq_len, device
+        self.W = lib.s2s_record_words(k)
+        self.sort_bytes = lib.s2s_sort_bytes(k)
+        self.n_items = n_seqs * 2 * (seq_len - k + 2)
+        n = self.n_items
+        i32 = dict(dtype=torch.int32, device=device)
+        self.a = torch.empty(n * self.W + 4, **i32)
+        self.b = torch.empty(n * self.W + 4, **i32)
+        self.ws = torch.empty(L.mhb_sort_workspace_bytes(n, self.W), dtype=torch.uint8, device=device)
+        self.scratch = torch.empty(L.mhb_s2s_emit_scratch_bytes(n), dtype=torch.uint8, device=device)
+        wpt = (k + 15) // 16
+        self.cap_bytes = n * (4 + 4 * wpt) + 16
+        self.bytes = torch.empty(self.cap_bytes, dtype=torch.uint8, device=device)
+        self.table = torch.zeros(65536 * 4, dtype=torch.int64, device=device)
+        self.totals = torch.zeros(16, dtype=torch.int64, device=device)
+        self.hist0 = torch.zeros(256, dtype=torch.int64, device=device)
+
+    def run(self, words: torch.Tensor, mult: torch.Tensor):
+        seqs = lib.DevSeqs(words.data_ptr(), words.numel(), self.n_seqs, self.seq_len, None, None, None, mult.data_ptr())
+        self.hist0.zero_()
+        lib._check(self.L.mhb_s2s_extract(_stream(), C.byref(seqs), self.k, _ptr(self.a), self.n_items, _ptr(self.hist0),
+                                          self.sort_bytes[0]))
+        srt = sort_records(self.a, self.b, self.n_items, self.W, self.sort_bytes, self.hist0, self.ws)
+        lib._check(self.L.mhb_s2s_emit(_stream(), _ptr(srt), self.n_items, self.k, _ptr(self.bytes), self.cap_bytes,
+                                       _ptr(self.table), _ptr(self.totals), _ptr(self.scratch), self.scratch.numel()))
+        return self.totals

@@ -1,0 +1,276 @@
+"""ctypes binding of libmhb.so (the C ABI declared in include/mhb.h).
+
+This is the host-side mirror of the reference's interface for the SdBG-construction path:
+`count_run` / `seq2sdbg_run` take the same options as `megahit_core count` / `seq2sdbg`
+(src/main_sdbg_build.cpp:42-57, :164-189), `count_host` / `s2s_host` are the in-memory equivalents of
+KmerCounter::Run / SeqToSdbg::Run, and the `dev_*` functions are the individual device stages working
+on torch tensors (device memory, streams = plumbing).
+
+There is NO CPU fallback: every compute entry point raises MhbError when the CUDA library or a device
+is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmhb.so")
+NUM_BUCKETS = 65536
+SENTINEL_OFFSET = 0xFFFFFFFF
+
+_lib = None
+
+
+class MhbError(RuntimeError):
+    pass
+
+
+class DevReads(C.Structure):
+    _fields_ = [("bin", C.c_void_p), ("bin_words", C.c_uint64), ("n_reads", C.c_uint64), ("fixed_len", C.c_uint32),
+                ("rec_off", C.c_void_p), ("edge_off", C.c_void_p)]
+
+
+class DevSeqs(C.Structure):
+    _fields_ = [("words", C.c_void_p), ("n_words", C.c_uint64), ("n_seqs", C.c_uint64), ("fixed_len", C.c_uint32),
+                ("word_off", C.c_void_p), ("len", C.c_void_p), ("item_off", C.c_void_p), ("mult", C.c_void_p)]
+
+
+class CountArgs(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("m", C.c_int32), ("bin", C.c_void_p), ("bin_words", C.c_uint64),
+                ("n_reads", C.c_uint64), ("want_mercy", C.c_int)]
+
+
+class CountResult(C.Structure):
+    _fields_ = [("n_edge_records", C.c_uint64), ("n_solid", C.c_uint64), ("words_per_edge", C.c_uint32),
+                ("edges", C.POINTER(C.c_uint32)), ("n_cand", C.c_uint64), ("cand_ids", C.POINTER(C.c_uint64)),
+                ("n_has_tips", C.c_uint64), ("counting", C.c_int64 * 65536),
+                ("t_h2d_ms", C.c_double), ("t_extract_ms", C.c_double), ("t_sort_ms", C.c_double),
+                ("t_count_ms", C.c_double), ("t_mercy_ms", C.c_double), ("t_d2h_ms", C.c_double),
+                ("t_total_ms", C.c_double), ("n_sort_passes", C.c_uint32), ("sort_pass_ms", C.c_double * 64)]
+
+
+class S2sArgs(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("words", C.c_void_p), ("word_off", C.c_void_p), ("len", C.c_void_p),
+                ("mult", C.c_void_p), ("n_seqs", C.c_uint64)]
+
+
+class S2sResult(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("n_items", C.c_uint64), ("n_tips", C.c_uint64),
+                ("n_large_mul", C.c_uint64), ("n_bytes", C.c_uint64), ("words_per_tip_label", C.c_uint32),
+                ("bytes", C.POINTER(C.c_uint8)), ("bucket_table", C.c_uint64 * (65536 * 4)),
+                ("w_count", C.c_uint64 * 9), ("ones_in_last", C.c_uint64),
+                ("t_total_ms", C.c_double), ("t_extract_ms", C.c_double), ("t_sort_ms", C.c_double),
+                ("t_emit_ms", C.c_double)]
+
+
+class CountOpts(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("m", C.c_int32), ("host_mem", C.c_double), ("num_cpu_threads", C.c_int32),
+                ("read_lib_file", C.c_char_p), ("output_prefix", C.c_char_p), ("mem_flag", C.c_int32)]
+
+
+class Seq2SdbgOpts(C.Structure):
+    _fields_ = [("host_mem", C.c_double), ("k", C.c_uint32), ("k_from", C.c_uint32), ("num_cpu_threads", C.c_int32),
+                ("contig", C.c_char_p), ("bubble", C.c_char_p), ("addi_contig", C.c_char_p),
+                ("local_contig", C.c_char_p), ("input_prefix", C.c_char_p), ("output_prefix", C.c_char_p),
+                ("need_mercy", C.c_int32), ("mem_flag", C.c_int32)]
+
+
+# every symbol include/mhb.h declares (tests/test_abi.py checks the header against this list)
+SYMBOLS = [
+    "mhb_last_error", "mhb_version", "mhb_device_count", "mhb_count_record_words", "mhb_words_per_edge",
+    "mhb_s2s_record_words", "mhb_count_sort_bytes", "mhb_s2s_sort_bytes", "mhb_sort_workspace_bytes",
+    "mhb_count_extract", "mhb_sort_records", "mhb_count_solid_scratch_bytes", "mhb_count_solid", "mhb_tipset_bytes",
+    "mhb_tipset_build", "mhb_count_mark_mercy", "mhb_count_tip_edges", "mhb_s2s_extract",
+    "mhb_s2s_emit_scratch_bytes", "mhb_s2s_emit", "mhb_set_device", "mhb_count_host", "mhb_s2s_host", "mhb_free",
+    "mhb_release", "mhb_count_run", "mhb_seq2sdbg_run", "mhb_selftest_count_record", "mhb_selftest_s2s_record",
+]
+
+
+def load():
+    """Load libmhb.so; raises MhbError if it has not been built (python __graft_entry__.py / make)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MhbError(f"{LIB_PATH} is missing: build it with `make -C megahit_b200/csrc` "
+                       "(there is no CPU fallback for the CUDA path)")
+    L = C.CDLL(LIB_PATH)
+    L.mhb_last_error.restype = C.c_char_p
+    L.mhb_version.restype = C.c_char_p
+    for f in ("mhb_count_record_words", "mhb_words_per_edge", "mhb_s2s_record_words", "mhb_count_sort_bytes",
+              "mhb_s2s_sort_bytes"):
+        getattr(L, f).restype = C.c_uint32
+    for f in ("mhb_sort_workspace_bytes", "mhb_count_solid_scratch_bytes", "mhb_tipset_bytes",
+              "mhb_s2s_emit_scratch_bytes"):
+        getattr(L, f).restype = C.c_size_t
+    L.mhb_sort_workspace_bytes.argtypes = [C.c_uint64, C.c_uint32]
+    L.mhb_count_solid_scratch_bytes.argtypes = [C.c_uint64]
+    L.mhb_tipset_bytes.argtypes = [C.c_uint64, C.c_uint32]
+    L.mhb_s2s_emit_scratch_bytes.argtypes = [C.c_uint64]
+    L.mhb_count_extract.argtypes = [C.c_void_p, C.POINTER(DevReads), C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
+                                    C.c_int]
+    L.mhb_sort_records.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32,
+                                   C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]
+    L.mhb_count_solid.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p,
+                                  C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.mhb_tipset_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_size_t,
+                                   C.c_uint64]
+    L.mhb_count_mark_mercy.argtypes = [C.c_void_p, C.POINTER(DevReads), C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p,
+                                       C.c_void_p]
+    L.mhb_count_tip_edges.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.mhb_s2s_extract.argtypes = [C.c_void_p, C.POINTER(DevSeqs), C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
+                                  C.c_int]
+    L.mhb_s2s_emit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_size_t]
+    L.mhb_count_host.argtypes = [C.POINTER(CountArgs), C.POINTER(CountResult)]
+    L.mhb_s2s_host.argtypes = [C.POINTER(S2sArgs), C.POINTER(S2sResult)]
+    L.mhb_free.argtypes = [C.c_void_p]
+    L.mhb_count_run.argtypes = [C.POINTER(CountOpts)]
+    L.mhb_seq2sdbg_run.argtypes = [C.POINTER(Seq2SdbgOpts)]
+    L.mhb_selftest_count_record.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                            C.POINTER(C.c_uint32)]
+    L.mhb_selftest_s2s_record.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                          C.c_uint32, C.c_void_p]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise MhbError(f"libmhb error {rc}: {load().mhb_last_error().decode()}")
+
+
+def device_count() -> int:
+    return load().mhb_device_count()
+
+
+# ------------------------------------------------------------------------------------------------
+# geometry
+# ------------------------------------------------------------------------------------------------
+def count_record_words(k: int) -> int:
+    return load().mhb_count_record_words(C.c_uint32(k))
+
+
+def words_per_edge(k: int) -> int:
+    return load().mhb_words_per_edge(C.c_uint32(k))
+
+
+def s2s_record_words(k: int) -> int:
+    return load().mhb_s2s_record_words(C.c_uint32(k))
+
+
+def count_sort_bytes(k: int) -> list[int]:
+    buf = (C.c_uint8 * 80)()
+    n = load().mhb_count_sort_bytes(C.c_uint32(k), buf)
+    return list(buf[:n])
+
+
+def s2s_sort_bytes(k: int) -> list[int]:
+    buf = (C.c_uint8 * 80)()
+    n = load().mhb_s2s_sort_bytes(C.c_uint32(k), buf)
+    return list(buf[:n])
+
+
+# ------------------------------------------------------------------------------------------------
+# host level
+# ------------------------------------------------------------------------------------------------
+def count_host(bin_words: np.ndarray, n_reads: int, k: int, m: int, want_mercy: bool = True) -> dict:
+    """KmerCounter::Run on host buffers.  bin_words: the `.bin` image as uint32 (numpy, or a pinned
+    torch tensor's numpy view)."""
+    L = load()
+    bin_words = np.ascontiguousarray(bin_words, dtype=np.uint32).reshape(-1)
+    a = CountArgs(k, m, bin_words.ctypes.data if len(bin_words) else None, len(bin_words), n_reads, int(want_mercy))
+    r = CountResult()
+    _check(L.mhb_count_host(C.byref(a), C.byref(r)))
+    wpe = r.words_per_edge
+    out = {
+        "n_edge_records": r.n_edge_records, "n_solid": r.n_solid, "words_per_edge": wpe,
+        "edges": np.ctypeslib.as_array(r.edges, (max(r.n_solid, 1) * wpe,))[: r.n_solid * wpe].reshape(-1, wpe).copy(),
+        "cand_ids": (np.ctypeslib.as_array(r.cand_ids, (max(r.n_cand, 1),))[: r.n_cand].copy()
+                     if want_mercy else np.zeros(0, np.uint64)),
+        "n_has_tips": r.n_has_tips, "counting": np.array(r.counting, dtype=np.int64),
+        "ms": {k_: getattr(r, f"t_{k_}_ms") for k_ in ("h2d", "extract", "sort", "count", "mercy", "d2h", "total")},
+        "sort_pass_ms": list(r.sort_pass_ms[: r.n_sort_passes]),
+    }
+    L.mhb_free(r.edges)
+    if want_mercy:
+        L.mhb_free(r.cand_ids)
+    return out
+
+
+def s2s_host(words: np.ndarray, word_off: np.ndarray, length: np.ndarray, mult: np.ndarray, k: int) -> dict:
+    """SeqToSdbg::Run (after Initialize) on host buffers of package-orientation sequences."""
+    L = load()
+    words = np.ascontiguousarray(words, np.uint32)
+    if len(words) == 0:
+        words = np.zeros(1, np.uint32)
+    word_off = np.ascontiguousarray(word_off, np.uint64)
+    n = len(word_off) - 1
+    length = np.ascontiguousarray(length, np.uint32) if n else np.zeros(1, np.uint32)
+    mult = np.ascontiguousarray(mult, np.uint16) if n else np.zeros(1, np.uint16)
+    a = S2sArgs(k, words.ctypes.data, word_off.ctypes.data, length.ctypes.data, mult.ctypes.data, n)
+    r = S2sResult()
+    _check(L.mhb_s2s_host(C.byref(a), C.byref(r)))
+    table = np.array(r.bucket_table, np.uint64).reshape(NUM_BUCKETS, 4)
+    out = {
+        "n_records": r.n_records, "n_items": r.n_items, "n_tips": r.n_tips, "n_large_mul": r.n_large_mul,
+        "n_bytes": r.n_bytes, "words_per_tip_label": r.words_per_tip_label,
+        "bytes": bytes(np.ctypeslib.as_array(r.bytes, (max(r.n_bytes, 1),))[: r.n_bytes]),
+        "bucket_table": table, "w_count": np.array(r.w_count, np.uint64), "ones_in_last": r.ones_in_last,
+        "ms": {k_: getattr(r, f"t_{k_}_ms") for k_ in ("extract", "sort", "emit", "total")},
+    }
+    L.mhb_free(r.bytes)
+    return out
+
+
+def sdbg_stream_from_table(table: np.ndarray, data: bytes) -> bytes:
+    """Canonical SdBG stream (formats.canonical_sdbg) from the {offset, items, tips, large} table."""
+    chunks = []
+    wpt_unknown = None  # byte extents follow from the next non-empty bucket's offset
+    idx = np.nonzero(table[:, 1])[0]
+    ends = list(table[idx[1:], 0]) + [len(data)] if len(idx) else []
+    for b, end in zip(idx, ends):
+        chunks.append(np.array([b], "<u4").tobytes() + np.array([table[b, 1]], "<u8").tobytes()
+                      + data[int(table[b, 0]):int(end)])
+    del wpt_unknown
+    return b"".join(chunks)
+
+
+# ------------------------------------------------------------------------------------------------
+# file level (the sub-commands)
+# ------------------------------------------------------------------------------------------------
+def count_run(read_lib_file: str, output_prefix: str, k: int = 21, m: int = 2, host_mem: float = 1e9,
+              num_cpu_threads: int = 0, mem_flag: int = 1) -> None:
+    o = CountOpts(k, m, host_mem, num_cpu_threads, read_lib_file.encode(), output_prefix.encode(), mem_flag)
+    _check(load().mhb_count_run(C.byref(o)))
+
+
+def seq2sdbg_run(output_prefix: str, k: int, k_from: int = 0, input_prefix: str = "", contig: str = "",
+                 bubble: str = "", addi_contig: str = "", local_contig: str = "", need_mercy: bool = False,
+                 host_mem: float = 1e9, num_cpu_threads: int = 0, mem_flag: int = 1) -> None:
+    o = Seq2SdbgOpts(host_mem, k, k_from, num_cpu_threads, contig.encode(), bubble.encode(), addi_contig.encode(),
+                     local_contig.encode(), input_prefix.encode(), output_prefix.encode(), int(need_mercy), mem_flag)
+    _check(load().mhb_seq2sdbg_run(C.byref(o)))
+
+
+# ------------------------------------------------------------------------------------------------
+# self-test hooks (host, one record at a time)
+# ------------------------------------------------------------------------------------------------
+def selftest_count_record(read_words: np.ndarray, L_: int, k: int, q: int):
+    read_words = np.ascontiguousarray(read_words, np.uint32)
+    rec = np.zeros(count_record_words(k), np.uint32)
+    strand = C.c_uint32()
+    _check(load().mhb_selftest_count_record(read_words.ctypes.data, len(read_words), L_, k, q, rec.ctypes.data,
+                                            C.byref(strand)))
+    return rec, strand.value
+
+
+def selftest_s2s_record(seq_words: np.ndarray, L_: int, k: int, strand: int, offset: int, mult: int):
+    seq_words = np.ascontiguousarray(seq_words, np.uint32)
+    rec = np.zeros(s2s_record_words(k), np.uint32)
+    _check(load().mhb_selftest_s2s_record(seq_words.ctypes.data, len(seq_words), L_, k, strand, offset, mult,
+                                          rec.ctypes.data))
+    return rec

@@ -1,0 +1,125 @@
+"""CPU checks of the record builders the kernels run (mhb_kernels.cuh is __host__ __device__; the
+mhb_selftest_* hooks execute it on the host): single records against a per-base Python restatement of
+the reference, and a whole simulated `count` (selftest records -> numpy sort on the advertised sort
+bytes -> run-length) against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from megahit_b200 import formats as F
+from megahit_b200 import lib
+from oracle_pipeline import load_reads, oracle_count
+
+
+def pack(bases):
+    return F.pack_reads_fixed(np.asarray(bases, np.uint8)[None, :])[0][1:]
+
+
+def expect_count_record(orig, k, q):
+    """kmer_counter.cpp:158-252 on the REVERSED read; q is the file-orientation position."""
+    L, K1 = len(orig), k + 1
+    rv = orig[::-1]
+    p = L - K1 - q
+    fwd = list(rv[p:p + K1])
+    rc = [3 - b for b in fwd[::-1]]
+    strand = 1 if rc < fwd else 0
+    key = rc if strand else fwd
+    prev = rv[p - 1] if p > 0 else 4
+    nxt = rv[p + K1] if p + K1 < L else 4
+    if strand:
+        prev, nxt = (4 if nxt == 4 else 3 - nxt), (4 if prev == 4 else 3 - prev)
+    wr = (2 * K1 + 6 + 31) // 32
+    rec = np.zeros(wr, np.uint64)
+    for i, b in enumerate(key):
+        rec[i >> 4] |= np.uint64(int(b) << (30 - 2 * (i & 15)))
+    rec[wr - 1] |= np.uint64((int(prev) << 3) | int(nxt))
+    return rec.astype(np.uint32), strand
+
+
+def expect_s2s_record(seq, k, strand, offset, mult):
+    """seq_to_sdbg.cpp:630-700."""
+    L = len(seq)
+    nc = k - (1 if offset + k > L else 0)
+    counting = mult if (offset > 0 and offset + k <= L) else 0
+    if strand == 0:
+        prev = 4 if offset == 0 else seq[offset - 1]
+        chars = list(seq[offset:offset + nc])
+    else:
+        prev = 4 if offset == 0 else 3 - seq[L - 1 - offset + 1]
+        off2 = max(0, L - 1 - offset - (k - 1))
+        chars = [3 - b for b in seq[off2:off2 + nc][::-1]]
+    w = (2 * k + 20 + 31) // 32
+    rec = np.zeros(w, np.uint64)
+    for i, b in enumerate(chars):
+        rec[i >> 4] |= np.uint64(int(b) << (30 - 2 * (i & 15)))
+    rec[w - 1] |= np.uint64((int(nc == k) << 19) | (int(prev) << 16) | max(0, 65535 - counting))
+    return rec.astype(np.uint32)
+
+
+@pytest.mark.parametrize("k", [9, 14, 15, 16, 21, 27, 28, 29, 31, 32, 47, 63, 64, 99, 141, 255])
+def test_count_record_builder(k):
+    rng = np.random.default_rng(k)
+    for _ in range(40):
+        L = int(rng.integers(k + 1, k + 40))
+        orig = rng.integers(0, 4, L).astype(np.uint8)
+        if rng.random() < 0.3:  # palindromic / low-complexity stress
+            orig[:] = rng.integers(0, 4)
+        words = pack(orig)
+        for q in {0, L - k - 1, int(rng.integers(0, L - k))}:
+            got, strand = lib.selftest_count_record(words, L, k, q)
+            exp, estrand = expect_count_record(orig, k, q)
+            assert strand == estrand and (got == exp).all(), (k, L, q)
+
+
+@pytest.mark.parametrize("k", [9, 15, 16, 21, 22, 27, 29, 31, 32, 39, 59, 79, 99, 119, 141, 255])
+def test_s2s_record_builder(k):
+    rng = np.random.default_rng(1000 + k)
+    for _ in range(30):
+        L = int(rng.integers(k + 1, k + 30))
+        seq = rng.integers(0, 4, L).astype(np.uint8)
+        words = pack(seq)
+        mult = int(rng.integers(0, 65536))
+        for strand in (0, 1):
+            for offset in {0, 1, L - k, L - k + 1, int(rng.integers(0, L - k + 2))}:
+                got = lib.selftest_s2s_record(words, L, k, strand, offset, mult)
+                exp = expect_s2s_record(seq, k, strand, offset, mult)
+                assert (got == exp).all(), (k, L, strand, offset)
+
+
+@pytest.mark.parametrize("name,k,m", [("toy_k21", 21, 2), ("tandem_k27", 28, 2), ("synvar_k31_m1", 31, 1)])
+def test_simulated_count_matches_oracle(name, k, m):
+    """records from the device code (run on the host) + a numpy LSD sort over mhb_count_sort_bytes +
+    run-length counting reproduce the oracle's solid edges: pins record layout and sort-byte selection."""
+    case = os.path.join(GOLDEN, name)
+    bin_words = np.fromfile(os.path.join(case, "reads.lib.bin"), np.uint32)
+    recs = []
+    pos = 0
+    while pos < len(bin_words):
+        L = int(bin_words[pos])
+        nw = (L + 15) // 16
+        w = bin_words[pos + 1:pos + 1 + nw]
+        for q in range(0, max(0, L - k)):
+            recs.append(lib.selftest_count_record(w, L, k, q)[0])
+        pos += 1 + nw
+    wr = lib.count_record_words(k)
+    recs = np.array(recs, np.uint32).reshape(-1, wr)
+    order = np.arange(len(recs))
+    for b in lib.count_sort_bytes(k):  # LSD: stable sort per byte, least significant first
+        digit = (recs[order, wr - 1 - (b >> 2)] >> (8 * (b & 3))) & 255
+        order = order[np.argsort(digit, kind="stable")]
+    srt = recs[order].copy()
+    srt[:, wr - 1] &= np.uint32(0xFFFFFFC0)
+    head = np.ones(len(srt), bool)
+    head[1:] = (srt[1:] != srt[:-1]).any(axis=1)
+    starts = np.nonzero(head)[0]
+    counts = np.diff(np.append(starts, len(srt)))
+    solid = counts >= m
+    wpe = lib.words_per_edge(k)
+    edges = np.zeros((int(solid.sum()), wpe), np.uint32)
+    kw = (2 * (k + 1) + 31) // 32
+    edges[:, :min(kw, wpe)] = srt[starts[solid]][:, :min(kw, wpe)]
+    edges[:, wpe - 1] |= np.minimum(counts[solid], 65535).astype(np.uint32)
+    c = oracle_count(load_reads(case), k, m)
+    assert (edges == c["edges"]).all() and len(edges) == c["n_solid"]
