@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- SdBG-construction hot path (count -> seq2sdbg) on synthetic 150 bp reads, k=27.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of reads: canonical (k+1)-mer edge extraction, LSD
+radix sort, solid-edge counting + mercy bookkeeping, then seq2sdbg item extraction, radix sort and SdBG
+emission from the device-resident solid edges.  `value` is whole-job edges/s with the read library already
+in HBM; `e2e` is the same metric through the host-buffer C ABI (mhb_count_host + mhb_s2s_host), H2D/D2H
+inside the timed region.  `--impl reference` times the unmodified reference's OpenMP path
+(oracle/_ref/megahit_core_ref count + seq2sdbg) on the host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sorted (k+1)-mer edges/sec at k=27 on 150bp reads"
+READ_LEN = 150
+GENOME_PER_READ = 5  # 5 Mb of genome per 1 M reads ~ 30x coverage
+ERR = 0.01
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the unmodified reference binary on the host cores, bounded sample
+# ------------------------------------------------------------------------------------------------
+def reference_run(n_reads: int, k: int, m: int, threads: int, seed: int = 1234):
+    from megahit_b200 import formats as F
+    from megahit_b200 import synth
+    ref = os.path.join(ROOT, "oracle", "_ref", "megahit_core_ref")
+    if not os.path.exists(ref):
+        return None
+    tmp = tempfile.mkdtemp(prefix="mhb_ref_")
+    try:
+        b = synth.synth_reads(n_reads, READ_LEN, GENOME_PER_READ * n_reads, ERR, seed=seed)
+        F.write_lib(os.path.join(tmp, "r"), b, n_reads, n_reads * READ_LEN, READ_LEN)
+        p = os.path.join(tmp, "k")
+        t0 = time.perf_counter()
+        subprocess.run([ref, "count", "-k", str(k), "-m", str(m), "--host_mem", "6e10", "--mem_flag", "1",
+                        "--output_prefix", p, "--num_cpu_threads", str(threads), "--read_lib_file",
+                        os.path.join(tmp, "r")], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        t1 = time.perf_counter()
+        subprocess.run([ref, "seq2sdbg", "--host_mem", "6e10", "--mem_flag", "1", "--output_prefix", p,
+                        "--num_cpu_threads", str(threads), "-k", str(k), "--kmer_from", "0", "--input_prefix", p,
+                        "--need_mercy"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        t2 = time.perf_counter()
+        return {"n_edges": n_reads * (READ_LEN - k), "t_count": t1 - t0, "t_s2s": t2 - t1}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = args.sample_reads
+    times = []
+    for i in range(args.warmup + args.steps):
+        r = reference_run(sample, args.k, args.m, threads, seed=1234 + i)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/megahit_core_ref was not built"}))
+            return
+        if i >= args.warmup:
+            times.append(r["t_count"] + r["t_s2s"])
+    n_edges = sample * (READ_LEN - args.k)
+    t = float(np.mean(times))
+    v = n_edges / t
+    desc = f"{sample} synthetic 150 bp reads/step, count+seq2sdbg --need_mercy, mem_flag 1"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "edges/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": f"reference megahit_core count+seq2sdbg k={args.k} m={args.m} on host cores", "sample": desc},
+        "cpu_baseline": {"value": v, "unit": "edges/s", "cores": threads, "kind": "reference", "sample": desc},
+        "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from megahit_b200 import dev, lib, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libmhb has no CPU path")
+    torch.cuda.set_device(local)
+    lib.load().mhb_set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    k, m, n_reads, L = args.k, args.m, args.reads, READ_LEN
+    n_edges = n_reads * (L - k)
+    bin2d = synth.synth_reads_torch(n_reads, L, GENOME_PER_READ * n_reads, ERR, seed=1 + rank, device=device)
+    bin_dev = torch.cat([bin2d.reshape(-1), torch.zeros(8, dtype=torch.int32, device=device)])
+    bin_words = n_reads * bin2d.shape[1]
+    del bin2d
+
+    if world > 1:
+        from megahit_b200 import multigpu
+        return multigpu.bench(args, bin_dev, bin_words, rank, world, device, METRIC)
+
+    plan = dev.CountPlan(n_reads, L, k, m, device, want_mercy=True)
+    n_solid = plan.run(bin_dev)  # sizes the SdBG stage (also the first warm-up)
+    s2s = dev.S2sPlan(int(n_solid * 1.05) + 1024, k + 1, k, device)
+
+    def step(timed=False):
+        ns = plan.run(bin_dev, timed=timed)
+        s2s.run(plan.edges, None, ns, plan.WE)
+        return ns
+
+    for _ in range(max(0, args.warmup - 1)):
+        step()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    clocks.start()
+    plan.events.clear()
+    sort_ms = {"count": [], "s2s": []}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step(timed=True)
+        # per-pass device times of this step's two sorts (events recorded inside the timed region)
+        sort_ms["s2s"].append(lib.sort_pass_ms(0)[0])
+        sort_ms["count"].append(lib.sort_pass_ms(1)[0])
+    e1.record()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms_per_step = e0.elapsed_time(e1) / args.steps
+    value = n_edges / (ms_per_step * 1e-3)
+
+    # stage split of the count stage
+    ev = plan.events
+    stage = {}
+    for a, b in (("t0", "extract"), ("extract", "sort"), ("sort", "count"), ("count", "mercy")):
+        stage[b] = float(np.mean([x.elapsed_time(y) for x, y in zip(ev[a], ev[b])]))
+
+    # roofline of the dominant kernel: the radix pass over the count records (2*N*S algorithmic bytes per launch)
+    peak, peak_src = peaks()
+    S = plan.WR * 4
+    cpass = np.array(sort_ms["count"])  # steps x passes
+    avg_pass_ms = float(cpass.mean())
+    achieved = 2.0 * n_edges * S / (avg_pass_ms * 1e-3) / 1e9
+    spass = np.array(sort_ms["s2s"])
+    n_items = s2s.n_items
+    s2s_achieved = 2.0 * n_items * s2s.W * 4 / (float(spass.mean()) * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": f"k_radix_pass<{plan.WR}> (count records, {S} B)", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": 2 * n_edges * S, "avg_launch_ms": avg_pass_ms,
+        "per_pass_ms": [float(x) for x in cpass.mean(axis=0)],
+        "per_pass_frac": [float(2.0 * n_edges * S / (x * 1e-3) / 1e9 / peak) for x in cpass.mean(axis=0)],
+        "s2s_pass": {"kernel": f"k_radix_pass<{s2s.W}>", "records": int(n_items), "avg_launch_ms": float(spass.mean()),
+                     "achieved": s2s_achieved, "frac": s2s_achieved / peak},
+    }
+
+    # kernels launched per step (ours only): extract, 7x(scan256+radix), mark/totals/scan/emit, tips/tipset/mercy,
+    # s2s extract, 10x(scan256+radix), size, 4 scans, write, finalize
+    launches = 1 + 2 * len(plan.sort_bytes) + 4 + 3 + 1 + 2 * len(s2s.sort_bytes) + 1 + 4 + 1 + 1
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    host_bin = torch.empty(bin_words, dtype=torch.int32).pin_memory()
+    host_bin.copy_(bin_dev[:bin_words])
+    hb = host_bin.numpy().view(np.uint32)
+    del plan, s2s
+    torch.cuda.empty_cache()
+    e2e_t, h2d, d2h = [], 0, 0
+    wpe = lib.words_per_edge(k)
+    ns = int(n_solid)
+    for i in range((1 + args.e2e_steps) if args.e2e_steps > 0 else 0):
+        t0 = time.perf_counter()
+        g = lib.count_host(hb, n_reads, k, m, want_mercy=True)
+        edges = g["edges"]
+        ns = len(edges)
+        words = np.ascontiguousarray(edges[:, :2])
+        mult = (edges[:, wpe - 1] & 0xFFFF).astype(np.uint16)
+        word_off = np.arange(ns + 1, dtype=np.uint64) * np.uint64(2)
+        lens = np.full(ns, k + 1, np.uint32)
+        gs = lib.s2s_host(words, word_off, lens, mult, k)
+        t1 = time.perf_counter()
+        if i > 0:
+            e2e_t.append(t1 - t0)
+        h2d = hb.nbytes + words.nbytes + word_off.nbytes + lens.nbytes + mult.nbytes + 8 * (ns + 1)
+        d2h = edges.nbytes + 65536 * 8 + 8 * n_reads + gs["n_bytes"] + 65536 * 32
+    lib.load().mhb_release()
+    e2e_v = n_edges / float(np.mean(e2e_t)) if e2e_t else None
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        r = reference_run(args.sample_reads, k, m, threads)
+        if r:
+            cpu = {"value": r["n_edges"] / (r["t_count"] + r["t_s2s"]), "unit": "edges/s", "cores": threads,
+                   "kind": "reference",
+                   "sample": f"{args.sample_reads} synthetic 150 bp reads, megahit_core count+seq2sdbg --need_mercy "
+                             f"(count {r['t_count']:.2f} s, seq2sdbg {r['t_s2s']:.2f} s)"}
+
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic",
+        "config": {"workload": f"synthetic {n_reads}x{L}bp reads (30x, 1% subst.), k={k}, m={m}, 1xB200 single-GPU "
+                               "sdbg_build: count (extract+radix+solid count+mercy marks) + seq2sdbg (extract+radix+emit) "
+                               "on the solid edges; mercy-edge generation (host) not in the device step",
+                   "n_edge_records": n_edges, "n_solid_edges": int(ns), "n_sdbg_sort_items": int(n_items),
+                   "l2_note": "inputs (>= 4.9 GB per kernel) exceed the 126 MB L2, no explicit flush needed"},
+        "stage_ms": {**stage, "count_total": float(sum(stage.values())),
+                     "s2s_total": ms_per_step - float(sum(stage.values()))},
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+        "e2e": {"value": e2e_v, "unit": "edges/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": float(np.mean(e2e_t)) * 1e3 if e2e_t else None, "api": "mhb_count_host + mhb_s2s_host (host buffers)"},
+        "gpu_launches": launches,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU")
+    ap.add_argument("--k", type=int, default=27)
+    ap.add_argument("--m", type=int, default=2)
+    ap.add_argument("--sample-reads", type=int, default=1_000_000, help="bounded CPU sample (reference arm / cpu_baseline)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        # exactly K timed + W warm-up steps; the per-step sample is sized so the whole run stays within minutes
+        # (~8 s per 1 M reads on 8 host cores)
+        budget_s = 160.0
+        per_step = budget_s / max(1, args.steps + args.warmup)
+        args.sample_reads = int(max(100_000, min(args.sample_reads, 1_000_000 * per_step / 8.0)))
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

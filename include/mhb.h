@@ -100,6 +100,11 @@ int mhb_sort_records(void *stream, uint32_t *a, uint32_t *b, uint64_t n, uint32_
                      const uint8_t *bytes, uint32_t n_bytes, const uint64_t *first_hist, void *ws,
                      size_t ws_bytes, int *result_in_b);
 
+/* Per-pass device times (ms, CUDA events on `stream`) of one of the last four sorts issued by this process:
+ * back = 0 is the most recent.  Synchronises on that sort's last event only. */
+int mhb_sort_pass_ms(int back, double *pass_ms, uint32_t max_passes, uint32_t *n_passes, uint64_t *n_records,
+                     uint32_t *words);
+
 /* A5/A6: run-length count over sorted records, solid filter, edge packing
  * (kmer_counter.cpp:254-381, PackEdge :32-52).
  *   edges_out   capacity_edges * mhb_words_per_edge(k) words, ascending solid edges
@@ -126,7 +131,9 @@ int mhb_count_mark_mercy(void *stream, const mhb_dev_reads *reads, uint32_t k, c
 int mhb_count_tip_edges(void *stream, const uint8_t *aux, uint64_t n_solid, uint64_t *n_tip_host);
 
 /* Sequences in package orientation for seq2sdbg: word-aligned 2-bit packing.
- * fixed_len > 0: sequence s starts at word s*ceil(fixed_len/16); seq_off/len/item_off may be NULL.
+ * fixed_len > 0: sequence s starts at word s*fixed_stride (fixed_stride = 0 means ceil(fixed_len/16));
+ * word_off/len/item_off may be NULL.  With mult == NULL the multiplicity of sequence s is the low 16 bits
+ * of the last word of its stride, i.e. `words` may be the `.edges` records themselves (edge_reader.h:49).
  * Otherwise word_off[n+1], len[n], item_off[n+1] (exclusive prefix of 2*(len-k+2) for len >= k+1, else 0). */
 typedef struct {
   const uint32_t *words;
@@ -137,6 +144,7 @@ typedef struct {
   const uint32_t *len;
   const uint64_t *item_off;
   const uint16_t *mult; /* per sequence */
+  uint32_t fixed_stride;
 } mhb_dev_seqs;
 
 /* A8/A9 (seq_to_sdbg.cpp:530-700): all sort items of both strands. */

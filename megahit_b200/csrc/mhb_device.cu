@@ -172,6 +172,20 @@ static int launch_radix_pass(cudaStream_t st, const u32 *in, u32 *out, u64 n, in
   return MHB_OK;
 }
 
+// Per-pass timing: every sort records one event before and after each pass into a small ring, so a
+// caller can ask afterwards (mhb_sort_pass_ms) how long each pass of a recent sort took without putting a
+// synchronisation inside its timed region.
+namespace {
+struct SortTrace {
+  cudaEvent_t ev[74];
+  bool created = false;
+  uint32_t n_passes = 0, words = 0;
+  uint64_t n = 0;
+};
+SortTrace g_trace[4];
+uint64_t g_trace_seq = 0;
+}  // namespace
+
 int mhb_sort_records_impl(void *stream, uint32_t *a, uint32_t *b, uint64_t n, uint32_t words, const uint8_t *bytes,
                           uint32_t n_bytes, const uint64_t *first_hist, void *ws, size_t ws_bytes, int *result_in_b,
                           double *pass_ms_host) {
@@ -182,8 +196,8 @@ int mhb_sort_records_impl(void *stream, uint32_t *a, uint32_t *b, uint64_t n, ui
   if (ws_bytes < mhb_sort_workspace_bytes(n, words)) return mhb_set_error(MHB_ERR_ARG, "sort workspace too small");
   if (n >= (1ull << 53)) return mhb_set_error(MHB_ERR_ARG, "too many records");
   cudaStream_t st = (cudaStream_t)stream;
-  u64 *hist = (u64 *)ws;                   // [n_bytes+1][256]
-  u64 *bin_base = hist + (72 + 1) * 256;   // [256]
+  u64 *hist = (u64 *)ws;                        // [n_bytes+1][256]
+  u64 *bin_base = hist + (72 + 1) * 256;        // [256]
   u32 *tile_counter = (u32 *)(bin_base + 256);  // [128]
   u64 *lookback = (u64 *)((char *)ws + kSortHeadBytes);
   CK(cudaMemsetAsync(ws, 0, mhb_sort_workspace_bytes(n, words), st));
@@ -196,11 +210,15 @@ int mhb_sort_records_impl(void *stream, uint32_t *a, uint32_t *b, uint64_t n, ui
 #undef M
     CK_LAUNCH();
   }
-  cudaEvent_t ev[74];
-  if (pass_ms_host) {
-    for (u32 p = 0; p <= n_bytes; ++p) CK(cudaEventCreate(&ev[p]));
-    CK(cudaEventRecord(ev[0], st));
+  SortTrace &tr = g_trace[g_trace_seq++ & 3];
+  if (!tr.created) {
+    for (int i = 0; i < 74; ++i) CK(cudaEventCreate(&tr.ev[i]));
+    tr.created = true;
   }
+  tr.n_passes = n_bytes;
+  tr.words = words;
+  tr.n = n;
+  CK(cudaEventRecord(tr.ev[0], st));
   u32 *in = a, *out = b;
   for (u32 p = 0; p < n_bytes; ++p) {
     k_hist_scan256<<<1, 256, 0, st>>>(hist + (u64)p * 256, bin_base);
@@ -213,21 +231,36 @@ int mhb_sort_records_impl(void *stream, uint32_t *a, uint32_t *b, uint64_t n, ui
     MHB_FOR_WR(M)
 #undef M
     if (rc) return rc;
-    if (pass_ms_host) CK(cudaEventRecord(ev[p + 1], st));
+    CK(cudaEventRecord(tr.ev[p + 1], st));
     u32 *t = in;
     in = out;
     out = t;
   }
   *result_in_b = (in == b) ? 1 : 0;
   if (pass_ms_host) {
-    CK(cudaStreamSynchronize(st));
+    CK(cudaEventSynchronize(tr.ev[n_bytes]));
     for (u32 p = 0; p < n_bytes; ++p) {
       float ms = 0;
-      CK(cudaEventElapsedTime(&ms, ev[p], ev[p + 1]));
+      CK(cudaEventElapsedTime(&ms, tr.ev[p], tr.ev[p + 1]));
       pass_ms_host[p] = ms;
     }
-    for (u32 p = 0; p <= n_bytes; ++p) cudaEventDestroy(ev[p]);
   }
+  return MHB_OK;
+}
+
+extern "C" int mhb_sort_pass_ms(int back, double *pass_ms, uint32_t max_passes, uint32_t *n_passes, uint64_t *n_records,
+                                uint32_t *words) {
+  if (back < 0 || back > 3 || (uint64_t)back >= g_trace_seq) return mhb_set_error(MHB_ERR_ARG, "no such sort in the trace ring");
+  SortTrace &tr = g_trace[(g_trace_seq - 1 - back) & 3];
+  CK(cudaEventSynchronize(tr.ev[tr.n_passes]));
+  for (u32 p = 0; p < tr.n_passes && p < max_passes; ++p) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, tr.ev[p], tr.ev[p + 1]));
+    pass_ms[p] = ms;
+  }
+  if (n_passes) *n_passes = tr.n_passes;
+  if (n_records) *n_records = tr.n;
+  if (words) *words = tr.words;
   return MHB_OK;
 }
 
@@ -356,6 +389,7 @@ static SeqsView make_seqs_view(const mhb_dev_seqs *s) {
   v.len = s->len;
   v.item_off = s->item_off;
   v.mult = s->mult;
+  v.fixed_stride = s->fixed_stride;
   return v;
 }
 
@@ -363,7 +397,8 @@ extern "C" int mhb_s2s_extract(void *stream, const mhb_dev_seqs *seqs, uint32_t 
                                uint64_t n_items, uint64_t *hist256, int hist_byte) {
   if (!seqs || k < 9 || k > MHB_MAX_K) return mhb_set_error(MHB_ERR_ARG, "kmer size must be >= 9 and <= 255");
   if (n_items == 0) return MHB_OK;
-  if (!seqs->mult) return mhb_set_error(MHB_ERR_ARG, "seqs->mult is NULL");
+  if (!seqs->mult && !(seqs->fixed_len && seqs->fixed_stride))
+    return mhb_set_error(MHB_ERR_ARG, "seqs->mult is NULL (only allowed for fixed-stride edge records)");
   if (!seqs->fixed_len && (!seqs->word_off || !seqs->len || !seqs->item_off))
     return mhb_set_error(MHB_ERR_ARG, "variable-length sequences need word_off, len and item_off");
   if (seqs->fixed_len && seqs->fixed_len < k + 1) return mhb_set_error(MHB_ERR_ARG, "fixed_len < k+1");

@@ -367,6 +367,7 @@ extern "C" int mhb_s2s_host(const mhb_s2s_args *args, mhb_s2s_result *res) {
   seqs.len = d_len;
   seqs.item_off = d_item_off;
   seqs.mult = d_mult;
+  seqs.fixed_stride = 0;
 
   t.start();
   CKR(mhb_s2s_extract(st, &seqs, k, d_a, n_items, d_hist0, sort_bytes[0]));

@@ -15,6 +15,7 @@ struct SeqsView {
   const u32 *len;
   const u64 *item_off;
   const uint16_t *mult;
+  u32 fixed_stride;
 };
 
 // S-extract (A8/A9; seq_to_sdbg.cpp:530-700): thread t builds sort item t.
@@ -35,7 +36,7 @@ __global__ void __launch_bounds__(256)
       seq = t / ips;
       rem = t - seq * ips;
       nwords = div_ceil(L, 16);
-      s = sv.words + seq * nwords;
+      s = sv.words + seq * (sv.fixed_stride ? sv.fixed_stride : nwords);
     } else {
       u64 lo = 0, hi = sv.n_seqs;  // last seq with item_off[seq] <= t
       while (hi - lo > 1) {
@@ -52,7 +53,8 @@ __global__ void __launch_bounds__(256)
     const u32 strand = rem >= per_strand ? 1u : 0u;
     const u32 offset = (u32)(rem - (u64)strand * per_strand);
     u32 rec[W];
-    make_s2s_record<W>(s, nwords, L, k, strand, offset, sv.mult[seq], rec);
+    const u32 mult = sv.mult ? (u32)sv.mult[seq] : (s[sv.fixed_stride - 1] & 0xFFFFu);
+    make_s2s_record<W>(s, nwords, L, k, strand, offset, mult, rec);
     st_rec<W>(records, t, rec);
     if (hist) atomicAdd(&s_hist[rec_byte<W>(rec, hist_byte)], 1u);
   }

@@ -147,8 +147,13 @@ class S2sPlan:
         self.totals = torch.zeros(16, dtype=torch.int64, device=device)
         self.hist0 = torch.zeros(256, dtype=torch.int64, device=device)
 
-    def run(self, words: torch.Tensor, mult: torch.Tensor):
-        seqs = lib.DevSeqs(words.data_ptr(), words.numel(), self.n_seqs, self.seq_len, None, None, None, mult.data_ptr())
+    def run(self, words: torch.Tensor, mult: torch.Tensor | None = None, n_seqs: int | None = None, stride: int = 0):
+        """words: packed sequences; with mult=None they are `.edges` records of `stride` words each."""
+        n_seqs = self.n_seqs if n_seqs is None else n_seqs
+        assert n_seqs <= self.n_seqs
+        self.n_items = n_seqs * 2 * (self.seq_len - self.k + 2)
+        seqs = lib.DevSeqs(words.data_ptr(), words.numel(), n_seqs, self.seq_len, None, None, None,
+                           mult.data_ptr() if mult is not None else None, stride)
         self.hist0.zero_()
         lib._check(self.L.mhb_s2s_extract(_stream(), C.byref(seqs), self.k, _ptr(self.a), self.n_items, _ptr(self.hist0),
                                           self.sort_bytes[0]))

@@ -35,7 +35,8 @@ class DevReads(C.Structure):
 
 class DevSeqs(C.Structure):
     _fields_ = [("words", C.c_void_p), ("n_words", C.c_uint64), ("n_seqs", C.c_uint64), ("fixed_len", C.c_uint32),
-                ("word_off", C.c_void_p), ("len", C.c_void_p), ("item_off", C.c_void_p), ("mult", C.c_void_p)]
+                ("word_off", C.c_void_p), ("len", C.c_void_p), ("item_off", C.c_void_p), ("mult", C.c_void_p),
+                ("fixed_stride", C.c_uint32)]
 
 
 class CountArgs(C.Structure):
@@ -82,7 +83,7 @@ class Seq2SdbgOpts(C.Structure):
 SYMBOLS = [
     "mhb_last_error", "mhb_version", "mhb_device_count", "mhb_count_record_words", "mhb_words_per_edge",
     "mhb_s2s_record_words", "mhb_count_sort_bytes", "mhb_s2s_sort_bytes", "mhb_sort_workspace_bytes",
-    "mhb_count_extract", "mhb_sort_records", "mhb_count_solid_scratch_bytes", "mhb_count_solid", "mhb_tipset_bytes",
+    "mhb_count_extract", "mhb_sort_records", "mhb_sort_pass_ms", "mhb_count_solid_scratch_bytes", "mhb_count_solid", "mhb_tipset_bytes",
     "mhb_tipset_build", "mhb_count_mark_mercy", "mhb_count_tip_edges", "mhb_s2s_extract",
     "mhb_s2s_emit_scratch_bytes", "mhb_s2s_emit", "mhb_set_device", "mhb_count_host", "mhb_s2s_host", "mhb_free",
     "mhb_release", "mhb_count_run", "mhb_seq2sdbg_run", "mhb_selftest_count_record", "mhb_selftest_s2s_record",
@@ -150,6 +151,14 @@ def device_count() -> int:
 # ------------------------------------------------------------------------------------------------
 # geometry
 # ------------------------------------------------------------------------------------------------
+def sort_pass_ms(back: int = 0):
+    """(per-pass ms list, n_records, words) of a recent sort; back=0 is the latest."""
+    buf = (C.c_double * 80)()
+    npass, nrec, words = C.c_uint32(), C.c_uint64(), C.c_uint32()
+    _check(load().mhb_sort_pass_ms(back, buf, 80, C.byref(npass), C.byref(nrec), C.byref(words)))
+    return list(buf[: npass.value]), nrec.value, words.value
+
+
 def count_record_words(k: int) -> int:
     return load().mhb_count_record_words(C.c_uint32(k))
 
