@@ -126,7 +126,7 @@ size_t mhb_tipset_bytes(uint64_t n_tip_edges, uint32_t k);
 int mhb_tipset_build(void *stream, const uint32_t *edges, const uint8_t *aux, uint64_t n_solid, uint32_t k,
                      void *tipset, size_t tipset_bytes, uint64_t n_tip_edges);
 int mhb_count_mark_mercy(void *stream, const mhb_dev_reads *reads, uint32_t k, const void *tipset,
-                         size_t tipset_bytes, uint32_t *first_0_out, uint32_t *last_0_in);
+                         size_t tipset_bytes, uint64_t n_tip_edges, uint32_t *first_0_out, uint32_t *last_0_in);
 /* number of solid edges with aux != 0 (device reduction; result to host) */
 int mhb_count_tip_edges(void *stream, const uint8_t *aux, uint64_t n_solid, uint64_t *n_tip_host);
 

@@ -273,26 +273,36 @@ __global__ void __launch_bounds__(kCompactThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
-// tip set: open-addressing hash set of the solid edges that lack an incoming or outgoing solid
-// neighbour (aux != 0).  Layout: u64 capacity (power of two), u64 pad, then capacity entries of
-// (1 + W) words: flags (0 = empty) followed by the (k+1)-mer.
+// tip set: the solid edges that lack an incoming or outgoing solid neighbour (aux != 0), as
+//   u64 capacity (power of two), u64 filter_words (power of two),
+//   u32 filter[filter_words]           one-bit-per-hash prefilter (~32 bits per tip edge, L2 resident)
+//   u32 table[capacity][1 + W]         open addressing: flags (0 = empty) followed by the (k+1)-mer
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline u64 tipset_capacity(u64 n_tip) {
   u64 c = 1024;
   while (c < 2 * n_tip) c <<= 1;
   return c;
 }
+__host__ __device__ inline u64 tipset_filter_words(u64 n_tip) {
+  u64 c = 1024;
+  while (c < n_tip) c <<= 1;
+  return c;
+}
 
 template <int W>
-__device__ __forceinline__ u64 hash_key(const u32 (&key)[W]) {
-  u64 h = 0x9E3779B97F4A7C15ull;
+__device__ __forceinline__ u32 hash_key(const u32 (&key)[W]) {
+  u32 h = 0x9E3779B1u;
 #pragma unroll
   for (int j = 0; j < W; ++j) {
-    h ^= key[j];
-    h *= 0xBF58476D1CE4E5B9ull;
-    h ^= h >> 29;
+    h = (h ^ key[j]) * 0x85EBCA77u;
+    h ^= h >> 15;
   }
-  return h;
+  h *= 0x2C1B3C6Du;
+  return h ^ (h >> 13);
+}
+__device__ __forceinline__ u32 hash2(u32 h) {  // second, independent-ish hash for the bit filter
+  h *= 0xC2B2AE3Du;
+  return h ^ (h >> 16);
 }
 
 __global__ void k_count_tips(const uint8_t *aux, u64 n, unsigned long long *out) {
@@ -305,7 +315,7 @@ __global__ void k_count_tips(const uint8_t *aux, u64 n, unsigned long long *out)
 
 template <int W>
 __global__ void k_tipset_insert(const u32 *__restrict__ edges, const uint8_t *__restrict__ aux, u64 n, u32 k,
-                                u32 *table, u64 cap) {
+                                u32 *filter, u64 filter_words, u32 *table, u64 cap) {
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || aux[i] == 0) return;
   const u32 WE = words_per_edge(k);
@@ -315,7 +325,10 @@ __global__ void k_tipset_insert(const u32 *__restrict__ edges, const uint8_t *__
     const u32 keep = 2 * (k + 1) - 32 * j;
     key[j] = edges[i * WE + j] & top_mask(keep > 32 ? 32 : keep);
   }
-  u64 slot = hash_key<W>(key) & (cap - 1);
+  const u32 h = hash_key<W>(key);
+  const u32 fb = hash2(h) & (u32)(filter_words * 32 - 1);
+  atomicOr(&filter[fb >> 5], 1u << (fb & 31));
+  u64 slot = h & (cap - 1);
   while (true) {
     u32 *e = table + slot * (W + 1);
     if (atomicCAS(e, 0u, (u32)aux[i]) == 0u) {
@@ -330,26 +343,43 @@ __global__ void k_tipset_insert(const u32 *__restrict__ edges, const uint8_t *__
 // K-mercy (kmer_counter.cpp:307-367): per read min/max over the occurrences of tip edges.
 template <int W, int WR>
 __global__ void __launch_bounds__(kExtractThreads)
-    k_mark_mercy(ReadsView rv, u32 k, const u32 *__restrict__ table, u64 cap, u32 *first_0_out, u32 *last_0_in) {
+    k_mark_mercy(ReadsView rv, u32 k, const u32 *__restrict__ filter, u64 filter_words, const u32 *__restrict__ table,
+                 u64 cap, u32 *first_0_out, u32 *last_0_in) {
   const u32 lane = lane_id();
   const u32 K1 = k + 1;
+  const u32 fmask = (u32)(filter_words * 32 - 1);
   for_each_read(rv, [&](u64 r, const u32 *s, u32 nwords, u32 L) {
     u32 first = 0xFFFFFFFFu;
     long long last = -1;
     if (L >= K1) {
       const u32 n_e = L - k;
-      for (u32 q0 = 0; q0 < n_e; q0 += 32) {
-        const u32 q = q0 + lane;
-        if (q < n_e) {
-          u32 rec[WR], strand;
-          make_count_record<W, WR>(s, nwords, L, k, q, rec, strand);
-          u32 key[W];
+      // two positions per lane per round so that both filter probes are in flight together
+      for (u32 q0 = 0; q0 < n_e; q0 += 64) {
+        u32 key[2][W], strand[2], fw[2], h[2];
+        bool live[2];
 #pragma unroll
-          for (int j = 0; j < W; ++j) {
-            const u32 keep = 2 * K1 - 32 * j;
-            key[j] = rec[j] & top_mask(keep > 32 ? 32 : keep);
+        for (int u = 0; u < 2; ++u) {
+          const u32 q = q0 + 32 * u + lane;
+          live[u] = q < n_e;
+          h[u] = 0;
+          fw[u] = 0;
+          strand[u] = 0;
+          if (live[u]) {
+            u32 rec[WR];
+            make_count_record<W, WR>(s, nwords, L, k, q, rec, strand[u]);
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+              const u32 keep = 2 * K1 - 32 * j;
+              key[u][j] = rec[j] & top_mask(keep > 32 ? 32 : keep);
+            }
+            h[u] = hash_key<W>(key[u]);
+            fw[u] = filter[(hash2(h[u]) & fmask) >> 5];
           }
-          u64 slot = hash_key<W>(key) & (cap - 1);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (!live[u] || !((fw[u] >> (hash2(h[u]) & 31)) & 1u)) continue;
+          u64 slot = h[u] & (cap - 1);
           u32 flags = 0;
           while (true) {
             const u32 *e = table + slot * (W + 1);
@@ -357,7 +387,7 @@ __global__ void __launch_bounds__(kExtractThreads)
             if (f == 0) break;
             bool eq = true;
 #pragma unroll
-            for (int j = 0; j < W; ++j) eq = eq && e[1 + j] == key[j];
+            for (int j = 0; j < W; ++j) eq = eq && e[1 + j] == key[u][j];
             if (eq) {
               flags = f;
               break;
@@ -365,13 +395,12 @@ __global__ void __launch_bounds__(kExtractThreads)
             slot = (slot + 1) & (cap - 1);
           }
           if (flags) {
-            const u32 off = L - K1 - q;  // offset in the reversed (package) read
-            const bool upd_last_in = (flags & 1u) && strand == 0;   // no in,  strand 0 -> last
-            const bool upd_first_in = (flags & 1u) && strand == 1;  // no in,  strand 1 -> first
-            const bool upd_first_out = (flags & 2u) && strand == 0; // no out, strand 0 -> first
-            const bool upd_last_out = (flags & 2u) && strand == 1;  // no out, strand 1 -> last
-            if (upd_last_in || upd_last_out) last = last > (long long)off ? last : (long long)off;
-            if (upd_first_in || upd_first_out) first = first < off + 1 ? first : off + 1;
+            const u32 off = L - K1 - (q0 + 32 * u + lane);  // offset in the reversed (package) read
+            const bool to_last = ((flags & 1u) && strand[u] == 0) || ((flags & 2u) && strand[u] == 1);
+            const bool to_first = ((flags & 1u) && strand[u] == 1) || ((flags & 2u) && strand[u] == 0);
+            // no in, strand 0 -> last; no in, strand 1 -> first; no out, strand 0 -> first; no out, strand 1 -> last
+            if (to_last) last = last > (long long)off ? last : (long long)off;
+            if (to_first) first = first < off + 1 ? first : off + 1;
           }
         }
       }
@@ -387,6 +416,495 @@ __global__ void __launch_bounds__(kExtractThreads)
       last_0_in[r] = last < 0 ? 0xFFFFFFFFu : (u32)last;
     }
   });
+}
+
+}  // namespace mhb
+
+namespace mhb {
+
+// ------------------------------------------------------------------------------------------------
+// K-count v2 (A5/A6): one pass, warp-cooperative.
+//
+// The sorted records are cut into chunks of CH records; warps claim chunks by ticket.  A warp OWNS every
+// run of equal edges whose first record lies in its chunk and follows such a run past the chunk end, so
+// no partial results cross warps.  Per 32-record slot the run structure comes from one ballot of the
+// head flags, and a run's multiplicity and its prev/next tallies (kmer_counter.cpp:279-305) are
+// popcounts of ballot masks restricted to the run's lanes - no per-record loop.  A run is finished (and
+// judged: solid / has_in / has_out) by the lane holding the NEXT run's head; a virtual head at index n
+// closes the last run.  Solid edges are packed (PackEdge, kmer_counter.cpp:32-52) into a per-warp
+// staging area in order; the warp then learns its global output offset by decoupled look-back over the
+// chunk totals and copies the staging area out with coalesced stores, so the edge list stays sorted.
+// ------------------------------------------------------------------------------------------------
+static constexpr int kCountWarps = 8;
+__host__ __device__ constexpr int count_chunk(int we) { return we <= 4 ? 256 : (we <= 8 ? 128 : 64); }
+
+template <int WR>
+__global__ void __launch_bounds__(kCountWarps * 32)
+    k_count_warp(const u32 *__restrict__ recs, u64 n, u32 k, int m, u32 n_chunks, u32 *ticket, u64 *lookback,
+                 u32 *__restrict__ edges, uint8_t *__restrict__ aux, u64 capacity, u64 *mul_hist, u64 *n_solid_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ u32 s_hist[kMulHistSmem];
+  const u32 W = count_key_words(k), WE = words_per_edge(k);
+  const int CH = count_chunk((int)WE);
+  const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+  u32 *stage = reinterpret_cast<u32 *>(smem_raw) + (size_t)warp * CH * WE;
+  uint8_t *stage_aux = smem_raw + (size_t)kCountWarps * CH * WE * 4 + (size_t)warp * CH;
+  for (int i = threadIdx.x; i < kMulHistSmem; i += kCountWarps * 32) s_hist[i] = 0;
+  __syncthreads();
+  const u32 lt = lanemask_lt();
+  u32 n_ones = 0;  // runs of multiplicity 1 seen by this warp (lane 0 only)
+
+  while (true) {
+    u32 chunk = 0;
+    if (lane == 0) chunk = atomicAdd(ticket, 1u);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    if (chunk >= n_chunks) break;
+    const u64 a = (u64)chunk * CH;
+    const u64 b = a + CH < n ? a + CH : n;
+
+    bool open = false;
+    u32 c_cnt = 0, c_p[4] = {0, 0, 0, 0}, c_n[4] = {0, 0, 0, 0};
+    u32 prev_rec[WR];
+    if (a > 0) ld_rec<WR>(recs, a - 1, prev_rec);
+    else {
+#pragma unroll
+      for (int j = 0; j < WR; ++j) prev_rec[j] = 0;
+    }
+    u32 n_staged = 0;
+
+    for (u64 pos0 = a;; pos0 += 32) {
+      const u64 i = pos0 + lane;
+      const bool valid = i < n;
+      u32 rec[WR], pr[WR];
+      if (valid) ld_rec<WR>(recs, i, rec);
+      else {
+#pragma unroll
+        for (int j = 0; j < WR; ++j) rec[j] = 0;
+      }
+#pragma unroll
+      for (int j = 0; j < WR; ++j) {
+        pr[j] = __shfl_up_sync(0xffffffffu, rec[j], 1);
+        if (lane == 0) pr[j] = prev_rec[j];
+      }
+      const bool is_head = (i == n) || (valid && (i == 0 || !same_edge<WR>(rec, pr)));
+      const u32 heads = __ballot_sync(0xffffffffu, is_head);
+      const u32 vmask = __ballot_sync(0xffffffffu, valid);
+      const u32 pn = rec[WR - 1] & 63u;
+      u32 mp[4], mn[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        mp[c] = __ballot_sync(0xffffffffu, valid && (pn >> 3) == (u32)c);
+        mn[c] = __ballot_sync(0xffffffffu, valid && (pn & 7u) == (u32)c);
+      }
+
+      // ---- lanes holding a head finish the run that ends just before them ----
+      bool emit = false, solid = false;
+      u32 count = 0, flags = 0;
+      if (is_head) {
+        const u32 below = heads & lt;
+        const bool has_h = below != 0;
+        const u32 hl = has_h ? 31u - __clz(below) : 0u;
+        const u32 seg = lt & ~((1u << hl) - 1u);  // lanes [hl, lane) -- hl = 0 when the run started earlier
+        const bool owned = has_h ? (pos0 + hl < b) : open;
+        if (owned) {
+          count = __popc(seg & vmask) + (has_h ? 0u : c_cnt);
+          bool has_in = false, has_out = false;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const u32 tp = __popc(seg & mp[c]) + (has_h ? 0u : c_p[c]);
+            const u32 tn = __popc(seg & mn[c]) + (has_h ? 0u : c_n[c]);
+            has_in = has_in || (long long)tp >= (long long)m;
+            has_out = has_out || (long long)tn >= (long long)m;
+          }
+          emit = count > 0;
+          solid = emit && (long long)count >= (long long)m;
+          flags = (has_in ? 0u : 1u) | (has_out ? 0u : 2u);
+        }
+      }
+      const u32 emit_mask = __ballot_sync(0xffffffffu, emit);
+      if (emit_mask) {
+        const u32 c16 = count > 65535u ? 65535u : count;
+        const u32 ones = __ballot_sync(0xffffffffu, emit && c16 == 1u);
+        n_ones += __popc(ones);
+        if (emit && c16 != 1u) {
+          if (c16 < (u32)kMulHistSmem) atomicAdd(&s_hist[c16], 1u);
+          else atomicAdd((unsigned long long *)&mul_hist[c16], 1ull);
+        }
+        const u32 solid_mask = __ballot_sync(0xffffffffu, solid);
+        if (solid) {
+          const u32 at = n_staged + __popc(solid_mask & lt);
+          u32 key[WR];
+#pragma unroll
+          for (int j = 0; j < WR; ++j) key[j] = pr[j];
+          key[WR - 1] &= ~63u;
+          u32 *e = stage + (size_t)at * WE;
+          for (u32 x = 0; x < WE; ++x) e[x] = (x < W && x < (u32)WR) ? pick<WR>(key, x) : 0u;
+          e[WE - 1] |= c16;
+          stage_aux[at] = (uint8_t)flags;
+        }
+        n_staged += __popc(solid_mask);
+      }
+
+      // ---- carry the run that is still open at the end of this slot ----
+      if (heads) {
+        const u32 H = 31u - __clz(heads);
+        const u32 tail = ~((1u << H) - 1u);
+        if (pos0 + H < n) {
+          open = pos0 + H < b;
+          c_cnt = __popc(vmask & tail);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            c_p[c] = __popc(mp[c] & tail);
+            c_n[c] = __popc(mn[c] & tail);
+          }
+        } else {
+          open = false;
+        }
+      } else if (open) {
+        c_cnt = min(c_cnt + (u32)__popc(vmask), 0x40000000u);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          c_p[c] = min(c_p[c] + (u32)__popc(mp[c]), 0x40000000u);
+          c_n[c] = min(c_n[c] + (u32)__popc(mn[c]), 0x40000000u);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < WR; ++j) prev_rec[j] = __shfl_sync(0xffffffffu, rec[j], 31);
+      const u64 next = pos0 + 32;
+      if (next > n || (next >= b && !open)) break;
+    }
+
+    // ---- global offset of this chunk's solid edges: decoupled look-back over chunk totals ----
+    u64 offset = 0;
+    if (lane == 0) {
+      u64 *my = lookback + chunk;
+      if (chunk == 0) {
+        st_relaxed(my, kLbInclusive | (u64)n_staged);
+      } else {
+        st_relaxed(my, kLbPartial | (u64)n_staged);
+        for (u32 p = chunk; p-- > 0;) {
+          u64 v;
+          do {
+            v = ld_relaxed(lookback + p);
+          } while ((v & kLbStatusMask) == 0);
+          offset += v & kLbValueMask;
+          if ((v & kLbStatusMask) == kLbInclusive) break;
+        }
+        st_relaxed(my, kLbInclusive | (offset + n_staged));
+      }
+      if (chunk == n_chunks - 1) *n_solid_out = offset + n_staged;
+    }
+    offset = __shfl_sync(0xffffffffu, offset, 0);
+    __syncwarp();
+    const u64 room = offset < capacity ? capacity - offset : 0;
+    const u32 n_out = (u64)n_staged < room ? n_staged : (u32)room;
+    for (u32 x = lane; x < n_out * WE; x += 32) edges[offset * WE + x] = stage[x];
+    for (u32 x = lane; x < n_out; x += 32) aux[offset + x] = stage_aux[x];
+    __syncwarp();
+  }
+
+  if (lane == 0 && n_ones) atomicAdd(&s_hist[1], n_ones);
+  __syncthreads();
+  for (int c = threadIdx.x; c < kMulHistSmem; c += kCountWarps * 32)
+    if (s_hist[c]) atomicAdd((unsigned long long *)&mul_hist[c], (unsigned long long)s_hist[c]);
+}
+
+}  // namespace mhb
+
+namespace mhb {
+
+// ------------------------------------------------------------------------------------------------
+// K-count v3 (A5/A6): one pass, each LANE walks IPL consecutive sorted records.
+//
+// A warp claims a chunk of 32*IPL records by ticket and stages it in shared memory (coalesced loads,
+// lane-blocked conflict-free layout).  Every lane scans its IPL records once, keeping byte-packed
+// prev/next tallies (kmer_counter.cpp:279-295) for the run it is in; runs that start and end inside a
+// lane are judged on the spot, the piece before a lane's first run head ("front") and the piece after
+// its last head ("back") are stitched across lanes by one segmented warp scan, and the chunk's last run
+// is followed past the chunk end with ballots.  A run is OWNED by the lane holding its first record, so
+// solid edges come out in sorted order: lane counts -> warp scan -> chunk offset by decoupled look-back
+// over chunk totals -> PackEdge (kmer_counter.cpp:32-52) straight into the output.
+// ------------------------------------------------------------------------------------------------
+static constexpr int kCount3Warps = 8;
+__host__ __device__ constexpr int count3_ipl(int wr) { return wr <= 4 ? 16 : (wr <= 8 ? 8 : 4); }
+__host__ __device__ constexpr int count3_lane_stride(int wr) {  // words; padded against bank conflicts
+  return count3_ipl(wr) * wr + (wr == 2 ? 2 : (wr == 4 ? 4 : ((count3_ipl(wr) * wr) % 2 == 0 ? 1 : 0)));
+}
+__host__ __device__ constexpr int count3_warp_words(int wr) {
+  return 32 * count3_lane_stride(wr) + ((wr + 3) & ~3) /*record a-1*/ + 32 * count3_ipl(wr) /*info*/;
+}
+
+__device__ __forceinline__ u64 spread16(u64 packed8) {  // 4 byte counters -> 4 u16 fields
+  return (packed8 & 0xFFull) | ((packed8 & 0xFF00ull) << 8) | ((packed8 & 0xFF0000ull) << 16) |
+         ((packed8 & 0xFF000000ull) << 24);
+}
+
+struct Tally {  // count + 4 prev + 4 next tallies as 16-bit fields
+  u32 cnt;
+  u64 p, n;
+};
+
+template <int WR>
+__global__ void __launch_bounds__(kCount3Warps * 32)
+    k_count_lanes(const u32 *__restrict__ recs, u64 n, u32 k, int m, u32 n_chunks, u32 *ticket, u64 *lookback,
+                  u32 *__restrict__ edges, uint8_t *__restrict__ aux, u64 capacity, u64 *mul_hist, u64 *n_solid_out) {
+  constexpr int IPL = count3_ipl(WR), CH = 32 * IPL, LS = count3_lane_stride(WR);
+  extern __shared__ __align__(16) u32 smem_w[];
+  __shared__ u32 s_hist[kMulHistSmem];
+  const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+  u32 *s_rec = smem_w + (size_t)warp * count3_warp_words(WR);  // lane-blocked records
+  u32 *s_prev = s_rec + 32 * LS;                                // record a-1
+  u32 *s_info = s_prev + ((WR + 3) & ~3);                       // per owned run head: judged result
+  const u32 W = count_key_words(k), WE = words_per_edge(k);
+  for (int i = threadIdx.x; i < kMulHistSmem; i += kCount3Warps * 32) s_hist[i] = 0;
+  __syncthreads();
+  u32 n_ones = 0;
+
+  auto judge = [&](u32 cnt, const u32 (&tp)[4], const u32 (&tn)[4]) -> u32 {
+    // -> 1 | solid<<1 | no_in<<2 | no_out<<3 | min(cnt,65535)<<8 ; also feeds the multiplicity histogram
+    const u32 c16 = cnt > 65535u ? 65535u : cnt;
+    if (c16 == 1u) ++n_ones;
+    else if (c16 < (u32)kMulHistSmem) atomicAdd(&s_hist[c16], 1u);
+    else atomicAdd((unsigned long long *)&mul_hist[c16], 1ull);
+    u32 word = 1u | (c16 << 8);
+    if ((long long)cnt >= (long long)m) {
+      bool has_in = false, has_out = false;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        has_in = has_in || (long long)tp[c] >= (long long)m;
+        has_out = has_out || (long long)tn[c] >= (long long)m;
+      }
+      word |= 2u | (has_in ? 0u : 4u) | (has_out ? 0u : 8u);
+    }
+    return word;
+  };
+
+  while (true) {
+    u32 chunk = 0;
+    if (lane == 0) chunk = atomicAdd(ticket, 1u);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    if (chunk >= n_chunks) break;
+    const u64 a = (u64)chunk * CH;
+    const u64 b = a + CH < n ? a + CH : n;
+    const u32 n_here = (u32)(b - a);
+
+    // ---- stage the chunk: coalesced global reads -> lane-blocked shared layout ----
+#pragma unroll
+    for (int i = 0; i < IPL; ++i) {
+      const u32 t = (u32)i * 32 + lane;
+      if (t < n_here) {
+        u32 r[WR];
+        ld_rec<WR>(recs, a + t, r);
+        u32 *dst = s_rec + (t / IPL) * LS + (t % IPL) * WR;
+        if constexpr (WR == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(r[0], r[1]);
+        else if constexpr (WR == 4) *reinterpret_cast<uint4 *>(dst) = make_uint4(r[0], r[1], r[2], r[3]);
+        else {
+#pragma unroll
+          for (int j = 0; j < WR; ++j) dst[j] = r[j];
+        }
+      }
+    }
+    if (lane < WR) s_prev[lane] = a > 0 ? recs[(a - 1) * WR + lane] : 0u;
+    __syncwarp();
+
+    // ---- every lane walks its records ----
+    const u32 my_first = lane * IPL;
+    const u32 my_n = n_here > my_first ? (n_here - my_first < (u32)IPL ? n_here - my_first : (u32)IPL) : 0u;
+    u32 prev[WR];
+    {
+      const u32 *pp = lane == 0 ? s_prev : s_rec + (lane - 1) * LS + (IPL - 1) * WR;
+#pragma unroll
+      for (int j = 0; j < WR; ++j) prev[j] = pp[j];
+    }
+    u32 cnt = 0, f_cnt = 0, head_slot = 0, solid_mask = 0, n_solid_lane = 0;
+    u64 cp = 0, cn = 0, f_cp = 0, f_cn = 0;  // byte-packed tallies (<= 16 per lane), byte 4 = sentinel
+    bool seen_head = false;
+    const u32 *mine = s_rec + lane * LS;
+    for (u32 j = 0; j < my_n; ++j) {
+      u32 r[WR];
+      if constexpr (WR == 2) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(mine + j * 2);
+        r[0] = v.x;
+        r[1] = v.y;
+      } else if constexpr (WR == 4) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(mine + j * 4);
+        r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+      } else {
+#pragma unroll
+        for (int q = 0; q < WR; ++q) r[q] = mine[j * WR + q];
+      }
+      const bool head = (a + my_first + j == 0) || !same_edge<WR>(r, prev);
+      if (head) {
+        if (!seen_head) {
+          f_cnt = cnt; f_cp = cp; f_cn = cn;
+          seen_head = true;
+        } else {  // a run that lives entirely inside this lane
+          u32 tp[4], tn[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            tp[c] = (u32)(cp >> (8 * c)) & 0xFFu;
+            tn[c] = (u32)(cn >> (8 * c)) & 0xFFu;
+          }
+          const u32 word = judge(cnt, tp, tn);
+          s_info[my_first + head_slot] = word;
+          if (word & 2u) {
+            solid_mask |= 1u << head_slot;
+            ++n_solid_lane;
+          }
+        }
+        cnt = 0; cp = 0; cn = 0;
+        head_slot = j;
+      }
+      const u32 pn = r[WR - 1] & 63u;
+      ++cnt;
+      cp += 1ull << (8 * (pn >> 3));
+      cn += 1ull << (8 * (pn & 7u));
+#pragma unroll
+      for (int q = 0; q < WR; ++q) prev[q] = r[q];
+    }
+    if (!seen_head) {  // the whole lane is the middle of somebody else's run
+      f_cnt = cnt; f_cp = cp; f_cn = cn;
+    }
+
+    // ---- stitch runs across lanes: S(y) = tallies of lanes y.. up to and including the first head lane ----
+    Tally S = {f_cnt, spread16(f_cp), spread16(f_cn)};
+    bool stop = seen_head;  // a head exists in [y, y+span)
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 o_cnt = __shfl_down_sync(0xffffffffu, S.cnt, d);
+      const u64 o_p = __shfl_down_sync(0xffffffffu, S.p, d);
+      const u64 o_n = __shfl_down_sync(0xffffffffu, S.n, d);
+      const bool o_stop = __shfl_down_sync(0xffffffffu, (int)stop, d) != 0;
+      if (lane + d < 32 && !stop) {
+        S.cnt += o_cnt; S.p += o_p; S.n += o_n;
+        stop = o_stop;
+      }
+    }
+    Tally nxt;  // S(lane+1)
+    nxt.cnt = __shfl_down_sync(0xffffffffu, S.cnt, 1);
+    nxt.p = __shfl_down_sync(0xffffffffu, S.p, 1);
+    nxt.n = __shfl_down_sync(0xffffffffu, S.n, 1);
+    bool later_head = __shfl_down_sync(0xffffffffu, (int)stop, 1) != 0;
+    if (lane == 31) {
+      nxt.cnt = 0; nxt.p = 0; nxt.n = 0;
+      later_head = false;
+    }
+
+    // ---- the chunk's last run may continue past the chunk: follow it (warp-cooperative) ----
+    const u32 any_head = __ballot_sync(0xffffffffu, seen_head);
+    u32 t_cnt = 0, t_p[4] = {0, 0, 0, 0}, t_n[4] = {0, 0, 0, 0};
+    if (any_head && b < n) {
+      u32 key[WR];
+      {
+        const u32 t = n_here - 1;
+        const u32 *lp = s_rec + (t / IPL) * LS + (t % IPL) * WR;
+#pragma unroll
+        for (int j = 0; j < WR; ++j) key[j] = lp[j];
+      }
+      for (u64 pos = b; pos < n; pos += 32) {
+        const u64 i = pos + lane;
+        u32 r[WR];
+        bool same = false;
+        if (i < n) {
+          ld_rec<WR>(recs, i, r);
+          same = same_edge<WR>(r, key);
+        } else {
+#pragma unroll
+          for (int j = 0; j < WR; ++j) r[j] = 0;
+        }
+        const u32 diff = ~__ballot_sync(0xffffffffu, same);
+        const u32 seg = diff ? ((1u << (__ffs(diff) - 1)) - 1u) : 0xffffffffu;  // lanes still in the run
+        const u32 pn = r[WR - 1] & 63u;
+        t_cnt = min(t_cnt + (u32)__popc(seg), 0x40000000u);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          t_p[c] = min(t_p[c] + (u32)__popc(seg & __ballot_sync(0xffffffffu, (pn >> 3) == (u32)c)), 0x40000000u);
+          t_n[c] = min(t_n[c] + (u32)__popc(seg & __ballot_sync(0xffffffffu, (pn & 7u) == (u32)c)), 0x40000000u);
+        }
+        if (diff) break;
+      }
+    }
+
+    // ---- judge each lane's last run (the one that may span lanes) ----
+    if (seen_head) {
+      u32 tp[4], tn[4];
+      const u64 bp = spread16(cp) + nxt.p, bn = spread16(cn) + nxt.n;
+      u32 total = cnt + nxt.cnt;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tp[c] = (u32)(bp >> (16 * c)) & 0xFFFFu;
+        tn[c] = (u32)(bn >> (16 * c)) & 0xFFFFu;
+      }
+      if (!later_head) {  // this run reaches the end of the chunk: add what lies beyond
+        total = min(total + t_cnt, 0x40000000u);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tp[c] += t_p[c];
+          tn[c] += t_n[c];
+        }
+      }
+      const u32 word = judge(total, tp, tn);
+      s_info[my_first + head_slot] = word;
+      if (word & 2u) {
+        solid_mask |= 1u << head_slot;
+        ++n_solid_lane;
+      }
+    }
+
+    // ---- output offsets: lane scan, chunk total, look-back over earlier chunks ----
+    u32 inc = n_solid_lane;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= (u32)d) inc += t;
+    }
+    const u32 chunk_total = __shfl_sync(0xffffffffu, inc, 31);
+    u64 offset = 0;
+    if (lane == 0) {
+      u64 *my = lookback + chunk;
+      if (chunk == 0) {
+        st_relaxed(my, kLbInclusive | (u64)chunk_total);
+      } else {
+        st_relaxed(my, kLbPartial | (u64)chunk_total);
+        for (u32 p = chunk; p-- > 0;) {
+          u64 v;
+          do {
+            v = ld_relaxed(lookback + p);
+          } while ((v & kLbStatusMask) == 0);
+          offset += v & kLbValueMask;
+          if ((v & kLbStatusMask) == kLbInclusive) break;
+        }
+        st_relaxed(my, kLbInclusive | (offset + chunk_total));
+      }
+      if (chunk == n_chunks - 1) *n_solid_out = offset + chunk_total;
+    }
+    offset = __shfl_sync(0xffffffffu, offset, 0) + (inc - n_solid_lane);
+
+    // ---- PackEdge for this lane's solid runs, in order ----
+    while (solid_mask) {
+      const u32 j = __ffs(solid_mask) - 1;
+      solid_mask &= solid_mask - 1;
+      if (offset < capacity) {
+        const u32 word = s_info[my_first + j];
+        const u32 *kp = mine + j * WR;
+        u32 *e = edges + offset * WE;
+        for (u32 x = 0; x < WE; ++x) {
+          u32 v = (x < W && x < (u32)WR) ? kp[x] : 0u;
+          if (x == (u32)WR - 1) v &= ~63u;
+          e[x] = v;
+        }
+        e[WE - 1] |= word >> 8;
+        aux[offset] = (uint8_t)((word >> 2) & 3u);
+      }
+      ++offset;
+    }
+    __syncwarp();
+  }
+
+  if (n_ones) atomicAdd(&s_hist[1], n_ones);
+  __syncthreads();
+  for (int c = threadIdx.x; c < kMulHistSmem; c += kCount3Warps * 32)
+    if (s_hist[c]) atomicAdd((unsigned long long *)&mul_hist[c], (unsigned long long)s_hist[c]);
 }
 
 }  // namespace mhb

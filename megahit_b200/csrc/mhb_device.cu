@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "mhb.h"
@@ -282,9 +283,66 @@ extern "C" int mhb_count_solid(void *stream, const uint32_t *sorted_records, uin
   const size_t need = mhb_count_solid_scratch_bytes(n);
   if (scratch_bytes < need) return mhb_set_error(MHB_ERR_ARG, "count scratch too small (%zu < %zu)", scratch_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
+  const u32 WR = count_record_words(k);
+  static const bool use_v1 = getenv("MHB_COUNT_V1") != nullptr, use_v2 = getenv("MHB_COUNT_V2") != nullptr;
+  if (!use_v1 && !use_v2) {
+    // v3: single pass, lane-blocked (mhb_count.cuh k_count_lanes)
+    u32 *ticket = (u32 *)scratch;
+    u64 *lookback = (u64 *)((char *)scratch + 64);
+#define M(WW)                                                                                                         \
+  if (WR == WW) {                                                                                                     \
+    constexpr int CH = 32 * count3_ipl(WW);                                                                           \
+    const u64 n_chunks = (n + CH - 1) / CH;                                                                           \
+    if (n_chunks >= (1ull << 32)) return mhb_set_error(MHB_ERR_ARG, "too many records for one count launch");         \
+    CK(cudaMemsetAsync(scratch, 0, 64 + n_chunks * 8, st));                                                           \
+    const size_t smem = (size_t)kCount3Warps * count3_warp_words(WW) * 4;                                             \
+    static int bps = 0;                                                                                               \
+    if (!bps) {                                                                                                       \
+      CK(cudaFuncSetAttribute(k_count_lanes<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_count_lanes<WW>, kCount3Warps * 32, smem));            \
+      if (bps < 1) bps = 1;                                                                                           \
+    }                                                                                                                 \
+    u64 grid = (u64)sm_count() * bps;                                                                                 \
+    if (grid > (n_chunks + kCount3Warps - 1) / kCount3Warps) grid = (n_chunks + kCount3Warps - 1) / kCount3Warps;     \
+    k_count_lanes<WW><<<(unsigned)grid, kCount3Warps * 32, smem, st>>>(sorted_records, n, k, m, (u32)n_chunks, ticket, \
+                                                                      lookback, edges_out, aux_out, capacity_edges,   \
+                                                                      mul_hist, n_solid_out);                        \
+  }
+    MHB_FOR_WR(M)
+#undef M
+    CK_LAUNCH();
+    return MHB_OK;
+  }
+  if (use_v2) {
+    // v2: single pass, warp-cooperative ballots (mhb_count.cuh k_count_warp); kept for A/B checks
+    const u32 WE = words_per_edge(k);
+    const int CH = count_chunk((int)WE);
+    const u64 n_chunks = (n + CH - 1) / CH;
+    if (n_chunks >= (1ull << 32)) return mhb_set_error(MHB_ERR_ARG, "too many records for one count launch");
+    u32 *ticket = (u32 *)scratch;
+    u64 *lookback = (u64 *)((char *)scratch + 64);
+    CK(cudaMemsetAsync(scratch, 0, 64 + n_chunks * 8, st));
+    const size_t smem = (size_t)kCountWarps * CH * (WE * 4 + 1);
+    u64 grid = (u64)sm_count() * 4;
+    if (grid > (n_chunks + kCountWarps - 1) / kCountWarps) grid = (n_chunks + kCountWarps - 1) / kCountWarps;
+#define M(WW)                                                                                                        \
+  if (WR == WW) {                                                                                                    \
+    static bool attr = false;                                                                                        \
+    if (!attr) {                                                                                                     \
+      CK(cudaFuncSetAttribute(k_count_warp<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));           \
+      attr = true;                                                                                                   \
+    }                                                                                                                \
+    k_count_warp<WW><<<(unsigned)grid, kCountWarps * 32, smem, st>>>(sorted_records, n, k, m, (u32)n_chunks, ticket,  \
+                                                                    lookback, edges_out, aux_out, capacity_edges,    \
+                                                                    mul_hist, n_solid_out);                         \
+  }
+    MHB_FOR_WR(M)
+#undef M
+    CK_LAUNCH();
+    return MHB_OK;
+  }
   u32 *info = (u32 *)scratch;
   u64 *btot = (u64 *)((char *)scratch + (((size_t)n * 4 + 63) & ~(size_t)63));
-  const u32 WR = count_record_words(k);
   const u64 gmark = (n + 255) / 256;
 #define M(WW) \
   if (WR == WW) k_count_mark<WW><<<(unsigned)gmark, 256, 0, st>>>(sorted_records, n, m, info, mul_hist);
@@ -314,7 +372,7 @@ extern "C" size_t mhb_count_solid_scratch_bytes(uint64_t n) {
 // count: mercy bookkeeping
 // ------------------------------------------------------------------------------------------------
 extern "C" size_t mhb_tipset_bytes(uint64_t n_tip_edges, uint32_t k) {
-  return 16 + tipset_capacity(n_tip_edges) * (size_t)(count_key_words(k) + 1) * 4;
+  return 16 + tipset_filter_words(n_tip_edges) * 4 + tipset_capacity(n_tip_edges) * (size_t)(count_key_words(k) + 1) * 4;
 }
 
 extern "C" int mhb_count_tip_edges(void *stream, const uint8_t *aux, uint64_t n_solid, uint64_t *n_tip_host) {
@@ -336,15 +394,17 @@ extern "C" int mhb_tipset_build(void *stream, const uint32_t *edges, const uint8
                                 void *tipset, size_t tipset_bytes, uint64_t n_tip_edges) {
   if (tipset_bytes < mhb_tipset_bytes(n_tip_edges, k)) return mhb_set_error(MHB_ERR_ARG, "tipset too small");
   cudaStream_t st = (cudaStream_t)stream;
-  const u64 cap = tipset_capacity(n_tip_edges);
+  const u64 hdr[2] = {tipset_capacity(n_tip_edges), tipset_filter_words(n_tip_edges)};
+  const u64 cap = hdr[0], fwords = hdr[1];
   CK(cudaMemsetAsync(tipset, 0, mhb_tipset_bytes(n_tip_edges, k), st));
-  CK(cudaMemcpyAsync(tipset, &cap, 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(tipset, hdr, 16, cudaMemcpyHostToDevice, st));
   if (n_solid == 0) return MHB_OK;
-  u32 *table = (u32 *)((char *)tipset + 16);
+  u32 *filter = (u32 *)((char *)tipset + 16);
+  u32 *table = filter + fwords;
   const u32 W = count_key_words(k);
   const u64 g = (n_solid + 255) / 256;
 #define M(WW) \
-  if (W == WW) k_tipset_insert<WW><<<(unsigned)g, 256, 0, st>>>(edges, aux, n_solid, k, table, cap);
+  if (W == WW) k_tipset_insert<WW><<<(unsigned)g, 256, 0, st>>>(edges, aux, n_solid, k, filter, fwords, table, cap);
   MHB_FOR_W(M)
 #undef M
   CK_LAUNCH();
@@ -352,23 +412,25 @@ extern "C" int mhb_tipset_build(void *stream, const uint32_t *edges, const uint8
 }
 
 extern "C" int mhb_count_mark_mercy(void *stream, const mhb_dev_reads *reads, uint32_t k, const void *tipset,
-                                    size_t tipset_bytes, uint32_t *first_0_out, uint32_t *last_0_in) {
+                                    size_t tipset_bytes, uint64_t n_tip_edges, uint32_t *first_0_out,
+                                    uint32_t *last_0_in) {
   if (int rc = check_reads(reads, k)) return rc;
   if (reads->n_reads == 0) return MHB_OK;
-  if (tipset_bytes < 16 + 1024 * 8) return mhb_set_error(MHB_ERR_ARG, "bad tipset");
+  if (tipset_bytes < mhb_tipset_bytes(n_tip_edges, k)) return mhb_set_error(MHB_ERR_ARG, "bad tipset");
   cudaStream_t st = (cudaStream_t)stream;
   const ReadsView rv = make_reads_view(reads);
   const u32 W = count_key_words(k), WR = count_record_words(k);
-  const u64 cap = (tipset_bytes - 16) / ((size_t)(W + 1) * 4);
-  if (cap & (cap - 1)) return mhb_set_error(MHB_ERR_ARG, "tipset capacity %llu is not a power of two", (unsigned long long)cap);
-  const u32 *table = (const u32 *)((const char *)tipset + 16);
+  const u64 cap = tipset_capacity(n_tip_edges), fwords = tipset_filter_words(n_tip_edges);
+  const u32 *filter = (const u32 *)((const char *)tipset + 16);
+  const u32 *table = filter + fwords;
   const u64 n_batches = (rv.n_reads + kReadsPerBatch - 1) / kReadsPerBatch;
   const int grid = (int)(n_batches < (u64)(sm_count() * 8) ? n_batches : (u64)(sm_count() * 8));
-#define M(WW)                                                                                                  \
-  if (W == WW && WR == WW)                                                                                     \
-    k_mark_mercy<WW, WW><<<grid, kExtractThreads, 0, st>>>(rv, k, table, cap, first_0_out, last_0_in);         \
-  else if (W == WW && WR == WW + 1)                                                                            \
-    k_mark_mercy<WW, WW + 1><<<grid, kExtractThreads, 0, st>>>(rv, k, table, cap, first_0_out, last_0_in);     \
+#define M(WW)                                                                                                          \
+  if (W == WW && WR == WW)                                                                                             \
+    k_mark_mercy<WW, WW><<<grid, kExtractThreads, 0, st>>>(rv, k, filter, fwords, table, cap, first_0_out, last_0_in);  \
+  else if (W == WW && WR == WW + 1)                                                                                    \
+    k_mark_mercy<WW, WW + 1><<<grid, kExtractThreads, 0, st>>>(rv, k, filter, fwords, table, cap, first_0_out,         \
+                                                               last_0_in);                                            \
   else
   MHB_FOR_W(M) return mhb_set_error(MHB_ERR_ARG, "unsupported k=%u", k);
 #undef M

@@ -251,7 +251,7 @@ extern "C" int mhb_count_host(const mhb_count_args *args, mhb_count_result *res)
       own = true;
     }
     int rc = mhb_tipset_build(st, d_edges, d_aux, n_solid, k, d_tips, ts_bytes, n_tip);
-    if (!rc) rc = mhb_count_mark_mercy(st, &reads, k, d_tips, ts_bytes, d_first, d_last);
+    if (!rc) rc = mhb_count_mark_mercy(st, &reads, k, d_tips, ts_bytes, n_tip, d_first, d_last);
     h_first.resize(n_reads);
     h_last.resize(n_reads);
     if (!rc) {

@@ -22,20 +22,38 @@ static constexpr u32 kSentinel = 4;  // kmer_counter.h:48 kSentinelValue
 template <int W, int WR>
 MHB_HD void make_count_record(const u32 *s, u32 nwords, u32 L, u32 k, u32 q, u32 (&rec)[WR], u32 &strand) {
   const u32 K1 = k + 1;
-  u32 S[W], A[W], B[W];
-  load_sub<W>(s, nwords, q, K1, S);
-  reverse_sub<W>(S, K1, A);
-  complement_sub<W>(S, K1, B);
-  const bool st = less_words<W>(B, A);
   const u32 prev_pkg = (q + K1 < L) ? base_at(s, q + K1) : kSentinel;
   const u32 next_pkg = (q > 0) ? base_at(s, q - 1) : kSentinel;
+  bool st;
+  if constexpr (W == 2) {
+    // 17 <= k+1 <= 32: the whole edge fits one 64-bit word -- same arithmetic as the generic path below
+    const u32 w0 = q >> 4, sh = (q & 15) * 2;
+    const u32 x0 = s[w0];
+    const u32 x1 = (w0 + 1 < nwords) ? s[w0 + 1] : 0u;
+    const u32 x2 = (w0 + 2 < nwords) ? s[w0 + 2] : 0u;
+    const u32 T = 64u - 2u * K1;  // zero bits below the edge, 0..30
+    const u64 S = ((((u64)fshl(x0, x1, sh) << 32) | fshl(x1, x2, sh)) >> T) << T;
+    const u64 B = ((~S) >> T) << T;                                      // complement(S)
+    const u64 A = (((u64)rev2((u32)S) << 32) | rev2((u32)(S >> 32))) << T;  // reverse(S)
+    st = B < A;
+    const u64 key = st ? B : A;
+    rec[0] = (u32)(key >> 32);
+    rec[1] = (u32)key;
+    if constexpr (WR == 3) rec[2] = 0u;
+  } else {
+    u32 S[W], A[W], B[W];
+    load_sub<W>(s, nwords, q, K1, S);
+    reverse_sub<W>(S, K1, A);
+    complement_sub<W>(S, K1, B);
+    st = less_words<W>(B, A);
+#pragma unroll
+    for (int j = 0; j < WR; ++j) rec[j] = j < W ? (st ? B[j] : A[j]) : 0u;
+  }
   u32 p = prev_pkg, n = next_pkg;
   if (st) {
     p = next_pkg == kSentinel ? kSentinel : 3u - next_pkg;
     n = prev_pkg == kSentinel ? kSentinel : 3u - prev_pkg;
   }
-#pragma unroll
-  for (int j = 0; j < WR; ++j) rec[j] = j < W ? (st ? B[j] : A[j]) : 0u;
   rec[WR - 1] |= (p << 3) | n;
   strand = st ? 1u : 0u;
 }
@@ -157,6 +175,11 @@ __device__ __forceinline__ u64 ld_relaxed(const u64 *p) {
 __device__ __forceinline__ void st_relaxed(u64 *p, u64 v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+
+// look-back descriptor: [63:62] status (0 invalid, 1 partial, 2 inclusive) [61:54] epoch [53:0] value
+static constexpr u64 kLbPartial = 1ull << 62, kLbInclusive = 2ull << 62, kLbStatusMask = 3ull << 62;
+static constexpr u64 kLbValueMask = (1ull << 54) - 1;
+__host__ __device__ inline u64 lb_epoch(u32 e) { return (u64)(e & 255u) << 54; }
 
 // block-wide exclusive scan of one u32 per thread (all THREADS threads must call)
 template <int THREADS>

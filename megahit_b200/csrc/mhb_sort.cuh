@@ -15,10 +15,6 @@
 
 namespace mhb {
 
-// look-back descriptor: [63:62] status (0 invalid, 1 partial, 2 inclusive) [61:54] epoch [53:0] value
-static constexpr u64 kLbPartial = 1ull << 62, kLbInclusive = 2ull << 62, kLbStatusMask = 3ull << 62;
-static constexpr u64 kLbValueMask = (1ull << 54) - 1;
-__host__ __device__ inline u64 lb_epoch(u32 e) { return (u64)(e & 255u) << 54; }
 
 template <int WR>
 struct SortCfg {
@@ -27,6 +23,7 @@ struct SortCfg {
   static constexpr int IPT = WR <= 2 ? 18 : (WR <= 3 ? 12 : (WR <= 4 ? 10 : (WR <= 6 ? 6 : (WR <= 9 ? 4 : 2))));
   static constexpr int TILE = THREADS * IPT;
   static constexpr int NW = THREADS / 32;
+  static constexpr int MIN_BLOCKS = 2;
   static constexpr size_t SMEM = (size_t)(NW * 256 + 256 + 256 + 8) * 4 + 256 * 8 + (size_t)TILE * WR * 4;
 };
 
@@ -61,8 +58,20 @@ __global__ void k_hist_byte(const u32 *in, u64 n, int byte_idx, u64 *hist) {
     if (s_h[i]) atomicAdd((unsigned long long *)&hist[i], (unsigned long long)s_h[i]);
 }
 
+// digit = byte `bsel` of word `widx` of the record (both warp-uniform, hoisted out of the loops)
 template <int WR>
-__global__ void __launch_bounds__(SortCfg<WR>::THREADS)
+__device__ __forceinline__ u32 rec_digit(const u32 (&r)[WR], u32 widx, u32 bsel) {
+  u32 w;
+  if constexpr (WR == 1) w = r[0];
+  else if constexpr (WR == 2) w = widx ? r[1] : r[0];
+  else w = pick<WR>(r, widx);
+  return __byte_perm(w, 0, 0x4440u | bsel);
+}
+
+static constexpr int kLbWindow = 4;  // look-back descriptors fetched per round trip
+
+template <int WR>
+__global__ void __launch_bounds__(SortCfg<WR>::THREADS, SortCfg<WR>::MIN_BLOCKS)
     k_radix_pass(const u32 *__restrict__ in, u32 *__restrict__ out, u64 n, u32 num_tiles, int byte_idx,
                  const u64 *__restrict__ bin_base, u64 *lookback, u32 *tile_counter, u64 *next_hist,
                  int next_byte, u32 epoch) {
@@ -73,13 +82,16 @@ __global__ void __launch_bounds__(SortCfg<WR>::THREADS)
   u32 *s_warp_hist = reinterpret_cast<u32 *>(s_glob + 256);  // NW*256
   u32 *s_bin_start = s_warp_hist + NW * 256;                 // 256
   u32 *s_next = s_bin_start + 256;                           // 256
-  u32 *s_misc = s_next + 256;                                // 8 (ticket + scan scratch is separate)
+  u32 *s_misc = s_next + 256;                                // 8 (ticket)
   u32 *s_recs = s_misc + 8;                                  // TILE*WR (16-byte aligned)
   __shared__ u32 s_scan[THREADS / 32 + 1];
 
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt_mask = lanemask_lt();
   const u64 ep = lb_epoch(epoch);
+  const u32 widx = (u32)(WR - 1 - (byte_idx >> 2)), bsel = (u32)(byte_idx & 3);
+  const u32 nwidx = (u32)(WR - 1 - (next_byte >> 2)), nbsel = (u32)(next_byte & 3);
+  u32 *my_hist = s_warp_hist + warp * 256;
 
   for (int i = tid; i < 256; i += THREADS) s_next[i] = 0;
 
@@ -94,37 +106,42 @@ __global__ void __launch_bounds__(SortCfg<WR>::THREADS)
 
     // ---- load (warp-striped: slot i of lane l = warp chunk[i*32 + l]) ----
     u32 r[IPT][WR];
-    const u64 warp_base = tile_base + (u64)warp * 32 * IPT;
+    const u64 warp_base = tile_base + (u64)warp * 32 * IPT + lane;
+    if (tile_base + TILE <= n) {
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      const u64 idx = warp_base + (u64)i * 32 + lane;
-      if (idx < n) {
-        ld_rec<WR>(in, idx, r[i]);
-      } else {
+      for (int i = 0; i < IPT; ++i) ld_rec<WR>(in, warp_base + (u64)i * 32, r[i]);
+    } else {
 #pragma unroll
-        for (int j = 0; j < WR; ++j) r[i][j] = 0xFFFFFFFFu;  // padding sorts to the very end of the tile
+      for (int i = 0; i < IPT; ++i) {
+        const u64 idx = warp_base + (u64)i * 32;
+        if (idx < n) {
+          ld_rec<WR>(in, idx, r[i]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < WR; ++j) r[i][j] = 0xFFFFFFFFu;  // padding sorts to the very end of the tile
+        }
       }
     }
 
-    // ---- rank inside the warp: match on the digit, leader bumps the warp's counter ----
-    u32 rk[IPT];
+    // ---- rank inside the warp: match on the digit; the highest peer lane bumps the warp's counter ----
+    u32 rk[IPT];  // digit << 16 | rank within (warp, digit)
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-      const u32 d = rec_byte<WR>(r[i], byte_idx);
+      const u32 d = rec_digit<WR>(r[i], widx, bsel);
       const u32 peers = __match_any_sync(0xffffffffu, d);
-      const u32 leader = __ffs(peers) - 1;
+      const u32 leader = 31u - __clz(peers);
       u32 old = 0;
       if (lane == leader) {
-        old = s_warp_hist[warp * 256 + d];
-        s_warp_hist[warp * 256 + d] = old + __popc(peers);
+        old = my_hist[d];
+        my_hist[d] = old + __popc(peers);
       }
       __syncwarp();
       old = __shfl_sync(0xffffffffu, old, leader);
-      rk[i] = old + __popc(peers & lt_mask);
+      rk[i] = (d << 16) | (old + __popc(peers & lt_mask));
     }
     __syncthreads();
 
-    // ---- per digit: prefix over warps, tile total, local start, global offset (look-back) ----
+    // ---- per digit: prefix over warps, tile total, local start; publish the tile's counts ----
     u32 total = 0;
     if (tid < 256) {
 #pragma unroll
@@ -136,24 +153,50 @@ __global__ void __launch_bounds__(SortCfg<WR>::THREADS)
     }
     u32 tile_total;
     const u32 excl = block_excl_scan<THREADS>(total, s_scan, tile_total);
+    // padding records all carry digit 255 and are not real: exclude them from what we publish
+    const u64 pub = (u64)total - ((tid == 255) ? (u64)(TILE - valid) : 0ull);
+    u64 *my = lookback + (u64)tile * 256 + tid;
+    u64 win[kLbWindow];
     if (tid < 256) {
       s_bin_start[tid] = excl;
-      // padding records all carry digit 255 and are not real: exclude them from what we publish
-      const u64 pub = (u64)total - ((tid == 255) ? (u64)(TILE - valid) : 0ull);
-      u64 *my = lookback + (u64)tile * 256 + tid;
+      st_relaxed(my, (tile == 0 ? kLbInclusive : kLbPartial) | ep | pub);
+      // first window of predecessor descriptors: in flight while the tile is reordered below
+#pragma unroll
+      for (int j = 0; j < kLbWindow; ++j)
+        win[j] = (tile > (u32)j) ? ld_relaxed(lookback + (u64)(tile - 1 - j) * 256 + tid) : 0ull;
+    }
+    __syncthreads();
+
+    // ---- reorder in shared memory: every digit's records become contiguous, input order kept ----
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const u32 d = rk[i] >> 16;
+      const u32 pos = s_bin_start[d] + my_hist[d] + (rk[i] & 0xFFFFu);
+      st_rec<WR>(s_recs, pos, r[i]);
+    }
+
+    // ---- global offsets by decoupled look-back, kLbWindow descriptors per round trip ----
+    if (tid < 256) {
       u64 prefix = 0;
-      if (tile == 0) {
-        st_relaxed(my, kLbInclusive | ep | pub);
-      } else {
-        st_relaxed(my, kLbPartial | ep | pub);
-        for (u32 p = tile; p-- > 0;) {
-          const u64 *pp = lookback + (u64)p * 256 + tid;
-          u64 v;
-          do {
-            v = ld_relaxed(pp);
-          } while ((v & kLbStatusMask) == 0 || (v & lb_epoch(255)) != ep);
-          prefix += v & kLbValueMask;
-          if ((v & kLbStatusMask) == kLbInclusive) break;
+      if (tile > 0) {
+        u32 p = tile - 1;  // descriptor win[0] belongs to tile p
+        bool done = false;
+        while (!done) {
+#pragma unroll
+          for (int j = 0; j < kLbWindow; ++j) {
+            if (done) break;
+            u64 v = win[j];
+            const u64 *pp = lookback + (u64)(p - j) * 256 + tid;
+            while ((v & kLbStatusMask) == 0 || (v & lb_epoch(255)) != ep) v = ld_relaxed(pp);
+            prefix += v & kLbValueMask;
+            if ((v & kLbStatusMask) == kLbInclusive || p == (u32)j) done = true;
+          }
+          if (!done) {
+            p -= kLbWindow;
+#pragma unroll
+            for (int j = 0; j < kLbWindow; ++j)
+              win[j] = (p >= (u32)j) ? ld_relaxed(lookback + (u64)(p - j) * 256 + tid) : 0ull;
+          }
         }
         st_relaxed(my, kLbInclusive | ep | (prefix + pub));
       }
@@ -161,25 +204,27 @@ __global__ void __launch_bounds__(SortCfg<WR>::THREADS)
     }
     __syncthreads();
 
-    // ---- reorder in shared memory: every digit's records become contiguous, input order kept ----
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      const u32 d = rec_byte<WR>(r[i], byte_idx);
-      const u32 pos = s_bin_start[d] + s_warp_hist[warp * 256 + d] + rk[i];
-      st_rec<WR>(s_recs, pos, r[i]);
-    }
-    __syncthreads();
-
     // ---- coalesced scatter + next digit's histogram ----
+    if (next_hist) {
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      const u32 p = (u32)i * THREADS + tid;
-      if (p < valid) {
-        u32 q[WR];
-        ld_rec<WR>(s_recs, p, q);
-        const u32 d = rec_byte<WR>(q, byte_idx);
-        st_rec<WR>(out, s_glob[d] + p, q);
-        if (next_hist) atomicAdd(&s_next[rec_byte<WR>(q, next_byte)], 1u);
+      for (int i = 0; i < IPT; ++i) {
+        const u32 p = (u32)i * THREADS + tid;
+        if (p < valid) {
+          u32 q[WR];
+          ld_rec<WR>(s_recs, p, q);
+          st_rec<WR>(out, s_glob[rec_digit<WR>(q, widx, bsel)] + p, q);
+          atomicAdd(&s_next[rec_digit<WR>(q, nwidx, nbsel)], 1u);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        const u32 p = (u32)i * THREADS + tid;
+        if (p < valid) {
+          u32 q[WR];
+          ld_rec<WR>(s_recs, p, q);
+          st_rec<WR>(out, s_glob[rec_digit<WR>(q, widx, bsel)] + p, q);
+        }
       }
     }
     __syncthreads();

@@ -97,7 +97,7 @@ class CountPlan:
         lib._check(self.L.mhb_tipset_build(_stream(), _ptr(self.edges), _ptr(self.aux), n_solid, self.k,
                                            _ptr(self.tipset), need, n_tip.value))
         lib._check(self.L.mhb_count_mark_mercy(_stream(), C.byref(self._reads(bin_dev)), self.k, _ptr(self.tipset),
-                                               need, _ptr(self.first), _ptr(self.last)))
+                                               need, n_tip.value, _ptr(self.first), _ptr(self.last)))
         return n_solid, n_tip.value
 
     def run(self, bin_dev: torch.Tensor, timed: bool = False):
@@ -146,8 +146,10 @@ class S2sPlan:
         self.table = torch.zeros(65536 * 4, dtype=torch.int64, device=device)
         self.totals = torch.zeros(16, dtype=torch.int64, device=device)
         self.hist0 = torch.zeros(256, dtype=torch.int64, device=device)
+        self.events = []
 
-    def run(self, words: torch.Tensor, mult: torch.Tensor | None = None, n_seqs: int | None = None, stride: int = 0):
+    def run(self, words: torch.Tensor, mult: torch.Tensor | None = None, n_seqs: int | None = None, stride: int = 0,
+            timed: bool = False):
         """words: packed sequences; with mult=None they are `.edges` records of `stride` words each."""
         n_seqs = self.n_seqs if n_seqs is None else n_seqs
         assert n_seqs <= self.n_seqs
@@ -155,9 +157,19 @@ class S2sPlan:
         seqs = lib.DevSeqs(words.data_ptr(), words.numel(), n_seqs, self.seq_len, None, None, None,
                            mult.data_ptr() if mult is not None else None, stride)
         self.hist0.zero_()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
+        if timed:
+            ev[0].record()
         lib._check(self.L.mhb_s2s_extract(_stream(), C.byref(seqs), self.k, _ptr(self.a), self.n_items, _ptr(self.hist0),
                                           self.sort_bytes[0]))
+        if timed:
+            ev[1].record()
         srt = sort_records(self.a, self.b, self.n_items, self.W, self.sort_bytes, self.hist0, self.ws)
+        if timed:
+            ev[2].record()
         lib._check(self.L.mhb_s2s_emit(_stream(), _ptr(srt), self.n_items, self.k, _ptr(self.bytes), self.cap_bytes,
                                        _ptr(self.table), _ptr(self.totals), _ptr(self.scratch), self.scratch.numel()))
+        if timed:
+            ev[3].record()
+            self.events.append(ev)
         return self.totals

@@ -119,8 +119,8 @@ def load():
                                   C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     L.mhb_tipset_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_size_t,
                                    C.c_uint64]
-    L.mhb_count_mark_mercy.argtypes = [C.c_void_p, C.POINTER(DevReads), C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p,
-                                       C.c_void_p]
+    L.mhb_count_mark_mercy.argtypes = [C.c_void_p, C.POINTER(DevReads), C.c_uint32, C.c_void_p, C.c_size_t, C.c_uint64,
+                                       C.c_void_p, C.c_void_p]
     L.mhb_count_tip_edges.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.mhb_s2s_extract.argtypes = [C.c_void_p, C.POINTER(DevSeqs), C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                   C.c_int]
