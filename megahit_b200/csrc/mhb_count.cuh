@@ -341,24 +341,32 @@ __global__ void k_tipset_insert(const u32 *__restrict__ edges, const uint8_t *__
 }
 
 // K-mercy (kmer_counter.cpp:307-367): per read min/max over the occurrences of tip edges.
+// One warp per read, straight from global memory (the library is ~3 % of the count stage's traffic and
+// L1 serves the re-reads), kMercyUnroll positions per lane per round so that the bit-filter probes of a
+// whole 150 bp read are in flight together; the kernel is bound by L2 latency, not bandwidth.
+static constexpr int kMercyUnroll = 4;
+
 template <int W, int WR>
-__global__ void __launch_bounds__(kExtractThreads)
+__global__ void __launch_bounds__(256)
     k_mark_mercy(ReadsView rv, u32 k, const u32 *__restrict__ filter, u64 filter_words, const u32 *__restrict__ table,
                  u64 cap, u32 *first_0_out, u32 *last_0_in) {
   const u32 lane = lane_id();
   const u32 K1 = k + 1;
   const u32 fmask = (u32)(filter_words * 32 - 1);
-  for_each_read(rv, [&](u64 r, const u32 *s, u32 nwords, u32 L) {
+  for (u64 r = (u64)blockIdx.x * 8 + (threadIdx.x >> 5); r < rv.n_reads; r += (u64)gridDim.x * 8) {
+    const u32 *rec0 = rv.bin + rv.rec_start(r);
+    const u32 L = rec0[0];
+    const u32 *s = rec0 + 1;
+    const u32 nwords = div_ceil(L, 16);
     u32 first = 0xFFFFFFFFu;
     long long last = -1;
     if (L >= K1) {
       const u32 n_e = L - k;
-      // two positions per lane per round so that both filter probes are in flight together
-      for (u32 q0 = 0; q0 < n_e; q0 += 64) {
-        u32 key[2][W], strand[2], fw[2], h[2];
-        bool live[2];
+      for (u32 q0 = 0; q0 < n_e; q0 += 32 * kMercyUnroll) {
+        u32 key[kMercyUnroll][W], strand[kMercyUnroll], fw[kMercyUnroll], h[kMercyUnroll];
+        bool live[kMercyUnroll];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < kMercyUnroll; ++u) {
           const u32 q = q0 + 32 * u + lane;
           live[u] = q < n_e;
           h[u] = 0;
@@ -377,7 +385,7 @@ __global__ void __launch_bounds__(kExtractThreads)
           }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < kMercyUnroll; ++u) {
           if (!live[u] || !((fw[u] >> (hash2(h[u]) & 31)) & 1u)) continue;
           u64 slot = h[u] & (cap - 1);
           u32 flags = 0;
@@ -396,9 +404,9 @@ __global__ void __launch_bounds__(kExtractThreads)
           }
           if (flags) {
             const u32 off = L - K1 - (q0 + 32 * u + lane);  // offset in the reversed (package) read
+            // no in, strand 0 -> last; no in, strand 1 -> first; no out, strand 0 -> first; no out, strand 1 -> last
             const bool to_last = ((flags & 1u) && strand[u] == 0) || ((flags & 2u) && strand[u] == 1);
             const bool to_first = ((flags & 1u) && strand[u] == 1) || ((flags & 2u) && strand[u] == 0);
-            // no in, strand 0 -> last; no in, strand 1 -> first; no out, strand 0 -> first; no out, strand 1 -> last
             if (to_last) last = last > (long long)off ? last : (long long)off;
             if (to_first) first = first < off + 1 ? first : off + 1;
           }
@@ -415,7 +423,7 @@ __global__ void __launch_bounds__(kExtractThreads)
       first_0_out[r] = first;
       last_0_in[r] = last < 0 ? 0xFFFFFFFFu : (u32)last;
     }
-  });
+  }
 }
 
 }  // namespace mhb
@@ -622,8 +630,11 @@ namespace mhb {
 // lane are judged on the spot, the piece before a lane's first run head ("front") and the piece after
 // its last head ("back") are stitched across lanes by one segmented warp scan, and the chunk's last run
 // is followed past the chunk end with ballots.  A run is OWNED by the lane holding its first record, so
-// solid edges come out in sorted order: lane counts -> warp scan -> chunk offset by decoupled look-back
-// over chunk totals -> PackEdge (kmer_counter.cpp:32-52) straight into the output.
+// solid edges come out in sorted order.  No serial dependency between chunks: the judge kernel leaves each
+// chunk's solid runs as a compact list (slot, judged word) in a scratch area plus the chunk's total; a
+// three-phase scan turns the totals into output offsets; k_count_write then gathers the keys and packs the
+// edges (PackEdge, kmer_counter.cpp:32-52).  (A decoupled look-back over 512-record chunks was measured to
+// spend > 55 % of the kernel waiting on the chunk chain.)
 // ------------------------------------------------------------------------------------------------
 static constexpr int kCount3Warps = 8;
 __host__ __device__ constexpr int count3_ipl(int wr) { return wr <= 4 ? 16 : (wr <= 8 ? 8 : 4); }
@@ -646,8 +657,9 @@ struct Tally {  // count + 4 prev + 4 next tallies as 16-bit fields
 
 template <int WR>
 __global__ void __launch_bounds__(kCount3Warps * 32)
-    k_count_lanes(const u32 *__restrict__ recs, u64 n, u32 k, int m, u32 n_chunks, u32 *ticket, u64 *lookback,
-                  u32 *__restrict__ edges, uint8_t *__restrict__ aux, u64 capacity, u64 *mul_hist, u64 *n_solid_out) {
+    k_count_lanes(const u32 *__restrict__ recs, u64 n, u32 k, int m, u32 n_chunks, u32 *ticket,
+                  uint2 *__restrict__ solid_list /*n entries: chunk c owns [c*CH, (c+1)*CH)*/,
+                  u32 *__restrict__ chunk_count, u64 *mul_hist) {
   constexpr int IPL = count3_ipl(WR), CH = 32 * IPL, LS = count3_lane_stride(WR);
   extern __shared__ __align__(16) u32 smem_w[];
   __shared__ u32 s_hist[kMulHistSmem];
@@ -655,7 +667,7 @@ __global__ void __launch_bounds__(kCount3Warps * 32)
   u32 *s_rec = smem_w + (size_t)warp * count3_warp_words(WR);  // lane-blocked records
   u32 *s_prev = s_rec + 32 * LS;                                // record a-1
   u32 *s_info = s_prev + ((WR + 3) & ~3);                       // per owned run head: judged result
-  const u32 W = count_key_words(k), WE = words_per_edge(k);
+  (void)k;
   for (int i = threadIdx.x; i < kMulHistSmem; i += kCount3Warps * 32) s_hist[i] = 0;
   __syncthreads();
   u32 n_ones = 0;
@@ -851,52 +863,20 @@ __global__ void __launch_bounds__(kCount3Warps * 32)
       }
     }
 
-    // ---- output offsets: lane scan, chunk total, look-back over earlier chunks ----
+    // ---- leave this chunk's solid runs as a compact, ordered list ----
     u32 inc = n_solid_lane;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const u32 t = __shfl_up_sync(0xffffffffu, inc, d);
       if (lane >= (u32)d) inc += t;
     }
-    const u32 chunk_total = __shfl_sync(0xffffffffu, inc, 31);
-    u64 offset = 0;
-    if (lane == 0) {
-      u64 *my = lookback + chunk;
-      if (chunk == 0) {
-        st_relaxed(my, kLbInclusive | (u64)chunk_total);
-      } else {
-        st_relaxed(my, kLbPartial | (u64)chunk_total);
-        for (u32 p = chunk; p-- > 0;) {
-          u64 v;
-          do {
-            v = ld_relaxed(lookback + p);
-          } while ((v & kLbStatusMask) == 0);
-          offset += v & kLbValueMask;
-          if ((v & kLbStatusMask) == kLbInclusive) break;
-        }
-        st_relaxed(my, kLbInclusive | (offset + chunk_total));
-      }
-      if (chunk == n_chunks - 1) *n_solid_out = offset + chunk_total;
-    }
-    offset = __shfl_sync(0xffffffffu, offset, 0) + (inc - n_solid_lane);
-
-    // ---- PackEdge for this lane's solid runs, in order ----
+    if (lane == 31) chunk_count[chunk] = inc;
+    u32 at = inc - n_solid_lane;
     while (solid_mask) {
       const u32 j = __ffs(solid_mask) - 1;
       solid_mask &= solid_mask - 1;
-      if (offset < capacity) {
-        const u32 word = s_info[my_first + j];
-        const u32 *kp = mine + j * WR;
-        u32 *e = edges + offset * WE;
-        for (u32 x = 0; x < WE; ++x) {
-          u32 v = (x < W && x < (u32)WR) ? kp[x] : 0u;
-          if (x == (u32)WR - 1) v &= ~63u;
-          e[x] = v;
-        }
-        e[WE - 1] |= word >> 8;
-        aux[offset] = (uint8_t)((word >> 2) & 3u);
-      }
-      ++offset;
+      solid_list[a + at] = make_uint2(my_first + j, s_info[my_first + j]);
+      ++at;
     }
     __syncwarp();
   }
@@ -905,6 +885,66 @@ __global__ void __launch_bounds__(kCount3Warps * 32)
   __syncthreads();
   for (int c = threadIdx.x; c < kMulHistSmem; c += kCount3Warps * 32)
     if (s_hist[c]) atomicAdd((unsigned long long *)&mul_hist[c], (unsigned long long)s_hist[c]);
+}
+
+
+// ---- three-phase exclusive scan of u32 counts into u64 offsets (4096 entries per block) ----
+static constexpr int kScanThreads = 1024, kScanItems = 4, kScanTile = kScanThreads * kScanItems;
+
+__global__ void __launch_bounds__(kScanThreads) k_scan32_sums(const u32 *in, u64 n, u64 *bsum) {
+  __shared__ u32 s_scan[kScanThreads / 32 + 1];
+  const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
+  u32 c = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j)
+    if (base + j < n) c += in[base + j];
+  u32 total;
+  block_excl_scan<kScanThreads>(c, s_scan, total);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan32_apply(const u32 *in, u64 n, const u64 *bsum, u64 *out) {
+  __shared__ u32 s_scan[kScanThreads / 32 + 1];
+  const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
+  u32 v[kScanItems], c = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    v[j] = base + j < n ? in[base + j] : 0u;
+    c += v[j];
+  }
+  u32 total;
+  u64 off = bsum[blockIdx.x] + block_excl_scan<kScanThreads>(c, s_scan, total);
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    if (base + j < n) out[base + j] = off;
+    off += v[j];
+  }
+}
+
+// PackEdge (kmer_counter.cpp:32-52): one warp per chunk turns the chunk's solid list into edges
+template <int WR>
+__global__ void __launch_bounds__(256)
+    k_count_write(const u32 *__restrict__ recs, u32 k, u32 n_chunks, const uint2 *__restrict__ solid_list,
+                  const u32 *__restrict__ chunk_count, const u64 *__restrict__ chunk_off, u32 *__restrict__ edges,
+                  uint8_t *__restrict__ aux, u64 capacity) {
+  constexpr int CH = 32 * count3_ipl(WR);
+  const u32 W = count_key_words(k), WE = words_per_edge(k);
+  const u32 lane = lane_id();
+  for (u64 chunk = (u64)blockIdx.x * 8 + (threadIdx.x >> 5); chunk < n_chunks; chunk += (u64)gridDim.x * 8) {
+    const u32 cnt = chunk_count[chunk];
+    const u64 off = chunk_off[chunk], a = chunk * CH;
+    for (u32 x = lane; x < cnt; x += 32) {
+      if (off + x >= capacity) break;
+      const uint2 ent = solid_list[a + x];
+      u32 r[WR];
+      ld_rec<WR>(recs, a + ent.x, r);
+      r[WR - 1] &= ~63u;
+      u32 *e = edges + (off + x) * WE;
+      for (u32 y = 0; y < WE; ++y) e[y] = (y < W && y < (u32)WR) ? pick<WR>(r, y) : 0u;
+      e[WE - 1] |= ent.y >> 8;
+      aux[off + x] = (uint8_t)((ent.y >> 2) & 3u);
+    }
+  }
 }
 
 }  // namespace mhb

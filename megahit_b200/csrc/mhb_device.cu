@@ -286,27 +286,46 @@ extern "C" int mhb_count_solid(void *stream, const uint32_t *sorted_records, uin
   const u32 WR = count_record_words(k);
   static const bool use_v1 = getenv("MHB_COUNT_V1") != nullptr, use_v2 = getenv("MHB_COUNT_V2") != nullptr;
   if (!use_v1 && !use_v2) {
-    // v3: single pass, lane-blocked (mhb_count.cuh k_count_lanes)
-    u32 *ticket = (u32 *)scratch;
-    u64 *lookback = (u64 *)((char *)scratch + 64);
-#define M(WW)                                                                                                         \
-  if (WR == WW) {                                                                                                     \
-    constexpr int CH = 32 * count3_ipl(WW);                                                                           \
-    const u64 n_chunks = (n + CH - 1) / CH;                                                                           \
-    if (n_chunks >= (1ull << 32)) return mhb_set_error(MHB_ERR_ARG, "too many records for one count launch");         \
-    CK(cudaMemsetAsync(scratch, 0, 64 + n_chunks * 8, st));                                                           \
-    const size_t smem = (size_t)kCount3Warps * count3_warp_words(WW) * 4;                                             \
-    static int bps = 0;                                                                                               \
-    if (!bps) {                                                                                                       \
-      CK(cudaFuncSetAttribute(k_count_lanes<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_count_lanes<WW>, kCount3Warps * 32, smem));            \
-      if (bps < 1) bps = 1;                                                                                           \
-    }                                                                                                                 \
-    u64 grid = (u64)sm_count() * bps;                                                                                 \
-    if (grid > (n_chunks + kCount3Warps - 1) / kCount3Warps) grid = (n_chunks + kCount3Warps - 1) / kCount3Warps;     \
-    k_count_lanes<WW><<<(unsigned)grid, kCount3Warps * 32, smem, st>>>(sorted_records, n, k, m, (u32)n_chunks, ticket, \
-                                                                      lookback, edges_out, aux_out, capacity_edges,   \
-                                                                      mul_hist, n_solid_out);                        \
+    // v3: lane-blocked judge -> scan of chunk totals -> gather/pack (mhb_count.cuh)
+#define M(WW)                                                                                                          \
+  if (WR == WW) {                                                                                                      \
+    constexpr int CH = 32 * count3_ipl(WW);                                                                            \
+    const u64 n_chunks = (n + CH - 1) / CH;                                                                            \
+    if (n_chunks >= (1ull << 32)) return mhb_set_error(MHB_ERR_ARG, "too many records for one count launch");          \
+    const u64 n_sblk = (n_chunks + kScanTile - 1) / kScanTile;                                                         \
+    char *p = (char *)scratch;                                                                                         \
+    u32 *ticket = (u32 *)p;                                                                                            \
+    p += 256;                                                                                                          \
+    uint2 *solid_list = (uint2 *)p;                                                                                    \
+    p += ((size_t)n_chunks * CH * 8 + 255) & ~(size_t)255;                                                             \
+    u32 *chunk_count = (u32 *)p;                                                                                       \
+    p += ((size_t)n_chunks * 4 + 255) & ~(size_t)255;                                                                  \
+    u64 *chunk_off = (u64 *)p;                                                                                         \
+    p += ((size_t)n_chunks * 8 + 255) & ~(size_t)255;                                                                  \
+    u64 *bsum = (u64 *)p;                                                                                              \
+    CK(cudaMemsetAsync(ticket, 0, 256, st));                                                                           \
+    const size_t smem = (size_t)kCount3Warps * count3_warp_words(WW) * 4;                                              \
+    static int bps = 0;                                                                                                \
+    if (!bps) {                                                                                                        \
+      CK(cudaFuncSetAttribute(k_count_lanes<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_count_lanes<WW>, kCount3Warps * 32, smem));             \
+      if (bps < 1) bps = 1;                                                                                            \
+    }                                                                                                                  \
+    u64 grid = (u64)sm_count() * bps;                                                                                  \
+    if (grid > (n_chunks + kCount3Warps - 1) / kCount3Warps) grid = (n_chunks + kCount3Warps - 1) / kCount3Warps;      \
+    k_count_lanes<WW><<<(unsigned)grid, kCount3Warps * 32, smem, st>>>(sorted_records, n, k, m, (u32)n_chunks, ticket,  \
+                                                                      solid_list, chunk_count, mul_hist);             \
+    CK_LAUNCH();                                                                                                       \
+    k_scan32_sums<<<(unsigned)n_sblk, kScanThreads, 0, st>>>(chunk_count, n_chunks, bsum);                             \
+    CK_LAUNCH();                                                                                                       \
+    k_scan_u64<<<1, 1024, 0, st>>>(bsum, n_sblk, n_solid_out);                                                         \
+    CK_LAUNCH();                                                                                                       \
+    k_scan32_apply<<<(unsigned)n_sblk, kScanThreads, 0, st>>>(chunk_count, n_chunks, bsum, chunk_off);                 \
+    CK_LAUNCH();                                                                                                       \
+    u64 gw = (n_chunks + 7) / 8;                                                                                       \
+    if (gw > (u64)sm_count() * 16) gw = (u64)sm_count() * 16;                                                          \
+    k_count_write<WW><<<(unsigned)gw, 256, 0, st>>>(sorted_records, k, (u32)n_chunks, solid_list, chunk_count,         \
+                                                    chunk_off, edges_out, aux_out, capacity_edges);                   \
   }
     MHB_FOR_WR(M)
 #undef M
@@ -364,8 +383,8 @@ extern "C" int mhb_count_solid(void *stream, const uint32_t *sorted_records, uin
 }
 
 extern "C" size_t mhb_count_solid_scratch_bytes(uint64_t n) {
-  const u64 nblk = (n + kCompactTile - 1) / kCompactTile;
-  return (((size_t)n * 4 + 63) & ~(size_t)63) + (size_t)nblk * 8 + 128;
+  // solid list (8 B per record slot, chunk-rounded) + per-chunk count/offset (chunks of >= 128 records) + slack
+  return (size_t)(n + 1024) * 8 + (size_t)(n / 128 + 2) * 12 + (size_t)(n / 128 / kScanTile + 2) * 8 + 4096;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -423,14 +442,14 @@ extern "C" int mhb_count_mark_mercy(void *stream, const mhb_dev_reads *reads, ui
   const u64 cap = tipset_capacity(n_tip_edges), fwords = tipset_filter_words(n_tip_edges);
   const u32 *filter = (const u32 *)((const char *)tipset + 16);
   const u32 *table = filter + fwords;
-  const u64 n_batches = (rv.n_reads + kReadsPerBatch - 1) / kReadsPerBatch;
-  const int grid = (int)(n_batches < (u64)(sm_count() * 8) ? n_batches : (u64)(sm_count() * 8));
+  u64 g64 = (rv.n_reads + 7) / 8;
+  if (g64 > (u64)sm_count() * 16) g64 = (u64)sm_count() * 16;
+  const int grid = (int)g64;
 #define M(WW)                                                                                                          \
   if (W == WW && WR == WW)                                                                                             \
-    k_mark_mercy<WW, WW><<<grid, kExtractThreads, 0, st>>>(rv, k, filter, fwords, table, cap, first_0_out, last_0_in);  \
+    k_mark_mercy<WW, WW><<<grid, 256, 0, st>>>(rv, k, filter, fwords, table, cap, first_0_out, last_0_in);              \
   else if (W == WW && WR == WW + 1)                                                                                    \
-    k_mark_mercy<WW, WW + 1><<<grid, kExtractThreads, 0, st>>>(rv, k, filter, fwords, table, cap, first_0_out,         \
-                                                               last_0_in);                                            \
+    k_mark_mercy<WW, WW + 1><<<grid, 256, 0, st>>>(rv, k, filter, fwords, table, cap, first_0_out, last_0_in);          \
   else
   MHB_FOR_W(M) return mhb_set_error(MHB_ERR_ARG, "unsupported k=%u", k);
 #undef M
