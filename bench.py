@@ -6,7 +6,7 @@
 One "step" = one pass of the hot path over one batch of reads: canonical (k+1)-mer edge extraction, LSD
 radix sort, solid-edge counting + mercy bookkeeping, then seq2sdbg item extraction, radix sort and SdBG
 emission from the device-resident solid edges.  `value` is whole-job edges/s with the read library already
-in HBM; `e2e` is the same metric through the host-buffer C ABI (mhb_count_host + mhb_s2s_host), H2D/D2H
+in HBM; `e2e` is the same metric through the host-buffer C ABI (mhb_build_host: count -> device mercy edges -> seq2sdbg), H2D/D2H
 inside the timed region.  `--impl reference` times the unmodified reference's OpenMP path
 (oracle/_ref/megahit_core_ref count + seq2sdbg) on the host cores on a bounded sample.
 """
@@ -234,30 +234,24 @@ def ours(args):
     # s2s extract, 10x(scan256+radix), size, 4 scans, write, finalize
     launches = 1 + 2 * len(plan.sort_bytes) + 4 + 3 + 1 + 2 * len(s2s.sort_bytes) + 1 + 4 + 1 + 1
 
-    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    # ---- e2e: host buffers through the C ABI (fused build), H2D/D2H copies inside the timed region ----
     host_bin = torch.empty(bin_words, dtype=torch.int32).pin_memory()
     host_bin.copy_(bin_dev[:bin_words])
     hb = host_bin.numpy().view(np.uint32)
+    n_items_dev = int(n_items)
     del plan, s2s
     torch.cuda.empty_cache()
-    e2e_t, h2d, d2h = [], 0, 0
-    wpe = lib.words_per_edge(k)
-    ns = int(n_solid)
+    out_buf = torch.empty(max(1 << 20, 3 * n_items_dev), dtype=torch.uint8).pin_memory().numpy()
+    e2e_t, h2d, d2h, e2e_ms = [], 0, 0, {}
     for i in range((1 + args.e2e_steps) if args.e2e_steps > 0 else 0):
         t0 = time.perf_counter()
-        g = lib.count_host(hb, n_reads, k, m, want_mercy=True)
-        edges = g["edges"]
-        ns = len(edges)
-        words = np.ascontiguousarray(edges[:, :2])
-        mult = (edges[:, wpe - 1] & 0xFFFF).astype(np.uint16)
-        word_off = np.arange(ns + 1, dtype=np.uint64) * np.uint64(2)
-        lens = np.full(ns, k + 1, np.uint32)
-        gs = lib.s2s_host(words, word_off, lens, mult, k)
+        g = lib.build_host(hb, n_reads, k, m, need_mercy=True, want_edges=False, sdbg_out=out_buf, copy_bytes=False)
         t1 = time.perf_counter()
         if i > 0:
             e2e_t.append(t1 - t0)
-        h2d = hb.nbytes + words.nbytes + word_off.nbytes + lens.nbytes + mult.nbytes + 8 * (ns + 1)
-        d2h = edges.nbytes + 65536 * 8 + 8 * n_reads + gs["n_bytes"] + 65536 * 32
+        h2d = hb.nbytes
+        d2h = int(g["n_bytes"]) + 65536 * 32 + 16 * 8
+        e2e_ms = {**g["ms"], "n_mercy": int(g["n_mercy"]), "n_cand": int(g["n_cand"]), "sdbg_items": int(g["n_items"])}
     lib.load().mhb_release()
     e2e_v = n_edges / float(np.mean(e2e_t)) if e2e_t else None
 
@@ -278,12 +272,13 @@ def ours(args):
         "config": {"workload": f"synthetic {n_reads}x{L}bp reads (30x, 1% subst.), k={k}, m={m}, 1xB200 single-GPU "
                                "sdbg_build: count (extract+radix+solid count+mercy marks) + seq2sdbg (extract+radix+emit) "
                                "on the solid edges; mercy-edge generation (host) not in the device step",
-                   "n_edge_records": n_edges, "n_solid_edges": int(ns), "n_sdbg_sort_items": int(n_items),
+                   "n_edge_records": n_edges, "n_solid_edges": int(n_solid), "n_sdbg_sort_items": int(n_items),
                    "l2_note": "inputs (>= 4.9 GB per kernel) exceed the 126 MB L2, no explicit flush needed"},
         "stage_ms": stage,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
         "e2e": {"value": e2e_v, "unit": "edges/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": float(np.mean(e2e_t)) * 1e3 if e2e_t else None, "api": "mhb_count_host + mhb_s2s_host (host buffers)"},
+                "ms_per_step": float(np.mean(e2e_t)) * 1e3 if e2e_t else None, "api": "mhb_build_host (pinned host buffers; count -> device mercy edges -> seq2sdbg, SdBG stream D2H)",
+                "stages": e2e_ms},
         "gpu_launches": launches,
     }))
 

@@ -130,6 +130,20 @@ int mhb_count_mark_mercy(void *stream, const mhb_dev_reads *reads, uint32_t k, c
 /* number of solid edges with aux != 0 (device reduction; result to host) */
 int mhb_count_tip_edges(void *stream, const uint8_t *aux, uint64_t n_solid, uint64_t *n_tip_host);
 
+/* A11 on the device (seq_to_sdbg.cpp:171-357 GenMercyEdges).
+ * mhb_mercy_candidates: ascending ids of the reads KmerCounter would write to `.cand`
+ *   (kmer_counter.cpp:390-401); cand_ids needs room for n_reads entries; *n_cand_host is set on return.
+ * mhb_mercy_edges: the mercy (k+1)-mers of those reads, searched in the sorted solid `edges` (n_edges records of
+ *   mhb_words_per_edge(k) words), written as `.edges`-format records with multiplicity 1 to mercy_out
+ *   (capacity records), candidates in id order, positions ascending.  max_read_len bounds the reads' lengths. */
+size_t mhb_mercy_candidates_scratch_bytes(uint64_t n_reads);
+int mhb_mercy_candidates(void *stream, const uint32_t *first_0_out, const uint32_t *last_0_in, uint64_t n_reads,
+                         uint64_t *cand_ids, uint64_t *n_cand_host, void *scratch, size_t scratch_bytes);
+size_t mhb_mercy_edges_scratch_bytes(uint64_t n_cand, uint32_t max_read_len);
+int mhb_mercy_edges(void *stream, const mhb_dev_reads *reads, const uint64_t *cand_ids, uint64_t n_cand,
+                    uint32_t max_read_len, uint32_t k, const uint32_t *edges, uint64_t n_edges, uint32_t *mercy_out,
+                    uint64_t capacity, uint64_t *n_mercy_host, void *scratch, size_t scratch_bytes);
+
 /* Sequences in package orientation for seq2sdbg: word-aligned 2-bit packing.
  * fixed_len > 0: sequence s starts at word s*fixed_stride (fixed_stride = 0 means ceil(fixed_len/16));
  * word_off/len/item_off may be NULL.  With mult == NULL the multiplicity of sequence s is the low 16 bits
@@ -212,6 +226,40 @@ typedef struct {
 } mhb_s2s_result;
 
 int mhb_s2s_host(const mhb_s2s_args *args, mhb_s2s_result *res);
+
+/* Fused k_min build: reads in, SdBG out, everything between stays in HBM.
+ * count (extract + sort + solid edges + mercy bookkeeping) -> mercy edges (device, need_mercy) -> seq2sdbg
+ * (extract + sort + emit) over solid + mercy edges.  Equivalent to `megahit_core count` followed by
+ * `megahit_core seq2sdbg --input_prefix P [--need_mercy]` without the `.edges`/`.cand` round trip.
+ * sdbg_out (optional, e.g. pinned memory) receives the item stream when it is large enough; otherwise the
+ * stream is malloc'ed into res->bytes.  want_edges additionally returns what `count` writes to disk. */
+typedef struct {
+  uint32_t k;
+  int32_t m;
+  const uint32_t *bin;
+  uint64_t bin_words;
+  uint64_t n_reads;
+  int32_t need_mercy;
+  int32_t want_edges;
+  uint8_t *sdbg_out;
+  uint64_t sdbg_out_capacity;
+} mhb_build_args;
+
+typedef struct {
+  uint64_t n_edge_records, n_solid, n_cand, n_mercy, n_sort_items;
+  uint32_t words_per_edge, words_per_tip_label;
+  uint64_t n_items, n_tips, n_large_mul, n_bytes;
+  uint8_t *bytes;         /* == args->sdbg_out when that was used, else malloc'ed (mhb_free) */
+  uint64_t *bucket_table; /* malloc'ed, 65536 x {byte offset, items, tips, large_mul} */
+  uint64_t w_count[9];
+  uint64_t ones_in_last;
+  uint32_t *edges;        /* want_edges: malloc'ed n_solid * words_per_edge */
+  uint64_t *cand_ids;     /* want_edges: malloc'ed n_cand */
+  int64_t *counting;      /* want_edges: malloc'ed 65536 */
+  double t_total_ms, t_h2d_ms, t_count_ms, t_mercy_ms, t_s2s_ms, t_d2h_ms;
+} mhb_build_result;
+
+int mhb_build_host(const mhb_build_args *args, mhb_build_result *res);
 
 void mhb_free(void *p);
 /* drop the cached device arena (host-level entry points keep it between calls) */

@@ -9,6 +9,7 @@
 #include "mhb.h"
 #include "mhb_count.cuh"
 #include "mhb_internal.h"
+#include "mhb_mercy.cuh"
 #include "mhb_s2s.cuh"
 #include "mhb_sort.cuh"
 
@@ -533,6 +534,99 @@ extern "C" int mhb_s2s_emit(void *stream, const uint32_t *sorted_records, uint64
   CK_LAUNCH();
   k_bucket_finalize<<<64, 256, 0, st>>>(bucket_start, totals, bucket_table);
   CK_LAUNCH();
+  return MHB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mercy edges on the device (A11)
+// ------------------------------------------------------------------------------------------------
+static int scan32(cudaStream_t st, const u32 *in, u64 n, u64 *out, u64 *total_dev, u64 *bsum) {
+  const u64 nb = (n + kScanTile - 1) / kScanTile;
+  k_scan32_sums<<<(unsigned)nb, kScanThreads, 0, st>>>(in, n, bsum);
+  CK_LAUNCH();
+  k_scan_u64<<<1, 1024, 0, st>>>(bsum, nb, total_dev);
+  CK_LAUNCH();
+  k_scan32_apply<<<(unsigned)nb, kScanThreads, 0, st>>>(in, n, bsum, out);
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
+extern "C" size_t mhb_mercy_candidates_scratch_bytes(uint64_t n_reads) {
+  return (size_t)(n_reads + 64) * 12 + (size_t)(n_reads / kScanTile + 2) * 8 + 1024;
+}
+
+extern "C" int mhb_mercy_candidates(void *stream, const uint32_t *first_0_out, const uint32_t *last_0_in,
+                                    uint64_t n_reads, uint64_t *cand_ids, uint64_t *n_cand_host, void *scratch,
+                                    size_t scratch_bytes) {
+  *n_cand_host = 0;
+  if (n_reads == 0) return MHB_OK;
+  if (scratch_bytes < mhb_mercy_candidates_scratch_bytes(n_reads)) return mhb_set_error(MHB_ERR_ARG, "scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  char *p = (char *)scratch;
+  u64 *total = (u64 *)p;
+  p += 256;
+  u32 *flag = (u32 *)p;
+  p += ((size_t)n_reads * 4 + 255) & ~(size_t)255;
+  u64 *off = (u64 *)p;
+  p += ((size_t)n_reads * 8 + 255) & ~(size_t)255;
+  u64 *bsum = (u64 *)p;
+  const unsigned g = (unsigned)((n_reads + 255) / 256);
+  k_cand_flags<<<g, 256, 0, st>>>(first_0_out, last_0_in, n_reads, flag);
+  CK_LAUNCH();
+  if (int rc = scan32(st, flag, n_reads, off, total, bsum)) return rc;
+  k_cand_compact<<<g, 256, 0, st>>>(flag, off, n_reads, cand_ids);
+  CK_LAUNCH();
+  CK(cudaMemcpyAsync(n_cand_host, total, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return MHB_OK;
+}
+
+extern "C" size_t mhb_mercy_edges_scratch_bytes(uint64_t n_cand, uint32_t max_read_len) {
+  const size_t wpr = (max_read_len + 31) / 32 + 1;
+  return (size_t)n_cand * 3 * wpr * 4 + (size_t)(n_cand + 64) * 12 + (size_t)(n_cand / kScanTile + 2) * 8 + 2048;
+}
+
+extern "C" int mhb_mercy_edges(void *stream, const mhb_dev_reads *reads, const uint64_t *cand_ids, uint64_t n_cand,
+                               uint32_t max_read_len, uint32_t k, const uint32_t *edges, uint64_t n_edges,
+                               uint32_t *mercy_out, uint64_t capacity, uint64_t *n_mercy_host, void *scratch,
+                               size_t scratch_bytes) {
+  *n_mercy_host = 0;
+  if (int rc = check_reads(reads, k)) return rc;
+  if (n_cand == 0) return MHB_OK;
+  if (k < 12) return mhb_set_error(MHB_ERR_ARG, "mercy edges need k >= 12 (12-mer look-up prefix)");
+  if (scratch_bytes < mhb_mercy_edges_scratch_bytes(n_cand, max_read_len)) return mhb_set_error(MHB_ERR_ARG, "scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const ReadsView rv = make_reads_view(reads);
+  const u32 wpr = (max_read_len + 31) / 32 + 1, WE = words_per_edge(k), WM = div_ceil(k + 1, 16);
+  char *p = (char *)scratch;
+  u64 *total = (u64 *)p;
+  p += 256;
+  u32 *bits = (u32 *)p;
+  p += ((size_t)n_cand * 3 * wpr * 4 + 255) & ~(size_t)255;
+  u32 *count = (u32 *)p;
+  p += ((size_t)n_cand * 4 + 255) & ~(size_t)255;
+  u64 *off = (u64 *)p;
+  p += ((size_t)n_cand * 8 + 255) & ~(size_t)255;
+  u64 *bsum = (u64 *)p;
+  u64 g64 = (n_cand + 7) / 8;
+  if (g64 > (u64)sm_count() * 16) g64 = (u64)sm_count() * 16;
+#define M(WW) \
+  if (WM == WW) k_mercy_probe<WW><<<(unsigned)g64, 256, 0, st>>>(rv, cand_ids, n_cand, k, edges, (long long)n_edges, WE, bits, wpr);
+  MHB_FOR_W(M)
+#undef M
+  CK_LAUNCH();
+  const unsigned g = (unsigned)((n_cand + 127) / 128);
+  k_mercy_emit<false><<<g, 128, 0, st>>>(rv, cand_ids, n_cand, k, bits, wpr, count, nullptr, nullptr, WE);
+  CK_LAUNCH();
+  if (int rc = scan32(st, count, n_cand, off, total, bsum)) return rc;
+  CK(cudaMemcpyAsync(n_mercy_host, total, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (*n_mercy_host > capacity) return mhb_set_error(MHB_ERR_NOMEM, "mercy edges (%llu) exceed capacity (%llu)",
+                                                     (unsigned long long)*n_mercy_host, (unsigned long long)capacity);
+  if (*n_mercy_host) {
+    k_mercy_emit<true><<<g, 128, 0, st>>>(rv, cand_ids, n_cand, k, bits, wpr, count, off, mercy_out, WE);
+    CK_LAUNCH();
+  }
   return MHB_OK;
 }
 

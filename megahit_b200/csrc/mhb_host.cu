@@ -398,6 +398,208 @@ extern "C" int mhb_s2s_host(const mhb_s2s_args *args, mhb_s2s_result *res) {
 }
 
 // ================================================================================================
+// fused k_min build: count -> mercy edges -> seq2sdbg, device resident
+// ================================================================================================
+extern "C" int mhb_build_host(const mhb_build_args *args, mhb_build_result *res) {
+  if (!args || !res) return mhb_set_error(MHB_ERR_ARG, "null args");
+  memset(res, 0, sizeof(*res));
+  const uint32_t k = args->k;
+  if (k < 9 || k > MHB_MAX_K) return mhb_set_error(MHB_ERR_ARG, "kmer size must be >= 9 and <= 255");
+  if (args->need_mercy && k < 12) return mhb_set_error(MHB_ERR_ARG, "mercy edges need k >= 12");
+  if (mhb_device_count() == 0) return mhb_set_error(MHB_ERR_CUDA, "no CUDA device: libmhb has no CPU path");
+  const uint32_t WR = count_record_words(k), WE = words_per_edge(k), W2 = s2s_record_words(k), WPT = words_per_tip_label(k);
+  res->words_per_edge = WE;
+  res->words_per_tip_label = WPT;
+
+  BinIndex ix;
+  CKR(index_bin(args->bin, args->bin_words, args->n_reads, k, &ix));
+  const uint64_t n = ix.n_edges, n_reads = args->n_reads;
+  res->n_edge_records = n;
+  uint32_t max_len = ix.fixed_len;
+  if (!ix.fixed_len)
+    for (uint64_t r = 0; r < n_reads; ++r) max_len = std::max(max_len, args->bin[ix.rec_off[r]]);
+
+  cudaStream_t st = 0;
+  Timer t_all(st), t(st);
+  t_all.start();
+
+  uint8_t cbytes[72], sbytes[72];
+  const uint32_t n_csort = mhb_count_sort_bytes(k, cbytes), n_ssort = mhb_s2s_sort_bytes(k, sbytes);
+  const int32_t m = args->m;
+  const uint64_t cap_edges = n / (uint64_t)std::max(1, m) + 1;
+  const size_t bin_bytes = (args->bin_words * 4 + 15) & ~(size_t)15;
+  const size_t c_ws = mhb_sort_workspace_bytes(n, WR), c_scr = mhb_count_solid_scratch_bytes(n);
+  const size_t count_work = 2 * Arena::pad((size_t)n * WR * 4 + 16) + Arena::pad(c_ws) + Arena::pad(c_scr);
+  // fixed part
+  size_t fixed = Arena::pad(bin_bytes + 16) + Arena::pad((size_t)cap_edges * WE * 4) + Arena::pad(cap_edges) +
+                 Arena::pad(65536 * 8) + 2 * Arena::pad(256 * 8) + Arena::pad(64) + Arena::pad((size_t)MHB_NUM_BUCKETS * 32) +
+                 Arena::pad(128) + 8192;
+  if (!ix.fixed_len) fixed += 2 * Arena::pad((n_reads + 1) * 8);
+  if (args->need_mercy) fixed += 2 * Arena::pad((n_reads + 1) * 4) + Arena::pad((n_reads + 1) * 8);
+  CKR(g_arena.reserve(fixed + count_work));
+
+  uint32_t *d_bin = g_arena.take<uint32_t>(bin_bytes / 4 + 4);
+  uint32_t *d_edges = g_arena.take<uint32_t>((size_t)cap_edges * WE);
+  uint8_t *d_aux = g_arena.take<uint8_t>(cap_edges);
+  uint64_t *d_mul_hist = g_arena.take<uint64_t>(65536);
+  uint64_t *d_hist0 = g_arena.take<uint64_t>(256);
+  uint64_t *d_hist1 = g_arena.take<uint64_t>(256);
+  uint64_t *d_nsolid = g_arena.take<uint64_t>(8);
+  uint64_t *d_table = g_arena.take<uint64_t>((size_t)MHB_NUM_BUCKETS * 4);
+  uint64_t *d_totals = g_arena.take<uint64_t>(16);
+  uint64_t *d_rec_off = nullptr, *d_edge_off = nullptr, *d_cand = nullptr;
+  uint32_t *d_first = nullptr, *d_last = nullptr;
+  if (!ix.fixed_len) {
+    d_rec_off = g_arena.take<uint64_t>(n_reads + 1);
+    d_edge_off = g_arena.take<uint64_t>(n_reads + 1);
+  }
+  if (args->need_mercy) {
+    d_first = g_arena.take<uint32_t>(n_reads + 1);
+    d_last = g_arena.take<uint32_t>(n_reads + 1);
+    d_cand = g_arena.take<uint64_t>(n_reads + 1);
+  }
+  char *work = g_arena.take<char>(count_work);
+  size_t work_bytes = count_work;
+  char *extra = nullptr;  // separately allocated work area when the SdBG stage outgrows the count stage's
+  struct ExtraGuard {
+    char *&p;
+    ~ExtraGuard() {
+      if (p) cudaFree(p);
+    }
+  } guard{extra};
+
+  // ---- H2D ----
+  t.start();
+  if (args->bin_words) CK(cudaMemcpyAsync(d_bin, args->bin, args->bin_words * 4, cudaMemcpyHostToDevice, st));
+  if (!ix.fixed_len && n_reads) {
+    CK(cudaMemcpyAsync(d_rec_off, ix.rec_off.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_edge_off, ix.edge_off.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaMemsetAsync(d_mul_hist, 0, 65536 * 8, st));
+  CK(cudaMemsetAsync(d_hist0, 0, 256 * 8, st));
+  CK(cudaMemsetAsync(d_hist1, 0, 256 * 8, st));
+  CK(cudaMemsetAsync(d_nsolid, 0, 64, st));
+  res->t_h2d_ms = t.stop();
+
+  mhb_dev_reads reads;
+  reads.bin = d_bin;
+  reads.bin_words = args->bin_words;
+  reads.n_reads = n_reads;
+  reads.fixed_len = ix.fixed_len;
+  reads.rec_off = d_rec_off;
+  reads.edge_off = d_edge_off;
+
+  // ---- count stage ----
+  t.start();
+  uint32_t *c_a = (uint32_t *)work;
+  uint32_t *c_b = (uint32_t *)(work + Arena::pad((size_t)n * WR * 4 + 16));
+  char *c_wsp = work + 2 * Arena::pad((size_t)n * WR * 4 + 16);
+  char *c_scrp = c_wsp + Arena::pad(c_ws);
+  CKR(mhb_count_extract(st, &reads, k, c_a, n, d_hist0, cbytes[0]));
+  int in_b = 0;
+  CKR(mhb_sort_records_impl(st, c_a, c_b, n, WR, cbytes, n_csort, d_hist0, c_wsp, c_ws, &in_b, nullptr));
+  CKR(mhb_count_solid(st, in_b ? c_b : c_a, n, k, m, d_edges, d_aux, cap_edges, d_mul_hist, d_nsolid, c_scrp, c_scr));
+  uint64_t n_solid = 0;
+  CK(cudaMemcpyAsync(&n_solid, d_nsolid, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (n_solid > cap_edges) return mhb_set_error(MHB_ERR_NOMEM, "internal: solid edges exceed capacity");
+  res->n_solid = n_solid;
+  res->t_count_ms = t.stop();
+
+  // ---- mercy: per-read marks -> candidates -> mercy edges appended to the solid edges ----
+  uint64_t n_cand = 0, n_mercy = 0;
+  if (args->need_mercy && n_reads) {
+    t.start();
+    uint64_t n_tip = 0;
+    CKR(mhb_count_tip_edges(st, d_aux, n_solid, &n_tip));
+    const size_t ts_bytes = mhb_tipset_bytes(n_tip, k);
+    const size_t cs_bytes = mhb_mercy_candidates_scratch_bytes(n_reads);
+    if (Arena::pad(ts_bytes) + Arena::pad(cs_bytes) > work_bytes) return mhb_set_error(MHB_ERR_NOMEM, "internal: mercy scratch");
+    char *d_tips = work;
+    char *d_cs = work + Arena::pad(ts_bytes);
+    CKR(mhb_tipset_build(st, d_edges, d_aux, n_solid, k, d_tips, ts_bytes, n_tip));
+    CKR(mhb_count_mark_mercy(st, &reads, k, d_tips, ts_bytes, n_tip, d_first, d_last));
+    CKR(mhb_mercy_candidates(st, d_first, d_last, n_reads, d_cand, &n_cand, d_cs, cs_bytes));
+    if (n_cand) {
+      const size_t ms_bytes = mhb_mercy_edges_scratch_bytes(n_cand, max_len);
+      if (ms_bytes > work_bytes) return mhb_set_error(MHB_ERR_NOMEM, "internal: mercy scratch");
+      CKR(mhb_mercy_edges(st, &reads, d_cand, n_cand, max_len, k, d_edges, n_solid, d_edges + (size_t)n_solid * WE,
+                          cap_edges - n_solid, &n_mercy, work, ms_bytes));
+    }
+    res->t_mercy_ms = t.stop();
+  }
+  res->n_cand = n_cand;
+  res->n_mercy = n_mercy;
+
+  // ---- SdBG stage over solid + mercy edges, straight from the device-resident edge records ----
+  t.start();
+  const uint64_t n_seqs = n_solid + n_mercy;
+  const uint64_t n_items = n_seqs * 6;  // 2 strands x (k+1 - k + 2)
+  res->n_sort_items = n_items;
+  const size_t s_ws = mhb_sort_workspace_bytes(n_items, W2), s_scr = mhb_s2s_emit_scratch_bytes(n_items);
+  const uint64_t cap_bytes = n_items * (4ull + 4ull * WPT) + 16;
+  const size_t s2s_work = 2 * Arena::pad((size_t)n_items * W2 * 4 + 16) + Arena::pad(s_ws) + Arena::pad(s_scr) + Arena::pad(cap_bytes);
+  char *sw = work;
+  if (s2s_work > work_bytes) {
+    cudaError_t e = cudaMalloc((void **)&extra, s2s_work);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return mhb_set_error(MHB_ERR_NOMEM, "cudaMalloc of %zu bytes for the SdBG stage failed", s2s_work);
+    }
+    sw = extra;
+  }
+  uint32_t *s_a = (uint32_t *)sw;
+  uint32_t *s_b = (uint32_t *)(sw + Arena::pad((size_t)n_items * W2 * 4 + 16));
+  char *s_wsp = sw + 2 * Arena::pad((size_t)n_items * W2 * 4 + 16);
+  char *s_scrp = s_wsp + Arena::pad(s_ws);
+  uint8_t *d_bytes = (uint8_t *)(s_scrp + Arena::pad(s_scr));
+  mhb_dev_seqs seqs;
+  memset(&seqs, 0, sizeof(seqs));
+  seqs.words = d_edges;
+  seqs.n_words = n_seqs * WE;
+  seqs.n_seqs = n_seqs;
+  seqs.fixed_len = k + 1;
+  seqs.fixed_stride = WE;
+  CKR(mhb_s2s_extract(st, &seqs, k, s_a, n_items, d_hist1, sbytes[0]));
+  int s_in_b = 0;
+  CKR(mhb_sort_records_impl(st, s_a, s_b, n_items, W2, sbytes, n_ssort, d_hist1, s_wsp, s_ws, &s_in_b, nullptr));
+  CKR(mhb_s2s_emit(st, s_in_b ? s_b : s_a, n_items, k, d_bytes, cap_bytes, d_table, d_totals, s_scrp, s_scr));
+  uint64_t totals[16];
+  CK(cudaMemcpyAsync(totals, d_totals, sizeof(totals), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  res->t_s2s_ms = t.stop();
+  res->n_bytes = totals[0];
+  res->n_items = totals[1];
+  res->n_tips = totals[2];
+  res->n_large_mul = totals[3];
+  for (int i = 0; i < 9; ++i) res->w_count[i] = totals[4 + i];
+  res->ones_in_last = totals[13];
+  if (res->n_bytes > cap_bytes) return mhb_set_error(MHB_ERR_NOMEM, "internal: SdBG byte stream exceeds capacity");
+
+  // ---- D2H ----
+  t.start();
+  res->bucket_table = (uint64_t *)malloc((size_t)MHB_NUM_BUCKETS * 32);
+  if (args->sdbg_out && args->sdbg_out_capacity >= res->n_bytes) res->bytes = args->sdbg_out;
+  else res->bytes = (uint8_t *)malloc(std::max<size_t>(1, res->n_bytes));
+  if (!res->bucket_table || !res->bytes) return mhb_set_error(MHB_ERR_NOMEM, "host malloc failed");
+  CK(cudaMemcpyAsync(res->bucket_table, d_table, (size_t)MHB_NUM_BUCKETS * 32, cudaMemcpyDeviceToHost, st));
+  if (res->n_bytes) CK(cudaMemcpyAsync(res->bytes, d_bytes, res->n_bytes, cudaMemcpyDeviceToHost, st));
+  if (args->want_edges) {
+    res->edges = (uint32_t *)malloc(std::max<size_t>(1, (size_t)n_solid * WE * 4));
+    res->cand_ids = (uint64_t *)malloc(std::max<size_t>(1, n_cand * 8));
+    res->counting = (int64_t *)malloc(65536 * 8);
+    if (!res->edges || !res->cand_ids || !res->counting) return mhb_set_error(MHB_ERR_NOMEM, "host malloc failed");
+    if (n_solid) CK(cudaMemcpyAsync(res->edges, d_edges, (size_t)n_solid * WE * 4, cudaMemcpyDeviceToHost, st));
+    if (n_cand) CK(cudaMemcpyAsync(res->cand_ids, d_cand, n_cand * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(res->counting, d_mul_hist, 65536 * 8, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  res->t_d2h_ms = t.stop();
+  res->t_total_ms = t_all.stop();
+  return MHB_OK;
+}
+
+// ================================================================================================
 // Self-test hooks: run the SAME record builders the kernels use (mhb_kernels.cuh, __host__ __device__)
 // on the host, so that `pytest -m "not gpu"` can check the bit arithmetic against the oracle without a
 // GPU.  They build one record at a time and are not a compute path.

@@ -67,6 +67,23 @@ class S2sResult(C.Structure):
                 ("t_emit_ms", C.c_double)]
 
 
+class BuildArgs(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("m", C.c_int32), ("bin", C.c_void_p), ("bin_words", C.c_uint64),
+                ("n_reads", C.c_uint64), ("need_mercy", C.c_int32), ("want_edges", C.c_int32),
+                ("sdbg_out", C.c_void_p), ("sdbg_out_capacity", C.c_uint64)]
+
+
+class BuildResult(C.Structure):
+    _fields_ = [("n_edge_records", C.c_uint64), ("n_solid", C.c_uint64), ("n_cand", C.c_uint64), ("n_mercy", C.c_uint64),
+                ("n_sort_items", C.c_uint64), ("words_per_edge", C.c_uint32), ("words_per_tip_label", C.c_uint32),
+                ("n_items", C.c_uint64), ("n_tips", C.c_uint64), ("n_large_mul", C.c_uint64), ("n_bytes", C.c_uint64),
+                ("bytes", C.POINTER(C.c_uint8)), ("bucket_table", C.POINTER(C.c_uint64)), ("w_count", C.c_uint64 * 9),
+                ("ones_in_last", C.c_uint64), ("edges", C.POINTER(C.c_uint32)), ("cand_ids", C.POINTER(C.c_uint64)),
+                ("counting", C.POINTER(C.c_int64)),
+                ("t_total_ms", C.c_double), ("t_h2d_ms", C.c_double), ("t_count_ms", C.c_double),
+                ("t_mercy_ms", C.c_double), ("t_s2s_ms", C.c_double), ("t_d2h_ms", C.c_double)]
+
+
 class CountOpts(C.Structure):
     _fields_ = [("k", C.c_uint32), ("m", C.c_int32), ("host_mem", C.c_double), ("num_cpu_threads", C.c_int32),
                 ("read_lib_file", C.c_char_p), ("output_prefix", C.c_char_p), ("mem_flag", C.c_int32)]
@@ -85,7 +102,8 @@ SYMBOLS = [
     "mhb_s2s_record_words", "mhb_count_sort_bytes", "mhb_s2s_sort_bytes", "mhb_sort_workspace_bytes",
     "mhb_count_extract", "mhb_sort_records", "mhb_sort_pass_ms", "mhb_count_solid_scratch_bytes", "mhb_count_solid", "mhb_tipset_bytes",
     "mhb_tipset_build", "mhb_count_mark_mercy", "mhb_count_tip_edges", "mhb_s2s_extract",
-    "mhb_s2s_emit_scratch_bytes", "mhb_s2s_emit", "mhb_set_device", "mhb_count_host", "mhb_s2s_host", "mhb_free",
+    "mhb_s2s_emit_scratch_bytes", "mhb_s2s_emit", "mhb_set_device", "mhb_count_host", "mhb_s2s_host", "mhb_build_host", "mhb_free",
+    "mhb_mercy_candidates_scratch_bytes", "mhb_mercy_candidates", "mhb_mercy_edges_scratch_bytes", "mhb_mercy_edges",
     "mhb_release", "mhb_count_run", "mhb_seq2sdbg_run", "mhb_selftest_count_record", "mhb_selftest_s2s_record",
 ]
 
@@ -128,6 +146,7 @@ def load():
                                C.c_void_p, C.c_void_p, C.c_size_t]
     L.mhb_count_host.argtypes = [C.POINTER(CountArgs), C.POINTER(CountResult)]
     L.mhb_s2s_host.argtypes = [C.POINTER(S2sArgs), C.POINTER(S2sResult)]
+    L.mhb_build_host.argtypes = [C.POINTER(BuildArgs), C.POINTER(BuildResult)]
     L.mhb_free.argtypes = [C.c_void_p]
     L.mhb_count_run.argtypes = [C.POINTER(CountOpts)]
     L.mhb_seq2sdbg_run.argtypes = [C.POINTER(Seq2SdbgOpts)]
@@ -232,6 +251,42 @@ def s2s_host(words: np.ndarray, word_off: np.ndarray, length: np.ndarray, mult: 
         "ms": {k_: getattr(r, f"t_{k_}_ms") for k_ in ("extract", "sort", "emit", "total")},
     }
     L.mhb_free(r.bytes)
+    return out
+
+
+def build_host(bin_words: np.ndarray, n_reads: int, k: int, m: int, need_mercy: bool = True, want_edges: bool = False,
+               sdbg_out: np.ndarray | None = None, copy_bytes: bool = True) -> dict:
+    """Fused k_min build: `.bin` image in, SdBG item stream out (count -> mercy edges -> seq2sdbg on the device).
+    sdbg_out: optional (pinned) uint8 buffer that receives the stream."""
+    L = load()
+    bin_words = np.ascontiguousarray(bin_words, dtype=np.uint32).reshape(-1)
+    a = BuildArgs(k, m, bin_words.ctypes.data if len(bin_words) else None, len(bin_words), n_reads, int(need_mercy),
+                  int(want_edges), sdbg_out.ctypes.data if sdbg_out is not None else None,
+                  sdbg_out.nbytes if sdbg_out is not None else 0)
+    r = BuildResult()
+    _check(L.mhb_build_host(C.byref(a), C.byref(r)))
+    in_place = sdbg_out is not None and C.addressof(r.bytes.contents) == sdbg_out.ctypes.data if r.n_bytes else sdbg_out is not None
+    out = {
+        "n_edge_records": r.n_edge_records, "n_solid": r.n_solid, "n_cand": r.n_cand, "n_mercy": r.n_mercy,
+        "n_sort_items": r.n_sort_items, "n_items": r.n_items, "n_tips": r.n_tips, "n_large_mul": r.n_large_mul,
+        "n_bytes": r.n_bytes, "words_per_tip_label": r.words_per_tip_label,
+        "bucket_table": np.ctypeslib.as_array(r.bucket_table, (NUM_BUCKETS * 4,)).reshape(NUM_BUCKETS, 4).copy(),
+        "w_count": np.array(r.w_count, np.uint64), "ones_in_last": r.ones_in_last,
+        "ms": {k_: getattr(r, f"t_{k_}_ms") for k_ in ("total", "h2d", "count", "mercy", "s2s", "d2h")},
+    }
+    if copy_bytes:
+        out["bytes"] = bytes(np.ctypeslib.as_array(r.bytes, (max(r.n_bytes, 1),))[: r.n_bytes])
+    if not in_place:
+        L.mhb_free(r.bytes)
+    L.mhb_free(r.bucket_table)
+    if want_edges:
+        wpe = r.words_per_edge
+        out["edges"] = np.ctypeslib.as_array(r.edges, (max(r.n_solid, 1) * wpe,))[: r.n_solid * wpe].reshape(-1, wpe).copy()
+        out["cand_ids"] = np.ctypeslib.as_array(r.cand_ids, (max(r.n_cand, 1),))[: r.n_cand].copy()
+        out["counting"] = np.ctypeslib.as_array(r.counting, (65536,)).copy()
+        L.mhb_free(r.edges)
+        L.mhb_free(r.cand_ids)
+        L.mhb_free(r.counting)
     return out
 
 

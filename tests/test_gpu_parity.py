@@ -125,6 +125,40 @@ def test_count_and_sdbg_match_oracle_and_reference(name, k, m, gold):
 
 
 # ------------------------------------------------------------------------------------------------
+# fused build (count -> device mercy edges -> seq2sdbg, nothing leaves HBM in between)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,k,m,gold", golden_cases())
+def test_fused_build_matches_reference(name, k, m, gold):
+    OP, O = _oracle()
+    case = os.path.join(GOLDEN, name)
+    bin_words = np.fromfile(os.path.join(case, "reads.lib.bin"), np.uint32)
+    _, n_reads = F.read_lib_info(os.path.join(case, "reads.lib"))
+    g = lib.build_host(bin_words, n_reads, k, m, need_mercy=True, want_edges=True)
+    assert g["n_solid"] == gold["n_solid"]
+    if gold["n_solid"]:
+        assert F.sha256(g["edges"].tobytes()) == gold["edges_sha256"]
+    reads = OP.load_reads(case)
+    assert F.sha256(reads.bin_bytes(g["cand_ids"])) == gold["cand_sha256"]
+    assert F.sha256(O.counting_text(g["counting"])) == gold["counting_sha256"]
+    # mercy edges: same multiset as the oracle's GenMercyEdges (order is irrelevant downstream)
+    oc = OP.oracle_count(reads, k, m)
+    cand = O.unpack_bin(oc["cand_bytes"], reverse=False)
+    assert g["n_mercy"] == len(O.gen_mercy(oc["edges"], cand, k))
+    assert g["n_items"] == gold["sdbg_items"] and g["n_tips"] == gold["sdbg_tips"]
+    assert g["n_large_mul"] == gold["sdbg_large_mul"]
+    assert F.sha256(lib.sdbg_stream_from_table(g["bucket_table"], g["bytes"])) == gold["sdbg_sha256"]
+
+
+def test_fused_build_into_caller_buffer():
+    case = os.path.join(GOLDEN, "syn150_k27")
+    gold = [c for c in golden_cases() if c.id == "syn150_k27-k27"][0].values[3]
+    bin_words = np.fromfile(os.path.join(case, "reads.lib.bin"), np.uint32)
+    buf = np.zeros(4 << 20, np.uint8)
+    g = lib.build_host(bin_words, 3000, 27, 2, need_mercy=True, sdbg_out=buf, copy_bytes=False)
+    assert F.sha256(lib.sdbg_stream_from_table(g["bucket_table"], buf[: g["n_bytes"]].tobytes())) == gold["sdbg_sha256"]
+
+
+# ------------------------------------------------------------------------------------------------
 # file level: the sub-commands on the reference's on-disk formats (incl. host-side mercy + writers)
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name,k,m,gold", [c for c in golden_cases()
