@@ -395,18 +395,29 @@ extern "C" size_t mhb_tipset_bytes(uint64_t n_tip_edges, uint32_t k) {
   return 16 + tipset_filter_words(n_tip_edges) * 4 + tipset_capacity(n_tip_edges) * (size_t)(count_key_words(k) + 1) * 4;
 }
 
+// a few device words for scalar results, allocated once per device (cudaMallocAsync/cudaFreeAsync per call
+// was measured to cost tens to hundreds of ms when most of HBM is already reserved)
+static int small_scratch(unsigned long long **out) {
+  static unsigned long long *buf[64] = {nullptr};
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return mhb_set_error(MHB_ERR_CUDA, "device index %d out of range", dev);
+  if (!buf[dev]) CK(cudaMalloc((void **)&buf[dev], 256));
+  *out = buf[dev];
+  return MHB_OK;
+}
+
 extern "C" int mhb_count_tip_edges(void *stream, const uint8_t *aux, uint64_t n_solid, uint64_t *n_tip_host) {
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long *d = nullptr;
   *n_tip_host = 0;
   if (n_solid == 0) return MHB_OK;
-  CK(cudaMallocAsync((void **)&d, 8, st));
+  if (int rc = small_scratch(&d)) return rc;
   CK(cudaMemsetAsync(d, 0, 8, st));
   k_count_tips<<<sm_count() * 4, 256, 0, st>>>(aux, n_solid, d);
   CK_LAUNCH();
   CK(cudaMemcpyAsync(n_tip_host, d, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  CK(cudaFreeAsync(d, st));
   return MHB_OK;
 }
 

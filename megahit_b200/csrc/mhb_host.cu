@@ -95,12 +95,10 @@ int index_bin(const uint32_t *bin, uint64_t bin_words, uint64_t n_reads, uint32_
   const uint64_t stride = 1 + div_ceil(L0, 16);
   bool fixed = L0 > 0 && bin_words == n_reads * stride;
   if (fixed) {
-    for (uint64_t r = 0; r < n_reads; ++r) {
-      if (bin[r * stride] != L0) {
-        fixed = false;
-        break;
-      }
-    }
+    int bad = 0;
+#pragma omp parallel for reduction(| : bad) schedule(static)
+    for (long long r = 0; r < (long long)n_reads; ++r) bad |= bin[(uint64_t)r * stride] != L0;
+    fixed = !bad;
   }
   if (fixed) {
     ix->fixed_len = L0;
