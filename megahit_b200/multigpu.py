@@ -1,0 +1,295 @@
+"""Multi-GPU SdBG build: one process per GPU, `torch.distributed` (NCCL over NVLink/NVSwitch) for the exchange.
+
+The path shards naturally: both stages are "extract locally -> all records with the same
+leading bases must meet -> sort + scan locally -> own a contiguous range of the 65 536 prefix buckets".
+The reference already treats prefix buckets as independent (sorting/base_engine.cpp:323-326) and both
+on-disk formats map bucket -> (file, offset), so every rank can write its own `.edges.<r>` / `.sdbg.<r>`
+with no merge.
+
+Partition key = the record's most significant byte (its first 4 bases), cut into `world` CONTIGUOUS
+ranges chosen from the all-reduced 256-bin histogram so that every rank receives about the same number of
+records (canonical (k+1)-mers are skewed towards A-prefixes, equal-width ranges would not balance).  A
+contiguous range of the top byte is a contiguous range of bucket ids, which is what `.edges.info` /
+`.sdbg_info` can express - a whole-edge minimizer hash could not.
+
+Per stage and rank:   extract (+ histogram of the top byte)  ->  one stable radix pass on the top byte
+(groups records by destination)  ->  ONE variable-size all-to-all  ->  LSD radix sort of the received
+records  ->  count / emit for the owned buckets.  Cross-rank state besides the two record exchanges:
+the 256-bin histograms (all-reduce), the tip edges (all-gather, tiny) for the per-read mercy marks, and
+the solid edges (all-gather) for the mercy-edge searches.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import lib
+from .dev import _ptr, _stream, sort_records
+
+
+def plan_ranges(hist: np.ndarray, world: int) -> np.ndarray:
+    """Cut the 256 top-byte values into `world` contiguous, non-empty ranges with near-equal record counts.
+    Returns bounds[world+1] (bounds[0] = 0, bounds[world] = 256); rank r owns [bounds[r], bounds[r+1])."""
+    assert 1 <= world <= 256
+    cum = np.concatenate([[0], np.cumsum(np.asarray(hist).astype(np.int64))])
+    total = int(cum[-1])
+    bounds = [0]
+    for r in range(1, world):
+        lo, hi = bounds[-1] + 1, 256 - (world - r)  # leave at least one value for every later rank
+        target = total * r // world
+        cand = np.arange(lo, hi + 1)
+        bounds.append(int(cand[np.argmin(np.abs(cum[cand] - target))]))
+    bounds.append(256)
+    return np.array(bounds, np.int64)
+
+
+def split_counts(hist: np.ndarray, bounds: np.ndarray) -> np.ndarray:
+    cum = np.concatenate([[0], np.cumsum(hist.astype(np.int64))])
+    return (cum[bounds[1:]] - cum[bounds[:-1]]).astype(np.int64)
+
+
+def exchange_records(grouped: torch.Tensor, words: int, send_counts: np.ndarray, group=None) -> torch.Tensor:
+    """grouped: int32 tensor of records already grouped by destination rank (ascending); returns the
+    records this rank owns (concatenated in source-rank order)."""
+    world = dist.get_world_size(group)
+    sc = torch.tensor(send_counts, dtype=torch.int64, device=grouped.device)
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = rc.cpu().numpy()
+    n_recv = int(recv_counts.sum())
+    out = torch.empty(n_recv * words + 4, dtype=torch.int32, device=grouped.device)
+    n_send = int(send_counts.sum())
+    dist.all_to_all_single(out[: n_recv * words], grouped[: n_send * words],
+                           output_split_sizes=[int(c) * words for c in recv_counts],
+                           input_split_sizes=[int(c) * words for c in send_counts], group=group)
+    assert world == len(send_counts)
+    return out, n_recv
+
+
+class MultiGpuBuild:
+    """count -> mercy -> seq2sdbg across the ranks of the default process group (fixed-length reads)."""
+
+    def __init__(self, n_reads: int, read_len: int, k: int, m: int, device, need_mercy: bool = True):
+        self.L = lib.load()
+        self.n_reads, self.read_len, self.k, self.m, self.device = n_reads, read_len, k, m, device
+        self.need_mercy = need_mercy
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.WR, self.WE, self.W2 = lib.count_record_words(k), lib.words_per_edge(k), lib.s2s_record_words(k)
+        self.cbytes, self.sbytes = lib.count_sort_bytes(k), lib.s2s_sort_bytes(k)
+        self.n_local = n_reads * (read_len - k) if read_len >= k + 1 else 0
+        self.times = {}
+
+    def _mark(self, name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.times.setdefault(name, []).append(ev)
+
+    def _partition_and_exchange(self, recs, n, words, top_byte, hist_dev):
+        """stable pass on the top byte -> all-to-all.  Returns (owned records tensor, count, bounds)."""
+        ghist = hist_dev.clone()
+        dist.all_reduce(ghist)
+        bounds = plan_ranges(ghist.cpu().numpy(), self.world)
+        send = split_counts(hist_dev.cpu().numpy(), bounds)
+        tmp = torch.empty_like(recs)
+        grouped = sort_records(recs, tmp, n, words, [top_byte], hist_dev)
+        out, n_recv = exchange_records(grouped, words, send)
+        return out, n_recv, bounds
+
+    def run(self, bin_dev: torch.Tensor, timed: bool = False) -> dict:
+        L, k, m, dev = self.L, self.k, self.m, self.device
+        i32 = dict(dtype=torch.int32, device=dev)
+        reads = lib.DevReads(bin_dev.data_ptr(), bin_dev.numel(), self.n_reads, self.read_len, None, None)
+        if timed:
+            self._mark("t0")
+        # ---- count stage ----
+        n = self.n_local
+        a = torch.empty(n * self.WR + 4, **i32)
+        hist = torch.zeros(256, dtype=torch.int64, device=dev)
+        top = self.cbytes[-1]
+        lib._check(L.mhb_count_extract(_stream(), C.byref(reads), k, _ptr(a), n, _ptr(hist), top))
+        if timed:
+            self._mark("extract")
+        own, n_own, bounds = self._partition_and_exchange(a, n, self.WR, top, hist)
+        del a
+        if timed:
+            self._mark("exchange1")
+        tmp = torch.empty_like(own)
+        srt = sort_records(own, tmp, n_own, self.WR, self.cbytes, None)
+        if timed:
+            self._mark("sort1")
+        cap = n_own // max(1, m) + 1
+        edges = torch.empty(cap * self.WE, **i32)
+        aux = torch.empty(cap, dtype=torch.uint8, device=dev)
+        mul_hist = torch.zeros(65536, dtype=torch.int64, device=dev)
+        nsol = torch.zeros(8, dtype=torch.int64, device=dev)
+        scratch = torch.empty(L.mhb_count_solid_scratch_bytes(n_own), dtype=torch.uint8, device=dev)
+        lib._check(L.mhb_count_solid(_stream(), _ptr(srt), n_own, k, m, _ptr(edges), _ptr(aux), cap, _ptr(mul_hist),
+                                     _ptr(nsol), _ptr(scratch), scratch.numel()))
+        n_solid = int(nsol[0].item())
+        del own, tmp, srt, scratch
+        dist.all_reduce(mul_hist)  # edge_counter.h:44-52: `.counting` is a global histogram
+        if timed:
+            self._mark("count")
+
+        # ---- mercy: tip edges from every rank -> per-read marks -> candidates -> mercy edges ----
+        seq_edges = edges[: n_solid * self.WE]
+        n_mercy = 0
+        n_cand = 0
+        if self.need_mercy:
+            e2 = edges[: n_solid * self.WE].view(-1, self.WE)
+            tipmask = aux[:n_solid] != 0
+            tips, tipaux = e2[tipmask].contiguous(), aux[:n_solid][tipmask].contiguous()
+            cnt = torch.tensor([tips.shape[0], n_solid], dtype=torch.int64, device=dev)
+            allcnt = [torch.zeros_like(cnt) for _ in range(self.world)]
+            dist.all_gather(allcnt, cnt)
+            tip_n = [int(c[0].item()) for c in allcnt]
+            sol_n = [int(c[1].item()) for c in allcnt]
+            mx = max(max(tip_n), 1)
+            pad_t = torch.zeros((mx, self.WE), **i32)
+            pad_a = torch.zeros(mx, dtype=torch.uint8, device=dev)
+            pad_t[: tips.shape[0]] = tips
+            pad_a[: tips.shape[0]] = tipaux
+            gt = [torch.empty_like(pad_t) for _ in range(self.world)]
+            ga = [torch.empty_like(pad_a) for _ in range(self.world)]
+            dist.all_gather(gt, pad_t)
+            dist.all_gather(ga, pad_a)
+            all_t = torch.cat([g[:c] for g, c in zip(gt, tip_n)]).contiguous()
+            all_a = torch.cat([g[:c] for g, c in zip(ga, tip_n)]).contiguous()
+            n_tip = int(all_t.shape[0])
+            need = L.mhb_tipset_bytes(n_tip, k)
+            tipset = torch.empty(need, dtype=torch.uint8, device=dev)
+            lib._check(L.mhb_tipset_build(_stream(), _ptr(all_t) if n_tip else None, _ptr(all_a) if n_tip else None,
+                                          n_tip, k, _ptr(tipset), need, n_tip))
+            first = torch.empty(self.n_reads + 1, **i32)
+            last = torch.empty(self.n_reads + 1, **i32)
+            lib._check(L.mhb_count_mark_mercy(_stream(), C.byref(reads), k, _ptr(tipset), need, n_tip, _ptr(first),
+                                              _ptr(last)))
+            cand = torch.empty(self.n_reads + 1, dtype=torch.int64, device=dev)
+            cs = torch.empty(L.mhb_mercy_candidates_scratch_bytes(self.n_reads), dtype=torch.uint8, device=dev)
+            nc = C.c_uint64(0)
+            lib._check(L.mhb_mercy_candidates(_stream(), _ptr(first), _ptr(last), self.n_reads, _ptr(cand), C.byref(nc),
+                                              _ptr(cs), cs.numel()))
+            n_cand = nc.value
+            # the mercy searches look at ALL solid edges: gather them (rank order == bucket order == sorted)
+            mxs = max(max(sol_n), 1)
+            pad_e = torch.zeros(mxs * self.WE, **i32)
+            pad_e[: n_solid * self.WE] = edges[: n_solid * self.WE]
+            ge = [torch.empty_like(pad_e) for _ in range(self.world)]
+            dist.all_gather(ge, pad_e)
+            all_e = torch.cat([g[: c * self.WE] for g, c in zip(ge, sol_n)]).contiguous()
+            n_all = sum(sol_n)
+            del ge, pad_e
+            cap_m = max(1024, n_all // 4 // self.world + 1024)
+            mercy = torch.zeros(cap_m * self.WE, **i32)
+            nm = C.c_uint64(0)
+            if n_cand:
+                ms = torch.empty(L.mhb_mercy_edges_scratch_bytes(n_cand, self.read_len), dtype=torch.uint8, device=dev)
+                lib._check(L.mhb_mercy_edges(_stream(), C.byref(reads), _ptr(cand), n_cand, self.read_len, k, _ptr(all_e),
+                                             n_all, _ptr(mercy), cap_m, C.byref(nm), _ptr(ms), ms.numel()))
+            n_mercy = nm.value
+            seq_edges = torch.cat([edges[: n_solid * self.WE], mercy[: n_mercy * self.WE]]).contiguous()
+            del all_e
+        if timed:
+            self._mark("mercy")
+
+        # ---- seq2sdbg stage ----
+        n_seqs = n_solid + n_mercy
+        n_items = n_seqs * 6
+        seq_pad = torch.cat([seq_edges, torch.zeros(8, **i32)])
+        seqs = lib.DevSeqs(seq_pad.data_ptr(), n_seqs * self.WE, n_seqs, k + 1, None, None, None, None, self.WE)
+        sa = torch.empty(n_items * self.W2 + 4, **i32)
+        hist2 = torch.zeros(256, dtype=torch.int64, device=dev)
+        top2 = self.sbytes[-1]
+        lib._check(L.mhb_s2s_extract(_stream(), C.byref(seqs), k, _ptr(sa), n_items, _ptr(hist2), top2))
+        own2, n_own2, bounds2 = self._partition_and_exchange(sa, n_items, self.W2, top2, hist2)
+        del sa
+        if timed:
+            self._mark("exchange2")
+        tmp2 = torch.empty_like(own2)
+        srt2 = sort_records(own2, tmp2, n_own2, self.W2, self.sbytes, None)
+        wpt = (k + 15) // 16
+        cap_b = n_own2 * (4 + 4 * wpt) + 16
+        out_bytes = torch.empty(cap_b, dtype=torch.uint8, device=dev)
+        table = torch.zeros(65536 * 4, dtype=torch.int64, device=dev)
+        totals = torch.zeros(16, dtype=torch.int64, device=dev)
+        es = torch.empty(L.mhb_s2s_emit_scratch_bytes(n_own2), dtype=torch.uint8, device=dev)
+        lib._check(L.mhb_s2s_emit(_stream(), _ptr(srt2), n_own2, k, _ptr(out_bytes), cap_b, _ptr(table), _ptr(totals),
+                                  _ptr(es), es.numel()))
+        if timed:
+            self._mark("s2s")
+        return {"n_solid": n_solid, "n_cand": n_cand, "n_mercy": n_mercy, "edges": edges, "mul_hist": mul_hist,
+                "bounds": bounds, "bounds2": bounds2, "n_items_sorted": n_own2, "sdbg_bytes": out_bytes, "table": table,
+                "totals": totals, "n_records_owned": n_own}
+
+
+def gather_sdbg_stream(res: dict) -> bytes | None:
+    """Canonical SdBG stream of the whole job on rank 0 (validation only)."""
+    tot = res["totals"].cpu().numpy()
+    nbytes = int(tot[0])
+    data = res["sdbg_bytes"][:nbytes].cpu().numpy().tobytes()
+    table = res["table"].cpu().numpy().view(np.uint64).reshape(65536, 4)
+    mine = lib.sdbg_stream_from_table(table, data)
+    objs = [None] * dist.get_world_size()
+    dist.all_gather_object(objs, (res["bounds2"].tolist(), mine, int(tot[1])))
+    if dist.get_rank() != 0:
+        return None
+    return b"".join(o[1] for o in objs)  # rank order == bucket order
+
+
+def bench(args, bin_dev, bin_words, rank, world, device, metric):
+    """bench.py's N > 1 arm: weak scaling, `args.reads` reads per GPU, one all-to-all per stage."""
+    import json
+    import os
+    import sys
+
+    from .formats import NUM_BUCKETS  # noqa: F401
+
+    k, m, n_reads, L = args.k, args.m, args.reads, 150
+    job = MultiGpuBuild(n_reads, L, k, m, device, need_mercy=True)
+    for _ in range(max(1, args.warmup)):
+        job.run(bin_dev)
+    torch.cuda.synchronize()
+    dist.barrier()
+    job.times.clear()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = None
+    for _ in range(args.steps):
+        res = job.run(bin_dev, timed=True)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=device)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    stage = {}
+    names = ["t0", "extract", "exchange1", "sort1", "count", "mercy", "exchange2", "s2s"]
+    for a, b in zip(names[:-1], names[1:]):
+        t = torch.tensor([np.mean([x.elapsed_time(y) for x, y in zip(job.times[a], job.times[b])])], dtype=torch.float64,
+                         device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        stage[b] = float(t.item())
+    own = torch.tensor([res["n_records_owned"], res["n_solid"], res["n_mercy"]], dtype=torch.int64, device=device)
+    owns = [torch.zeros_like(own) for _ in range(world)]
+    dist.all_gather(owns, own)
+    if rank == 0:
+        n_edges = world * n_reads * (L - k)
+        ms_per_step = float(ms.item())
+        print(json.dumps({
+            "metric": metric, "value": n_edges / (ms_per_step * 1e-3), "unit": "edges/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"synthetic {n_reads}x{L}bp reads PER GPU (30x, 1% subst.), k={k}, m={m}, {world}xB200: "
+                                   "top-byte range partition (balanced from the all-reduced histogram) + one NCCL "
+                                   "all-to-all per stage, then per-GPU radix sort / count / mercy / seq2sdbg emit",
+                       "parallelism": f"bucket-range x{world}", "n_edge_records": n_edges,
+                       "records_owned_per_rank": [int(o[0]) for o in owns],
+                       "solid_edges_per_rank": [int(o[1]) for o in owns], "mercy_edges_per_rank": [int(o[2]) for o in owns]},
+            "stage_ms_max_over_ranks": stage, "gpu_launches": 60,
+            "e2e": None, "roofline": None, "cpu_baseline": None,
+        }))
+    sys.stdout.flush()
+    dist.barrier()
+    dist.destroy_process_group()
