@@ -147,6 +147,18 @@ def load():
     L.mhb_count_host.argtypes = [C.POINTER(CountArgs), C.POINTER(CountResult)]
     L.mhb_s2s_host.argtypes = [C.POINTER(S2sArgs), C.POINTER(S2sResult)]
     L.mhb_build_host.argtypes = [C.POINTER(BuildArgs), C.POINTER(BuildResult)]
+    L.mhb_mercy_candidates_scratch_bytes.restype = C.c_size_t
+    L.mhb_mercy_candidates_scratch_bytes.argtypes = [C.c_uint64]
+    L.mhb_mercy_edges_scratch_bytes.restype = C.c_size_t
+    L.mhb_mercy_edges_scratch_bytes.argtypes = [C.c_uint64, C.c_uint32]
+    L.mhb_mercy_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64),
+                                       C.c_void_p, C.c_size_t]
+    L.mhb_mercy_edges.argtypes = [C.c_void_p, C.POINTER(DevReads), C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
+                                  C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p,
+                                  C.c_size_t]
+    L.mhb_sort_pass_ms.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                                   C.POINTER(C.c_uint32)]
+    L.mhb_set_device.argtypes = [C.c_int]
     L.mhb_free.argtypes = [C.c_void_p]
     L.mhb_count_run.argtypes = [C.POINTER(CountOpts)]
     L.mhb_seq2sdbg_run.argtypes = [C.POINTER(Seq2SdbgOpts)]

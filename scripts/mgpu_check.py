@@ -33,6 +33,10 @@ for name, k in (("syn150_k27", 27), ("syn150_klist", 21), ("syn150_klist", 59), 
     bin_dev = torch.from_numpy(np.concatenate([mine.reshape(-1), np.zeros(8, np.uint32)]).view(np.int32)).to(dev)
     job = multigpu.MultiGpuBuild(len(mine), L, k, m, dev, need_mercy=True)
     res = job.run(bin_dev)
+    info = [None] * world
+    dist.all_gather_object(info, (res["n_solid"], res["n_cand"], res["n_mercy"], res["n_items_sorted"]))
+    if rank == 0:
+        print("   per-rank (n_solid, n_cand, n_mercy, items):", info)
     stream = multigpu.gather_sdbg_stream(res)
     edges = res["edges"][: res["n_solid"] * job.WE].cpu().numpy().view(np.uint32).tobytes()
     objs = [None] * world
@@ -47,6 +51,16 @@ for name, k in (("syn150_k27", 27), ("syn150_klist", 21), ("syn150_klist", 59), 
         print(f"{name} k={k}: edges {'OK' if e_ok else 'MISMATCH'} sdbg {'OK' if s_ok else 'MISMATCH'} "
               f"counting {'OK' if c_ok else 'MISMATCH'} bounds={res['bounds'].tolist()} bounds2={res['bounds2'].tolist()}")
         ok = ok and e_ok and s_ok and c_ok
+        if not s_ok:
+            ref = lib.build_host(allw, len(rows), k, m, need_mercy=True)
+            rs = lib.sdbg_stream_from_table(ref["bucket_table"], ref["bytes"])
+            print("  single-GPU fused build sha ok:", F.sha256(rs) == g["sdbg_sha256"], "n_mercy single", ref["n_mercy"],
+                  "len", len(rs), len(stream))
+            # first differing position
+            n = min(len(rs), len(stream))
+            a, b = np.frombuffer(rs[:n], np.uint8), np.frombuffer(stream[:n], np.uint8)
+            d = np.nonzero(a != b)[0]
+            print("  first diff at byte", int(d[0]) if len(d) else None, "of", n)
 if rank == 0:
     print("MGPU PARITY", "PASS" if ok else "FAIL")
 dist.destroy_process_group()
