@@ -921,6 +921,61 @@ __global__ void __launch_bounds__(kScanThreads) k_scan32_apply(const u32 *in, u6
   }
 }
 
+// same three phases for u64 values, in place (exclusive)
+__global__ void __launch_bounds__(kScanThreads) k_scan64_sums(const u64 *in, u64 n, u64 *bsum) {
+  __shared__ u64 s_w[33];
+  const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
+  u64 c = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j)
+    if (base + j < n) c += in[base + j];
+  for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+  if (lane_id() == 0) s_w[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    u64 v = s_w[threadIdx.x];
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan64_apply(u64 *v, u64 n, const u64 *bsum) {
+  __shared__ u64 s_w[33];
+  const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+  const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
+  u64 x[kScanItems], c = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    x[j] = base + j < n ? v[base + j] : 0ull;
+    c += x[j];
+  }
+  u64 inc = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u64 t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= (u32)d) inc += t;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const u64 w = s_w[lane];
+    u64 winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u64 t = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= (u32)d) winc += t;
+    }
+    s_w[lane] = winc - w;
+  }
+  __syncthreads();
+  u64 off = bsum[blockIdx.x] + s_w[warp] + inc - c;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    if (base + j < n) v[base + j] = off;
+    off += x[j];
+  }
+}
+
 // PackEdge (kmer_counter.cpp:32-52): one warp per chunk turns the chunk's solid list into edges
 template <int WR>
 __global__ void __launch_bounds__(256)

@@ -63,13 +63,16 @@ extern "C" uint32_t mhb_count_sort_bytes(uint32_t k, uint8_t *bytes) {
   return n;
 }
 extern "C" uint32_t mhb_s2s_sort_bytes(uint32_t k, uint8_t *bytes) {
-  // whole record is the key (no payload): low 20 flag bits + the k-mer bits; all-zero bytes in
-  // between are skipped
+  // The reference sorts the whole record (seq_to_sdbg.cpp: no payload words).  The low 16 bits
+  // (65535 - multiplicity) only decide which of several records with identical bases and flags comes first, and
+  // the only use of that is "the first record of an (a,b) run carries the largest multiplicity" (:778-785); the
+  // emit kernel takes the run's minimum instead, so those two bytes are not sorted.  Byte 2 holds the flag bits
+  // 16..19 (prev char, non-dollar); all-zero bytes between the flags and the k-mer are skipped.
   const u32 w = s2s_record_words(k), total_bits = 32 * w, key_bits = 2 * k;
   const u32 lo = (total_bits - key_bits) / 8;
   u32 n = 0;
-  for (u32 b = 0; b < 4 * w; ++b)
-    if (b < 3 || b >= lo) bytes[n++] = (uint8_t)b;
+  for (u32 b = 2; b < 4 * w; ++b)
+    if (b == 2 || b >= lo) bytes[n++] = (uint8_t)b;
   return n;
 }
 
@@ -138,9 +141,30 @@ extern "C" int mhb_count_extract(void *stream, const mhb_dev_reads *reads, uint3
 // ------------------------------------------------------------------------------------------------
 // sort
 // ------------------------------------------------------------------------------------------------
+static int sort_cfg() {
+  static int cfg = -1;
+  if (cfg < 0) {
+    const char *e = getenv("MHB_SORT_CFG");
+    cfg = e ? atoi(e) : 0;
+    if (cfg < 0 || cfg > 3) cfg = 0;
+  }
+  return cfg;
+}
+template <int WR, int CFG>
+static u64 sort_tiles_cfg(u64 n) {
+  return (n + SortCfg<WR, CFG>::TILE - 1) / SortCfg<WR, CFG>::TILE;
+}
 template <int WR>
 static u64 sort_tiles(u64 n) {
-  return (n + SortCfg<WR>::TILE - 1) / SortCfg<WR>::TILE;
+  if constexpr (WR <= 3) {
+    switch (sort_cfg()) {
+      case 1: return sort_tiles_cfg<WR, 1>(n);
+      case 2: return sort_tiles_cfg<WR, 2>(n);
+      case 3: return sort_tiles_cfg<WR, 3>(n);
+      default: break;
+    }
+  }
+  return sort_tiles_cfg<WR, 0>(n);
 }
 static u64 sort_num_tiles(u64 n, u32 words) {
 #define M(WW) \
@@ -152,26 +176,44 @@ static u64 sort_num_tiles(u64 n, u32 words) {
 static constexpr size_t kSortHeadBytes = (size_t)(72 + 1) * 256 * 8 /*hist*/ + 256 * 8 /*bin_base*/ + 128 * 4;
 
 extern "C" size_t mhb_sort_workspace_bytes(uint64_t n, uint32_t words) {
-  return kSortHeadBytes + sort_num_tiles(n, words) * 256 * 8 + 256;
+  // sized for the smallest tile of any configuration so that a workspace stays valid across MHB_SORT_CFG values
+  u64 tiles = sort_num_tiles(n, words);
+  if (words <= 3) tiles = (n + 256 * 8 - 1) / (256 * 8) > tiles ? (n + 256 * 8 - 1) / (256 * 8) : tiles;
+  return kSortHeadBytes + tiles * 256 * 8 + 256;
+}
+
+template <int WR, int CFG>
+static int launch_radix_pass_cfg(cudaStream_t st, const u32 *in, u32 *out, u64 n, int byte_idx, const u64 *bin_base,
+                                 u64 *lookback, u32 *tile_counter, u64 *next_hist, int next_byte, u32 epoch) {
+  using C = SortCfg<WR, CFG>;
+  static int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    CK(cudaFuncSetAttribute(k_radix_pass<WR, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_radix_pass<WR, CFG>, C::THREADS, C::SMEM));
+    if (blocks_per_sm < 1) return mhb_set_error(MHB_ERR_CUDA, "radix pass kernel (WR=%d) does not fit an SM", WR);
+    if (getenv("MHB_VERBOSE")) fprintf(stderr, "[mhb] radix pass WR=%d cfg=%d: %d threads x %d rec, %zu B smem, %d CTA/SM\n", WR, CFG, C::THREADS, C::IPT, C::SMEM, blocks_per_sm);
+  }
+  const u64 tiles = sort_tiles_cfg<WR, CFG>(n);
+  u64 grid = (u64)blocks_per_sm * sm_count();
+  if (grid > tiles) grid = tiles;
+  k_radix_pass<WR, CFG><<<(int)grid, C::THREADS, C::SMEM, st>>>(in, out, n, (u32)tiles, byte_idx, bin_base, lookback,
+                                                                 tile_counter, next_hist, next_byte, epoch);
+  CK_LAUNCH();
+  return MHB_OK;
 }
 
 template <int WR>
 static int launch_radix_pass(cudaStream_t st, const u32 *in, u32 *out, u64 n, int byte_idx, const u64 *bin_base,
                              u64 *lookback, u32 *tile_counter, u64 *next_hist, int next_byte, u32 epoch) {
-  using C = SortCfg<WR>;
-  static int blocks_per_sm = 0;
-  if (!blocks_per_sm) {
-    CK(cudaFuncSetAttribute(k_radix_pass<WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_radix_pass<WR>, C::THREADS, C::SMEM));
-    if (blocks_per_sm < 1) return mhb_set_error(MHB_ERR_CUDA, "radix pass kernel (WR=%d) does not fit an SM", WR);
+  if constexpr (WR <= 3) {
+    switch (sort_cfg()) {
+      case 1: return launch_radix_pass_cfg<WR, 1>(st, in, out, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
+      case 2: return launch_radix_pass_cfg<WR, 2>(st, in, out, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
+      case 3: return launch_radix_pass_cfg<WR, 3>(st, in, out, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
+      default: break;
+    }
   }
-  const u64 tiles = sort_tiles<WR>(n);
-  u64 grid = (u64)blocks_per_sm * sm_count();
-  if (grid > tiles) grid = tiles;
-  k_radix_pass<WR><<<(int)grid, C::THREADS, C::SMEM, st>>>(in, out, n, (u32)tiles, byte_idx, bin_base, lookback,
-                                                            tile_counter, next_hist, next_byte, epoch);
-  CK_LAUNCH();
-  return MHB_OK;
+  return launch_radix_pass_cfg<WR, 0>(st, in, out, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
 }
 
 // Per-pass timing: every sort records one event before and after each pass into a small ring, so a
@@ -508,9 +550,21 @@ extern "C" int mhb_s2s_extract(void *stream, const mhb_dev_seqs *seqs, uint32_t 
   return MHB_OK;
 }
 
+// in-place exclusive scan of n u64 values (three phases, no serial chain); total -> *total_dev
+static int scan64(cudaStream_t st, u64 *v, u64 n, u64 *total_dev, u64 *bsum) {
+  const u64 nb = (n + kScanTile - 1) / kScanTile;
+  k_scan64_sums<<<(unsigned)nb, kScanThreads, 0, st>>>(v, n, bsum);
+  CK_LAUNCH();
+  k_scan_u64<<<1, 1024, 0, st>>>(bsum, nb, total_dev);
+  CK_LAUNCH();
+  k_scan64_apply<<<(unsigned)nb, kScanThreads, 0, st>>>(v, n, bsum);
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
 extern "C" size_t mhb_s2s_emit_scratch_bytes(uint64_t n) {
   const u64 nblk = (n + kEmitThreads - 1) / kEmitThreads;
-  return (size_t)nblk * 4 * 8 + (size_t)MHB_NUM_BUCKETS * 4 * 8 + 256;
+  return (size_t)nblk * 4 * 8 + (size_t)MHB_NUM_BUCKETS * 4 * 8 + (size_t)(nblk / kScanTile + 2) * 8 + 512;
 }
 
 extern "C" int mhb_s2s_emit(void *stream, const uint32_t *sorted_records, uint64_t n, uint32_t k, uint8_t *bytes_out,
@@ -532,10 +586,9 @@ extern "C" int mhb_s2s_emit(void *stream, const uint32_t *sorted_records, uint64
   MHB_FOR_WR(M)
 #undef M
   CK_LAUNCH();
-  for (int q = 0; q < 4; ++q) {
-    k_scan_u64<<<1, 1024, 0, st>>>(btot + (u64)q * nblk, nblk, totals + q);
-    CK_LAUNCH();
-  }
+  u64 *bsum = btot + 4 * nblk;
+  for (int q = 0; q < 4; ++q)
+    if (int rc = scan64(st, btot + (u64)q * nblk, nblk, totals + q, bsum)) return rc;
 #define M(WW)                                                                                                    \
   if (W == WW)                                                                                                   \
     k_s2s_write<WW><<<(unsigned)nblk, kEmitThreads, 0, st>>>(sorted_records, n, k, btot, bytes_out, capacity_bytes, \

@@ -374,6 +374,14 @@ int read_contigs(const std::string &path, uint32_t min_len, uint32_t k_from, uin
   *n_read = 0;
   FILE *f = fopen(path.c_str(), "rb");
   if (!f) return MHB_OK;  // the reference opens a missing file as an empty stream
+  {
+    const int c0 = fgetc(f), c1 = fgetc(f);
+    if (c0 == 0x1f && c1 == 0x8b) {
+      fclose(f);
+      return mhb_set_error(MHB_ERR_IO, "%s is gzip-compressed: the GPU seq2sdbg reads plain FASTA contigs only", path.c_str());
+    }
+    rewind(f);
+  }
   const bool extend_loop = k_from < k_to;
   std::string header, seq, line;
   char *buf = nullptr;

@@ -122,11 +122,13 @@ __device__ __forceinline__ void s2s_group(const u32 *__restrict__ recs, u64 n, u
     u64 t = j + 1;
     u32 na = 0xFF, nb = 0xFF;  // (a,b) of the next run in this group, if any
     u32 nx[W];
+    u32 best = cur[W - 1] & 0xFFFFu;  // smallest stored (= largest multiplicity) in the run; the sort ignores it
     while (t < e) {
       ld_rec<W>(recs, t, nx);
       na = s2s_a<W>(nx, k);
       nb = s2s_b<W>(nx);
       if (na != a || nb != b) break;
+      best = min(best, nx[W - 1] & 0xFFFFu);
       ++t;
     }
     const bool more = t < e;
@@ -137,7 +139,7 @@ __device__ __forceinline__ void s2s_group(const u32 *__restrict__ recs, u64 n, u
       u32 last = 0;
       if (a != kSentinel) last = (b == kSentinel) ? 1u : ((!more || na != a || nb == kSentinel) ? 1u : 0u);
       outputed_b |= 1u << b;
-      const u32 mul = 65535u - (cur[W - 1] & 0xFFFFu);
+      const u32 mul = 65535u - best;
       const u32 tip = a == kSentinel ? 1u : 0u;
       const u32 sz = 2u + (mul > 254u ? 2u : 0u) + (tip ? 4u * WPT : 0u);
       if (WRITE) {
@@ -147,7 +149,8 @@ __device__ __forceinline__ void s2s_group(const u32 *__restrict__ recs, u64 n, u
         if (mul > 254u) o[p++] = (uint16_t)mul;
         if (tip) {
           for (u32 q = 0; q < WPT; ++q) {
-            const u32 lw = pick<W>(cur, q);
+            u32 lw = pick<W>(cur, q);
+            if (q == (u32)W - 1) lw = (lw & 0xFFFF0000u) | best;  // label = raw words of the run's first sorted record
             o[p++] = (uint16_t)(lw & 0xFFFFu);
             o[p++] = (uint16_t)(lw >> 16);
           }

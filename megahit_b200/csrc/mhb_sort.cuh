@@ -16,14 +16,17 @@
 namespace mhb {
 
 
-template <int WR>
+// Tile geometry.  CFG selects a (threads, records per thread, CTAs per SM) variant; 0 is the default, the others
+// exist for tuning runs (env MHB_SORT_CFG) and are only instantiated for the narrow records.
+template <int WR, int CFG = 0>
 struct SortCfg {
-  // tile = THREADS * IPT records; sized so that two CTAs fit in one SM's shared memory
-  static constexpr int THREADS = 384;
-  static constexpr int IPT = WR <= 2 ? 18 : (WR <= 3 ? 12 : (WR <= 4 ? 10 : (WR <= 6 ? 6 : (WR <= 9 ? 4 : 2))));
+  static constexpr int THREADS = CFG == 1 ? 256 : (CFG == 2 ? 256 : (CFG == 3 ? 512 : 384));
+  static constexpr int MIN_BLOCKS = CFG == 1 ? 3 : (CFG == 2 ? 4 : 2);
+  static constexpr int IPT_NARROW = CFG == 1 ? 18 : (CFG == 2 ? 12 : (CFG == 3 ? 14 : 18));
+  static constexpr int IPT = WR <= 2 ? IPT_NARROW
+                                     : (WR <= 3 ? (IPT_NARROW * 2) / 3 : (WR <= 4 ? 10 : (WR <= 6 ? 6 : (WR <= 9 ? 4 : 2))));
   static constexpr int TILE = THREADS * IPT;
   static constexpr int NW = THREADS / 32;
-  static constexpr int MIN_BLOCKS = 2;
   static constexpr size_t SMEM = (size_t)(NW * 256 + 256 + 256 + 8) * 4 + 256 * 8 + (size_t)TILE * WR * 4;
 };
 
@@ -70,12 +73,12 @@ __device__ __forceinline__ u32 rec_digit(const u32 (&r)[WR], u32 widx, u32 bsel)
 
 static constexpr int kLbWindow = 4;  // look-back descriptors fetched per round trip
 
-template <int WR>
-__global__ void __launch_bounds__(SortCfg<WR>::THREADS, SortCfg<WR>::MIN_BLOCKS)
+template <int WR, int CFG = 0>
+__global__ void __launch_bounds__(SortCfg<WR, CFG>::THREADS, SortCfg<WR, CFG>::MIN_BLOCKS)
     k_radix_pass(const u32 *__restrict__ in, u32 *__restrict__ out, u64 n, u32 num_tiles, int byte_idx,
                  const u64 *__restrict__ bin_base, u64 *lookback, u32 *tile_counter, u64 *next_hist,
                  int next_byte, u32 epoch) {
-  using C = SortCfg<WR>;
+  using C = SortCfg<WR, CFG>;
   constexpr int THREADS = C::THREADS, IPT = C::IPT, TILE = C::TILE, NW = C::NW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64 *s_glob = reinterpret_cast<u64 *>(smem_raw);          // 256: global offset - local bin start
