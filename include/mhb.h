@@ -169,8 +169,8 @@ int mhb_s2s_extract(void *stream, const mhb_dev_seqs *seqs, uint32_t k, uint32_t
  *   bytes_out     capacity_bytes; the variable-length item stream in sorted (= bucket) order
  *   bucket_table  uint64[65536*4] device: per bucket {byte offset, #items, #tips, #large_mul};
  *   totals        uint64[16] device: [0]=bytes [1]=items [2]=tips [3]=large_mul [4..12]=w counts [13]=ones in last
- *   scratch       mhb_s2s_emit_scratch_bytes(n) */
-size_t mhb_s2s_emit_scratch_bytes(uint64_t n);
+ *   scratch       mhb_s2s_emit_scratch_bytes(n, k) */
+size_t mhb_s2s_emit_scratch_bytes(uint64_t n, uint32_t k);
 int mhb_s2s_emit(void *stream, const uint32_t *sorted_records, uint64_t n, uint32_t k, uint8_t *bytes_out,
                  uint64_t capacity_bytes, uint64_t *bucket_table, uint64_t *totals, void *scratch,
                  size_t scratch_bytes);

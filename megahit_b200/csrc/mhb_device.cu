@@ -540,6 +540,17 @@ extern "C" int mhb_s2s_extract(void *stream, const mhb_dev_seqs *seqs, uint32_t 
   cudaStream_t st = (cudaStream_t)stream;
   const SeqsView sv = make_seqs_view(seqs);
   const u32 W = s2s_record_words(k);
+  if (seqs->fixed_len == k + 1 && seqs->fixed_stride && !seqs->mult && k + 1 <= 32 && k + 1 > 16 &&
+      n_items == seqs->n_seqs * 6) {
+    // `.edges` records of short (k+1)-mers: one thread per edge, 64-bit arithmetic
+    u64 ge = (seqs->n_seqs + 255) / 256;
+    if (ge > (u64)sm_count() * 32) ge = (u64)sm_count() * 32;
+    if (W == 2) k_s2s_extract_edges<2><<<(unsigned)ge, 256, 0, st>>>(seqs->words, seqs->n_seqs, seqs->fixed_stride, k, records, hist256, hist_byte);
+    else if (W == 3) k_s2s_extract_edges<3><<<(unsigned)ge, 256, 0, st>>>(seqs->words, seqs->n_seqs, seqs->fixed_stride, k, records, hist256, hist_byte);
+    else return mhb_set_error(MHB_ERR_ARG, "internal: unexpected record width %u", W);
+    CK_LAUNCH();
+    return MHB_OK;
+  }
   u64 g = (n_items + 255) / 256;
   if (g > (u64)sm_count() * 32) g = (u64)sm_count() * 32;
 #define M(WW) \
@@ -550,6 +561,7 @@ extern "C" int mhb_s2s_extract(void *stream, const mhb_dev_seqs *seqs, uint32_t 
   return MHB_OK;
 }
 
+static int scan32(cudaStream_t st, const u32 *in, u64 n, u64 *out, u64 *total_dev, u64 *bsum);
 // in-place exclusive scan of n u64 values (three phases, no serial chain); total -> *total_dev
 static int scan64(cudaStream_t st, u64 *v, u64 n, u64 *total_dev, u64 *bsum) {
   const u64 nb = (n + kScanTile - 1) / kScanTile;
@@ -562,9 +574,29 @@ static int scan64(cudaStream_t st, u64 *v, u64 n, u64 *total_dev, u64 *bsum) {
   return MHB_OK;
 }
 
-extern "C" size_t mhb_s2s_emit_scratch_bytes(uint64_t n) {
-  const u64 nblk = (n + kEmitThreads - 1) / kEmitThreads;
-  return (size_t)nblk * 4 * 8 + (size_t)MHB_NUM_BUCKETS * 4 * 8 + (size_t)(nblk / kScanTile + 2) * 8 + 512;
+static u64 emit2_chunks(u64 n, u32 W) {
+#define M(WW) \
+  if (W == WW) return (n + emit2_chunk(WW) - 1) / emit2_chunk(WW);
+  MHB_FOR_WR(M)
+#undef M
+  return 0;
+}
+static u32 emit2_chunk_records(u32 W) {
+#define M(WW) \
+  if (W == WW) return (u32)emit2_chunk(WW);
+  MHB_FOR_WR(M)
+#undef M
+  return 0;
+}
+
+extern "C" size_t mhb_s2s_emit_scratch_bytes(uint64_t n, uint32_t k) {
+  const u32 W = s2s_record_words(k);
+  const u64 nc = emit2_chunks(n, W);
+  const u64 nblk = (n + kEmitThreads - 1) / kEmitThreads;  // v1 layout (MHB_EMIT_V1)
+  const size_t v1 = (size_t)nblk * 4 * 8 + (size_t)MHB_NUM_BUCKETS * 4 * 8 + (size_t)(nblk / kScanTile + 2) * 8 + 512;
+  const size_t v2 = (size_t)MHB_NUM_BUCKETS * (4 * 8 + 5 * 4) + (size_t)nc * 4 * (4 + 8) + (size_t)(nc / kScanTile + 2) * 8 +
+                    (size_t)nc * emit2_chunk_records(W) * emit2_max_item_bytes(k) + 4096;
+  return v1 > v2 ? v1 : v2;
 }
 
 extern "C" int mhb_s2s_emit(void *stream, const uint32_t *sorted_records, uint64_t n, uint32_t k, uint8_t *bytes_out,
@@ -575,12 +607,59 @@ extern "C" int mhb_s2s_emit(void *stream, const uint32_t *sorted_records, uint64
   CK(cudaMemsetAsync(totals, 0, 16 * 8, st));
   CK(cudaMemsetAsync(bucket_table, 0, (size_t)MHB_NUM_BUCKETS * 4 * 8, st));
   if (n == 0) return MHB_OK;
-  if (scratch_bytes < mhb_s2s_emit_scratch_bytes(n)) return mhb_set_error(MHB_ERR_ARG, "emit scratch too small");
+  if (scratch_bytes < mhb_s2s_emit_scratch_bytes(n, k)) return mhb_set_error(MHB_ERR_ARG, "emit scratch too small");
+  const u32 W = s2s_record_words(k);
+  static const bool use_v1 = getenv("MHB_EMIT_V1") != nullptr;
+  if (!use_v1) {
+    const u64 nc = emit2_chunks(n, W);
+    if (nc >= (1ull << 32)) return mhb_set_error(MHB_ERR_ARG, "too many records for one emit launch");
+    const u32 chrec = emit2_chunk_records(W), maxb = emit2_max_item_bytes(k);
+    char *p = (char *)scratch;
+    u64 *bucket_start = (u64 *)p;
+    p += (size_t)MHB_NUM_BUCKETS * 4 * 8;
+    u32 *bucket_local = (u32 *)p;
+    p += (size_t)MHB_NUM_BUCKETS * 5 * 4;
+    u64 *chunk_off = (u64 *)p;
+    p += (size_t)nc * 4 * 8;
+    u64 *bsum = (u64 *)p;
+    p += (size_t)(nc / kScanTile + 2) * 8;
+    u32 *chunk_tot = (u32 *)p;
+    p += ((size_t)nc * 4 * 4 + 255) & ~(size_t)255;
+    uint8_t *tmp = (uint8_t *)p;
+    CK(cudaMemsetAsync(bucket_local, 0xFF, (size_t)MHB_NUM_BUCKETS * 5 * 4, st));
+#define M(WW)                                                                                                       \
+  if (W == WW) {                                                                                                    \
+    const size_t smem = (size_t)kEmit2Warps * emit2_slots(WW) * WW * 4;                                             \
+    static int bps = 0;                                                                                             \
+    if (!bps) {                                                                                                     \
+      CK(cudaFuncSetAttribute(k_s2s_judge<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_s2s_judge<WW>, kEmit2Warps * 32, smem));             \
+      if (bps < 1) bps = 1;                                                                                         \
+    }                                                                                                               \
+    u64 grid = (u64)sm_count() * bps;                                                                               \
+    if (grid > (nc + kEmit2Warps - 1) / kEmit2Warps) grid = (nc + kEmit2Warps - 1) / kEmit2Warps;                   \
+    k_s2s_judge<WW><<<(unsigned)grid, kEmit2Warps * 32, smem, st>>>(sorted_records, n, k, (u32)nc, tmp, chunk_tot,   \
+                                                                   bucket_local, totals);                          \
+  }
+    MHB_FOR_WR(M)
+#undef M
+    CK_LAUNCH();
+    for (int q = 0; q < 4; ++q)
+      if (int rc = scan32(st, chunk_tot + (u64)q * nc, nc, chunk_off + (u64)q * nc, totals + q, bsum)) return rc;
+    u64 gg = (nc + 7) / 8;
+    if (gg > (u64)sm_count() * 16) gg = (u64)sm_count() * 16;
+    k_s2s_gather<<<(unsigned)gg, 256, 0, st>>>(tmp, chrec, maxb, (u32)nc, chunk_tot, chunk_off, bytes_out, capacity_bytes);
+    CK_LAUNCH();
+    k_bucket_starts<<<64, 256, 0, st>>>(bucket_local, chunk_off, nc, bucket_start);
+    CK_LAUNCH();
+    k_bucket_finalize<<<64, 256, 0, st>>>(bucket_start, totals, bucket_table);
+    CK_LAUNCH();
+    return MHB_OK;
+  }
   const u64 nblk = (n + kEmitThreads - 1) / kEmitThreads;
   u64 *bucket_start = (u64 *)scratch;
   u64 *btot = bucket_start + (size_t)MHB_NUM_BUCKETS * 4;
   CK(cudaMemsetAsync(bucket_start, 0xFF, (size_t)MHB_NUM_BUCKETS * 4 * 8, st));
-  const u32 W = s2s_record_words(k);
 #define M(WW) \
   if (W == WW) k_s2s_size<WW><<<(unsigned)nblk, kEmitThreads, 0, st>>>(sorted_records, n, k, btot);
   MHB_FOR_WR(M)

@@ -325,7 +325,7 @@ extern "C" int mhb_s2s_host(const mhb_s2s_args *args, mhb_s2s_result *res) {
   uint8_t sort_bytes[72];
   const uint32_t n_sort = mhb_s2s_sort_bytes(k, sort_bytes);
   const size_t ws_bytes = mhb_sort_workspace_bytes(n_items, W);
-  const size_t scratch_bytes = mhb_s2s_emit_scratch_bytes(n_items);
+  const size_t scratch_bytes = mhb_s2s_emit_scratch_bytes(n_items, k);
   // worst case bytes per sort item: 2 + 2 + 4*WPT (every item a large-multiplicity tip)
   const uint64_t cap_bytes = n_items * (4ull + 4ull * res->words_per_tip_label) + 16;
   size_t need = Arena::pad(n_words * 4 + 64) + Arena::pad((ns + 1) * 8) * 2 + Arena::pad((ns + 1) * 4) +
@@ -534,7 +534,7 @@ extern "C" int mhb_build_host(const mhb_build_args *args, mhb_build_result *res)
   const uint64_t n_seqs = n_solid + n_mercy;
   const uint64_t n_items = n_seqs * 6;  // 2 strands x (k+1 - k + 2)
   res->n_sort_items = n_items;
-  const size_t s_ws = mhb_sort_workspace_bytes(n_items, W2), s_scr = mhb_s2s_emit_scratch_bytes(n_items);
+  const size_t s_ws = mhb_sort_workspace_bytes(n_items, W2), s_scr = mhb_s2s_emit_scratch_bytes(n_items, k);
   const uint64_t cap_bytes = n_items * (4ull + 4ull * WPT) + 16;
   const size_t s2s_work = 2 * Arena::pad((size_t)n_items * W2 * 4 + 16) + Arena::pad(s_ws) + Arena::pad(s_scr) + Arena::pad(cap_bytes);
   char *sw = work;

@@ -22,8 +22,7 @@ static constexpr u32 kSentinel = 4;  // kmer_counter.h:48 kSentinelValue
 template <int W, int WR>
 MHB_HD void make_count_record(const u32 *s, u32 nwords, u32 L, u32 k, u32 q, u32 (&rec)[WR], u32 &strand) {
   const u32 K1 = k + 1;
-  const u32 prev_pkg = (q + K1 < L) ? base_at(s, q + K1) : kSentinel;
-  const u32 next_pkg = (q > 0) ? base_at(s, q - 1) : kSentinel;
+  u32 prev_pkg, next_pkg;
   bool st;
   if constexpr (W == 2) {
     // 17 <= k+1 <= 32: the whole edge fits one 64-bit word -- same arithmetic as the generic path below
@@ -31,6 +30,12 @@ MHB_HD void make_count_record(const u32 *s, u32 nwords, u32 L, u32 k, u32 q, u32
     const u32 x0 = s[w0];
     const u32 x1 = (w0 + 1 < nwords) ? s[w0 + 1] : 0u;
     const u32 x2 = (w0 + 2 < nwords) ? s[w0 + 2] : 0u;
+    // neighbours from the words already in registers: base q+K1 lives in word w0+1 or w0+2, base q-1 in w0 or w0-1
+    const u32 pi = q + K1;
+    const u32 pw = ((pi >> 4) == w0 + 1) ? x1 : x2;
+    prev_pkg = (pi < L) ? ((pw >> (30 - 2 * (pi & 15))) & 3u) : kSentinel;
+    const u32 nwd = (q & 15) ? x0 : (q ? s[w0 - 1] : 0u);
+    next_pkg = (q > 0) ? ((nwd >> (30 - 2 * ((q - 1) & 15))) & 3u) : kSentinel;
     const u32 T = 64u - 2u * K1;  // zero bits below the edge, 0..30
     const u64 S = ((((u64)fshl(x0, x1, sh) << 32) | fshl(x1, x2, sh)) >> T) << T;
     const u64 B = ((~S) >> T) << T;                                      // complement(S)
@@ -41,6 +46,8 @@ MHB_HD void make_count_record(const u32 *s, u32 nwords, u32 L, u32 k, u32 q, u32
     rec[1] = (u32)key;
     if constexpr (WR == 3) rec[2] = 0u;
   } else {
+    prev_pkg = (q + K1 < L) ? base_at(s, q + K1) : kSentinel;
+    next_pkg = (q > 0) ? base_at(s, q - 1) : kSentinel;
     u32 S[W], A[W], B[W];
     load_sub<W>(s, nwords, q, K1, S);
     reverse_sub<W>(S, K1, A);

@@ -64,6 +64,63 @@ __global__ void __launch_bounds__(256)
       if (s_hist[i]) atomicAdd((unsigned long long *)&hist[i], (unsigned long long)s_hist[i]);
 }
 
+// S-extract fast path: the sequences are `.edges` records of (k+1)-mers with k+1 <= 32 (the k_min case).  One
+// thread turns one edge into its six sort items (both strands x offsets 0,1,2) with 64-bit arithmetic; strand 1
+// is strand 0 of the reverse complement (seq_to_sdbg.cpp:672-690).  Item order matches k_s2s_extract.
+template <int W>
+__global__ void __launch_bounds__(256)
+    k_s2s_extract_edges(const u32 *__restrict__ edges, u64 n_edges, u32 we, u32 k, u32 *__restrict__ records, u64 *hist,
+                        int hist_byte) {
+  __shared__ u32 s_hist[256];
+  __shared__ __align__(16) u32 s_out[256 * 6 * W];  // the CTA's 1536 items, written out with coalesced 16 B stores
+  for (int i = threadIdx.x; i < 256; i += 256) s_hist[i] = 0;
+  __syncthreads();
+  const u32 K1 = k + 1, T = 64u - 2u * K1;
+  for (u64 base = (u64)blockIdx.x * 256; base < n_edges; base += (u64)gridDim.x * 256) {
+    const u64 e = base + threadIdx.x;
+    if (e < n_edges) {
+      const u32 *ep = edges + e * we;
+      const u32 e1 = we > 1 ? ep[1] : 0u;
+      const u64 X0 = ((((u64)ep[0] << 32) | e1) >> T) << T;
+      const u32 mult = ep[we - 1] & 0xFFFFu;
+      const u64 R = ((u64)rev2((u32)X0) << 32) | rev2((u32)(X0 >> 32));  // reversed, right-aligned
+      const u64 X1 = ((~R) << T);                                           // reverse complement, left-aligned
+#pragma unroll
+      for (int strand = 0; strand < 2; ++strand) {
+        const u64 X = strand ? X1 : X0;
+#pragma unroll
+        for (int off = 0; off < 3; ++off) {
+          const u32 nc = off == 2 ? k - 1 : k;
+          const u64 chars = ((X << (2 * off)) >> (64 - 2 * nc)) << (64 - 2 * nc);
+          const u32 prev = off == 0 ? kSentinel : (u32)(X >> (64 - 2 * off)) & 3u;
+          const u32 low = ((off == 2 ? 0u : 1u) << 19) | (prev << 16) | (65535u - (off == 1 ? mult : 0u));
+          u32 rec[W];
+          rec[0] = (u32)(chars >> 32);
+          if constexpr (W >= 2) rec[1] = (u32)chars;
+#pragma unroll
+          for (int j = 2; j < W; ++j) rec[j] = 0u;
+          rec[W - 1] |= low;
+          u32 *dst = s_out + (threadIdx.x * 6 + strand * 3 + off) * W;
+#pragma unroll
+          for (int j = 0; j < W; ++j) dst[j] = rec[j];
+          if (hist) atomicAdd(&s_hist[rec_byte<W>(rec, hist_byte)], 1u);
+        }
+      }
+    }
+    __syncthreads();
+    const u64 left = n_edges - base;
+    const u32 nw = (u32)(left < 256 ? left : 256) * 6 * W;  // words this CTA produced; base*6*W*4 is 16 B aligned
+    uint4 *gdst = reinterpret_cast<uint4 *>(records + base * 6 * W);
+    const uint4 *ssrc = reinterpret_cast<const uint4 *>(s_out);
+    for (u32 x = threadIdx.x; x < nw / 4; x += 256) gdst[x] = ssrc[x];
+    for (u32 x = (nw & ~3u) + threadIdx.x; x < nw; x += 256) records[base * 6 * W + x] = s_out[x];
+    __syncthreads();
+  }
+  if (hist)
+    for (int i = threadIdx.x; i < 256; i += 256)
+      if (s_hist[i]) atomicAdd((unsigned long long *)&hist[i], (unsigned long long)s_hist[i]);
+}
+
 // ---- record field access (seq_to_sdbg.cpp:71-97) ----
 template <int W>
 __device__ __forceinline__ u32 s2s_a(const u32 (&r)[W], u32 k) {
@@ -282,6 +339,246 @@ __global__ void k_bucket_finalize(const u64 *bucket_start, const u64 *totals, u6
     o[1] = end[1] - s[1];
     o[2] = end[2] - s[2];
     o[3] = end[3] - s[3];
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// S-emit v2 (A10): shared-memory staged, lane-blocked, no serial chain.
+//
+// A warp stages a chunk of 32*IPL sorted records (+ one record before, + a halo after) in shared memory with
+// coalesced loads; lane l owns the (k-1)-mer groups whose first record lies in its IPL records and walks them
+// out of shared memory (records beyond the halo come from global memory, so arbitrarily long groups stay
+// correct).  Two walks: sizes -> warp scan -> items written to the chunk's compact slot of a scratch stream.
+// Chunk totals are scanned (3-phase) and k_s2s_gather copies every chunk's bytes to its final offset.
+// ------------------------------------------------------------------------------------------------
+static constexpr int kEmit2Warps = 8, kEmit2Halo = 32;
+__host__ __device__ constexpr int emit2_ipl(int w) { return w <= 4 ? 8 : (w <= 8 ? 4 : 2); }
+__host__ __device__ constexpr int emit2_chunk(int w) { return 32 * emit2_ipl(w); }
+__host__ __device__ constexpr int emit2_slots(int w) {  // staged record slots incl. one pad slot per IPL records
+  return (1 + emit2_chunk(w) + kEmit2Halo) + (1 + emit2_chunk(w) + kEmit2Halo) / emit2_ipl(w) + 1;
+}
+__host__ __device__ inline u32 emit2_max_item_bytes(u32 k) { return 4u + 4u * words_per_tip_label(k); }
+
+template <int W>
+struct StagedRecs {
+  const u32 *smem;  // staged window
+  const u32 *glob;  // all records
+  u64 a0;           // global index of staged slot 0
+  u32 ns;           // staged records
+  __device__ __forceinline__ void get(u64 t, u32 (&r)[W]) const {
+    const u64 slot = t - a0;
+    if (slot < ns) {
+      const u32 *p = smem + ((u32)slot + (u32)slot / emit2_ipl(W)) * W;
+#pragma unroll
+      for (int j = 0; j < W; ++j) r[j] = p[j];
+    } else {
+      ld_rec<W>(glob, t, r);
+    }
+  }
+};
+
+// walk the group starting at record i; returns its end.  WRITE: append item bytes at out + acc.bytes.
+template <int W, bool WRITE>
+__device__ __forceinline__ u64 s2s_group2(const StagedRecs<W> &sr, u64 n, u64 i, u32 k, EmitAcc &acc, uint8_t *out,
+                                          u32 *w_count, u32 &ones) {
+  const u32 WPT = words_per_tip_label(k);
+  u32 r0[W], x[W];
+  sr.get(i, r0);
+  u32 hsa = 0, hsb = 0;
+  u64 e = i;
+  for (u64 j = i; j < n; ++j) {  // :724-738
+    sr.get(j, x);
+    if (j > i && diff_km1<W>(r0, x, k)) break;
+    const u32 a = s2s_a<W>(x, k), b = s2s_b<W>(x);
+    if (a != kSentinel && b != kSentinel) {
+      hsa |= 1u << a;
+      hsb |= 1u << b;
+    }
+    e = j + 1;
+  }
+  u32 outputed_b = 0;
+  u64 j = i;
+  u32 cur[W];
+#pragma unroll
+  for (int q = 0; q < W; ++q) cur[q] = r0[q];
+  while (j < e) {  // :740-786
+    const u32 a = s2s_a<W>(cur, k), b = s2s_b<W>(cur);
+    u64 t = j + 1;
+    u32 na = 0xFF, nb = 0xFF;
+    u32 nx[W];
+    u32 best = cur[W - 1] & 0xFFFFu;
+    while (t < e) {
+      sr.get(t, nx);
+      na = s2s_a<W>(nx, k);
+      nb = s2s_b<W>(nx);
+      if (na != a || nb != b) break;
+      best = min(best, nx[W - 1] & 0xFFFFu);
+      ++t;
+    }
+    const bool more = t < e;
+    const bool skip = (a == kSentinel && ((hsb >> b) & 1u)) || (b == kSentinel && ((hsa >> a) & 1u));
+    if (!skip) {
+      const u32 w = (b == kSentinel) ? 0u : (((outputed_b >> b) & 1u) ? b + 5u : b + 1u);
+      u32 last = 0;
+      if (a != kSentinel) last = (b == kSentinel) ? 1u : ((!more || na != a || nb == kSentinel) ? 1u : 0u);
+      outputed_b |= 1u << b;
+      const u32 mul = 65535u - best;
+      const u32 tip = a == kSentinel ? 1u : 0u;
+      const u32 sz = 2u + (mul > 254u ? 2u : 0u) + (tip ? 4u * WPT : 0u);
+      if (WRITE) {
+        uint16_t *o = reinterpret_cast<uint16_t *>(out + acc.bytes);
+        o[0] = (uint16_t)((w | (last << 4) | (tip << 5)) | ((mul > 255u ? 255u : mul) << 8));
+        u32 p = 1;
+        if (mul > 254u) o[p++] = (uint16_t)mul;
+        if (tip) {
+          for (u32 q = 0; q < WPT; ++q) {
+            u32 lw = pick<W>(cur, q);
+            if (q == (u32)W - 1) lw = (lw & 0xFFFF0000u) | best;
+            o[p++] = (uint16_t)(lw & 0xFFFFu);
+            o[p++] = (uint16_t)(lw >> 16);
+          }
+        }
+        atomicAdd(&w_count[w], 1u);
+        ones += last;
+      }
+      acc.bytes += sz;
+      acc.items += 1;
+      acc.tips += tip;
+      acc.large += mul > 254u ? 1u : 0u;
+    }
+    j = t;
+    if (more) {
+#pragma unroll
+      for (int q = 0; q < W; ++q) cur[q] = nx[q];
+    }
+  }
+  return e;
+}
+
+template <int W>
+__global__ void __launch_bounds__(kEmit2Warps * 32)
+    k_s2s_judge(const u32 *__restrict__ recs, u64 n, u32 k, u32 n_chunks, uint8_t *__restrict__ tmp,
+                u32 *__restrict__ chunk_tot /*4 planes of n_chunks*/, u32 *__restrict__ bucket_local /*65536 x 5*/,
+                u64 *totals) {
+  constexpr int IPL = emit2_ipl(W), CH = emit2_chunk(W);
+  extern __shared__ __align__(16) u32 smem_e[];
+  __shared__ u32 s_w[9];
+  const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+  u32 *my = smem_e + (size_t)warp * emit2_slots(W) * W;
+  if (threadIdx.x < 9) s_w[threadIdx.x] = 0;
+  __syncthreads();
+  const u32 maxb = emit2_max_item_bytes(k);
+  u32 ones = 0;
+  for (u64 chunk = (u64)blockIdx.x * kEmit2Warps + warp; chunk < n_chunks; chunk += (u64)gridDim.x * kEmit2Warps) {
+    const u64 a = chunk * CH;
+    const u64 b = a + CH < n ? a + CH : n;
+    const u64 a0 = a > 0 ? a - 1 : 0;
+    const u64 hi = a + CH + kEmit2Halo < n ? a + CH + kEmit2Halo : n;
+    const u32 ns = (u32)(hi - a0);
+    __syncwarp();
+    for (u32 t = lane; t < ns; t += 32) {
+      u32 r[W];
+      ld_rec<W>(recs, a0 + t, r);
+      u32 *dst = my + (t + t / IPL) * W;
+#pragma unroll
+      for (int j = 0; j < W; ++j) dst[j] = r[j];
+    }
+    __syncwarp();
+    const StagedRecs<W> sr{my, recs, a0, ns};
+
+    // this lane's first group head (if any) in [lo, hi_l)
+    const u64 lo = a + (u64)lane * IPL;
+    const u64 hi_l = lo + IPL < b ? lo + IPL : b;
+    u64 first = hi_l;
+    if (lo < b) {
+      u32 p[W], c[W];
+      if (lo > 0) sr.get(lo - 1, p);
+      for (u64 t = lo; t < hi_l; ++t) {
+        sr.get(t, c);
+        if (t == 0 || diff_km1<W>(p, c, k)) {
+          first = t;
+          break;
+        }
+#pragma unroll
+        for (int q = 0; q < W; ++q) p[q] = c[q];
+      }
+    }
+    // walk 1: sizes
+    EmitAcc acc = {0, 0, 0, 0};
+    u32 dummy = 0;
+    for (u64 t = first; t < hi_l;) t = s2s_group2<W, false>(sr, n, t, k, acc, nullptr, nullptr, dummy);
+    // lane prefixes + chunk totals
+    u32 inc[4] = {acc.bytes, acc.items, acc.tips, acc.large};
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const u32 v = __shfl_up_sync(0xffffffffu, inc[q], d);
+        if (lane >= (u32)d) inc[q] += v;
+      }
+    }
+    if (lane == 31) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) chunk_tot[(u64)q * n_chunks + chunk] = inc[q];
+    }
+    const u32 pre[4] = {inc[0] - acc.bytes, inc[1] - acc.items, inc[2] - acc.tips, inc[3] - acc.large};
+    // walk 2: write items into the chunk's compact slot; note where each bucket starts
+    uint8_t *out = tmp + chunk * (u64)CH * maxb + pre[0];
+    EmitAcc wacc = {0, 0, 0, 0};
+    for (u64 t = first; t < hi_l;) {
+      u32 h[W], pv[W];
+      sr.get(t, h);
+      const u32 bucket = h[0] >> 16;
+      bool new_bucket = t == 0;
+      if (t > 0) {
+        sr.get(t - 1, pv);
+        new_bucket = (pv[0] >> 16) != bucket;
+      }
+      if (new_bucket) {
+        u32 *bl = bucket_local + 5ull * bucket;
+        bl[0] = (u32)chunk;
+        bl[1] = pre[0] + wacc.bytes;
+        bl[2] = pre[1] + wacc.items;
+        bl[3] = pre[2] + wacc.tips;
+        bl[4] = pre[3] + wacc.large;
+      }
+      t = s2s_group2<W, true>(sr, n, t, k, wacc, out, s_w, ones);
+    }
+  }
+  for (int d = 16; d; d >>= 1) ones += __shfl_xor_sync(0xffffffffu, ones, d);
+  if (lane == 0 && ones) atomicAdd((unsigned long long *)&totals[13], (unsigned long long)ones);
+  __syncthreads();
+  if (threadIdx.x < 9 && s_w[threadIdx.x])
+    atomicAdd((unsigned long long *)&totals[4 + threadIdx.x], (unsigned long long)s_w[threadIdx.x]);
+}
+
+// copy every chunk's compact bytes to their final position (all sizes and offsets are even)
+__global__ void __launch_bounds__(256)
+    k_s2s_gather(const uint8_t *__restrict__ tmp, u32 chunk_records, u32 maxb, u32 n_chunks,
+                 const u32 *__restrict__ chunk_bytes, const u64 *__restrict__ chunk_off, uint8_t *__restrict__ out,
+                 u64 capacity) {
+  const u32 lane = lane_id();
+  for (u64 chunk = (u64)blockIdx.x * 8 + (threadIdx.x >> 5); chunk < n_chunks; chunk += (u64)gridDim.x * 8) {
+    const u32 nb = chunk_bytes[chunk];
+    const u64 off = chunk_off[chunk];
+    if (off + nb > capacity) continue;
+    const uint16_t *src = reinterpret_cast<const uint16_t *>(tmp + chunk * (u64)chunk_records * maxb);
+    uint16_t *dst = reinterpret_cast<uint16_t *>(out + off);
+    for (u32 x = lane; x < nb / 2; x += 32) dst[x] = src[x];
+  }
+}
+
+// bucket_local {chunk, bytes, items, tips, large within the chunk} + the chunks' global offsets -> bucket_start
+__global__ void k_bucket_starts(const u32 *bucket_local, const u64 *chunk_off /*4 planes*/, u64 n_chunks, u64 *bucket_start) {
+  for (u32 b = blockIdx.x * blockDim.x + threadIdx.x; b < MHB_NUM_BUCKETS; b += gridDim.x * blockDim.x) {
+    const u32 *bl = bucket_local + 5ull * b;
+    u64 *o = bucket_start + 4ull * b;
+    if (bl[0] == 0xFFFFFFFFu) {
+      o[0] = o[1] = o[2] = o[3] = ~0ull;
+    } else {
+      for (int q = 0; q < 4; ++q) o[q] = chunk_off[(u64)q * n_chunks + bl[0]] + bl[1 + q];
+    }
   }
 }
 

@@ -139,7 +139,7 @@ class S2sPlan:
         self.a = torch.empty(n * self.W + 4, **i32)
         self.b = torch.empty(n * self.W + 4, **i32)
         self.ws = torch.empty(L.mhb_sort_workspace_bytes(n, self.W), dtype=torch.uint8, device=device)
-        self.scratch = torch.empty(L.mhb_s2s_emit_scratch_bytes(n), dtype=torch.uint8, device=device)
+        self.scratch = torch.empty(L.mhb_s2s_emit_scratch_bytes(n, k), dtype=torch.uint8, device=device)
         wpt = (k + 15) // 16
         self.cap_bytes = n * (4 + 4 * wpt) + 16
         self.bytes = torch.empty(self.cap_bytes, dtype=torch.uint8, device=device)

@@ -128,7 +128,7 @@ def load():
     L.mhb_sort_workspace_bytes.argtypes = [C.c_uint64, C.c_uint32]
     L.mhb_count_solid_scratch_bytes.argtypes = [C.c_uint64]
     L.mhb_tipset_bytes.argtypes = [C.c_uint64, C.c_uint32]
-    L.mhb_s2s_emit_scratch_bytes.argtypes = [C.c_uint64]
+    L.mhb_s2s_emit_scratch_bytes.argtypes = [C.c_uint64, C.c_uint32]
     L.mhb_count_extract.argtypes = [C.c_void_p, C.POINTER(DevReads), C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                     C.c_int]
     L.mhb_sort_records.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32,

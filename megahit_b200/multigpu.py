@@ -215,7 +215,7 @@ class MultiGpuBuild:
         out_bytes = torch.empty(cap_b, dtype=torch.uint8, device=dev)
         table = torch.zeros(65536 * 4, dtype=torch.int64, device=dev)
         totals = torch.zeros(16, dtype=torch.int64, device=dev)
-        es = torch.empty(L.mhb_s2s_emit_scratch_bytes(n_own2), dtype=torch.uint8, device=dev)
+        es = torch.empty(L.mhb_s2s_emit_scratch_bytes(n_own2, k), dtype=torch.uint8, device=dev)
         lib._check(L.mhb_s2s_emit(_stream(), _ptr(srt2), n_own2, k, _ptr(out_bytes), cap_b, _ptr(table), _ptr(totals),
                                   _ptr(es), es.numel()))
         if timed:
@@ -245,8 +245,6 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric):
     import os
     import sys
 
-    from .formats import NUM_BUCKETS  # noqa: F401
-
     k, m, n_reads, L = args.k, args.m, args.reads, 150
     job = MultiGpuBuild(n_reads, L, k, m, device, need_mercy=True)
     for _ in range(max(1, args.warmup)):
@@ -257,8 +255,11 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     res = None
+    pass_ms = []
     for _ in range(args.steps):
         res = job.run(bin_dev, timed=True)
+        # sorts issued per step: partition1, sort1 (count records), partition2, sort2 -> sort1 is 2 back
+        pass_ms.append(lib.sort_pass_ms(2)[0])
     e1.record()
     torch.cuda.synchronize()
     dist.barrier()
@@ -274,9 +275,47 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric):
     own = torch.tensor([res["n_records_owned"], res["n_solid"], res["n_mercy"]], dtype=torch.int64, device=device)
     owns = [torch.zeros_like(own) for _ in range(world)]
     dist.all_gather(owns, own)
+    # slowest rank's mean radix pass over the count records
+    pm = torch.tensor([float(np.mean(pass_ms))], dtype=torch.float64, device=device)
+    dist.all_reduce(pm, op=dist.ReduceOp.MAX)
+
+    # ---- e2e: pinned host reads -> device, build, SdBG bytes -> pinned host; device-timed, max over ranks ----
+    host_bin = torch.empty(bin_words, dtype=torch.int32).pin_memory()
+    host_bin.copy_(bin_dev[:bin_words])
+    stage_dev = torch.empty_like(bin_dev)
+    out_host = torch.empty(max(1 << 20, int(res["totals"][0].item()) * 2), dtype=torch.uint8).pin_memory()
+    e2e_ms = []
+    for i in range(1 + max(1, args.e2e_steps)):
+        dist.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        stage_dev[:bin_words].copy_(host_bin, non_blocking=True)
+        r2 = job.run(stage_dev)
+        nb = int(r2["totals"][0].item())
+        out_host[:nb].copy_(r2["sdbg_bytes"][:nb], non_blocking=True)
+        tbl = r2["table"].cpu()
+        a1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if i > 0:
+            e2e_ms.append(float(t.item()))
+        del tbl
+    nbytes = torch.tensor([nb], dtype=torch.int64, device=device)
+    dist.all_reduce(nbytes)
     if rank == 0:
+        from .lib import count_record_words
+        peak = 6650.0
+        src = "fallback (B200_PROFILING.md 6.65 TB/s)"
+        pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peak, src = float(json.load(open(pk))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         n_edges = world * n_reads * (L - k)
         ms_per_step = float(ms.item())
+        S = count_record_words(k) * 4
+        n_max = max(int(o[0]) for o in owns)
+        ach = 2.0 * n_max * S / (float(pm.item()) * 1e-3) / 1e9
+        e2e_v = n_edges / (float(np.mean(e2e_ms)) * 1e-3)
         print(json.dumps({
             "metric": metric, "value": n_edges / (ms_per_step * 1e-3), "unit": "edges/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -286,9 +325,19 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric):
                                    "all-to-all per stage, then per-GPU radix sort / count / mercy / seq2sdbg emit",
                        "parallelism": f"bucket-range x{world}", "n_edge_records": n_edges,
                        "records_owned_per_rank": [int(o[0]) for o in owns],
-                       "solid_edges_per_rank": [int(o[1]) for o in owns], "mercy_edges_per_rank": [int(o[2]) for o in owns]},
-            "stage_ms_max_over_ranks": stage, "gpu_launches": 60,
-            "e2e": None, "roofline": None, "cpu_baseline": None,
+                       "solid_edges_per_rank": [int(o[1]) for o in owns], "mercy_edges_per_rank": [int(o[2]) for o in owns],
+                       "l2_note": "inputs (>= 4.9 GB per kernel) exceed the 126 MB L2, no explicit flush needed"},
+            "stage_ms_max_over_ranks": stage,
+            "roofline": {"bound": "hbm", "kernel": f"k_radix_pass<{S // 4}> (count records, {S} B), slowest rank",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "peak_source": src, "avg_launch_ms": float(pm.item()),
+                         "algorithmic_bytes_per_launch": 2 * n_max * S},
+            "cpu_baseline": None,
+            "e2e": {"value": e2e_v, "unit": "edges/s", "h2d_bytes_per_step": int(world * bin_words * 4),
+                    "d2h_bytes_per_step": int(nbytes.item()) + world * 65536 * 32, "ms_per_step": float(np.mean(e2e_ms)),
+                    "api": "MultiGpuBuild.run on reads copied from pinned host memory each step; SdBG bytes + bucket "
+                           "table copied back to pinned host memory"},
+            "gpu_launches": 60,
         }))
     sys.stdout.flush()
     dist.barrier()
