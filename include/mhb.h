@@ -100,6 +100,20 @@ int mhb_sort_records(void *stream, uint32_t *a, uint32_t *b, uint64_t n, uint32_
                      const uint8_t *bytes, uint32_t n_bytes, const uint64_t *first_hist, void *ws,
                      size_t ws_bytes, int *result_in_b);
 
+/* Fused partition + exchange for the multi-GPU path: ONE stable radix pass over record byte `byte` whose per-digit
+ * destinations are arbitrary device byte addresses (bin_addr_dev[256], device memory): the address of the first
+ * record of digit d coming from THIS call.  Digits owned by another GPU point into that GPU's receive buffer
+ * (opened with mhb_ipc_open), so the scatter stores cross NVLink inside the sorting kernel and no separate
+ * all-to-all is needed.  ws as for mhb_sort_records. */
+int mhb_partition_scatter(void *stream, const uint32_t *recs, uint64_t n, uint32_t words, int byte,
+                          const uint64_t *bin_addr_dev, void *ws, size_t ws_bytes);
+/* cudaMalloc'ed buffers that can be shared between the per-GPU processes of one node (CUDA IPC) */
+int mhb_dev_malloc(void **ptr, size_t bytes);
+int mhb_dev_free(void *ptr);
+int mhb_ipc_export(const void *dev_ptr, uint8_t *handle64);
+int mhb_ipc_open(const uint8_t *handle64, void **peer_ptr);
+int mhb_ipc_close(void *peer_ptr);
+
 /* Per-pass device times (ms, CUDA events on `stream`) of one of the last four sorts issued by this process:
  * back = 0 is the most recent.  Synchronises on that sort's last event only. */
 int mhb_sort_pass_ms(int back, double *pass_ms, uint32_t max_passes, uint32_t *n_passes, uint64_t *n_records,

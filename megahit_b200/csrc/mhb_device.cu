@@ -183,7 +183,7 @@ extern "C" size_t mhb_sort_workspace_bytes(uint64_t n, uint32_t words) {
 }
 
 template <int WR, int CFG>
-static int launch_radix_pass_cfg(cudaStream_t st, const u32 *in, u32 *out, u64 n, int byte_idx, const u64 *bin_base,
+static int launch_radix_pass_cfg(cudaStream_t st, const u32 *in, u64 n, int byte_idx, const u64 *bin_base,
                                  u64 *lookback, u32 *tile_counter, u64 *next_hist, int next_byte, u32 epoch) {
   using C = SortCfg<WR, CFG>;
   static int blocks_per_sm = 0;
@@ -196,24 +196,24 @@ static int launch_radix_pass_cfg(cudaStream_t st, const u32 *in, u32 *out, u64 n
   const u64 tiles = sort_tiles_cfg<WR, CFG>(n);
   u64 grid = (u64)blocks_per_sm * sm_count();
   if (grid > tiles) grid = tiles;
-  k_radix_pass<WR, CFG><<<(int)grid, C::THREADS, C::SMEM, st>>>(in, out, n, (u32)tiles, byte_idx, bin_base, lookback,
+  k_radix_pass<WR, CFG><<<(int)grid, C::THREADS, C::SMEM, st>>>(in, n, (u32)tiles, byte_idx, bin_base, lookback,
                                                                  tile_counter, next_hist, next_byte, epoch);
   CK_LAUNCH();
   return MHB_OK;
 }
 
 template <int WR>
-static int launch_radix_pass(cudaStream_t st, const u32 *in, u32 *out, u64 n, int byte_idx, const u64 *bin_base,
+static int launch_radix_pass(cudaStream_t st, const u32 *in, u64 n, int byte_idx, const u64 *bin_base,
                              u64 *lookback, u32 *tile_counter, u64 *next_hist, int next_byte, u32 epoch) {
   if constexpr (WR <= 3) {
     switch (sort_cfg()) {
-      case 1: return launch_radix_pass_cfg<WR, 1>(st, in, out, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
-      case 2: return launch_radix_pass_cfg<WR, 2>(st, in, out, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
-      case 3: return launch_radix_pass_cfg<WR, 3>(st, in, out, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
+      case 1: return launch_radix_pass_cfg<WR, 1>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
+      case 2: return launch_radix_pass_cfg<WR, 2>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
+      case 3: return launch_radix_pass_cfg<WR, 3>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
       default: break;
     }
   }
-  return launch_radix_pass_cfg<WR, 0>(st, in, out, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
+  return launch_radix_pass_cfg<WR, 0>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
 }
 
 // Per-pass timing: every sort records one event before and after each pass into a small ring, so a
@@ -265,13 +265,13 @@ int mhb_sort_records_impl(void *stream, uint32_t *a, uint32_t *b, uint64_t n, ui
   CK(cudaEventRecord(tr.ev[0], st));
   u32 *in = a, *out = b;
   for (u32 p = 0; p < n_bytes; ++p) {
-    k_hist_scan256<<<1, 256, 0, st>>>(hist + (u64)p * 256, bin_base);
+    k_hist_scan256<<<1, 256, 0, st>>>(hist + (u64)p * 256, bin_base, (u64)(uintptr_t)out, words * 4);
     CK_LAUNCH();
     u64 *next_hist = p + 1 < n_bytes ? hist + (u64)(p + 1) * 256 : nullptr;
     const int next_byte = p + 1 < n_bytes ? bytes[p + 1] : 0;
     int rc = MHB_ERR_ARG;
 #define M(WW) \
-  if (words == WW) rc = launch_radix_pass<WW>(st, in, out, n, bytes[p], bin_base, lookback, tile_counter + p, next_hist, next_byte, p + 1);
+  if (words == WW) rc = launch_radix_pass<WW>(st, in, n, bytes[p], bin_base, lookback, tile_counter + p, next_hist, next_byte, p + 1);
     MHB_FOR_WR(M)
 #undef M
     if (rc) return rc;
@@ -289,6 +289,55 @@ int mhb_sort_records_impl(void *stream, uint32_t *a, uint32_t *b, uint64_t n, ui
       pass_ms_host[p] = ms;
     }
   }
+  return MHB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused partition + exchange: one radix pass whose per-digit destinations are arbitrary device addresses, e.g.
+// slots inside OTHER GPUs' receive buffers opened through CUDA IPC.  The scatter stores travel over NVLink while
+// the rest of the tile is still being ranked - no separate all-to-all.
+// ------------------------------------------------------------------------------------------------
+extern "C" int mhb_partition_scatter(void *stream, const uint32_t *recs, uint64_t n, uint32_t words, int byte,
+                                     const uint64_t *bin_addr_dev, void *ws, size_t ws_bytes) {
+  if (words < 1 || words > 17 || byte < 0 || byte >= (int)(4 * words)) return mhb_set_error(MHB_ERR_ARG, "bad geometry");
+  if (n == 0) return MHB_OK;
+  if (ws_bytes < mhb_sort_workspace_bytes(n, words)) return mhb_set_error(MHB_ERR_ARG, "sort workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  u64 *hist = (u64 *)ws;
+  u32 *tile_counter = (u32 *)(hist + (72 + 1) * 256 + 256);
+  u64 *lookback = (u64 *)((char *)ws + kSortHeadBytes);
+  CK(cudaMemsetAsync(ws, 0, mhb_sort_workspace_bytes(n, words), st));
+  int rc = MHB_ERR_ARG;
+#define M(WW) \
+  if (words == WW) rc = launch_radix_pass<WW>(st, recs, n, byte, bin_addr_dev, lookback, tile_counter, nullptr, 0, 1);
+  MHB_FOR_WR(M)
+#undef M
+  return rc;
+}
+
+extern "C" int mhb_dev_malloc(void **ptr, size_t bytes) {
+  CK(cudaMalloc(ptr, bytes));
+  return MHB_OK;
+}
+extern "C" int mhb_dev_free(void *ptr) {
+  CK(cudaFree(ptr));
+  return MHB_OK;
+}
+extern "C" int mhb_ipc_export(const void *dev_ptr, uint8_t *handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+  memcpy(handle64, &h, 64);
+  return MHB_OK;
+}
+extern "C" int mhb_ipc_open(const uint8_t *handle64, void **peer_ptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  CK(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return MHB_OK;
+}
+extern "C" int mhb_ipc_close(void *peer_ptr) {
+  CK(cudaIpcCloseMemHandle(peer_ptr));
   return MHB_OK;
 }
 

@@ -30,8 +30,10 @@ struct SortCfg {
   static constexpr size_t SMEM = (size_t)(NW * 256 + 256 + 256 + 8) * 4 + 256 * 8 + (size_t)TILE * WR * 4;
 };
 
-// exclusive scan of a 256-bin histogram (one block of 256 threads)
-__global__ void k_hist_scan256(const u64 *hist, u64 *bin_base) {
+// exclusive scan of a 256-bin histogram (one block of 256 threads) -> where each digit's records start, as a
+// BYTE ADDRESS: out + offset * rec_bytes.  (The pass kernel takes per-digit addresses so that the same kernel can
+// scatter straight into other GPUs' memory, see mhb_partition_scatter.)
+__global__ void k_hist_scan256(const u64 *hist, u64 *bin_addr, u64 out_addr, u32 rec_bytes) {
   __shared__ u64 s[256];
   const u32 t = threadIdx.x;
   s[t] = hist[t];
@@ -42,7 +44,7 @@ __global__ void k_hist_scan256(const u64 *hist, u64 *bin_base) {
     s[t] += v;
     __syncthreads();
   }
-  bin_base[t] = s[t] - hist[t];
+  bin_addr[t] = out_addr + (s[t] - hist[t]) * rec_bytes;
 }
 
 // standalone digit histogram (only needed when the producer of the records did not provide one)
@@ -75,13 +77,13 @@ static constexpr int kLbWindow = 4;  // look-back descriptors fetched per round 
 
 template <int WR, int CFG = 0>
 __global__ void __launch_bounds__(SortCfg<WR, CFG>::THREADS, SortCfg<WR, CFG>::MIN_BLOCKS)
-    k_radix_pass(const u32 *__restrict__ in, u32 *__restrict__ out, u64 n, u32 num_tiles, int byte_idx,
-                 const u64 *__restrict__ bin_base, u64 *lookback, u32 *tile_counter, u64 *next_hist,
-                 int next_byte, u32 epoch) {
+    k_radix_pass(const u32 *__restrict__ in, u64 n, u32 num_tiles, int byte_idx,
+                 const u64 *__restrict__ bin_addr /*byte address of each digit's first output record*/,
+                 u64 *lookback, u32 *tile_counter, u64 *next_hist, int next_byte, u32 epoch) {
   using C = SortCfg<WR, CFG>;
   constexpr int THREADS = C::THREADS, IPT = C::IPT, TILE = C::TILE, NW = C::NW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  u64 *s_glob = reinterpret_cast<u64 *>(smem_raw);          // 256: global offset - local bin start
+  u64 *s_glob = reinterpret_cast<u64 *>(smem_raw);          // 256: byte address of the digit's slot for tile position 0
   u32 *s_warp_hist = reinterpret_cast<u32 *>(s_glob + 256);  // NW*256
   u32 *s_bin_start = s_warp_hist + NW * 256;                 // 256
   u32 *s_next = s_bin_start + 256;                           // 256
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(SortCfg<WR, CFG>::THREADS, SortCfg<WR, CFG>::M
         }
         st_relaxed(my, kLbInclusive | ep | (prefix + pub));
       }
-      s_glob[tid] = bin_base[tid] + prefix - (u64)excl;
+      s_glob[tid] = bin_addr[tid] + (prefix - (u64)excl) * (u64)(WR * 4);  // may address another GPU's memory
     }
     __syncthreads();
 
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(SortCfg<WR, CFG>::THREADS, SortCfg<WR, CFG>::M
         if (p < valid) {
           u32 q[WR];
           ld_rec<WR>(s_recs, p, q);
-          st_rec<WR>(out, s_glob[rec_digit<WR>(q, widx, bsel)] + p, q);
+          st_rec<WR>(reinterpret_cast<u32 *>(s_glob[rec_digit<WR>(q, widx, bsel)] + (u64)p * (WR * 4)), 0, q);
           atomicAdd(&s_next[rec_digit<WR>(q, nwidx, nbsel)], 1u);
         }
       }
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(SortCfg<WR, CFG>::THREADS, SortCfg<WR, CFG>::M
         if (p < valid) {
           u32 q[WR];
           ld_rec<WR>(s_recs, p, q);
-          st_rec<WR>(out, s_glob[rec_digit<WR>(q, widx, bsel)] + p, q);
+          st_rec<WR>(reinterpret_cast<u32 *>(s_glob[rec_digit<WR>(q, widx, bsel)] + (u64)p * (WR * 4)), 0, q);
         }
       }
     }

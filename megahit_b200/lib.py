@@ -100,7 +100,8 @@ class Seq2SdbgOpts(C.Structure):
 SYMBOLS = [
     "mhb_last_error", "mhb_version", "mhb_device_count", "mhb_count_record_words", "mhb_words_per_edge",
     "mhb_s2s_record_words", "mhb_count_sort_bytes", "mhb_s2s_sort_bytes", "mhb_sort_workspace_bytes",
-    "mhb_count_extract", "mhb_sort_records", "mhb_sort_pass_ms", "mhb_count_solid_scratch_bytes", "mhb_count_solid", "mhb_tipset_bytes",
+    "mhb_count_extract", "mhb_sort_records", "mhb_sort_pass_ms", "mhb_partition_scatter", "mhb_dev_malloc", "mhb_dev_free",
+    "mhb_ipc_export", "mhb_ipc_open", "mhb_ipc_close", "mhb_count_solid_scratch_bytes", "mhb_count_solid", "mhb_tipset_bytes",
     "mhb_tipset_build", "mhb_count_mark_mercy", "mhb_count_tip_edges", "mhb_s2s_extract",
     "mhb_s2s_emit_scratch_bytes", "mhb_s2s_emit", "mhb_set_device", "mhb_count_host", "mhb_s2s_host", "mhb_build_host", "mhb_free",
     "mhb_mercy_candidates_scratch_bytes", "mhb_mercy_candidates", "mhb_mercy_edges_scratch_bytes", "mhb_mercy_edges",
@@ -159,6 +160,13 @@ def load():
     L.mhb_sort_pass_ms.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
                                    C.POINTER(C.c_uint32)]
     L.mhb_set_device.argtypes = [C.c_int]
+    L.mhb_partition_scatter.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.c_size_t]
+    L.mhb_dev_malloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    L.mhb_dev_free.argtypes = [C.c_void_p]
+    L.mhb_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.mhb_ipc_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.mhb_ipc_close.argtypes = [C.c_void_p]
     L.mhb_free.argtypes = [C.c_void_p]
     L.mhb_count_run.argtypes = [C.POINTER(CountOpts)]
     L.mhb_seq2sdbg_run.argtypes = [C.POINTER(Seq2SdbgOpts)]

@@ -69,6 +69,40 @@ def exchange_records(grouped: torch.Tensor, words: int, send_counts: np.ndarray,
     return out, n_recv
 
 
+class PeerBuffers:
+    """One receive buffer per rank for a stage, cudaMalloc'ed by libmhb and opened on every rank through CUDA IPC,
+    so that a rank's partition kernel can store records straight into their owner's memory over NVLink."""
+
+    def __init__(self, nbytes: int):
+        L = lib.load()
+        self.L, self.nbytes = L, int(nbytes)
+        p = C.c_void_p()
+        lib._check(L.mhb_dev_malloc(C.byref(p), self.nbytes))
+        self.ptr = p.value
+        h = (C.c_uint8 * 64)()
+        lib._check(L.mhb_ipc_export(C.c_void_p(self.ptr), h))
+        handles = [None] * dist.get_world_size()
+        dist.all_gather_object(handles, bytes(h))
+        self.peers = []
+        for r, hb in enumerate(handles):
+            if r == dist.get_rank():
+                self.peers.append(self.ptr)
+            else:
+                q = C.c_void_p()
+                buf = (C.c_uint8 * 64).from_buffer_copy(hb)
+                lib._check(L.mhb_ipc_open(buf, C.byref(q)))
+                self.peers.append(q.value)
+        dist.barrier()
+
+    def close(self):
+        dist.barrier()
+        for r, q in enumerate(self.peers):
+            if r != dist.get_rank():
+                self.L.mhb_ipc_close(C.c_void_p(q))
+        dist.barrier()
+        self.L.mhb_dev_free(C.c_void_p(self.ptr))
+
+
 class MultiGpuBuild:
     """count -> mercy -> seq2sdbg across the ranks of the default process group (fixed-length reads)."""
 
@@ -81,55 +115,131 @@ class MultiGpuBuild:
         self.cbytes, self.sbytes = lib.count_sort_bytes(k), lib.s2s_sort_bytes(k)
         self.n_local = n_reads * (read_len - k) if read_len >= k + 1 else 0
         self.times = {}
+        import os
+        self.fused = self.world > 1 and not os.environ.get("MHB_MGPU_NCCL_A2A")
+        self.peer = {}
 
     def _mark(self, name):
         ev = torch.cuda.Event(enable_timing=True)
         ev.record()
         self.times.setdefault(name, []).append(ev)
 
-    def _partition_and_exchange(self, recs, n, words, top_byte, hist_dev):
-        """stable pass on the top byte -> all-to-all.  Returns (owned records tensor, count, bounds)."""
+    def _buf(self, name, numel, dtype=torch.int32, slack=1.0):
+        """grow-only named device buffer: steady-state steps allocate nothing"""
+        if not hasattr(self, "_bufs"):
+            self._bufs = {}
+        t = self._bufs.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = torch.empty(int(numel * slack) + 64, dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t
+
+    def _partition_and_exchange(self, recs, n, words, top_byte, hist_dev, tag):
+        """Group the records by owner (one stable radix pass on the top byte) and move them to their owners.
+        Fused mode: the pass's scatter stores go straight into the owners' receive buffers over NVLink (CUDA IPC peer
+        pointers) - ONE kernel does partition + exchange.  Fallback (MHB_MGPU_NCCL_A2A=1): local pass, then one
+        variable-size NCCL all-to-all.  Returns (pointer to the owned records, count, bounds)."""
+        L = self.L
         ghist = hist_dev.clone()
         dist.all_reduce(ghist)
+        hist_h = hist_dev.cpu().numpy().astype(np.int64)
         bounds = plan_ranges(ghist.cpu().numpy(), self.world)
-        send = split_counts(hist_dev.cpu().numpy(), bounds)
-        tmp = torch.empty_like(recs)
-        grouped = sort_records(recs, tmp, n, words, [top_byte], hist_dev)
-        out, n_recv = exchange_records(grouped, words, send)
-        return out, n_recv, bounds
+        send = split_counts(hist_h, bounds)
+        if self._timed:
+            self._mark(tag + "_plan")
+        ws = self._buf(tag + "_ws", L.mhb_sort_workspace_bytes(max(n, 1), words), torch.uint8)
+        if not self.fused:
+            tmp = self._buf(tag + "_part", recs.numel())
+            grouped = sort_records(recs, tmp, n, words, [top_byte], hist_dev, ws)
+            if self._timed:
+                self._mark(tag + "_partition")
+            sc = torch.tensor(send, dtype=torch.int64, device=recs.device)
+            rc = torch.empty_like(sc)
+            dist.all_to_all_single(rc, sc)
+            recv_counts = rc.cpu().numpy()
+            n_recv = int(recv_counts.sum())
+            out = self._buf(tag + "_own", n_recv * words + 4, slack=1.15)
+            if self._timed:
+                self._mark(tag + "_counts")
+            dist.all_to_all_single(out[: n_recv * words], grouped[: int(send.sum()) * words],
+                                   output_split_sizes=[int(c) * words for c in recv_counts],
+                                   input_split_sizes=[int(c) * words for c in send])
+            return out.data_ptr(), n_recv, bounds
+        # ---- fused: who sends how much to whom, where my block starts inside every owner's buffer ----
+        sc = torch.tensor(send, dtype=torch.int64, device=recs.device)
+        allsend = [torch.empty_like(sc) for _ in range(self.world)]
+        dist.all_gather(allsend, sc)
+        M = torch.stack(allsend).cpu().numpy()  # M[r][o] = records rank r sends to owner o
+        recv_tot = M.sum(axis=0)
+        need = int(recv_tot.max()) * words * 4 + 64
+        pb = self.peer.get(tag)
+        if pb is None or pb.nbytes < need:  # same decision on every rank: M is identical everywhere
+            if pb is not None:
+                pb.close()
+            pb = self.peer[tag] = PeerBuffers(int(need * 1.2))
+        rb = words * 4
+        my_off = M[: self.rank].sum(axis=0)  # my block's first record inside owner o's buffer
+        addr = np.zeros(256, np.uint64)
+        for o in range(self.world):
+            lo, hi = int(bounds[o]), int(bounds[o + 1])
+            pre = np.concatenate([[0], np.cumsum(hist_h[lo:hi])[:-1]])
+            addr[lo:hi] = np.uint64(pb.peers[o]) + (np.uint64(my_off[o]) + pre.astype(np.uint64)) * np.uint64(rb)
+        addr_dev = torch.from_numpy(addr.view(np.int64)).to(recs.device)
+        if self._timed:
+            self._mark(tag + "_partition")
+        dist.barrier()  # every owner is done with what it received in the previous step
+        if self._timed:
+            self._mark(tag + "_counts")
+        lib._check(L.mhb_partition_scatter(_stream(), _ptr(recs), n, words, top_byte, _ptr(addr_dev), _ptr(ws), ws.numel()))
+        dist.barrier()  # all ranks' scatter kernels have completed: my buffer is complete
+        return pb.ptr, int(recv_tot[self.rank]), bounds
+
+    def close(self):
+        for pb in self.peer.values():
+            pb.close()
+        self.peer = {}
+
+    def _sort_raw(self, ptr_a, n, words, sort_bytes, tag):
+        """LSD sort of n records at raw device pointer ptr_a; returns the pointer holding the result."""
+        L = self.L
+        tmp = self._buf(tag + "_tmp", n * words + 4, slack=1.15)
+        ws = self._buf(tag + "_ws2", L.mhb_sort_workspace_bytes(max(n, 1), words), torch.uint8)
+        arr = (C.c_uint8 * len(sort_bytes))(*sort_bytes)
+        in_b = C.c_int(0)
+        lib._check(L.mhb_sort_records(_stream(), C.c_void_p(ptr_a), _ptr(tmp), n, words, arr, len(sort_bytes), None, _ptr(ws),
+                                      ws.numel(), C.byref(in_b)))
+        return tmp.data_ptr() if in_b.value else ptr_a
 
     def run(self, bin_dev: torch.Tensor, timed: bool = False) -> dict:
         L, k, m, dev = self.L, self.k, self.m, self.device
+        self._timed = timed
         i32 = dict(dtype=torch.int32, device=dev)
         reads = lib.DevReads(bin_dev.data_ptr(), bin_dev.numel(), self.n_reads, self.read_len, None, None)
         if timed:
             self._mark("t0")
         # ---- count stage ----
         n = self.n_local
-        a = torch.empty(n * self.WR + 4, **i32)
+        a = self._buf("c_a", n * self.WR + 4)
         hist = torch.zeros(256, dtype=torch.int64, device=dev)
         top = self.cbytes[-1]
         lib._check(L.mhb_count_extract(_stream(), C.byref(reads), k, _ptr(a), n, _ptr(hist), top))
         if timed:
             self._mark("extract")
-        own, n_own, bounds = self._partition_and_exchange(a, n, self.WR, top, hist)
-        del a
+        own, n_own, bounds = self._partition_and_exchange(a, n, self.WR, top, hist, "c")
         if timed:
             self._mark("exchange1")
-        tmp = torch.empty_like(own)
-        srt = sort_records(own, tmp, n_own, self.WR, self.cbytes, None)
+        srt = self._sort_raw(own, n_own, self.WR, self.cbytes, "c")
         if timed:
             self._mark("sort1")
         cap = n_own // max(1, m) + 1
-        edges = torch.empty(cap * self.WE, **i32)
-        aux = torch.empty(cap, dtype=torch.uint8, device=dev)
+        edges = self._buf("edges", cap * self.WE, slack=1.15)
+        aux = self._buf("aux", cap, torch.uint8, slack=1.15)
         mul_hist = torch.zeros(65536, dtype=torch.int64, device=dev)
         nsol = torch.zeros(8, dtype=torch.int64, device=dev)
-        scratch = torch.empty(L.mhb_count_solid_scratch_bytes(n_own), dtype=torch.uint8, device=dev)
-        lib._check(L.mhb_count_solid(_stream(), _ptr(srt), n_own, k, m, _ptr(edges), _ptr(aux), cap, _ptr(mul_hist),
+        scratch = self._buf("c_scratch", L.mhb_count_solid_scratch_bytes(n_own), torch.uint8, slack=1.15)
+        lib._check(L.mhb_count_solid(_stream(), C.c_void_p(srt), n_own, k, m, _ptr(edges), _ptr(aux), cap, _ptr(mul_hist),
                                      _ptr(nsol), _ptr(scratch), scratch.numel()))
         n_solid = int(nsol[0].item())
-        del own, tmp, srt, scratch
         dist.all_reduce(mul_hist)  # edge_counter.h:44-52: `.counting` is a global histogram
         if timed:
             self._mark("count")
@@ -200,23 +310,21 @@ class MultiGpuBuild:
         n_items = n_seqs * 6
         seq_pad = torch.cat([seq_edges, torch.zeros(8, **i32)])
         seqs = lib.DevSeqs(seq_pad.data_ptr(), n_seqs * self.WE, n_seqs, k + 1, None, None, None, None, self.WE)
-        sa = torch.empty(n_items * self.W2 + 4, **i32)
+        sa = self._buf("s_a", n_items * self.W2 + 4, slack=1.1)
         hist2 = torch.zeros(256, dtype=torch.int64, device=dev)
         top2 = self.sbytes[-1]
         lib._check(L.mhb_s2s_extract(_stream(), C.byref(seqs), k, _ptr(sa), n_items, _ptr(hist2), top2))
-        own2, n_own2, bounds2 = self._partition_and_exchange(sa, n_items, self.W2, top2, hist2)
-        del sa
+        own2, n_own2, bounds2 = self._partition_and_exchange(sa, n_items, self.W2, top2, hist2, "s")
         if timed:
             self._mark("exchange2")
-        tmp2 = torch.empty_like(own2)
-        srt2 = sort_records(own2, tmp2, n_own2, self.W2, self.sbytes, None)
+        srt2 = self._sort_raw(own2, n_own2, self.W2, self.sbytes, "s")
         wpt = (k + 15) // 16
         cap_b = n_own2 * (4 + 4 * wpt) + 16
-        out_bytes = torch.empty(cap_b, dtype=torch.uint8, device=dev)
+        out_bytes = self._buf("sdbg", cap_b, torch.uint8, slack=1.1)
         table = torch.zeros(65536 * 4, dtype=torch.int64, device=dev)
         totals = torch.zeros(16, dtype=torch.int64, device=dev)
-        es = torch.empty(L.mhb_s2s_emit_scratch_bytes(n_own2, k), dtype=torch.uint8, device=dev)
-        lib._check(L.mhb_s2s_emit(_stream(), _ptr(srt2), n_own2, k, _ptr(out_bytes), cap_b, _ptr(table), _ptr(totals),
+        es = self._buf("s_scratch", L.mhb_s2s_emit_scratch_bytes(n_own2, k), torch.uint8, slack=1.1)
+        lib._check(L.mhb_s2s_emit(_stream(), C.c_void_p(srt2), n_own2, k, _ptr(out_bytes), cap_b, _ptr(table), _ptr(totals),
                                   _ptr(es), es.numel()))
         if timed:
             self._mark("s2s")
@@ -266,7 +374,8 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric):
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=device)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     stage = {}
-    names = ["t0", "extract", "exchange1", "sort1", "count", "mercy", "exchange2", "s2s"]
+    names = ["t0", "extract", "c_plan", "c_partition", "c_counts", "exchange1", "sort1", "count", "mercy", "s_plan",
+             "s_partition", "s_counts", "exchange2", "s2s"]
     for a, b in zip(names[:-1], names[1:]):
         t = torch.tensor([np.mean([x.elapsed_time(y) for x, y in zip(job.times[a], job.times[b])])], dtype=torch.float64,
                          device=device)
@@ -340,5 +449,7 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric):
             "gpu_launches": 60,
         }))
     sys.stdout.flush()
+    torch.cuda.synchronize()
+    job.close()
     dist.barrier()
     dist.destroy_process_group()

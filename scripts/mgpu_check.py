@@ -38,6 +38,7 @@ for name, k in (("syn150_k27", 27), ("syn150_klist", 21), ("syn150_klist", 59), 
     if rank == 0:
         print("   per-rank (n_solid, n_cand, n_mercy, items):", info)
     stream = multigpu.gather_sdbg_stream(res)
+    torch.cuda.synchronize()
     edges = res["edges"][: res["n_solid"] * job.WE].cpu().numpy().view(np.uint32).tobytes()
     objs = [None] * world
     dist.all_gather_object(objs, edges)
@@ -61,6 +62,7 @@ for name, k in (("syn150_k27", 27), ("syn150_klist", 21), ("syn150_klist", 59), 
             a, b = np.frombuffer(rs[:n], np.uint8), np.frombuffer(stream[:n], np.uint8)
             d = np.nonzero(a != b)[0]
             print("  first diff at byte", int(d[0]) if len(d) else None, "of", n)
+    job.close()
 if rank == 0:
     print("MGPU PARITY", "PASS" if ok else "FAIL")
 dist.destroy_process_group()
