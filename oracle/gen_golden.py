@@ -158,7 +158,53 @@ def gen_degenerate():
         make_case("tandem_k27", f"{tmp}/t", [27, 28], 2)
 
 
-CASES = {"toy": gen_toy, "syn150": gen_syn150, "synvar": gen_synvar, "degenerate": gen_degenerate}
+def gen_chain():
+    """k > k_min: seq2sdbg fed by the reference's own assemble/local/iterate outputs (contigs with multiplicity and
+    flags, bubble sequences, additional + local contigs, UNSORTED iterative edges).  Captured by running the
+    reference's Python driver (src/megahit, used from /root/reference at generation time only) with --keep-tmp-files."""
+    R = os.path.join(REFROOT, "test_data")
+    jobs = {
+        "chain_syn150": None,  # reads written below
+        "chain_toy": ["-1", f"{R}/r3_1.fa", "-2", f"{R}/r3_2.fa", "--12", f"{R}/r1.il.fa.gz,{R}/r2.il.fa.bz2", "-r",
+                      f"{R}/r4.fa,{R}/loop.fa"],
+    }
+    for name, reads_args in jobs.items():
+        with tempfile.TemporaryDirectory() as tmp:
+            os.makedirs(f"{tmp}/bin")
+            shutil.copy(os.path.join(REFROOT, "src", "megahit"), f"{tmp}/bin/megahit")
+            os.symlink(REF, f"{tmp}/bin/megahit_core")
+            if reads_args is None:
+                b = synth.synth_reads(3000, 150, 15000, 0.01, seed=7)
+                with open(f"{tmp}/reads.fa", "w") as f:
+                    for i, row in enumerate(b):
+                        L, w = int(row[0]), row[1:]
+                        f.write(f">r{i}\n" + "".join("ACGT"[(int(w[j >> 4]) >> (30 - 2 * (j & 15))) & 3] for j in range(L)) + "\n")
+                reads_args = ["-r", f"{tmp}/reads.fa"]
+            run([sys.executable, f"{tmp}/bin/megahit", *reads_args, "--k-list", "21,29,39", "-o", f"{tmp}/out",
+                 "--keep-tmp-files", "-t", "4"])
+            d = case_dir(name)
+            ic = f"{tmp}/out/intermediate_contigs"
+            for fn in ("k21.contigs.fa", "k21.bubble_seq.fa", "k21.addi.fa", "k21.local.fa"):
+                shutil.copy(f"{ic}/{fn}", d)
+                shutil.copy(f"{ic}/{fn}.info", d)
+            for fn in ("29.edges.0", "29.edges.info"):
+                shutil.copy(f"{tmp}/out/tmp/k29/{fn}", d)
+            info, stream, table = F.canonical_sdbg(f"{tmp}/out/tmp/k29/29")
+            res = {"k": 29, "k_from": 21, "sdbg_k": info.k, "sdbg_words_per_tip_label": info.words_per_tip_label,
+                   "sdbg_items": int(table[:, 0].sum()), "sdbg_tips": int(table[:, 1].sum()),
+                   "sdbg_large_mul": int(table[:, 2].sum()), "sdbg_sha256": F.sha256(stream), "sdbg_bytes": len(stream)}
+            # thread-count independence of the reference on this input
+            p1 = f"{tmp}/t1"
+            run([REF, "seq2sdbg", "--host_mem", "4e9", "--mem_flag", "1", "--output_prefix", p1, "--num_cpu_threads", "1",
+                 "-k", "29", "--kmer_from", "21", "--input_prefix", f"{tmp}/out/tmp/k29/29", "--addi_contig", f"{ic}/k21.addi.fa",
+                 "--local_contig", f"{ic}/k21.local.fa", "--contig", f"{ic}/k21.contigs.fa", "--bubble", f"{ic}/k21.bubble_seq.fa"])
+            assert F.sha256(F.canonical_sdbg(p1)[1]) == res["sdbg_sha256"]
+            json.dump(res, open(os.path.join(d, "chain.json"), "w"), indent=1, sort_keys=True)
+            print(name, res["sdbg_items"], res["sdbg_tips"], "loop contigs:",
+                  sum(1 for l in open(f"{d}/k21.contigs.fa") if l.startswith(">") and "flag=2" in l or "flag=3" in l))
+
+
+CASES = {"chain": gen_chain, "toy": gen_toy, "syn150": gen_syn150, "synvar": gen_synvar, "degenerate": gen_degenerate}
 
 if __name__ == "__main__":
     if not os.path.exists(REF):
