@@ -100,13 +100,14 @@ int mhb_sort_records(void *stream, uint32_t *a, uint32_t *b, uint64_t n, uint32_
                      const uint8_t *bytes, uint32_t n_bytes, const uint64_t *first_hist, void *ws,
                      size_t ws_bytes, int *result_in_b);
 
-/* Fused partition + exchange for the multi-GPU path: ONE stable radix pass over record byte `byte` whose per-digit
- * destinations are arbitrary device byte addresses (bin_addr_dev[256], device memory): the address of the first
- * record of digit d coming from THIS call.  Digits owned by another GPU point into that GPU's receive buffer
- * (opened with mhb_ipc_open), so the scatter stores cross NVLink inside the sorting kernel and no separate
- * all-to-all is needed.  ws as for mhb_sort_records. */
+/* Fused partition + exchange for the multi-GPU path: ONE stable radix pass whose per-digit destinations are arbitrary
+ * device byte addresses (bin_addr_dev[256], device memory) = where the first record of digit d coming from THIS call
+ * goes.  The digit of a record is owner_of_byte_dev[record byte `byte`] (256-entry device table mapping the record's
+ * leading byte to the owning rank) or the byte itself when that table is NULL.  Digits owned by another GPU point
+ * into that GPU's receive buffer (opened with mhb_ipc_open), so the scatter stores cross NVLink inside the sorting
+ * kernel and no separate all-to-all is needed.  ws as for mhb_sort_records. */
 int mhb_partition_scatter(void *stream, const uint32_t *recs, uint64_t n, uint32_t words, int byte,
-                          const uint64_t *bin_addr_dev, void *ws, size_t ws_bytes);
+                          const uint8_t *owner_of_byte_dev, const uint64_t *bin_addr_dev, void *ws, size_t ws_bytes);
 /* cudaMalloc'ed buffers that can be shared between the per-GPU processes of one node (CUDA IPC) */
 int mhb_dev_malloc(void **ptr, size_t bytes);
 int mhb_dev_free(void *ptr);
@@ -157,6 +158,19 @@ size_t mhb_mercy_edges_scratch_bytes(uint64_t n_cand, uint32_t max_read_len);
 int mhb_mercy_edges(void *stream, const mhb_dev_reads *reads, const uint64_t *cand_ids, uint64_t n_cand,
                     uint32_t max_read_len, uint32_t k, const uint32_t *edges, uint64_t n_edges, uint32_t *mercy_out,
                     uint64_t capacity, uint64_t *n_mercy_host, void *scratch, size_t scratch_bytes);
+
+/* Same, with the sorted solid edges given as n_segs (<= 16) segments: segment owner_of_byte[b] holds every edge whose
+ * leading byte is b (host arrays; the segment pointers are device pointers and may be CUDA IPC peer pointers into
+ * other GPUs' memory, so a multi-GPU build needs no gather of the edges). */
+int mhb_mercy_edges_segs(void *stream, const mhb_dev_reads *reads, const uint64_t *cand_ids, uint64_t n_cand,
+                         uint32_t max_read_len, uint32_t k, uint32_t n_segs, const uint32_t *const *seg_edges,
+                         const uint64_t *seg_counts, const void *const *seg_luts, const uint8_t *owner_of_byte,
+                         uint32_t *mercy_out, uint64_t capacity, uint64_t *n_mercy_host, void *scratch,
+                         size_t scratch_bytes);
+/* 12-base prefix -> [first,last] edge index table of one sorted edge segment (InitLookupTable, seq_to_sdbg.cpp:100-127);
+ * mhb_edge_lut_bytes() bytes of device memory, one per segment, required by mhb_mercy_edges_segs. */
+size_t mhb_edge_lut_bytes(void);
+int mhb_edge_lut_build(void *stream, const uint32_t *edges, uint64_t n_edges, uint32_t k, void *lut);
 
 /* Sequences in package orientation for seq2sdbg: word-aligned 2-bit packing.
  * fixed_len > 0: sequence s starts at word s*fixed_stride (fixed_stride = 0 means ceil(fixed_len/16));

@@ -297,21 +297,50 @@ int mhb_sort_records_impl(void *stream, uint32_t *a, uint32_t *b, uint64_t n, ui
 // slots inside OTHER GPUs' receive buffers opened through CUDA IPC.  The scatter stores travel over NVLink while
 // the rest of the tile is still being ranked - no separate all-to-all.
 // ------------------------------------------------------------------------------------------------
+template <int WR>
+static int launch_partition_pass(cudaStream_t st, const u32 *in, u64 n, int byte_idx, const u64 *bin_addr, u64 *lookback,
+                                 u32 *tile_counter, const uint8_t *lut) {
+  using C = SortCfg<WR, 0>;
+  static int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    CK(cudaFuncSetAttribute(k_radix_pass<WR, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_radix_pass<WR, 0, true>, C::THREADS, C::SMEM));
+    if (blocks_per_sm < 1) return mhb_set_error(MHB_ERR_CUDA, "partition pass kernel (WR=%d) does not fit an SM", WR);
+  }
+  const u64 tiles = sort_tiles_cfg<WR, 0>(n);
+  u64 grid = (u64)blocks_per_sm * sm_count();
+  if (grid > tiles) grid = tiles;
+  k_radix_pass<WR, 0, true><<<(int)grid, C::THREADS, C::SMEM, st>>>(in, n, (u32)tiles, byte_idx, bin_addr, lookback,
+                                                                     tile_counter, nullptr, 0, 1, lut);
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
 extern "C" int mhb_partition_scatter(void *stream, const uint32_t *recs, uint64_t n, uint32_t words, int byte,
-                                     const uint64_t *bin_addr_dev, void *ws, size_t ws_bytes) {
+                                     const uint8_t *owner_of_byte_dev, const uint64_t *bin_addr_dev, void *ws,
+                                     size_t ws_bytes) {
   if (words < 1 || words > 17 || byte < 0 || byte >= (int)(4 * words)) return mhb_set_error(MHB_ERR_ARG, "bad geometry");
   if (n == 0) return MHB_OK;
-  if (ws_bytes < mhb_sort_workspace_bytes(n, words)) return mhb_set_error(MHB_ERR_ARG, "sort workspace too small");
+  const u64 tiles = sort_num_tiles(n, words);
+  const size_t need = kSortHeadBytes + (size_t)tiles * 256 * 8 + 256;
+  if (ws_bytes < need) return mhb_set_error(MHB_ERR_ARG, "sort workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   u64 *hist = (u64 *)ws;
   u32 *tile_counter = (u32 *)(hist + (72 + 1) * 256 + 256);
   u64 *lookback = (u64 *)((char *)ws + kSortHeadBytes);
-  CK(cudaMemsetAsync(ws, 0, mhb_sort_workspace_bytes(n, words), st));
+  CK(cudaMemsetAsync(ws, 0, need, st));
   int rc = MHB_ERR_ARG;
+  if (owner_of_byte_dev) {
 #define M(WW) \
-  if (words == WW) rc = launch_radix_pass<WW>(st, recs, n, byte, bin_addr_dev, lookback, tile_counter, nullptr, 0, 1);
-  MHB_FOR_WR(M)
+  if (words == WW) rc = launch_partition_pass<WW>(st, recs, n, byte, bin_addr_dev, lookback, tile_counter, owner_of_byte_dev);
+    MHB_FOR_WR(M)
 #undef M
+  } else {
+#define M(WW) \
+  if (words == WW) rc = launch_radix_pass_cfg<WW, 0>(st, recs, n, byte, bin_addr_dev, lookback, tile_counter, nullptr, 0, 1);
+    MHB_FOR_WR(M)
+#undef M
+  }
   return rc;
 }
 
@@ -773,22 +802,56 @@ extern "C" int mhb_mercy_candidates(void *stream, const uint32_t *first_0_out, c
   return MHB_OK;
 }
 
-extern "C" size_t mhb_mercy_edges_scratch_bytes(uint64_t n_cand, uint32_t max_read_len) {
+extern "C" size_t mhb_edge_lut_bytes(void);
+static size_t mercy_core_scratch(uint64_t n_cand, uint32_t max_read_len) {
   const size_t wpr = (max_read_len + 31) / 32 + 1;
   return (size_t)n_cand * 3 * wpr * 4 + (size_t)(n_cand + 64) * 12 + (size_t)(n_cand / kScanTile + 2) * 8 + 2048;
 }
+// scratch for mhb_mercy_edges (single segment: includes room for its look-up table); the segmented call needs
+// this minus mhb_edge_lut_bytes()
+extern "C" size_t mhb_mercy_edges_scratch_bytes(uint64_t n_cand, uint32_t max_read_len) {
+  return ((mercy_core_scratch(n_cand, max_read_len) + 255) & ~(size_t)255) + 512 + mhb_edge_lut_bytes();
+}
 
-extern "C" int mhb_mercy_edges(void *stream, const mhb_dev_reads *reads, const uint64_t *cand_ids, uint64_t n_cand,
-                               uint32_t max_read_len, uint32_t k, const uint32_t *edges, uint64_t n_edges,
-                               uint32_t *mercy_out, uint64_t capacity, uint64_t *n_mercy_host, void *scratch,
-                               size_t scratch_bytes) {
+extern "C" size_t mhb_edge_lut_bytes(void) { return (size_t)kLutEntries * sizeof(uint2); }
+
+extern "C" int mhb_edge_lut_build(void *stream, const uint32_t *edges, uint64_t n_edges, uint32_t k, void *lut) {
+  if (n_edges >= 0xFFFFFFFFull) return mhb_set_error(MHB_ERR_ARG, "too many edges for the 32-bit look-up table");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(lut, 0xFF, mhb_edge_lut_bytes(), st));
+  if (n_edges == 0) return MHB_OK;
+  u64 g = (n_edges + 255) / 256;
+  if (g > (u64)sm_count() * 16) g = (u64)sm_count() * 16;
+  k_edge_lut<<<(unsigned)g, 256, 0, st>>>(edges, n_edges, words_per_edge(k), (uint2 *)lut);
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
+extern "C" int mhb_mercy_edges_segs(void *stream, const mhb_dev_reads *reads, const uint64_t *cand_ids, uint64_t n_cand,
+                                    uint32_t max_read_len, uint32_t k, uint32_t n_segs, const uint32_t *const *seg_edges,
+                                    const uint64_t *seg_counts, const void *const *seg_luts, const uint8_t *owner_of_byte,
+                                    uint32_t *mercy_out, uint64_t capacity, uint64_t *n_mercy_host, void *scratch,
+                                    size_t scratch_bytes) {
   *n_mercy_host = 0;
   if (int rc = check_reads(reads, k)) return rc;
   if (n_cand == 0) return MHB_OK;
   if (k < 12) return mhb_set_error(MHB_ERR_ARG, "mercy edges need k >= 12 (12-mer look-up prefix)");
-  if (scratch_bytes < mhb_mercy_edges_scratch_bytes(n_cand, max_read_len)) return mhb_set_error(MHB_ERR_ARG, "scratch too small");
+  if (n_segs < 1 || n_segs > 16) return mhb_set_error(MHB_ERR_ARG, "1..16 edge segments supported");
+  if (scratch_bytes < mercy_core_scratch(n_cand, max_read_len)) return mhb_set_error(MHB_ERR_ARG, "scratch too small");
   cudaStream_t st = (cudaStream_t)stream;
   const ReadsView rv = make_reads_view(reads);
+  EdgeSegs sg;
+  memset(&sg, 0, sizeof(sg));
+  for (u32 i = 0; i < n_segs; ++i) {
+    sg.ptr[i] = seg_edges[i];
+    sg.n[i] = (long long)seg_counts[i];
+    sg.lut[i] = (const uint2 *)seg_luts[i];
+    if (!sg.lut[i]) return mhb_set_error(MHB_ERR_ARG, "segment %u has no look-up table (mhb_edge_lut_build)", i);
+  }
+  for (int b = 0; b < 256; ++b) {
+    sg.owner[b] = owner_of_byte ? owner_of_byte[b] : 0;
+    if (sg.owner[b] >= n_segs) return mhb_set_error(MHB_ERR_ARG, "owner_of_byte[%d] = %u out of range", b, sg.owner[b]);
+  }
   const u32 wpr = (max_read_len + 31) / 32 + 1, WE = words_per_edge(k), WM = div_ceil(k + 1, 16);
   char *p = (char *)scratch;
   u64 *total = (u64 *)p;
@@ -803,7 +866,7 @@ extern "C" int mhb_mercy_edges(void *stream, const mhb_dev_reads *reads, const u
   u64 g64 = (n_cand + 7) / 8;
   if (g64 > (u64)sm_count() * 16) g64 = (u64)sm_count() * 16;
 #define M(WW) \
-  if (WM == WW) k_mercy_probe<WW><<<(unsigned)g64, 256, 0, st>>>(rv, cand_ids, n_cand, k, edges, (long long)n_edges, WE, bits, wpr);
+  if (WM == WW) k_mercy_probe<WW><<<(unsigned)g64, 256, 0, st>>>(rv, cand_ids, n_cand, k, sg, WE, bits, wpr);
   MHB_FOR_W(M)
 #undef M
   CK_LAUNCH();
@@ -820,6 +883,22 @@ extern "C" int mhb_mercy_edges(void *stream, const mhb_dev_reads *reads, const u
     CK_LAUNCH();
   }
   return MHB_OK;
+}
+
+extern "C" int mhb_mercy_edges(void *stream, const mhb_dev_reads *reads, const uint64_t *cand_ids, uint64_t n_cand,
+                               uint32_t max_read_len, uint32_t k, const uint32_t *edges, uint64_t n_edges,
+                               uint32_t *mercy_out, uint64_t capacity, uint64_t *n_mercy_host, void *scratch,
+                               size_t scratch_bytes) {
+  *n_mercy_host = 0;
+  if (n_cand == 0) return MHB_OK;
+  // single segment: the look-up table lives behind the core scratch in the caller's buffer
+  const size_t core = (mercy_core_scratch(n_cand, max_read_len) + 255) & ~(size_t)255;
+  if (scratch_bytes < core + mhb_edge_lut_bytes()) return mhb_set_error(MHB_ERR_ARG, "scratch too small");
+  void *lut = (char *)scratch + core;
+  if (int rc = mhb_edge_lut_build(stream, edges, n_edges, k, lut)) return rc;
+  const void *luts[1] = {lut};
+  return mhb_mercy_edges_segs(stream, reads, cand_ids, n_cand, max_read_len, k, 1, &edges, &n_edges, luts, nullptr, mercy_out,
+                              capacity, n_mercy_host, scratch, core);
 }
 
 extern "C" int mhb_set_device(int device) {

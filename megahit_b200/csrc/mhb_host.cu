@@ -512,17 +512,30 @@ extern "C" int mhb_build_host(const mhb_build_args *args, mhb_build_result *res)
     CKR(mhb_count_tip_edges(st, d_aux, n_solid, &n_tip));
     const size_t ts_bytes = mhb_tipset_bytes(n_tip, k);
     const size_t cs_bytes = mhb_mercy_candidates_scratch_bytes(n_reads);
-    if (Arena::pad(ts_bytes) + Arena::pad(cs_bytes) > work_bytes) return mhb_set_error(MHB_ERR_NOMEM, "internal: mercy scratch");
-    char *d_tips = work;
-    char *d_cs = work + Arena::pad(ts_bytes);
+    // the count stage's work area is free now; small inputs may need more than it offers (12-mer look-up table)
+    auto work_area = [&](size_t bytes) -> char * {
+      if (bytes <= work_bytes) return work;
+      if (extra) cudaFree(extra);
+      extra = nullptr;
+      if (cudaMalloc((void **)&extra, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+      return extra;
+    };
+    char *d_tips = work_area(Arena::pad(ts_bytes) + Arena::pad(cs_bytes));
+    if (!d_tips) return mhb_set_error(MHB_ERR_NOMEM, "cudaMalloc for the mercy stage failed");
+    char *d_cs = d_tips + Arena::pad(ts_bytes);
     CKR(mhb_tipset_build(st, d_edges, d_aux, n_solid, k, d_tips, ts_bytes, n_tip));
     CKR(mhb_count_mark_mercy(st, &reads, k, d_tips, ts_bytes, n_tip, d_first, d_last));
     CKR(mhb_mercy_candidates(st, d_first, d_last, n_reads, d_cand, &n_cand, d_cs, cs_bytes));
     if (n_cand) {
       const size_t ms_bytes = mhb_mercy_edges_scratch_bytes(n_cand, max_len);
-      if (ms_bytes > work_bytes) return mhb_set_error(MHB_ERR_NOMEM, "internal: mercy scratch");
+      CK(cudaStreamSynchronize(st));  // the tip set / candidate scratch may be released by work_area()
+      char *d_ms = work_area(ms_bytes);
+      if (!d_ms) return mhb_set_error(MHB_ERR_NOMEM, "cudaMalloc for the mercy stage failed");
       CKR(mhb_mercy_edges(st, &reads, d_cand, n_cand, max_len, k, d_edges, n_solid, d_edges + (size_t)n_solid * WE,
-                          cap_edges - n_solid, &n_mercy, work, ms_bytes));
+                          cap_edges - n_solid, &n_mercy, d_ms, ms_bytes));
     }
     res->t_mercy_ms = t.stop();
   }
@@ -539,6 +552,9 @@ extern "C" int mhb_build_host(const mhb_build_args *args, mhb_build_result *res)
   const size_t s2s_work = 2 * Arena::pad((size_t)n_items * W2 * 4 + 16) + Arena::pad(s_ws) + Arena::pad(s_scr) + Arena::pad(cap_bytes);
   char *sw = work;
   if (s2s_work > work_bytes) {
+    CK(cudaStreamSynchronize(st));
+    if (extra) cudaFree(extra);
+    extra = nullptr;
     cudaError_t e = cudaMalloc((void **)&extra, s2s_work);
     if (e != cudaSuccess) {
       cudaGetLastError();

@@ -32,6 +32,27 @@ __global__ void k_cand_compact(const u32 *flag, const u64 *off, u64 n_reads, u64
   if (r < n_reads && flag[r]) ids[off[r]] = r;
 }
 
+// The sorted solid edges as up to 16 segments, segment o holding every edge whose leading byte maps to o (one
+// segment = everything on a single GPU; several = the bucket ranges of the ranks of a multi-GPU build, each in its
+// owner's memory and read through CUDA IPC peer pointers - no gather of the edges is needed).
+struct EdgeSegs {
+  const u32 *ptr[16];
+  long long n[16];
+  const uint2 *lut[16];  // per segment: [first,last] edge index of every 12-base prefix (0xFFFFFFFF = none)
+  uint8_t owner[256];
+};
+
+// InitLookupTable (seq_to_sdbg.cpp:100-127) for one segment: lut[p] = {first, last} index of the edges whose first
+// 12 bases are p.  lut must be pre-filled with 0xFF.
+static constexpr u32 kLutEntries = 1u << 24;
+__global__ void k_edge_lut(const u32 *__restrict__ edges, u64 n, u32 we, uint2 *lut) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u32 p = edges[i * we] >> 8;
+    if (i == 0 || (edges[(i - 1) * we] >> 8) != p) lut[p].x = (u32)i;
+    if (i + 1 == n || (edges[(i + 1) * we] >> 8) != p) lut[p].y = (u32)i;
+  }
+}
+
 template <int WM>  // WM = ceil((k+1)/16) words
 struct MercyOps {
   // compare the first nb bases of x and y (both left-aligned, arbitrary tail bits)
@@ -46,31 +67,25 @@ struct MercyOps {
     }
     return 0;
   }
-  // BinarySearchKmer (seq_to_sdbg.cpp:132-161) over `n` sorted edges of `we` words each
-  __device__ static long long search(const u32 *edges, long long n, u32 we, const u32 (&km)[WM], u32 ksz) {
-    if (n == 0) return -1;
-    const u32 prefix = km[0] >> 8;  // 12 bases (kLookUpPrefixLength)
-    long long lo = 0, hi = n;       // first edge with prefix >= ours
-    while (lo < hi) {
-      const long long mid = (lo + hi) >> 1;
-      if ((edges[mid * we] >> 8) < prefix) lo = mid + 1; else hi = mid;
-    }
-    long long l = lo;
-    if (l >= n || (edges[l * we] >> 8) != prefix) return -1;  // lookup_table[...] == -1
-    hi = n;  // first edge with prefix > ours
-    while (lo < hi) {
-      const long long mid = (lo + hi) >> 1;
-      if ((edges[mid * we] >> 8) <= prefix) lo = mid + 1; else hi = mid;
-    }
-    long long r = lo - 1;
+  // BinarySearchKmer (seq_to_sdbg.cpp:132-161).  Edges sharing a 12-base prefix share their leading byte, hence
+  // their segment, so searching inside the owning segment probes exactly the edges the reference would probe.
+  // Returns the matching edge record or nullptr.
+  __device__ static const u32 *search(const EdgeSegs &sg, u32 we, const u32 (&km)[WM], u32 ksz) {
+    const u32 seg = sg.owner[km[0] >> 24];
+    const u32 *edges = sg.ptr[seg];
+    const long long n = sg.n[seg];
+    if (n == 0) return nullptr;
+    const uint2 lr = sg.lut[seg][km[0] >> 8];  // 12 bases (kLookUpPrefixLength)
+    if (lr.x == 0xFFFFFFFFu) return nullptr;   // lookup_table[...] == -1
+    long long l = lr.x, r = lr.y;
     while (l <= r) {
       const long long mid = (l + r) / 2;
       const int c = cmp(km, edges + mid * we, ksz);
       if (c > 0) l = mid + 1;
       else if (c < 0) r = mid - 1;
-      else return mid;
+      else return edges + mid * we;
     }
-    return -1;
+    return nullptr;
   }
   // x (nb bases) -> c followed by x's first nb bases (nb+1 bases)   [Kmer::ShiftPreappend, kmer.h:151-166]
   __device__ static void preappend(const u32 (&x)[WM], u32 c, u32 nb, u32 (&out)[WM]) {
@@ -96,8 +111,8 @@ __device__ __forceinline__ u32 pkg_base(const u32 *s, u32 L, u32 p) { return bas
 // bits layout per candidate read: 3 planes (A, O, N) of `words_per_read` u32 each
 template <int WM>
 __global__ void __launch_bounds__(256)
-    k_mercy_probe(ReadsView rv, const u64 *__restrict__ cand_ids, u64 n_cand, u32 k, const u32 *__restrict__ edges,
-                  long long n_edges, u32 we, u32 *__restrict__ bits, u32 words_per_read) {
+    k_mercy_probe(ReadsView rv, const u64 *__restrict__ cand_ids, u64 n_cand, u32 k, const EdgeSegs sg, u32 we,
+                  u32 *__restrict__ bits, u32 words_per_read) {
   using Ops = MercyOps<WM>;
   const u32 lane = lane_id();
   for (u64 c = (u64)blockIdx.x * 8 + (threadIdx.x >> 5); c < n_cand; c += (u64)gridDim.x * 8) {
@@ -118,7 +133,7 @@ __global__ void __launch_bounds__(256)
         reverse_sub<WM>(S, k, km);
         complement_sub<WM>(S, k, rvk);  // rc(reverse(S)) = complement(S)
         // ---- has_in searches (:225-251) ----
-        if (Ops::search(edges, n_edges, we, rvk, k) != -1) {
+        if (Ops::search(sg, we, rvk, k) != nullptr) {
           A = true;
         } else {
           u32 rv1[WM], km1[WM];
@@ -129,17 +144,17 @@ __global__ void __launch_bounds__(256)
           for (u32 ch = 0; ch < 4; ++ch) {
             Ops::set_base(km1, 0, ch);
             if (Ops::cmp(km1, rv1, k + 1) > 0) break;
-            if (Ops::search(edges, n_edges, we, km1, k + 1) != -1) {
+            if (Ops::search(sg, we, km1, k + 1) != nullptr) {
               A = true;
               break;
             }
           }
         }
         // ---- has_out searches (:254-298) ----
-        const long long e = Ops::search(edges, n_edges, we, km, k);
-        if (e != -1) {
+        const u32 *e = Ops::search(sg, we, km, k);
+        if (e != nullptr) {
           O = true;
-          if (i + k < L && base_at(edges + e * we, k) == pkg_base(s, L, i + k)) N = true;
+          if (i + k < L && base_at(e, k) == pkg_base(s, L, i + k)) N = true;
         } else {
           u32 km1[WM], rv1[WM];
 #pragma unroll
@@ -147,7 +162,7 @@ __global__ void __launch_bounds__(256)
           Ops::set_base(km1, k, 3);
           const u32 next_char = i + k < L ? 3u - pkg_base(s, L, i + k) : 0u;
           Ops::preappend(rvk, next_char, k, rv1);
-          if (Ops::cmp(rv1, km1, k + 1) <= 0 && Ops::search(edges, n_edges, we, rv1, k + 1) != -1) {
+          if (Ops::cmp(rv1, km1, k + 1) <= 0 && Ops::search(sg, we, rv1, k + 1) != nullptr) {
             O = true;
             N = true;
           } else {
@@ -155,7 +170,7 @@ __global__ void __launch_bounds__(256)
               if (ch == next_char) continue;
               Ops::set_base(rv1, 0, ch);
               if (Ops::cmp(rv1, km1, k + 1) > 0) break;
-              if (Ops::search(edges, n_edges, we, rv1, k + 1) != -1) {
+              if (Ops::search(sg, we, rv1, k + 1) != nullptr) {
                 O = true;
                 break;
               }

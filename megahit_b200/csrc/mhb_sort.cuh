@@ -75,11 +75,15 @@ __device__ __forceinline__ u32 rec_digit(const u32 (&r)[WR], u32 widx, u32 bsel)
 
 static constexpr int kLbWindow = 4;  // look-back descriptors fetched per round trip
 
-template <int WR, int CFG = 0>
+// OWNER_LUT: the digit is digit_lut[record byte] instead of the byte itself (multi-GPU partition pass: the digit is the
+// owning rank, so each tile leaves ONE long contiguous run per destination GPU instead of one short run per byte value
+// - NVLink-friendly stores; the full sort on the owner re-sorts that byte anyway).
+template <int WR, int CFG = 0, bool OWNER_LUT = false>
 __global__ void __launch_bounds__(SortCfg<WR, CFG>::THREADS, SortCfg<WR, CFG>::MIN_BLOCKS)
     k_radix_pass(const u32 *__restrict__ in, u64 n, u32 num_tiles, int byte_idx,
                  const u64 *__restrict__ bin_addr /*byte address of each digit's first output record*/,
-                 u64 *lookback, u32 *tile_counter, u64 *next_hist, int next_byte, u32 epoch) {
+                 u64 *lookback, u32 *tile_counter, u64 *next_hist, int next_byte, u32 epoch,
+                 const uint8_t *__restrict__ digit_lut = nullptr) {
   using C = SortCfg<WR, CFG>;
   constexpr int THREADS = C::THREADS, IPT = C::IPT, TILE = C::TILE, NW = C::NW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -99,6 +103,11 @@ __global__ void __launch_bounds__(SortCfg<WR, CFG>::THREADS, SortCfg<WR, CFG>::M
   u32 *my_hist = s_warp_hist + warp * 256;
 
   for (int i = tid; i < 256; i += THREADS) s_next[i] = 0;
+  __shared__ uint8_t s_lut[OWNER_LUT ? 256 : 1];
+  if constexpr (OWNER_LUT) {
+    for (int i = tid; i < 256; i += THREADS) s_lut[i] = digit_lut[i];
+    __syncthreads();
+  }
 
   while (true) {
     if (tid == 0) s_misc[0] = atomicAdd(tile_counter, 1u);
@@ -135,7 +144,8 @@ __global__ void __launch_bounds__(SortCfg<WR, CFG>::THREADS, SortCfg<WR, CFG>::M
     u32 rk[IPT];  // digit << 16 | rank within (warp, digit)
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
-      const u32 d = rec_digit<WR>(r[i], widx, bsel);
+      u32 d = rec_digit<WR>(r[i], widx, bsel);
+      if constexpr (OWNER_LUT) d = s_lut[d];
       u32 peers = 0xffffffffu;
 #pragma unroll
       for (int bit = 0; bit < 8; ++bit) {
@@ -232,7 +242,9 @@ __global__ void __launch_bounds__(SortCfg<WR, CFG>::THREADS, SortCfg<WR, CFG>::M
         if (p < valid) {
           u32 q[WR];
           ld_rec<WR>(s_recs, p, q);
-          st_rec<WR>(reinterpret_cast<u32 *>(s_glob[rec_digit<WR>(q, widx, bsel)] + (u64)p * (WR * 4)), 0, q);
+          u32 dd = rec_digit<WR>(q, widx, bsel);
+          if constexpr (OWNER_LUT) dd = s_lut[dd];
+          st_rec<WR>(reinterpret_cast<u32 *>(s_glob[dd] + (u64)p * (WR * 4)), 0, q);
           atomicAdd(&s_next[rec_digit<WR>(q, nwidx, nbsel)], 1u);
         }
       }
@@ -243,7 +255,9 @@ __global__ void __launch_bounds__(SortCfg<WR, CFG>::THREADS, SortCfg<WR, CFG>::M
         if (p < valid) {
           u32 q[WR];
           ld_rec<WR>(s_recs, p, q);
-          st_rec<WR>(reinterpret_cast<u32 *>(s_glob[rec_digit<WR>(q, widx, bsel)] + (u64)p * (WR * 4)), 0, q);
+          u32 dd = rec_digit<WR>(q, widx, bsel);
+          if constexpr (OWNER_LUT) dd = s_lut[dd];
+          st_rec<WR>(reinterpret_cast<u32 *>(s_glob[dd] + (u64)p * (WR * 4)), 0, q);
         }
       }
     }

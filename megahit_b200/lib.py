@@ -104,7 +104,7 @@ SYMBOLS = [
     "mhb_ipc_export", "mhb_ipc_open", "mhb_ipc_close", "mhb_count_solid_scratch_bytes", "mhb_count_solid", "mhb_tipset_bytes",
     "mhb_tipset_build", "mhb_count_mark_mercy", "mhb_count_tip_edges", "mhb_s2s_extract",
     "mhb_s2s_emit_scratch_bytes", "mhb_s2s_emit", "mhb_set_device", "mhb_count_host", "mhb_s2s_host", "mhb_build_host", "mhb_free",
-    "mhb_mercy_candidates_scratch_bytes", "mhb_mercy_candidates", "mhb_mercy_edges_scratch_bytes", "mhb_mercy_edges",
+    "mhb_mercy_candidates_scratch_bytes", "mhb_mercy_candidates", "mhb_mercy_edges_scratch_bytes", "mhb_mercy_edges", "mhb_mercy_edges_segs", "mhb_edge_lut_bytes", "mhb_edge_lut_build",
     "mhb_release", "mhb_count_run", "mhb_seq2sdbg_run", "mhb_selftest_count_record", "mhb_selftest_s2s_record",
 ]
 
@@ -157,11 +157,16 @@ def load():
     L.mhb_mercy_edges.argtypes = [C.c_void_p, C.POINTER(DevReads), C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
                                   C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p,
                                   C.c_size_t]
+    L.mhb_mercy_edges_segs.argtypes = [C.c_void_p, C.POINTER(DevReads), C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
+                                       C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                       C.POINTER(C.c_uint64), C.c_void_p, C.c_size_t]
+    L.mhb_edge_lut_bytes.restype = C.c_size_t
+    L.mhb_edge_lut_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
     L.mhb_sort_pass_ms.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
                                    C.POINTER(C.c_uint32)]
     L.mhb_set_device.argtypes = [C.c_int]
     L.mhb_partition_scatter.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p,
-                                        C.c_size_t]
+                                        C.c_void_p, C.c_size_t]
     L.mhb_dev_malloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     L.mhb_dev_free.argtypes = [C.c_void_p]
     L.mhb_ipc_export.argtypes = [C.c_void_p, C.c_void_p]

@@ -69,6 +69,13 @@ def exchange_records(grouped: torch.Tensor, words: int, send_counts: np.ndarray,
     return out, n_recv
 
 
+class _RawView:
+    """int32 torch view over raw (cudaMalloc'ed) device memory, via the CUDA array interface"""
+
+    def __init__(self, ptr, nelem):
+        self.__cuda_array_interface__ = {"shape": (int(nelem),), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
+
+
 class PeerBuffers:
     """One receive buffer per rank for a stage, cudaMalloc'ed by libmhb and opened on every rank through CUDA IPC,
     so that a rank's partition kernel can store records straight into their owner's memory over NVLink."""
@@ -159,6 +166,9 @@ class MultiGpuBuild:
             recv_counts = rc.cpu().numpy()
             n_recv = int(recv_counts.sum())
             out = self._buf(tag + "_own", n_recv * words + 4, slack=1.15)
+            allr = [torch.empty_like(rc[:1]) for _ in range(self.world)]
+            dist.all_gather(allr, torch.tensor([n_recv], dtype=torch.int64, device=recs.device))
+            self._recv_tot = np.array([int(x.item()) for x in allr], np.int64)
             if self._timed:
                 self._mark(tag + "_counts")
             dist.all_to_all_single(out[: n_recv * words], grouped[: int(send.sum()) * words],
@@ -171,6 +181,7 @@ class MultiGpuBuild:
         dist.all_gather(allsend, sc)
         M = torch.stack(allsend).cpu().numpy()  # M[r][o] = records rank r sends to owner o
         recv_tot = M.sum(axis=0)
+        self._recv_tot = recv_tot
         need = int(recv_tot.max()) * words * 4 + 64
         pb = self.peer.get(tag)
         if pb is None or pb.nbytes < need:  # same decision on every rank: M is identical everywhere
@@ -179,18 +190,21 @@ class MultiGpuBuild:
             pb = self.peer[tag] = PeerBuffers(int(need * 1.2))
         rb = words * 4
         my_off = M[: self.rank].sum(axis=0)  # my block's first record inside owner o's buffer
+        # digit of the partition pass = owning rank: one long contiguous run per destination and tile
         addr = np.zeros(256, np.uint64)
+        lut = np.zeros(256, np.uint8)
         for o in range(self.world):
-            lo, hi = int(bounds[o]), int(bounds[o + 1])
-            pre = np.concatenate([[0], np.cumsum(hist_h[lo:hi])[:-1]])
-            addr[lo:hi] = np.uint64(pb.peers[o]) + (np.uint64(my_off[o]) + pre.astype(np.uint64)) * np.uint64(rb)
+            lut[int(bounds[o]):int(bounds[o + 1])] = o
+            addr[o] = np.uint64(pb.peers[o]) + np.uint64(my_off[o]) * np.uint64(rb)
         addr_dev = torch.from_numpy(addr.view(np.int64)).to(recs.device)
+        lut_dev = torch.from_numpy(lut).to(recs.device)
         if self._timed:
             self._mark(tag + "_partition")
         dist.barrier()  # every owner is done with what it received in the previous step
         if self._timed:
             self._mark(tag + "_counts")
-        lib._check(L.mhb_partition_scatter(_stream(), _ptr(recs), n, words, top_byte, _ptr(addr_dev), _ptr(ws), ws.numel()))
+        lib._check(L.mhb_partition_scatter(_stream(), _ptr(recs), n, words, top_byte, _ptr(lut_dev), _ptr(addr_dev), _ptr(ws),
+                                           ws.numel()))
         dist.barrier()  # all ranks' scatter kernels have completed: my buffer is complete
         return pb.ptr, int(recv_tot[self.rank]), bounds
 
@@ -232,7 +246,17 @@ class MultiGpuBuild:
         if timed:
             self._mark("sort1")
         cap = n_own // max(1, m) + 1
-        edges = self._buf("edges", cap * self.WE, slack=1.15)
+        # the solid edges live in a buffer every rank can read (CUDA IPC): the mercy searches of other ranks look
+        # edges up in their owner's memory over NVLink instead of gathering 12 B x all edges onto every GPU
+        lut_bytes = L.mhb_edge_lut_bytes()
+        need_e = (int(self._recv_tot.max()) // max(1, m) + 2) * self.WE * 4 + 256 + lut_bytes  # identical on every rank
+        pe = self.peer.get("edges")
+        if pe is None or pe.nbytes < need_e:
+            if pe is not None:
+                pe.close()
+            pe = self.peer["edges"] = PeerBuffers(int((need_e - lut_bytes) * 1.1) + lut_bytes)
+        lut_off = (pe.nbytes - lut_bytes) & ~255  # the 12-mer look-up table sits at the end of the shared buffer
+        edges = torch.as_tensor(_RawView(pe.ptr, lut_off // 4), device=dev)
         aux = self._buf("aux", cap, torch.uint8, slack=1.15)
         mul_hist = torch.zeros(65536, dtype=torch.int64, device=dev)
         nsol = torch.zeros(8, dtype=torch.int64, device=dev)
@@ -245,16 +269,16 @@ class MultiGpuBuild:
             self._mark("count")
 
         # ---- mercy: tip edges from every rank -> per-read marks -> candidates -> mercy edges ----
-        seq_edges = edges[: n_solid * self.WE]
         n_mercy = 0
         n_cand = 0
         if self.need_mercy:
             e2 = edges[: n_solid * self.WE].view(-1, self.WE)
             tipmask = aux[:n_solid] != 0
             tips, tipaux = e2[tipmask].contiguous(), aux[:n_solid][tipmask].contiguous()
+            lib._check(L.mhb_edge_lut_build(_stream(), C.c_void_p(pe.ptr), n_solid, k, C.c_void_p(pe.ptr + lut_off)))
             cnt = torch.tensor([tips.shape[0], n_solid], dtype=torch.int64, device=dev)
             allcnt = [torch.zeros_like(cnt) for _ in range(self.world)]
-            dist.all_gather(allcnt, cnt)
+            dist.all_gather(allcnt, cnt)  # also orders: every rank's solid edges are complete from here on
             tip_n = [int(c[0].item()) for c in allcnt]
             sol_n = [int(c[1].item()) for c in allcnt]
             mx = max(max(tip_n), 1)
@@ -270,46 +294,43 @@ class MultiGpuBuild:
             all_a = torch.cat([g[:c] for g, c in zip(ga, tip_n)]).contiguous()
             n_tip = int(all_t.shape[0])
             need = L.mhb_tipset_bytes(n_tip, k)
-            tipset = torch.empty(need, dtype=torch.uint8, device=dev)
+            tipset = self._buf("tipset", need, torch.uint8, slack=1.2)
             lib._check(L.mhb_tipset_build(_stream(), _ptr(all_t) if n_tip else None, _ptr(all_a) if n_tip else None,
                                           n_tip, k, _ptr(tipset), need, n_tip))
-            first = torch.empty(self.n_reads + 1, **i32)
-            last = torch.empty(self.n_reads + 1, **i32)
+            first = self._buf("first", self.n_reads + 1)
+            last = self._buf("last", self.n_reads + 1)
             lib._check(L.mhb_count_mark_mercy(_stream(), C.byref(reads), k, _ptr(tipset), need, n_tip, _ptr(first),
                                               _ptr(last)))
-            cand = torch.empty(self.n_reads + 1, dtype=torch.int64, device=dev)
-            cs = torch.empty(L.mhb_mercy_candidates_scratch_bytes(self.n_reads), dtype=torch.uint8, device=dev)
+            cand = self._buf("cand", self.n_reads + 1, torch.int64)
+            cs = self._buf("cand_scratch", L.mhb_mercy_candidates_scratch_bytes(self.n_reads), torch.uint8)
             nc = C.c_uint64(0)
             lib._check(L.mhb_mercy_candidates(_stream(), _ptr(first), _ptr(last), self.n_reads, _ptr(cand), C.byref(nc),
                                               _ptr(cs), cs.numel()))
             n_cand = nc.value
-            # the mercy searches look at ALL solid edges: gather them (rank order == bucket order == sorted)
-            mxs = max(max(sol_n), 1)
-            pad_e = torch.zeros(mxs * self.WE, **i32)
-            pad_e[: n_solid * self.WE] = edges[: n_solid * self.WE]
-            ge = [torch.empty_like(pad_e) for _ in range(self.world)]
-            dist.all_gather(ge, pad_e)
-            all_e = torch.cat([g[: c * self.WE] for g, c in zip(ge, sol_n)]).contiguous()
-            n_all = sum(sol_n)
-            del ge, pad_e
-            cap_m = max(1024, n_all // 4 // self.world + 1024)
-            mercy = torch.zeros(cap_m * self.WE, **i32)
             nm = C.c_uint64(0)
             if n_cand:
-                ms = torch.empty(L.mhb_mercy_edges_scratch_bytes(n_cand, self.read_len), dtype=torch.uint8, device=dev)
-                lib._check(L.mhb_mercy_edges(_stream(), C.byref(reads), _ptr(cand), n_cand, self.read_len, k, _ptr(all_e),
-                                             n_all, _ptr(mercy), cap_m, C.byref(nm), _ptr(ms), ms.numel()))
+                seg_p = (C.c_void_p * self.world)(*[C.c_void_p(q) for q in pe.peers])
+                seg_n = (C.c_uint64 * self.world)(*sol_n)
+                seg_l = (C.c_void_p * self.world)(*[C.c_void_p(q + lut_off) for q in pe.peers])
+                lut = np.zeros(256, np.uint8)
+                for o in range(self.world):
+                    lut[int(bounds[o]):int(bounds[o + 1])] = o
+                lut_c = (C.c_uint8 * 256)(*lut.tolist())
+                ms = self._buf("mercy_scratch", L.mhb_mercy_edges_scratch_bytes(n_cand, self.read_len) - lut_bytes,
+                               torch.uint8, slack=1.2)
+                # mercy edges are appended right behind this rank's solid edges (peers only read the solid part)
+                lib._check(L.mhb_mercy_edges_segs(_stream(), C.byref(reads), _ptr(cand), n_cand, self.read_len, k, self.world,
+                                                  seg_p, seg_n, seg_l, lut_c, C.c_void_p(pe.ptr + n_solid * self.WE * 4),
+                                                  cap - n_solid, C.byref(nm), _ptr(ms), ms.numel()))
             n_mercy = nm.value
-            seq_edges = torch.cat([edges[: n_solid * self.WE], mercy[: n_mercy * self.WE]]).contiguous()
-            del all_e
+        seq_edges = edges
         if timed:
             self._mark("mercy")
 
         # ---- seq2sdbg stage ----
         n_seqs = n_solid + n_mercy
         n_items = n_seqs * 6
-        seq_pad = torch.cat([seq_edges, torch.zeros(8, **i32)])
-        seqs = lib.DevSeqs(seq_pad.data_ptr(), n_seqs * self.WE, n_seqs, k + 1, None, None, None, None, self.WE)
+        seqs = lib.DevSeqs(seq_edges.data_ptr(), n_seqs * self.WE, n_seqs, k + 1, None, None, None, None, self.WE)
         sa = self._buf("s_a", n_items * self.W2 + 4, slack=1.1)
         hist2 = torch.zeros(256, dtype=torch.int64, device=dev)
         top2 = self.sbytes[-1]
