@@ -115,6 +115,10 @@ int mhb_ipc_export(const void *dev_ptr, uint8_t *handle64);
 int mhb_ipc_open(const uint8_t *handle64, void **peer_ptr);
 int mhb_ipc_close(void *peer_ptr);
 
+/* Tuning hook: selects the tile geometry / ranking variant of the radix pass for subsequent sorts (0 = default;
+ * also read once from the environment variable MHB_SORT_CFG).  Every variant produces the same output. */
+int mhb_set_sort_cfg(int cfg);
+
 /* Per-pass device times (ms, CUDA events on `stream`) of one of the last four sorts issued by this process:
  * back = 0 is the most recent.  Synchronises on that sort's last event only. */
 int mhb_sort_pass_ms(int back, double *pass_ms, uint32_t max_passes, uint32_t *n_passes, uint64_t *n_records,

@@ -12,6 +12,7 @@
 #include "mhb_mercy.cuh"
 #include "mhb_s2s.cuh"
 #include "mhb_sort.cuh"
+#include "mhb_sort3.cuh"
 
 using namespace mhb;
 
@@ -141,18 +142,28 @@ extern "C" int mhb_count_extract(void *stream, const mhb_dev_reads *reads, uint3
 // ------------------------------------------------------------------------------------------------
 // sort
 // ------------------------------------------------------------------------------------------------
+static int g_sort_cfg = -1;
+extern "C" int mhb_set_sort_cfg(int cfg) {
+  if (cfg < 0 || cfg > 12) return mhb_set_error(MHB_ERR_ARG, "unknown sort configuration %d", cfg);
+  g_sort_cfg = cfg;
+  return MHB_OK;
+}
 static int sort_cfg() {
-  static int cfg = -1;
+  int &cfg = g_sort_cfg;
   if (cfg < 0) {
     const char *e = getenv("MHB_SORT_CFG");
     cfg = e ? atoi(e) : 0;
-    if (cfg < 0 || cfg > 3) cfg = 0;
+    if (cfg < 0 || cfg > 12) cfg = 0;
   }
   return cfg;
 }
 template <int WR, int CFG>
 static u64 sort_tiles_cfg(u64 n) {
   return (n + SortCfg<WR, CFG>::TILE - 1) / SortCfg<WR, CFG>::TILE;
+}
+template <int WR, int CFG>
+static u64 sort_tiles_cfg3(u64 n) {
+  return (n + SortCfg3<WR, CFG>::TILE - 1) / SortCfg3<WR, CFG>::TILE;
 }
 template <int WR>
 static u64 sort_tiles(u64 n) {
@@ -161,9 +172,18 @@ static u64 sort_tiles(u64 n) {
       case 1: return sort_tiles_cfg<WR, 1>(n);
       case 2: return sort_tiles_cfg<WR, 2>(n);
       case 3: return sort_tiles_cfg<WR, 3>(n);
+      case 5: return sort_tiles_cfg3<WR, 5>(n);
+      case 6: return sort_tiles_cfg3<WR, 6>(n);
+      case 7: return sort_tiles_cfg3<WR, 7>(n);
+      case 8: return sort_tiles_cfg3<WR, 8>(n);
+      case 9: return sort_tiles_cfg3<WR, 9>(n);
+      case 10: return sort_tiles_cfg3<WR, 10>(n);
+      case 11: return sort_tiles_cfg3<WR, 11>(n);
+      case 12: return sort_tiles_cfg3<WR, 12>(n);
       default: break;
     }
   }
+  if (sort_cfg() >= 4) return sort_tiles_cfg3<WR, 4>(n);
   return sort_tiles_cfg<WR, 0>(n);
 }
 static u64 sort_num_tiles(u64 n, u32 words) {
@@ -202,17 +222,52 @@ static int launch_radix_pass_cfg(cudaStream_t st, const u32 *in, u64 n, int byte
   return MHB_OK;
 }
 
+template <int WR, int CFG>
+static int launch_radix_pass_cfg3(cudaStream_t st, const u32 *in, u64 n, int byte_idx, const u64 *bin_base,
+                                  u64 *lookback, u32 *tile_counter, u64 *next_hist, int next_byte, u32 epoch) {
+  using C = SortCfg3<WR, CFG>;
+  static int blocks_per_sm = 0;
+  if (!blocks_per_sm) {
+    CK(cudaFuncSetAttribute(k_radix_pass3<WR, CFG, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CK(cudaFuncSetAttribute(k_radix_pass3<WR, CFG, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_radix_pass3<WR, CFG, false, true>, C::THREADS, C::SMEM));
+    if (blocks_per_sm < 1) return mhb_set_error(MHB_ERR_CUDA, "radix pass v3 kernel (WR=%d) does not fit an SM", WR);
+    if (getenv("MHB_VERBOSE")) fprintf(stderr, "[mhb] radix pass v3 WR=%d cfg=%d: %d threads x %d rec, rank mode %d, %zu B smem, %d CTA/SM\n", WR, CFG, C::THREADS, C::IPT, C::RANK, C::SMEM, blocks_per_sm);
+  }
+  const u64 tiles = sort_tiles_cfg3<WR, CFG>(n);
+  u64 grid = (u64)blocks_per_sm * sm_count();
+  if (grid > tiles) grid = tiles;
+  if (next_hist)
+    k_radix_pass3<WR, CFG, false, true><<<(int)grid, C::THREADS, C::SMEM, st>>>(in, n, (u32)tiles, byte_idx, bin_base, lookback,
+                                                                                 tile_counter, next_hist, next_byte, epoch);
+  else
+    k_radix_pass3<WR, CFG, false, false><<<(int)grid, C::THREADS, C::SMEM, st>>>(in, n, (u32)tiles, byte_idx, bin_base, lookback,
+                                                                                  tile_counter, nullptr, 0, epoch);
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
 template <int WR>
 static int launch_radix_pass(cudaStream_t st, const u32 *in, u64 n, int byte_idx, const u64 *bin_base,
                              u64 *lookback, u32 *tile_counter, u64 *next_hist, int next_byte, u32 epoch) {
   if constexpr (WR <= 3) {
     switch (sort_cfg()) {
+      case 5: return launch_radix_pass_cfg3<WR, 5>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
+      case 6: return launch_radix_pass_cfg3<WR, 6>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
+      case 7: return launch_radix_pass_cfg3<WR, 7>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
+      case 8: return launch_radix_pass_cfg3<WR, 8>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
+      case 9: return launch_radix_pass_cfg3<WR, 9>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
+      case 10: return launch_radix_pass_cfg3<WR, 10>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
+      case 11: return launch_radix_pass_cfg3<WR, 11>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
+      case 12: return launch_radix_pass_cfg3<WR, 12>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
       case 1: return launch_radix_pass_cfg<WR, 1>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
       case 2: return launch_radix_pass_cfg<WR, 2>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
       case 3: return launch_radix_pass_cfg<WR, 3>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
       default: break;
     }
   }
+  if (sort_cfg() >= 4)
+    return launch_radix_pass_cfg3<WR, 4>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
   return launch_radix_pass_cfg<WR, 0>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
 }
 

@@ -1,0 +1,288 @@
+// mhb_sort3.cuh -- radix pass v3: the same one-sweep LSD pass as k_radix_pass (mhb_sort.cuh: ticketed tiles, warp
+// ranking, decoupled look-back, shared-memory reorder, coalesced scatter, next digit's histogram fused into the
+// scatter) rebuilt around the instruction budget.  v2 was issue-bound at ~125 thread-instructions per record
+// (profiles/r1_radix_v2_*.txt: 24 % issue-active with 2 CTAs/SM, DRAM traffic 1.01x algorithmic), of which only ~26
+// are the eight ballots.  v3 removes what surrounded them:
+//   * one tile ticket is prefetched a whole tile ahead (the global atomic's latency is never exposed);
+//   * per-warp digit counters are read by ALL lanes before the leader bumps them (no shuffle, no divergent load);
+//   * the prefix over warps, the tile scan and the fold of the digit's start run as ONE pass of 256 threads
+//     (6 block barriers per tile instead of 9, no separate fold loop, no s_bin_start array);
+//   * full tiles take a scatter path without per-record bounds checks;
+//   * counters are cleared with 128-bit stores while the scatter's global stores are in flight.
+// RANK selects how a lane finds the lanes holding the same digit:
+//   0 = eight vote.ballot (constant cost, no shared-memory traffic),
+//   1 = shared-memory OR-match: red.or the lane bit into a per-warp {mask,count} slot, read both back with one
+//       64-bit load (2 shared-memory instructions instead of ~26 ALU ones; cost depends on digit collisions).
+#pragma once
+#include "mhb_sort.cuh"
+
+namespace mhb {
+
+template <int WR, int CFG>
+struct SortCfg3 {
+  // CFG: 4 = 384x18 ballot, 5 = 384x18 OR-match, 6 = 256x18 ballot 3 CTA/SM, 7 = 384x16 ballot + prefetch,
+  //      8 = 256x18 OR-match 3 CTA/SM, 9 = 4 + prefetch, 10 = 6 + prefetch, 11 = 8 + prefetch, 12 = 5 + prefetch
+  static constexpr int RANK = (CFG == 5 || CFG == 8 || CFG == 11 || CFG == 12) ? 1 : 0;
+  static constexpr bool PREFETCH = CFG == 7 || CFG >= 9;
+  static constexpr int THREADS = (CFG == 6 || CFG == 8 || CFG == 10 || CFG == 11) ? 256 : 384;
+  static constexpr int MIN_BLOCKS = THREADS == 256 ? 3 : 2;
+  static constexpr int IPT_NARROW = CFG == 7 ? 16 : 18;
+  static constexpr int IPT = WR <= 2 ? IPT_NARROW
+                                     : (WR <= 3 ? (IPT_NARROW * 2) / 3 : (WR <= 4 ? 10 : (WR <= 6 ? 6 : (WR <= 9 ? 4 : 2))));
+  static constexpr int TILE = THREADS * IPT;
+  static constexpr int NW = THREADS / 32;
+  static constexpr int CSTRIDE = RANK == 1 ? 2 : 1;  // words per counter slot ({mask,count} when OR-matching)
+  static constexpr size_t SMEM = 256 * 8 /*s_glob*/ + (size_t)NW * 256 * CSTRIDE * 4 /*counters*/ + 256 * 4 /*s_next*/ +
+                                 16 * 4 /*misc*/ + (size_t)TILE * WR * 4;
+};
+
+static constexpr int kLbWin3 = 2;  // look-back descriptors fetched per round trip (v3: register budget)
+
+// the next tile's records are requested as soon as this tile's registers are free (after the shared-memory reorder), so
+// the DRAM latency of the loads hides behind the look-back and the scatter.  asm volatile pins the loads there.
+template <int WR>
+__device__ __forceinline__ void ld_rec_pinned(const u32 *base, u64 idx, u32 (&r)[WR]) {
+  if constexpr (WR == 2) {
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "l"(base + idx * 2));
+  } else if constexpr (WR == 4) {
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "l"(base + idx * 4));
+  } else {
+    const u32 *p = base + idx * WR;
+#pragma unroll
+    for (int j = 0; j < WR; ++j) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r[j]) : "l"(p + j));
+  }
+}
+
+template <int WR, int CFG, bool OWNER_LUT = false, bool HAS_NEXT = true>
+__global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>::MIN_BLOCKS)
+    k_radix_pass3(const u32 *__restrict__ in, u64 n, u32 num_tiles, int byte_idx,
+                  const u64 *__restrict__ bin_addr /*byte address of each digit's first output record*/, u64 *lookback,
+                  u32 *tile_counter, u64 *next_hist, int next_byte, u32 epoch,
+                  const uint8_t *__restrict__ digit_lut = nullptr) {
+  using C = SortCfg3<WR, CFG>;
+  constexpr int THREADS = C::THREADS, IPT = C::IPT, TILE = C::TILE, NW = C::NW, RANK = C::RANK, CS = C::CSTRIDE;
+  constexpr int CO = CS - 1;  // word offset of the count inside a slot
+  constexpr bool PREFETCH = C::PREFETCH;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u64 *s_glob = reinterpret_cast<u64 *>(smem_raw);        // 256: byte address of the digit's slot for tile position 0
+  u32 *s_cnt = reinterpret_cast<u32 *>(s_glob + 256);     // NW * 256 * CS
+  u32 *s_next = s_cnt + NW * 256 * CS;                    // 256
+  u32 *s_misc = s_next + 256;                             // 16: [0] ticket, [4..12] scan
+  u32 *s_recs = s_misc + 16;                              // TILE * WR (16-byte aligned)
+  __shared__ uint8_t s_lut[OWNER_LUT ? 256 : 1];
+
+  const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 lt_mask = lanemask_lt();
+  const u32 widx = (u32)(WR - 1 - (byte_idx >> 2)), bsel = (u32)(byte_idx & 3);
+  const u32 nwidx = (u32)(WR - 1 - (next_byte >> 2)), nbsel = (u32)(next_byte & 3);
+  u32 *my_cnt = s_cnt + warp * 256 * CS;
+
+  for (int i = tid; i < 256; i += THREADS) s_next[i] = 0;
+  for (int i = tid; i < NW * 256 * CS; i += THREADS) s_cnt[i] = 0;
+  if constexpr (OWNER_LUT) {
+    for (int i = tid; i < 256; i += THREADS) s_lut[i] = digit_lut[i];
+  }
+  if (tid == 0) s_misc[0] = atomicAdd(tile_counter, 1u);
+  __syncthreads();
+  u32 tile = s_misc[0];
+  const u32 pad_digit = OWNER_LUT ? (u32)s_lut[255] : 255u;  // digit the 0xFF padding records of a ragged tile get
+
+  // ---- load (warp-striped: slot i of lane l = warp chunk[i*32 + l]) ----
+  u32 r[IPT][WR];
+  auto load_tile = [&](u32 t) {
+    const u64 tb = (u64)t * TILE;
+    const u64 warp_base = tb + (u64)warp * 32 * IPT + lane;
+    if (tb + TILE <= n) {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) ld_rec_pinned<WR>(in, warp_base + (u64)i * 32, r[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        const u64 idx = warp_base + (u64)i * 32;
+        if (idx < n) {
+          ld_rec_pinned<WR>(in, idx, r[i]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < WR; ++j) r[i][j] = 0xFFFFFFFFu;  // padding sorts to the very end of the tile
+        }
+      }
+    }
+  };
+  if constexpr (PREFETCH) {
+    if (tile < num_tiles) load_tile(tile);
+  }
+
+  while (tile < num_tiles) {
+    // ticket of the NEXT tile: requested now, stored to shared memory just before this tile's last barrier, so the
+    // global atomic's latency is never waited for.  Tickets are still handed out in start order (a CTA only ever
+    // waits on smaller tickets than the ones it holds), so the look-back cannot deadlock.
+    u32 next_ticket = 0;
+    if (tid == 0) next_ticket = atomicAdd(tile_counter, 1u);
+    const u64 tile_base = (u64)tile * TILE;
+    const bool full = tile_base + TILE <= n;
+    const u32 valid = full ? (u32)TILE : (u32)(n - tile_base);
+
+    if constexpr (!PREFETCH) load_tile(tile);
+
+    // ---- rank inside the warp: rk = rank among the warp's records with the same digit << 8 | digit ----
+    u32 rk[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      u32 d = rec_digit<WR>(r[i], widx, bsel);
+      if constexpr (OWNER_LUT) d = s_lut[d];
+      u32 peers, old, below;
+      if constexpr (RANK == 0) {
+        peers = 0xffffffffu;
+#pragma unroll
+        for (int bit = 0; bit < 8; ++bit) {
+          u32 mask;
+          asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
+              "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t@!p not.b32 %0, %0;\n\t}"
+              : "=r"(mask)
+              : "r"(d), "r"(1u << bit));
+          peers &= mask;
+        }
+        volatile u32 *slot = my_cnt + d;
+        old = *slot;  // every lane reads the running count before the leader bumps it
+        __syncwarp();
+        below = __popc(peers & lt_mask);
+        if ((peers >> lane) <= 1u) *slot = old + below + 1u;  // highest peer lane: below + 1 = popc(peers)
+        __syncwarp();
+      } else {
+        u32 *slot = my_cnt + d * 2;
+        const u32 sa = smem_u32(slot);
+        asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(sa), "r"(1u << lane) : "memory");
+        __syncwarp();
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(peers), "=r"(old) : "r"(sa) : "memory");
+        __syncwarp();
+        below = __popc(peers & lt_mask);
+        if ((peers >> lane) <= 1u)  // highest peer lane: clear the mask, bump the count (below + 1 = popc(peers))
+          asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa), "r"(0u), "r"(old + below + 1u) : "memory");
+        __syncwarp();
+      }
+      rk[i] = ((old + below) << 8) | d;
+    }
+    __syncthreads();  // B1: all warps' counters final
+
+    // ---- per digit (threads 0..255): tile total, scan over digits, warp bases; publish; first look-back window ----
+    u32 total = 0, excl = 0;
+    if (tid < 256) {
+#pragma unroll
+      for (int w = 0; w < NW; ++w) total += s_cnt[(w * 256 + tid) * CS + CO];
+      u32 inc = total;
+#pragma unroll
+      for (int dd = 1; dd < 32; dd <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, inc, dd);
+        if (lane >= (u32)dd) inc += t;
+      }
+      if (lane == 31) s_misc[4 + warp] = inc;
+      excl = inc - total;
+    }
+    __syncthreads();  // B2
+    u32 pub = 0;
+    u64 win[kLbWin3];
+    if (tid == 0) s_misc[0] = next_ticket;  // requested a whole rank phase ago: no wait
+    if (tid < 256) {
+#pragma unroll
+      for (int w = 0; w < 7; ++w) excl += (warp > (u32)w) ? s_misc[4 + w] : 0u;
+      // padding records all carry digit 255 and are not real: exclude them from what we publish
+      pub = total - ((tid == pad_digit) ? (u32)(TILE - valid) : 0u);
+      st_relaxed(lookback + (u64)tile * 256 + tid, (tile == 0 ? kLbInclusive : kLbPartial) | lb_epoch(epoch) | (u64)pub);
+#pragma unroll
+      for (int j = 0; j < kLbWin3; ++j)
+        win[j] = (tile > (u32)j) ? ld_relaxed(lookback + (u64)(tile - 1 - j) * 256 + tid) : 0ull;
+      // counters become: position in the tile of the warp's first record with this digit
+      u32 run = excl;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const u32 c = s_cnt[(w * 256 + tid) * CS + CO];
+        s_cnt[(w * 256 + tid) * CS + CO] = run;
+        run += c;
+      }
+    }
+    __syncthreads();  // B3
+
+    // ---- reorder in shared memory: every digit's records become contiguous, input order kept ----
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const u32 pos = my_cnt[(rk[i] & 255u) * CS + CO] + (rk[i] >> 8);
+      st_rec<WR>(s_recs, pos, r[i]);
+    }
+    const u32 next_tile = s_misc[0];  // written before B3, rewritten only after the next tile's B2
+    if constexpr (PREFETCH) {
+      if (next_tile < num_tiles) load_tile(next_tile);
+    }
+
+    // ---- global offsets by decoupled look-back, kLbWin3 descriptors per round trip ----
+    if (tid < 256) {
+      u64 prefix = 0;
+      if (tile > 0) {
+        u32 p = tile - 1;  // descriptor win[0] belongs to tile p
+        bool done = false;
+        while (!done) {
+#pragma unroll
+          for (int j = 0; j < kLbWin3; ++j) {
+            if (done) break;
+            u64 v = win[j];
+            const u64 *pp = lookback + (u64)(p - j) * 256 + tid;
+            while ((v & kLbStatusMask) == 0 || (v & lb_epoch(255)) != lb_epoch(epoch)) v = ld_relaxed(pp);
+            prefix += v & kLbValueMask;
+            if ((v & kLbStatusMask) == kLbInclusive || p == (u32)j) done = true;
+          }
+          if (!done) {
+            p -= kLbWin3;
+#pragma unroll
+            for (int j = 0; j < kLbWin3; ++j)
+              win[j] = (p >= (u32)j) ? ld_relaxed(lookback + (u64)(p - j) * 256 + tid) : 0ull;
+          }
+        }
+        st_relaxed(lookback + (u64)tile * 256 + tid, kLbInclusive | lb_epoch(epoch) | (prefix + (u64)pub));
+      }
+      s_glob[tid] = bin_addr[tid] + (prefix - (u64)excl) * (u64)(WR * 4);  // may address another GPU's memory
+    }
+    __syncthreads();  // B4: s_recs and s_glob complete; nobody reads the counters any more
+
+    // ---- coalesced scatter + next digit's histogram; clear the counters for the next tile ----
+    {
+      uint4 *z = reinterpret_cast<uint4 *>(s_cnt);
+      for (int i = tid; i < NW * 256 * CS / 4; i += THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    const u64 my_off = (u64)tid * (WR * 4);
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        const u32 p = (u32)i * THREADS + tid;
+        u32 q[WR];
+        ld_rec<WR>(s_recs, p, q);
+        u32 dd = rec_digit<WR>(q, widx, bsel);
+        if constexpr (OWNER_LUT) dd = s_lut[dd];
+        st_rec<WR>(reinterpret_cast<u32 *>(s_glob[dd] + my_off + (u64)i * (THREADS * WR * 4)), 0, q);
+        if constexpr (HAS_NEXT) atomicAdd(&s_next[rec_digit<WR>(q, nwidx, nbsel)], 1u);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        const u32 p = (u32)i * THREADS + tid;
+        if (p < valid) {
+          u32 q[WR];
+          ld_rec<WR>(s_recs, p, q);
+          u32 dd = rec_digit<WR>(q, widx, bsel);
+          if constexpr (OWNER_LUT) dd = s_lut[dd];
+          st_rec<WR>(reinterpret_cast<u32 *>(s_glob[dd] + (u64)p * (WR * 4)), 0, q);
+          if constexpr (HAS_NEXT) atomicAdd(&s_next[rec_digit<WR>(q, nwidx, nbsel)], 1u);
+        }
+      }
+    }
+    __syncthreads();  // B5: s_recs / s_glob free, counters zero
+    tile = next_tile;
+  }
+
+  if constexpr (HAS_NEXT) {
+    for (int i = tid; i < 256; i += THREADS)
+      if (s_next[i]) atomicAdd((unsigned long long *)&next_hist[i], (unsigned long long)s_next[i]);
+  }
+}
+
+}  // namespace mhb
