@@ -92,6 +92,16 @@ typedef struct {
 int mhb_count_extract(void *stream, const mhb_dev_reads *reads, uint32_t k, uint32_t *records,
                       uint64_t n_edges, uint64_t *hist256, int hist_byte);
 
+/* A13 (base_engine.cpp:54-141, 254-281: Lv1 passes over bucket ranges): the same extraction restricted to the edges
+ * whose leading record byte (first four bases) lies in [lo, hi], for libraries whose records do not fit in HBM at
+ * once.  Two calls per round: write = 0 fills per_read[0..n_reads] (device uint64) with the exclusive prefix of the
+ * per-read in-range edge counts and *total_dev with their sum; write = 1 stores the in-range records compactly, in
+ * read order, at records[per_read[r]...).  hist256 (optional, caller-zeroed) += histogram of record byte hist_byte
+ * over the in-range records. */
+int mhb_count_extract_range(void *stream, const mhb_dev_reads *reads, uint32_t k, uint32_t lo, uint32_t hi, int write,
+                            uint64_t *per_read, uint32_t *records, uint64_t *hist256, int hist_byte,
+                            uint64_t *total_dev);
+
 /* A4: stable LSD radix sort of n records of `words` uint32 each, ascending on the given byte
  * positions (least significant first).  `first_hist` = histogram of bytes[0] if the caller already has
  * it (from mhb_count_extract / mhb_s2s_extract), else NULL.  Result is left in `a` if *result_in_b == 0
@@ -232,10 +242,15 @@ typedef struct {
   int64_t counting[MHB_MAX_MUL + 1]; /* edge_counter.h:44-52 */
   double t_h2d_ms, t_extract_ms, t_sort_ms, t_count_ms, t_mercy_ms, t_d2h_ms, t_total_ms;
   uint32_t n_sort_passes;
+  uint32_t n_rounds;        /* 1, or the number of leading-byte rounds when the records did not fit at once (A13) */
   double sort_pass_ms[64];
 } mhb_count_result;
 
 int mhb_count_host(const mhb_count_args *args, mhb_count_result *res);
+/* A13 (base_engine.cpp:54-141 AdjustMemory): mhb_count_host runs in rounds over ranges of the leading record byte
+ * when the records of the whole library do not fit in device memory; this caps a round at max_records_per_round
+ * records regardless of memory (0 = derive from free device memory).  The result does not depend on the cap. */
+int mhb_set_round_limit(uint64_t max_records_per_round);
 
 typedef struct {
   uint32_t k;

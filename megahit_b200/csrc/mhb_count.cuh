@@ -115,6 +115,53 @@ __global__ void __launch_bounds__(kExtractThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
+// K-extract restricted to a range of leading bytes (A13; base_engine.cpp:254-281 Lv1 passes over bucket ranges):
+// when the records of a whole library do not fit in HBM the count stage runs in rounds, each round extracting only
+// the edges whose first four bases (top record byte) lie in [lo, hi].  Two launches, no atomics, read order kept:
+//   WRITE = false: per_read[r] = number of in-range edges of read r (+ optional histogram of record byte hist_byte)
+//   WRITE = true : per_read[r] = exclusive prefix of those counts; in-range records are stored compactly from there
+// ------------------------------------------------------------------------------------------------
+template <int W, int WR, bool WRITE>
+__global__ void __launch_bounds__(kExtractThreads)
+    k_count_extract_range(ReadsView rv, u32 k, u32 lo, u32 hi, u64 *__restrict__ per_read, u32 *__restrict__ records,
+                          u64 *hist, int hist_byte) {
+  __shared__ u32 s_hist[256];
+  for (int i = threadIdx.x; i < 256; i += kExtractThreads) s_hist[i] = 0;
+  const u32 lane = lane_id();
+  const u32 lt_mask = lanemask_lt();
+  const u32 K1 = k + 1;
+  for_each_read(rv, [&](u64 r, const u32 *s, u32 nwords, u32 L) {
+    if (L < K1) {  // kmer_counter.cpp:124
+      if (!WRITE && lane == 0) per_read[r] = 0;
+      return;
+    }
+    const u32 n_e = L - k;
+    u64 run = WRITE ? per_read[r] : 0ull;
+    for (u32 q0 = 0; q0 < n_e; q0 += 32) {
+      const u32 q = q0 + lane;
+      u32 rec[WR], strand;
+      bool in = false;
+      if (q < n_e) {
+        make_count_record<W, WR>(s, nwords, L, k, q, rec, strand);
+        const u32 top = rec[0] >> 24;
+        in = top >= lo && top <= hi;
+      }
+      const u32 mask = __ballot_sync(0xffffffffu, in);
+      if (in) {
+        if constexpr (WRITE) st_rec<WR>(records, run + __popc(mask & lt_mask), rec);
+        if (hist) atomicAdd(&s_hist[rec_byte<WR>(rec, hist_byte)], 1u);
+      }
+      run += __popc(mask);
+    }
+    if (!WRITE && lane == 0) per_read[r] = run;
+  });
+  __syncthreads();
+  if (hist)
+    for (int i = threadIdx.x; i < 256; i += kExtractThreads)
+      if (s_hist[i]) atomicAdd((unsigned long long *)&hist[i], (unsigned long long)s_hist[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K-count (A5/A6; kmer_counter.cpp:254-381).  v1: one thread per run head walks its run.
 // info[i] = 0 for non-heads, else 1 | solid<<1 | no_in<<2 | no_out<<3 | min(count,65535)<<8
 // ------------------------------------------------------------------------------------------------

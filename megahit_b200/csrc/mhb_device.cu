@@ -139,6 +139,45 @@ extern "C" int mhb_count_extract(void *stream, const mhb_dev_reads *reads, uint3
   return MHB_OK;
 }
 
+// A13: one round of the out-of-core count stage.  write == 0: per_read[r] <- in-range edge count of read r, then an
+// in-place exclusive scan (per_read[n_reads] and *total_dev <- total); hist256 (optional) += histogram of byte
+// hist_byte over the in-range records.  write != 0: per_read holds the scanned offsets; the in-range records go to
+// records[per_read[r] ...) in read order and hist256 += histogram of hist_byte (the first sort digit).
+extern "C" int mhb_count_extract_range(void *stream, const mhb_dev_reads *reads, uint32_t k, uint32_t lo, uint32_t hi,
+                                       int write, uint64_t *per_read, uint32_t *records, uint64_t *hist256, int hist_byte,
+                                       uint64_t *total_dev) {
+  if (int rc = check_reads(reads, k)) return rc;
+  if (lo > hi || hi > 255) return mhb_set_error(MHB_ERR_ARG, "bad leading-byte range [%u, %u]", lo, hi);
+  if (!per_read || (write && !records) || (!write && !total_dev)) return mhb_set_error(MHB_ERR_ARG, "null buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (reads->n_reads == 0) {
+    if (!write) CK(cudaMemsetAsync(total_dev, 0, 8, st));
+    return MHB_OK;
+  }
+  const ReadsView rv = make_reads_view(reads);
+  const u32 W = count_key_words(k), WR = count_record_words(k);
+  const u64 n_batches = (rv.n_reads + kReadsPerBatch - 1) / kReadsPerBatch;
+  const int grid = (int)(n_batches < (u64)(sm_count() * 8) ? n_batches : (u64)(sm_count() * 8));
+#define M2(WW, WRR)                                                                                                   \
+  if (W == WW && WR == WRR) {                                                                                         \
+    if (write)                                                                                                        \
+      k_count_extract_range<WW, WRR, true><<<grid, kExtractThreads, 0, st>>>(rv, k, lo, hi, per_read, records, hist256, hist_byte); \
+    else                                                                                                              \
+      k_count_extract_range<WW, WRR, false><<<grid, kExtractThreads, 0, st>>>(rv, k, lo, hi, per_read, records, hist256, hist_byte); \
+  } else
+#define M(WW) M2(WW, WW) M2(WW, WW + 1)
+  MHB_FOR_W(M) return mhb_set_error(MHB_ERR_ARG, "unsupported k=%u", k);
+#undef M
+#undef M2
+  CK_LAUNCH();
+  if (!write) {
+    k_scan_u64<<<1, 1024, 0, st>>>(per_read, rv.n_reads, total_dev);
+    CK_LAUNCH();
+    CK(cudaMemcpyAsync(per_read + rv.n_reads, total_dev, 8, cudaMemcpyDeviceToDevice, st));
+  }
+  return MHB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // sort
 // ------------------------------------------------------------------------------------------------

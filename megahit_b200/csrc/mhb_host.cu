@@ -133,6 +133,246 @@ extern "C" int mhb_release(void) {
 }
 
 // ================================================================================================
+// count, out of core (A13): rounds over ranges of the leading record byte
+// ================================================================================================
+namespace {
+uint64_t g_round_limit = 0;  // 0 = derive from free device memory
+
+// bytes of device memory one round of `n` records needs besides the resident read library
+size_t round_bytes(uint64_t n, uint32_t WR, uint32_t WE, int32_t m) {
+  const uint64_t cap_edges = n / (uint64_t)std::max(1, m) + 1;
+  return 2 * Arena::pad((size_t)n * WR * 4 + 16) + Arena::pad(mhb_sort_workspace_bytes(n, WR)) +
+         Arena::pad(mhb_count_solid_scratch_bytes(n)) + Arena::pad((size_t)cap_edges * WE * 4) + Arena::pad(cap_edges);
+}
+}  // namespace
+
+extern "C" int mhb_set_round_limit(uint64_t max_records_per_round) {
+  g_round_limit = max_records_per_round;
+  return MHB_OK;
+}
+
+// The reference plans Lv1 passes over bucket ranges so that every pass fits the memory it was given
+// (base_engine.cpp:54-141 AdjustMemory, :254-281 Lv1FindEndBuckets); the output does not depend on where the pass
+// boundaries fall.  Here a round = a contiguous range of leading record bytes (four bases) whose records fit in HBM
+// next to the resident read library: extract that range -> sort -> solid edges -> append to the host result.  Rounds
+// ascend, so the concatenated edges are sorted.  Tip edges (aux != 0) of all rounds are collected on the host and the
+// mercy bookkeeping runs once at the end over the whole library.
+static int count_host_rounds(const mhb_count_args *args, mhb_count_result *res, const BinIndex &ix, uint64_t max_records) {
+  const uint32_t k = args->k;
+  const int32_t m = args->m;
+  const uint64_t n = ix.n_edges, n_reads = args->n_reads;
+  const uint32_t WR = count_record_words(k), WE = words_per_edge(k);
+  uint8_t sort_bytes[72];
+  const uint32_t n_sort = mhb_count_sort_bytes(k, sort_bytes);
+  const int top_byte = (int)(4 * WR - 1);
+  cudaStream_t st = 0;
+  Timer t_all(st), t(st);
+  t_all.start();
+
+  const size_t bin_bytes = (args->bin_words * 4 + 15) & ~(size_t)15;
+  size_t fixed = Arena::pad(bin_bytes + 16) + Arena::pad((n_reads + 2) * 8) + Arena::pad(65536 * 8) + 2 * Arena::pad(256 * 8) +
+                 Arena::pad(64) + 8192;
+  if (!ix.fixed_len) fixed += 2 * Arena::pad((n_reads + 1) * 8);
+  if (args->want_mercy) fixed += 2 * Arena::pad((size_t)(n_reads + 1) * 4);
+  if (!max_records) {
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t avail = (size_t)((double)(free_b + g_arena.cap) * 0.92);
+    if (avail <= fixed) return mhb_set_error(MHB_ERR_NOMEM, "the read library alone (%zu bytes) does not fit the device", fixed);
+    uint64_t lo = 1, hi = n;  // largest round that fits (round_bytes is monotone)
+    while (lo < hi) {
+      const uint64_t mid = lo + (hi - lo + 1) / 2;
+      if (fixed + round_bytes(mid, WR, WE, m) <= avail) lo = mid;
+      else hi = mid - 1;
+    }
+    max_records = lo;
+  }
+  max_records = std::min<uint64_t>(std::max<uint64_t>(max_records, 1), std::max<uint64_t>(n, 1));
+  const uint64_t cap_edges = max_records / (uint64_t)std::max(1, m) + 1;
+  CKR(g_arena.reserve(fixed + round_bytes(max_records, WR, WE, m)));
+
+  uint32_t *d_bin = g_arena.take<uint32_t>(bin_bytes / 4 + 4);
+  uint64_t *d_per_read = g_arena.take<uint64_t>(n_reads + 2);
+  uint64_t *d_mul_hist = g_arena.take<uint64_t>(65536);
+  uint64_t *d_hist0 = g_arena.take<uint64_t>(256);
+  uint64_t *d_hist_top = g_arena.take<uint64_t>(256);
+  uint64_t *d_scalars = g_arena.take<uint64_t>(8);  // [0] n_solid, [1] round total
+  uint64_t *d_rec_off = nullptr, *d_edge_off = nullptr;
+  uint32_t *d_first = nullptr, *d_last = nullptr;
+  if (!ix.fixed_len) {
+    d_rec_off = g_arena.take<uint64_t>(n_reads + 1);
+    d_edge_off = g_arena.take<uint64_t>(n_reads + 1);
+  }
+  if (args->want_mercy) {
+    d_first = g_arena.take<uint32_t>(n_reads + 1);
+    d_last = g_arena.take<uint32_t>(n_reads + 1);
+  }
+  uint32_t *d_a = g_arena.take<uint32_t>((size_t)max_records * WR + 4);
+  uint32_t *d_b = g_arena.take<uint32_t>((size_t)max_records * WR + 4);
+  const size_t ws_bytes = mhb_sort_workspace_bytes(max_records, WR);
+  const size_t scratch_bytes = mhb_count_solid_scratch_bytes(max_records);
+  char *d_ws = g_arena.take<char>(ws_bytes);
+  char *d_scratch = g_arena.take<char>(scratch_bytes);
+  uint32_t *d_edges = g_arena.take<uint32_t>((size_t)cap_edges * WE);
+  uint8_t *d_aux = g_arena.take<uint8_t>(cap_edges);
+
+  t.start();
+  if (args->bin_words) CK(cudaMemcpyAsync(d_bin, args->bin, args->bin_words * 4, cudaMemcpyHostToDevice, st));
+  if (!ix.fixed_len && n_reads) {
+    CK(cudaMemcpyAsync(d_rec_off, ix.rec_off.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_edge_off, ix.edge_off.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaMemsetAsync(d_mul_hist, 0, 65536 * 8, st));
+  CK(cudaMemsetAsync(d_hist_top, 0, 256 * 8, st));
+  res->t_h2d_ms = t.stop();
+
+  mhb_dev_reads reads;
+  reads.bin = d_bin;
+  reads.bin_words = args->bin_words;
+  reads.n_reads = n_reads;
+  reads.fixed_len = ix.fixed_len;
+  reads.rec_off = d_rec_off;
+  reads.edge_off = d_edge_off;
+
+  // ---- plan: histogram of the leading byte over the whole library, then greedy contiguous ranges ----
+  t.start();
+  uint64_t h_top[256];
+  CKR(mhb_count_extract_range(st, &reads, k, 0, 255, 0, d_per_read, nullptr, d_hist_top, top_byte, d_scalars + 1));
+  CK(cudaMemcpyAsync(h_top, d_hist_top, sizeof(h_top), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  std::vector<std::pair<uint32_t, uint32_t>> ranges;
+  {
+    uint32_t lo = 0;
+    uint64_t acc = 0;
+    for (uint32_t b = 0; b < 256; ++b) {
+      if (h_top[b] > max_records)
+        return mhb_set_error(MHB_ERR_NOMEM, "leading byte 0x%02x alone holds %llu records, more than one round can take (%llu)",
+                             b, (unsigned long long)h_top[b], (unsigned long long)max_records);
+      if (acc + h_top[b] > max_records) {
+        ranges.push_back({lo, b - 1});
+        lo = b;
+        acc = 0;
+      }
+      acc += h_top[b];
+    }
+    ranges.push_back({lo, 255});
+  }
+  res->t_extract_ms = t.stop();
+
+  std::vector<uint32_t> h_edges;      // all solid edges, ascending
+  std::vector<uint32_t> h_tip_edges;  // the ones with aux != 0
+  std::vector<uint8_t> h_tip_aux, h_aux;
+  uint64_t n_solid_total = 0;
+  for (const auto &rg : ranges) {
+    // ---- extract the range ----
+    t.start();
+    uint64_t n_round = 0;
+    CKR(mhb_count_extract_range(st, &reads, k, rg.first, rg.second, 0, d_per_read, nullptr, nullptr, 0, d_scalars + 1));
+    CK(cudaMemcpyAsync(&n_round, d_scalars + 1, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemsetAsync(d_hist0, 0, 256 * 8, st));
+    CK(cudaMemsetAsync(d_scalars, 0, 8, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_round > max_records) return mhb_set_error(MHB_ERR_NOMEM, "internal: round of %llu records exceeds its plan", (unsigned long long)n_round);
+    if (n_round == 0) continue;
+    CKR(mhb_count_extract_range(st, &reads, k, rg.first, rg.second, 1, d_per_read, d_a, d_hist0, sort_bytes[0], nullptr));
+    res->t_extract_ms += t.stop();
+    // ---- sort + solid edges ----
+    t.start();
+    int in_b = 0;
+    CKR(mhb_sort_records_impl(st, d_a, d_b, n_round, WR, sort_bytes, n_sort, d_hist0, d_ws, ws_bytes, &in_b, nullptr));
+    res->t_sort_ms += t.stop();
+    t.start();
+    CKR(mhb_count_solid(st, in_b ? d_b : d_a, n_round, k, m, d_edges, d_aux, cap_edges, d_mul_hist, d_scalars, d_scratch, scratch_bytes));
+    uint64_t n_solid = 0;
+    CK(cudaMemcpyAsync(&n_solid, d_scalars, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    res->t_count_ms += t.stop();
+    if (n_solid > cap_edges) return mhb_set_error(MHB_ERR_NOMEM, "internal: solid edges exceed capacity");
+    // ---- append to the host result ----
+    t.start();
+    const size_t e0 = h_edges.size();
+    h_edges.resize(e0 + (size_t)n_solid * WE);
+    h_aux.resize(n_solid);
+    if (n_solid) {
+      CK(cudaMemcpyAsync(h_edges.data() + e0, d_edges, (size_t)n_solid * WE * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(h_aux.data(), d_aux, n_solid, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    if (args->want_mercy)
+      for (uint64_t i = 0; i < n_solid; ++i)
+        if (h_aux[i]) {
+          h_tip_edges.insert(h_tip_edges.end(), h_edges.begin() + e0 + i * WE, h_edges.begin() + e0 + (i + 1) * WE);
+          h_tip_aux.push_back(h_aux[i]);
+        }
+    n_solid_total += n_solid;
+    res->t_d2h_ms += t.stop();
+    ++res->n_rounds;
+  }
+  res->n_solid = n_solid_total;
+
+  // ---- mercy bookkeeping over the whole library with the tip edges of all rounds ----
+  std::vector<uint32_t> h_first, h_last;
+  if (args->want_mercy && n_reads) {
+    t.start();
+    const uint64_t n_tip = h_tip_aux.size();
+    const size_t ts_bytes = mhb_tipset_bytes(n_tip, k);
+    const size_t list_bytes = Arena::pad(h_tip_edges.size() * 4 + 16) + Arena::pad(n_tip + 16);
+    // the per-round buffers are free now
+    char *d_tmp = nullptr;
+    bool own = false;
+    const size_t have = (size_t)max_records * WR * 4 * 2;
+    if (ts_bytes + list_bytes + 512 <= have) d_tmp = (char *)d_a;
+    else {
+      CK(cudaMalloc((void **)&d_tmp, ts_bytes + list_bytes + 512));
+      own = true;
+    }
+    uint32_t *d_tip_edges = (uint32_t *)d_tmp;
+    uint8_t *d_tip_aux = (uint8_t *)(d_tmp + Arena::pad(h_tip_edges.size() * 4 + 16));
+    char *d_tips = d_tmp + list_bytes;
+    int rc = MHB_OK;
+    if (n_tip) {
+      if (cudaMemcpyAsync(d_tip_edges, h_tip_edges.data(), h_tip_edges.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+          cudaMemcpyAsync(d_tip_aux, h_tip_aux.data(), n_tip, cudaMemcpyHostToDevice, st) != cudaSuccess)
+        rc = mhb_set_error(MHB_ERR_CUDA, "tip edge upload failed");
+    }
+    if (!rc) rc = mhb_tipset_build(st, d_tip_edges, d_tip_aux, n_tip, k, d_tips, ts_bytes, n_tip);
+    if (!rc) rc = mhb_count_mark_mercy(st, &reads, k, d_tips, ts_bytes, n_tip, d_first, d_last);
+    h_first.resize(n_reads);
+    h_last.resize(n_reads);
+    if (!rc) {
+      cudaMemcpyAsync(h_first.data(), d_first, n_reads * 4, cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(h_last.data(), d_last, n_reads * 4, cudaMemcpyDeviceToHost, st);
+      if (cudaStreamSynchronize(st) != cudaSuccess) rc = mhb_set_error(MHB_ERR_CUDA, "mercy marking failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (own) cudaFree(d_tmp);
+    if (rc) return rc;
+    res->t_mercy_ms = t.stop();
+  }
+
+  res->edges = (uint32_t *)malloc(std::max<size_t>(1, h_edges.size() * 4));
+  if (!res->edges) return mhb_set_error(MHB_ERR_NOMEM, "host malloc failed");
+  if (!h_edges.empty()) memcpy(res->edges, h_edges.data(), h_edges.size() * 4);
+  std::vector<uint64_t> h_hist(65536);
+  CK(cudaMemcpy(h_hist.data(), d_mul_hist, 65536 * 8, cudaMemcpyDeviceToHost));
+  for (int i = 0; i <= MHB_MAX_MUL; ++i) res->counting[i] = (int64_t)h_hist[i];
+  if (args->want_mercy) {  // kmer_counter.cpp:390-401
+    std::vector<uint64_t> ids;
+    for (uint64_t r = 0; r < n_reads; ++r) {
+      const uint32_t f = h_first[r], l = h_last[r];
+      if (f != MHB_SENTINEL_OFFSET && l != MHB_SENTINEL_OFFSET) {
+        ++res->n_has_tips;
+        if (l > f) ids.push_back(r);
+      }
+    }
+    res->n_cand = ids.size();
+    res->cand_ids = (uint64_t *)malloc(std::max<size_t>(1, ids.size() * 8));
+    if (!ids.empty()) memcpy(res->cand_ids, ids.data(), ids.size() * 8);
+  }
+  res->t_total_ms = t_all.stop();
+  return MHB_OK;
+}
+
+// ================================================================================================
 // count
 // ================================================================================================
 extern "C" int mhb_count_host(const mhb_count_args *args, mhb_count_result *res) {
@@ -166,6 +406,17 @@ extern "C" int mhb_count_host(const mhb_count_args *args, mhb_count_result *res)
                 Arena::pad(65536 * 8) + Arena::pad(256 * 8) + 4096;
   if (!ix.fixed_len) need += 2 * Arena::pad((n_reads + 1) * 8);
   if (args->want_mercy) need += 2 * Arena::pad((size_t)(n_reads + 1) * 4);
+  {
+    // A13: when one pass over all records does not fit the device (or the caller capped the round size), run the
+    // stage in rounds over ranges of the leading record byte
+    bool rounds = g_round_limit && n > g_round_limit;
+    if (!rounds && need > g_arena.cap) {
+      size_t free_b = 0, total_b = 0;
+      CK(cudaMemGetInfo(&free_b, &total_b));
+      rounds = (double)need > 0.92 * (double)(free_b + g_arena.cap);
+    }
+    if (rounds) return count_host_rounds(args, res, ix, g_round_limit);
+  }
   CKR(g_arena.reserve(need));
 
   uint32_t *d_bin = g_arena.take<uint32_t>(bin_bytes / 4 + 4);
@@ -218,6 +469,7 @@ extern "C" int mhb_count_host(const mhb_count_args *args, mhb_count_result *res)
   t.start();
   int in_b = 0;
   res->n_sort_passes = n ? n_sort : 0;
+  res->n_rounds = 1;
   CKR(mhb_sort_records_impl(st, d_a, d_b, n, WR, sort_bytes, n_sort, d_hist0, d_ws, ws_bytes, &in_b, res->sort_pass_ms));
   res->t_sort_ms = t.stop();
   const uint32_t *d_sorted = in_b ? d_b : d_a;

@@ -20,13 +20,15 @@ namespace mhb {
 
 template <int WR, int CFG>
 struct SortCfg3 {
-  // CFG: 4 = 384x18 ballot, 5 = 384x18 OR-match, 6 = 256x18 ballot 3 CTA/SM, 7 = 384x16 ballot + prefetch,
-  //      8 = 256x18 OR-match 3 CTA/SM, 9 = 4 + prefetch, 10 = 6 + prefetch, 11 = 8 + prefetch, 12 = 5 + prefetch
+  // CFG: 4 = 384x16 ballot, 5 = 384x16 OR-match, 6 = 256x18 ballot 3 CTA/SM, 7 = 4 + prefetch, 8 = 256x18 OR-match
+  //      3 CTA/SM, 9 = 384x18 ballot + prefetch, 10 = 6 + prefetch, 11 = 8 + prefetch, 12 = 5 + prefetch
+  //      (384 threads x 18 records needs a few spill slots under the 80-register cap of 2 CTAs/SM; x16 does not)
   static constexpr int RANK = (CFG == 5 || CFG == 8 || CFG == 11 || CFG == 12) ? 1 : 0;
   static constexpr bool PREFETCH = CFG == 7 || CFG >= 9;
   static constexpr int THREADS = (CFG == 6 || CFG == 8 || CFG == 10 || CFG == 11) ? 256 : 384;
   static constexpr int MIN_BLOCKS = THREADS == 256 ? 3 : 2;
-  static constexpr int IPT_NARROW = CFG == 7 ? 16 : 18;
+  static constexpr int IPT_NARROW = (THREADS == 384 && CFG != 9) ? 16 : 18;
+  static constexpr int LBW = PREFETCH ? 8 : 16;  // descriptors per look-back round trip (prefetch keeps the tile in registers)
   static constexpr int IPT = WR <= 2 ? IPT_NARROW
                                      : (WR <= 3 ? (IPT_NARROW * 2) / 3 : (WR <= 4 ? 10 : (WR <= 6 ? 6 : (WR <= 9 ? 4 : 2))));
   static constexpr int TILE = THREADS * IPT;
@@ -55,6 +57,38 @@ __device__ __forceinline__ void ld_rec_pinned(const u32 *base, u64 idx, u32 (&r)
   }
 }
 
+// Stores/reductions issued from the unrolled reorder / scatter loops.  As plain C++ they would be generic-address
+// stores that may alias shared memory, which forces the compiler to serialise "load record i+1" behind "store record
+// i"; as asm without a memory clobber the shared-memory loads of a whole chunk are issued back to back (the kernel is
+// latency-bound at 2 CTAs/SM, so every exposed 30-cycle LDS round trip counts).  Nothing read inside those loops is
+// written by them: s_recs/s_glob are complete before the barrier that precedes the scatter.
+template <int WR>
+__device__ __forceinline__ void st_global_rec(u64 addr, const u32 (&q)[WR]) {
+  if constexpr (WR == 2) {
+    asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(addr), "r"(q[0]), "r"(q[1]));
+  } else if constexpr (WR == 4) {
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < WR; ++j) asm volatile("st.global.u32 [%0], %1;" ::"l"(addr + 4 * j), "r"(q[j]));
+  }
+}
+__device__ __forceinline__ void red_shared_inc(u32 *p) {
+  asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_u32(p)));
+}
+template <int WR>
+__device__ __forceinline__ void st_shared_rec(u32 *base, u32 idx, const u32 (&q)[WR]) {
+  const u32 a = smem_u32(base) + idx * (WR * 4);
+  if constexpr (WR == 2) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(q[0]), "r"(q[1]));
+  } else if constexpr (WR == 4) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < WR; ++j) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + 4 * j), "r"(q[j]));
+  }
+}
+
 template <int WR, int CFG, bool OWNER_LUT = false, bool HAS_NEXT = true>
 __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>::MIN_BLOCKS)
     k_radix_pass3(const u32 *__restrict__ in, u64 n, u32 num_tiles, int byte_idx,
@@ -65,6 +99,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
   constexpr int THREADS = C::THREADS, IPT = C::IPT, TILE = C::TILE, NW = C::NW, RANK = C::RANK, CS = C::CSTRIDE;
   constexpr int CO = CS - 1;  // word offset of the count inside a slot
   constexpr bool PREFETCH = C::PREFETCH;
+  constexpr int LBW = C::LBW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64 *s_glob = reinterpret_cast<u64 *>(smem_raw);        // 256: byte address of the digit's slot for tile position 0
   u32 *s_cnt = reinterpret_cast<u32 *>(s_glob + 256);     // NW * 256 * CS
@@ -195,50 +230,72 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
         win[j] = (tile > (u32)j) ? ld_relaxed(lookback + (u64)(tile - 1 - j) * 256 + tid) : 0ull;
       // counters become: position in the tile of the warp's first record with this digit
       u32 run = excl;
+      constexpr int H = (NW + 1) / 2;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) {
-        const u32 c = s_cnt[(w * 256 + tid) * CS + CO];
-        s_cnt[(w * 256 + tid) * CS + CO] = run;
-        run += c;
+      for (int h0 = 0; h0 < NW; h0 += H) {
+        u32 c[H];
+#pragma unroll
+        for (int w = 0; w < H; ++w) c[w] = (h0 + w < NW) ? s_cnt[((h0 + w) * 256 + tid) * CS + CO] : 0u;
+#pragma unroll
+        for (int w = 0; w < H; ++w)
+          if (h0 + w < NW) {
+            s_cnt[((h0 + w) * 256 + tid) * CS + CO] = run;
+            run += c[w];
+          }
       }
     }
     __syncthreads();  // B3
 
     // ---- reorder in shared memory: every digit's records become contiguous, input order kept ----
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      const u32 pos = my_cnt[(rk[i] & 255u) * CS + CO] + (rk[i] >> 8);
-      st_rec<WR>(s_recs, pos, r[i]);
-    }
+    for (int i = 0; i < IPT; ++i) rk[i] = my_cnt[(rk[i] & 255u) * CS + CO] + (rk[i] >> 8);
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) st_shared_rec<WR>(s_recs, rk[i], r[i]);
     const u32 next_tile = s_misc[0];  // written before B3, rewritten only after the next tile's B2
     if constexpr (PREFETCH) {
       if (next_tile < num_tiles) load_tile(next_tile);
     }
 
-    // ---- global offsets by decoupled look-back, kLbWin3 descriptors per round trip ----
+    // ---- global offsets by decoupled look-back.  All CTAs run the same phases almost in step, so the nearest
+    // predecessors are still "partial" when a tile looks back and the walk to the last "inclusive" descriptor is long
+    // (profiles/r1b: 25 % of all warp samples were this loop + the CTA waiting for it at B4 when it fetched 2
+    // descriptors per L2 round trip).  After the two prefetched descriptors the walk therefore fetches LBW at a
+    // time - all loads in flight together, one round trip per LBW predecessors.
     if (tid < 256) {
       u64 prefix = 0;
       if (tile > 0) {
+        const u64 epv = lb_epoch(epoch);
         u32 p = tile - 1;  // descriptor win[0] belongs to tile p
         bool done = false;
-        while (!done) {
 #pragma unroll
-          for (int j = 0; j < kLbWin3; ++j) {
-            if (done) break;
+        for (int j = 0; j < kLbWin3; ++j) {
+          if (!done) {
             u64 v = win[j];
             const u64 *pp = lookback + (u64)(p - j) * 256 + tid;
-            while ((v & kLbStatusMask) == 0 || (v & lb_epoch(255)) != lb_epoch(epoch)) v = ld_relaxed(pp);
+            while ((v & kLbStatusMask) == 0 || (v & lb_epoch(255)) != epv) v = ld_relaxed(pp);
             prefix += v & kLbValueMask;
             if ((v & kLbStatusMask) == kLbInclusive || p == (u32)j) done = true;
           }
-          if (!done) {
-            p -= kLbWin3;
-#pragma unroll
-            for (int j = 0; j < kLbWin3; ++j)
-              win[j] = (p >= (u32)j) ? ld_relaxed(lookback + (u64)(p - j) * 256 + tid) : 0ull;
-          }
         }
-        st_relaxed(lookback + (u64)tile * 256 + tid, kLbInclusive | lb_epoch(epoch) | (prefix + (u64)pub));
+        while (!done) {
+          p -= kLbWin3;
+          u64 wv[LBW];
+#pragma unroll
+          for (int j = 0; j < LBW; ++j)
+            wv[j] = (p >= (u32)j) ? ld_relaxed(lookback + (u64)(p - j) * 256 + tid) : 0ull;
+#pragma unroll
+          for (int j = 0; j < LBW; ++j) {
+            if (!done) {
+              u64 v = wv[j];
+              const u64 *pp = lookback + (u64)(p - j) * 256 + tid;
+              while ((v & kLbStatusMask) == 0 || (v & lb_epoch(255)) != epv) v = ld_relaxed(pp);
+              prefix += v & kLbValueMask;
+              if ((v & kLbStatusMask) == kLbInclusive || p == (u32)j) done = true;
+            }
+          }
+          p -= (LBW - kLbWin3);  // so that the next `p -= kLbWin3` lands LBW further back
+        }
+        st_relaxed(lookback + (u64)tile * 256 + tid, kLbInclusive | epv | (prefix + (u64)pub));
       }
       s_glob[tid] = bin_addr[tid] + (prefix - (u64)excl) * (u64)(WR * 4);  // may address another GPU's memory
     }
@@ -251,15 +308,27 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
     }
     const u64 my_off = (u64)tid * (WR * 4);
     if (full) {
+      constexpr int CH = PREFETCH ? 4 : (WR <= 2 ? 6 : (WR <= 4 ? 4 : 2));  // records whose loads are issued together
 #pragma unroll
-      for (int i = 0; i < IPT; ++i) {
-        const u32 p = (u32)i * THREADS + tid;
-        u32 q[WR];
-        ld_rec<WR>(s_recs, p, q);
-        u32 dd = rec_digit<WR>(q, widx, bsel);
-        if constexpr (OWNER_LUT) dd = s_lut[dd];
-        st_rec<WR>(reinterpret_cast<u32 *>(s_glob[dd] + my_off + (u64)i * (THREADS * WR * 4)), 0, q);
-        if constexpr (HAS_NEXT) atomicAdd(&s_next[rec_digit<WR>(q, nwidx, nbsel)], 1u);
+      for (int c0 = 0; c0 < IPT; c0 += CH) {
+        u32 q[CH][WR];
+        u64 g[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+          if (c0 + j < IPT) ld_rec<WR>(s_recs, (u32)(c0 + j) * THREADS + tid, q[j]);
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+          if (c0 + j < IPT) {
+            u32 dd = rec_digit<WR>(q[j], widx, bsel);
+            if constexpr (OWNER_LUT) dd = s_lut[dd];
+            g[j] = s_glob[dd];
+          }
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+          if (c0 + j < IPT) {
+            st_global_rec<WR>(g[j] + my_off + (u64)(c0 + j) * (THREADS * WR * 4), q[j]);
+            if constexpr (HAS_NEXT) red_shared_inc(&s_next[rec_digit<WR>(q[j], nwidx, nbsel)]);
+          }
       }
     } else {
 #pragma unroll

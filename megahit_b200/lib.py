@@ -50,7 +50,7 @@ class CountResult(C.Structure):
                 ("n_has_tips", C.c_uint64), ("counting", C.c_int64 * 65536),
                 ("t_h2d_ms", C.c_double), ("t_extract_ms", C.c_double), ("t_sort_ms", C.c_double),
                 ("t_count_ms", C.c_double), ("t_mercy_ms", C.c_double), ("t_d2h_ms", C.c_double),
-                ("t_total_ms", C.c_double), ("n_sort_passes", C.c_uint32), ("sort_pass_ms", C.c_double * 64)]
+                ("t_total_ms", C.c_double), ("n_sort_passes", C.c_uint32), ("n_rounds", C.c_uint32), ("sort_pass_ms", C.c_double * 64)]
 
 
 class S2sArgs(C.Structure):
@@ -100,7 +100,7 @@ class Seq2SdbgOpts(C.Structure):
 SYMBOLS = [
     "mhb_last_error", "mhb_version", "mhb_device_count", "mhb_count_record_words", "mhb_words_per_edge",
     "mhb_s2s_record_words", "mhb_count_sort_bytes", "mhb_s2s_sort_bytes", "mhb_sort_workspace_bytes",
-    "mhb_count_extract", "mhb_sort_records", "mhb_sort_pass_ms", "mhb_set_sort_cfg", "mhb_partition_scatter", "mhb_dev_malloc", "mhb_dev_free",
+    "mhb_count_extract", "mhb_count_extract_range", "mhb_set_round_limit", "mhb_sort_records", "mhb_sort_pass_ms", "mhb_set_sort_cfg", "mhb_partition_scatter", "mhb_dev_malloc", "mhb_dev_free",
     "mhb_ipc_export", "mhb_ipc_open", "mhb_ipc_close", "mhb_count_solid_scratch_bytes", "mhb_count_solid", "mhb_tipset_bytes",
     "mhb_tipset_build", "mhb_count_mark_mercy", "mhb_count_tip_edges", "mhb_s2s_extract",
     "mhb_s2s_emit_scratch_bytes", "mhb_s2s_emit", "mhb_set_device", "mhb_count_host", "mhb_s2s_host", "mhb_build_host", "mhb_free",
@@ -195,6 +195,13 @@ def device_count() -> int:
 # ------------------------------------------------------------------------------------------------
 # geometry
 # ------------------------------------------------------------------------------------------------
+def set_round_limit(max_records: int = 0):
+    """Cap the records per round of the out-of-core count stage (0 = derive from free device memory)."""
+    L = load()
+    L.mhb_set_round_limit.argtypes = [C.c_uint64]
+    _check(L.mhb_set_round_limit(int(max_records)))
+
+
 def sort_pass_ms(back: int = 0):
     """(per-pass ms list, n_records, words) of a recent sort; back=0 is the latest."""
     buf = (C.c_double * 80)()
@@ -246,7 +253,7 @@ def count_host(bin_words: np.ndarray, n_reads: int, k: int, m: int, want_mercy: 
                      if want_mercy else np.zeros(0, np.uint64)),
         "n_has_tips": r.n_has_tips, "counting": np.array(r.counting, dtype=np.int64),
         "ms": {k_: getattr(r, f"t_{k_}_ms") for k_ in ("h2d", "extract", "sort", "count", "mercy", "d2h", "total")},
-        "sort_pass_ms": list(r.sort_pass_ms[: r.n_sort_passes]),
+        "sort_pass_ms": list(r.sort_pass_ms[: r.n_sort_passes]), "n_rounds": int(r.n_rounds),
     }
     L.mhb_free(r.edges)
     if want_mercy:
