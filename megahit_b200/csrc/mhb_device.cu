@@ -181,9 +181,24 @@ extern "C" int mhb_count_extract_range(void *stream, const mhb_dev_reads *reads,
 // ------------------------------------------------------------------------------------------------
 // sort
 // ------------------------------------------------------------------------------------------------
+// Radix-pass variants.  0..3 = v2 geometries (mhb_sort.cuh); 256 + bits = v3 (mhb_sort3.cuh, see SortCfg3 for the
+// bit field).  Only the listed v3 combinations are instantiated (all for 8- and 12-byte records, the first one for
+// every record width).
+#define MHB_V3_DEFAULT 0x009
+#define MHB_V3_LIST(X)                                                                                               \
+  X(0x000) X(0x009) X(0x00A) X(0x019) X(0x029) X(0x039) X(0x049) X(0x089) X(0x0A9) X(0x109) X(0x020) X(0x030) X(0x040) \
+  X(0x080) X(0x0B0) X(0x00D) X(0x08A) X(0x0AA)
+static bool v3_listed(int bits) {
+#define X(B) \
+  if (bits == B) return true;
+  MHB_V3_LIST(X)
+#undef X
+  return false;
+}
 static int g_sort_cfg = -1;
 extern "C" int mhb_set_sort_cfg(int cfg) {
-  if (cfg < 0 || cfg > 12) return mhb_set_error(MHB_ERR_ARG, "unknown sort configuration %d", cfg);
+  if (!((cfg >= 0 && cfg <= 3) || (cfg >= 256 && v3_listed(cfg - 256))))
+    return mhb_set_error(MHB_ERR_ARG, "unknown sort configuration %d", cfg);
   g_sort_cfg = cfg;
   return MHB_OK;
 }
@@ -192,7 +207,7 @@ static int sort_cfg() {
   if (cfg < 0) {
     const char *e = getenv("MHB_SORT_CFG");
     cfg = e ? atoi(e) : 0;
-    if (cfg < 0 || cfg > 12) cfg = 0;
+    if (!((cfg >= 0 && cfg <= 3) || (cfg >= 256 && v3_listed(cfg - 256)))) cfg = 0;
   }
   return cfg;
 }
@@ -206,23 +221,24 @@ static u64 sort_tiles_cfg3(u64 n) {
 }
 template <int WR>
 static u64 sort_tiles(u64 n) {
+  const int cfg = sort_cfg();
+  if (cfg >= 256) {
+    if constexpr (WR <= 3) {
+#define X(B) \
+  if (cfg - 256 == B) return sort_tiles_cfg3<WR, B>(n);
+      MHB_V3_LIST(X)
+#undef X
+    }
+    return sort_tiles_cfg3<WR, MHB_V3_DEFAULT>(n);
+  }
   if constexpr (WR <= 3) {
-    switch (sort_cfg()) {
+    switch (cfg) {
       case 1: return sort_tiles_cfg<WR, 1>(n);
       case 2: return sort_tiles_cfg<WR, 2>(n);
       case 3: return sort_tiles_cfg<WR, 3>(n);
-      case 5: return sort_tiles_cfg3<WR, 5>(n);
-      case 6: return sort_tiles_cfg3<WR, 6>(n);
-      case 7: return sort_tiles_cfg3<WR, 7>(n);
-      case 8: return sort_tiles_cfg3<WR, 8>(n);
-      case 9: return sort_tiles_cfg3<WR, 9>(n);
-      case 10: return sort_tiles_cfg3<WR, 10>(n);
-      case 11: return sort_tiles_cfg3<WR, 11>(n);
-      case 12: return sort_tiles_cfg3<WR, 12>(n);
       default: break;
     }
   }
-  if (sort_cfg() >= 4) return sort_tiles_cfg3<WR, 4>(n);
   return sort_tiles_cfg<WR, 0>(n);
 }
 static u64 sort_num_tiles(u64 n, u32 words) {
@@ -271,7 +287,7 @@ static int launch_radix_pass_cfg3(cudaStream_t st, const u32 *in, u64 n, int byt
     CK(cudaFuncSetAttribute(k_radix_pass3<WR, CFG, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_radix_pass3<WR, CFG, false, true>, C::THREADS, C::SMEM));
     if (blocks_per_sm < 1) return mhb_set_error(MHB_ERR_CUDA, "radix pass v3 kernel (WR=%d) does not fit an SM", WR);
-    if (getenv("MHB_VERBOSE")) fprintf(stderr, "[mhb] radix pass v3 WR=%d cfg=%d: %d threads x %d rec, rank mode %d, %zu B smem, %d CTA/SM\n", WR, CFG, C::THREADS, C::IPT, C::RANK, C::SMEM, blocks_per_sm);
+    if (getenv("MHB_VERBOSE")) fprintf(stderr, "[mhb] radix pass v3 WR=%d bits=0x%03x: %d threads x %d rec, rank %d, prefetch %d, look-back %d/%d, batch %d, early %d, %zu B smem, %d CTA/SM\n", WR, CFG, C::THREADS, C::IPT, C::RANK, (int)C::PREFETCH, C::LB1, C::LBW, (int)C::BATCH, (int)C::EARLY, C::SMEM, blocks_per_sm);
   }
   const u64 tiles = sort_tiles_cfg3<WR, CFG>(n);
   u64 grid = (u64)blocks_per_sm * sm_count();
@@ -289,24 +305,24 @@ static int launch_radix_pass_cfg3(cudaStream_t st, const u32 *in, u64 n, int byt
 template <int WR>
 static int launch_radix_pass(cudaStream_t st, const u32 *in, u64 n, int byte_idx, const u64 *bin_base,
                              u64 *lookback, u32 *tile_counter, u64 *next_hist, int next_byte, u32 epoch) {
+  const int cfg = sort_cfg();
+  if (cfg >= 256) {
+    if constexpr (WR <= 3) {
+#define X(B) \
+  if (cfg - 256 == B) return launch_radix_pass_cfg3<WR, B>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
+      MHB_V3_LIST(X)
+#undef X
+    }
+    return launch_radix_pass_cfg3<WR, MHB_V3_DEFAULT>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
+  }
   if constexpr (WR <= 3) {
-    switch (sort_cfg()) {
-      case 5: return launch_radix_pass_cfg3<WR, 5>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
-      case 6: return launch_radix_pass_cfg3<WR, 6>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
-      case 7: return launch_radix_pass_cfg3<WR, 7>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
-      case 8: return launch_radix_pass_cfg3<WR, 8>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
-      case 9: return launch_radix_pass_cfg3<WR, 9>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
-      case 10: return launch_radix_pass_cfg3<WR, 10>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
-      case 11: return launch_radix_pass_cfg3<WR, 11>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
-      case 12: return launch_radix_pass_cfg3<WR, 12>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
+    switch (cfg) {
       case 1: return launch_radix_pass_cfg<WR, 1>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
       case 2: return launch_radix_pass_cfg<WR, 2>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
       case 3: return launch_radix_pass_cfg<WR, 3>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
       default: break;
     }
   }
-  if (sort_cfg() >= 4)
-    return launch_radix_pass_cfg3<WR, 4>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
   return launch_radix_pass_cfg<WR, 0>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
 }
 

@@ -18,27 +18,34 @@
 
 namespace mhb {
 
+// CFG is a bit field so that single design choices can be A/B-ed on the GPU (scripts/sort_sweep.py):
+//   bits 0-1  geometry: 0 = 384 thr x 18 rec (2 CTA/SM), 1 = 384 x 20, 2 = 256 x 18 (3 CTA/SM), 3 = 384 x 16
+//   bit  2    ranking: 0 = eight ballots, 1 = shared-memory OR-match
+//   bit  3    register prefetch of the next tile
+//   bits 4-5  look-back descriptors per round trip after the first window: 2, 4, 8, 16
+//   bit  6    reorder / scatter with batched shared-memory loads (asm stores without memory clobber)
+//   bit  7    early publish: a tile's digit counts are histogrammed and published right after its load, before ranking
+//   bit  8    first (prefetched) look-back window of 4 descriptors instead of 2
 template <int WR, int CFG>
 struct SortCfg3 {
-  // CFG: 4 = 384x16 ballot, 5 = 384x16 OR-match, 6 = 256x18 ballot 3 CTA/SM, 7 = 4 + prefetch, 8 = 256x18 OR-match
-  //      3 CTA/SM, 9 = 384x18 ballot + prefetch, 10 = 6 + prefetch, 11 = 8 + prefetch, 12 = 5 + prefetch
-  //      (384 threads x 18 records needs a few spill slots under the 80-register cap of 2 CTAs/SM; x16 does not)
-  static constexpr int RANK = (CFG == 5 || CFG == 8 || CFG == 11 || CFG == 12) ? 1 : 0;
-  static constexpr bool PREFETCH = CFG == 7 || CFG >= 9;
-  static constexpr int THREADS = (CFG == 6 || CFG == 8 || CFG == 10 || CFG == 11) ? 256 : 384;
+  static constexpr int GEOM = CFG & 3;
+  static constexpr int RANK = (CFG >> 2) & 1;
+  static constexpr bool PREFETCH = (CFG >> 3) & 1;
+  static constexpr int LBW = 2 << ((CFG >> 4) & 3);
+  static constexpr bool BATCH = (CFG >> 6) & 1;
+  static constexpr bool EARLY = (CFG >> 7) & 1;
+  static constexpr int LB1 = ((CFG >> 8) & 1) ? 4 : 2;
+  static constexpr int THREADS = GEOM == 2 ? 256 : 384;
   static constexpr int MIN_BLOCKS = THREADS == 256 ? 3 : 2;
-  static constexpr int IPT_NARROW = (THREADS == 384 && CFG != 9) ? 16 : 18;
-  static constexpr int LBW = PREFETCH ? 8 : 16;  // descriptors per look-back round trip (prefetch keeps the tile in registers)
+  static constexpr int IPT_NARROW = GEOM == 1 ? 20 : (GEOM == 3 ? 16 : 18);
   static constexpr int IPT = WR <= 2 ? IPT_NARROW
                                      : (WR <= 3 ? (IPT_NARROW * 2) / 3 : (WR <= 4 ? 10 : (WR <= 6 ? 6 : (WR <= 9 ? 4 : 2))));
   static constexpr int TILE = THREADS * IPT;
   static constexpr int NW = THREADS / 32;
   static constexpr int CSTRIDE = RANK == 1 ? 2 : 1;  // words per counter slot ({mask,count} when OR-matching)
   static constexpr size_t SMEM = 256 * 8 /*s_glob*/ + (size_t)NW * 256 * CSTRIDE * 4 /*counters*/ + 256 * 4 /*s_next*/ +
-                                 16 * 4 /*misc*/ + (size_t)TILE * WR * 4;
+                                 256 * 4 /*s_early*/ + 16 * 4 /*misc*/ + (size_t)TILE * WR * 4;
 };
-
-static constexpr int kLbWin3 = 2;  // look-back descriptors fetched per round trip (v3: register budget)
 
 // the next tile's records are requested as soon as this tile's registers are free (after the shared-memory reorder), so
 // the DRAM latency of the loads hides behind the look-back and the scatter.  asm volatile pins the loads there.
@@ -99,12 +106,14 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
   constexpr int THREADS = C::THREADS, IPT = C::IPT, TILE = C::TILE, NW = C::NW, RANK = C::RANK, CS = C::CSTRIDE;
   constexpr int CO = CS - 1;  // word offset of the count inside a slot
   constexpr bool PREFETCH = C::PREFETCH;
-  constexpr int LBW = C::LBW;
+  constexpr int LBW = C::LBW, LB1 = C::LB1;
+  constexpr bool BATCH = C::BATCH, EARLY = C::EARLY;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64 *s_glob = reinterpret_cast<u64 *>(smem_raw);        // 256: byte address of the digit's slot for tile position 0
   u32 *s_cnt = reinterpret_cast<u32 *>(s_glob + 256);     // NW * 256 * CS
   u32 *s_next = s_cnt + NW * 256 * CS;                    // 256
-  u32 *s_misc = s_next + 256;                             // 16: [0] ticket, [4..12] scan
+  u32 *s_early = s_next + 256;                            // 256: tile digit counts taken right after the load (EARLY)
+  u32 *s_misc = s_early + 256;                            // 16: [0] ticket, [4..12] scan
   u32 *s_recs = s_misc + 16;                              // TILE * WR (16-byte aligned)
   __shared__ uint8_t s_lut[OWNER_LUT ? 256 : 1];
 
@@ -115,6 +124,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
   u32 *my_cnt = s_cnt + warp * 256 * CS;
 
   for (int i = tid; i < 256; i += THREADS) s_next[i] = 0;
+  for (int i = tid; i < 256; i += THREADS) s_early[i] = 0;
   for (int i = tid; i < NW * 256 * CS; i += THREADS) s_cnt[i] = 0;
   if constexpr (OWNER_LUT) {
     for (int i = tid; i < 256; i += THREADS) s_lut[i] = digit_lut[i];
@@ -160,6 +170,22 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
     const u32 valid = full ? (u32)TILE : (u32)(n - tile_base);
 
     if constexpr (!PREFETCH) load_tile(tile);
+
+    // ---- EARLY: histogram the tile's digits and publish the counts now, a whole rank phase before the tile needs its
+    // predecessors: when the following tiles look back, this descriptor is already there (no spinning on "invalid")
+    if constexpr (EARLY) {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        u32 d = rec_digit<WR>(r[i], widx, bsel);
+        if constexpr (OWNER_LUT) d = s_lut[d];
+        red_shared_inc(&s_early[d]);
+      }
+      __syncthreads();
+      if (tid < 256) {
+        const u32 c = s_early[tid] - ((tid == pad_digit) ? (u32)(TILE - valid) : 0u);
+        st_relaxed(lookback + (u64)tile * 256 + tid, (tile == 0 ? kLbInclusive : kLbPartial) | lb_epoch(epoch) | (u64)c);
+      }
+    }
 
     // ---- rank inside the warp: rk = rank among the warp's records with the same digit << 8 | digit ----
     u32 rk[IPT];
@@ -217,40 +243,58 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
     }
     __syncthreads();  // B2
     u32 pub = 0;
-    u64 win[kLbWin3];
+    u64 win[LB1];
     if (tid == 0) s_misc[0] = next_ticket;  // requested a whole rank phase ago: no wait
     if (tid < 256) {
 #pragma unroll
       for (int w = 0; w < 7; ++w) excl += (warp > (u32)w) ? s_misc[4 + w] : 0u;
       // padding records all carry digit 255 and are not real: exclude them from what we publish
       pub = total - ((tid == pad_digit) ? (u32)(TILE - valid) : 0u);
-      st_relaxed(lookback + (u64)tile * 256 + tid, (tile == 0 ? kLbInclusive : kLbPartial) | lb_epoch(epoch) | (u64)pub);
+      if constexpr (!EARLY)
+        st_relaxed(lookback + (u64)tile * 256 + tid, (tile == 0 ? kLbInclusive : kLbPartial) | lb_epoch(epoch) | (u64)pub);
 #pragma unroll
-      for (int j = 0; j < kLbWin3; ++j)
+      for (int j = 0; j < LB1; ++j)
         win[j] = (tile > (u32)j) ? ld_relaxed(lookback + (u64)(tile - 1 - j) * 256 + tid) : 0ull;
       // counters become: position in the tile of the warp's first record with this digit
       u32 run = excl;
-      constexpr int H = (NW + 1) / 2;
+      if constexpr (BATCH) {
+        constexpr int H = (NW + 1) / 2;
 #pragma unroll
-      for (int h0 = 0; h0 < NW; h0 += H) {
-        u32 c[H];
+        for (int h0 = 0; h0 < NW; h0 += H) {
+          u32 c[H];
 #pragma unroll
-        for (int w = 0; w < H; ++w) c[w] = (h0 + w < NW) ? s_cnt[((h0 + w) * 256 + tid) * CS + CO] : 0u;
+          for (int w = 0; w < H; ++w) c[w] = (h0 + w < NW) ? s_cnt[((h0 + w) * 256 + tid) * CS + CO] : 0u;
 #pragma unroll
-        for (int w = 0; w < H; ++w)
-          if (h0 + w < NW) {
-            s_cnt[((h0 + w) * 256 + tid) * CS + CO] = run;
-            run += c[w];
-          }
+          for (int w = 0; w < H; ++w)
+            if (h0 + w < NW) {
+              s_cnt[((h0 + w) * 256 + tid) * CS + CO] = run;
+              run += c[w];
+            }
+        }
+      } else {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          const u32 c = s_cnt[(w * 256 + tid) * CS + CO];
+          s_cnt[(w * 256 + tid) * CS + CO] = run;
+          run += c;
+        }
       }
     }
     __syncthreads();  // B3
 
     // ---- reorder in shared memory: every digit's records become contiguous, input order kept ----
+    if constexpr (BATCH) {
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) rk[i] = my_cnt[(rk[i] & 255u) * CS + CO] + (rk[i] >> 8);
+      for (int i = 0; i < IPT; ++i) rk[i] = my_cnt[(rk[i] & 255u) * CS + CO] + (rk[i] >> 8);
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) st_shared_rec<WR>(s_recs, rk[i], r[i]);
+      for (int i = 0; i < IPT; ++i) st_shared_rec<WR>(s_recs, rk[i], r[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        const u32 pos = my_cnt[(rk[i] & 255u) * CS + CO] + (rk[i] >> 8);
+        st_rec<WR>(s_recs, pos, r[i]);
+      }
+    }
     const u32 next_tile = s_misc[0];  // written before B3, rewritten only after the next tile's B2
     if constexpr (PREFETCH) {
       if (next_tile < num_tiles) load_tile(next_tile);
@@ -268,7 +312,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
         u32 p = tile - 1;  // descriptor win[0] belongs to tile p
         bool done = false;
 #pragma unroll
-        for (int j = 0; j < kLbWin3; ++j) {
+        for (int j = 0; j < LB1; ++j) {
           if (!done) {
             u64 v = win[j];
             const u64 *pp = lookback + (u64)(p - j) * 256 + tid;
@@ -278,7 +322,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
           }
         }
         while (!done) {
-          p -= kLbWin3;
+          p -= LB1;
           u64 wv[LBW];
 #pragma unroll
           for (int j = 0; j < LBW; ++j)
@@ -293,7 +337,8 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
               if ((v & kLbStatusMask) == kLbInclusive || p == (u32)j) done = true;
             }
           }
-          p -= (LBW - kLbWin3);  // so that the next `p -= kLbWin3` lands LBW further back
+          p += (u32)LB1;
+          p -= (u32)LBW;  // so that the next `p -= LB1` lands LBW further back (p >= LBW here)
         }
         st_relaxed(lookback + (u64)tile * 256 + tid, kLbInclusive | epv | (prefix + (u64)pub));
       }
@@ -305,9 +350,22 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
     {
       uint4 *z = reinterpret_cast<uint4 *>(s_cnt);
       for (int i = tid; i < NW * 256 * CS / 4; i += THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+      if constexpr (EARLY)
+        for (int i = tid; i < 256; i += THREADS) s_early[i] = 0;
     }
     const u64 my_off = (u64)tid * (WR * 4);
-    if (full) {
+    if (full && !BATCH) {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        const u32 p = (u32)i * THREADS + tid;
+        u32 q[WR];
+        ld_rec<WR>(s_recs, p, q);
+        u32 dd = rec_digit<WR>(q, widx, bsel);
+        if constexpr (OWNER_LUT) dd = s_lut[dd];
+        st_rec<WR>(reinterpret_cast<u32 *>(s_glob[dd] + my_off + (u64)i * (THREADS * WR * 4)), 0, q);
+        if constexpr (HAS_NEXT) atomicAdd(&s_next[rec_digit<WR>(q, nwidx, nbsel)], 1u);
+      }
+    } else if (full) {
       constexpr int CH = PREFETCH ? 4 : (WR <= 2 ? 6 : (WR <= 4 ? 4 : 2));  // records whose loads are issued together
 #pragma unroll
       for (int c0 = 0; c0 < IPT; c0 += CH) {

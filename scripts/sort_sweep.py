@@ -42,7 +42,7 @@ for words, n, sb in ((2, 1, [1, 2, 3, 4, 5, 6, 7]), (2, 4607, [1, 2, 3, 4, 5, 6,
         res.setdefault("failed", []).append([words, n])
 res["ok"] = ok
 
-def timeit(words, n, sort_bytes, reps=3):
+def timeit(words, n, sort_bytes, reps=2):
     a = torch.randint(-2**31, 2**31 - 1, (n * words + 4,), generator=g, device="cuda", dtype=torch.int32)
     b = torch.empty_like(a)
     ws = torch.empty(lib.load().mhb_sort_workspace_bytes(n, words), dtype=torch.uint8, device="cuda")
@@ -76,7 +76,7 @@ print("RESULT " + json.dumps(res))
 
 
 def main():
-    cfgs = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0, 4, 5, 6, 7, 8, 10, 12]
+    cfgs = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0] + [256 + b for b in (0x000, 0x009, 0x00A, 0x019, 0x029, 0x039, 0x049, 0x089, 0x0A9, 0x109, 0x020, 0x030, 0x040, 0x080, 0x0B0, 0x00D, 0x08A, 0x0AA)]
     n2 = int(float(sys.argv[2])) if len(sys.argv) > 2 else 1_230_000_000
     n3 = int(float(sys.argv[3])) if len(sys.argv) > 3 else 347_000_000
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
