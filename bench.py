@@ -33,6 +33,22 @@ GENOME_PER_READ = 5  # 5 Mb of genome per 1 M reads ~ 30x coverage (SURVEY.md 8d
 ERR = 0.01
 
 
+def ncu_traffic(n_reads: int, k: int):
+    """DRAM bytes (read + write) of one launch of the dominant kernel from a committed `ncu --set full` capture of this
+    same workload (profiles/radix_traffic.json, written by scripts/ncu_traffic.py); None when no capture matches."""
+    p = os.path.join(ROOT, "profiles", "radix_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    try:
+        j = json.load(open(p))
+        for e in j.get("captures", []):
+            if e.get("reads") == n_reads and e.get("k") == k:
+                return float(e["dram_bytes_per_launch"]), e.get("source")
+    except Exception:
+        pass
+    return None, None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -169,7 +185,7 @@ def ours(args):
 
     if world > 1:
         from megahit_b200 import multigpu
-        return multigpu.bench(args, bin_dev, bin_words, rank, world, device, METRIC)
+        return multigpu.bench(args, bin_dev, bin_words, rank, world, device, METRIC, clocks=ClockSampler(local))
 
     plan = dev.CountPlan(n_reads, L, k, m, device, want_mercy=True)
     n_solid = plan.run(bin_dev)  # sizes the SdBG stage (also the first warm-up)
@@ -220,9 +236,10 @@ def ours(args):
     spass = np.array(sort_ms["s2s"])
     n_items = s2s.n_items
     s2s_achieved = 2.0 * n_items * s2s.W * 4 / (float(spass.mean()) * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(n_reads, k)
     roofline = {
         "bound": "hbm", "kernel": f"k_radix_pass<{plan.WR}> (count records, {S} B)", "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": 2 * n_edges * S, "avg_launch_ms": avg_pass_ms,
         "per_pass_ms": [float(x) for x in cpass.mean(axis=0)],
         "per_pass_frac": [float(2.0 * n_edges * S / (x * 1e-3) / 1e9 / peak) for x in cpass.mean(axis=0)],

@@ -184,10 +184,10 @@ extern "C" int mhb_count_extract_range(void *stream, const mhb_dev_reads *reads,
 // Radix-pass variants.  0..3 = v2 geometries (mhb_sort.cuh); 256 + bits = v3 (mhb_sort3.cuh, see SortCfg3 for the
 // bit field).  Only the listed v3 combinations are instantiated (all for 8- and 12-byte records, the first one for
 // every record width).
-#define MHB_V3_DEFAULT 0x009
+#define MHB_V3_DEFAULT 0x080
 #define MHB_V3_LIST(X)                                                                                               \
-  X(0x000) X(0x009) X(0x00A) X(0x019) X(0x029) X(0x039) X(0x049) X(0x089) X(0x0A9) X(0x109) X(0x020) X(0x030) X(0x040) \
-  X(0x080) X(0x0B0) X(0x00D) X(0x08A) X(0x0AA)
+  X(0x080) X(0x000) X(0x009) X(0x00A) X(0x088) X(0x083) X(0x08B) X(0x081) X(0x082) X(0x08A) X(0x180) X(0x0B0) X(0x280) \
+  X(0x288) X(0x480) X(0x488) X(0x084) X(0x284)
 static bool v3_listed(int bits) {
 #define X(B) \
   if (bits == B) return true;
@@ -206,8 +206,8 @@ static int sort_cfg() {
   int &cfg = g_sort_cfg;
   if (cfg < 0) {
     const char *e = getenv("MHB_SORT_CFG");
-    cfg = e ? atoi(e) : 0;
-    if (!((cfg >= 0 && cfg <= 3) || (cfg >= 256 && v3_listed(cfg - 256)))) cfg = 0;
+    cfg = e ? atoi(e) : 256 + MHB_V3_DEFAULT;
+    if (!((cfg >= 0 && cfg <= 3) || (cfg >= 256 && v3_listed(cfg - 256)))) cfg = 256 + MHB_V3_DEFAULT;
   }
   return cfg;
 }

@@ -22,22 +22,27 @@ namespace mhb {
 //   bits 0-1  geometry: 0 = 384 thr x 18 rec (2 CTA/SM), 1 = 384 x 20, 2 = 256 x 18 (3 CTA/SM), 3 = 384 x 16
 //   bit  2    ranking: 0 = eight ballots, 1 = shared-memory OR-match
 //   bit  3    register prefetch of the next tile
-//   bits 4-5  look-back descriptors per round trip after the first window: 2, 4, 8, 16
+//   bits 4-5  look-back descriptors per round trip after the first window: 2, 4, 8, 1
 //   bit  6    reorder / scatter with batched shared-memory loads (asm stores without memory clobber)
 //   bit  7    early publish: a tile's digit counts are histogrammed and published right after its load, before ranking
-//   bit  8    first (prefetched) look-back window of 4 descriptors instead of 2
+//   bit  8    first (prefetched) look-back window of 1 descriptor instead of 2
+//   bits 9-10 high-occupancy geometries (override bits 0-1): 1 = 256 thr x 12 rec, 4 CTA/SM; 2 = 512 x 12, 2 CTA/SM
+// Measured on B200, 1.23 G 8-byte records, ms per pass (profiles/r1d_sort_sweep.txt): v2 7.24; v3 base 6.93;
+// + prefetch 6.72; + early publish 6.44 (default); wider look-back windows (8, 16) 6.8-7.6; batched loads 7.1-7.3;
+// OR-match ranking 7.3.
 template <int WR, int CFG>
 struct SortCfg3 {
   static constexpr int GEOM = CFG & 3;
+  static constexpr int GEOMX = (CFG >> 9) & 3;
   static constexpr int RANK = (CFG >> 2) & 1;
   static constexpr bool PREFETCH = (CFG >> 3) & 1;
-  static constexpr int LBW = 2 << ((CFG >> 4) & 3);
+  static constexpr int LBW = ((CFG >> 4) & 3) == 3 ? 1 : (2 << ((CFG >> 4) & 3));
   static constexpr bool BATCH = (CFG >> 6) & 1;
   static constexpr bool EARLY = (CFG >> 7) & 1;
-  static constexpr int LB1 = ((CFG >> 8) & 1) ? 4 : 2;
-  static constexpr int THREADS = GEOM == 2 ? 256 : 384;
-  static constexpr int MIN_BLOCKS = THREADS == 256 ? 3 : 2;
-  static constexpr int IPT_NARROW = GEOM == 1 ? 20 : (GEOM == 3 ? 16 : 18);
+  static constexpr int LB1 = ((CFG >> 8) & 1) ? 1 : 2;
+  static constexpr int THREADS = GEOMX == 1 ? 256 : (GEOMX == 2 ? 512 : (GEOM == 2 ? 256 : 384));
+  static constexpr int MIN_BLOCKS = GEOMX == 1 ? 4 : (GEOMX == 2 ? 2 : (THREADS == 256 ? 3 : 2));
+  static constexpr int IPT_NARROW = GEOMX ? 12 : (GEOM == 1 ? 20 : (GEOM == 3 ? 16 : 18));
   static constexpr int IPT = WR <= 2 ? IPT_NARROW
                                      : (WR <= 3 ? (IPT_NARROW * 2) / 3 : (WR <= 4 ? 10 : (WR <= 6 ? 6 : (WR <= 9 ? 4 : 2))));
   static constexpr int TILE = THREADS * IPT;

@@ -368,7 +368,7 @@ def gather_sdbg_stream(res: dict) -> bytes | None:
     return b"".join(o[1] for o in objs)  # rank order == bucket order
 
 
-def bench(args, bin_dev, bin_words, rank, world, device, metric):
+def bench(args, bin_dev, bin_words, rank, world, device, metric, clocks=None):
     """bench.py's N > 1 arm: weak scaling, `args.reads` reads per GPU, one all-to-all per stage."""
     import json
     import os
@@ -381,6 +381,8 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric):
     torch.cuda.synchronize()
     dist.barrier()
     job.times.clear()
+    if clocks is not None:
+        clocks.start()  # nvidia-smi clocks / throttle reasons of this rank's GPU during the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     res = None
@@ -392,6 +394,7 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric):
     e1.record()
     torch.cuda.synchronize()
     dist.barrier()
+    clk = clocks.stop() if clocks is not None else None
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=device)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     stage = {}
@@ -451,8 +454,9 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"synthetic {n_reads}x{L}bp reads PER GPU (30x, 1% subst.), k={k}, m={m}, {world}xB200: "
-                                   "top-byte range partition (balanced from the all-reduced histogram) + one NCCL "
-                                   "all-to-all per stage, then per-GPU radix sort / count / mercy / seq2sdbg emit",
+                                   "top-byte range partition (balanced from the all-reduced histogram), one fused partition+"
+                                   "exchange pass per stage storing into the owners' buffers over NVLink (CUDA IPC peer "
+                                   "memory), then per-GPU radix sort / count / mercy / seq2sdbg emit",
                        "parallelism": f"bucket-range x{world}", "n_edge_records": n_edges,
                        "records_owned_per_rank": [int(o[0]) for o in owns],
                        "solid_edges_per_rank": [int(o[1]) for o in owns], "mercy_edges_per_rank": [int(o[2]) for o in owns],
@@ -462,7 +466,7 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric):
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                          "peak_source": src, "avg_launch_ms": float(pm.item()),
                          "algorithmic_bytes_per_launch": 2 * n_max * S},
-            "cpu_baseline": None,
+            "cpu_baseline": None, "clocks": clk,
             "e2e": {"value": e2e_v, "unit": "edges/s", "h2d_bytes_per_step": int(world * bin_words * 4),
                     "d2h_bytes_per_step": int(nbytes.item()) + world * 65536 * 32, "ms_per_step": float(np.mean(e2e_ms)),
                     "api": "MultiGpuBuild.run on reads copied from pinned host memory each step; SdBG bytes + bucket "

@@ -75,7 +75,7 @@ def test_sort_skewed_digits():
     assert (got == _np_lsd(recs, sort_bytes)).all()
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3] + [256 + b for b in (0x000, 0x009, 0x00A, 0x039, 0x049, 0x089, 0x0A9, 0x109, 0x0B0, 0x00D, 0x0AA)])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3] + [256 + b for b in (0x080, 0x000, 0x009, 0x00A, 0x088, 0x083, 0x08B, 0x081, 0x082, 0x08A, 0x180, 0x0B0, 0x280, 0x288, 0x480, 0x488, 0x084, 0x284)])
 def test_sort_every_pass_variant(cfg):
     """every tile geometry / ranking variant of the radix pass (mhb_set_sort_cfg) gives the same stable LSD order,
     including ragged last tiles and single-tile inputs"""
@@ -95,7 +95,7 @@ def test_sort_every_pass_variant(cfg):
             got = out[: n * words].cpu().numpy().view(np.uint32).reshape(n, words)
             assert (got == _np_lsd(recs, sort_bytes)).all(), (cfg, words, n)
     finally:
-        lib._check(L.mhb_set_sort_cfg(int(os.environ.get("MHB_SORT_CFG", "0"))))
+        lib._check(L.mhb_set_sort_cfg(int(os.environ.get("MHB_SORT_CFG", str(256 + 0x080)))))
 
 
 # ------------------------------------------------------------------------------------------------
