@@ -27,6 +27,9 @@ namespace mhb {
 //   bit  7    early publish: a tile's digit counts are histogrammed and published right after its load, before ranking
 //   bit  8    first (prefetched) look-back window of 1 descriptor instead of 2
 //   bits 9-10 high-occupancy geometries (override bits 0-1): 1 = 256 thr x 12 rec, 4 CTA/SM; 2 = 512 x 12, 2 CTA/SM
+//   bit  11   (with bit 3) the prefetch is issued after the look-back, at the start of the scatter, instead of before it
+//   bit  12   (with bit 7) the scan over the digit totals also runs early, on the early histogram: one barrier and the
+//             per-warp total loop leave the critical path between ranking and the reorder
 // Measured on B200, 1.23 G 8-byte records, ms per pass (profiles/r1d_sort_sweep.txt): v2 7.24; v3 base 6.93;
 // + prefetch 6.72; + early publish 6.44 (default); wider look-back windows (8, 16) 6.8-7.6; batched loads 7.1-7.3;
 // OR-match ranking 7.3.
@@ -40,6 +43,8 @@ struct SortCfg3 {
   static constexpr bool BATCH = (CFG >> 6) & 1;
   static constexpr bool EARLY = (CFG >> 7) & 1;
   static constexpr int LB1 = ((CFG >> 8) & 1) ? 1 : 2;
+  static constexpr bool LATEPF = (CFG >> 11) & 1;
+  static constexpr bool ESCAN = EARLY && ((CFG >> 12) & 1);
   static constexpr int THREADS = GEOMX == 1 ? 256 : (GEOMX == 2 ? 512 : (GEOM == 2 ? 256 : 384));
   static constexpr int MIN_BLOCKS = GEOMX == 1 ? 4 : (GEOMX == 2 ? 2 : (THREADS == 256 ? 3 : 2));
   static constexpr int IPT_NARROW = GEOMX ? 12 : (GEOM == 1 ? 20 : (GEOM == 3 ? 16 : 18));
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
   constexpr int CO = CS - 1;  // word offset of the count inside a slot
   constexpr bool PREFETCH = C::PREFETCH;
   constexpr int LBW = C::LBW, LB1 = C::LB1;
-  constexpr bool BATCH = C::BATCH, EARLY = C::EARLY;
+  constexpr bool BATCH = C::BATCH, EARLY = C::EARLY, LATEPF = C::LATEPF, ESCAN = C::ESCAN;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64 *s_glob = reinterpret_cast<u64 *>(smem_raw);        // 256: byte address of the digit's slot for tile position 0
   u32 *s_cnt = reinterpret_cast<u32 *>(s_glob + 256);     // NW * 256 * CS
@@ -178,6 +183,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
 
     // ---- EARLY: histogram the tile's digits and publish the counts now, a whole rank phase before the tile needs its
     // predecessors: when the following tiles look back, this descriptor is already there (no spinning on "invalid")
+    u32 e_total = 0, e_excl = 0;
     if constexpr (EARLY) {
 #pragma unroll
       for (int i = 0; i < IPT; ++i) {
@@ -187,8 +193,19 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
       }
       __syncthreads();
       if (tid < 256) {
-        const u32 c = s_early[tid] - ((tid == pad_digit) ? (u32)(TILE - valid) : 0u);
+        e_total = s_early[tid];
+        const u32 c = e_total - ((tid == pad_digit) ? (u32)(TILE - valid) : 0u);
         st_relaxed(lookback + (u64)tile * 256 + tid, (tile == 0 ? kLbInclusive : kLbPartial) | lb_epoch(epoch) | (u64)c);
+        if constexpr (ESCAN) {
+          u32 inc = e_total;
+#pragma unroll
+          for (int dd = 1; dd < 32; dd <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, inc, dd);
+            if (lane >= (u32)dd) inc += t;
+          }
+          if (lane == 31) s_misc[4 + warp] = inc;  // read after B1
+          e_excl = inc - e_total;
+        }
       }
     }
 
@@ -234,19 +251,24 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
 
     // ---- per digit (threads 0..255): tile total, scan over digits, warp bases; publish; first look-back window ----
     u32 total = 0, excl = 0;
-    if (tid < 256) {
+    if constexpr (ESCAN) {
+      total = e_total;
+      excl = e_excl;
+    } else {
+      if (tid < 256) {
 #pragma unroll
-      for (int w = 0; w < NW; ++w) total += s_cnt[(w * 256 + tid) * CS + CO];
-      u32 inc = total;
+        for (int w = 0; w < NW; ++w) total += s_cnt[(w * 256 + tid) * CS + CO];
+        u32 inc = total;
 #pragma unroll
-      for (int dd = 1; dd < 32; dd <<= 1) {
-        const u32 t = __shfl_up_sync(0xffffffffu, inc, dd);
-        if (lane >= (u32)dd) inc += t;
+        for (int dd = 1; dd < 32; dd <<= 1) {
+          const u32 t = __shfl_up_sync(0xffffffffu, inc, dd);
+          if (lane >= (u32)dd) inc += t;
+        }
+        if (lane == 31) s_misc[4 + warp] = inc;
+        excl = inc - total;
       }
-      if (lane == 31) s_misc[4 + warp] = inc;
-      excl = inc - total;
+      __syncthreads();  // B2
     }
-    __syncthreads();  // B2
     u32 pub = 0;
     u64 win[LB1];
     if (tid == 0) s_misc[0] = next_ticket;  // requested a whole rank phase ago: no wait
@@ -300,8 +322,8 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
         st_rec<WR>(s_recs, pos, r[i]);
       }
     }
-    const u32 next_tile = s_misc[0];  // written before B3, rewritten only after the next tile's B2
-    if constexpr (PREFETCH) {
+    const u32 next_tile = s_misc[0];  // written before B3, rewritten only after the next tile's B1
+    if constexpr (PREFETCH && !LATEPF) {
       if (next_tile < num_tiles) load_tile(next_tile);
     }
 
@@ -351,6 +373,9 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
     }
     __syncthreads();  // B4: s_recs and s_glob complete; nobody reads the counters any more
 
+    if constexpr (PREFETCH && LATEPF) {
+      if (next_tile < num_tiles) load_tile(next_tile);  // in flight during the scatter; does not delay the look-back
+    }
     // ---- coalesced scatter + next digit's histogram; clear the counters for the next tile ----
     {
       uint4 *z = reinterpret_cast<uint4 *>(s_cnt);
