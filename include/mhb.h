@@ -251,6 +251,11 @@ int mhb_count_host(const mhb_count_args *args, mhb_count_result *res);
  * when the records of the whole library do not fit in device memory; this caps a round at max_records_per_round
  * records regardless of memory (0 = derive from free device memory).  The result does not depend on the cap. */
 int mhb_set_round_limit(uint64_t max_records_per_round);
+/* The round planner itself (host only, no GPU needed): cuts the 256 leading-byte values, given their record counts,
+ * into contiguous ranges [lo_out[i], hi_out[i]] of at most max_records records each (cf. Lv1FindEndBuckets,
+ * base_engine.cpp:254-281).  Returns the number of ranges, or -1 (mhb_last_error) when one byte value alone
+ * exceeds the cap.  lo_out / hi_out need room for 256 entries. */
+int mhb_plan_rounds(const uint64_t *hist256, uint64_t max_records, uint32_t *lo_out, uint32_t *hi_out);
 
 typedef struct {
   uint32_t k;

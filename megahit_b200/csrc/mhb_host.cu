@@ -146,6 +146,37 @@ size_t round_bytes(uint64_t n, uint32_t WR, uint32_t WE, int32_t m) {
 }
 }  // namespace
 
+// Greedy cut of the 256 leading-byte values into contiguous ranges of at most max_records records each (pure host
+// logic, callable without a GPU).  Returns the number of ranges (>= 1), or -1 when a single byte value alone exceeds
+// the cap (poly-A like skew: reported, never mis-sorted).
+extern "C" int mhb_plan_rounds(const uint64_t *hist256, uint64_t max_records, uint32_t *lo_out, uint32_t *hi_out) {
+  if (!hist256 || !lo_out || !hi_out || max_records == 0) {
+    mhb_set_error(MHB_ERR_ARG, "bad round plan arguments");
+    return -1;
+  }
+  int n = 0;
+  uint32_t lo = 0;
+  uint64_t acc = 0;
+  for (uint32_t b = 0; b < 256; ++b) {
+    if (hist256[b] > max_records) {
+      mhb_set_error(MHB_ERR_NOMEM, "leading byte 0x%02x alone holds %llu records, more than one round can take (%llu)", b,
+                    (unsigned long long)hist256[b], (unsigned long long)max_records);
+      return -1;
+    }
+    if (acc + hist256[b] > max_records) {
+      lo_out[n] = lo;
+      hi_out[n] = b - 1;
+      ++n;
+      lo = b;
+      acc = 0;
+    }
+    acc += hist256[b];
+  }
+  lo_out[n] = lo;
+  hi_out[n] = 255;
+  return n + 1;
+}
+
 extern "C" int mhb_set_round_limit(uint64_t max_records_per_round) {
   g_round_limit = max_records_per_round;
   return MHB_OK;
@@ -240,23 +271,11 @@ static int count_host_rounds(const mhb_count_args *args, mhb_count_result *res, 
   CKR(mhb_count_extract_range(st, &reads, k, 0, 255, 0, d_per_read, nullptr, d_hist_top, top_byte, d_scalars + 1));
   CK(cudaMemcpyAsync(h_top, d_hist_top, sizeof(h_top), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  uint32_t r_lo[256], r_hi[256];
+  const int n_ranges = mhb_plan_rounds(h_top, max_records, r_lo, r_hi);
+  if (n_ranges < 0) return MHB_ERR_NOMEM;  // message set by the planner
   std::vector<std::pair<uint32_t, uint32_t>> ranges;
-  {
-    uint32_t lo = 0;
-    uint64_t acc = 0;
-    for (uint32_t b = 0; b < 256; ++b) {
-      if (h_top[b] > max_records)
-        return mhb_set_error(MHB_ERR_NOMEM, "leading byte 0x%02x alone holds %llu records, more than one round can take (%llu)",
-                             b, (unsigned long long)h_top[b], (unsigned long long)max_records);
-      if (acc + h_top[b] > max_records) {
-        ranges.push_back({lo, b - 1});
-        lo = b;
-        acc = 0;
-      }
-      acc += h_top[b];
-    }
-    ranges.push_back({lo, 255});
-  }
+  for (int i = 0; i < n_ranges; ++i) ranges.push_back({r_lo[i], r_hi[i]});
   res->t_extract_ms = t.stop();
 
   std::vector<uint32_t> h_edges;      // all solid edges, ascending

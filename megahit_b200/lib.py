@@ -100,7 +100,7 @@ class Seq2SdbgOpts(C.Structure):
 SYMBOLS = [
     "mhb_last_error", "mhb_version", "mhb_device_count", "mhb_count_record_words", "mhb_words_per_edge",
     "mhb_s2s_record_words", "mhb_count_sort_bytes", "mhb_s2s_sort_bytes", "mhb_sort_workspace_bytes",
-    "mhb_count_extract", "mhb_count_extract_range", "mhb_set_round_limit", "mhb_sort_records", "mhb_sort_pass_ms", "mhb_set_sort_cfg", "mhb_partition_scatter", "mhb_dev_malloc", "mhb_dev_free",
+    "mhb_count_extract", "mhb_count_extract_range", "mhb_set_round_limit", "mhb_plan_rounds", "mhb_sort_records", "mhb_sort_pass_ms", "mhb_set_sort_cfg", "mhb_partition_scatter", "mhb_dev_malloc", "mhb_dev_free",
     "mhb_ipc_export", "mhb_ipc_open", "mhb_ipc_close", "mhb_count_solid_scratch_bytes", "mhb_count_solid", "mhb_tipset_bytes",
     "mhb_tipset_build", "mhb_count_mark_mercy", "mhb_count_tip_edges", "mhb_s2s_extract",
     "mhb_s2s_emit_scratch_bytes", "mhb_s2s_emit", "mhb_set_device", "mhb_count_host", "mhb_s2s_host", "mhb_build_host", "mhb_free",
@@ -195,6 +195,19 @@ def device_count() -> int:
 # ------------------------------------------------------------------------------------------------
 # geometry
 # ------------------------------------------------------------------------------------------------
+def plan_rounds(hist256, max_records: int):
+    """Leading-byte ranges of the out-of-core count stage (host logic only): list of (lo, hi)."""
+    L = load()
+    h = np.ascontiguousarray(hist256, dtype=np.uint64)
+    assert h.shape == (256,)
+    lo, hi = (C.c_uint32 * 256)(), (C.c_uint32 * 256)()
+    L.mhb_plan_rounds.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    n = L.mhb_plan_rounds(h.ctypes.data, int(max_records), lo, hi)
+    if n < 0:
+        raise MhbError(L.mhb_last_error().decode())
+    return [(int(lo[i]), int(hi[i])) for i in range(n)]
+
+
 def set_round_limit(max_records: int = 0):
     """Cap the records per round of the out-of-core count stage (0 = derive from free device memory)."""
     L = load()

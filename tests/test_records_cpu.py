@@ -123,3 +123,37 @@ def test_simulated_count_matches_oracle(name, k, m):
     edges[:, wpe - 1] |= np.minimum(counts[solid], 65535).astype(np.uint32)
     c = oracle_count(load_reads(case), k, m)
     assert (edges == c["edges"]).all() and len(edges) == c["n_solid"]
+
+
+# ------------------------------------------------------------------------------------------------
+# A13: the round planner of the out-of-core count stage (host logic, no GPU)
+# ------------------------------------------------------------------------------------------------
+def test_plan_rounds_covers_all_bytes_within_cap():
+    from megahit_b200 import lib
+    rng = np.random.default_rng(5)
+    for trial in range(50):
+        hist = rng.integers(0, 1000, size=256).astype(np.uint64)
+        if trial % 5 == 0:
+            hist[rng.integers(0, 256, size=200)] = 0  # sparse: most leading bytes absent
+        cap = int(max(int(hist.max()), int(hist.sum()) // int(rng.integers(1, 40))))
+        ranges = lib.plan_rounds(hist, cap)
+        # contiguous, ascending, complete
+        assert ranges[0][0] == 0 and ranges[-1][1] == 255
+        for (a, b), (c, d) in zip(ranges[:-1], ranges[1:]):
+            assert a <= b and c == b + 1
+        sums = [int(hist[a:b + 1].sum()) for a, b in ranges]
+        assert all(s <= cap for s in sums) and sum(sums) == int(hist.sum())
+        # greedy: a range could not have taken the next byte as well
+        for (a, b), s in zip(ranges[:-1], sums[:-1]):
+            assert s + int(hist[b + 1]) > cap
+
+
+def test_plan_rounds_single_round_and_oversized_byte():
+    from megahit_b200 import lib
+    hist = np.full(256, 10, np.uint64)
+    assert lib.plan_rounds(hist, 2560) == [(0, 255)]
+    assert lib.plan_rounds(hist, 10) == [(i, i) for i in range(256)]
+    hist[7] = 11
+    with pytest.raises(lib.MhbError, match="more than one round can take"):
+        lib.plan_rounds(hist, 10)
+    assert lib.plan_rounds(np.zeros(256, np.uint64), 1) == [(0, 255)]
