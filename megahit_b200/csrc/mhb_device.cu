@@ -326,6 +326,15 @@ static int launch_radix_pass(cudaStream_t st, const u32 *in, u64 n, int byte_idx
   return launch_radix_pass_cfg<WR, 0>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
 }
 
+#ifdef MHB_SORT_TIMELINE
+// diagnostic build only: point the v3 radix pass at a device buffer of rows x 16 uint64 (see mhb_sort3.cuh)
+extern "C" int mhb_debug_set_sort_timeline(unsigned long long *dev_buf, unsigned long long rows) {
+  CK(cudaMemcpyToSymbol(g_sort_timeline, &dev_buf, sizeof(dev_buf)));
+  CK(cudaMemcpyToSymbol(g_sort_timeline_rows, &rows, sizeof(rows)));
+  return MHB_OK;
+}
+#endif
+
 // Per-pass timing: every sort records one event before and after each pass into a small ring, so a
 // caller can ask afterwards (mhb_sort_pass_ms) how long each pass of a recent sort took without putting a
 // synchronisation inside its timed region.

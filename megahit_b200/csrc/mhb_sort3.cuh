@@ -106,6 +106,67 @@ __device__ __forceinline__ void st_shared_rec(u32 *base, u32 idx, const u32 (&q)
   }
 }
 
+// Optional per-tile timeline (diagnostic build only: `make timeline` -> libmhb_timeline.so, -DMHB_SORT_TIMELINE; the
+// production library contains none of this).  One 16-word row per tile: tile, SM id, globaltimer at the tile's start,
+// then clock64 deltas from the start at: records in registers, early publish done, ranking done (B1), warp bases
+// done (B3), reorder done, look-back done, B4 passed, scatter done (B5); then max / sum over the 256 digit threads of
+// the descriptors examined and of the re-polls of unpublished descriptors.
+#ifdef MHB_SORT_TIMELINE
+__device__ unsigned long long *g_sort_timeline = nullptr;
+__device__ unsigned long long g_sort_timeline_rows = 0;
+#define MHB_TL_DECL                                                                             \
+  __shared__ unsigned int s_tl_depth_max, s_tl_depth_sum, s_tl_spin_max, s_tl_spin_sum;         \
+  unsigned long long tl_t0 = 0, tl_g0 = 0, tl_v[8] = {0, 0, 0, 0, 0, 0, 0, 0};                  \
+  unsigned int tl_depth = 0, tl_spin = 0;
+#define MHB_TL_START()                                                                          \
+  do {                                                                                          \
+    if (tid == 0) {                                                                             \
+      tl_t0 = clock64();                                                                        \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl_g0));                                 \
+      s_tl_depth_max = s_tl_depth_sum = s_tl_spin_max = s_tl_spin_sum = 0;                      \
+    }                                                                                           \
+    tl_depth = tl_spin = 0;                                                                     \
+  } while (0)
+#define MHB_TL_MARK(i)                         \
+  do {                                         \
+    if (tid == 0) tl_v[i] = clock64() - tl_t0; \
+  } while (0)
+#define MHB_TL_DEPTH() (++tl_depth)
+#define MHB_TL_SPIN() (++tl_spin)
+#define MHB_TL_LB_DONE()                       \
+  do {                                         \
+    atomicMax(&s_tl_depth_max, tl_depth);      \
+    atomicAdd(&s_tl_depth_sum, tl_depth);      \
+    atomicMax(&s_tl_spin_max, tl_spin);        \
+    atomicAdd(&s_tl_spin_sum, tl_spin);        \
+  } while (0)
+#define MHB_TL_FLUSH()                                                                          \
+  do {                                                                                          \
+    if (tid == 0 && g_sort_timeline && (unsigned long long)tile < g_sort_timeline_rows) {       \
+      unsigned long long *row = g_sort_timeline + (unsigned long long)tile * 16;                \
+      unsigned int smid;                                                                        \
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));                                         \
+      row[0] = tile;                                                                            \
+      row[1] = smid;                                                                            \
+      row[2] = tl_g0;                                                                           \
+      for (int q_ = 0; q_ < 8; ++q_) row[3 + q_] = tl_v[q_];                                    \
+      row[11] = s_tl_depth_max;                                                                 \
+      row[12] = s_tl_depth_sum;                                                                 \
+      row[13] = s_tl_spin_max;                                                                  \
+      row[14] = s_tl_spin_sum;                                                                  \
+      row[15] = blockIdx.x;                                                                     \
+    }                                                                                           \
+  } while (0)
+#else
+#define MHB_TL_DECL
+#define MHB_TL_START() ((void)0)
+#define MHB_TL_MARK(i) ((void)0)
+#define MHB_TL_DEPTH() ((void)0)
+#define MHB_TL_SPIN() ((void)0)
+#define MHB_TL_LB_DONE() ((void)0)
+#define MHB_TL_FLUSH() ((void)0)
+#endif
+
 template <int WR, int CFG, bool OWNER_LUT = false, bool HAS_NEXT = true>
 __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>::MIN_BLOCKS)
     k_radix_pass3(const u32 *__restrict__ in, u64 n, u32 num_tiles, int byte_idx,
@@ -132,6 +193,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
   const u32 widx = (u32)(WR - 1 - (byte_idx >> 2)), bsel = (u32)(byte_idx & 3);
   const u32 nwidx = (u32)(WR - 1 - (next_byte >> 2)), nbsel = (u32)(next_byte & 3);
   u32 *my_cnt = s_cnt + warp * 256 * CS;
+  MHB_TL_DECL
 
   for (int i = tid; i < 256; i += THREADS) s_next[i] = 0;
   for (int i = tid; i < 256; i += THREADS) s_early[i] = 0;
@@ -174,6 +236,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
     // global atomic's latency is never waited for.  Tickets are still handed out in start order (a CTA only ever
     // waits on smaller tickets than the ones it holds), so the look-back cannot deadlock.
     u32 next_ticket = 0;
+    MHB_TL_START();
     if (tid == 0) next_ticket = atomicAdd(tile_counter, 1u);
     const u64 tile_base = (u64)tile * TILE;
     const bool full = tile_base + TILE <= n;
@@ -184,6 +247,13 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
     // ---- EARLY: histogram the tile's digits and publish the counts now, a whole rank phase before the tile needs its
     // predecessors: when the following tiles look back, this descriptor is already there (no spinning on "invalid")
     u32 e_total = 0, e_excl = 0;
+#ifdef MHB_SORT_TIMELINE
+    if (tid == 0) {  // first use of the tile's records: the wait for the loads ends here
+      volatile u32 sink = r[0][0];
+      (void)sink;
+      tl_v[0] = clock64() - tl_t0;
+    }
+#endif
     if constexpr (EARLY) {
 #pragma unroll
       for (int i = 0; i < IPT; ++i) {
@@ -209,6 +279,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
       }
     }
 
+    MHB_TL_MARK(1);
     // ---- rank inside the warp: rk = rank among the warp's records with the same digit << 8 | digit ----
     u32 rk[IPT];
 #pragma unroll
@@ -248,6 +319,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
       rk[i] = ((old + below) << 8) | d;
     }
     __syncthreads();  // B1: all warps' counters final
+    MHB_TL_MARK(2);
 
     // ---- per digit (threads 0..255): tile total, scan over digits, warp bases; publish; first look-back window ----
     u32 total = 0, excl = 0;
@@ -308,6 +380,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
       }
     }
     __syncthreads();  // B3
+    MHB_TL_MARK(3);
 
     // ---- reorder in shared memory: every digit's records become contiguous, input order kept ----
     if constexpr (BATCH) {
@@ -322,6 +395,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
         st_rec<WR>(s_recs, pos, r[i]);
       }
     }
+    MHB_TL_MARK(4);
     const u32 next_tile = s_misc[0];  // written before B3, rewritten only after the next tile's B1
     if constexpr (PREFETCH && !LATEPF) {
       if (next_tile < num_tiles) load_tile(next_tile);
@@ -343,7 +417,11 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
           if (!done) {
             u64 v = win[j];
             const u64 *pp = lookback + (u64)(p - j) * 256 + tid;
-            while ((v & kLbStatusMask) == 0 || (v & lb_epoch(255)) != epv) v = ld_relaxed(pp);
+            MHB_TL_DEPTH();
+            while ((v & kLbStatusMask) == 0 || (v & lb_epoch(255)) != epv) {
+              MHB_TL_SPIN();
+              v = ld_relaxed(pp);
+            }
             prefix += v & kLbValueMask;
             if ((v & kLbStatusMask) == kLbInclusive || p == (u32)j) done = true;
           }
@@ -359,7 +437,11 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
             if (!done) {
               u64 v = wv[j];
               const u64 *pp = lookback + (u64)(p - j) * 256 + tid;
-              while ((v & kLbStatusMask) == 0 || (v & lb_epoch(255)) != epv) v = ld_relaxed(pp);
+              MHB_TL_DEPTH();
+              while ((v & kLbStatusMask) == 0 || (v & lb_epoch(255)) != epv) {
+                MHB_TL_SPIN();
+                v = ld_relaxed(pp);
+              }
               prefix += v & kLbValueMask;
               if ((v & kLbStatusMask) == kLbInclusive || p == (u32)j) done = true;
             }
@@ -370,8 +452,11 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
         st_relaxed(lookback + (u64)tile * 256 + tid, kLbInclusive | epv | (prefix + (u64)pub));
       }
       s_glob[tid] = bin_addr[tid] + (prefix - (u64)excl) * (u64)(WR * 4);  // may address another GPU's memory
+      MHB_TL_LB_DONE();
+      MHB_TL_MARK(5);
     }
     __syncthreads();  // B4: s_recs and s_glob complete; nobody reads the counters any more
+    MHB_TL_MARK(6);
 
     if constexpr (PREFETCH && LATEPF) {
       if (next_tile < num_tiles) load_tile(next_tile);  // in flight during the scatter; does not delay the look-back
@@ -433,6 +518,8 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
       }
     }
     __syncthreads();  // B5: s_recs / s_glob free, counters zero
+    MHB_TL_MARK(7);
+    MHB_TL_FLUSH();
     tile = next_tile;
   }
 

@@ -17,7 +17,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmhb.so")
+# MHB_LIB selects another build of the same library (e.g. libmhb_timeline.so, the diagnostic build); never a fallback
+LIB_PATH = os.environ.get("MHB_LIB") or os.path.join(_HERE, "libmhb.so")
 NUM_BUCKETS = 65536
 SENTINEL_OFFSET = 0xFFFFFFFF
 
