@@ -187,7 +187,7 @@ extern "C" int mhb_count_extract_range(void *stream, const mhb_dev_reads *reads,
 #define MHB_V3_DEFAULT 0x080
 #define MHB_V3_LIST(X)                                                                                               \
   X(0x080) X(0x000) X(0x009) X(0x00A) X(0x088) X(0x083) X(0x082) X(0x180) X(0x480) X(0x084) X(0x1080) X(0x0888) X(0x1888) \
-  X(0x188B) X(0x1180) X(0x1988) X(0x1082) X(0x188A)
+  X(0x188B) X(0x1180) X(0x1988) X(0x1082) X(0x188A) X(0x2080) X(0x4080) X(0x6080)
 static bool v3_listed(int bits) {
 #define X(B) \
   if (bits == B) return true;

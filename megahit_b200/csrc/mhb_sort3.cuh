@@ -28,6 +28,7 @@ namespace mhb {
 //   bit  8    first (prefetched) look-back window of 1 descriptor instead of 2
 //   bits 9-10 high-occupancy geometries (override bits 0-1): 1 = 256 thr x 12 rec, 4 CTA/SM; 2 = 512 x 12, 2 CTA/SM
 //   bit  11   (with bit 3) the prefetch is issued after the look-back, at the start of the scatter, instead of before it
+//   bit  13   batched loads in the reorder only; bit 14: in the warp-base loop only (bit 6 = both + the asm scatter)
 //   bit  12   (with bit 7) the scan over the digit totals also runs early, on the early histogram: one barrier and the
 //             per-warp total loop leave the critical path between ranking and the reorder
 // Measured on B200, 1.23 G 8-byte records, ms per pass (profiles/r1d_sort_sweep.txt): v2 7.24; v3 base 6.93;
@@ -41,6 +42,8 @@ struct SortCfg3 {
   static constexpr bool PREFETCH = (CFG >> 3) & 1;
   static constexpr int LBW = ((CFG >> 4) & 3) == 3 ? 1 : (2 << ((CFG >> 4) & 3));
   static constexpr bool BATCH = (CFG >> 6) & 1;
+  static constexpr bool BATCH_R = BATCH || ((CFG >> 13) & 1);
+  static constexpr bool BATCH_P = BATCH || ((CFG >> 14) & 1);
   static constexpr bool EARLY = (CFG >> 7) & 1;
   static constexpr int LB1 = ((CFG >> 8) & 1) ? 1 : 2;
   static constexpr bool LATEPF = (CFG >> 11) & 1;
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
   constexpr int CO = CS - 1;  // word offset of the count inside a slot
   constexpr bool PREFETCH = C::PREFETCH;
   constexpr int LBW = C::LBW, LB1 = C::LB1;
-  constexpr bool BATCH = C::BATCH, EARLY = C::EARLY, LATEPF = C::LATEPF, ESCAN = C::ESCAN;
+  constexpr bool BATCH = C::BATCH, BATCH_R = C::BATCH_R, BATCH_P = C::BATCH_P, EARLY = C::EARLY, LATEPF = C::LATEPF, ESCAN = C::ESCAN;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64 *s_glob = reinterpret_cast<u64 *>(smem_raw);        // 256: byte address of the digit's slot for tile position 0
   u32 *s_cnt = reinterpret_cast<u32 *>(s_glob + 256);     // NW * 256 * CS
@@ -356,7 +359,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
         win[j] = (tile > (u32)j) ? ld_relaxed(lookback + (u64)(tile - 1 - j) * 256 + tid) : 0ull;
       // counters become: position in the tile of the warp's first record with this digit
       u32 run = excl;
-      if constexpr (BATCH) {
+      if constexpr (BATCH_P) {
         constexpr int H = (NW + 1) / 2;
 #pragma unroll
         for (int h0 = 0; h0 < NW; h0 += H) {
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
     MHB_TL_MARK(3);
 
     // ---- reorder in shared memory: every digit's records become contiguous, input order kept ----
-    if constexpr (BATCH) {
+    if constexpr (BATCH_R) {
 #pragma unroll
       for (int i = 0; i < IPT; ++i) rk[i] = my_cnt[(rk[i] & 255u) * CS + CO] + (rk[i] >> 8);
 #pragma unroll
