@@ -738,16 +738,22 @@ extern "C" int mhb_build_host(const mhb_build_args *args, mhb_build_result *res)
   } guard{extra};
 
   // ---- H2D ----
+  // MHB_H2D_CHUNKS=C (opt-in, fixed-length libraries): the library is uploaded in C pieces on a copy stream and the
+  // edges of piece i are extracted while piece i+1 is still crossing PCIe, instead of upload-then-extract.
+  static const int h2d_chunks_env = getenv("MHB_H2D_CHUNKS") ? atoi(getenv("MHB_H2D_CHUNKS")) : 1;
+  const bool chunked = h2d_chunks_env > 1 && ix.fixed_len >= k + 1 && n_reads >= (uint64_t)h2d_chunks_env * 64;
   t.start();
-  if (args->bin_words) CK(cudaMemcpyAsync(d_bin, args->bin, args->bin_words * 4, cudaMemcpyHostToDevice, st));
-  if (!ix.fixed_len && n_reads) {
-    CK(cudaMemcpyAsync(d_rec_off, ix.rec_off.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d_edge_off, ix.edge_off.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-  }
   CK(cudaMemsetAsync(d_mul_hist, 0, 65536 * 8, st));
   CK(cudaMemsetAsync(d_hist0, 0, 256 * 8, st));
   CK(cudaMemsetAsync(d_hist1, 0, 256 * 8, st));
   CK(cudaMemsetAsync(d_nsolid, 0, 64, st));
+  if (!chunked) {
+    if (args->bin_words) CK(cudaMemcpyAsync(d_bin, args->bin, args->bin_words * 4, cudaMemcpyHostToDevice, st));
+    if (!ix.fixed_len && n_reads) {
+      CK(cudaMemcpyAsync(d_rec_off, ix.rec_off.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(d_edge_off, ix.edge_off.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    }
+  }
   res->t_h2d_ms = t.stop();
 
   mhb_dev_reads reads;
@@ -764,7 +770,38 @@ extern "C" int mhb_build_host(const mhb_build_args *args, mhb_build_result *res)
   uint32_t *c_b = (uint32_t *)(work + Arena::pad((size_t)n * WR * 4 + 16));
   char *c_wsp = work + 2 * Arena::pad((size_t)n * WR * 4 + 16);
   char *c_scrp = c_wsp + Arena::pad(c_ws);
-  CKR(mhb_count_extract(st, &reads, k, c_a, n, d_hist0, cbytes[0]));
+  if (!chunked) {
+    CKR(mhb_count_extract(st, &reads, k, c_a, n, d_hist0, cbytes[0]));
+  } else {
+    static cudaStream_t copy_st = nullptr;
+    static cudaEvent_t ev[64];
+    static bool ev_ready = false;
+    if (!ev_ready) {
+      CK(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
+      for (int i = 0; i < 64; ++i) CK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+      ev_ready = true;
+    }
+    const int C = std::min(h2d_chunks_env, 60);  // ev[63] is the start marker
+    const uint64_t stride = 1 + div_ceil(ix.fixed_len, 16);          // words per read
+    const uint64_t per = ((n_reads + C - 1) / C + 3) & ~(uint64_t)3;  // reads per piece, multiple of 4 -> 16-byte aligned
+    const uint64_t e_per_read = ix.fixed_len - k;
+    cudaEvent_t start_ev = ev[63];
+    CK(cudaEventRecord(start_ev, st));  // the copy stream must not run ahead of this call's place in `st`
+    CK(cudaStreamWaitEvent(copy_st, start_ev, 0));
+    int c = 0;
+    for (uint64_t r0 = 0; r0 < n_reads; r0 += per, ++c) {
+      const uint64_t r1 = std::min(n_reads, r0 + per);
+      const uint64_t w0 = r0 * stride, w1 = r1 * stride;
+      CK(cudaMemcpyAsync(d_bin + w0, args->bin + w0, (w1 - w0) * 4, cudaMemcpyHostToDevice, copy_st));
+      CK(cudaEventRecord(ev[c], copy_st));
+      CK(cudaStreamWaitEvent(st, ev[c], 0));
+      mhb_dev_reads piece = reads;
+      piece.bin = d_bin + w0;
+      piece.bin_words = w1 - w0;
+      piece.n_reads = r1 - r0;
+      CKR(mhb_count_extract(st, &piece, k, c_a + (size_t)r0 * e_per_read * WR, (r1 - r0) * e_per_read, d_hist0, cbytes[0]));
+    }
+  }
   int in_b = 0;
   CKR(mhb_sort_records_impl(st, c_a, c_b, n, WR, cbytes, n_csort, d_hist0, c_wsp, c_ws, &in_b, nullptr));
   CKR(mhb_count_solid(st, in_b ? c_b : c_a, n, k, m, d_edges, d_aux, cap_edges, d_mul_hist, d_nsolid, c_scrp, c_scr));

@@ -1,0 +1,41 @@
+"""GPU tests for code paths written after this round's GPU budget was spent: they are opt-in paths (environment
+variables) that do not change the default behaviour, marked xfail(strict=False) until a GPU run has confirmed them -
+a pass shows up as XPASS, a failure cannot break the suite.  Remove the marker once verified."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="written without GPU access; verify, then drop the marker")]
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_CHILD = r"""
+import json, os, sys
+import numpy as np
+sys.path.insert(0, %r)
+from megahit_b200 import formats as F, lib
+case, k, m = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+bin_words = np.fromfile(os.path.join(case, "reads.lib.bin"), np.uint32)
+_, n_reads = F.read_lib_info(os.path.join(case, "reads.lib"))
+g = lib.build_host(bin_words, n_reads, k, m, need_mercy=True, want_edges=True)
+print("RESULT " + json.dumps({"sdbg": F.sha256(lib.sdbg_stream_from_table(g["bucket_table"], g["bytes"])),
+                              "edges": F.sha256(g["edges"].tobytes()), "n_items": int(g["n_items"])}))
+""" % ROOT
+
+
+@pytest.mark.parametrize("name,k,m,gold", [c for c in golden_cases() if c.values[0] in ("syn150_k27", "tandem_k27", "polya_k27")])
+def test_fused_build_with_chunked_upload_matches_reference(name, k, m, gold):
+    """MHB_H2D_CHUNKS: the library uploaded in pieces, extraction overlapping the copies -> same SdBG as the reference"""
+    import json
+    env = dict(os.environ, MHB_H2D_CHUNKS="3")
+    p = subprocess.run([sys.executable, "-c", _CHILD, os.path.join(GOLDEN, name), str(k), str(m)], env=env,
+                       capture_output=True, text=True, timeout=300)
+    line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+    assert line, p.stderr[-800:]
+    r = json.loads(line[-1][7:])
+    assert r["sdbg"] == gold["sdbg_sha256"] and r["edges"] == gold["edges_sha256"]
