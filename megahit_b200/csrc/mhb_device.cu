@@ -254,6 +254,10 @@ extern "C" size_t mhb_sort_workspace_bytes(uint64_t n, uint32_t words) {
   // sized for the smallest tile of any configuration so that a workspace stays valid across MHB_SORT_CFG values
   u64 tiles = sort_num_tiles(n, words);
   if (words <= 3) tiles = (n + 256 * 8 - 1) / (256 * 8) > tiles ? (n + 256 * 8 - 1) / (256 * 8) : tiles;
+#define M(WW) \
+  if (words == WW && sort_tiles_cfg<WW, 0>(n) > tiles) tiles = sort_tiles_cfg<WW, 0>(n);  // partition pass geometry
+  MHB_FOR_WR(M)
+#undef M
   return kSortHeadBytes + tiles * 256 * 8 + 256;
 }
 
@@ -440,7 +444,12 @@ extern "C" int mhb_partition_scatter(void *stream, const uint32_t *recs, uint64_
                                      size_t ws_bytes) {
   if (words < 1 || words > 17 || byte < 0 || byte >= (int)(4 * words)) return mhb_set_error(MHB_ERR_ARG, "bad geometry");
   if (n == 0) return MHB_OK;
-  const u64 tiles = sort_num_tiles(n, words);
+  // the partition pass always runs the v2 kernel in geometry 0, whatever variant the sorts use
+  u64 tiles = 0;
+#define M(WW) \
+  if (words == WW) tiles = sort_tiles_cfg<WW, 0>(n);
+  MHB_FOR_WR(M)
+#undef M
   const size_t need = kSortHeadBytes + (size_t)tiles * 256 * 8 + 256;
   if (ws_bytes < need) return mhb_set_error(MHB_ERR_ARG, "sort workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
