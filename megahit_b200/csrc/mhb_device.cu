@@ -367,7 +367,8 @@ int mhb_sort_records_impl(void *stream, uint32_t *a, uint32_t *b, uint64_t n, ui
   u64 *bin_base = hist + (72 + 1) * 256;        // [256]
   u32 *tile_counter = (u32 *)(bin_base + 256);  // [128]
   u64 *lookback = (u64 *)((char *)ws + kSortHeadBytes);
-  CK(cudaMemsetAsync(ws, 0, mhb_sort_workspace_bytes(n, words), st));
+  // only what this sort's tile geometry touches (the workspace itself is sized for the smallest tile of any variant)
+  CK(cudaMemsetAsync(ws, 0, kSortHeadBytes + (size_t)sort_num_tiles(n, words) * 256 * 8 + 256, st));
   if (first_hist) {
     CK(cudaMemcpyAsync(hist, first_hist, 256 * 8, cudaMemcpyDeviceToDevice, st));
   } else {
