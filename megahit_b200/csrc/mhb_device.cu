@@ -187,7 +187,8 @@ extern "C" int mhb_count_extract_range(void *stream, const mhb_dev_reads *reads,
 #define MHB_V3_DEFAULT 0x080
 #define MHB_V3_LIST(X)                                                                                               \
   X(0x080) X(0x000) X(0x009) X(0x00A) X(0x088) X(0x083) X(0x082) X(0x180) X(0x480) X(0x084) X(0x1080) X(0x0888) X(0x1888) \
-  X(0x188B) X(0x1180) X(0x1988) X(0x1082) X(0x188A) X(0x2080) X(0x4080) X(0x6080)
+  X(0x188B) X(0x1180) X(0x1988) X(0x1082) X(0x188A) X(0x2080) X(0x4080) X(0x6080) X(0x8080) X(0x10080) X(0x18080)       \
+  X(0x9080) X(0x8082) X(0x10082)
 static bool v3_listed(int bits) {
 #define X(B) \
   if (bits == B) return true;
@@ -249,6 +250,9 @@ static u64 sort_num_tiles(u64 n, u32 words) {
   return 0;
 }
 static constexpr size_t kSortHeadBytes = (size_t)(72 + 1) * 256 * 8 /*hist*/ + 256 * 8 /*bin_base*/ + 128 * 4;
+// look-back storage for `tiles` tiles: 256 64-bit descriptors per tile + (compact-descriptor variants) one 16-byte
+// word per digit and group of four tiles behind them
+static size_t lb_bytes(u64 tiles) { return (size_t)tiles * 256 * 8 + (size_t)((tiles + 3) / 4) * 256 * 16; }
 
 extern "C" size_t mhb_sort_workspace_bytes(uint64_t n, uint32_t words) {
   // sized for the smallest tile of any configuration so that a workspace stays valid across MHB_SORT_CFG values
@@ -258,7 +262,7 @@ extern "C" size_t mhb_sort_workspace_bytes(uint64_t n, uint32_t words) {
   if (words == WW && sort_tiles_cfg<WW, 0>(n) > tiles) tiles = sort_tiles_cfg<WW, 0>(n);  // partition pass geometry
   MHB_FOR_WR(M)
 #undef M
-  return kSortHeadBytes + tiles * 256 * 8 + 256;
+  return kSortHeadBytes + lb_bytes(tiles) + 256;
 }
 
 template <int WR, int CFG>
@@ -368,7 +372,7 @@ int mhb_sort_records_impl(void *stream, uint32_t *a, uint32_t *b, uint64_t n, ui
   u32 *tile_counter = (u32 *)(bin_base + 256);  // [128]
   u64 *lookback = (u64 *)((char *)ws + kSortHeadBytes);
   // only what this sort's tile geometry touches (the workspace itself is sized for the smallest tile of any variant)
-  CK(cudaMemsetAsync(ws, 0, kSortHeadBytes + (size_t)sort_num_tiles(n, words) * 256 * 8 + 256, st));
+  CK(cudaMemsetAsync(ws, 0, kSortHeadBytes + lb_bytes(sort_num_tiles(n, words)) + 256, st));
   if (first_hist) {
     CK(cudaMemcpyAsync(hist, first_hist, 256 * 8, cudaMemcpyDeviceToDevice, st));
   } else {

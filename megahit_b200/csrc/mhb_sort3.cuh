@@ -28,6 +28,10 @@ namespace mhb {
 //   bit  8    first (prefetched) look-back window of 1 descriptor instead of 2
 //   bits 9-10 high-occupancy geometries (override bits 0-1): 1 = 256 thr x 12 rec, 4 CTA/SM; 2 = 512 x 12, 2 CTA/SM
 //   bit  11   (with bit 3) the prefetch is issued after the look-back, at the start of the scatter, instead of before it
+//   bit  15   compact look-back descriptors: the partial counts of 4 consecutive tiles share one 16-byte word per digit
+//             (one load examines 4 predecessors), the 64-bit inclusive prefixes live in a separate array
+//   bit  16   ranking in two interleaved streams per warp (records 0..H-1 and H..IPT-1 with separate counter rows):
+//             two independent shared-memory dependency chains instead of one
 //   bit  13   batched loads in the reorder only; bit 14: in the warp-base loop only (bit 6 = both + the asm scatter)
 //   bit  12   (with bit 7) the scan over the digit totals also runs early, on the early histogram: one barrier and the
 //             per-warp total loop leave the critical path between ranking and the reorder
@@ -48,6 +52,8 @@ struct SortCfg3 {
   static constexpr int LB1 = ((CFG >> 8) & 1) ? 1 : 2;
   static constexpr bool LATEPF = (CFG >> 11) & 1;
   static constexpr bool ESCAN = EARLY && ((CFG >> 12) & 1);
+  static constexpr bool CDESC = EARLY && ((CFG >> 15) & 1);
+  static constexpr bool RANK2 = RANK == 0 && ((CFG >> 16) & 1);
   static constexpr int THREADS = GEOMX == 1 ? 256 : (GEOMX == 2 ? 512 : (GEOM == 2 ? 256 : 384));
   static constexpr int MIN_BLOCKS = GEOMX == 1 ? 4 : (GEOMX == 2 ? 2 : (THREADS == 256 ? 3 : 2));
   static constexpr int IPT_NARROW = GEOMX ? 12 : (GEOM == 1 ? 20 : (GEOM == 3 ? 16 : 18));
@@ -55,8 +61,10 @@ struct SortCfg3 {
                                      : (WR <= 3 ? (IPT_NARROW * 2) / 3 : (WR <= 4 ? 10 : (WR <= 6 ? 6 : (WR <= 9 ? 4 : 2))));
   static constexpr int TILE = THREADS * IPT;
   static constexpr int NW = THREADS / 32;
+  static constexpr int NROW = RANK2 ? 2 * NW : NW;   // counter rows: one per warp, or one per (warp, stream)
+  static constexpr int HA = RANK2 ? (IPT + 1) / 2 : IPT;  // records of the first stream
   static constexpr int CSTRIDE = RANK == 1 ? 2 : 1;  // words per counter slot ({mask,count} when OR-matching)
-  static constexpr size_t SMEM = 256 * 8 /*s_glob*/ + (size_t)NW * 256 * CSTRIDE * 4 /*counters*/ + 256 * 4 /*s_next*/ +
+  static constexpr size_t SMEM = 256 * 8 /*s_glob*/ + (size_t)NROW * 256 * CSTRIDE * 4 /*counters*/ + 256 * 4 /*s_next*/ +
                                  256 * 4 /*s_early*/ + 16 * 4 /*misc*/ + (size_t)TILE * WR * 4;
 };
 
@@ -93,6 +101,15 @@ __device__ __forceinline__ void st_global_rec(u64 addr, const u32 (&q)[WR]) {
     for (int j = 0; j < WR; ++j) asm volatile("st.global.u32 [%0], %1;" ::"l"(addr + 4 * j), "r"(q[j]));
   }
 }
+__device__ __forceinline__ void st_relaxed_u32(u32 *p, u32 v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_relaxed_v4(const u32 *p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ u32 pick4(const uint4 &v, u32 e) { return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w)); }
 __device__ __forceinline__ void red_shared_inc(u32 *p) {
   asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_u32(p)));
 }
@@ -181,11 +198,13 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
   constexpr int CO = CS - 1;  // word offset of the count inside a slot
   constexpr bool PREFETCH = C::PREFETCH;
   constexpr int LBW = C::LBW, LB1 = C::LB1;
+  constexpr bool CDESC = C::CDESC, RANK2 = C::RANK2;
+  constexpr int NROW = C::NROW, HA = C::HA;
   constexpr bool BATCH = C::BATCH, BATCH_R = C::BATCH_R, BATCH_P = C::BATCH_P, EARLY = C::EARLY, LATEPF = C::LATEPF, ESCAN = C::ESCAN;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64 *s_glob = reinterpret_cast<u64 *>(smem_raw);        // 256: byte address of the digit's slot for tile position 0
-  u32 *s_cnt = reinterpret_cast<u32 *>(s_glob + 256);     // NW * 256 * CS
-  u32 *s_next = s_cnt + NW * 256 * CS;                    // 256
+  u32 *s_cnt = reinterpret_cast<u32 *>(s_glob + 256);     // NROW * 256 * CS
+  u32 *s_next = s_cnt + NROW * 256 * CS;                  // 256
   u32 *s_early = s_next + 256;                            // 256: tile digit counts taken right after the load (EARLY)
   u32 *s_misc = s_early + 256;                            // 16: [0] ticket, [4..12] scan
   u32 *s_recs = s_misc + 16;                              // TILE * WR (16-byte aligned)
@@ -195,12 +214,16 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
   const u32 lt_mask = lanemask_lt();
   const u32 widx = (u32)(WR - 1 - (byte_idx >> 2)), bsel = (u32)(byte_idx & 3);
   const u32 nwidx = (u32)(WR - 1 - (next_byte >> 2)), nbsel = (u32)(next_byte & 3);
-  u32 *my_cnt = s_cnt + warp * 256 * CS;
+  u32 *my_cnt = s_cnt + (RANK2 ? 2 * warp : warp) * 256 * CS;  // RANK2: the second stream's row follows at +256
+  // compact descriptors (CDESC): part[(tile >> 2) * 256 + digit][tile & 3] = status<<30 | epoch<<22 | count behind the
+  // inclusive array; status 1 = count valid, 3 = count valid and the tile's inclusive prefix is in lookback[]
+  u32 *part = reinterpret_cast<u32 *>(lookback + (u64)num_tiles * 256);
+  const u32 ep22 = (epoch & 255u) << 22;
   MHB_TL_DECL
 
   for (int i = tid; i < 256; i += THREADS) s_next[i] = 0;
   for (int i = tid; i < 256; i += THREADS) s_early[i] = 0;
-  for (int i = tid; i < NW * 256 * CS; i += THREADS) s_cnt[i] = 0;
+  for (int i = tid; i < NROW * 256 * CS; i += THREADS) s_cnt[i] = 0;
   if constexpr (OWNER_LUT) {
     for (int i = tid; i < 256; i += THREADS) s_lut[i] = digit_lut[i];
   }
@@ -268,7 +291,12 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
       if (tid < 256) {
         e_total = s_early[tid];
         const u32 c = e_total - ((tid == pad_digit) ? (u32)(TILE - valid) : 0u);
-        st_relaxed(lookback + (u64)tile * 256 + tid, (tile == 0 ? kLbInclusive : kLbPartial) | lb_epoch(epoch) | (u64)c);
+        if constexpr (CDESC) {
+          if (tile == 0) st_relaxed(lookback + tid, kLbInclusive | lb_epoch(epoch) | (u64)c);  // before the flag below
+          st_relaxed_u32(part + ((u64)(tile >> 2) * 256 + tid) * 4 + (tile & 3u), ((tile == 0 ? 3u : 1u) << 30) | ep22 | c);
+        } else {
+          st_relaxed(lookback + (u64)tile * 256 + tid, (tile == 0 ? kLbInclusive : kLbPartial) | lb_epoch(epoch) | (u64)c);
+        }
         if constexpr (ESCAN) {
           u32 inc = e_total;
 #pragma unroll
@@ -285,41 +313,73 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
     MHB_TL_MARK(1);
     // ---- rank inside the warp: rk = rank among the warp's records with the same digit << 8 | digit ----
     u32 rk[IPT];
+    auto ballot_peers = [&](u32 d) {
+      u32 peers = 0xffffffffu;
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      u32 d = rec_digit<WR>(r[i], widx, bsel);
-      if constexpr (OWNER_LUT) d = s_lut[d];
-      u32 peers, old, below;
-      if constexpr (RANK == 0) {
-        peers = 0xffffffffu;
-#pragma unroll
-        for (int bit = 0; bit < 8; ++bit) {
-          u32 mask;
-          asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
-              "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t@!p not.b32 %0, %0;\n\t}"
-              : "=r"(mask)
-              : "r"(d), "r"(1u << bit));
-          peers &= mask;
-        }
-        volatile u32 *slot = my_cnt + d;
-        old = *slot;  // every lane reads the running count before the leader bumps it
-        __syncwarp();
-        below = __popc(peers & lt_mask);
-        if ((peers >> lane) <= 1u) *slot = old + below + 1u;  // highest peer lane: below + 1 = popc(peers)
-        __syncwarp();
-      } else {
-        u32 *slot = my_cnt + d * 2;
-        const u32 sa = smem_u32(slot);
-        asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(sa), "r"(1u << lane) : "memory");
-        __syncwarp();
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(peers), "=r"(old) : "r"(sa) : "memory");
-        __syncwarp();
-        below = __popc(peers & lt_mask);
-        if ((peers >> lane) <= 1u)  // highest peer lane: clear the mask, bump the count (below + 1 = popc(peers))
-          asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa), "r"(0u), "r"(old + below + 1u) : "memory");
-        __syncwarp();
+      for (int bit = 0; bit < 8; ++bit) {
+        u32 mask;
+        asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
+            "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t@!p not.b32 %0, %0;\n\t}"
+            : "=r"(mask)
+            : "r"(d), "r"(1u << bit));
+        peers &= mask;
       }
-      rk[i] = ((old + below) << 8) | d;
+      return peers;
+    };
+    if constexpr (RANK2) {
+      // two independent streams: record j of the first half and record HA + j of the second are ranked together, each
+      // against its own counter row, so the two load -> store -> load chains through shared memory overlap
+#pragma unroll
+      for (int j = 0; j < HA; ++j) {
+        const bool hasb = HA + j < IPT;
+        u32 da = rec_digit<WR>(r[j], widx, bsel);
+        u32 db = hasb ? rec_digit<WR>(r[hasb ? HA + j : j], widx, bsel) : 0u;
+        if constexpr (OWNER_LUT) {
+          da = s_lut[da];
+          db = s_lut[db];
+        }
+        const u32 pa = ballot_peers(da);
+        const u32 pb = hasb ? ballot_peers(db) : 0u;
+        volatile u32 *sla = my_cnt + da;
+        volatile u32 *slb = my_cnt + 256 + db;
+        const u32 olda = *sla;
+        const u32 oldb = hasb ? *slb : 0u;
+        __syncwarp();
+        const u32 ba = __popc(pa & lt_mask), bb = __popc(pb & lt_mask);
+        if ((pa >> lane) <= 1u) *sla = olda + ba + 1u;
+        if (hasb && (pb >> lane) <= 1u) *slb = oldb + bb + 1u;
+        __syncwarp();
+        rk[j] = ((olda + ba) << 8) | da;
+        if (hasb) rk[hasb ? HA + j : j] = ((oldb + bb) << 8) | db;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        u32 d = rec_digit<WR>(r[i], widx, bsel);
+        if constexpr (OWNER_LUT) d = s_lut[d];
+        u32 peers, old, below;
+        if constexpr (RANK == 0) {
+          peers = ballot_peers(d);
+          volatile u32 *slot = my_cnt + d;
+          old = *slot;  // every lane reads the running count before the leader bumps it
+          __syncwarp();
+          below = __popc(peers & lt_mask);
+          if ((peers >> lane) <= 1u) *slot = old + below + 1u;  // highest peer lane: below + 1 = popc(peers)
+          __syncwarp();
+        } else {
+          u32 *slot = my_cnt + d * 2;
+          const u32 sa = smem_u32(slot);
+          asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(sa), "r"(1u << lane) : "memory");
+          __syncwarp();
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(peers), "=r"(old) : "r"(sa) : "memory");
+          __syncwarp();
+          below = __popc(peers & lt_mask);
+          if ((peers >> lane) <= 1u)  // highest peer lane: clear the mask, bump the count (below + 1 = popc(peers))
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa), "r"(0u), "r"(old + below + 1u) : "memory");
+          __syncwarp();
+        }
+        rk[i] = ((old + below) << 8) | d;
+      }
     }
     __syncthreads();  // B1: all warps' counters final
     MHB_TL_MARK(2);
@@ -332,7 +392,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
     } else {
       if (tid < 256) {
 #pragma unroll
-        for (int w = 0; w < NW; ++w) total += s_cnt[(w * 256 + tid) * CS + CO];
+        for (int w = 0; w < NROW; ++w) total += s_cnt[(w * 256 + tid) * CS + CO];
         u32 inc = total;
 #pragma unroll
         for (int dd = 1; dd < 32; dd <<= 1) {
@@ -346,6 +406,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
     }
     u32 pub = 0;
     u64 win[LB1];
+    uint4 cwin = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) s_misc[0] = next_ticket;  // requested a whole rank phase ago: no wait
     if (tid < 256) {
 #pragma unroll
@@ -354,28 +415,32 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
       pub = total - ((tid == pad_digit) ? (u32)(TILE - valid) : 0u);
       if constexpr (!EARLY)
         st_relaxed(lookback + (u64)tile * 256 + tid, (tile == 0 ? kLbInclusive : kLbPartial) | lb_epoch(epoch) | (u64)pub);
+      if constexpr (CDESC) {
+        if (tile > 0) cwin = ld_relaxed_v4(part + ((u64)((tile - 1) >> 2) * 256 + tid) * 4);  // up to 4 predecessors
+      } else {
 #pragma unroll
-      for (int j = 0; j < LB1; ++j)
-        win[j] = (tile > (u32)j) ? ld_relaxed(lookback + (u64)(tile - 1 - j) * 256 + tid) : 0ull;
+        for (int j = 0; j < LB1; ++j)
+          win[j] = (tile > (u32)j) ? ld_relaxed(lookback + (u64)(tile - 1 - j) * 256 + tid) : 0ull;
+      }
       // counters become: position in the tile of the warp's first record with this digit
       u32 run = excl;
       if constexpr (BATCH_P) {
-        constexpr int H = (NW + 1) / 2;
+        constexpr int H = (NROW + 1) / 2;
 #pragma unroll
-        for (int h0 = 0; h0 < NW; h0 += H) {
+        for (int h0 = 0; h0 < NROW; h0 += H) {
           u32 c[H];
 #pragma unroll
-          for (int w = 0; w < H; ++w) c[w] = (h0 + w < NW) ? s_cnt[((h0 + w) * 256 + tid) * CS + CO] : 0u;
+          for (int w = 0; w < H; ++w) c[w] = (h0 + w < NROW) ? s_cnt[((h0 + w) * 256 + tid) * CS + CO] : 0u;
 #pragma unroll
           for (int w = 0; w < H; ++w)
-            if (h0 + w < NW) {
+            if (h0 + w < NROW) {
               s_cnt[((h0 + w) * 256 + tid) * CS + CO] = run;
               run += c[w];
             }
         }
       } else {
 #pragma unroll
-        for (int w = 0; w < NW; ++w) {
+        for (int w = 0; w < NROW; ++w) {
           const u32 c = s_cnt[(w * 256 + tid) * CS + CO];
           s_cnt[(w * 256 + tid) * CS + CO] = run;
           run += c;
@@ -388,13 +453,13 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
     // ---- reorder in shared memory: every digit's records become contiguous, input order kept ----
     if constexpr (BATCH_R) {
 #pragma unroll
-      for (int i = 0; i < IPT; ++i) rk[i] = my_cnt[(rk[i] & 255u) * CS + CO] + (rk[i] >> 8);
+      for (int i = 0; i < IPT; ++i) rk[i] = my_cnt[(i >= HA ? 256 : 0) + (rk[i] & 255u) * CS + CO] + (rk[i] >> 8);
 #pragma unroll
       for (int i = 0; i < IPT; ++i) st_shared_rec<WR>(s_recs, rk[i], r[i]);
     } else {
 #pragma unroll
       for (int i = 0; i < IPT; ++i) {
-        const u32 pos = my_cnt[(rk[i] & 255u) * CS + CO] + (rk[i] >> 8);
+        const u32 pos = my_cnt[(i >= HA ? 256 : 0) + (rk[i] & 255u) * CS + CO] + (rk[i] >> 8);
         st_rec<WR>(s_recs, pos, r[i]);
       }
     }
@@ -409,7 +474,42 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
     // (profiles/r1b: 25 % of all warp samples were this loop + the CTA waiting for it at B4 when it fetched 2
     // descriptors per L2 round trip).  After the two prefetched descriptors the walk therefore fetches LBW at a
     // time - all loads in flight together, one round trip per LBW predecessors.
-    if (tid < 256) {
+    if constexpr (CDESC) {
+      if (tid < 256) {
+        u64 prefix = 0;
+        if (tile > 0) {
+          u32 tcur = tile - 1;  // the predecessor to account for next; cwin holds its group of four
+          uint4 cur = cwin;
+          while (true) {
+            const u32 e = tcur & 3u;
+            const u32 *gp = part + ((u64)(tcur >> 2) * 256 + tid) * 4;
+            u32 w = pick4(cur, e);
+            MHB_TL_DEPTH();
+            while ((w >> 30) == 0u || (w & (255u << 22)) != ep22) {  // not published yet (or a previous pass's word)
+              MHB_TL_SPIN();
+              cur = ld_relaxed_v4(gp);
+              w = pick4(cur, e);
+            }
+            if ((w >> 30) == 3u) {  // this tile's inclusive prefix exists: one 64-bit load ends the walk
+              const u64 *ip = lookback + (u64)tcur * 256 + tid;
+              u64 v = ld_relaxed(ip);
+              while ((v & kLbStatusMask) != kLbInclusive || (v & lb_epoch(255)) != lb_epoch(epoch)) v = ld_relaxed(ip);
+              prefix += v & kLbValueMask;
+              break;
+            }
+            prefix += w & 0x3FFFFFu;
+            if (tcur == 0) break;  // not reachable: tile 0 always carries status 3
+            --tcur;
+            if ((tcur & 3u) == 3u) cur = ld_relaxed_v4(part + ((u64)(tcur >> 2) * 256 + tid) * 4);  // next group of four
+          }
+          st_relaxed(lookback + (u64)tile * 256 + tid, kLbInclusive | lb_epoch(epoch) | (prefix + (u64)pub));
+          st_relaxed_u32(part + ((u64)(tile >> 2) * 256 + tid) * 4 + (tile & 3u), (3u << 30) | ep22 | pub);
+        }
+        s_glob[tid] = bin_addr[tid] + (prefix - (u64)excl) * (u64)(WR * 4);
+        MHB_TL_LB_DONE();
+        MHB_TL_MARK(5);
+      }
+    } else if (tid < 256) {
       u64 prefix = 0;
       if (tile > 0) {
         const u64 epv = lb_epoch(epoch);
@@ -467,7 +567,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
     // ---- coalesced scatter + next digit's histogram; clear the counters for the next tile ----
     {
       uint4 *z = reinterpret_cast<uint4 *>(s_cnt);
-      for (int i = tid; i < NW * 256 * CS / 4; i += THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = tid; i < NROW * 256 * CS / 4; i += THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
       if constexpr (EARLY)
         for (int i = tid; i < 256; i += THREADS) s_early[i] = 0;
     }

@@ -76,7 +76,7 @@ print("RESULT " + json.dumps(res))
 
 
 def main():
-    cfgs = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [256 + b for b in (0x080, 0x180, 0x1080, 0x1180, 0x0888, 0x1888, 0x188B, 0x1988, 0x1082, 0x188A)]
+    cfgs = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [256 + b for b in (0x080, 0x180, 0x1080, 0x8080, 0x10080, 0x18080, 0x9080, 0x8082, 0x10082, 0x082)]
     n2 = int(float(sys.argv[2])) if len(sys.argv) > 2 else 1_230_000_000
     n3 = int(float(sys.argv[3])) if len(sys.argv) > 3 else 347_000_000
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
