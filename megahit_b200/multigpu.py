@@ -389,8 +389,13 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric, clocks=None):
     pass_ms = []
     for _ in range(args.steps):
         res = job.run(bin_dev, timed=True)
-        # sorts issued per step: partition1, sort1 (count records), partition2, sort2 -> sort1 is 2 back
-        pass_ms.append(lib.sort_pass_ms(2)[0])
+        # the most recent traced sort over count-width records of this rank's owned count = this step's sort1 (the
+        # fused partition pass is not traced; with the NCCL fallback the partitions are, so search instead of counting)
+        for back in range(4):
+            pm, nrec, words = lib.sort_pass_ms(back)
+            if words == job.WR and nrec == res["n_records_owned"] and len(pm) == len(job.cbytes):
+                pass_ms.append(pm)
+                break
     e1.record()
     torch.cuda.synchronize()
     dist.barrier()
@@ -409,7 +414,7 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric, clocks=None):
     owns = [torch.zeros_like(own) for _ in range(world)]
     dist.all_gather(owns, own)
     # slowest rank's mean radix pass over the count records
-    pm = torch.tensor([float(np.mean(pass_ms))], dtype=torch.float64, device=device)
+    pm = torch.tensor([float(np.mean(pass_ms)) if pass_ms else float("nan")], dtype=torch.float64, device=device)
     dist.all_reduce(pm, op=dist.ReduceOp.MAX)
 
     # ---- e2e: pinned host reads -> device, build, SdBG bytes -> pinned host; device-timed, max over ranks ----
