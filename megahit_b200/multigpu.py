@@ -396,6 +396,8 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric, clocks=None):
             if words == job.WR and nrec == res["n_records_owned"] and len(pm) == len(job.cbytes):
                 pass_ms.append(pm)
                 break
+        else:
+            pass_ms.append(lib.sort_pass_ms(1)[0])  # fused mode: [sort1, sort2] per step
     e1.record()
     torch.cuda.synchronize()
     dist.barrier()
@@ -414,7 +416,7 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric, clocks=None):
     owns = [torch.zeros_like(own) for _ in range(world)]
     dist.all_gather(owns, own)
     # slowest rank's mean radix pass over the count records
-    pm = torch.tensor([float(np.mean(pass_ms)) if pass_ms else float("nan")], dtype=torch.float64, device=device)
+    pm = torch.tensor([float(np.mean([np.mean(x) for x in pass_ms]))], dtype=torch.float64, device=device)
     dist.all_reduce(pm, op=dist.ReduceOp.MAX)
 
     # ---- e2e: pinned host reads -> device, build, SdBG bytes -> pinned host; device-timed, max over ranks ----
