@@ -354,6 +354,8 @@ int mhb_seq2sdbg_run(const mhb_seq2sdbg_opts *opts);
  * ------------------------------------------------------------------------------------------- */
 int mhb_selftest_count_record(const uint32_t *read_words, uint32_t nwords, uint32_t L, uint32_t k, uint32_t q,
                               uint32_t *rec_out, uint32_t *strand_out);
+int mhb_selftest_count_records_roll(const uint32_t *read_words, uint32_t nwords, uint32_t L, uint32_t k, uint32_t q,
+                                    uint64_t *rec4_out, uint32_t *strand4_out);
 int mhb_selftest_s2s_record(const uint32_t *seq_words, uint32_t nwords, uint32_t L, uint32_t k, uint32_t strand,
                             uint32_t offset, uint32_t mult, uint32_t *rec_out);
 

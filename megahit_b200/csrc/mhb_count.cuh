@@ -115,6 +115,46 @@ __global__ void __launch_bounds__(kExtractThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
+// K-extract, rolling variant for 8-byte records (17 <= k+1 <= 29; opt-in: MHB_EXTRACT_ROLL=1): a lane builds FOUR
+// consecutive records, the first from the packed words, the other three by rolling the forward / reverse /
+// complement strings one base on (make_count_records_roll): ~55 instead of ~120 thread-instructions per record.
+// A 150 bp read at k=27 (123 edges) is one warp step.  Same output as k_count_extract<2, 2>.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kExtractThreads)
+    k_count_extract_roll(ReadsView rv, u32 k, u32 *__restrict__ records, u64 *hist, int hist_byte) {
+  __shared__ u32 s_hist[256];
+  for (int i = threadIdx.x; i < 256; i += kExtractThreads) s_hist[i] = 0;
+  const u32 lane = lane_id();
+  const u32 K1 = k + 1;
+  const u32 hshift = 8u * (u32)hist_byte;
+  for_each_read(rv, [&](u64 r, const u32 *s, u32 nwords, u32 L) {
+    if (L < K1) return;  // kmer_counter.cpp:124
+    const u32 n_e = L - k;
+    const u64 base = rv.fixed_len ? r * (u64)(rv.fixed_len - k) : rv.edge_off[r];
+    for (u32 q0 = 0; q0 < n_e; q0 += 128) {
+      const u32 q = q0 + 4 * lane;
+      if (q < n_e) {
+        u64 rec[4];
+        u32 strand[4];
+        make_count_records_roll<4>(s, nwords, L, k, q, rec, strand);
+        const u32 cnt = n_e - q < 4u ? n_e - q : 4u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if ((u32)j < cnt) {
+            reinterpret_cast<uint2 *>(records)[base + q + j] = make_uint2((u32)(rec[j] >> 32), (u32)rec[j]);
+            if (hist) atomicAdd(&s_hist[(u32)(rec[j] >> hshift) & 255u], 1u);
+          }
+        }
+      }
+    }
+  });
+  __syncthreads();
+  if (hist)
+    for (int i = threadIdx.x; i < 256; i += kExtractThreads)
+      if (s_hist[i]) atomicAdd((unsigned long long *)&hist[i], (unsigned long long)s_hist[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K-extract restricted to a range of leading bytes (A13; base_engine.cpp:254-281 Lv1 passes over bucket ranges):
 // when the records of a whole library do not fit in HBM the count stage runs in rounds, each round extracting only
 // the edges whose first four bases (top record byte) lie in [lo, hi].  Two launches, no atomics, read order kept:
@@ -452,6 +492,80 @@ __global__ void __launch_bounds__(256)
           if (flags) {
             const u32 off = L - K1 - (q0 + 32 * u + lane);  // offset in the reversed (package) read
             // no in, strand 0 -> last; no in, strand 1 -> first; no out, strand 0 -> first; no out, strand 1 -> last
+            const bool to_last = ((flags & 1u) && strand[u] == 0) || ((flags & 2u) && strand[u] == 1);
+            const bool to_first = ((flags & 1u) && strand[u] == 1) || ((flags & 2u) && strand[u] == 0);
+            if (to_last) last = last > (long long)off ? last : (long long)off;
+            if (to_first) first = first < off + 1 ? first : off + 1;
+          }
+        }
+      }
+    }
+    for (int d = 16; d; d >>= 1) {
+      const u32 f2 = __shfl_xor_sync(0xffffffffu, first, d);
+      const long long l2 = __shfl_xor_sync(0xffffffffu, last, d);
+      first = first < f2 ? first : f2;
+      last = last > l2 ? last : l2;
+    }
+    if (lane == 0) {
+      first_0_out[r] = first;
+      last_0_in[r] = last < 0 ? 0xFFFFFFFFu : (u32)last;
+    }
+  }
+}
+
+// Rolling variant of k_mark_mercy for 8-byte records (opt-in with MHB_EXTRACT_ROLL=1): a lane re-derives four
+// consecutive canonical (k+1)-mers with make_count_records_roll and probes the filter for all four at once.
+__global__ void __launch_bounds__(256)
+    k_mark_mercy_roll(ReadsView rv, u32 k, const u32 *__restrict__ filter, u64 filter_words, const u32 *__restrict__ table,
+                      u64 cap, u32 *first_0_out, u32 *last_0_in) {
+  constexpr int W = 2;
+  const u32 lane = lane_id();
+  const u32 K1 = k + 1;
+  const u32 fmask = (u32)(filter_words * 32 - 1);
+  for (u64 r = (u64)blockIdx.x * 8 + (threadIdx.x >> 5); r < rv.n_reads; r += (u64)gridDim.x * 8) {
+    const u32 *rec0 = rv.bin + rv.rec_start(r);
+    const u32 L = rec0[0];
+    const u32 *s = rec0 + 1;
+    const u32 nwords = div_ceil(L, 16);
+    u32 first = 0xFFFFFFFFu;
+    long long last = -1;
+    if (L >= K1) {
+      const u32 n_e = L - k;
+      for (u32 q0 = 0; q0 < n_e; q0 += 128) {
+        const u32 q = q0 + 4 * lane;
+        u32 key[4][W], strand[4] = {0, 0, 0, 0}, fw[4] = {0, 0, 0, 0}, h[4] = {0, 0, 0, 0};
+        bool live[4] = {false, false, false, false};
+        if (q < n_e) {
+          u64 rec[4];
+          make_count_records_roll<4>(s, nwords, L, k, q, rec, strand);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            live[u] = q + u < n_e;
+            key[u][0] = (u32)(rec[u] >> 32);
+            key[u][1] = (u32)rec[u] & ~63u;  // drop prev/next: the (k+1)-mer alone, as the tip set stores it
+            if (live[u]) {
+              h[u] = hash_key<W>(key[u]);
+              fw[u] = filter[(hash2(h[u]) & fmask) >> 5];
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!live[u] || !((fw[u] >> (hash2(h[u]) & 31)) & 1u)) continue;
+          u64 slot = h[u] & (cap - 1);
+          u32 flags = 0;
+          while (true) {
+            const u32 *e = table + slot * (W + 1);
+            const u32 f = e[0];
+            if (f == 0) break;
+            if (e[1] == key[u][0] && e[2] == key[u][1]) {
+              flags = f;
+              break;
+            }
+            slot = (slot + 1) & (cap - 1);
+          }
+          if (flags) {
+            const u32 off = L - K1 - (q + u);  // offset in the reversed (package) read
             const bool to_last = ((flags & 1u) && strand[u] == 0) || ((flags & 2u) && strand[u] == 1);
             const bool to_first = ((flags & 1u) && strand[u] == 1) || ((flags & 2u) && strand[u] == 0);
             if (to_last) last = last > (long long)off ? last : (long long)off;

@@ -950,6 +950,20 @@ extern "C" int mhb_selftest_count_record(const uint32_t *read_words, uint32_t nw
   return mhb_set_error(MHB_ERR_ARG, "unsupported k");
 }
 
+// the rolling builder (mhb_kernels.cuh make_count_records_roll) run on the host: 4 records from position q on
+extern "C" int mhb_selftest_count_records_roll(const uint32_t *read_words, uint32_t nwords, uint32_t L, uint32_t k, uint32_t q,
+                                               uint64_t *rec4_out, uint32_t *strand4_out) {
+  if (k + 1 < 17 || k + 1 > 32 || L < k + 1 || q + k + 1 > L) return mhb_set_error(MHB_ERR_ARG, "bad selftest args");
+  u64 r[4];
+  u32 st[4];
+  make_count_records_roll<4>(read_words, nwords, L, k, q, r, st);
+  for (int j = 0; j < 4; ++j) {
+    rec4_out[j] = r[j];
+    strand4_out[j] = st[j];
+  }
+  return MHB_OK;
+}
+
 extern "C" int mhb_selftest_s2s_record(const uint32_t *seq_words, uint32_t nwords, uint32_t L, uint32_t k, uint32_t strand,
                                        uint32_t offset, uint32_t mult, uint32_t *rec_out) {
   const uint32_t W = s2s_record_words(k);

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(SortCfg3<WR, CFG>::THREADS, SortCfg3<WR, CFG>:
                   u32 *tile_counter, u64 *next_hist, int next_byte, u32 epoch,
                   const uint8_t *__restrict__ digit_lut = nullptr) {
   using C = SortCfg3<WR, CFG>;
-  constexpr int THREADS = C::THREADS, IPT = C::IPT, TILE = C::TILE, NW = C::NW, RANK = C::RANK, CS = C::CSTRIDE;
+  constexpr int THREADS = C::THREADS, IPT = C::IPT, TILE = C::TILE, RANK = C::RANK, CS = C::CSTRIDE;
   constexpr int CO = CS - 1;  // word offset of the count inside a slot
   constexpr bool PREFETCH = C::PREFETCH;
   constexpr int LBW = C::LBW, LB1 = C::LB1;

@@ -106,7 +106,7 @@ SYMBOLS = [
     "mhb_tipset_build", "mhb_count_mark_mercy", "mhb_count_tip_edges", "mhb_s2s_extract",
     "mhb_s2s_emit_scratch_bytes", "mhb_s2s_emit", "mhb_set_device", "mhb_count_host", "mhb_s2s_host", "mhb_build_host", "mhb_free",
     "mhb_mercy_candidates_scratch_bytes", "mhb_mercy_candidates", "mhb_mercy_edges_scratch_bytes", "mhb_mercy_edges", "mhb_mercy_edges_segs", "mhb_edge_lut_bytes", "mhb_edge_lut_build",
-    "mhb_release", "mhb_count_run", "mhb_seq2sdbg_run", "mhb_selftest_count_record", "mhb_selftest_s2s_record",
+    "mhb_release", "mhb_count_run", "mhb_seq2sdbg_run", "mhb_selftest_count_record", "mhb_selftest_count_records_roll", "mhb_selftest_s2s_record",
 ]
 
 
@@ -178,6 +178,8 @@ def load():
     L.mhb_seq2sdbg_run.argtypes = [C.POINTER(Seq2SdbgOpts)]
     L.mhb_selftest_count_record.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
                                             C.POINTER(C.c_uint32)]
+    L.mhb_selftest_count_records_roll.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                                  C.c_void_p]
     L.mhb_selftest_s2s_record.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_uint32, C.c_void_p]
     _lib = L
@@ -376,6 +378,16 @@ def selftest_count_record(read_words: np.ndarray, L_: int, k: int, q: int):
     _check(load().mhb_selftest_count_record(read_words.ctypes.data, len(read_words), L_, k, q, rec.ctypes.data,
                                             C.byref(strand)))
     return rec, strand.value
+
+
+def selftest_count_records_roll(read_words: np.ndarray, L_: int, k: int, q: int):
+    """4 consecutive 8-byte count records from position q on, built by the rolling builder (host run)."""
+    read_words = np.ascontiguousarray(read_words, np.uint32)
+    rec = np.zeros(4, np.uint64)
+    strand = np.zeros(4, np.uint32)
+    _check(load().mhb_selftest_count_records_roll(read_words.ctypes.data, len(read_words), L_, k, q, rec.ctypes.data,
+                                                  strand.ctypes.data))
+    return rec, strand
 
 
 def selftest_s2s_record(seq_words: np.ndarray, L_: int, k: int, strand: int, offset: int, mult: int):

@@ -157,3 +157,30 @@ def test_plan_rounds_single_round_and_oversized_byte():
     with pytest.raises(lib.MhbError, match="more than one round can take"):
         lib.plan_rounds(hist, 10)
     assert lib.plan_rounds(np.zeros(256, np.uint64), 1) == [(0, 255)]
+
+
+# ------------------------------------------------------------------------------------------------
+# the rolling record builder (4 consecutive positions per call) against the position-by-position builder
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [16, 20, 21, 26, 27, 28, 29, 31])
+def test_rolling_count_record_builder_matches(k):
+    rng = np.random.default_rng(77 + k)
+    wr = lib.count_record_words(k)
+    for trial in range(25):
+        L = int(rng.integers(k + 1, k + 140))
+        orig = rng.integers(0, 4, L).astype(np.uint8)
+        if trial % 6 == 0:
+            orig[:] = rng.integers(0, 4)  # homopolymer: forward == reverse complement ties, strand flips
+        if trial % 9 == 0:
+            h = orig[: L // 2].copy()
+            orig[L - len(h):] = 3 - h[::-1]  # reverse-complement palindrome across the read
+        words = pack(orig)
+        for q in range(0, L - k):
+            rec, strand = lib.selftest_count_records_roll(words, L, k, q)
+            for j in range(4):
+                if q + j + k + 1 <= L:
+                    e, es = lib.selftest_count_record(words, L, k, q + j)
+                    ev = (int(e[0]) << 32) | int(e[1])
+                    if wr == 3:
+                        ev |= int(e[2])  # 3-word record: key in words 0-1, prev/next in word 2
+                    assert ev == int(rec[j]) and es == int(strand[j]), (k, L, q, j)
