@@ -207,6 +207,15 @@ typedef struct {
 int mhb_s2s_extract(void *stream, const mhb_dev_seqs *seqs, uint32_t k, uint32_t *records, uint64_t n_items,
                     uint64_t *hist256, int hist_byte);
 
+/* A13 for seq2sdbg (base_engine.cpp:254-281): the sort items whose leading record byte (first four bases) lies in
+ * [lo, hi].  records == NULL: count only - hist256 (caller-zeroed) += histogram of record byte hist_byte over the
+ * in-range items.  Otherwise the in-range records are appended (in no particular order) at records[*cursor_dev ...);
+ * cursor_dev (device uint64, caller-zeroed) ends at the number of in-range items; items beyond `capacity` are not
+ * stored. */
+int mhb_s2s_extract_range(void *stream, const mhb_dev_seqs *seqs, uint32_t k, uint32_t *records, uint64_t n_items,
+                          uint32_t lo, uint32_t hi, uint64_t *cursor_dev, uint64_t capacity, uint64_t *hist256,
+                          int hist_byte);
+
 /* A10 (seq_to_sdbg.cpp:702-789 + sdbg_writer.cpp:25-58): SdBG item stream from sorted records.
  *   bytes_out     capacity_bytes; the variable-length item stream in sorted (= bucket) order
  *   bucket_table  uint64[65536*4] device: per bucket {byte offset, #items, #tips, #large_mul};

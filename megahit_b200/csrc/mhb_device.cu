@@ -784,6 +784,37 @@ extern "C" int mhb_s2s_extract(void *stream, const mhb_dev_seqs *seqs, uint32_t 
   return MHB_OK;
 }
 
+// A13 for seq2sdbg: the items whose leading record byte lies in [lo, hi].  records == NULL counts only (hist256 +=
+// histogram of record byte hist_byte over the in-range items); otherwise the in-range records are appended at
+// records[*cursor_dev ...) (cursor_dev: device uint64, caller-zeroed; ends at the number of in-range items even when
+// that exceeds `capacity`, in which case the surplus was not stored).
+extern "C" int mhb_s2s_extract_range(void *stream, const mhb_dev_seqs *seqs, uint32_t k, uint32_t *records, uint64_t n_items,
+                                     uint32_t lo, uint32_t hi, uint64_t *cursor_dev, uint64_t capacity, uint64_t *hist256,
+                                     int hist_byte) {
+  if (!seqs || k < 9 || k > MHB_MAX_K) return mhb_set_error(MHB_ERR_ARG, "kmer size must be >= 9 and <= 255");
+  if (lo > hi || hi > 255) return mhb_set_error(MHB_ERR_ARG, "bad leading-byte range [%u, %u]", lo, hi);
+  if (records && !cursor_dev) return mhb_set_error(MHB_ERR_ARG, "cursor is NULL");
+  if (n_items == 0) return MHB_OK;
+  if (!seqs->mult && !(seqs->fixed_len && seqs->fixed_stride))
+    return mhb_set_error(MHB_ERR_ARG, "seqs->mult is NULL (only allowed for fixed-stride edge records)");
+  if (!seqs->fixed_len && (!seqs->word_off || !seqs->len || !seqs->item_off))
+    return mhb_set_error(MHB_ERR_ARG, "variable-length sequences need word_off, len and item_off");
+  if (seqs->fixed_len && seqs->fixed_len < k + 1) return mhb_set_error(MHB_ERR_ARG, "fixed_len < k+1");
+  cudaStream_t st = (cudaStream_t)stream;
+  const SeqsView sv = make_seqs_view(seqs);
+  const u32 W = s2s_record_words(k);
+  u64 g = (n_items + 255) / 256;
+  if (g > (u64)sm_count() * 32) g = (u64)sm_count() * 32;
+#define M(WW)                                                                                                        \
+  if (W == WW)                                                                                                       \
+    k_s2s_extract_range<WW><<<(unsigned)g, 256, 0, st>>>(sv, k, records, n_items, lo, hi, (unsigned long long *)cursor_dev, \
+                                                         capacity, hist256, hist_byte);
+  MHB_FOR_WR(M)
+#undef M
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
 static int scan32(cudaStream_t st, const u32 *in, u64 n, u64 *out, u64 *total_dev, u64 *bsum);
 // in-place exclusive scan of n u64 values (three phases, no serial chain); total -> *total_dev
 static int scan64(cudaStream_t st, u64 *v, u64 n, u64 *total_dev, u64 *bsum) {

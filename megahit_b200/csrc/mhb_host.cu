@@ -562,6 +562,151 @@ extern "C" int mhb_count_host(const mhb_count_args *args, mhb_count_result *res)
 }
 
 // ================================================================================================
+// seq2sdbg, out of core (A13): rounds over ranges of the leading record byte
+// ================================================================================================
+namespace {
+size_t s2s_round_bytes(uint64_t n, uint32_t W, uint32_t k) {
+  return 2 * Arena::pad((size_t)n * W * 4 + 16) + Arena::pad(mhb_sort_workspace_bytes(n, W)) +
+         Arena::pad(mhb_s2s_emit_scratch_bytes(n, k)) + Arena::pad((size_t)n * (4ull + 4ull * words_per_tip_label(k)) + 16);
+}
+}  // namespace
+
+// Same idea as count_host_rounds: the sort items of all sequences do not fit in HBM next to the sequences, so the
+// stage runs once per contiguous range of leading record bytes (a (k-1)-mer group, and a bucket, never spans two
+// ranges): extract the range -> sort -> emit -> append the item bytes and that range's rows of the bucket table to the
+// host result.  Ranges ascend, so the concatenated stream is in bucket order.
+static int s2s_host_rounds(const mhb_s2s_args *args, mhb_s2s_result *res, const std::vector<uint64_t> &item_off,
+                           uint64_t n_items, bool fixed, uint32_t L0, uint64_t n_words, uint64_t max_items) {
+  const uint32_t k = args->k;
+  const uint64_t ns = args->n_seqs;
+  const uint32_t W = s2s_record_words(k), WPT = words_per_tip_label(k);
+  uint8_t sort_bytes[72];
+  const uint32_t n_sort = mhb_s2s_sort_bytes(k, sort_bytes);
+  const int top_byte = (int)(4 * W - 1);
+  cudaStream_t st = 0;
+  Timer t_all(st), t(st);
+  t_all.start();
+
+  const size_t fixed_b = Arena::pad(n_words * 4 + 64) + Arena::pad((ns + 1) * 8) * 2 + Arena::pad((ns + 1) * 4) +
+                         Arena::pad((ns + 1) * 2) + Arena::pad((size_t)MHB_NUM_BUCKETS * 4 * 8) + 2 * Arena::pad(256 * 8) +
+                         Arena::pad(16 * 8) + Arena::pad(64) + 8192;
+  if (!max_items) {
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t avail = (size_t)((double)(free_b + g_arena.cap) * 0.92);
+    if (avail <= fixed_b) return mhb_set_error(MHB_ERR_NOMEM, "the sequences alone (%zu bytes) do not fit the device", fixed_b);
+    uint64_t lo = 1, hi = n_items;
+    while (lo < hi) {
+      const uint64_t mid = lo + (hi - lo + 1) / 2;
+      if (fixed_b + s2s_round_bytes(mid, W, k) <= avail) lo = mid;
+      else hi = mid - 1;
+    }
+    max_items = lo;
+  }
+  max_items = std::min<uint64_t>(std::max<uint64_t>(max_items, 1), std::max<uint64_t>(n_items, 1));
+  CKR(g_arena.reserve(fixed_b + s2s_round_bytes(max_items, W, k)));
+  uint32_t *d_words = g_arena.take<uint32_t>(n_words + 16);
+  uint64_t *d_word_off = g_arena.take<uint64_t>(ns + 1);
+  uint64_t *d_item_off = g_arena.take<uint64_t>(ns + 1);
+  uint32_t *d_len = g_arena.take<uint32_t>(ns + 1);
+  uint16_t *d_mult = g_arena.take<uint16_t>(ns + 1);
+  uint64_t *d_table = g_arena.take<uint64_t>((size_t)MHB_NUM_BUCKETS * 4);
+  uint64_t *d_hist0 = g_arena.take<uint64_t>(256);
+  uint64_t *d_hist_top = g_arena.take<uint64_t>(256);
+  uint64_t *d_totals = g_arena.take<uint64_t>(16);
+  uint64_t *d_cursor = g_arena.take<uint64_t>(8);
+  uint32_t *d_a = g_arena.take<uint32_t>((size_t)max_items * W + 4);
+  uint32_t *d_b = g_arena.take<uint32_t>((size_t)max_items * W + 4);
+  const size_t ws_bytes = mhb_sort_workspace_bytes(max_items, W);
+  const size_t scratch_bytes = mhb_s2s_emit_scratch_bytes(max_items, k);
+  const uint64_t cap_bytes = max_items * (4ull + 4ull * WPT) + 16;
+  char *d_ws = g_arena.take<char>(ws_bytes);
+  char *d_scratch = g_arena.take<char>(scratch_bytes);
+  uint8_t *d_bytes = g_arena.take<uint8_t>(cap_bytes);
+
+  if (ns) {
+    CK(cudaMemcpyAsync(d_words, args->words, n_words * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_word_off, args->word_off, (ns + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_item_off, item_off.data(), (ns + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_len, args->len, ns * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_mult, args->mult, ns * 2, cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaMemsetAsync(d_hist_top, 0, 256 * 8, st));
+  mhb_dev_seqs seqs;
+  seqs.words = d_words;
+  seqs.n_words = n_words;
+  seqs.n_seqs = ns;
+  seqs.fixed_len = fixed ? L0 : 0;
+  seqs.word_off = d_word_off;
+  seqs.len = d_len;
+  seqs.item_off = d_item_off;
+  seqs.mult = d_mult;
+  seqs.fixed_stride = 0;
+
+  // ---- plan ----
+  t.start();
+  uint64_t h_top[256];
+  CKR(mhb_s2s_extract_range(st, &seqs, k, nullptr, n_items, 0, 255, nullptr, 0, d_hist_top, top_byte));
+  CK(cudaMemcpyAsync(h_top, d_hist_top, sizeof(h_top), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  uint32_t r_lo[256], r_hi[256];
+  const int n_ranges = mhb_plan_rounds(h_top, max_items, r_lo, r_hi);
+  if (n_ranges < 0) return MHB_ERR_NOMEM;
+  res->t_extract_ms = t.stop();
+
+  std::vector<uint8_t> h_bytes;
+  std::vector<uint64_t> h_table((size_t)MHB_NUM_BUCKETS * 4), h_round_table((size_t)MHB_NUM_BUCKETS * 4);
+  uint64_t tot[16] = {0};
+  for (int ri = 0; ri < n_ranges; ++ri) {
+    t.start();
+    CK(cudaMemsetAsync(d_hist0, 0, 256 * 8, st));
+    CK(cudaMemsetAsync(d_cursor, 0, 64, st));
+    CKR(mhb_s2s_extract_range(st, &seqs, k, d_a, n_items, r_lo[ri], r_hi[ri], d_cursor, max_items, d_hist0, sort_bytes[0]));
+    uint64_t n_round = 0;
+    CK(cudaMemcpyAsync(&n_round, d_cursor, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    res->t_extract_ms += t.stop();
+    if (n_round > max_items) return mhb_set_error(MHB_ERR_NOMEM, "internal: round of %llu items exceeds its plan", (unsigned long long)n_round);
+    if (n_round == 0) continue;
+    t.start();
+    int in_b = 0;
+    CKR(mhb_sort_records_impl(st, d_a, d_b, n_round, W, sort_bytes, n_sort, d_hist0, d_ws, ws_bytes, &in_b, nullptr));
+    res->t_sort_ms += t.stop();
+    t.start();
+    CKR(mhb_s2s_emit(st, in_b ? d_b : d_a, n_round, k, d_bytes, cap_bytes, d_table, d_totals, d_scratch, scratch_bytes));
+    uint64_t rt[16];
+    CK(cudaMemcpyAsync(rt, d_totals, sizeof(rt), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_round_table.data(), d_table, h_round_table.size() * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (rt[0] > cap_bytes) return mhb_set_error(MHB_ERR_NOMEM, "internal: SdBG byte stream exceeds capacity");
+    const size_t base = h_bytes.size();
+    h_bytes.resize(base + rt[0]);
+    if (rt[0]) CK(cudaMemcpy(h_bytes.data() + base, d_bytes, rt[0], cudaMemcpyDeviceToHost));
+    for (size_t b = 0; b < (size_t)MHB_NUM_BUCKETS; ++b)
+      if (h_round_table[4 * b + 1]) {
+        h_table[4 * b + 0] = h_round_table[4 * b + 0] + base;
+        h_table[4 * b + 1] = h_round_table[4 * b + 1];
+        h_table[4 * b + 2] = h_round_table[4 * b + 2];
+        h_table[4 * b + 3] = h_round_table[4 * b + 3];
+      }
+    for (int i = 0; i < 16; ++i) tot[i] += rt[i];
+    res->t_emit_ms += t.stop();
+  }
+  res->n_bytes = tot[0];
+  res->n_items = tot[1];
+  res->n_tips = tot[2];
+  res->n_large_mul = tot[3];
+  for (int i = 0; i < 9; ++i) res->w_count[i] = tot[4 + i];
+  res->ones_in_last = tot[13];
+  memcpy(res->bucket_table, h_table.data(), sizeof(res->bucket_table));
+  res->bytes = (uint8_t *)malloc(std::max<size_t>(1, h_bytes.size()));
+  if (!res->bytes) return mhb_set_error(MHB_ERR_NOMEM, "host malloc failed");
+  if (!h_bytes.empty()) memcpy(res->bytes, h_bytes.data(), h_bytes.size());
+  res->t_total_ms = t_all.stop();
+  return MHB_OK;
+}
+
+// ================================================================================================
 // seq2sdbg
 // ================================================================================================
 extern "C" int mhb_s2s_host(const mhb_s2s_args *args, mhb_s2s_result *res) {
@@ -603,6 +748,16 @@ extern "C" int mhb_s2s_host(const mhb_s2s_args *args, mhb_s2s_result *res) {
                 Arena::pad((ns + 1) * 2) + 2 * Arena::pad((size_t)n_items * W * 4 + 16) + Arena::pad(ws_bytes) +
                 Arena::pad(scratch_bytes) + Arena::pad(cap_bytes) + Arena::pad((size_t)MHB_NUM_BUCKETS * 4 * 8) +
                 Arena::pad(256 * 8) + Arena::pad(16 * 8) + 4096;
+  {
+    // A13: items that do not fit the device at once (or a caller-imposed cap) -> rounds over leading-byte ranges
+    bool rounds = g_round_limit && n_items > g_round_limit;
+    if (!rounds && need > g_arena.cap) {
+      size_t free_b = 0, total_b = 0;
+      CK(cudaMemGetInfo(&free_b, &total_b));
+      rounds = (double)need > 0.92 * (double)(free_b + g_arena.cap);
+    }
+    if (rounds) return s2s_host_rounds(args, res, item_off, n_items, fixed, L0, n_words, g_round_limit);
+  }
   CKR(g_arena.reserve(need));
   uint32_t *d_words = g_arena.take<uint32_t>(n_words + 16);
   uint64_t *d_word_off = g_arena.take<uint64_t>(ns + 1);

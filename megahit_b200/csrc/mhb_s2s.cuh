@@ -64,6 +64,76 @@ __global__ void __launch_bounds__(256)
       if (s_hist[i]) atomicAdd((unsigned long long *)&hist[i], (unsigned long long)s_hist[i]);
 }
 
+// S-extract restricted to the items whose leading record byte (first four bases) lies in [lo, hi] (A13: seq2sdbg in
+// rounds when the items of all sequences do not fit in HBM; base_engine.cpp:254-281).  records == nullptr: count only
+// (histogram of record byte hist_byte over the in-range items, e.g. the leading byte itself for the planner).
+// Otherwise the in-range records are appended at records[*cursor ...) with one warp-aggregated atomic per 32 items
+// (their order is irrelevant: equal keys are equal records up to the multiplicity bits, of which the emit takes the
+// minimum).  Items beyond `capacity` are counted by the cursor but not stored.
+template <int W>
+__global__ void __launch_bounds__(256)
+    k_s2s_extract_range(SeqsView sv, u32 k, u32 *__restrict__ records, u64 n_items, u32 lo, u32 hi,
+                        unsigned long long *cursor, u64 capacity, u64 *hist, int hist_byte) {
+  __shared__ u32 s_hist[256];
+  for (int i = threadIdx.x; i < 256; i += 256) s_hist[i] = 0;
+  __syncthreads();
+  const u32 lane = threadIdx.x & 31;
+  const u32 lt = lanemask_lt();
+  for (u64 t0 = (u64)blockIdx.x * 256 + (threadIdx.x & ~31u); t0 < n_items; t0 += (u64)gridDim.x * 256) {  // warp-uniform
+    const u64 t = t0 + lane;
+    bool in = false;
+    u32 rec[W];
+    if (t < n_items) {
+      u64 seq, rem;
+      u32 L;
+      const u32 *s;
+      u32 nwords;
+      if (sv.fixed_len) {
+        L = sv.fixed_len;
+        const u64 ips = 2ull * (L - k + 2);
+        seq = t / ips;
+        rem = t - seq * ips;
+        nwords = div_ceil(L, 16);
+        s = sv.words + seq * (sv.fixed_stride ? sv.fixed_stride : nwords);
+      } else {
+        u64 a = 0, b = sv.n_seqs;  // last seq with item_off[seq] <= t
+        while (b - a > 1) {
+          const u64 mid = (a + b) >> 1;
+          if (sv.item_off[mid] <= t) a = mid; else b = mid;
+        }
+        seq = a;
+        rem = t - sv.item_off[seq];
+        L = sv.len[seq];
+        nwords = div_ceil(L, 16);
+        s = sv.words + sv.word_off[seq];
+      }
+      const u32 per_strand = L - k + 2;
+      const u32 strand = rem >= per_strand ? 1u : 0u;
+      const u32 offset = (u32)(rem - (u64)strand * per_strand);
+      const u32 mult = sv.mult ? (u32)sv.mult[seq] : (s[sv.fixed_stride - 1] & 0xFFFFu);
+      make_s2s_record<W>(s, nwords, L, k, strand, offset, mult, rec);
+      const u32 top = rec[0] >> 24;
+      in = top >= lo && top <= hi;
+    }
+    const u32 mask = __ballot_sync(0xffffffffu, in);
+    if (mask == 0) continue;
+    if (records) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(mask));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (in) {
+        const u64 pos = base + __popc(mask & lt);
+        if (pos < capacity) st_rec<W>(records, pos, rec);
+      }
+    }
+    if (in && hist) atomicAdd(&s_hist[rec_byte<W>(rec, hist_byte)], 1u);
+  }
+  __syncthreads();
+  if (hist)
+    for (int i = threadIdx.x; i < 256; i += 256)
+      if (s_hist[i]) atomicAdd((unsigned long long *)&hist[i], (unsigned long long)s_hist[i]);
+}
+
 // S-extract fast path: the sequences are `.edges` records of (k+1)-mers with k+1 <= 32 (the k_min case).  One
 // thread turns one edge into its six sort items (both strands x offsets 0,1,2) with 64-bit arithmetic; strand 1
 // is strand 0 of the reverse complement (seq_to_sdbg.cpp:672-690).  Item order matches k_s2s_extract.

@@ -88,3 +88,52 @@ def test_rolling_extract_and_mark_match_default(name, k, m, gold):
         out.append(json.loads(line[-1][7:]))
     assert out[0] == out[1]
     assert out[1]["edges"] == gold["edges_sha256"] and out[1]["n_solid"] == gold["n_solid"]
+
+
+_CHILD_S2S = r"""
+import json, os, sys
+import numpy as np
+sys.path.insert(0, %r)
+sys.path.insert(0, os.path.join(%r, "tests"))
+from megahit_b200 import formats as F, lib
+import oracle_pipeline as OP
+from oracle import oracle as O
+case, k, m, div = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+reads = OP.load_reads(case)
+oc = OP.oracle_count(reads, k, m)
+seqs, mult = O.edges_as_seqs(oc["edges"], k)
+one = lib.s2s_host(seqs.words, seqs.word_off, seqs.len, mult, k)
+lib.set_round_limit(max(1, int(one["n_records"]) // div))
+try:
+    g = lib.s2s_host(seqs.words, seqs.word_off, seqs.len, mult, k)
+    err = None
+except lib.MhbError as e:
+    g, err = None, str(e)
+lib.set_round_limit(0)
+out = {"err": err}
+if g is not None:
+    out.update(same_bytes=bool(g["bytes"] == one["bytes"]), same_table=bool((g["bucket_table"] == one["bucket_table"]).all()),
+               n_items=[int(g["n_items"]), int(one["n_items"])], n_tips=[int(g["n_tips"]), int(one["n_tips"])],
+               w=[[int(x) for x in g["w_count"]], [int(x) for x in one["w_count"]]],
+               ones=[int(g["ones_in_last"]), int(one["ones_in_last"])])
+print("RESULT " + json.dumps(out))
+""" % (ROOT, ROOT)
+
+
+@pytest.mark.parametrize("name,k,m,gold", [c for c in golden_cases() if c.values[0] in ("syn150_k27", "toy_k21", "synvar_k31_m1")])
+@pytest.mark.parametrize("div", [3, 11])
+def test_seq2sdbg_in_rounds_matches_one_pass(name, k, m, gold, div):
+    """A13 for seq2sdbg: rounds over leading-byte ranges (forced by capping the items per round) reproduce the item
+    stream, the bucket table and the counters of the single pass"""
+    import json
+    p = subprocess.run([sys.executable, "-c", _CHILD_S2S, os.path.join(GOLDEN, name), str(k), str(m), str(div)],
+                       capture_output=True, text=True, timeout=600)
+    line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+    assert line, p.stderr[-800:]
+    r = json.loads(line[-1][7:])
+    if r["err"] is not None:
+        assert "more than one round can take" in r["err"]
+        return
+    assert r["same_bytes"] and r["same_table"]
+    assert r["n_items"][0] == r["n_items"][1] and r["n_tips"][0] == r["n_tips"][1]
+    assert r["w"][0] == r["w"][1] and r["ones"][0] == r["ones"][1]
