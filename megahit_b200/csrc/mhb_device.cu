@@ -192,8 +192,7 @@ extern "C" int mhb_count_extract_range(void *stream, const mhb_dev_reads *reads,
 // every record width).
 #define MHB_V3_DEFAULT 0x080
 #define MHB_V3_LIST(X)                                                                                               \
-  X(0x080) X(0x000) X(0x009) X(0x00A) X(0x088) X(0x083) X(0x082) X(0x180) X(0x480) X(0x084) X(0x1080) X(0x0888) X(0x1888) \
-  X(0x188B) X(0x1180) X(0x1988) X(0x1082) X(0x188A) X(0x2080) X(0x4080) X(0x6080) X(0x8080) X(0x10080) X(0x18080)       \
+  X(0x080) X(0x000) X(0x009) X(0x082) X(0x180) X(0x480) X(0x084) X(0x1080) X(0x0888) X(0x8080) X(0x10080) X(0x18080)  \
   X(0x9080) X(0x8082) X(0x10082)
 static bool v3_listed(int bits) {
 #define X(B) \
@@ -230,7 +229,7 @@ template <int WR>
 static u64 sort_tiles(u64 n) {
   const int cfg = sort_cfg();
   if (cfg >= 256) {
-    if constexpr (WR <= 3) {
+    if constexpr (WR == 2 || WR == 3) {
 #define X(B) \
   if (cfg - 256 == B) return sort_tiles_cfg3<WR, B>(n);
       MHB_V3_LIST(X)
@@ -321,7 +320,7 @@ static int launch_radix_pass(cudaStream_t st, const u32 *in, u64 n, int byte_idx
                              u64 *lookback, u32 *tile_counter, u64 *next_hist, int next_byte, u32 epoch) {
   const int cfg = sort_cfg();
   if (cfg >= 256) {
-    if constexpr (WR <= 3) {
+    if constexpr (WR == 2 || WR == 3) {
 #define X(B) \
   if (cfg - 256 == B) return launch_radix_pass_cfg3<WR, B>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
       MHB_V3_LIST(X)

@@ -75,7 +75,7 @@ def test_sort_skewed_digits():
     assert (got == _np_lsd(recs, sort_bytes)).all()
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3] + [256 + b for b in (0x080, 0x000, 0x009, 0x00A, 0x088, 0x083, 0x082, 0x180, 0x480, 0x084, 0x1080, 0x0888, 0x1888, 0x188B, 0x1180, 0x1988, 0x1082, 0x188A)])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3] + [256 + b for b in (0x080, 0x000, 0x009, 0x082, 0x180, 0x480, 0x084, 0x1080, 0x0888)])
 def test_sort_every_pass_variant(cfg):
     """every tile geometry / ranking variant of the radix pass (mhb_set_sort_cfg) gives the same stable LSD order,
     including ragged last tiles and single-tile inputs"""
