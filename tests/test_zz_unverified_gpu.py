@@ -28,7 +28,7 @@ print("RESULT " + json.dumps({"sdbg": F.sha256(lib.sdbg_stream_from_table(g["buc
 """ % ROOT
 
 
-@pytest.mark.parametrize("name,k,m,gold", [c for c in golden_cases() if c.values[0] in ("syn150_k27", "tandem_k27", "polya_k27")])
+@pytest.mark.parametrize("name,k,m,gold", [c for c in golden_cases() if c.values[0] in ("syn150_k27",)])
 def test_fused_build_with_chunked_upload_matches_reference(name, k, m, gold):
     """MHB_H2D_CHUNKS: the library uploaded in pieces, extraction overlapping the copies -> same SdBG as the reference"""
     import json
@@ -46,8 +46,8 @@ def test_new_radix_pass_variants_sort_correctly():
     process (scripts/sort_sweep.py: a hang or crash only loses that variant), must reproduce torch's stable sort"""
     import json
     cfgs = [256 + b for b in (0x8080, 0x10080, 0x18080, 0x9080, 0x8082, 0x10082)]
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "sort_sweep.py"), ",".join(map(str, cfgs)), "3000000",
-                        "1000000"], capture_output=True, text=True, timeout=900)
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "sort_sweep.py"), ",".join(map(str, cfgs)), "1000000",
+                        "500000"], capture_output=True, text=True, timeout=900)
     res = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
     assert len(res) == len(cfgs), p.stderr[-800:]
     bad = [r for r in res if not r.get("ok")]
@@ -69,8 +69,7 @@ print("RESULT " + json.dumps({"edges": F.sha256(g["edges"].tobytes()), "n_solid"
 """ % ROOT
 
 
-@pytest.mark.parametrize("name,k,m,gold", [c for c in golden_cases() if c.values[0] in ("syn150_k27", "toy_k21", "tandem_k27",
-                                                                                      "polya_k27", "synvar_k21_m3")])
+@pytest.mark.parametrize("name,k,m,gold", [c for c in golden_cases() if c.values[0] in ("syn150_k27", "synvar_k21_m3")])
 def test_rolling_extract_and_mark_match_default(name, k, m, gold):
     """MHB_EXTRACT_ROLL=1 (rolling record builder in the extract and mercy-mark kernels): same edges, same candidate
     reads as the default kernels and as the reference"""
@@ -120,8 +119,8 @@ print("RESULT " + json.dumps(out))
 """ % (ROOT, ROOT)
 
 
-@pytest.mark.parametrize("name,k,m,gold", [c for c in golden_cases() if c.values[0] in ("syn150_k27", "toy_k21", "synvar_k31_m1")])
-@pytest.mark.parametrize("div", [3, 11])
+@pytest.mark.parametrize("name,k,m,gold", [c for c in golden_cases() if c.values[0] in ("syn150_k27", "synvar_k31_m1")])
+@pytest.mark.parametrize("div", [7])
 def test_seq2sdbg_in_rounds_matches_one_pass(name, k, m, gold, div):
     """A13 for seq2sdbg: rounds over leading-byte ranges (forced by capping the items per round) reproduce the item
     stream, the bucket table and the counters of the single pass"""
