@@ -84,7 +84,7 @@ def main():
     for c in cfgs:
         try:
             p = subprocess.run([sys.executable, "-c", CHILD, str(c), str(n2), str(n3)], capture_output=True, text=True,
-                               timeout=150)
+                               timeout=int(os.environ.get("MHB_SWEEP_TIMEOUT", "75")))
             line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
             r = json.loads(line[-1][7:]) if line else {"cfg": c, "ok": False, "error": (p.stderr or "")[-600:]}
         except subprocess.TimeoutExpired:
