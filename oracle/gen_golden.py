@@ -204,7 +204,23 @@ def gen_chain():
                   sum(1 for l in open(f"{d}/k21.contigs.fa") if l.startswith(">") and "flag=2" in l or "flag=3" in l))
 
 
-CASES = {"chain": gen_chain, "toy": gen_toy, "syn150": gen_syn150, "synvar": gen_synvar, "degenerate": gen_degenerate}
+def gen_kmax():
+    """The largest k the reference supports (kmax = 255, main.cpp:100-103): 17-word count records, 16-word tip labels.
+    Kept apart from tests/golden/ (tests/golden_kmax/): the oracle is pinned against it on the CPU, the GPU comparison
+    at this width has not been run yet."""
+    global GOLD
+    keep = GOLD
+    GOLD = os.path.join(ROOT, "tests", "golden_kmax")
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            b = synth.synth_reads(700, 300, 9000, 0.004, seed=21)
+            F.write_lib(f"{tmp}/r", b, 700, 700 * 300, 300)
+            make_case("syn300_k255", f"{tmp}/r", [255, 199], 2)
+    finally:
+        GOLD = keep
+
+
+CASES = {"kmax": gen_kmax, "chain": gen_chain, "toy": gen_toy, "syn150": gen_syn150, "synvar": gen_synvar, "degenerate": gen_degenerate}
 
 if __name__ == "__main__":
     if not os.path.exists(REF):

@@ -128,3 +128,29 @@ def test_seq2sdbg_in_rounds_matches_one_pass(name, k, m, gold, div):
     assert r["same_bytes"] and r["same_table"]
     assert r["n_items"][0] == r["n_items"][1] and r["n_tips"][0] == r["n_tips"][1]
     assert r["w"][0] == r["w"][1] and r["ones"][0] == r["ones"][1]
+
+
+def _kmax_cases():
+    import json
+    base = os.path.join(ROOT, "tests", "golden_kmax")
+    out = []
+    for name in sorted(os.listdir(base)):
+        g = json.load(open(os.path.join(base, name, "golden.json")))
+        for k, v in sorted(g["by_k"].items(), key=lambda kv: int(kv[0])):
+            out.append(pytest.param(os.path.join(base, name), int(k), g["m"], v, id=f"{name}-k{k}"))
+    return out
+
+
+@pytest.mark.parametrize("case,k,m,gold", _kmax_cases())
+def test_fused_build_at_largest_k_matches_reference(case, k, m, gold):
+    """k = 255 (17-word records, the reference's kmax) and k = 199: the widest record templates have only been
+    exercised by the sort and record-builder tests so far; the fixture is pinned on the CPU (test_oracle_kmax.py)"""
+    import json
+    env = dict(os.environ)
+    env.pop("MHB_H2D_CHUNKS", None)
+    p = subprocess.run([sys.executable, "-c", _CHILD, case, str(k), str(m)], env=env, capture_output=True, text=True,
+                       timeout=300)
+    line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+    assert line, p.stderr[-800:]
+    r = json.loads(line[-1][7:])
+    assert r["edges"] == gold["edges_sha256"] and r["sdbg"] == gold["sdbg_sha256"] and r["n_items"] == gold["sdbg_items"]
