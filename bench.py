@@ -247,6 +247,27 @@ def ours(args):
                      "achieved": s2s_achieved, "frac": s2s_achieved / peak},
     }
 
+    # achieved HBM GB/s of the other stages against their algorithmic bytes; informational, never fatal
+    stage_roofline = {}
+    try:
+        E, WE = int(n_solid), plan.WE
+        M_items, W2 = int(n_items), s2s.W
+        alg = {
+            "extract": n_edges * S + bin_words * 4,                      # records written + packed reads read
+            "sort": len(plan.sort_bytes) * 2 * n_edges * S,
+            "count": n_edges * S + E * (WE * 4 + 1),                     # sorted records read + edges and flags written
+            "mercy": bin_words * 4,                                      # reads re-scanned against the tip set
+            "s2s_extract": E * WE * 4 + M_items * W2 * 4,
+            "s2s_sort": len(s2s.sort_bytes) * 2 * M_items * W2 * 4,
+            "s2s_emit": 2 * M_items * W2 * 4,
+        }
+        for nm, b in alg.items():
+            if stage.get(nm):
+                gbs = b / (stage[nm] * 1e-3) / 1e9
+                stage_roofline[nm] = {"algorithmic_bytes": int(b), "gbs": gbs, "frac": gbs / peak}
+    except Exception as e:  # pragma: no cover
+        stage_roofline = {"error": str(e)}
+
     # kernels launched per step (ours only): extract, 7x(scan256+radix), mark/totals/scan/emit, tips/tipset/mercy,
     # s2s extract, 10x(scan256+radix), size, 4 scans, write, finalize
     launches = 1 + 2 * len(plan.sort_bytes) + 4 + 3 + 1 + 2 * len(s2s.sort_bytes) + 1 + 4 + 1 + 1
@@ -291,7 +312,7 @@ def ours(args):
                                "on the solid edges; mercy-edge generation (host) not in the device step",
                    "n_edge_records": n_edges, "n_solid_edges": int(n_solid), "n_sdbg_sort_items": int(n_items),
                    "l2_note": "inputs (>= 4.9 GB per kernel) exceed the 126 MB L2, no explicit flush needed"},
-        "stage_ms": stage,
+        "stage_ms": stage, "stage_roofline": stage_roofline,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
         "e2e": {"value": e2e_v, "unit": "edges/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": float(np.mean(e2e_t)) * 1e3 if e2e_t else None, "api": "mhb_build_host (pinned host buffers; count -> device mercy edges -> seq2sdbg, SdBG stream D2H)",
