@@ -93,8 +93,8 @@ int mhb_count_extract(void *stream, const mhb_dev_reads *reads, uint32_t k, uint
                       uint64_t n_edges, uint64_t *hist256, int hist_byte);
 
 /* A13 (base_engine.cpp:54-141, 254-281: Lv1 passes over bucket ranges): the same extraction restricted to the edges
- * whose leading record byte (first four bases) lies in [lo, hi], for libraries whose records do not fit in HBM at
- * once.  Two calls per round: write = 0 fills per_read[0..n_reads] (device uint64) with the exclusive prefix of the
+ * whose 16-bit bucket id (first eight bases, kNumBuckets = 65536) lies in [lo, hi], for libraries whose records do
+ * not fit in HBM at once.  Two calls per round: write = 0 fills per_read[0..n_reads] (device uint64) with the exclusive prefix of the
  * per-read in-range edge counts and *total_dev with their sum; write = 1 stores the in-range records compactly, in
  * read order, at records[per_read[r]...).  hist256 (optional, caller-zeroed) += histogram of record byte hist_byte
  * over the in-range records. */
@@ -172,6 +172,17 @@ size_t mhb_mercy_edges_scratch_bytes(uint64_t n_cand, uint32_t max_read_len);
 int mhb_mercy_edges(void *stream, const mhb_dev_reads *reads, const uint64_t *cand_ids, uint64_t n_cand,
                     uint32_t max_read_len, uint32_t k, const uint32_t *edges, uint64_t n_edges, uint32_t *mercy_out,
                     uint64_t capacity, uint64_t *n_mercy_host, void *scratch, size_t scratch_bytes);
+/* The two halves of the search, for callers that size the destination from the exact count (the reference reserves
+ * +25 % and grows, seq_to_sdbg.cpp:371-379): _count runs the probes and leaves per-read counts + offsets in `scratch`
+ * (mhb_mercy_edges_scratch_bytes() minus mhb_edge_lut_bytes() bytes, luts built by the caller with mhb_edge_lut_build),
+ * returning the number of mercy edges; _write emits exactly n_mercy records from the same, untouched scratch. */
+int mhb_mercy_edges_count(void *stream, const mhb_dev_reads *reads, const uint64_t *cand_ids, uint64_t n_cand,
+                          uint32_t max_read_len, uint32_t k, uint32_t n_segs, const uint32_t *const *seg_edges,
+                          const uint64_t *seg_counts, const void *const *seg_luts, const uint8_t *owner_of_byte,
+                          uint64_t *n_mercy_host, void *scratch, size_t scratch_bytes);
+int mhb_mercy_edges_write(void *stream, const mhb_dev_reads *reads, const uint64_t *cand_ids, uint64_t n_cand,
+                          uint32_t max_read_len, uint32_t k, uint32_t *mercy_out, uint64_t capacity, uint64_t n_mercy,
+                          void *scratch, size_t scratch_bytes);
 
 /* Same, with the sorted solid edges given as n_segs (<= 16) segments: segment owner_of_byte[b] holds every edge whose
  * leading byte is b (host arrays; the segment pointers are device pointers and may be CUDA IPC peer pointers into
@@ -207,7 +218,7 @@ typedef struct {
 int mhb_s2s_extract(void *stream, const mhb_dev_seqs *seqs, uint32_t k, uint32_t *records, uint64_t n_items,
                     uint64_t *hist256, int hist_byte);
 
-/* A13 for seq2sdbg (base_engine.cpp:254-281): the sort items whose leading record byte (first four bases) lies in
+/* A13 for seq2sdbg (base_engine.cpp:254-281): the sort items whose 16-bit bucket id (first eight bases) lies in
  * [lo, hi].  records == NULL: count only - hist256 (caller-zeroed) += histogram of record byte hist_byte over the
  * in-range items.  Otherwise the in-range records are appended (in no particular order) at records[*cursor_dev ...);
  * cursor_dev (device uint64, caller-zeroed) ends at the number of in-range items; items beyond `capacity` are not
@@ -229,6 +240,8 @@ int mhb_s2s_emit(void *stream, const uint32_t *sorted_records, uint64_t n, uint3
 /* ---------------------------------------------------------------------------------------------
  * 2. Host level (buffers in host memory; device 0 unless mhb_set_device was called)
  * ------------------------------------------------------------------------------------------- */
+/* One process drives one GPU: call this before any compute entry point.  Selecting the same device again is a no-op;
+ * switching after the first compute call fails with MHB_ERR_ARG (per-process arena, kernel attributes, caches). */
 int mhb_set_device(int device);
 
 typedef struct {
@@ -260,11 +273,21 @@ int mhb_count_host(const mhb_count_args *args, mhb_count_result *res);
  * when the records of the whole library do not fit in device memory; this caps a round at max_records_per_round
  * records regardless of memory (0 = derive from free device memory).  The result does not depend on the cap. */
 int mhb_set_round_limit(uint64_t max_records_per_round);
+/* the same cap for mhb_s2s_host, in sort items per round (independent of the count cap; 0 = derive from memory) */
+int mhb_set_s2s_round_limit(uint64_t max_items_per_round);
 /* The round planner itself (host only, no GPU needed): cuts the 256 leading-byte values, given their record counts,
  * into contiguous ranges [lo_out[i], hi_out[i]] of at most max_records records each (cf. Lv1FindEndBuckets,
  * base_engine.cpp:254-281).  Returns the number of ranges, or -1 (mhb_last_error) when one byte value alone
  * exceeds the cap.  lo_out / hi_out need room for 256 entries. */
 int mhb_plan_rounds(const uint64_t *hist256, uint64_t max_records, uint32_t *lo_out, uint32_t *hi_out);
+/* The planner the host rounds use: leading bytes as above, except that a leading byte holding more than max_records is
+ * cut on its second byte, i.e. on the reference's own 16-bit bucket ids (base_engine.cpp:254-281) - canonical
+ * (k+1)-mers are skewed towards A-prefixes and poly-A / low-complexity data more so.  sub_hist = 256 x 256 counts,
+ * row b = histogram of the second byte among records with leading byte b (only rows of oversized bytes are read; NULL
+ * when there are none).  Outputs ranges [lo16, hi16] of bucket ids tiling 0..65535 (room for cap_out entries); returns
+ * their number, or -1 when a single bucket exceeds the cap. */
+int mhb_plan_rounds16(const uint64_t *hist256, const uint64_t *sub_hist, uint64_t max_records, uint32_t *lo16_out,
+                      uint32_t *hi16_out, uint32_t cap_out);
 
 typedef struct {
   uint32_t k;
@@ -321,6 +344,13 @@ typedef struct {
 } mhb_build_result;
 
 int mhb_build_host(const mhb_build_args *args, mhb_build_result *res);
+
+/* A11 from host buffers (SeqToSdbg::GenMercyEdges, seq_to_sdbg.cpp:171-357, as `seq2sdbg --need_mercy` runs it between
+ * loading `.edges` / `.cand` and the sort): edges = n_edges sorted `.edges`-format records, cand_bin = the `.cand` image
+ * (`.bin` record format, reads in the reversed orientation KmerCounter wrote them, kmer_counter.cpp:387-401).
+ * *mercy_out = malloc'ed n_mercy `.edges`-format records with multiplicity 1 (mhb_free). */
+int mhb_mercy_host(uint32_t k, const uint32_t *edges, uint64_t n_edges, const uint32_t *cand_bin, uint64_t cand_words,
+                   uint32_t **mercy_out, uint64_t *n_mercy_out, uint64_t *n_cand_reads_out);
 
 void mhb_free(void *p);
 /* drop the cached device arena (host-level entry points keep it between calls) */

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kExtractThreads)
 // ------------------------------------------------------------------------------------------------
 // K-extract restricted to a range of leading bytes (A13; base_engine.cpp:254-281 Lv1 passes over bucket ranges):
 // when the records of a whole library do not fit in HBM the count stage runs in rounds, each round extracting only
-// the edges whose first four bases (top record byte) lie in [lo, hi].  Two launches, no atomics, read order kept:
+// the edges whose first eight bases (the 16-bit bucket id) lie in [lo, hi].  Two launches, no atomics, read order kept:
 //   WRITE = false: per_read[r] = number of in-range edges of read r (+ optional histogram of record byte hist_byte)
 //   WRITE = true : per_read[r] = exclusive prefix of those counts; in-range records are stored compactly from there
 // ------------------------------------------------------------------------------------------------
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kExtractThreads)
       bool in = false;
       if (q < n_e) {
         make_count_record<W, WR>(s, nwords, L, k, q, rec, strand);
-        const u32 top = rec[0] >> 24;
+        const u32 top = rec[0] >> 16;  // the 8-base bucket id (base_engine.h kNumBuckets)
         in = top >= lo && top <= hi;
       }
       const u32 mask = __ballot_sync(0xffffffffu, in);

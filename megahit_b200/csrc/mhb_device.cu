@@ -84,12 +84,14 @@ extern "C" uint32_t mhb_s2s_sort_bytes(uint32_t k, uint8_t *bytes) {
 #define MHB_FOR_WR(M) MHB_FOR_W(M) M(17)
 
 static int g_sm_count = 0;
+static int g_bound_device = -1;
 static int sm_count() {
   if (!g_sm_count) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (g_sm_count <= 0) g_sm_count = 148;
+    if (g_bound_device < 0) g_bound_device = dev;  // first compute call: the process stays on this device
   }
   return g_sm_count;
 }
@@ -114,6 +116,27 @@ static int check_reads(const mhb_dev_reads *r, uint32_t k) {
     return mhb_set_error(MHB_ERR_ARG, "variable-length reads need rec_off and edge_off");
   return MHB_OK;
 }
+
+// grow-only per-device scratch for block sums of scans issued from entry points that take no scratch argument
+static int grow_scratch(size_t bytes, void **out) {
+  static void *buf[64] = {nullptr};
+  static size_t cap[64] = {0};
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return mhb_set_error(MHB_ERR_CUDA, "device index %d out of range", dev);
+  if (cap[dev] < bytes) {
+    CK(cudaDeviceSynchronize());
+    if (buf[dev]) cudaFree(buf[dev]);
+    buf[dev] = nullptr;
+    cap[dev] = 0;
+    const size_t want = (bytes + 4095) & ~(size_t)4095;
+    CK(cudaMalloc(&buf[dev], want));
+    cap[dev] = want;
+  }
+  *out = buf[dev];
+  return MHB_OK;
+}
+static int scan64(cudaStream_t st, u64 *v, u64 n, u64 *total_dev, u64 *bsum);
 
 // ------------------------------------------------------------------------------------------------
 // count: extract
@@ -153,7 +176,7 @@ extern "C" int mhb_count_extract_range(void *stream, const mhb_dev_reads *reads,
                                        int write, uint64_t *per_read, uint32_t *records, uint64_t *hist256, int hist_byte,
                                        uint64_t *total_dev) {
   if (int rc = check_reads(reads, k)) return rc;
-  if (lo > hi || hi > 255) return mhb_set_error(MHB_ERR_ARG, "bad leading-byte range [%u, %u]", lo, hi);
+  if (lo > hi || hi > 65535) return mhb_set_error(MHB_ERR_ARG, "bad bucket range [%u, %u]", lo, hi);
   if (!per_read || (write && !records) || (!write && !total_dev)) return mhb_set_error(MHB_ERR_ARG, "null buffer");
   cudaStream_t st = (cudaStream_t)stream;
   if (reads->n_reads == 0) {
@@ -177,8 +200,11 @@ extern "C" int mhb_count_extract_range(void *stream, const mhb_dev_reads *reads,
 #undef M2
   CK_LAUNCH();
   if (!write) {
-    k_scan_u64<<<1, 1024, 0, st>>>(per_read, rv.n_reads, total_dev);
-    CK_LAUNCH();
+    // three-phase scan (the block sums live in this device's small scratch): a single-CTA scan over all reads would
+    // dominate a library that needs many rounds
+    u64 *bsum = nullptr;
+    if (int rc = grow_scratch(((rv.n_reads / kScanTile) + 2) * 8, (void **)&bsum)) return rc;
+    if (int rc = scan64(st, per_read, rv.n_reads, total_dev, bsum)) return rc;
     CK(cudaMemcpyAsync(per_read + rv.n_reads, total_dev, 8, cudaMemcpyDeviceToDevice, st));
   }
   return MHB_OK;
@@ -791,7 +817,7 @@ extern "C" int mhb_s2s_extract_range(void *stream, const mhb_dev_seqs *seqs, uin
                                      uint32_t lo, uint32_t hi, uint64_t *cursor_dev, uint64_t capacity, uint64_t *hist256,
                                      int hist_byte) {
   if (!seqs || k < 9 || k > MHB_MAX_K) return mhb_set_error(MHB_ERR_ARG, "kmer size must be >= 9 and <= 255");
-  if (lo > hi || hi > 255) return mhb_set_error(MHB_ERR_ARG, "bad leading-byte range [%u, %u]", lo, hi);
+  if (lo > hi || hi > 65535) return mhb_set_error(MHB_ERR_ARG, "bad bucket range [%u, %u]", lo, hi);
   if (records && !cursor_dev) return mhb_set_error(MHB_ERR_ARG, "cursor is NULL");
   if (n_items == 0) return MHB_OK;
   if (!seqs->mult && !(seqs->fixed_len && seqs->fixed_stride))
@@ -1002,11 +1028,33 @@ extern "C" int mhb_edge_lut_build(void *stream, const uint32_t *edges, uint64_t 
   return MHB_OK;
 }
 
-extern "C" int mhb_mercy_edges_segs(void *stream, const mhb_dev_reads *reads, const uint64_t *cand_ids, uint64_t n_cand,
-                                    uint32_t max_read_len, uint32_t k, uint32_t n_segs, const uint32_t *const *seg_edges,
-                                    const uint64_t *seg_counts, const void *const *seg_luts, const uint8_t *owner_of_byte,
-                                    uint32_t *mercy_out, uint64_t capacity, uint64_t *n_mercy_host, void *scratch,
-                                    size_t scratch_bytes) {
+// Layout of the mercy scratch shared by the count and the write half
+struct MercyScratch {
+  u64 *total;
+  u32 *bits, *count;
+  u64 *off, *bsum;
+  u32 wpr;
+};
+static MercyScratch mercy_scratch_layout(void *scratch, uint64_t n_cand, uint32_t max_read_len) {
+  MercyScratch m;
+  m.wpr = (max_read_len + 31) / 32 + 1;
+  char *p = (char *)scratch;
+  m.total = (u64 *)p;
+  p += 256;
+  m.bits = (u32 *)p;
+  p += ((size_t)n_cand * 3 * m.wpr * 4 + 255) & ~(size_t)255;
+  m.count = (u32 *)p;
+  p += ((size_t)n_cand * 4 + 255) & ~(size_t)255;
+  m.off = (u64 *)p;
+  p += ((size_t)n_cand * 8 + 255) & ~(size_t)255;
+  m.bsum = (u64 *)p;
+  return m;
+}
+
+extern "C" int mhb_mercy_edges_count(void *stream, const mhb_dev_reads *reads, const uint64_t *cand_ids, uint64_t n_cand,
+                                     uint32_t max_read_len, uint32_t k, uint32_t n_segs, const uint32_t *const *seg_edges,
+                                     const uint64_t *seg_counts, const void *const *seg_luts, const uint8_t *owner_of_byte,
+                                     uint64_t *n_mercy_host, void *scratch, size_t scratch_bytes) {
   *n_mercy_host = 0;
   if (int rc = check_reads(reads, k)) return rc;
   if (n_cand == 0) return MHB_OK;
@@ -1027,37 +1075,51 @@ extern "C" int mhb_mercy_edges_segs(void *stream, const mhb_dev_reads *reads, co
     sg.owner[b] = owner_of_byte ? owner_of_byte[b] : 0;
     if (sg.owner[b] >= n_segs) return mhb_set_error(MHB_ERR_ARG, "owner_of_byte[%d] = %u out of range", b, sg.owner[b]);
   }
-  const u32 wpr = (max_read_len + 31) / 32 + 1, WE = words_per_edge(k), WM = div_ceil(k + 1, 16);
-  char *p = (char *)scratch;
-  u64 *total = (u64 *)p;
-  p += 256;
-  u32 *bits = (u32 *)p;
-  p += ((size_t)n_cand * 3 * wpr * 4 + 255) & ~(size_t)255;
-  u32 *count = (u32 *)p;
-  p += ((size_t)n_cand * 4 + 255) & ~(size_t)255;
-  u64 *off = (u64 *)p;
-  p += ((size_t)n_cand * 8 + 255) & ~(size_t)255;
-  u64 *bsum = (u64 *)p;
+  const u32 WE = words_per_edge(k), WM = div_ceil(k + 1, 16);
+  const MercyScratch ms = mercy_scratch_layout(scratch, n_cand, max_read_len);
   u64 g64 = (n_cand + 7) / 8;
   if (g64 > (u64)sm_count() * 16) g64 = (u64)sm_count() * 16;
 #define M(WW) \
-  if (WM == WW) k_mercy_probe<WW><<<(unsigned)g64, 256, 0, st>>>(rv, cand_ids, n_cand, k, sg, WE, bits, wpr);
+  if (WM == WW) k_mercy_probe<WW><<<(unsigned)g64, 256, 0, st>>>(rv, cand_ids, n_cand, k, sg, WE, ms.bits, ms.wpr);
   MHB_FOR_W(M)
 #undef M
   CK_LAUNCH();
   const unsigned g = (unsigned)((n_cand + 127) / 128);
-  k_mercy_emit<false><<<g, 128, 0, st>>>(rv, cand_ids, n_cand, k, bits, wpr, count, nullptr, nullptr, WE);
+  k_mercy_emit<false><<<g, 128, 0, st>>>(rv, cand_ids, n_cand, k, ms.bits, ms.wpr, ms.count, nullptr, nullptr, WE);
   CK_LAUNCH();
-  if (int rc = scan32(st, count, n_cand, off, total, bsum)) return rc;
-  CK(cudaMemcpyAsync(n_mercy_host, total, 8, cudaMemcpyDeviceToHost, st));
+  if (int rc = scan32(st, ms.count, n_cand, ms.off, ms.total, ms.bsum)) return rc;
+  CK(cudaMemcpyAsync(n_mercy_host, ms.total, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  if (*n_mercy_host > capacity) return mhb_set_error(MHB_ERR_NOMEM, "mercy edges (%llu) exceed capacity (%llu)",
-                                                     (unsigned long long)*n_mercy_host, (unsigned long long)capacity);
-  if (*n_mercy_host) {
-    k_mercy_emit<true><<<g, 128, 0, st>>>(rv, cand_ids, n_cand, k, bits, wpr, count, off, mercy_out, WE);
-    CK_LAUNCH();
-  }
   return MHB_OK;
+}
+
+extern "C" int mhb_mercy_edges_write(void *stream, const mhb_dev_reads *reads, const uint64_t *cand_ids, uint64_t n_cand,
+                                     uint32_t max_read_len, uint32_t k, uint32_t *mercy_out, uint64_t capacity,
+                                     uint64_t n_mercy, void *scratch, size_t scratch_bytes) {
+  if (int rc = check_reads(reads, k)) return rc;
+  if (n_cand == 0 || n_mercy == 0) return MHB_OK;
+  if (scratch_bytes < mercy_core_scratch(n_cand, max_read_len)) return mhb_set_error(MHB_ERR_ARG, "scratch too small");
+  if (n_mercy > capacity) return mhb_set_error(MHB_ERR_NOMEM, "mercy edges (%llu) exceed capacity (%llu)",
+                                               (unsigned long long)n_mercy, (unsigned long long)capacity);
+  cudaStream_t st = (cudaStream_t)stream;
+  const ReadsView rv = make_reads_view(reads);
+  const MercyScratch ms = mercy_scratch_layout(scratch, n_cand, max_read_len);
+  const unsigned g = (unsigned)((n_cand + 127) / 128);
+  k_mercy_emit<true><<<g, 128, 0, st>>>(rv, cand_ids, n_cand, k, ms.bits, ms.wpr, ms.count, ms.off, mercy_out, words_per_edge(k));
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
+extern "C" int mhb_mercy_edges_segs(void *stream, const mhb_dev_reads *reads, const uint64_t *cand_ids, uint64_t n_cand,
+                                    uint32_t max_read_len, uint32_t k, uint32_t n_segs, const uint32_t *const *seg_edges,
+                                    const uint64_t *seg_counts, const void *const *seg_luts, const uint8_t *owner_of_byte,
+                                    uint32_t *mercy_out, uint64_t capacity, uint64_t *n_mercy_host, void *scratch,
+                                    size_t scratch_bytes) {
+  if (int rc = mhb_mercy_edges_count(stream, reads, cand_ids, n_cand, max_read_len, k, n_segs, seg_edges, seg_counts, seg_luts,
+                                     owner_of_byte, n_mercy_host, scratch, scratch_bytes))
+    return rc;
+  return mhb_mercy_edges_write(stream, reads, cand_ids, n_cand, max_read_len, k, mercy_out, capacity, *n_mercy_host, scratch,
+                               scratch_bytes);
 }
 
 extern "C" int mhb_mercy_edges(void *stream, const mhb_dev_reads *reads, const uint64_t *cand_ids, uint64_t n_cand,
@@ -1076,8 +1138,15 @@ extern "C" int mhb_mercy_edges(void *stream, const mhb_dev_reads *reads, const u
                               capacity, n_mercy_host, scratch, core);
 }
 
+// One process drives one GPU (the multi-GPU build is one process per GPU): kernel attributes, occupancy caches and the
+// host-level arena are per process, so the device can be chosen once, before the first compute call; choosing the same
+// device again is a no-op, switching afterwards is refused instead of silently dereferencing the other GPU's memory.
 extern "C" int mhb_set_device(int device) {
+  if (g_bound_device >= 0 && device != g_bound_device)
+    return mhb_set_error(MHB_ERR_ARG, "this process is bound to CUDA device %d: mhb_set_device(%d) must be the first libmhb call "
+                         "(one process per GPU)", g_bound_device, device);
   CK(cudaSetDevice(device));
+  g_bound_device = device;
   g_sm_count = 0;
   return MHB_OK;
 }

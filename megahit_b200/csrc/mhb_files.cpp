@@ -1,6 +1,6 @@
 // mhb_files.cpp -- file-level C ABI (include/mhb.h, layer 3): the `count` and `seq2sdbg` sub-commands on
-// the reference's on-disk formats.  Host-side IO only; all sorting/counting/emission runs on the GPU
-// through mhb_count_host / mhb_s2s_host.
+// the reference's on-disk formats.  Host-side IO only; all sorting/counting/mercy-edge search/emission runs on the
+// GPU through mhb_count_host / mhb_mercy_host / mhb_s2s_host.
 //
 // Formats follow voutcn/megahit v1.2.9 (paths relative to src/):
 //   read library   sequence/io/sequence_lib.cpp:93-118, sequence/sequence_package.h:224-240
@@ -8,7 +8,6 @@
 //   candidates     sorting/kmer_counter.cpp:383-401 ; counting: sorting/edge_counter.h:44-52
 //   contigs        sequence/io/contig/contig_reader.h:52-119
 //   SdBG           sdbg/sdbg_writer.cpp:25-79, sdbg/sdbg_meta.cpp:12-61
-#include <omp.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -196,177 +195,6 @@ int write_edges(const std::string &prefix, uint32_t k, const uint32_t *edges, ui
 }
 
 // ------------------------------------------------------------------------------------------------
-// mercy edges (seq_to_sdbg.cpp:100-357) -- host side, OpenMP over candidate reads.
-// Operates on base arrays for clarity; candidate reads are few (~0.2 % of reads).
-// ------------------------------------------------------------------------------------------------
-struct EdgeIndex {
-  const uint32_t *e;
-  int64_t n;
-  uint32_t wpe;
-  std::vector<int64_t> lut;  // [first,last] per 12-mer prefix, -1 = empty
-  uint32_t base(int64_t id, uint32_t i) const { return base_at(e + (size_t)id * wpe, i); }
-  void build() {  // InitLookupTable :100-127
-    lut.assign(2u << 24, -1);
-    if (n == 0) return;
-    uint32_t cur = e[0] >> 8;
-    lut[2 * (size_t)cur] = 0;
-    for (int64_t i = 1; i < n; ++i) {
-      const uint32_t p = e[(size_t)i * wpe] >> 8;
-      if (p > cur) {
-        lut[2 * (size_t)cur + 1] = i - 1;
-        cur = p;
-        lut[2 * (size_t)cur] = i;
-      }
-    }
-    lut[2 * (size_t)cur + 1] = n - 1;
-  }
-  int64_t search(const uint8_t *km, uint32_t ksz) const {  // BinarySearchKmer :132-161
-    uint32_t prefix = 0;
-    for (uint32_t i = 0; i < 12; ++i) prefix = (prefix << 2) | (i < ksz ? km[i] : 0u);
-    int64_t l = lut[2 * (size_t)prefix];
-    if (l == -1) return -1;
-    int64_t r = lut[2 * (size_t)prefix + 1];
-    while (l <= r) {
-      const int64_t mid = (l + r) / 2;
-      int cmp = 0;
-      for (uint32_t i = 0; i < ksz; ++i) {
-        const uint32_t eb = base(mid, i);
-        if (km[i] != eb) {
-          cmp = km[i] < eb ? -1 : 1;
-          break;
-        }
-      }
-      if (cmp > 0) l = mid + 1;
-      else if (cmp < 0) r = mid - 1;
-      else return mid;
-    }
-    return -1;
-  }
-};
-
-int cmp_bases(const uint8_t *x, const uint8_t *y, uint32_t n) {
-  for (uint32_t i = 0; i < n; ++i)
-    if (x[i] != y[i]) return x[i] < y[i] ? -1 : 1;
-  return 0;
-}
-
-// cand: `.cand` image (u32 len + words per read, package orientation).  Appends (k+1)-mers with mult 1.
-int gen_mercy_edges(const std::vector<uint32_t> &edges, uint32_t wpe, const std::vector<uint32_t> &cand, uint32_t k,
-                    int n_threads, HostSeqs *out, int64_t *n_reads_out, int64_t *n_mercy_out) {
-  EdgeIndex ix{edges.data(), (int64_t)(edges.size() / wpe), wpe, {}};
-  ix.build();
-  std::vector<size_t> starts;
-  for (size_t pos = 0; pos < cand.size();) {
-    starts.push_back(pos);
-    pos += 1 + div_ceil(cand[pos], 16);
-  }
-  const int64_t nr = (int64_t)starts.size();
-  std::vector<std::vector<uint32_t>> per_read(nr);  // mercy edges of each read, WM words each
-  const uint32_t WM = div_ceil(k + 1, 16);
-#pragma omp parallel for schedule(dynamic, 64) num_threads(n_threads > 0 ? n_threads : 1)
-  for (int64_t r = 0; r < nr; ++r) {
-    const uint32_t L = cand[starts[r]];
-    const uint32_t *w = cand.data() + starts[r] + 1;
-    if (L < k + 2) continue;  // :206-208
-    std::vector<uint8_t> has_in(L + 2, 0), has_out(L + 2, 0), km(k + 2), rv(k + 2);
-    for (uint32_t i = 0; i < k; ++i) {
-      km[i] = (uint8_t)base_at(w, i);
-      rv[i] = (uint8_t)(3u - base_at(w, k - 1 - i));
-    }
-    km[k] = rv[k] = 0;
-    for (uint32_t i = 0; i + k <= L; ++i) {  // :224-307
-      if (!has_in[i]) {
-        if (ix.search(rv.data(), k) != -1) {
-          has_in[i] = 1;
-        } else {
-          rv[k] = 3;
-          memmove(&km[1], &km[0], k);
-          for (uint32_t c = 0; c < 4; ++c) {
-            km[0] = (uint8_t)c;
-            if (cmp_bases(km.data(), rv.data(), k + 1) > 0) break;
-            if (ix.search(km.data(), k + 1) != -1) {
-              has_in[i] = 1;
-              break;
-            }
-          }
-          rv[k] = 0;
-          memmove(&km[0], &km[1], k);
-          km[k] = 0;
-        }
-      }
-      const int64_t edge_id = ix.search(km.data(), k);
-      if (edge_id != -1) {
-        has_out[i] = 1;
-        if (i + k < L && ix.base(edge_id, k) == base_at(w, i + k)) has_in[i + 1] = 1;
-      } else {
-        km[k] = 3;
-        const uint32_t next_char = i + k < L ? 3u - base_at(w, i + k) : 0u;
-        memmove(&rv[1], &rv[0], k);
-        rv[0] = (uint8_t)next_char;
-        if (cmp_bases(rv.data(), km.data(), k + 1) <= 0 && ix.search(rv.data(), k + 1) != -1) {
-          has_out[i] = 1;
-          has_in[i + 1] = 1;
-        } else {
-          for (uint32_t c = 0; c < 4; ++c) {
-            if (c == next_char) continue;
-            rv[0] = (uint8_t)c;
-            if (cmp_bases(rv.data(), km.data(), k + 1) > 0) break;
-            if (ix.search(rv.data(), k + 1) != -1) {
-              has_out[i] = 1;
-              break;
-            }
-          }
-        }
-        km[k] = 0;
-        memmove(&rv[0], &rv[1], k);
-        rv[k] = 0;
-      }
-      if (i + k < L) {
-        const uint32_t nc = base_at(w, i + k);
-        memmove(&km[0], &km[1], k - 1);
-        km[k - 1] = (uint8_t)nc;
-        memmove(&rv[1], &rv[0], k - 1);
-        rv[0] = (uint8_t)(3u - nc);
-      }
-    }
-    int last_no_out = -1;  // :310-352
-    for (uint32_t i = 0; i + k <= L; ++i) {
-      switch (has_in[i] | (has_out[i] << 1)) {
-        case 1:
-          last_no_out = (int)i;
-          break;
-        case 2:
-          if (last_no_out >= 0) {
-            for (uint32_t j = (uint32_t)last_no_out; j < i; ++j) {
-              const size_t at = per_read[r].size();
-              per_read[r].resize(at + WM, 0);
-              for (uint32_t x = 0; x < k + 1; ++x)
-                per_read[r][at + (x >> 4)] |= base_at(w, j + x) << (30 - 2 * (x & 15));
-            }
-          }
-          last_no_out = -1;
-          break;
-        case 3:
-          last_no_out = -1;
-          break;
-        default:
-          break;
-      }
-    }
-  }
-  int64_t n_mercy = 0;
-  for (int64_t r = 0; r < nr; ++r) {
-    for (size_t at = 0; at < per_read[r].size(); at += WM) {
-      out->append_packed(per_read[r].data() + at, k + 1, 1);
-      ++n_mercy;
-    }
-  }
-  *n_reads_out = nr;
-  *n_mercy_out = n_mercy;
-  return MHB_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
 // contigs (contig_reader.h:52-119): FASTA with "flag=F multi=M len=N" comments
 // ------------------------------------------------------------------------------------------------
 int read_contigs(const std::string &path, uint32_t min_len, uint32_t k_from, uint32_t k_to, bool reverse,
@@ -510,7 +338,6 @@ extern "C" int mhb_seq2sdbg_run(const mhb_seq2sdbg_opts *o) {
   if (o->host_mem == 0) return mhb_set_error(MHB_ERR_ARG, "Please specify the host memory!");
   const uint32_t k = o->k;
   const double t0 = now_s();
-  const int n_threads = o->num_cpu_threads > 0 ? o->num_cpu_threads : omp_get_max_threads();
 
   HostSeqs seqs;
   if (!input.empty()) {  // seq_to_sdbg.cpp:424-434
@@ -528,8 +355,12 @@ extern "C" int mhb_seq2sdbg_run(const mhb_seq2sdbg_opts *o) {
       std::vector<uint32_t> cand;
       if (!meta.is_sorted) return mhb_set_error(MHB_ERR_ARG, "--need_mercy needs sorted edges");
       read_file(input + ".cand", &cand, false);
-      int64_t nr = 0, nm = 0;
-      if (int rc = gen_mercy_edges(edges, W, cand, k, std::max(1, n_threads - 1), &seqs, &nr, &nm)) return rc;
+      // GenMercyEdges (seq_to_sdbg.cpp:171-357) on the device: k_mercy_probe / k_mercy_emit through the host-level ABI
+      uint32_t *mercy = nullptr;
+      uint64_t nm = 0, nr = 0;
+      if (int rc = mhb_mercy_host(k, edges.data(), n, cand.data(), cand.size(), &mercy, &nm, &nr)) return rc;
+      for (uint64_t i = 0; i < nm; ++i) seqs.append_packed(mercy + i * W, k + 1, 1);
+      mhb_free(mercy);
       XINFO("Number of reads: %lld, Number of mercy edges: %lld\n", (long long)nr, (long long)nm);
       XINFO("Adding mercy Done. Time elapsed: %.4f\n", now_s() - t1);
     }

@@ -136,7 +136,8 @@ extern "C" int mhb_release(void) {
 // count, out of core (A13): rounds over ranges of the leading record byte
 // ================================================================================================
 namespace {
-uint64_t g_round_limit = 0;  // 0 = derive from free device memory
+uint64_t g_round_limit = 0;      // count records per round; 0 = derive from free device memory
+uint64_t g_s2s_round_limit = 0;  // seq2sdbg sort items per round; 0 = derive from free device memory
 
 // bytes of device memory one round of `n` records needs besides the resident read library
 size_t round_bytes(uint64_t n, uint32_t WR, uint32_t WE, int32_t m) {
@@ -177,8 +178,81 @@ extern "C" int mhb_plan_rounds(const uint64_t *hist256, uint64_t max_records, ui
   return n + 1;
 }
 
+// Two-level planner (cf. Lv1FindEndBuckets, base_engine.cpp:254-281, which cuts on the 65 536 8-base buckets): the
+// unit is the leading byte (256 bucket ids) unless that byte alone exceeds the cap - canonical (k+1)-mers are skewed
+// towards A-prefixes, poly-A / low-complexity data more so - in which case the byte is cut on its second byte, i.e. on
+// bucket ids.  sub_hist = 256 x 256 counts (row b = second-byte histogram of leading byte b); only rows of oversized
+// bytes are read, and it may be NULL when there are none.  Output: ranges of 16-bit bucket ids.  Returns the number of
+// ranges, -1 when a single bucket exceeds the cap or more than cap_out ranges are needed.
+extern "C" int mhb_plan_rounds16(const uint64_t *hist256, const uint64_t *sub_hist, uint64_t max_records, uint32_t *lo_out,
+                                 uint32_t *hi_out, uint32_t cap_out) {
+  if (!hist256 || !lo_out || !hi_out || max_records == 0 || cap_out == 0) {
+    mhb_set_error(MHB_ERR_ARG, "bad round plan arguments");
+    return -1;
+  }
+  uint32_t n = 0, lo = 0;
+  uint64_t acc = 0;
+  bool open = false;
+  auto close_at = [&](uint32_t hi) -> bool {  // ends the open range at bucket id hi
+    if (n >= cap_out) return false;
+    lo_out[n] = lo;
+    hi_out[n] = hi;
+    ++n;
+    return true;
+  };
+  auto add = [&](uint32_t a_lo, uint32_t a_hi, uint64_t cnt) -> int {  // next atom [a_lo, a_hi] with cnt records
+    if (cnt > max_records) {
+      mhb_set_error(MHB_ERR_NOMEM, "bucket 0x%04x alone holds %llu records, more than one round can take (%llu)", a_lo,
+                    (unsigned long long)cnt, (unsigned long long)max_records);
+      return -1;
+    }
+    if (open && acc + cnt > max_records) {
+      if (!close_at(a_lo - 1)) return -2;
+      open = false;
+    }
+    if (!open) {
+      lo = a_lo;
+      acc = 0;
+      open = true;
+    }
+    acc += cnt;
+    (void)a_hi;
+    return 0;
+  };
+  for (uint32_t b = 0; b < 256; ++b) {
+    int rc = 0;
+    if (hist256[b] > max_records) {
+      if (!sub_hist) {
+        mhb_set_error(MHB_ERR_NOMEM, "leading byte 0x%02x alone holds %llu records, more than one round can take (%llu)", b,
+                      (unsigned long long)hist256[b], (unsigned long long)max_records);
+        return -1;
+      }
+      for (uint32_t c = 0; c < 256 && !rc; ++c) rc = add((b << 8) | c, (b << 8) | c, sub_hist[(size_t)b * 256 + c]);
+    } else {
+      rc = add(b << 8, (b << 8) | 255u, hist256[b]);
+    }
+    if (rc == -1) return -1;
+    if (rc == -2) break;
+  }
+  if (!open) {  // no records at all: one empty range covering everything
+    lo = 0;
+    open = true;
+  }
+  if (lo_out && n < cap_out) {
+    lo_out[n] = n ? lo : 0;
+    hi_out[n] = 65535;
+    return (int)n + 1;
+  }
+  mhb_set_error(MHB_ERR_NOMEM, "round plan needs more than %u ranges", cap_out);
+  return -1;
+}
+
 extern "C" int mhb_set_round_limit(uint64_t max_records_per_round) {
   g_round_limit = max_records_per_round;
+  return MHB_OK;
+}
+extern "C" int mhb_set_s2s_round_limit(uint64_t max_items_per_round) {
+  g_s2s_round_limit = max_items_per_round;
   return MHB_OK;
 }
 
@@ -265,14 +339,25 @@ static int count_host_rounds(const mhb_count_args *args, mhb_count_result *res, 
   reads.rec_off = d_rec_off;
   reads.edge_off = d_edge_off;
 
-  // ---- plan: histogram of the leading byte over the whole library, then greedy contiguous ranges ----
+  // ---- plan: histogram of the leading byte over the whole library (+ of the second byte inside every leading byte
+  // that alone exceeds a round), then greedy contiguous ranges of bucket ids ----
   t.start();
   uint64_t h_top[256];
-  CKR(mhb_count_extract_range(st, &reads, k, 0, 255, 0, d_per_read, nullptr, d_hist_top, top_byte, d_scalars + 1));
+  CKR(mhb_count_extract_range(st, &reads, k, 0, 65535, 0, d_per_read, nullptr, d_hist_top, top_byte, d_scalars + 1));
   CK(cudaMemcpyAsync(h_top, d_hist_top, sizeof(h_top), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  uint32_t r_lo[256], r_hi[256];
-  const int n_ranges = mhb_plan_rounds(h_top, max_records, r_lo, r_hi);
+  std::vector<uint64_t> h_sub;
+  for (uint32_t b = 0; b < 256; ++b) {
+    if (h_top[b] <= max_records) continue;
+    if (WR * 4 < 2) return mhb_set_error(MHB_ERR_NOMEM, "leading byte 0x%02x exceeds a round and the record has no second byte", b);
+    if (h_sub.empty()) h_sub.assign(256 * 256, 0);
+    CK(cudaMemsetAsync(d_hist0, 0, 256 * 8, st));
+    CKR(mhb_count_extract_range(st, &reads, k, b << 8, (b << 8) | 255u, 0, d_per_read, nullptr, d_hist0, top_byte - 1, d_scalars + 1));
+    CK(cudaMemcpyAsync(h_sub.data() + (size_t)b * 256, d_hist0, 256 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  std::vector<uint32_t> r_lo(65536), r_hi(65536);
+  const int n_ranges = mhb_plan_rounds16(h_top, h_sub.empty() ? nullptr : h_sub.data(), max_records, r_lo.data(), r_hi.data(), 65536);
   if (n_ranges < 0) return MHB_ERR_NOMEM;  // message set by the planner
   std::vector<std::pair<uint32_t, uint32_t>> ranges;
   for (int i = 0; i < n_ranges; ++i) ranges.push_back({r_lo[i], r_hi[i]});
@@ -643,14 +728,23 @@ static int s2s_host_rounds(const mhb_s2s_args *args, mhb_s2s_result *res, const 
   seqs.mult = d_mult;
   seqs.fixed_stride = 0;
 
-  // ---- plan ----
+  // ---- plan (two-level, as in count_host_rounds) ----
   t.start();
   uint64_t h_top[256];
-  CKR(mhb_s2s_extract_range(st, &seqs, k, nullptr, n_items, 0, 255, nullptr, 0, d_hist_top, top_byte));
+  CKR(mhb_s2s_extract_range(st, &seqs, k, nullptr, n_items, 0, 65535, nullptr, 0, d_hist_top, top_byte));
   CK(cudaMemcpyAsync(h_top, d_hist_top, sizeof(h_top), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  uint32_t r_lo[256], r_hi[256];
-  const int n_ranges = mhb_plan_rounds(h_top, max_items, r_lo, r_hi);
+  std::vector<uint64_t> h_sub;
+  for (uint32_t b = 0; b < 256; ++b) {
+    if (h_top[b] <= max_items) continue;
+    if (h_sub.empty()) h_sub.assign(256 * 256, 0);
+    CK(cudaMemsetAsync(d_hist0, 0, 256 * 8, st));
+    CKR(mhb_s2s_extract_range(st, &seqs, k, nullptr, n_items, b << 8, (b << 8) | 255u, nullptr, 0, d_hist0, top_byte - 1));
+    CK(cudaMemcpyAsync(h_sub.data() + (size_t)b * 256, d_hist0, 256 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  std::vector<uint32_t> r_lo(65536), r_hi(65536);
+  const int n_ranges = mhb_plan_rounds16(h_top, h_sub.empty() ? nullptr : h_sub.data(), max_items, r_lo.data(), r_hi.data(), 65536);
   if (n_ranges < 0) return MHB_ERR_NOMEM;
   res->t_extract_ms = t.stop();
 
@@ -750,13 +844,13 @@ extern "C" int mhb_s2s_host(const mhb_s2s_args *args, mhb_s2s_result *res) {
                 Arena::pad(256 * 8) + Arena::pad(16 * 8) + 4096;
   {
     // A13: items that do not fit the device at once (or a caller-imposed cap) -> rounds over leading-byte ranges
-    bool rounds = g_round_limit && n_items > g_round_limit;
+    bool rounds = g_s2s_round_limit && n_items > g_s2s_round_limit;
     if (!rounds && need > g_arena.cap) {
       size_t free_b = 0, total_b = 0;
       CK(cudaMemGetInfo(&free_b, &total_b));
       rounds = (double)need > 0.92 * (double)(free_b + g_arena.cap);
     }
-    if (rounds) return s2s_host_rounds(args, res, item_off, n_items, fixed, L0, n_words, g_round_limit);
+    if (rounds) return s2s_host_rounds(args, res, item_off, n_items, fixed, L0, n_words, g_s2s_round_limit);
   }
   CKR(g_arena.reserve(need));
   uint32_t *d_words = g_arena.take<uint32_t>(n_words + 16);
@@ -885,12 +979,14 @@ extern "C" int mhb_build_host(const mhb_build_args *args, mhb_build_result *res)
   char *work = g_arena.take<char>(count_work);
   size_t work_bytes = count_work;
   char *extra = nullptr;  // separately allocated work area when the SdBG stage outgrows the count stage's
+  char *big_edges = nullptr;  // solid + mercy edges when the mercy edges do not fit behind the solid ones in d_edges
   struct ExtraGuard {
     char *&p;
     ~ExtraGuard() {
       if (p) cudaFree(p);
     }
-  } guard{extra};
+  } guard{extra}, guard2{big_edges};
+  uint32_t *d_all_edges = d_edges;
 
   // ---- H2D ----
   // MHB_H2D_CHUNKS=C (opt-in, fixed-length libraries): the library is uploaded in C pieces on a copy stream and the
@@ -997,8 +1093,27 @@ extern "C" int mhb_build_host(const mhb_build_args *args, mhb_build_result *res)
       CK(cudaStreamSynchronize(st));  // the tip set / candidate scratch may be released by work_area()
       char *d_ms = work_area(ms_bytes);
       if (!d_ms) return mhb_set_error(MHB_ERR_NOMEM, "cudaMalloc for the mercy stage failed");
-      CKR(mhb_mercy_edges(st, &reads, d_cand, n_cand, max_len, k, d_edges, n_solid, d_edges + (size_t)n_solid * WE,
-                          cap_edges - n_solid, &n_mercy, d_ms, ms_bytes));
+      // count first (probe + per-read counts + scan), then size the destination: reads that overlap only at their ends
+      // can put more mercy edges between two tips than n/m + 1 - n_solid (the reference reserves +25 % and grows,
+      // seq_to_sdbg.cpp:371-379; here the exact number is known before anything is written)
+      const size_t core = ms_bytes - mhb_edge_lut_bytes();
+      void *lut = d_ms + core;
+      CKR(mhb_edge_lut_build(st, d_edges, n_solid, k, lut));
+      const uint32_t *seg_e[1] = {d_edges};
+      const uint64_t seg_n[1] = {n_solid};
+      const void *seg_l[1] = {lut};
+      CKR(mhb_mercy_edges_count(st, &reads, d_cand, n_cand, max_len, k, 1, seg_e, seg_n, seg_l, nullptr, &n_mercy, d_ms, core));
+      if (n_mercy > cap_edges - n_solid) {
+        const size_t eb = Arena::pad((size_t)(n_solid + n_mercy) * WE * 4 + 16);
+        if (cudaMalloc((void **)&big_edges, eb) != cudaSuccess) {
+          cudaGetLastError();
+          return mhb_set_error(MHB_ERR_NOMEM, "cudaMalloc of %zu bytes for solid + mercy edges failed", eb);
+        }
+        CK(cudaMemcpyAsync(big_edges, d_edges, (size_t)n_solid * WE * 4, cudaMemcpyDeviceToDevice, st));
+        d_all_edges = (uint32_t *)big_edges;
+      }
+      CKR(mhb_mercy_edges_write(st, &reads, d_cand, n_cand, max_len, k, d_all_edges + (size_t)n_solid * WE, n_mercy, n_mercy,
+                                d_ms, core));
     }
     res->t_mercy_ms = t.stop();
   }
@@ -1032,7 +1147,7 @@ extern "C" int mhb_build_host(const mhb_build_args *args, mhb_build_result *res)
   uint8_t *d_bytes = (uint8_t *)(s_scrp + Arena::pad(s_scr));
   mhb_dev_seqs seqs;
   memset(&seqs, 0, sizeof(seqs));
-  seqs.words = d_edges;
+  seqs.words = d_all_edges;
   seqs.n_words = n_seqs * WE;
   seqs.n_seqs = n_seqs;
   seqs.fixed_len = k + 1;
@@ -1073,6 +1188,103 @@ extern "C" int mhb_build_host(const mhb_build_args *args, mhb_build_result *res)
   CK(cudaStreamSynchronize(st));
   res->t_d2h_ms = t.stop();
   res->t_total_ms = t_all.stop();
+  return MHB_OK;
+}
+
+// ================================================================================================
+// mercy edges from host buffers (what `seq2sdbg --need_mercy` needs between reading `.edges`/`.cand` and SeqToSdbg::Run)
+// ================================================================================================
+extern "C" int mhb_mercy_host(uint32_t k, const uint32_t *edges, uint64_t n_edges, const uint32_t *cand_bin,
+                              uint64_t cand_words, uint32_t **mercy_out, uint64_t *n_mercy_out, uint64_t *n_cand_reads_out) {
+  if (!mercy_out || !n_mercy_out) return mhb_set_error(MHB_ERR_ARG, "null output");
+  *mercy_out = nullptr;
+  *n_mercy_out = 0;
+  if (n_cand_reads_out) *n_cand_reads_out = 0;
+  if (k < 12 || k > MHB_MAX_K) return mhb_set_error(MHB_ERR_ARG, "mercy edges need 12 <= k <= 255");
+  if (mhb_device_count() == 0) return mhb_set_error(MHB_ERR_CUDA, "no CUDA device: libmhb has no CPU path");
+  const uint32_t WE = words_per_edge(k);
+  // `.cand` holds the reads as KmerCounter held them: REVERSED (kmer_counter.cpp:387-401; read back with reverse=false,
+  // seq_to_sdbg.cpp:175-176).  The device kernels take a library in file orientation and apply the reversal themselves,
+  // so every candidate read is turned around once here (they are ~0.2 % of a library).
+  std::vector<uint32_t> bin;
+  std::vector<uint64_t> rec_off, edge_off;
+  bin.reserve(cand_words + 8);
+  uint32_t max_len = 0;
+  uint64_t pos = 0, e = 0;
+  while (pos < cand_words) {
+    const uint32_t L = cand_bin[pos], nw = div_ceil(L, 16);
+    if (pos + 1 + nw > cand_words) return mhb_set_error(MHB_ERR_IO, "candidate read image is truncated");
+    rec_off.push_back(bin.size());
+    edge_off.push_back(e);
+    if (L >= k + 1) e += L - k;
+    const size_t at = bin.size();
+    bin.resize(at + 1 + nw, 0);
+    bin[at] = L;
+    for (uint32_t i = 0; i < L; ++i)
+      bin[at + 1 + (i >> 4)] |= base_at(cand_bin + pos + 1, L - 1 - i) << (30 - 2 * (i & 15));
+    max_len = std::max(max_len, L);
+    pos += 1 + nw;
+  }
+  const uint64_t n_reads = rec_off.size();
+  rec_off.push_back(bin.size());
+  edge_off.push_back(e);
+  if (n_cand_reads_out) *n_cand_reads_out = n_reads;
+  if (n_reads == 0 || n_edges == 0) {
+    *mercy_out = (uint32_t *)malloc(4);
+    return MHB_OK;
+  }
+  const size_t bin_bytes = (bin.size() * 4 + 15) & ~(size_t)15;
+  const size_t ms_bytes = mhb_mercy_edges_scratch_bytes(n_reads, max_len);
+  const size_t need = Arena::pad(bin_bytes + 16) + 3 * Arena::pad((n_reads + 1) * 8) + Arena::pad((size_t)n_edges * WE * 4 + 16) +
+                      Arena::pad(ms_bytes) + 4096;
+  CKR(g_arena.reserve(need));
+  cudaStream_t st = 0;
+  uint32_t *d_bin = g_arena.take<uint32_t>(bin_bytes / 4 + 4);
+  uint64_t *d_rec_off = g_arena.take<uint64_t>(n_reads + 1);
+  uint64_t *d_edge_off = g_arena.take<uint64_t>(n_reads + 1);
+  uint64_t *d_ids = g_arena.take<uint64_t>(n_reads + 1);
+  uint32_t *d_edges = g_arena.take<uint32_t>((size_t)n_edges * WE + 4);
+  char *d_ms = g_arena.take<char>(ms_bytes);
+  std::vector<uint64_t> ids(n_reads);
+  for (uint64_t r = 0; r < n_reads; ++r) ids[r] = r;
+  CK(cudaMemcpyAsync(d_bin, bin.data(), bin.size() * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_rec_off, rec_off.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_edge_off, edge_off.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_ids, ids.data(), n_reads * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_edges, edges, (size_t)n_edges * WE * 4, cudaMemcpyHostToDevice, st));
+  mhb_dev_reads reads;
+  reads.bin = d_bin;
+  reads.bin_words = bin.size();
+  reads.n_reads = n_reads;
+  reads.fixed_len = 0;
+  reads.rec_off = d_rec_off;
+  reads.edge_off = d_edge_off;
+  const size_t core = ms_bytes - mhb_edge_lut_bytes();
+  void *lut = d_ms + core;
+  CKR(mhb_edge_lut_build(st, d_edges, n_edges, k, lut));
+  const uint32_t *seg_e[1] = {d_edges};
+  const uint64_t seg_n[1] = {n_edges};
+  const void *seg_l[1] = {lut};
+  uint64_t n_mercy = 0;
+  CKR(mhb_mercy_edges_count(st, &reads, d_ids, n_reads, max_len, k, 1, seg_e, seg_n, seg_l, nullptr, &n_mercy, d_ms, core));
+  *mercy_out = (uint32_t *)malloc(std::max<size_t>(4, (size_t)n_mercy * WE * 4));
+  if (!*mercy_out) return mhb_set_error(MHB_ERR_NOMEM, "host malloc failed");
+  if (n_mercy) {
+    uint32_t *d_out = nullptr;
+    CK(cudaMalloc((void **)&d_out, (size_t)n_mercy * WE * 4));
+    int rc = mhb_mercy_edges_write(st, &reads, d_ids, n_reads, max_len, k, d_out, n_mercy, n_mercy, d_ms, core);
+    if (!rc && cudaMemcpyAsync(*mercy_out, d_out, (size_t)n_mercy * WE * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+      rc = mhb_set_error(MHB_ERR_CUDA, "mercy edge download failed");
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess)
+      rc = mhb_set_error(MHB_ERR_CUDA, "mercy edge kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_out);
+    if (rc) {
+      free(*mercy_out);
+      *mercy_out = nullptr;
+      return rc;
+    }
+  }
+  *n_mercy_out = n_mercy;
   return MHB_OK;
 }
 

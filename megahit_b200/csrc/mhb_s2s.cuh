@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256)
       if (s_hist[i]) atomicAdd((unsigned long long *)&hist[i], (unsigned long long)s_hist[i]);
 }
 
-// S-extract restricted to the items whose leading record byte (first four bases) lies in [lo, hi] (A13: seq2sdbg in
+// S-extract restricted to the items whose 16-bit bucket id (first eight bases) lies in [lo, hi] (A13: seq2sdbg in
 // rounds when the items of all sequences do not fit in HBM; base_engine.cpp:254-281).  records == nullptr: count only
 // (histogram of record byte hist_byte over the in-range items, e.g. the leading byte itself for the planner).
 // Otherwise the in-range records are appended at records[*cursor ...) with one warp-aggregated atomic per 32 items
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256)
       const u32 offset = (u32)(rem - (u64)strand * per_strand);
       const u32 mult = sv.mult ? (u32)sv.mult[seq] : (s[sv.fixed_stride - 1] & 0xFFFFu);
       make_s2s_record<W>(s, nwords, L, k, strand, offset, mult, rec);
-      const u32 top = rec[0] >> 24;
+      const u32 top = rec[0] >> 16;  // the 8-base bucket id
       in = top >= lo && top <= hi;
     }
     const u32 mask = __ballot_sync(0xffffffffu, in);

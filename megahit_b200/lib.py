@@ -101,11 +101,11 @@ class Seq2SdbgOpts(C.Structure):
 SYMBOLS = [
     "mhb_last_error", "mhb_version", "mhb_device_count", "mhb_count_record_words", "mhb_words_per_edge",
     "mhb_s2s_record_words", "mhb_count_sort_bytes", "mhb_s2s_sort_bytes", "mhb_sort_workspace_bytes",
-    "mhb_count_extract", "mhb_count_extract_range", "mhb_set_round_limit", "mhb_plan_rounds", "mhb_sort_records", "mhb_sort_pass_ms", "mhb_set_sort_cfg", "mhb_partition_scatter", "mhb_dev_malloc", "mhb_dev_free",
+    "mhb_count_extract", "mhb_count_extract_range", "mhb_set_round_limit", "mhb_set_s2s_round_limit", "mhb_plan_rounds", "mhb_plan_rounds16", "mhb_sort_records", "mhb_sort_pass_ms", "mhb_set_sort_cfg", "mhb_partition_scatter", "mhb_dev_malloc", "mhb_dev_free",
     "mhb_ipc_export", "mhb_ipc_open", "mhb_ipc_close", "mhb_count_solid_scratch_bytes", "mhb_count_solid", "mhb_tipset_bytes",
     "mhb_tipset_build", "mhb_count_mark_mercy", "mhb_count_tip_edges", "mhb_s2s_extract", "mhb_s2s_extract_range",
     "mhb_s2s_emit_scratch_bytes", "mhb_s2s_emit", "mhb_set_device", "mhb_count_host", "mhb_s2s_host", "mhb_build_host", "mhb_free",
-    "mhb_mercy_candidates_scratch_bytes", "mhb_mercy_candidates", "mhb_mercy_edges_scratch_bytes", "mhb_mercy_edges", "mhb_mercy_edges_segs", "mhb_edge_lut_bytes", "mhb_edge_lut_build",
+    "mhb_mercy_candidates_scratch_bytes", "mhb_mercy_candidates", "mhb_mercy_edges_scratch_bytes", "mhb_mercy_edges", "mhb_mercy_edges_count", "mhb_mercy_edges_write", "mhb_mercy_edges_segs", "mhb_mercy_host", "mhb_edge_lut_bytes", "mhb_edge_lut_build",
     "mhb_release", "mhb_count_run", "mhb_seq2sdbg_run", "mhb_selftest_count_record", "mhb_selftest_count_records_roll", "mhb_selftest_s2s_record",
 ]
 
@@ -211,11 +211,47 @@ def plan_rounds(hist256, max_records: int):
     return [(int(lo[i]), int(hi[i])) for i in range(n)]
 
 
+def plan_rounds16(hist256, sub_hist, max_records: int, cap: int = 65536):
+    """Two-level planner of the host rounds: list of (lo16, hi16) bucket-id ranges."""
+    L = load()
+    h = np.ascontiguousarray(hist256, dtype=np.uint64)
+    sub = None if sub_hist is None else np.ascontiguousarray(sub_hist, dtype=np.uint64).reshape(256, 256)
+    lo, hi = (C.c_uint32 * cap)(), (C.c_uint32 * cap)()
+    L.mhb_plan_rounds16.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
+    n = L.mhb_plan_rounds16(h.ctypes.data, sub.ctypes.data if sub is not None else None, int(max_records), lo, hi, cap)
+    if n < 0:
+        raise MhbError(L.mhb_last_error().decode())
+    return [(int(lo[i]), int(hi[i])) for i in range(n)]
+
+
 def set_round_limit(max_records: int = 0):
     """Cap the records per round of the out-of-core count stage (0 = derive from free device memory)."""
     L = load()
     L.mhb_set_round_limit.argtypes = [C.c_uint64]
     _check(L.mhb_set_round_limit(int(max_records)))
+
+
+def set_s2s_round_limit(max_items: int = 0):
+    """Cap the sort items per round of the out-of-core seq2sdbg stage (0 = derive from free device memory)."""
+    L = load()
+    L.mhb_set_s2s_round_limit.argtypes = [C.c_uint64]
+    _check(L.mhb_set_s2s_round_limit(int(max_items)))
+
+
+def mercy_host(k: int, edges: np.ndarray, cand_bin: np.ndarray) -> np.ndarray:
+    """GenMercyEdges on the device from host buffers: sorted `.edges` records + the `.cand` image -> mercy edge records."""
+    L = load()
+    we = words_per_edge(k)
+    edges = np.ascontiguousarray(edges, np.uint32).reshape(-1, we)
+    cand = np.ascontiguousarray(cand_bin, np.uint32).reshape(-1)
+    out, nm, nr = C.POINTER(C.c_uint32)(), C.c_uint64(), C.c_uint64()
+    L.mhb_mercy_host.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.POINTER(C.c_uint32)),
+                                 C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    _check(L.mhb_mercy_host(k, edges.ctypes.data if len(edges) else None, len(edges), cand.ctypes.data if len(cand) else None,
+                            len(cand), C.byref(out), C.byref(nm), C.byref(nr)))
+    res = np.ctypeslib.as_array(out, (max(nm.value, 1) * we,))[: nm.value * we].reshape(-1, we).copy()
+    L.mhb_free(out)
+    return res
 
 
 def sort_pass_ms(back: int = 0):

@@ -220,7 +220,23 @@ def gen_kmax():
         GOLD = keep
 
 
-CASES = {"kmax": gen_kmax, "chain": gen_chain, "toy": gen_toy, "syn150": gen_syn150, "synvar": gen_synvar, "degenerate": gen_degenerate}
+def gen_lowcov():
+    """Reads that overlap only at their ends (coverage 1, 2 inside the 30-base overlaps): with m = 2 only the overlap
+    (k+1)-mers are solid, every read has a "no out" tip at its left overlap and a "no in" tip at its right one, so almost
+    every (k+1)-mer of every read comes back as a mercy edge - far more mercy edges than solid ones, and more than
+    n/m + 1 - n_solid (the capacity the fused build used to give them: ADVICE r1)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        rng = np.random.default_rng(21)
+        L, ov, n = 150, 30, 400
+        g = rng.integers(0, 4, (L - ov) * n + ov, dtype=np.uint8)
+        reads = np.stack([g[i * (L - ov): i * (L - ov) + L] for i in range(n)])
+        flip = rng.random(n) < 0.5  # random strand
+        reads[flip] = (3 - reads[flip])[:, ::-1]
+        F.write_lib(f"{tmp}/l", F.pack_reads_fixed(reads), n, n * L, L)
+        make_case("lowcov_k21", f"{tmp}/l", [21], 2)
+
+
+CASES = {"lowcov": gen_lowcov, "kmax": gen_kmax, "chain": gen_chain, "toy": gen_toy, "syn150": gen_syn150, "synvar": gen_synvar, "degenerate": gen_degenerate}
 
 if __name__ == "__main__":
     if not os.path.exists(REF):

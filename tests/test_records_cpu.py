@@ -184,3 +184,43 @@ def test_rolling_count_record_builder_matches(k):
                     if wr == 3:
                         ev |= int(e[2])  # 3-word record: key in words 0-1, prev/next in word 2
                     assert ev == int(rec[j]) and es == int(strand[j]), (k, L, q, j)
+
+
+def test_plan_rounds16_cuts_an_oversized_leading_byte_on_bucket_ids():
+    """A13 planner used by the host rounds: a leading byte above the cap (A-prefix skew, poly-A) is cut on its second
+    byte = on the reference's 16-bit bucket ids (base_engine.cpp:254-281), everything else on whole leading bytes"""
+    rng = np.random.default_rng(5)
+    hist = rng.integers(0, 1000, 256).astype(np.uint64)
+    sub = np.zeros((256, 256), np.uint64)
+    for b in (0, 17):  # two hot bytes
+        sub[b] = rng.integers(0, 400, 256).astype(np.uint64)
+        hist[b] = sub[b].sum()
+    cap = 3000
+    assert hist[0] > cap and hist[17] > cap
+    ranges = lib.plan_rounds16(hist, sub, cap)
+    # tiling of the bucket ids, ascending, every range within the cap
+    assert ranges[0][0] == 0 and ranges[-1][1] == 65535
+    per_bucket = np.zeros(65536, np.uint64)
+    for b in range(256):
+        if hist[b] > cap:
+            per_bucket[b * 256:(b + 1) * 256] = sub[b]
+        else:
+            per_bucket[b * 256] = hist[b]  # unit = the whole byte: a cut may only fall on a byte boundary
+    for (lo, hi), nxt in zip(ranges, ranges[1:] + [None]):
+        assert lo <= hi and int(per_bucket[lo:hi + 1].sum()) <= cap
+        if nxt is not None:
+            assert nxt[0] == hi + 1
+            assert (nxt[0] & 255) == 0 or hist[nxt[0] >> 8] > cap
+    # without oversized bytes it degenerates to the byte planner
+    h2 = np.full(256, 10, np.uint64)
+    assert lib.plan_rounds16(h2, None, 25) == [(lo << 8, (hi << 8) | 255) for lo, hi in lib.plan_rounds(h2, 25)]
+    assert lib.plan_rounds16(np.zeros(256, np.uint64), None, 1) == [(0, 65535)]
+    # a single bucket above the cap is reported, and an oversized byte without its second-level histogram too
+    sub2 = np.zeros((256, 256), np.uint64)
+    sub2[3, 9] = 50
+    h3 = np.zeros(256, np.uint64)
+    h3[3] = 50
+    with pytest.raises(lib.MhbError, match="bucket 0x0309"):
+        lib.plan_rounds16(h3, sub2, 10)
+    with pytest.raises(lib.MhbError, match="leading byte 0x03"):
+        lib.plan_rounds16(h3, None, 10)
