@@ -207,12 +207,14 @@ def ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
+    launches0 = lib.launch_count()
     for _ in range(args.steps):
         step(timed=True)
         # per-pass device times of this step's two sorts (events recorded inside the timed region)
         sort_ms["s2s"].append(lib.sort_pass_ms(0)[0])
         sort_ms["count"].append(lib.sort_pass_ms(1)[0])
     e1.record()
+    launches = (lib.launch_count() - launches0) // max(1, args.steps)  # counted by libmhb at every launch site
     torch.cuda.synchronize()
     clk = clocks.stop()
     ms_per_step = e0.elapsed_time(e1) / args.steps
@@ -267,10 +269,6 @@ def ours(args):
                 stage_roofline[nm] = {"algorithmic_bytes": int(b), "gbs": gbs, "frac": gbs / peak}
     except Exception as e:  # pragma: no cover
         stage_roofline = {"error": str(e)}
-
-    # kernels launched per step (ours only): extract, 7x(scan256+radix), mark/totals/scan/emit, tips/tipset/mercy,
-    # s2s extract, 10x(scan256+radix), size, 4 scans, write, finalize
-    launches = 1 + 2 * len(plan.sort_bytes) + 4 + 3 + 1 + 2 * len(s2s.sort_bytes) + 1 + 4 + 1 + 1
 
     # ---- e2e: host buffers through the C ABI (fused build), H2D/D2H copies inside the timed region ----
     host_bin = torch.empty(bin_words, dtype=torch.int32).pin_memory()

@@ -47,6 +47,8 @@ const char *mhb_last_error(void);
 const char *mhb_version(void);
 /* number of visible CUDA devices (0 when none); never fails */
 int mhb_device_count(void);
+/* kernels launched by this process through libmhb so far (counted at every launch site; bench.py's gpu_launches) */
+uint64_t mhb_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Geometry helpers (pure host arithmetic, callable without a GPU)
@@ -118,6 +120,16 @@ int mhb_sort_records(void *stream, uint32_t *a, uint32_t *b, uint64_t n, uint32_
  * kernel and no separate all-to-all is needed.  ws as for mhb_sort_records. */
 int mhb_partition_scatter(void *stream, const uint32_t *recs, uint64_t n, uint32_t words, int byte,
                           const uint8_t *owner_of_byte_dev, const uint64_t *bin_addr_dev, void *ws, size_t ws_bytes);
+/* The bucket-range plan of one stage of the multi-GPU build, computed on the device from the all-gathered top-byte
+ * histograms hist_all_dev[world][256] (so that nothing but a few counters has to visit the host between the histogram
+ * exchange and the partition pass): rank r owns the leading-byte values [bounds[r], bounds[r+1]), cut where the
+ * cumulative record count is closest to r/world of the total (canonical (k+1)-mers are A-skewed: equal-width ranges
+ * would not balance).  Outputs, all device memory: owner_lut_dev[256] (leading byte -> owning rank),
+ * bin_addr_dev[256] (entry o < world: byte address, inside owner o's receive buffer peer_base_host[o], where THIS
+ * rank's block starts; for mhb_partition_scatter), plan_dev[64] = {[0..15] records owner o receives in total,
+ * [16..31] records this rank sends to owner o, [32..32+world] bounds}.  world <= 16. */
+int mhb_plan_partition(void *stream, const uint64_t *hist_all_dev, uint32_t world, uint32_t rank, uint32_t record_bytes,
+                       const uint64_t *peer_base_host, uint8_t *owner_lut_dev, uint64_t *bin_addr_dev, uint64_t *plan_dev);
 /* cudaMalloc'ed buffers that can be shared between the per-GPU processes of one node (CUDA IPC) */
 int mhb_dev_malloc(void **ptr, size_t bytes);
 int mhb_dev_free(void *ptr);
@@ -184,7 +196,22 @@ int mhb_mercy_edges_write(void *stream, const mhb_dev_reads *reads, const uint64
                           uint32_t max_read_len, uint32_t k, uint32_t *mercy_out, uint64_t capacity, uint64_t n_mercy,
                           void *scratch, size_t scratch_bytes);
 
-/* Same, with the sorted solid edges given as n_segs (<= 16) segments: segment owner_of_byte[b] holds every edge whose
+/* Multi-GPU form of the search (one process per GPU, each owning a contiguous range of leading bytes): every binary
+ * search GenMercyEdges issues targets exactly one owner, and has_in / has_out are ORs over search outcomes, so each
+ * rank answers - for the candidate reads of ALL ranks - the searches that land in its own range from local memory:
+ * mhb_mercy_probe_owned writes 5 answer planes per read (mhb_mercy_planes_words() u32 words for n_cand reads;
+ * cand_ids may be NULL = reads 0..n_cand-1), the ranks exchange planes, and mhb_mercy_count_planes ORs the n_src
+ * planes of this rank's own candidates (source s at planes + s*src_stride_words), leaving scratch ready for
+ * mhb_mercy_edges_write exactly as mhb_mercy_edges_count does. */
+size_t mhb_mercy_planes_words(uint64_t n_cand, uint32_t max_read_len);
+int mhb_mercy_probe_owned(void *stream, const mhb_dev_reads *reads, const uint64_t *cand_ids, uint64_t n_cand,
+                          uint32_t max_read_len, uint32_t k, const uint32_t *edges, uint64_t n_edges, const void *lut,
+                          const uint8_t *owner_of_byte, uint32_t me, uint32_t *planes_out);
+int mhb_mercy_count_planes(void *stream, const mhb_dev_reads *reads, const uint64_t *cand_ids, uint64_t n_cand,
+                           uint32_t max_read_len, uint32_t k, const uint32_t *planes, uint32_t n_src,
+                           uint64_t src_stride_words, uint64_t *n_mercy_host, void *scratch, size_t scratch_bytes);
+
+/* Same as mhb_mercy_edges, with the sorted solid edges given as n_segs (<= 16) segments: segment owner_of_byte[b] holds every edge whose
  * leading byte is b (host arrays; the segment pointers are device pointers and may be CUDA IPC peer pointers into
  * other GPUs' memory, so a multi-GPU build needs no gather of the edges). */
 int mhb_mercy_edges_segs(void *stream, const mhb_dev_reads *reads, const uint64_t *cand_ids, uint64_t n_cand,

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kExtractThreads)
 // complement strings one base on (make_count_records_roll): ~55 instead of ~120 thread-instructions per record.
 // A 150 bp read at k=27 (123 edges) is one warp step.  Same output as k_count_extract<2, 2>.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kExtractThreads)
+static __global__ void __launch_bounds__(kExtractThreads)
     k_count_extract_roll(ReadsView rv, u32 k, u32 *__restrict__ records, u64 *hist, int hist_byte) {
   __shared__ u32 s_hist[256];
   for (int i = threadIdx.x; i < 256; i += kExtractThreads) s_hist[i] = 0;
@@ -202,8 +202,7 @@ __global__ void __launch_bounds__(kExtractThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K-count (A5/A6; kmer_counter.cpp:254-381).  v1: one thread per run head walks its run.
-// info[i] = 0 for non-heads, else 1 | solid<<1 | no_in<<2 | no_out<<3 | min(count,65535)<<8
+// K-count helpers (A5/A6; kmer_counter.cpp:254-381)
 // ------------------------------------------------------------------------------------------------
 template <int WR>
 __device__ __forceinline__ bool same_edge(const u32 (&a)[WR], const u32 (&b)[WR]) {
@@ -218,76 +217,8 @@ __device__ __forceinline__ bool same_edge(const u32 (&a)[WR], const u32 (&b)[WR]
 
 static constexpr int kMulHistSmem = 1024;
 
-template <int WR>
-__global__ void __launch_bounds__(256)
-    k_count_mark(const u32 *__restrict__ recs, u64 n, int m, u32 *__restrict__ info, u64 *mul_hist) {
-  __shared__ u32 s_hist[kMulHistSmem];
-  for (int i = threadIdx.x; i < kMulHistSmem; i += 256) s_hist[i] = 0;
-  __syncthreads();
-  const u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
-  if (i < n) {
-    u32 r[WR], p[WR];
-    ld_rec<WR>(recs, i, r);
-    bool head = true;
-    if (i > 0) {
-      ld_rec<WR>(recs, i - 1, p);
-      head = !same_edge<WR>(r, p);
-    }
-    u32 word = 0;
-    if (head) {
-      u32 count = 0, cp[5] = {0, 0, 0, 0, 0}, cn[5] = {0, 0, 0, 0, 0};
-      u32 x[WR];
-#pragma unroll
-      for (int j = 0; j < WR; ++j) x[j] = r[j];
-      u64 j = i;
-      while (true) {
-        const u32 pn = x[WR - 1] & 63u;  // kmer_counter.cpp:288-295
-        count += count < 0x40000000u ? 1u : 0u;
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-          cp[c] += ((pn >> 3) == (u32)c && cp[c] < 0x40000000u) ? 1u : 0u;
-          cn[c] += ((pn & 7u) == (u32)c && cn[c] < 0x40000000u) ? 1u : 0u;
-        }
-        if (++j >= n) break;
-        ld_rec<WR>(recs, j, x);
-        if (!same_edge<WR>(x, r)) break;
-      }
-      bool has_in = false, has_out = false;  // :297-305
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        has_in = has_in || (long long)cp[c] >= (long long)m;
-        has_out = has_out || (long long)cn[c] >= (long long)m;
-      }
-      const bool solid = (long long)count >= (long long)m;
-      const u32 c16 = count > 65535u ? 65535u : count;
-      word = 1u | (solid ? 2u : 0u) | (has_in ? 0u : 4u) | (has_out ? 0u : 8u) | (c16 << 8);
-      if (c16 < (u32)kMulHistSmem) atomicAdd(&s_hist[c16], 1u);  // edge_counter.h:30-33
-      else atomicAdd((unsigned long long *)&mul_hist[c16], 1ull);
-    }
-    info[i] = word;
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < kMulHistSmem; c += 256)
-    if (s_hist[c]) atomicAdd((unsigned long long *)&mul_hist[c], (unsigned long long)s_hist[c]);
-}
-
-// ordered compaction helpers: per-block totals, single-block scan of the totals, apply
-static constexpr int kCompactThreads = 256, kCompactItems = 8, kCompactTile = kCompactThreads * kCompactItems;
-
-__global__ void __launch_bounds__(kCompactThreads) k_solid_block_totals(const u32 *info, u64 n, u64 *btot) {
-  __shared__ u32 s_scan[kCompactThreads / 32 + 1];
-  const u64 base = (u64)blockIdx.x * kCompactTile + (u64)threadIdx.x * kCompactItems;
-  u32 c = 0;
-#pragma unroll
-  for (int j = 0; j < kCompactItems; ++j)
-    if (base + j < n) c += (info[base + j] >> 1) & 1u;
-  u32 total;
-  block_excl_scan<kCompactThreads>(c, s_scan, total);
-  if (threadIdx.x == 0) btot[blockIdx.x] = total;
-}
-
 // in-place exclusive scan of nb u64 values by ONE block; writes the grand total
-__global__ void __launch_bounds__(1024) k_scan_u64(u64 *v, u64 nb, u64 *total_out) {
+static __global__ void __launch_bounds__(1024) k_scan_u64(u64 *v, u64 nb, u64 *total_out) {
   __shared__ u64 s_w[33];
   __shared__ u64 s_carry;
   if (threadIdx.x == 0) s_carry = 0;
@@ -323,42 +254,6 @@ __global__ void __launch_bounds__(1024) k_scan_u64(u64 *v, u64 nb, u64 *total_ou
   if (threadIdx.x == 0 && total_out) *total_out = s_carry;
 }
 
-// PackEdge (kmer_counter.cpp:32-52) for every solid run head, in sorted order
-template <int WR>
-__global__ void __launch_bounds__(kCompactThreads)
-    k_count_emit(const u32 *__restrict__ recs, const u32 *__restrict__ info, u64 n, u32 k, const u64 *btot,
-                 u32 *__restrict__ edges, uint8_t *__restrict__ aux, u64 capacity) {
-  __shared__ u32 s_scan[kCompactThreads / 32 + 1];
-  const u64 base = (u64)blockIdx.x * kCompactTile + (u64)threadIdx.x * kCompactItems;
-  u32 w[kCompactItems];
-  u32 c = 0;
-#pragma unroll
-  for (int j = 0; j < kCompactItems; ++j) {
-    w[j] = base + j < n ? info[base + j] : 0u;
-    c += (w[j] >> 1) & 1u;
-  }
-  u32 total;
-  const u32 excl = block_excl_scan<kCompactThreads>(c, s_scan, total);
-  if (c == 0) return;
-  u64 pos = btot[blockIdx.x] + excl;
-  const u32 W = count_key_words(k), WE = words_per_edge(k);
-#pragma unroll
-  for (int j = 0; j < kCompactItems; ++j) {
-    if ((w[j] >> 1) & 1u) {
-      if (pos < capacity) {
-        u32 r[WR];
-        ld_rec<WR>(recs, base + j, r);
-        r[WR - 1] &= ~63u;  // drop prev/next; what is left of the key words has zero tail bits
-        u32 *e = edges + pos * WE;
-        for (u32 x = 0; x < WE; ++x) e[x] = (x < W && x < (u32)WR) ? pick<WR>(r, x) : 0u;
-        e[WE - 1] |= w[j] >> 8;  // min(count, kMaxMul)
-        aux[pos] = (uint8_t)((w[j] >> 2) & 3u);
-      }
-      ++pos;
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // tip set: the solid edges that lack an incoming or outgoing solid neighbour (aux != 0), as
 //   u64 capacity (power of two), u64 filter_words (power of two),
@@ -392,7 +287,7 @@ __device__ __forceinline__ u32 hash2(u32 h) {  // second, independent-ish hash f
   return h ^ (h >> 16);
 }
 
-__global__ void k_count_tips(const uint8_t *aux, u64 n, unsigned long long *out) {
+static __global__ void k_count_tips(const uint8_t *aux, u64 n, unsigned long long *out) {
   u64 c = 0;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
     c += aux[i] != 0;
@@ -515,7 +410,7 @@ __global__ void __launch_bounds__(256)
 
 // Rolling variant of k_mark_mercy for 8-byte records (opt-in with MHB_EXTRACT_ROLL=1): a lane re-derives four
 // consecutive canonical (k+1)-mers with make_count_records_roll and probes the filter for all four at once.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
     k_mark_mercy_roll(ReadsView rv, u32 k, const u32 *__restrict__ filter, u64 filter_words, const u32 *__restrict__ table,
                       u64 cap, u32 *first_0_out, u32 *last_0_in) {
   constexpr int W = 2;
@@ -585,197 +480,6 @@ __global__ void __launch_bounds__(256)
       last_0_in[r] = last < 0 ? 0xFFFFFFFFu : (u32)last;
     }
   }
-}
-
-}  // namespace mhb
-
-namespace mhb {
-
-// ------------------------------------------------------------------------------------------------
-// K-count v2 (A5/A6): one pass, warp-cooperative.
-//
-// The sorted records are cut into chunks of CH records; warps claim chunks by ticket.  A warp OWNS every
-// run of equal edges whose first record lies in its chunk and follows such a run past the chunk end, so
-// no partial results cross warps.  Per 32-record slot the run structure comes from one ballot of the
-// head flags, and a run's multiplicity and its prev/next tallies (kmer_counter.cpp:279-305) are
-// popcounts of ballot masks restricted to the run's lanes - no per-record loop.  A run is finished (and
-// judged: solid / has_in / has_out) by the lane holding the NEXT run's head; a virtual head at index n
-// closes the last run.  Solid edges are packed (PackEdge, kmer_counter.cpp:32-52) into a per-warp
-// staging area in order; the warp then learns its global output offset by decoupled look-back over the
-// chunk totals and copies the staging area out with coalesced stores, so the edge list stays sorted.
-// ------------------------------------------------------------------------------------------------
-static constexpr int kCountWarps = 8;
-__host__ __device__ constexpr int count_chunk(int we) { return we <= 4 ? 256 : (we <= 8 ? 128 : 64); }
-
-template <int WR>
-__global__ void __launch_bounds__(kCountWarps * 32)
-    k_count_warp(const u32 *__restrict__ recs, u64 n, u32 k, int m, u32 n_chunks, u32 *ticket, u64 *lookback,
-                 u32 *__restrict__ edges, uint8_t *__restrict__ aux, u64 capacity, u64 *mul_hist, u64 *n_solid_out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ u32 s_hist[kMulHistSmem];
-  const u32 W = count_key_words(k), WE = words_per_edge(k);
-  const int CH = count_chunk((int)WE);
-  const u32 lane = lane_id(), warp = threadIdx.x >> 5;
-  u32 *stage = reinterpret_cast<u32 *>(smem_raw) + (size_t)warp * CH * WE;
-  uint8_t *stage_aux = smem_raw + (size_t)kCountWarps * CH * WE * 4 + (size_t)warp * CH;
-  for (int i = threadIdx.x; i < kMulHistSmem; i += kCountWarps * 32) s_hist[i] = 0;
-  __syncthreads();
-  const u32 lt = lanemask_lt();
-  u32 n_ones = 0;  // runs of multiplicity 1 seen by this warp (lane 0 only)
-
-  while (true) {
-    u32 chunk = 0;
-    if (lane == 0) chunk = atomicAdd(ticket, 1u);
-    chunk = __shfl_sync(0xffffffffu, chunk, 0);
-    if (chunk >= n_chunks) break;
-    const u64 a = (u64)chunk * CH;
-    const u64 b = a + CH < n ? a + CH : n;
-
-    bool open = false;
-    u32 c_cnt = 0, c_p[4] = {0, 0, 0, 0}, c_n[4] = {0, 0, 0, 0};
-    u32 prev_rec[WR];
-    if (a > 0) ld_rec<WR>(recs, a - 1, prev_rec);
-    else {
-#pragma unroll
-      for (int j = 0; j < WR; ++j) prev_rec[j] = 0;
-    }
-    u32 n_staged = 0;
-
-    for (u64 pos0 = a;; pos0 += 32) {
-      const u64 i = pos0 + lane;
-      const bool valid = i < n;
-      u32 rec[WR], pr[WR];
-      if (valid) ld_rec<WR>(recs, i, rec);
-      else {
-#pragma unroll
-        for (int j = 0; j < WR; ++j) rec[j] = 0;
-      }
-#pragma unroll
-      for (int j = 0; j < WR; ++j) {
-        pr[j] = __shfl_up_sync(0xffffffffu, rec[j], 1);
-        if (lane == 0) pr[j] = prev_rec[j];
-      }
-      const bool is_head = (i == n) || (valid && (i == 0 || !same_edge<WR>(rec, pr)));
-      const u32 heads = __ballot_sync(0xffffffffu, is_head);
-      const u32 vmask = __ballot_sync(0xffffffffu, valid);
-      const u32 pn = rec[WR - 1] & 63u;
-      u32 mp[4], mn[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        mp[c] = __ballot_sync(0xffffffffu, valid && (pn >> 3) == (u32)c);
-        mn[c] = __ballot_sync(0xffffffffu, valid && (pn & 7u) == (u32)c);
-      }
-
-      // ---- lanes holding a head finish the run that ends just before them ----
-      bool emit = false, solid = false;
-      u32 count = 0, flags = 0;
-      if (is_head) {
-        const u32 below = heads & lt;
-        const bool has_h = below != 0;
-        const u32 hl = has_h ? 31u - __clz(below) : 0u;
-        const u32 seg = lt & ~((1u << hl) - 1u);  // lanes [hl, lane) -- hl = 0 when the run started earlier
-        const bool owned = has_h ? (pos0 + hl < b) : open;
-        if (owned) {
-          count = __popc(seg & vmask) + (has_h ? 0u : c_cnt);
-          bool has_in = false, has_out = false;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const u32 tp = __popc(seg & mp[c]) + (has_h ? 0u : c_p[c]);
-            const u32 tn = __popc(seg & mn[c]) + (has_h ? 0u : c_n[c]);
-            has_in = has_in || (long long)tp >= (long long)m;
-            has_out = has_out || (long long)tn >= (long long)m;
-          }
-          emit = count > 0;
-          solid = emit && (long long)count >= (long long)m;
-          flags = (has_in ? 0u : 1u) | (has_out ? 0u : 2u);
-        }
-      }
-      const u32 emit_mask = __ballot_sync(0xffffffffu, emit);
-      if (emit_mask) {
-        const u32 c16 = count > 65535u ? 65535u : count;
-        const u32 ones = __ballot_sync(0xffffffffu, emit && c16 == 1u);
-        n_ones += __popc(ones);
-        if (emit && c16 != 1u) {
-          if (c16 < (u32)kMulHistSmem) atomicAdd(&s_hist[c16], 1u);
-          else atomicAdd((unsigned long long *)&mul_hist[c16], 1ull);
-        }
-        const u32 solid_mask = __ballot_sync(0xffffffffu, solid);
-        if (solid) {
-          const u32 at = n_staged + __popc(solid_mask & lt);
-          u32 key[WR];
-#pragma unroll
-          for (int j = 0; j < WR; ++j) key[j] = pr[j];
-          key[WR - 1] &= ~63u;
-          u32 *e = stage + (size_t)at * WE;
-          for (u32 x = 0; x < WE; ++x) e[x] = (x < W && x < (u32)WR) ? pick<WR>(key, x) : 0u;
-          e[WE - 1] |= c16;
-          stage_aux[at] = (uint8_t)flags;
-        }
-        n_staged += __popc(solid_mask);
-      }
-
-      // ---- carry the run that is still open at the end of this slot ----
-      if (heads) {
-        const u32 H = 31u - __clz(heads);
-        const u32 tail = ~((1u << H) - 1u);
-        if (pos0 + H < n) {
-          open = pos0 + H < b;
-          c_cnt = __popc(vmask & tail);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            c_p[c] = __popc(mp[c] & tail);
-            c_n[c] = __popc(mn[c] & tail);
-          }
-        } else {
-          open = false;
-        }
-      } else if (open) {
-        c_cnt = min(c_cnt + (u32)__popc(vmask), 0x40000000u);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          c_p[c] = min(c_p[c] + (u32)__popc(mp[c]), 0x40000000u);
-          c_n[c] = min(c_n[c] + (u32)__popc(mn[c]), 0x40000000u);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < WR; ++j) prev_rec[j] = __shfl_sync(0xffffffffu, rec[j], 31);
-      const u64 next = pos0 + 32;
-      if (next > n || (next >= b && !open)) break;
-    }
-
-    // ---- global offset of this chunk's solid edges: decoupled look-back over chunk totals ----
-    u64 offset = 0;
-    if (lane == 0) {
-      u64 *my = lookback + chunk;
-      if (chunk == 0) {
-        st_relaxed(my, kLbInclusive | (u64)n_staged);
-      } else {
-        st_relaxed(my, kLbPartial | (u64)n_staged);
-        for (u32 p = chunk; p-- > 0;) {
-          u64 v;
-          do {
-            v = ld_relaxed(lookback + p);
-          } while ((v & kLbStatusMask) == 0);
-          offset += v & kLbValueMask;
-          if ((v & kLbStatusMask) == kLbInclusive) break;
-        }
-        st_relaxed(my, kLbInclusive | (offset + n_staged));
-      }
-      if (chunk == n_chunks - 1) *n_solid_out = offset + n_staged;
-    }
-    offset = __shfl_sync(0xffffffffu, offset, 0);
-    __syncwarp();
-    const u64 room = offset < capacity ? capacity - offset : 0;
-    const u32 n_out = (u64)n_staged < room ? n_staged : (u32)room;
-    for (u32 x = lane; x < n_out * WE; x += 32) edges[offset * WE + x] = stage[x];
-    for (u32 x = lane; x < n_out; x += 32) aux[offset + x] = stage_aux[x];
-    __syncwarp();
-  }
-
-  if (lane == 0 && n_ones) atomicAdd(&s_hist[1], n_ones);
-  __syncthreads();
-  for (int c = threadIdx.x; c < kMulHistSmem; c += kCountWarps * 32)
-    if (s_hist[c]) atomicAdd((unsigned long long *)&mul_hist[c], (unsigned long long)s_hist[c]);
 }
 
 }  // namespace mhb
@@ -1052,7 +756,7 @@ __global__ void __launch_bounds__(kCount3Warps * 32)
 // ---- three-phase exclusive scan of u32 counts into u64 offsets (4096 entries per block) ----
 static constexpr int kScanThreads = 1024, kScanItems = 4, kScanTile = kScanThreads * kScanItems;
 
-__global__ void __launch_bounds__(kScanThreads) k_scan32_sums(const u32 *in, u64 n, u64 *bsum) {
+static __global__ void __launch_bounds__(kScanThreads) k_scan32_sums(const u32 *in, u64 n, u64 *bsum) {
   __shared__ u32 s_scan[kScanThreads / 32 + 1];
   const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
   u32 c = 0;
@@ -1064,7 +768,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan32_sums(const u32 *in, u64
   if (threadIdx.x == 0) bsum[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan32_apply(const u32 *in, u64 n, const u64 *bsum, u64 *out) {
+static __global__ void __launch_bounds__(kScanThreads) k_scan32_apply(const u32 *in, u64 n, const u64 *bsum, u64 *out) {
   __shared__ u32 s_scan[kScanThreads / 32 + 1];
   const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
   u32 v[kScanItems], c = 0;
@@ -1083,7 +787,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan32_apply(const u32 *in, u6
 }
 
 // same three phases for u64 values, in place (exclusive)
-__global__ void __launch_bounds__(kScanThreads) k_scan64_sums(const u64 *in, u64 n, u64 *bsum) {
+static __global__ void __launch_bounds__(kScanThreads) k_scan64_sums(const u64 *in, u64 n, u64 *bsum) {
   __shared__ u64 s_w[33];
   const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
   u64 c = 0;
@@ -1100,7 +804,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan64_sums(const u64 *in, u64
   }
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan64_apply(u64 *v, u64 n, const u64 *bsum) {
+static __global__ void __launch_bounds__(kScanThreads) k_scan64_apply(u64 *v, u64 n, const u64 *bsum) {
   __shared__ u64 s_w[33];
   const u32 lane = lane_id(), warp = threadIdx.x >> 5;
   const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;

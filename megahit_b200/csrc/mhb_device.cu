@@ -11,8 +11,7 @@
 #include "mhb_internal.h"
 #include "mhb_mercy.cuh"
 #include "mhb_s2s.cuh"
-#include "mhb_sort.cuh"
-#include "mhb_sort3.cuh"
+#include "mhb_common.cuh"
 
 using namespace mhb;
 
@@ -38,15 +37,9 @@ extern "C" int mhb_device_count(void) {
   return n;
 }
 extern "C" void mhb_free(void *p) { free(p); }
+unsigned long long g_mhb_launches = 0;
+extern "C" uint64_t mhb_launch_count(void) { return g_mhb_launches; }
 
-#define CK(call)                                                                                   \
-  do {                                                                                             \
-    cudaError_t e_ = (call);                                                                       \
-    if (e_ != cudaSuccess)                                                                         \
-      return mhb_set_error(MHB_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,      \
-                           cudaGetErrorString(e_));                                                \
-  } while (0)
-#define CK_LAUNCH() CK(cudaGetLastError())
 
 // ------------------------------------------------------------------------------------------------
 // geometry
@@ -80,12 +73,10 @@ extern "C" uint32_t mhb_s2s_sort_bytes(uint32_t k, uint8_t *bytes) {
 // ------------------------------------------------------------------------------------------------
 // dispatch helpers
 // ------------------------------------------------------------------------------------------------
-#define MHB_FOR_W(M) M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12) M(13) M(14) M(15) M(16)
-#define MHB_FOR_WR(M) MHB_FOR_W(M) M(17)
 
 static int g_sm_count = 0;
 static int g_bound_device = -1;
-static int sm_count() {
+int mhb_sm_count() {
   if (!g_sm_count) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -96,7 +87,7 @@ static int sm_count() {
   return g_sm_count;
 }
 
-static ReadsView make_reads_view(const mhb_dev_reads *r) {
+ReadsView make_reads_view(const mhb_dev_reads *r) {
   ReadsView v;
   v.bin = r->bin;
   v.bin_words = r->bin_words;
@@ -108,7 +99,7 @@ static ReadsView make_reads_view(const mhb_dev_reads *r) {
   return v;
 }
 
-static int check_reads(const mhb_dev_reads *r, uint32_t k) {
+int check_reads(const mhb_dev_reads *r, uint32_t k) {
   if (!r || k < 1 || k > MHB_MAX_K) return mhb_set_error(MHB_ERR_ARG, "bad reads/k (k=%u)", k);
   if (r->n_reads && !r->bin) return mhb_set_error(MHB_ERR_ARG, "reads->bin is NULL");
   if (((uintptr_t)r->bin & 15) != 0) return mhb_set_error(MHB_ERR_ARG, "reads->bin must be 16-byte aligned");
@@ -211,352 +202,6 @@ extern "C" int mhb_count_extract_range(void *stream, const mhb_dev_reads *reads,
 }
 
 // ------------------------------------------------------------------------------------------------
-// sort
-// ------------------------------------------------------------------------------------------------
-// Radix-pass variants.  0..3 = v2 geometries (mhb_sort.cuh); 256 + bits = v3 (mhb_sort3.cuh, see SortCfg3 for the
-// bit field).  Only the listed v3 combinations are instantiated (all for 8- and 12-byte records, the first one for
-// every record width).
-#define MHB_V3_DEFAULT 0x080
-#define MHB_V3_LIST(X)                                                                                               \
-  X(0x080) X(0x000) X(0x009) X(0x082) X(0x180) X(0x480) X(0x084) X(0x1080) X(0x0888) X(0x8080) X(0x10080) X(0x18080)  \
-  X(0x9080) X(0x8082) X(0x10082)
-static bool v3_listed(int bits) {
-#define X(B) \
-  if (bits == B) return true;
-  MHB_V3_LIST(X)
-#undef X
-  return false;
-}
-static int g_sort_cfg = -1;
-extern "C" int mhb_set_sort_cfg(int cfg) {
-  if (!((cfg >= 0 && cfg <= 3) || (cfg >= 256 && v3_listed(cfg - 256))))
-    return mhb_set_error(MHB_ERR_ARG, "unknown sort configuration %d", cfg);
-  g_sort_cfg = cfg;
-  return MHB_OK;
-}
-static int sort_cfg() {
-  int &cfg = g_sort_cfg;
-  if (cfg < 0) {
-    const char *e = getenv("MHB_SORT_CFG");
-    cfg = e ? atoi(e) : 256 + MHB_V3_DEFAULT;
-    if (!((cfg >= 0 && cfg <= 3) || (cfg >= 256 && v3_listed(cfg - 256)))) cfg = 256 + MHB_V3_DEFAULT;
-  }
-  return cfg;
-}
-template <int WR, int CFG>
-static u64 sort_tiles_cfg(u64 n) {
-  return (n + SortCfg<WR, CFG>::TILE - 1) / SortCfg<WR, CFG>::TILE;
-}
-template <int WR, int CFG>
-static u64 sort_tiles_cfg3(u64 n) {
-  return (n + SortCfg3<WR, CFG>::TILE - 1) / SortCfg3<WR, CFG>::TILE;
-}
-template <int WR>
-static u64 sort_tiles(u64 n) {
-  const int cfg = sort_cfg();
-  if (cfg >= 256) {
-    if constexpr (WR == 2 || WR == 3) {
-#define X(B) \
-  if (cfg - 256 == B) return sort_tiles_cfg3<WR, B>(n);
-      MHB_V3_LIST(X)
-#undef X
-    }
-    return sort_tiles_cfg3<WR, MHB_V3_DEFAULT>(n);
-  }
-  if constexpr (WR <= 3) {
-    switch (cfg) {
-      case 1: return sort_tiles_cfg<WR, 1>(n);
-      case 2: return sort_tiles_cfg<WR, 2>(n);
-      case 3: return sort_tiles_cfg<WR, 3>(n);
-      default: break;
-    }
-  }
-  return sort_tiles_cfg<WR, 0>(n);
-}
-static u64 sort_num_tiles(u64 n, u32 words) {
-#define M(WW) \
-  if (words == WW) return sort_tiles<WW>(n);
-  MHB_FOR_WR(M)
-#undef M
-  return 0;
-}
-static constexpr size_t kSortHeadBytes = (size_t)(72 + 1) * 256 * 8 /*hist*/ + 256 * 8 /*bin_base*/ + 128 * 4;
-// look-back storage for `tiles` tiles: 256 64-bit descriptors per tile + (compact-descriptor variants) one 16-byte
-// word per digit and group of four tiles behind them
-static size_t lb_bytes(u64 tiles) { return (size_t)tiles * 256 * 8 + (size_t)((tiles + 3) / 4) * 256 * 16; }
-
-extern "C" size_t mhb_sort_workspace_bytes(uint64_t n, uint32_t words) {
-  // sized for the smallest tile of any configuration so that a workspace stays valid across MHB_SORT_CFG values
-  u64 tiles = sort_num_tiles(n, words);
-  if (words <= 3) tiles = (n + 256 * 8 - 1) / (256 * 8) > tiles ? (n + 256 * 8 - 1) / (256 * 8) : tiles;
-#define M(WW) \
-  if (words == WW && sort_tiles_cfg<WW, 0>(n) > tiles) tiles = sort_tiles_cfg<WW, 0>(n);  // partition pass geometry
-  MHB_FOR_WR(M)
-#undef M
-  return kSortHeadBytes + lb_bytes(tiles) + 256;
-}
-
-template <int WR, int CFG>
-static int launch_radix_pass_cfg(cudaStream_t st, const u32 *in, u64 n, int byte_idx, const u64 *bin_base,
-                                 u64 *lookback, u32 *tile_counter, u64 *next_hist, int next_byte, u32 epoch) {
-  using C = SortCfg<WR, CFG>;
-  static int blocks_per_sm = 0;
-  if (!blocks_per_sm) {
-    CK(cudaFuncSetAttribute(k_radix_pass<WR, CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_radix_pass<WR, CFG>, C::THREADS, C::SMEM));
-    if (blocks_per_sm < 1) return mhb_set_error(MHB_ERR_CUDA, "radix pass kernel (WR=%d) does not fit an SM", WR);
-    if (getenv("MHB_VERBOSE")) fprintf(stderr, "[mhb] radix pass WR=%d cfg=%d: %d threads x %d rec, %zu B smem, %d CTA/SM\n", WR, CFG, C::THREADS, C::IPT, C::SMEM, blocks_per_sm);
-  }
-  const u64 tiles = sort_tiles_cfg<WR, CFG>(n);
-  u64 grid = (u64)blocks_per_sm * sm_count();
-  if (grid > tiles) grid = tiles;
-  k_radix_pass<WR, CFG><<<(int)grid, C::THREADS, C::SMEM, st>>>(in, n, (u32)tiles, byte_idx, bin_base, lookback,
-                                                                 tile_counter, next_hist, next_byte, epoch);
-  CK_LAUNCH();
-  return MHB_OK;
-}
-
-template <int WR, int CFG>
-static int launch_radix_pass_cfg3(cudaStream_t st, const u32 *in, u64 n, int byte_idx, const u64 *bin_base,
-                                  u64 *lookback, u32 *tile_counter, u64 *next_hist, int next_byte, u32 epoch) {
-  using C = SortCfg3<WR, CFG>;
-  static int blocks_per_sm = 0;
-  if (!blocks_per_sm) {
-    CK(cudaFuncSetAttribute(k_radix_pass3<WR, CFG, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    CK(cudaFuncSetAttribute(k_radix_pass3<WR, CFG, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_radix_pass3<WR, CFG, false, true>, C::THREADS, C::SMEM));
-    if (blocks_per_sm < 1) return mhb_set_error(MHB_ERR_CUDA, "radix pass v3 kernel (WR=%d) does not fit an SM", WR);
-    if (getenv("MHB_VERBOSE")) fprintf(stderr, "[mhb] radix pass v3 WR=%d bits=0x%03x: %d threads x %d rec, rank %d, prefetch %d, look-back %d/%d, batch %d, early %d, %zu B smem, %d CTA/SM\n", WR, CFG, C::THREADS, C::IPT, C::RANK, (int)C::PREFETCH, C::LB1, C::LBW, (int)C::BATCH, (int)C::EARLY, C::SMEM, blocks_per_sm);
-  }
-  const u64 tiles = sort_tiles_cfg3<WR, CFG>(n);
-  u64 grid = (u64)blocks_per_sm * sm_count();
-  if (grid > tiles) grid = tiles;
-  if (next_hist)
-    k_radix_pass3<WR, CFG, false, true><<<(int)grid, C::THREADS, C::SMEM, st>>>(in, n, (u32)tiles, byte_idx, bin_base, lookback,
-                                                                                 tile_counter, next_hist, next_byte, epoch);
-  else
-    k_radix_pass3<WR, CFG, false, false><<<(int)grid, C::THREADS, C::SMEM, st>>>(in, n, (u32)tiles, byte_idx, bin_base, lookback,
-                                                                                  tile_counter, nullptr, 0, epoch);
-  CK_LAUNCH();
-  return MHB_OK;
-}
-
-template <int WR>
-static int launch_radix_pass(cudaStream_t st, const u32 *in, u64 n, int byte_idx, const u64 *bin_base,
-                             u64 *lookback, u32 *tile_counter, u64 *next_hist, int next_byte, u32 epoch) {
-  const int cfg = sort_cfg();
-  if (cfg >= 256) {
-    if constexpr (WR == 2 || WR == 3) {
-#define X(B) \
-  if (cfg - 256 == B) return launch_radix_pass_cfg3<WR, B>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
-      MHB_V3_LIST(X)
-#undef X
-    }
-    return launch_radix_pass_cfg3<WR, MHB_V3_DEFAULT>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
-  }
-  if constexpr (WR <= 3) {
-    switch (cfg) {
-      case 1: return launch_radix_pass_cfg<WR, 1>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
-      case 2: return launch_radix_pass_cfg<WR, 2>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
-      case 3: return launch_radix_pass_cfg<WR, 3>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
-      default: break;
-    }
-  }
-  return launch_radix_pass_cfg<WR, 0>(st, in, n, byte_idx, bin_base, lookback, tile_counter, next_hist, next_byte, epoch);
-}
-
-#ifdef MHB_SORT_TIMELINE
-// diagnostic build only: point the v3 radix pass at a device buffer of rows x 16 uint64 (see mhb_sort3.cuh)
-extern "C" int mhb_debug_set_sort_timeline(unsigned long long *dev_buf, unsigned long long rows) {
-  CK(cudaMemcpyToSymbol(g_sort_timeline, &dev_buf, sizeof(dev_buf)));
-  CK(cudaMemcpyToSymbol(g_sort_timeline_rows, &rows, sizeof(rows)));
-  return MHB_OK;
-}
-#endif
-
-// Per-pass timing: every sort records one event before and after each pass into a small ring, so a
-// caller can ask afterwards (mhb_sort_pass_ms) how long each pass of a recent sort took without putting a
-// synchronisation inside its timed region.
-namespace {
-struct SortTrace {
-  cudaEvent_t ev[74];
-  bool created = false;
-  uint32_t n_passes = 0, words = 0;
-  uint64_t n = 0;
-};
-SortTrace g_trace[4];
-uint64_t g_trace_seq = 0;
-}  // namespace
-
-int mhb_sort_records_impl(void *stream, uint32_t *a, uint32_t *b, uint64_t n, uint32_t words, const uint8_t *bytes,
-                          uint32_t n_bytes, const uint64_t *first_hist, void *ws, size_t ws_bytes, int *result_in_b,
-                          double *pass_ms_host) {
-  if (words < 1 || words > 17 || n_bytes > 72 || !result_in_b)
-    return mhb_set_error(MHB_ERR_ARG, "bad sort geometry (words=%u n_bytes=%u)", words, n_bytes);
-  *result_in_b = 0;
-  if (n == 0 || n_bytes == 0) return MHB_OK;
-  if (ws_bytes < mhb_sort_workspace_bytes(n, words)) return mhb_set_error(MHB_ERR_ARG, "sort workspace too small");
-  if (n >= (1ull << 53)) return mhb_set_error(MHB_ERR_ARG, "too many records");
-  cudaStream_t st = (cudaStream_t)stream;
-  u64 *hist = (u64 *)ws;                        // [n_bytes+1][256]
-  u64 *bin_base = hist + (72 + 1) * 256;        // [256]
-  u32 *tile_counter = (u32 *)(bin_base + 256);  // [128]
-  u64 *lookback = (u64 *)((char *)ws + kSortHeadBytes);
-  // only what this sort's tile geometry touches (the workspace itself is sized for the smallest tile of any variant)
-  CK(cudaMemsetAsync(ws, 0, kSortHeadBytes + lb_bytes(sort_num_tiles(n, words)) + 256, st));
-  if (first_hist) {
-    CK(cudaMemcpyAsync(hist, first_hist, 256 * 8, cudaMemcpyDeviceToDevice, st));
-  } else {
-#define M(WW) \
-  if (words == WW) k_hist_byte<WW><<<sm_count() * 4, 256, 0, st>>>(a, n, bytes[0], hist);
-    MHB_FOR_WR(M)
-#undef M
-    CK_LAUNCH();
-  }
-  SortTrace &tr = g_trace[g_trace_seq++ & 3];
-  if (!tr.created) {
-    for (int i = 0; i < 74; ++i) CK(cudaEventCreate(&tr.ev[i]));
-    tr.created = true;
-  }
-  tr.n_passes = n_bytes;
-  tr.words = words;
-  tr.n = n;
-  CK(cudaEventRecord(tr.ev[0], st));
-  u32 *in = a, *out = b;
-  for (u32 p = 0; p < n_bytes; ++p) {
-    k_hist_scan256<<<1, 256, 0, st>>>(hist + (u64)p * 256, bin_base, (u64)(uintptr_t)out, words * 4);
-    CK_LAUNCH();
-    u64 *next_hist = p + 1 < n_bytes ? hist + (u64)(p + 1) * 256 : nullptr;
-    const int next_byte = p + 1 < n_bytes ? bytes[p + 1] : 0;
-    int rc = MHB_ERR_ARG;
-#define M(WW) \
-  if (words == WW) rc = launch_radix_pass<WW>(st, in, n, bytes[p], bin_base, lookback, tile_counter + p, next_hist, next_byte, p + 1);
-    MHB_FOR_WR(M)
-#undef M
-    if (rc) return rc;
-    CK(cudaEventRecord(tr.ev[p + 1], st));
-    u32 *t = in;
-    in = out;
-    out = t;
-  }
-  *result_in_b = (in == b) ? 1 : 0;
-  if (pass_ms_host) {
-    CK(cudaEventSynchronize(tr.ev[n_bytes]));
-    for (u32 p = 0; p < n_bytes; ++p) {
-      float ms = 0;
-      CK(cudaEventElapsedTime(&ms, tr.ev[p], tr.ev[p + 1]));
-      pass_ms_host[p] = ms;
-    }
-  }
-  return MHB_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// fused partition + exchange: one radix pass whose per-digit destinations are arbitrary device addresses, e.g.
-// slots inside OTHER GPUs' receive buffers opened through CUDA IPC.  The scatter stores travel over NVLink while
-// the rest of the tile is still being ranked - no separate all-to-all.
-// ------------------------------------------------------------------------------------------------
-template <int WR>
-static int launch_partition_pass(cudaStream_t st, const u32 *in, u64 n, int byte_idx, const u64 *bin_addr, u64 *lookback,
-                                 u32 *tile_counter, const uint8_t *lut) {
-  using C = SortCfg<WR, 0>;
-  static int blocks_per_sm = 0;
-  if (!blocks_per_sm) {
-    CK(cudaFuncSetAttribute(k_radix_pass<WR, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_radix_pass<WR, 0, true>, C::THREADS, C::SMEM));
-    if (blocks_per_sm < 1) return mhb_set_error(MHB_ERR_CUDA, "partition pass kernel (WR=%d) does not fit an SM", WR);
-  }
-  const u64 tiles = sort_tiles_cfg<WR, 0>(n);
-  u64 grid = (u64)blocks_per_sm * sm_count();
-  if (grid > tiles) grid = tiles;
-  k_radix_pass<WR, 0, true><<<(int)grid, C::THREADS, C::SMEM, st>>>(in, n, (u32)tiles, byte_idx, bin_addr, lookback,
-                                                                     tile_counter, nullptr, 0, 1, lut);
-  CK_LAUNCH();
-  return MHB_OK;
-}
-
-extern "C" int mhb_partition_scatter(void *stream, const uint32_t *recs, uint64_t n, uint32_t words, int byte,
-                                     const uint8_t *owner_of_byte_dev, const uint64_t *bin_addr_dev, void *ws,
-                                     size_t ws_bytes) {
-  if (words < 1 || words > 17 || byte < 0 || byte >= (int)(4 * words)) return mhb_set_error(MHB_ERR_ARG, "bad geometry");
-  if (n == 0) return MHB_OK;
-  // the partition pass always runs the v2 kernel in geometry 0, whatever variant the sorts use
-  u64 tiles = 0;
-#define M(WW) \
-  if (words == WW) tiles = sort_tiles_cfg<WW, 0>(n);
-  MHB_FOR_WR(M)
-#undef M
-  const size_t need = kSortHeadBytes + (size_t)tiles * 256 * 8 + 256;
-  if (ws_bytes < need) return mhb_set_error(MHB_ERR_ARG, "sort workspace too small");
-  cudaStream_t st = (cudaStream_t)stream;
-  u64 *hist = (u64 *)ws;
-  u32 *tile_counter = (u32 *)(hist + (72 + 1) * 256 + 256);
-  u64 *lookback = (u64 *)((char *)ws + kSortHeadBytes);
-  CK(cudaMemsetAsync(ws, 0, need, st));
-  int rc = MHB_ERR_ARG;
-  if (owner_of_byte_dev) {
-#define M(WW) \
-  if (words == WW) rc = launch_partition_pass<WW>(st, recs, n, byte, bin_addr_dev, lookback, tile_counter, owner_of_byte_dev);
-    MHB_FOR_WR(M)
-#undef M
-  } else {
-#define M(WW) \
-  if (words == WW) rc = launch_radix_pass_cfg<WW, 0>(st, recs, n, byte, bin_addr_dev, lookback, tile_counter, nullptr, 0, 1);
-    MHB_FOR_WR(M)
-#undef M
-  }
-  return rc;
-}
-
-extern "C" int mhb_dev_malloc(void **ptr, size_t bytes) {
-  CK(cudaMalloc(ptr, bytes));
-  return MHB_OK;
-}
-extern "C" int mhb_dev_free(void *ptr) {
-  CK(cudaFree(ptr));
-  return MHB_OK;
-}
-extern "C" int mhb_ipc_export(const void *dev_ptr, uint8_t *handle64) {
-  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
-  cudaIpcMemHandle_t h;
-  CK(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
-  memcpy(handle64, &h, 64);
-  return MHB_OK;
-}
-extern "C" int mhb_ipc_open(const uint8_t *handle64, void **peer_ptr) {
-  cudaIpcMemHandle_t h;
-  memcpy(&h, handle64, 64);
-  CK(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
-  return MHB_OK;
-}
-extern "C" int mhb_ipc_close(void *peer_ptr) {
-  CK(cudaIpcCloseMemHandle(peer_ptr));
-  return MHB_OK;
-}
-
-extern "C" int mhb_sort_pass_ms(int back, double *pass_ms, uint32_t max_passes, uint32_t *n_passes, uint64_t *n_records,
-                                uint32_t *words) {
-  if (back < 0 || back > 3 || (uint64_t)back >= g_trace_seq) return mhb_set_error(MHB_ERR_ARG, "no such sort in the trace ring");
-  SortTrace &tr = g_trace[(g_trace_seq - 1 - back) & 3];
-  CK(cudaEventSynchronize(tr.ev[tr.n_passes]));
-  for (u32 p = 0; p < tr.n_passes && p < max_passes; ++p) {
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, tr.ev[p], tr.ev[p + 1]));
-    pass_ms[p] = ms;
-  }
-  if (n_passes) *n_passes = tr.n_passes;
-  if (n_records) *n_records = tr.n;
-  if (words) *words = tr.words;
-  return MHB_OK;
-}
-
-extern "C" int mhb_sort_records(void *stream, uint32_t *a, uint32_t *b, uint64_t n, uint32_t words,
-                                const uint8_t *bytes, uint32_t n_bytes, const uint64_t *first_hist, void *ws,
-                                size_t ws_bytes, int *result_in_b) {
-  return mhb_sort_records_impl(stream, a, b, n, words, bytes, n_bytes, first_hist, ws, ws_bytes, result_in_b, nullptr);
-}
-
-// ------------------------------------------------------------------------------------------------
 // count: solid edges
 // ------------------------------------------------------------------------------------------------
 extern "C" int mhb_count_solid(void *stream, const uint32_t *sorted_records, uint64_t n, uint32_t k, int32_t m,
@@ -564,13 +209,11 @@ extern "C" int mhb_count_solid(void *stream, const uint32_t *sorted_records, uin
                                uint64_t *n_solid_out, void *scratch, size_t scratch_bytes) {
   if (k < 1 || k > MHB_MAX_K || !mul_hist || !n_solid_out) return mhb_set_error(MHB_ERR_ARG, "bad args");
   if (n == 0) return MHB_OK;
-  const u64 nblk = (n + kCompactTile - 1) / kCompactTile;
   const size_t need = mhb_count_solid_scratch_bytes(n);
   if (scratch_bytes < need) return mhb_set_error(MHB_ERR_ARG, "count scratch too small (%zu < %zu)", scratch_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
   const u32 WR = count_record_words(k);
-  static const bool use_v1 = getenv("MHB_COUNT_V1") != nullptr, use_v2 = getenv("MHB_COUNT_V2") != nullptr;
-  if (!use_v1 && !use_v2) {
+  {
     // v3: lane-blocked judge -> scan of chunk totals -> gather/pack (mhb_count.cuh)
 #define M(WW)                                                                                                          \
   if (WR == WW) {                                                                                                      \
@@ -617,54 +260,7 @@ extern "C" int mhb_count_solid(void *stream, const uint32_t *sorted_records, uin
     CK_LAUNCH();
     return MHB_OK;
   }
-  if (use_v2) {
-    // v2: single pass, warp-cooperative ballots (mhb_count.cuh k_count_warp); kept for A/B checks
-    const u32 WE = words_per_edge(k);
-    const int CH = count_chunk((int)WE);
-    const u64 n_chunks = (n + CH - 1) / CH;
-    if (n_chunks >= (1ull << 32)) return mhb_set_error(MHB_ERR_ARG, "too many records for one count launch");
-    u32 *ticket = (u32 *)scratch;
-    u64 *lookback = (u64 *)((char *)scratch + 64);
-    CK(cudaMemsetAsync(scratch, 0, 64 + n_chunks * 8, st));
-    const size_t smem = (size_t)kCountWarps * CH * (WE * 4 + 1);
-    u64 grid = (u64)sm_count() * 4;
-    if (grid > (n_chunks + kCountWarps - 1) / kCountWarps) grid = (n_chunks + kCountWarps - 1) / kCountWarps;
-#define M(WW)                                                                                                        \
-  if (WR == WW) {                                                                                                    \
-    static bool attr = false;                                                                                        \
-    if (!attr) {                                                                                                     \
-      CK(cudaFuncSetAttribute(k_count_warp<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));           \
-      attr = true;                                                                                                   \
-    }                                                                                                                \
-    k_count_warp<WW><<<(unsigned)grid, kCountWarps * 32, smem, st>>>(sorted_records, n, k, m, (u32)n_chunks, ticket,  \
-                                                                    lookback, edges_out, aux_out, capacity_edges,    \
-                                                                    mul_hist, n_solid_out);                         \
-  }
-    MHB_FOR_WR(M)
-#undef M
-    CK_LAUNCH();
-    return MHB_OK;
-  }
-  u32 *info = (u32 *)scratch;
-  u64 *btot = (u64 *)((char *)scratch + (((size_t)n * 4 + 63) & ~(size_t)63));
-  const u64 gmark = (n + 255) / 256;
-#define M(WW) \
-  if (WR == WW) k_count_mark<WW><<<(unsigned)gmark, 256, 0, st>>>(sorted_records, n, m, info, mul_hist);
-  MHB_FOR_WR(M)
-#undef M
-  CK_LAUNCH();
-  k_solid_block_totals<<<(unsigned)nblk, kCompactThreads, 0, st>>>(info, n, btot);
-  CK_LAUNCH();
-  k_scan_u64<<<1, 1024, 0, st>>>(btot, nblk, n_solid_out);
-  CK_LAUNCH();
-#define M(WW)                                                                                                       \
-  if (WR == WW)                                                                                                     \
-    k_count_emit<WW><<<(unsigned)nblk, kCompactThreads, 0, st>>>(sorted_records, info, n, k, btot, edges_out, aux_out, \
-                                                                 capacity_edges);
-  MHB_FOR_WR(M)
-#undef M
-  CK_LAUNCH();
-  return MHB_OK;
+  return mhb_set_error(MHB_ERR_ARG, "unsupported k=%u", k);
 }
 
 extern "C" size_t mhb_count_solid_scratch_bytes(uint64_t n) {
@@ -840,7 +436,6 @@ extern "C" int mhb_s2s_extract_range(void *stream, const mhb_dev_seqs *seqs, uin
   return MHB_OK;
 }
 
-static int scan32(cudaStream_t st, const u32 *in, u64 n, u64 *out, u64 *total_dev, u64 *bsum);
 // in-place exclusive scan of n u64 values (three phases, no serial chain); total -> *total_dev
 static int scan64(cudaStream_t st, u64 *v, u64 n, u64 *total_dev, u64 *bsum) {
   const u64 nb = (n + kScanTile - 1) / kScanTile;
@@ -962,7 +557,7 @@ extern "C" int mhb_s2s_emit(void *stream, const uint32_t *sorted_records, uint64
 // ------------------------------------------------------------------------------------------------
 // mercy edges on the device (A11)
 // ------------------------------------------------------------------------------------------------
-static int scan32(cudaStream_t st, const u32 *in, u64 n, u64 *out, u64 *total_dev, u64 *bsum) {
+int scan32(cudaStream_t st, const u32 *in, u64 n, u64 *out, u64 *total_dev, u64 *bsum) {
   const u64 nb = (n + kScanTile - 1) / kScanTile;
   k_scan32_sums<<<(unsigned)nb, kScanThreads, 0, st>>>(in, n, bsum);
   CK_LAUNCH();
@@ -1004,7 +599,7 @@ extern "C" int mhb_mercy_candidates(void *stream, const uint32_t *first_0_out, c
 }
 
 extern "C" size_t mhb_edge_lut_bytes(void);
-static size_t mercy_core_scratch(uint64_t n_cand, uint32_t max_read_len) {
+size_t mercy_core_scratch(uint64_t n_cand, uint32_t max_read_len) {
   const size_t wpr = (max_read_len + 31) / 32 + 1;
   return (size_t)n_cand * 3 * wpr * 4 + (size_t)(n_cand + 64) * 12 + (size_t)(n_cand / kScanTile + 2) * 8 + 2048;
 }
@@ -1028,14 +623,7 @@ extern "C" int mhb_edge_lut_build(void *stream, const uint32_t *edges, uint64_t 
   return MHB_OK;
 }
 
-// Layout of the mercy scratch shared by the count and the write half
-struct MercyScratch {
-  u64 *total;
-  u32 *bits, *count;
-  u64 *off, *bsum;
-  u32 wpr;
-};
-static MercyScratch mercy_scratch_layout(void *scratch, uint64_t n_cand, uint32_t max_read_len) {
+MercyScratch mercy_scratch_layout(void *scratch, uint64_t n_cand, uint32_t max_read_len) {
   MercyScratch m;
   m.wpr = (max_read_len + 31) / 32 + 1;
   char *p = (char *)scratch;

@@ -21,13 +21,13 @@
 namespace mhb {
 
 // candidate reads: first_0_out / last_0_in both set and last > first (kmer_counter.cpp:395-401)
-__global__ void k_cand_flags(const u32 *first, const u32 *last, u64 n_reads, u32 *flag) {
+static __global__ void k_cand_flags(const u32 *first, const u32 *last, u64 n_reads, u32 *flag) {
   const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
   const u32 f = first[r], l = last[r];
   flag[r] = (f != MHB_SENTINEL_OFFSET && l != MHB_SENTINEL_OFFSET && l > f) ? 1u : 0u;
 }
-__global__ void k_cand_compact(const u32 *flag, const u64 *off, u64 n_reads, u64 *ids) {
+static __global__ void k_cand_compact(const u32 *flag, const u64 *off, u64 n_reads, u64 *ids) {
   const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (r < n_reads && flag[r]) ids[off[r]] = r;
 }
@@ -45,7 +45,7 @@ struct EdgeSegs {
 // InitLookupTable (seq_to_sdbg.cpp:100-127) for one segment: lut[p] = {first, last} index of the edges whose first
 // 12 bases are p.  lut must be pre-filled with 0xFF.
 static constexpr u32 kLutEntries = 1u << 24;
-__global__ void k_edge_lut(const u32 *__restrict__ edges, u64 n, u32 we, uint2 *lut) {
+static __global__ void k_edge_lut(const u32 *__restrict__ edges, u64 n, u32 we, uint2 *lut) {
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
     const u32 p = edges[i * we] >> 8;
     if (i == 0 || (edges[(i - 1) * we] >> 8) != p) lut[p].x = (u32)i;
@@ -231,4 +231,19 @@ __global__ void k_mercy_emit(ReadsView rv, const u64 *__restrict__ cand_ids, u64
   if (!WRITE) count[c] = n_out;
 }
 
+// Layout of the mercy scratch shared by the count and the write half (mhb_mercy_edges_count / _write)
+struct MercyScratch {
+  u64 *total;
+  u32 *bits, *count;
+  u64 *off, *bsum;
+  u32 wpr;
+};
+
 }  // namespace mhb
+
+// host helpers defined in mhb_device.cu, shared with mhb_multi.cu
+mhb::ReadsView make_reads_view(const mhb_dev_reads *r);
+int check_reads(const mhb_dev_reads *r, uint32_t k);
+int scan32(cudaStream_t st, const uint32_t *in, uint64_t n, uint64_t *out, uint64_t *total_dev, uint64_t *bsum);
+size_t mercy_core_scratch(uint64_t n_cand, uint32_t max_read_len);
+mhb::MercyScratch mercy_scratch_layout(void *scratch, uint64_t n_cand, uint32_t max_read_len);

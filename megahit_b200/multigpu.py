@@ -99,6 +99,7 @@ class PeerBuffers:
                 buf = (C.c_uint8 * 64).from_buffer_copy(hb)
                 lib._check(L.mhb_ipc_open(buf, C.byref(q)))
                 self.peers.append(q.value)
+        self.peers_c = (C.c_uint64 * 16)(*self.peers)
         dist.barrier()
 
     def close(self):
@@ -111,21 +112,35 @@ class PeerBuffers:
 
 
 class MultiGpuBuild:
-    """count -> mercy -> seq2sdbg across the ranks of the default process group (fixed-length reads)."""
+    """count -> mercy -> seq2sdbg across the ranks of the default process group (fixed-length reads).
+
+    Host involvement per step is limited to reading a handful of counters (records owned, solid edges, tips,
+    candidates, mercy edges) that size the next launches; plans, owner tables and destination addresses are computed
+    on the device (mhb_plan_partition) from one all-gather of the 256-bin histograms, and the ranks order their
+    accesses to each other's buffers with stream-ordered collectives (the histogram all-gather before the scatter, a
+    one-word all-reduce after it) instead of host barriers."""
 
     def __init__(self, n_reads: int, read_len: int, k: int, m: int, device, need_mercy: bool = True):
+        import os
         self.L = lib.load()
         self.n_reads, self.read_len, self.k, self.m, self.device = n_reads, read_len, k, m, device
         self.need_mercy = need_mercy
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        if self.world > 16:
+            raise lib.MhbError("the multi-GPU build supports up to 16 ranks (one node)")
         self.WR, self.WE, self.W2 = lib.count_record_words(k), lib.words_per_edge(k), lib.s2s_record_words(k)
         self.cbytes, self.sbytes = lib.count_sort_bytes(k), lib.s2s_sort_bytes(k)
         self.n_local = n_reads * (read_len - k) if read_len >= k + 1 else 0
+        self.stride = 1 + (read_len + 15) // 16
         self.times = {}
-        import os
         self.fused = self.world > 1 and not os.environ.get("MHB_MGPU_NCCL_A2A")
         self.peer = {}
+        self._bufs = {}
+        self._tok = torch.zeros(1, dtype=torch.int32, device=device)
+        self._pin = torch.empty(64, dtype=torch.int64).pin_memory()
+        self._timed = False
 
+    # ------------------------------------------------------------------ helpers
     def _mark(self, name):
         ev = torch.cuda.Event(enable_timing=True)
         ev.record()
@@ -133,80 +148,87 @@ class MultiGpuBuild:
 
     def _buf(self, name, numel, dtype=torch.int32, slack=1.0):
         """grow-only named device buffer: steady-state steps allocate nothing"""
-        if not hasattr(self, "_bufs"):
-            self._bufs = {}
         t = self._bufs.get(name)
         if t is None or t.numel() < numel or t.dtype != dtype:
             t = torch.empty(int(numel * slack) + 64, dtype=dtype, device=self.device)
             self._bufs[name] = t
         return t
 
-    def _partition_and_exchange(self, recs, n, words, top_byte, hist_dev, tag):
-        """Group the records by owner (one stable radix pass on the top byte) and move them to their owners.
-        Fused mode: the pass's scatter stores go straight into the owners' receive buffers over NVLink (CUDA IPC peer
-        pointers) - ONE kernel does partition + exchange.  Fallback (MHB_MGPU_NCCL_A2A=1): local pass, then one
-        variable-size NCCL all-to-all.  Returns (pointer to the owned records, count, bounds)."""
-        L = self.L
-        ghist = hist_dev.clone()
-        dist.all_reduce(ghist)
-        hist_h = hist_dev.cpu().numpy().astype(np.int64)
-        bounds = plan_ranges(ghist.cpu().numpy(), self.world)
-        send = split_counts(hist_h, bounds)
+    def _to_host(self, t: torch.Tensor) -> np.ndarray:
+        """small device int64 tensor -> numpy through one pinned staging buffer (ONE stream sync)"""
+        n = t.numel()
+        self._pin[:n].copy_(t.reshape(-1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._pin[:n].numpy().copy()
+
+    def _stream_barrier(self):
+        """every rank's earlier work on its stream is complete before any rank's later work starts (no host sync)"""
+        dist.all_reduce(self._tok)
+
+    def _gather_counts(self, *vals) -> np.ndarray:
+        """all-gather a few host integers; returns an array [world][len(vals)] (one sync)"""
+        t = torch.tensor(list(vals), dtype=torch.int64, device=self.device)
+        out = torch.empty(self.world * len(vals), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(out, t)
+        return self._to_host(out).reshape(self.world, len(vals))
+
+    def _peer(self, tag, need_bytes):
+        """(re)allocate the IPC receive buffers of a stage - a collective: `need_bytes` must be the same on every rank"""
+        pb = self.peer.get(tag)
+        if pb is not None:
+            pb.close()
+        pb = self.peer[tag] = PeerBuffers(int(need_bytes * 1.25) + 4096)
+        return pb
+
+    def _partition_and_exchange(self, recs, n, words, top_byte, hist_dev, tag, expect_own):
+        """Move every record to the rank owning its leading byte.  Fused mode: ONE kernel does partition + exchange -
+        the radix pass's scatter stores go straight into the owners' receive buffers over NVLink (CUDA IPC peer
+        pointers).  Fallback (MHB_MGPU_NCCL_A2A=1): local pass, then one variable-size NCCL all-to-all.
+        Returns (pointer to the owned records, count, bounds[world+1] numpy, owner table numpy uint8[256])."""
+        L, W = self.L, self.world
+        rb = words * 4
+        hist_all = self._buf(tag + "_hist_all", W * 256, torch.int64)
+        # the all-gather also orders the ranks: when it completes, every rank has finished the previous step's reads
+        # of its receive buffer, so the scatter below may overwrite it
+        dist.all_gather_into_tensor(hist_all[: W * 256], hist_dev)
+        lut_dev = self._buf(tag + "_lut", 256, torch.uint8)
+        addr_dev = self._buf(tag + "_addr", 256, torch.int64)
+        plan_dev = self._buf(tag + "_plan", 64, torch.int64)
+        # the receive buffers have the SAME size on every rank, derived from the plan (identical everywhere), so that all
+        # ranks take the same (collective) reallocation decision; expect_own only matters for the log
+        pb = self.peer.get(tag) if self.fused else None
+        for attempt in range(2):
+            peers_c = pb.peers_c if pb is not None else (C.c_uint64 * 16)()
+            lib._check(L.mhb_plan_partition(_stream(), _ptr(hist_all), W, self.rank, rb, peers_c, _ptr(lut_dev), _ptr(addr_dev),
+                                            _ptr(plan_dev)))
+            plan = self._to_host(plan_dev[:64])
+            recv_tot, send, bounds = plan[:W], plan[16:16 + W], plan[32:33 + W]
+            self._recv_tot = recv_tot
+            need = int(recv_tot.max()) * rb + 64
+            if not self.fused or (pb is not None and need <= pb.nbytes):
+                break
+            pb = self._peer(tag, need)  # addresses change: plan once more
+        owner = np.repeat(np.arange(W, dtype=np.uint8), np.diff(bounds).astype(np.int64))
         if self._timed:
             self._mark(tag + "_plan")
         ws = self._buf(tag + "_ws", L.mhb_sort_workspace_bytes(max(n, 1), words), torch.uint8)
+        n_own = int(recv_tot[self.rank])
         if not self.fused:
             tmp = self._buf(tag + "_part", recs.numel())
             grouped = sort_records(recs, tmp, n, words, [top_byte], hist_dev, ws)
-            if self._timed:
-                self._mark(tag + "_partition")
             sc = torch.tensor(send, dtype=torch.int64, device=recs.device)
             rc = torch.empty_like(sc)
             dist.all_to_all_single(rc, sc)
-            recv_counts = rc.cpu().numpy()
-            n_recv = int(recv_counts.sum())
-            out = self._buf(tag + "_own", n_recv * words + 4, slack=1.15)
-            allr = [torch.empty_like(rc[:1]) for _ in range(self.world)]
-            dist.all_gather(allr, torch.tensor([n_recv], dtype=torch.int64, device=recs.device))
-            self._recv_tot = np.array([int(x.item()) for x in allr], np.int64)
-            if self._timed:
-                self._mark(tag + "_counts")
-            dist.all_to_all_single(out[: n_recv * words], grouped[: int(send.sum()) * words],
+            recv_counts = self._to_host(rc)
+            out = self._buf(tag + "_own", n_own * words + 4, slack=1.15)
+            dist.all_to_all_single(out[: n_own * words], grouped[: int(send.sum()) * words],
                                    output_split_sizes=[int(c) * words for c in recv_counts],
                                    input_split_sizes=[int(c) * words for c in send])
-            return out.data_ptr(), n_recv, bounds
-        # ---- fused: who sends how much to whom, where my block starts inside every owner's buffer ----
-        sc = torch.tensor(send, dtype=torch.int64, device=recs.device)
-        allsend = [torch.empty_like(sc) for _ in range(self.world)]
-        dist.all_gather(allsend, sc)
-        M = torch.stack(allsend).cpu().numpy()  # M[r][o] = records rank r sends to owner o
-        recv_tot = M.sum(axis=0)
-        self._recv_tot = recv_tot
-        need = int(recv_tot.max()) * words * 4 + 64
-        pb = self.peer.get(tag)
-        if pb is None or pb.nbytes < need:  # same decision on every rank: M is identical everywhere
-            if pb is not None:
-                pb.close()
-            pb = self.peer[tag] = PeerBuffers(int(need * 1.2))
-        rb = words * 4
-        my_off = M[: self.rank].sum(axis=0)  # my block's first record inside owner o's buffer
-        # digit of the partition pass = owning rank: one long contiguous run per destination and tile
-        addr = np.zeros(256, np.uint64)
-        lut = np.zeros(256, np.uint8)
-        for o in range(self.world):
-            lut[int(bounds[o]):int(bounds[o + 1])] = o
-            addr[o] = np.uint64(pb.peers[o]) + np.uint64(my_off[o]) * np.uint64(rb)
-        addr_dev = torch.from_numpy(addr.view(np.int64)).to(recs.device)
-        lut_dev = torch.from_numpy(lut).to(recs.device)
-        if self._timed:
-            self._mark(tag + "_partition")
-        dist.barrier()  # every owner is done with what it received in the previous step
-        if self._timed:
-            self._mark(tag + "_counts")
+            return out.data_ptr(), n_own, bounds, owner
         lib._check(L.mhb_partition_scatter(_stream(), _ptr(recs), n, words, top_byte, _ptr(lut_dev), _ptr(addr_dev), _ptr(ws),
                                            ws.numel()))
-        dist.barrier()  # all ranks' scatter kernels have completed: my buffer is complete
-        return pb.ptr, int(recv_tot[self.rank]), bounds
+        self._stream_barrier()  # all ranks' scatter kernels have completed: my buffer is complete
+        return pb.ptr, n_own, bounds, owner
 
     def close(self):
         for pb in self.peer.values():
@@ -224,106 +246,128 @@ class MultiGpuBuild:
                                       ws.numel(), C.byref(in_b)))
         return tmp.data_ptr() if in_b.value else ptr_a
 
+    # ------------------------------------------------------------------ mercy stage
+    def _mercy(self, reads, bin_dev, edges, aux, n_solid, n_tip, owner):
+        """tip edges of every rank -> per-read marks -> candidate reads -> searches answered by the owners of the
+        searched prefixes -> mercy edges appended behind this rank's solid edges.  Returns (edges tensor, n_cand, n_mercy)."""
+        L, k, dev, W, WE = self.L, self.k, self.device, self.world, self.WE
+        i32 = dict(dtype=torch.int32, device=dev)
+        e2 = edges[: n_solid * WE].view(-1, WE)
+        # ---- tip edges of all ranks (0.5 % of the solid edges): one padded all-gather, padding has aux = 0 ----
+        cnt = self._gather_counts(n_tip, n_solid)
+        mx = max(int(cnt[:, 0].max()), 1)
+        pad_t = self._buf("tip_pad", mx * WE)[: mx * WE].view(mx, WE)
+        pad_a = self._buf("tip_pad_a", mx, torch.uint8)[:mx]
+        pad_a.zero_()
+        if n_tip:
+            idx = torch.nonzero(aux[:n_solid]).reshape(-1)
+            pad_t[:n_tip] = e2[idx]
+            pad_a[:n_tip] = aux[:n_solid][idx]
+        all_t = self._buf("tip_all", W * mx * WE)[: W * mx * WE]
+        all_a = self._buf("tip_all_a", W * mx, torch.uint8)[: W * mx]
+        dist.all_gather_into_tensor(all_t, pad_t.reshape(-1))
+        dist.all_gather_into_tensor(all_a, pad_a)
+        n_tip_all = int(cnt[:, 0].sum())
+        need = L.mhb_tipset_bytes(n_tip_all, k)
+        tipset = self._buf("tipset", need, torch.uint8, slack=1.2)
+        lib._check(L.mhb_tipset_build(_stream(), _ptr(all_t), _ptr(all_a), W * mx, k, _ptr(tipset), need, n_tip_all))
+        first = self._buf("first", self.n_reads + 1)
+        last = self._buf("last", self.n_reads + 1)
+        lib._check(L.mhb_count_mark_mercy(_stream(), C.byref(reads), k, _ptr(tipset), need, n_tip_all, _ptr(first), _ptr(last)))
+        cand = self._buf("cand", self.n_reads + 1, torch.int64)
+        cs = self._buf("cand_scratch", L.mhb_mercy_candidates_scratch_bytes(self.n_reads), torch.uint8)
+        nc = C.c_uint64(0)
+        lib._check(L.mhb_mercy_candidates(_stream(), _ptr(first), _ptr(last), self.n_reads, _ptr(cand), C.byref(nc), _ptr(cs),
+                                          cs.numel()))
+        n_cand = nc.value
+        # ---- candidate reads of all ranks, padded (a zero length word = no positions) ----
+        ccnt = self._gather_counts(n_cand)[:, 0]
+        mc = int(ccnt.max())
+        if mc == 0:
+            return edges, 0, 0
+        st = self.stride
+        cpad = self._buf("cand_pad", mc * st)[: mc * st].view(mc, st)
+        cpad.zero_()
+        if n_cand:
+            cpad[:n_cand] = bin_dev[: self.n_reads * st].view(self.n_reads, st)[cand[:n_cand]]
+        call = self._buf("cand_all", W * mc * st + 8)
+        dist.all_gather_into_tensor(call[: W * mc * st], cpad.reshape(-1))
+        # ---- every rank answers the searches that land in its own bucket range, for ALL candidates ----
+        lut = self._buf("edge_lut", L.mhb_edge_lut_bytes(), torch.uint8)
+        lib._check(L.mhb_edge_lut_build(_stream(), _ptr(edges), n_solid, k, _ptr(lut)))
+        pw = L.mhb_mercy_planes_words(mc, self.read_len)  # per source rank
+        planes = self._buf("planes", W * pw)
+        greads = lib.DevReads(call.data_ptr(), W * mc * st, W * mc, self.read_len, None, None)
+        owner_c = (C.c_uint8 * 256)(*owner.tolist())
+        lib._check(L.mhb_mercy_probe_owned(_stream(), C.byref(greads), None, W * mc, self.read_len, k, _ptr(edges), n_solid,
+                                           _ptr(lut), owner_c, self.rank, _ptr(planes)))
+        # planes[o] = my answers about rank o's candidates  ->  mine[s] = rank s's answers about MY candidates
+        mine = self._buf("planes_mine", W * pw)
+        dist.all_to_all_single(mine[: W * pw], planes[: W * pw])
+        n_mercy = 0
+        if n_cand:
+            ms = self._buf("mercy_scratch", L.mhb_mercy_edges_scratch_bytes(n_cand, self.read_len) - L.mhb_edge_lut_bytes(),
+                           torch.uint8, slack=1.2)
+            nm = C.c_uint64(0)
+            lib._check(L.mhb_mercy_count_planes(_stream(), C.byref(reads), _ptr(cand), n_cand, self.read_len, k, _ptr(mine), W, pw,
+                                                C.byref(nm), _ptr(ms), ms.numel()))
+            n_mercy = nm.value
+            if n_mercy:
+                have = edges.numel() // WE
+                if n_solid + n_mercy > have:  # reads overlapping only at their ends: more mercy than solid edges
+                    big = self._buf("edges_big", (n_solid + n_mercy) * WE + 4, slack=1.1)
+                    big[: n_solid * WE].copy_(edges[: n_solid * WE])
+                    edges = big
+                lib._check(L.mhb_mercy_edges_write(_stream(), C.byref(reads), _ptr(cand), n_cand, self.read_len, k,
+                                                   C.c_void_p(edges.data_ptr() + n_solid * WE * 4), n_mercy, n_mercy, _ptr(ms),
+                                                   ms.numel()))
+        return edges, n_cand, n_mercy
+
+    # ------------------------------------------------------------------ one step
     def run(self, bin_dev: torch.Tensor, timed: bool = False) -> dict:
         L, k, m, dev = self.L, self.k, self.m, self.device
         self._timed = timed
-        i32 = dict(dtype=torch.int32, device=dev)
         reads = lib.DevReads(bin_dev.data_ptr(), bin_dev.numel(), self.n_reads, self.read_len, None, None)
         if timed:
             self._mark("t0")
         # ---- count stage ----
         n = self.n_local
         a = self._buf("c_a", n * self.WR + 4)
-        hist = torch.zeros(256, dtype=torch.int64, device=dev)
+        hist = self._buf("c_hist", 256, torch.int64)[:256]
+        hist.zero_()
         top = self.cbytes[-1]
         lib._check(L.mhb_count_extract(_stream(), C.byref(reads), k, _ptr(a), n, _ptr(hist), top))
         if timed:
             self._mark("extract")
-        own, n_own, bounds = self._partition_and_exchange(a, n, self.WR, top, hist, "c")
+        own, n_own, bounds, owner = self._partition_and_exchange(a, n, self.WR, top, hist, "c", max(n, 1))
         if timed:
             self._mark("exchange1")
         srt = self._sort_raw(own, n_own, self.WR, self.cbytes, "c")
         if timed:
             self._mark("sort1")
         cap = n_own // max(1, m) + 1
-        # the solid edges live in a buffer every rank can read (CUDA IPC): the mercy searches of other ranks look
-        # edges up in their owner's memory over NVLink instead of gathering 12 B x all edges onto every GPU
-        lut_bytes = L.mhb_edge_lut_bytes()
-        need_e = (int(self._recv_tot.max()) // max(1, m) + 2) * self.WE * 4 + 256 + lut_bytes  # identical on every rank
-        pe = self.peer.get("edges")
-        if pe is None or pe.nbytes < need_e:
-            if pe is not None:
-                pe.close()
-            pe = self.peer["edges"] = PeerBuffers(int((need_e - lut_bytes) * 1.1) + lut_bytes)
-        lut_off = (pe.nbytes - lut_bytes) & ~255  # the 12-mer look-up table sits at the end of the shared buffer
-        edges = torch.as_tensor(_RawView(pe.ptr, lut_off // 4), device=dev)
+        edges = self._buf("edges", cap * self.WE + 4, slack=1.15)
         aux = self._buf("aux", cap, torch.uint8, slack=1.15)
-        mul_hist = torch.zeros(65536, dtype=torch.int64, device=dev)
-        nsol = torch.zeros(8, dtype=torch.int64, device=dev)
+        mul_hist = self._buf("mul_hist", 65536, torch.int64)[:65536]
+        mul_hist.zero_()
+        nsol = self._buf("nsol", 8, torch.int64)[:8]
+        nsol.zero_()
         scratch = self._buf("c_scratch", L.mhb_count_solid_scratch_bytes(n_own), torch.uint8, slack=1.15)
         lib._check(L.mhb_count_solid(_stream(), C.c_void_p(srt), n_own, k, m, _ptr(edges), _ptr(aux), cap, _ptr(mul_hist),
                                      _ptr(nsol), _ptr(scratch), scratch.numel()))
-        n_solid = int(nsol[0].item())
         dist.all_reduce(mul_hist)  # edge_counter.h:44-52: `.counting` is a global histogram
+        n_solid = int(self._to_host(nsol[:1])[0])
+        if n_solid > cap:
+            raise lib.MhbError("internal: solid edges exceed capacity")
+        n_tip = int((aux[:n_solid] != 0).sum().item()) if (self.need_mercy and n_solid) else 0
         if timed:
             self._mark("count")
 
-        # ---- mercy: tip edges from every rank -> per-read marks -> candidates -> mercy edges ----
-        n_mercy = 0
-        n_cand = 0
-        if self.need_mercy:
-            e2 = edges[: n_solid * self.WE].view(-1, self.WE)
-            tipmask = aux[:n_solid] != 0
-            tips, tipaux = e2[tipmask].contiguous(), aux[:n_solid][tipmask].contiguous()
-            lib._check(L.mhb_edge_lut_build(_stream(), C.c_void_p(pe.ptr), n_solid, k, C.c_void_p(pe.ptr + lut_off)))
-            cnt = torch.tensor([tips.shape[0], n_solid], dtype=torch.int64, device=dev)
-            allcnt = [torch.zeros_like(cnt) for _ in range(self.world)]
-            dist.all_gather(allcnt, cnt)  # also orders: every rank's solid edges are complete from here on
-            tip_n = [int(c[0].item()) for c in allcnt]
-            sol_n = [int(c[1].item()) for c in allcnt]
-            mx = max(max(tip_n), 1)
-            pad_t = torch.zeros((mx, self.WE), **i32)
-            pad_a = torch.zeros(mx, dtype=torch.uint8, device=dev)
-            pad_t[: tips.shape[0]] = tips
-            pad_a[: tips.shape[0]] = tipaux
-            gt = [torch.empty_like(pad_t) for _ in range(self.world)]
-            ga = [torch.empty_like(pad_a) for _ in range(self.world)]
-            dist.all_gather(gt, pad_t)
-            dist.all_gather(ga, pad_a)
-            all_t = torch.cat([g[:c] for g, c in zip(gt, tip_n)]).contiguous()
-            all_a = torch.cat([g[:c] for g, c in zip(ga, tip_n)]).contiguous()
-            n_tip = int(all_t.shape[0])
-            need = L.mhb_tipset_bytes(n_tip, k)
-            tipset = self._buf("tipset", need, torch.uint8, slack=1.2)
-            lib._check(L.mhb_tipset_build(_stream(), _ptr(all_t) if n_tip else None, _ptr(all_a) if n_tip else None,
-                                          n_tip, k, _ptr(tipset), need, n_tip))
-            first = self._buf("first", self.n_reads + 1)
-            last = self._buf("last", self.n_reads + 1)
-            lib._check(L.mhb_count_mark_mercy(_stream(), C.byref(reads), k, _ptr(tipset), need, n_tip, _ptr(first),
-                                              _ptr(last)))
-            cand = self._buf("cand", self.n_reads + 1, torch.int64)
-            cs = self._buf("cand_scratch", L.mhb_mercy_candidates_scratch_bytes(self.n_reads), torch.uint8)
-            nc = C.c_uint64(0)
-            lib._check(L.mhb_mercy_candidates(_stream(), _ptr(first), _ptr(last), self.n_reads, _ptr(cand), C.byref(nc),
-                                              _ptr(cs), cs.numel()))
-            n_cand = nc.value
-            nm = C.c_uint64(0)
-            if n_cand:
-                seg_p = (C.c_void_p * self.world)(*[C.c_void_p(q) for q in pe.peers])
-                seg_n = (C.c_uint64 * self.world)(*sol_n)
-                seg_l = (C.c_void_p * self.world)(*[C.c_void_p(q + lut_off) for q in pe.peers])
-                lut = np.zeros(256, np.uint8)
-                for o in range(self.world):
-                    lut[int(bounds[o]):int(bounds[o + 1])] = o
-                lut_c = (C.c_uint8 * 256)(*lut.tolist())
-                ms = self._buf("mercy_scratch", L.mhb_mercy_edges_scratch_bytes(n_cand, self.read_len) - lut_bytes,
-                               torch.uint8, slack=1.2)
-                # mercy edges are appended right behind this rank's solid edges (peers only read the solid part)
-                lib._check(L.mhb_mercy_edges_segs(_stream(), C.byref(reads), _ptr(cand), n_cand, self.read_len, k, self.world,
-                                                  seg_p, seg_n, seg_l, lut_c, C.c_void_p(pe.ptr + n_solid * self.WE * 4),
-                                                  cap - n_solid, C.byref(nm), _ptr(ms), ms.numel()))
-            n_mercy = nm.value
+        # ---- mercy ----
+        n_mercy = n_cand = 0
         seq_edges = edges
+        if self.need_mercy:
+            seq_edges, n_cand, n_mercy = self._mercy(reads, bin_dev, edges, aux, n_solid, n_tip, owner)
         if timed:
             self._mark("mercy")
 
@@ -332,24 +376,27 @@ class MultiGpuBuild:
         n_items = n_seqs * 6
         seqs = lib.DevSeqs(seq_edges.data_ptr(), n_seqs * self.WE, n_seqs, k + 1, None, None, None, None, self.WE)
         sa = self._buf("s_a", n_items * self.W2 + 4, slack=1.1)
-        hist2 = torch.zeros(256, dtype=torch.int64, device=dev)
+        hist2 = self._buf("s_hist", 256, torch.int64)[:256]
+        hist2.zero_()
         top2 = self.sbytes[-1]
         lib._check(L.mhb_s2s_extract(_stream(), C.byref(seqs), k, _ptr(sa), n_items, _ptr(hist2), top2))
-        own2, n_own2, bounds2 = self._partition_and_exchange(sa, n_items, self.W2, top2, hist2, "s")
+        own2, n_own2, bounds2, _ = self._partition_and_exchange(sa, n_items, self.W2, top2, hist2, "s", max(n_items, 1))
         if timed:
             self._mark("exchange2")
         srt2 = self._sort_raw(own2, n_own2, self.W2, self.sbytes, "s")
         wpt = (k + 15) // 16
         cap_b = n_own2 * (4 + 4 * wpt) + 16
         out_bytes = self._buf("sdbg", cap_b, torch.uint8, slack=1.1)
-        table = torch.zeros(65536 * 4, dtype=torch.int64, device=dev)
-        totals = torch.zeros(16, dtype=torch.int64, device=dev)
+        table = self._buf("table", 65536 * 4, torch.int64)[: 65536 * 4]
+        table.zero_()
+        totals = self._buf("totals", 16, torch.int64)[:16]
+        totals.zero_()
         es = self._buf("s_scratch", L.mhb_s2s_emit_scratch_bytes(n_own2, k), torch.uint8, slack=1.1)
         lib._check(L.mhb_s2s_emit(_stream(), C.c_void_p(srt2), n_own2, k, _ptr(out_bytes), cap_b, _ptr(table), _ptr(totals),
                                   _ptr(es), es.numel()))
         if timed:
             self._mark("s2s")
-        return {"n_solid": n_solid, "n_cand": n_cand, "n_mercy": n_mercy, "edges": edges, "mul_hist": mul_hist,
+        return {"n_solid": n_solid, "n_cand": n_cand, "n_mercy": n_mercy, "edges": seq_edges, "mul_hist": mul_hist,
                 "bounds": bounds, "bounds2": bounds2, "n_items_sorted": n_own2, "sdbg_bytes": out_bytes, "table": table,
                 "totals": totals, "n_records_owned": n_own}
 
@@ -368,6 +415,138 @@ def gather_sdbg_stream(res: dict) -> bytes | None:
     return b"".join(o[1] for o in objs)  # rank order == bucket order
 
 
+def _reverse_rows(rows: np.ndarray, read_len: int) -> np.ndarray:
+    """`.bin` records (u32 length + packed words) of fixed-length reads -> the same reads reversed (no complement), the
+    orientation KmerCounter holds them in and writes to `.cand` (sequence_package.h:284-295, kmer_counter.cpp:387-401)"""
+    from . import formats as F
+    n = len(rows)
+    if n == 0:
+        return rows.reshape(0, 1 + (read_len + 15) // 16)
+    w = rows[:, 1:].astype(np.uint32)
+    idx = np.arange(read_len)
+    bases = ((w[:, idx >> 4] >> (30 - 2 * (idx & 15)).astype(np.uint32)) & 3).astype(np.uint8)
+    return F.pack_reads_fixed(bases[:, ::-1])
+
+
+def write_outputs(job: "MultiGpuBuild", res: dict, my_rows: np.ndarray, prefix: str) -> None:
+    """The reference's on-disk outputs from a partitioned build (collective): rank r writes `P.edges.<r>` and `P.sdbg.<r>`
+    - its contiguous range of the 65 536 buckets, each bucket one contiguous run in exactly one file - and rank 0 the
+    merged `P.edges.info` (edge_io_meta.h:25-44: bucket -> file, offset in edges, count), `P.sdbg_info`
+    (sdbg_meta.cpp:44-61: records ordered by (file, starting offset), unused ones last), `P.cand` and `P.counting`.
+    num_files = world; the consumers are the reference's own readers (edge_reader.h, sdbg_raw_content.cpp:18-95)."""
+    world, rank, k, WE = job.world, job.rank, job.k, job.WE
+    n_solid = res["n_solid"]
+    torch.cuda.synchronize()
+    e = res["edges"][: n_solid * WE].cpu().numpy().view(np.uint32).reshape(-1, WE)
+    e.tofile(f"{prefix}.edges.{rank}")
+    ecnt = np.bincount((e[:, 0] >> 16).astype(np.int64), minlength=65536).astype(np.int64) if n_solid else np.zeros(65536, np.int64)
+    tot = res["totals"].cpu().numpy()
+    nbytes = int(tot[0])
+    res["sdbg_bytes"][:nbytes].cpu().numpy().tofile(f"{prefix}.sdbg.{rank}")
+    table = res["table"].cpu().numpy().view(np.uint64).reshape(65536, 4)
+    cand_ids = job._bufs["cand"][: res["n_cand"]].cpu().numpy() if res["n_cand"] else np.zeros(0, np.int64)
+    cand = _reverse_rows(my_rows[cand_ids], job.read_len).tobytes() if len(cand_ids) else b""
+    objs = [None] * world
+    dist.all_gather_object(objs, (ecnt, table, cand))
+    if rank == 0:
+        with open(prefix + ".edges.info", "w") as f:
+            n_edges = int(sum(int(o[0].sum()) for o in objs))
+            f.write(f"kmer_size {k}\nwords_per_edge {WE}\nnum_files {world}\nnum_buckets 65536\nnum_edges {n_edges}\nis_sorted 1\n")
+            off = [np.concatenate([[0], np.cumsum(o[0])[:-1]]) for o in objs]
+            owner_of = np.full(65536, -1, np.int64)
+            for r, o in enumerate(objs):
+                assert (owner_of[o[0] > 0] == -1).all(), "a bucket landed on two ranks"
+                owner_of[o[0] > 0] = r
+            for b in range(65536):
+                r = owner_of[b]
+                f.write(f"{b} -1 0 0\n" if r < 0 else f"{b} {r} {int(off[r][b])} {int(objs[r][0][b])}\n")
+        with open(prefix + ".sdbg_info", "w") as f:
+            wpt = (k + 15) // 16
+            f.write(f"k {k}\nwords_per_tip_label {wpt}\nnum_buckets 65536\nnum_files {world}\n")
+            used = 0
+            for r, o in enumerate(objs):  # rank order, and inside a rank ascending buckets = ascending offsets
+                t = o[1]
+                for b in np.nonzero(t[:, 1])[0]:
+                    f.write(f"{int(b)} {r} {int(t[b, 0])} {int(t[b, 1])} {int(t[b, 2])} {int(t[b, 3])}\n")
+                    used += 1
+            for _ in range(65536 - used):
+                f.write("18446744073709551615 18446744073709551615 0 0 0 0\n")
+        with open(prefix + ".cand", "wb") as f:
+            for o in objs:  # reads are dealt to the ranks in contiguous blocks: rank order = read order
+                f.write(o[2])
+        cnt = res["mul_hist"].cpu().numpy()
+        with open(prefix + ".counting", "w") as f:
+            f.write("".join(f"{i} {int(cnt[i])}\n" for i in range(1, 65536)))
+    dist.barrier()
+
+
+PARITY_CASES = (("syn150_k27", 27), ("syn150_klist", 21), ("syn150_klist", 141), ("polya_k27", 27), ("tandem_k27", 28),
+                ("lowcov_k21", 21))
+
+
+def parity_check(device, cases=PARITY_CASES, verbose=False, files_dir=None) -> dict:
+    """Bit-exactness of the partitioned build at the current world size: for every golden case (fixtures minted by the
+    unmodified reference, tests/golden) the reads are dealt to the ranks in contiguous blocks, MultiGpuBuild runs its
+    normal fused path, and the rank-ordered concatenation of the solid edges, the `.counting` histogram and the
+    canonical SdBG stream must reproduce the reference's sha256 digests.  Collective; returns the verdict on every rank."""
+    import json
+    import os
+    from . import formats as F
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    world, rank = dist.get_world_size(), dist.get_rank()
+    out = {"world": world, "cases": [], "ok": True}
+    for name, k in cases:
+        case = os.path.join(root, "tests", "golden", name)
+        gold = json.load(open(os.path.join(case, "golden.json")))
+        g, m = gold["by_k"][str(k)], gold["m"]
+        allw = np.fromfile(os.path.join(case, "reads.lib.bin"), np.uint32)
+        rl = int(allw[0])
+        stride = 1 + (rl + 15) // 16
+        rows = allw.reshape(-1, stride)
+        per = (len(rows) + world - 1) // world
+        mine = rows[rank * per:(rank + 1) * per]
+        bin_dev = torch.from_numpy(np.concatenate([mine.reshape(-1), np.zeros(8, np.uint32)]).view(np.int32)).to(device)
+        job = MultiGpuBuild(len(mine), rl, k, m, device, need_mercy=True)
+        res = job.run(bin_dev)
+        stream = gather_sdbg_stream(res)
+        torch.cuda.synchronize()
+        edges = res["edges"][: res["n_solid"] * job.WE].cpu().numpy().view(np.uint32).tobytes()
+        objs = [None] * world
+        dist.all_gather_object(objs, (edges, res["n_solid"], res["n_cand"], res["n_mercy"]))
+        verdict = [None]
+        if rank == 0:
+            cnt = res["mul_hist"].cpu().numpy()
+            v = {"case": f"{name}-k{k}",
+                 "edges": g["n_solid"] == 0 or F.sha256(b"".join(o[0] for o in objs)) == g["edges_sha256"],
+                 "counting": F.sha256("".join(f"{i} {int(cnt[i])}\n" for i in range(1, 65536)).encode()) == g["counting_sha256"],
+                 "sdbg": F.sha256(stream) == g["sdbg_sha256"],
+                 "n_solid": [int(o[1]) for o in objs], "n_mercy": [int(o[3]) for o in objs]}
+            v["ok"] = bool(v["edges"] and v["counting"] and v["sdbg"])
+            verdict[0] = v
+            if verbose:
+                print("parity", v, flush=True)
+        if files_dir is not None:
+            # file level: every rank writes its own `.edges.<r>` / `.sdbg.<r>`; the canonical streams read back through the
+            # bucket tables (formats.py, the reference's reader order) must give the same digests
+            prefix = os.path.join(files_dir, f"{name}_k{k}_n{world}")
+            write_outputs(job, res, mine, prefix)
+            if rank == 0:
+                v = verdict[0]
+                ce = F.canonical_edges(prefix)
+                info, cs, _ = F.canonical_sdbg(prefix)
+                v["files"] = bool((g["n_solid"] == 0 or F.sha256(ce.tobytes()) == g["edges_sha256"])
+                                  and F.sha256(cs) == g["sdbg_sha256"] and F.file_sha256(prefix + ".cand") == g["cand_sha256"]
+                                  and F.file_sha256(prefix + ".counting") == g["counting_sha256"] and info.num_files == world)
+                v["prefix"] = prefix
+                v["ok"] = bool(v["ok"] and v["files"])
+        dist.broadcast_object_list(verdict, src=0)
+        out["cases"].append(verdict[0])
+        out["ok"] = out["ok"] and verdict[0]["ok"]
+        job.close()
+        del job, res, bin_dev
+    return out
+
+
 def bench(args, bin_dev, bin_words, rank, world, device, metric, clocks=None):
     """bench.py's N > 1 arm: weak scaling, `args.reads` reads per GPU, one all-to-all per stage."""
     import json
@@ -375,6 +554,8 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric, clocks=None):
     import sys
 
     k, m, n_reads, L = args.k, args.m, args.reads, 150
+    # correctness anchor of every N > 1 number: the same fused path on the reference-minted fixtures, before timing
+    parity = parity_check(device)
     job = MultiGpuBuild(n_reads, L, k, m, device, need_mercy=True)
     for _ in range(max(1, args.warmup)):
         job.run(bin_dev)
@@ -387,6 +568,7 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric, clocks=None):
     e0.record()
     res = None
     pass_ms = []
+    launches0 = lib.launch_count()
     for _ in range(args.steps):
         res = job.run(bin_dev, timed=True)
         # the most recent traced sort over count-width records of this rank's owned count = this step's sort1 (the
@@ -399,14 +581,14 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric, clocks=None):
         else:
             pass_ms.append(lib.sort_pass_ms(1)[0])  # fused mode: [sort1, sort2] per step
     e1.record()
+    launches = (lib.launch_count() - launches0) // max(1, args.steps)
     torch.cuda.synchronize()
     dist.barrier()
     clk = clocks.stop() if clocks is not None else None
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=device)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     stage = {}
-    names = ["t0", "extract", "c_plan", "c_partition", "c_counts", "exchange1", "sort1", "count", "mercy", "s_plan",
-             "s_partition", "s_counts", "exchange2", "s2s"]
+    names = ["t0", "extract", "c_plan", "exchange1", "sort1", "count", "mercy", "s_plan", "exchange2", "s2s"]
     for a, b in zip(names[:-1], names[1:]):
         t = torch.tensor([np.mean([x.elapsed_time(y) for x, y in zip(job.times[a], job.times[b])])], dtype=torch.float64,
                          device=device)
@@ -474,14 +656,19 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric, clocks=None):
                          "peak_source": src, "avg_launch_ms": float(pm.item()),
                          "algorithmic_bytes_per_launch": 2 * n_max * S},
             "cpu_baseline": None, "clocks": clk,
+            "parity": {"ok": parity["ok"], "world": world, "against": "sha256 digests minted by the unmodified reference "
+                       "(tests/golden): edges, .counting, canonical SdBG stream",
+                       "cases": [{kk: c[kk] for kk in ("case", "edges", "counting", "sdbg")} for c in parity["cases"]]},
             "e2e": {"value": e2e_v, "unit": "edges/s", "h2d_bytes_per_step": int(world * bin_words * 4),
                     "d2h_bytes_per_step": int(nbytes.item()) + world * 65536 * 32, "ms_per_step": float(np.mean(e2e_ms)),
                     "api": "MultiGpuBuild.run on reads copied from pinned host memory each step; SdBG bytes + bucket "
                            "table copied back to pinned host memory"},
-            "gpu_launches": 60,
+            "gpu_launches": int(launches),
         }))
     sys.stdout.flush()
     torch.cuda.synchronize()
     job.close()
     dist.barrier()
     dist.destroy_process_group()
+    if not parity["ok"]:
+        raise SystemExit("multi-GPU parity check FAILED: " + json.dumps(parity["cases"]))
