@@ -127,6 +127,21 @@ def reference_run(n_reads: int, k: int, m: int, threads: int, seed: int = 1234):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def cpu_info():
+    """CPU model / sockets / NUMA nodes of the box the CPU arm runs on (the arm varied 3x between boxes in round 1)"""
+    info = {"logical_cpus": os.cpu_count()}
+    try:
+        txt = open("/proc/cpuinfo").read()
+        models = [l.split(":", 1)[1].strip() for l in txt.splitlines() if l.startswith("model name")]
+        info["model"] = models[0] if models else None
+        info["sockets"] = len({l.split(":", 1)[1].strip() for l in txt.splitlines() if l.startswith("physical id")}) or None
+        info["numa_nodes"] = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])
+        info["loadavg_1m"] = float(open("/proc/loadavg").read().split()[0])
+    except Exception:
+        pass
+    return info
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -135,7 +150,7 @@ def reference_arm(args):
     sample = args.sample_reads
     times = []
     for i in range(args.warmup + args.steps):
-        r = reference_run(sample, args.k, args.m, threads, seed=1234 + i)
+        r = reference_run(sample, args.k, args.m, threads, seed=1234)  # the same library every step
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/megahit_core_ref was not built"}))
             return
@@ -144,13 +159,14 @@ def reference_arm(args):
     n_edges = sample * (READ_LEN - args.k)
     t = float(np.mean(times))
     v = n_edges / t
-    desc = f"{sample} synthetic 150 bp reads/step, count+seq2sdbg --need_mercy, mem_flag 1"
+    desc = f"{sample} synthetic 150 bp reads/step (seed 1234), count+seq2sdbg --need_mercy, mem_flag 1"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "edges/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": f"reference megahit_core count+seq2sdbg k={args.k} m={args.m} on host cores", "sample": desc},
-        "cpu_baseline": {"value": v, "unit": "edges/s", "cores": threads, "kind": "reference", "sample": desc},
+        "cpu_baseline": {"value": v, "unit": "edges/s", "cores": threads, "kind": "reference", "sample": desc,
+                         "step_times_s": [round(x, 3) for x in times], "cpu": cpu_info()},
         "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -187,7 +203,7 @@ def ours(args):
         from megahit_b200 import multigpu
         return multigpu.bench(args, bin_dev, bin_words, rank, world, device, METRIC, clocks=ClockSampler(local))
 
-    plan = dev.CountPlan(n_reads, L, k, m, device, want_mercy=True)
+    plan = dev.CountPlan(n_reads, L, k, m, device, want_mercy=True, mode=args.count_mode)
     n_solid = plan.run(bin_dev)  # sizes the SdBG stage (also the first warm-up)
     s2s = dev.S2sPlan(int(n_solid * 1.05) + 1024, k + 1, k, device)
 
@@ -225,6 +241,10 @@ def ours(args):
     stage = {}
     for a, b in (("t0", "extract"), ("extract", "sort"), ("sort", "count"), ("count", "mercy")):
         stage[b] = float(np.mean([x.elapsed_time(y) for x, y in zip(ev[a], ev[b])]))
+    if plan.hashed:
+        # the two partition passes run inside the count call: split the stage with their own event times
+        p_ms = float(np.mean([sum(x) for x in sort_ms["count"]]))
+        stage["sort"], stage["count"] = p_ms, stage["count"] - p_ms
 
     for i, nm in enumerate(("s2s_extract", "s2s_sort", "s2s_emit")):
         stage[nm] = float(np.mean([e[i].elapsed_time(e[i + 1]) for e in s2s.events]))
@@ -256,7 +276,7 @@ def ours(args):
         M_items, W2 = int(n_items), s2s.W
         alg = {
             "extract": n_edges * S + bin_words * 4,                      # records written + packed reads read
-            "sort": len(plan.sort_bytes) * 2 * n_edges * S,
+            "sort": (2 if plan.hashed else len(plan.sort_bytes)) * 2 * n_edges * S,
             "count": n_edges * S + E * (WE * 4 + 1),                     # sorted records read + edges and flags written
             "mercy": bin_words * 4,                                      # reads re-scanned against the tip set
             "s2s_extract": E * WE * 4 + M_items * W2 * 4,
@@ -270,6 +290,8 @@ def ours(args):
     except Exception as e:  # pragma: no cover
         stage_roofline = {"error": str(e)}
 
+    count_mode = ("hashed: 2 radix passes on the leading key bytes (the 16-bit bucket id) + per-bucket hash aggregation in "
+                  "shared memory" if plan.hashed else "sort: LSD radix sort on all key bytes + run-length count")
     # ---- e2e: host buffers through the C ABI (fused build), H2D/D2H copies inside the timed region ----
     host_bin = torch.empty(bin_words, dtype=torch.int32).pin_memory()
     host_bin.copy_(bin_dev[:bin_words])
@@ -294,12 +316,15 @@ def ours(args):
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        r = reference_run(args.sample_reads, k, m, threads)
-        if r:
+        runs = [reference_run(args.sample_reads, k, m, threads) for _ in range(3)]  # same library, three times: median
+        if all(runs):
+            runs.sort(key=lambda r: r["t_count"] + r["t_s2s"])
+            r = runs[1]
             cpu = {"value": r["n_edges"] / (r["t_count"] + r["t_s2s"]), "unit": "edges/s", "cores": threads,
                    "kind": "reference",
-                   "sample": f"{args.sample_reads} synthetic 150 bp reads, megahit_core count+seq2sdbg --need_mercy "
-                             f"(count {r['t_count']:.2f} s, seq2sdbg {r['t_s2s']:.2f} s)"}
+                   "sample": f"{args.sample_reads} synthetic 150 bp reads (seed 1234), megahit_core count+seq2sdbg --need_mercy, "
+                             f"median of 3 runs (count {r['t_count']:.2f} s, seq2sdbg {r['t_s2s']:.2f} s)",
+                   "run_times_s": [round(x["t_count"] + x["t_s2s"], 3) for x in runs], "cpu": cpu_info()}
 
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -307,7 +332,8 @@ def ours(args):
         "data": "synthetic",
         "config": {"workload": f"synthetic {n_reads}x{L}bp reads (30x, 1% subst.), k={k}, m={m}, 1xB200 single-GPU "
                                "sdbg_build: count (extract+radix+solid count+mercy marks) + seq2sdbg (extract+radix+emit) "
-                               "on the solid edges; mercy-edge generation (host) not in the device step",
+                               "on the solid edges; mercy-edge generation is in e2e, not in the device step",
+                   "count_mode": count_mode,
                    "n_edge_records": n_edges, "n_solid_edges": int(n_solid), "n_sdbg_sort_items": int(n_items),
                    "l2_note": "inputs (>= 4.9 GB per kernel) exceed the 126 MB L2, no explicit flush needed"},
         "stage_ms": stage, "stage_roofline": stage_roofline,
@@ -331,6 +357,8 @@ def main():
     ap.add_argument("--sample-reads", type=int, default=1_000_000, help="bounded CPU sample (reference arm / cpu_baseline)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--count-mode", default=None, choices=["sort", "hashed", "auto"],
+                    help="count stage algorithm (default: $MHB_COUNT_MODE, else hashed where supported)")
     args = ap.parse_args()
     if args.impl == "reference":
         # exactly K timed + W warm-up steps; the per-step sample is sized so the whole run stays within minutes

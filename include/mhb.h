@@ -160,6 +160,19 @@ int mhb_count_solid(void *stream, const uint32_t *sorted_records, uint64_t n, ui
                     uint32_t *edges_out, uint8_t *aux_out, uint64_t capacity_edges, uint64_t *mul_hist,
                     uint64_t *n_solid_out, void *scratch, size_t scratch_bytes);
 
+/* A4 + A5 without the full sort, for 8-byte count records (11 <= k <= 28) and 1 <= m <= 1024: the records are grouped
+ * by their leading 24 key bits with three radix passes (record bytes 5, 6, 7), cut into key-closed slices inside the
+ * reference's 16-bit buckets, and every slice is aggregated by a hash table in shared memory - occurrence counts,
+ * prev/next tallies of the keys that reach m, a counting sort of the slice's solid keys.  Same outputs, bit for bit,
+ * as mhb_sort_records on all key bytes followed by mhb_count_solid, for under half of the memory traffic.  recs_a holds
+ * the n extracted records (any order) and recs_b is a same-sized buffer; both are clobbered.  hist_byte5 = histogram
+ * of record byte 5 (from mhb_count_extract) or NULL.  mul_hist / n_solid_out caller-zeroed as for mhb_count_solid.  ws = mhb_count_hashed_workspace_bytes(). */
+int mhb_count_hashed_supported(uint32_t k, int32_t m);
+size_t mhb_count_hashed_workspace_bytes(uint64_t n, uint32_t k, int32_t m);
+int mhb_count_solid_hashed(void *stream, uint32_t *recs_a, uint32_t *recs_b, uint64_t n, uint32_t k, int32_t m,
+                           const uint64_t *hist_byte5, uint32_t *edges_out, uint8_t *aux_out, uint64_t capacity_edges,
+                           uint64_t *mul_hist, uint64_t *n_solid_out, void *ws, size_t ws_bytes);
+
 /* A5 (mercy bookkeeping, kmer_counter.cpp:307-367): for every read, first_0_out / last_0_in exactly as
  * KmerCounter leaves them.  tips = hash set built by mhb_tipset_build from the solid edges whose aux
  * flags are non-zero. */

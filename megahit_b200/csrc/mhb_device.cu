@@ -141,7 +141,7 @@ extern "C" int mhb_count_extract(void *stream, const mhb_dev_reads *reads, uint3
   const u32 W = count_key_words(k), WR = count_record_words(k);
   const u64 n_batches = (rv.n_reads + kReadsPerBatch - 1) / kReadsPerBatch;
   const int grid = (int)(n_batches < (u64)(sm_count() * 8) ? n_batches : (u64)(sm_count() * 8));
-  static const bool roll = getenv("MHB_EXTRACT_ROLL") != nullptr;  // opt-in rolling builder (8-byte records)
+  static const bool roll = getenv("MHB_EXTRACT_ROLL") && !strcmp(getenv("MHB_EXTRACT_ROLL"), "1");  // opt-in (no gain measured)
   if (roll && W == 2 && WR == 2 && k + 1 >= 17) {
     k_count_extract_roll<<<grid, kExtractThreads, 0, st>>>(rv, k, records, hist256, hist_byte);
     CK_LAUNCH();
@@ -337,7 +337,9 @@ extern "C" int mhb_count_mark_mercy(void *stream, const mhb_dev_reads *reads, ui
   u64 g64 = (rv.n_reads + 7) / 8;
   if (g64 > (u64)sm_count() * 16) g64 = (u64)sm_count() * 16;
   const int grid = (int)g64;
-  static const bool roll = getenv("MHB_EXTRACT_ROLL") != nullptr;
+  // rolling record builder (4 positions per lane, three of them by shifting): 6.5 vs 7.4 ms on the bench workload
+  // (profiles/r2a_bench_roll.json); MHB_EXTRACT_ROLL=0 selects the per-position kernel
+  static const bool roll = !(getenv("MHB_EXTRACT_ROLL") && !strcmp(getenv("MHB_EXTRACT_ROLL"), "0"));
   if (roll && W == 2 && WR == 2 && k + 1 >= 17) {
     k_mark_mercy_roll<<<grid, 256, 0, st>>>(rv, k, filter, fwords, table, cap, first_0_out, last_0_in);
     CK_LAUNCH();

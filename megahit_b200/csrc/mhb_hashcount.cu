@@ -1,0 +1,577 @@
+// mhb_hashcount.cu -- solid-edge counting by radix PARTITION + per-bucket HASH AGGREGATION (A4 + A5 for 8-byte count
+// records, i.e. k <= 28), an alternative to "sort all records by all 7 key bytes, then run-length count".
+//
+// Why: the run-length count (kmer_counter.cpp:254-305) needs equal (k+1)-mers to meet, not a total order of the 1.23 G
+// records; only the SOLID edges (5 % of the distinct ones on the bench workload) have to come out sorted.  So:
+//   1. three stable radix passes on the three leading key bytes (the same k_radix_pass3 the sort uses) group the
+//      records by their leading 24 key bits - 3 x 2NS bytes instead of 7 x 2NS;
+//   2. k_bucket_bounds finds the 65 537 boundaries of the reference's 16-bit buckets (base_engine.h kNumBuckets) by
+//      binary search, and every bucket is cut into slices of ~6000 records whose boundaries are moved to the next
+//      change of the 24-bit prefix: a slice is contiguous and key-closed;
+//   3. k_hash_count: a CTA takes a slice and aggregates it in a shared-memory open-addressing table keyed by the
+//      remaining 42 record bits: occurrence counts first, then, for the keys that reached the solid threshold, the
+//      4 + 4 prev/next tallies (has_in / has_out, :279-305) in a second sweep over the same records (L2 hits); the solid
+//      keys of the slice (a few hundred) are ordered by a counting sort in shared memory and appended to the slice's
+//      area of a scratch list.  A slice with more distinct keys than the table holds is split into four key
+//      sub-ranges, recursively (the slice is re-streamed per sub-range) - correctness never depends on the key
+//      distribution, only speed does;
+//   4. a scan over the per-slice solid counts + k_hash_gather write the `.edges`-format records (PackEdge, :32-52),
+//      the aux flags and the multiplicity histogram exactly as mhb_count_solid does.
+// Output is bit-identical to sort + mhb_count_solid (tests/test_gpu_parity.py).  HBM traffic of the count stage falls
+// from (7 x 2 + 1) NS to (3 x 2 + 1) NS bytes.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "mhb.h"
+#include "mhb_common.cuh"
+#include "mhb_count.cuh"
+
+using namespace mhb;
+
+namespace {
+
+constexpr int kHcThreads = 512;
+constexpr int kHcSlots = 4096;                 // hash slots per CTA (power of two)
+constexpr int kHcMaxSolid = 1024;              // solid keys per sub-range (sort buffer)
+constexpr int kHcHist = 1024;                  // multiplicities < kHcHist are histogrammed in shared memory
+constexpr u64 kHcEmpty = ~0ull;
+constexpr u32 kHcSolidFlag = 0x80000000u;
+constexpr int kHcBatch = 4;                    // records per thread in flight while streaming a bucket
+constexpr u32 kRemBits = 42;                   // record bits 47..6
+
+__device__ __forceinline__ u64 rec_key64(const uint2 r) { return ((u64)r.x << 32) | r.y; }
+__device__ __forceinline__ u32 hc_hash(u64 r) { return (u32)((r * 0x9E3779B97F4A7C15ull) >> (64 - 12)); }
+
+// bounds[b] = first record whose 16-bit prefix is >= b (b = 0..65536); the records are sorted on that prefix
+__global__ void k_bucket_bounds(const uint2 *__restrict__ recs, u64 n, u64 *__restrict__ bounds) {
+  const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > 65536u) return;
+  u64 lo = 0, hi = n;
+  while (lo < hi) {
+    const u64 mid = (lo + hi) >> 1;
+    if ((recs[mid].x >> 16) < b) lo = mid + 1;
+    else hi = mid;
+  }
+  bounds[b] = lo;
+}
+
+constexpr int kHcCells = 1024;                 // counting-sort cells that order a sub-range's solid keys
+constexpr int kHcMaxOcc = 2900;                // occupied slots per sub-range (load factor 0.7)
+constexpr int kHcMaxProbes = 96;
+constexpr int kHcStack = 72;
+
+struct HcShared {
+  u64 keys[kHcSlots];
+  u32 cnt[kHcSlots];
+  uint16_t rk[kHcSlots];       // rank of a solid slot inside its sub-range
+  uint16_t occ[kHcSlots];      // dense list of the occupied slots (judged and cleared through it)
+  u32 tally[kHcMaxSolid][4];   // prev01, prev23, next01, next23 as 16-bit fields; re-used as u64 tmp[] while ordering
+  u64 sorted[kHcMaxSolid];     // rem42 << 22 | cnt16 << 6 | aux
+  u32 cell_base[kHcCells];
+  u32 cell_cur[kHcCells];
+  u32 cta_hist[kHcHist];
+  u64 st_prefix[kHcStack];
+  u32 st_bits[kHcStack];
+  u32 warp_sum[kHcThreads / 32];
+  u32 n_occ, n_solid, overflow, bucket, out_cursor, sp;
+};
+
+__device__ __forceinline__ u32 lane_lt_mask() { return (1u << (threadIdx.x & 31)) - 1u; }
+
+// slot of key r, inserting it when absent (new slots are appended to the dense list with one warp-aggregated atomic).
+// Returns kHcSlots when the probe sequence gets too long: the sub-range holds too many distinct keys for the table.
+__device__ __forceinline__ u32 hc_insert(HcShared &s, u64 r) {
+  u32 h = hc_hash(r);
+  for (int probes = 0; probes < kHcMaxProbes; ++probes) {
+    u64 cur = s.keys[h];
+    if (cur == r) return h;
+    if (cur == kHcEmpty) {
+      cur = atomicCAS((unsigned long long *)&s.keys[h], kHcEmpty, r);
+      if (cur == kHcEmpty) {
+        const u32 am = __activemask();
+        const int leader = __ffs(am) - 1;
+        u32 basep = 0;
+        if ((int)(threadIdx.x & 31) == leader) basep = atomicAdd(&s.n_occ, (u32)__popc(am));
+        basep = __shfl_sync(am, basep, leader);
+        const u32 pos = basep + __popc(am & lane_lt_mask());
+        if (pos < (u32)kHcSlots) s.occ[pos] = (uint16_t)h;
+        return h;
+      }
+      if (cur == r) return h;
+    }
+    h = (h + 1) & (kHcSlots - 1);
+  }
+  return kHcSlots;
+}
+__device__ __forceinline__ u32 hc_find(const HcShared &s, u64 r) {
+  u32 h = hc_hash(r);
+  while (s.keys[h] != r) h = (h + 1) & (kHcSlots - 1);
+  return h;
+}
+
+// multiplicity histogram contribution (+1 / -1) of the occupied slots; the singletons and doubletons of a sub-range
+// would serialise on one shared-memory counter, so they are counted with ballots
+__device__ __forceinline__ void hc_hist_update(HcShared &s, u32 n_occ, u64 *mul_hist, bool add) {
+  for (u32 i0 = 0; i0 < n_occ; i0 += kHcThreads) {
+    const u32 i = i0 + threadIdx.x;
+    const bool on = i < n_occ;
+    const u32 c = on ? s.cnt[s.occ[i]] : 0u;
+    const u32 c16 = c > 65535u ? 65535u : c;
+    const u32 ones = __ballot_sync(0xffffffffu, on && c16 == 1u), twos = __ballot_sync(0xffffffffu, on && c16 == 2u);
+    const u32 d = add ? 1u : 0xFFFFFFFFu;
+    if (on && c16 > 2u) {
+      if (c16 < (u32)kHcHist) atomicAdd(&s.cta_hist[c16], d);
+      else atomicAdd((unsigned long long *)&mul_hist[c16], add ? 1ull : ~0ull);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (ones) atomicAdd(&s.cta_hist[1], add ? (u32)__popc(ones) : 0u - (u32)__popc(ones));
+      if (twos) atomicAdd(&s.cta_hist[2], add ? (u32)__popc(twos) : 0u - (u32)__popc(twos));
+    }
+  }
+}
+
+// exclusive scan of s.cell_base[0 .. kHcCells) in place (kHcCells = 2 * kHcThreads)
+__device__ __forceinline__ void hc_scan_cells(HcShared &s) {
+  const u32 t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const u32 a = s.cell_base[2 * t], b = s.cell_base[2 * t + 1];
+  u32 v = a + b;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u32 o = __shfl_up_sync(0xffffffffu, v, d);
+    if ((int)lane >= d) v += o;
+  }
+  if (lane == 31) s.warp_sum[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    u32 x = lane < kHcThreads / 32 ? s.warp_sum[lane] : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 o = __shfl_up_sync(0xffffffffu, x, d);
+      if ((int)lane >= d) x += o;
+    }
+    if (lane < kHcThreads / 32) s.warp_sum[lane] = x;  // inclusive
+  }
+  __syncthreads();
+  const u32 excl = v - (a + b) + (w ? s.warp_sum[w - 1] : 0u);
+  s.cell_base[2 * t] = excl;
+  s.cell_base[2 * t + 1] = excl + a;
+  s.cell_cur[2 * t] = excl;
+  s.cell_cur[2 * t + 1] = excl + a;
+  __syncthreads();
+}
+
+// first index q in [p, hi] that may start a slice: q == lo, q == hi, or the 24-bit prefix changes between q-1 and q
+// (records with equal keys share their prefix, so they never straddle such a boundary).  Block-wide.
+__device__ __forceinline__ u64 hc_align(const uint2 *__restrict__ recs, u64 p, u64 lo, u64 hi, u32 *s_min) {
+  if (p <= lo) return lo;
+  if (p >= hi) return hi;
+  for (u64 q0 = p; q0 < hi; q0 += kHcThreads) {
+    __syncthreads();
+    if (threadIdx.x == 0) *s_min = 0xFFFFFFFFu;
+    __syncthreads();
+    const u64 q = q0 + threadIdx.x;
+    if (q < hi && (recs[q].x >> 8) != (recs[q - 1].x >> 8)) atomicMin(s_min, threadIdx.x);
+    __syncthreads();
+    const u32 f = *s_min;
+    if (f != 0xFFFFFFFFu) return q0 + f;
+  }
+  return hi;
+}
+
+// Work unit = a SLICE of the prefix-sorted records: bucket b (16-bit prefix) is cut into ceil(n_b / T) slices whose
+// boundaries are moved forward to the next change of the 24-bit prefix, so that a slice is a contiguous, key-closed
+// range read exactly once per sweep with every lane busy.  slice_off[b] = first slice id of bucket b (exclusive scan of
+// the per-bucket slice counts).  list: slice s's solid entries go to list[a_s / m + s ...) with a_s the slice's first
+// record (a slice of n records holds at most n / m solid keys and floor is super-additive: the areas never overlap).
+__global__ void __launch_bounds__(kHcThreads, 2)
+    k_hash_count(const uint2 *__restrict__ recs, const u64 *__restrict__ bounds, const u64 *__restrict__ slice_off,
+                 const u64 *__restrict__ n_slices_dev, u32 slice_records, int m, u32 *ticket, u64 *__restrict__ list,
+                 u32 *__restrict__ slice_count, u64 *__restrict__ slice_base, u32 *__restrict__ slice_bucket, u64 *mul_hist,
+                 u32 *err_flag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  HcShared &s = *reinterpret_cast<HcShared *>(smem_raw);
+  const u32 tid = threadIdx.x;
+  for (u32 i = tid; i < kHcHist; i += kHcThreads) s.cta_hist[i] = 0;
+  for (u32 i = tid; i < kHcSlots; i += kHcThreads) {
+    s.keys[i] = kHcEmpty;
+    s.cnt[i] = 0;
+  }
+  if (tid == 0) s.n_occ = 0;
+  __syncthreads();
+  const u64 n_slices = *n_slices_dev;
+  while (true) {
+    if (tid == 0) {
+      const u32 sl = atomicAdd(ticket, 1u);
+      s.bucket = sl;
+      if (sl < n_slices) {  // bucket of this slice: last b with slice_off[b] <= sl
+        u32 a = 0, z = 65536;
+        while (z - a > 1) {
+          const u32 mid = (a + z) >> 1;
+          if (slice_off[mid] <= sl) a = mid; else z = mid;
+        }
+        s.sp = a;
+      }
+    }
+    __syncthreads();
+    const u32 sl = s.bucket;
+    if (sl >= n_slices) break;
+    const u32 b = s.sp;
+    __syncthreads();
+    const u64 blo = bounds[b], bhi = bounds[b + 1];
+    const u64 n_in_b = slice_off[b + 1] - slice_off[b], idx = sl - slice_off[b];
+    const u64 step = (bhi - blo + n_in_b - 1) / n_in_b;
+    const u64 lo = hc_align(recs, blo + idx * step, blo, bhi, &s.overflow);
+    const u64 hi = idx + 1 == n_in_b ? bhi : hc_align(recs, blo + (idx + 1) * step, blo, bhi, &s.overflow);
+    __syncthreads();
+    const u64 base = lo / (u64)m + sl;
+    if (tid == 0) {
+      slice_base[sl] = base;
+      slice_bucket[sl] = b;
+      s.out_cursor = 0;
+    }
+    if (hi <= lo) {  // a 24-bit group longer than a slice swallowed this one
+      if (tid == 0) slice_count[sl] = 0;
+      __syncthreads();
+      continue;
+    }
+    (void)slice_records;
+    const u32 top_bits = 0;
+    __syncthreads();
+    for (u64 top = 0; top < (1ull << top_bits); ++top) {
+      if (tid == 0) {
+        s.st_prefix[0] = top;
+        s.st_bits[0] = top_bits;
+        s.sp = 1;
+      }
+      __syncthreads();
+      while (s.sp > 0) {
+        // ---------------- one key sub-range: the records whose remainder starts with `prefix` (`bits` bits) -------
+        const u32 sp = s.sp - 1;
+        const u64 prefix = s.st_prefix[sp];
+        const u32 bits = s.st_bits[sp];
+        __syncthreads();
+        if (tid == 0) {
+          s.sp = sp;
+          s.n_solid = 0;
+          s.overflow = 0;
+        }
+        __syncthreads();
+        // ---- sweep 1: occurrence counts ----
+        for (u64 i0 = lo + tid; i0 < hi; i0 += (u64)kHcThreads * kHcBatch) {
+          uint2 v[kHcBatch];
+#pragma unroll
+          for (int j = 0; j < kHcBatch; ++j) {
+            const u64 i = i0 + (u64)j * kHcThreads;
+            v[j] = i < hi ? recs[i] : make_uint2(0, 0);
+          }
+#pragma unroll
+          for (int j = 0; j < kHcBatch; ++j) {
+            const u64 i = i0 + (u64)j * kHcThreads;
+            if (i >= hi) break;
+            const u64 r = (rec_key64(v[j]) >> 6) & ((1ull << kRemBits) - 1);
+            if (bits && (r >> (kRemBits - bits)) != prefix) continue;
+            const u32 h = hc_insert(s, r);
+            if (h == (u32)kHcSlots) s.overflow = 1;
+            else atomicAdd(&s.cnt[h], 1u);
+          }
+          if (s.overflow || s.n_occ > (u32)kHcMaxOcc) break;
+        }
+        __syncthreads();
+        u32 n_occ = s.n_occ;
+        bool failed = s.overflow || n_occ > (u32)kHcMaxOcc;
+        if (n_occ > (u32)kHcSlots) n_occ = kHcSlots;
+        u32 ns = 0;
+        if (!failed) {
+          // ---- judge: multiplicity histogram, ranks for the keys that reached the solid threshold ----
+          hc_hist_update(s, n_occ, mul_hist, true);
+          for (u32 i0 = 0; i0 < n_occ; i0 += kHcThreads) {
+            const u32 i = i0 + tid;
+            const bool on = i < n_occ;
+            const u32 slot = on ? s.occ[i] : 0u;
+            const u32 c = on ? s.cnt[slot] : 0u;
+            const bool solid = on && (long long)c >= (long long)m;
+            const u32 sm_ = __ballot_sync(0xffffffffu, solid);
+            u32 wbase = 0;
+            if ((tid & 31) == 0 && sm_) wbase = atomicAdd(&s.n_solid, (u32)__popc(sm_));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (solid) {
+              const u32 rank = wbase + __popc(sm_ & lane_lt_mask());
+              if (rank < (u32)kHcMaxSolid) {
+                s.rk[slot] = (uint16_t)rank;
+                s.sorted[rank] = (s.keys[slot] << 22) | ((u64)(c > 65535u ? 65535u : c) << 6);
+                s.tally[rank][0] = s.tally[rank][1] = s.tally[rank][2] = s.tally[rank][3] = 0;
+              }
+            }
+          }
+          __syncthreads();
+          ns = s.n_solid;
+          if (ns > (u32)kHcMaxSolid) {  // too many solid keys for the ordering buffers: take the histogram back, split
+            hc_hist_update(s, n_occ, mul_hist, false);
+            failed = true;
+          }
+        }
+        if (!failed && ns) {
+          // ---- sweep 2: prev / next tallies of the solid keys (16-bit fields; clamped to m between chunks of 32768
+          // records so that a field can never wrap, whatever the multiplicity) ----
+          const u64 chunk = 32768;
+          for (u64 c0 = lo; c0 < hi; c0 += chunk) {
+            const u64 c1 = c0 + chunk < hi ? c0 + chunk : hi;
+            for (u64 i0 = c0 + tid; i0 < c1; i0 += (u64)kHcThreads * kHcBatch) {
+              uint2 v[kHcBatch];
+#pragma unroll
+              for (int j = 0; j < kHcBatch; ++j) {
+                const u64 i = i0 + (u64)j * kHcThreads;
+                v[j] = i < c1 ? recs[i] : make_uint2(0, 0);
+              }
+#pragma unroll
+              for (int j = 0; j < kHcBatch; ++j) {
+                const u64 i = i0 + (u64)j * kHcThreads;
+                if (i >= c1) break;
+                const u64 key = rec_key64(v[j]);
+                const u64 r = (key >> 6) & ((1ull << kRemBits) - 1);
+                if (bits && (r >> (kRemBits - bits)) != prefix) continue;
+                const u32 slot = hc_find(s, r);
+                if ((long long)s.cnt[slot] < (long long)m) continue;
+                const u32 rank = s.rk[slot];
+                const u32 p = (u32)(key >> 3) & 7u, nx = (u32)key & 7u;
+                if (p < 4) atomicAdd(&s.tally[rank][p >> 1], 1u << (16 * (p & 1)));
+                if (nx < 4) atomicAdd(&s.tally[rank][2 + (nx >> 1)], 1u << (16 * (nx & 1)));
+              }
+            }
+            if (c1 < hi) {  // more chunks follow: clamp
+              __syncthreads();
+              for (u32 i = tid; i < ns * 4; i += kHcThreads) {
+                const u32 t = s.tally[i >> 2][i & 3];
+                u32 a = t & 0xFFFFu, bb = t >> 16;
+                a = a > (u32)m ? (u32)m : a;
+                bb = bb > (u32)m ? (u32)m : bb;
+                s.tally[i >> 2][i & 3] = a | (bb << 16);
+              }
+              __syncthreads();
+            }
+          }
+          __syncthreads();
+          // ---- aux flags ----
+          for (u32 i = tid; i < ns; i += kHcThreads) {
+            bool has_in = false, has_out = false;
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+              const u32 tp = s.tally[i][w], tn = s.tally[i][2 + w];
+              has_in = has_in || (tp & 0xFFFFu) >= (u32)m || (tp >> 16) >= (u32)m;
+              has_out = has_out || (tn & 0xFFFFu) >= (u32)m || (tn >> 16) >= (u32)m;
+            }
+            s.sorted[i] |= (has_in ? 0ull : 1ull) | (has_out ? 0ull : 2ull);
+          }
+          for (u32 i = tid; i < (u32)kHcCells; i += kHcThreads) s.cell_base[i] = 0;
+          __syncthreads();
+          // ---- order the solid keys: counting sort on the next 10 key bits, ties ranked inside their cell ----
+          u64 *tmp = reinterpret_cast<u64 *>(&s.tally[0][0]);
+          const u32 cshift = 22 + (kRemBits - 10);  // entry bits 63..22 hold the remainder
+          for (u32 i = tid; i < ns; i += kHcThreads) atomicAdd(&s.cell_base[(u32)((s.sorted[i] << bits) >> cshift)], 1u);
+          __syncthreads();
+          hc_scan_cells(s);
+          for (u32 i = tid; i < ns; i += kHcThreads) {
+            const u64 e = s.sorted[i];
+            tmp[atomicAdd(&s.cell_cur[(u32)((e << bits) >> cshift)], 1u)] = e;
+          }
+          __syncthreads();
+          const u32 at = s.out_cursor;
+          for (u32 i = tid; i < ns; i += kHcThreads) {
+            const u64 e = tmp[i];
+            const u32 c = (u32)((e << bits) >> cshift);
+            const u32 b0 = s.cell_base[c], b1 = c + 1 < (u32)kHcCells ? s.cell_base[c + 1] : ns;
+            u32 r = b0;
+            for (u32 j = b0; j < b1; ++j) r += tmp[j] < e ? 1u : 0u;
+            list[base + at + r] = e;
+          }
+          __syncthreads();
+          if (tid == 0) s.out_cursor = at + ns;
+        }
+        // ---- clear the table through the dense list ----
+        for (u32 i = tid; i < n_occ; i += kHcThreads) {
+          const u32 slot = s.occ[i];
+          s.keys[slot] = kHcEmpty;
+          s.cnt[slot] = 0;
+        }
+        if (n_occ >= (u32)kHcSlots)  // the list itself overflowed: wipe everything
+          for (u32 i = tid; i < kHcSlots; i += kHcThreads) {
+            s.keys[i] = kHcEmpty;
+            s.cnt[i] = 0;
+          }
+        __syncthreads();
+        if (tid == 0) {
+          s.n_occ = 0;
+          if (failed) {  // split this sub-range in four (ascending order is kept: the smallest child is popped first)
+            if (bits + 2 > kRemBits || s.sp + 4 > (u32)kHcStack) atomicExch(err_flag, 1u);
+            else
+              for (int c = 3; c >= 0; --c) {
+                s.st_prefix[s.sp] = (prefix << 2) | (u64)c;
+                s.st_bits[s.sp] = bits + 2;
+                ++s.sp;
+              }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // ---- the slice is complete ----
+    if (tid == 0) slice_count[sl] = s.out_cursor;
+    __syncthreads();
+  }
+  for (u32 i = tid; i < kHcHist; i += kHcThreads)
+    if (s.cta_hist[i]) atomicAdd((unsigned long long *)&mul_hist[i], (unsigned long long)s.cta_hist[i]);
+}
+
+// per-bucket slice counts: ceil(n_b / T) (0 for an empty bucket)
+__global__ void k_slice_counts(const u64 *__restrict__ bounds, u32 T, u32 *__restrict__ cnt) {
+  const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= 65536u) return;
+  const u64 nb = bounds[b + 1] - bounds[b];
+  cnt[b] = (u32)((nb + T - 1) / T);
+}
+
+// PackEdge (kmer_counter.cpp:32-52): every slice's ordered solid entries -> `.edges` records + aux flags, in slice
+// (= key) order
+__global__ void __launch_bounds__(256)
+    k_hash_gather(const u64 *__restrict__ list, const u64 *__restrict__ n_slices_dev, const u32 *__restrict__ slice_count,
+                  const u64 *__restrict__ slice_dst, const u64 *__restrict__ slice_base, const u32 *__restrict__ slice_bucket,
+                  u32 we, u32 *__restrict__ edges, uint8_t *__restrict__ aux, u64 capacity, const u32 *err_flag,
+                  u64 *n_solid_out) {
+  const u32 lane = threadIdx.x & 31;
+  // a sub-range that could not be split any further (cannot happen for 42-bit remainders) must never pass silently:
+  // the caller sees an impossible solid count
+  if (blockIdx.x == 0 && threadIdx.x == 0 && *err_flag) *n_solid_out = ~0ull;
+  const u64 n_slices = *n_slices_dev;
+  for (u64 sl = (u64)blockIdx.x * 8 + (threadIdx.x >> 5); sl < n_slices; sl += (u64)gridDim.x * 8) {
+    const u32 cnt = slice_count[sl];
+    if (!cnt) continue;
+    const u64 base = slice_base[sl], off = slice_dst[sl], b = slice_bucket[sl];
+    for (u32 x = lane; x < cnt; x += 32) {
+      if (off + x >= capacity) break;
+      const u64 ent = list[base + x];
+      const u64 key = (b << 48) | ((ent >> 22) << 6);
+      u32 *e = edges + (off + x) * we;
+      e[0] = (u32)(key >> 32);
+      e[1] = (u32)key;
+      if (we == 3) e[2] = 0;
+      e[we - 1] |= (u32)(ent >> 6) & 0xFFFFu;
+      aux[off + x] = (uint8_t)(ent & 3u);
+    }
+  }
+}
+
+int scan_counts(cudaStream_t st, const u32 *in, u64 n, u64 *out, u64 *total_dev, u64 *bsum) {
+  const u64 nb = (n + kScanTile - 1) / kScanTile;
+  k_scan32_sums<<<(unsigned)nb, kScanThreads, 0, st>>>(in, n, bsum);
+  CK_LAUNCH();
+  k_scan_u64<<<1, 1024, 0, st>>>(bsum, nb, total_dev);
+  CK_LAUNCH();
+  k_scan32_apply<<<(unsigned)nb, kScanThreads, 0, st>>>(in, n, bsum, out);
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
+constexpr u32 kHcSliceRecords = 6000;  // ~2200 distinct keys on 30x reads with 1 % errors (table limit 2900)
+
+struct HcLayout {
+  size_t sort_ws, off_bounds, off_bcnt, off_soff, off_bsum, off_misc, off_scount, off_sdst, off_sbase, off_sbucket, off_list, total;
+  uint64_t max_slices;
+};
+HcLayout hc_layout(uint64_t n, int32_t m) {
+  HcLayout L;
+  auto pad = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  L.max_slices = n / kHcSliceRecords + 65536 + 2;
+  L.sort_ws = pad(mhb_sort_workspace_bytes(n, 2));
+  size_t p = L.sort_ws;
+  L.off_bounds = p;
+  p += pad(65537 * 8);
+  L.off_bcnt = p;
+  p += pad(65537 * 4);
+  L.off_soff = p;
+  p += pad(65537 * 8);
+  L.off_bsum = p;
+  p += pad((L.max_slices / kScanTile + 4) * 8);
+  L.off_misc = p;
+  p += 256;
+  L.off_scount = p;
+  p += pad(L.max_slices * 4);
+  L.off_sdst = p;
+  p += pad(L.max_slices * 8);
+  L.off_sbase = p;
+  p += pad(L.max_slices * 8);
+  L.off_sbucket = p;
+  p += pad(L.max_slices * 4);
+  L.off_list = p;
+  p += pad((size_t)(n / (uint64_t)(m < 1 ? 1 : m) + L.max_slices + 8) * 8);
+  L.total = p;
+  return L;
+}
+
+}  // namespace
+
+extern "C" int mhb_count_hashed_supported(uint32_t k, int32_t m) {
+  return count_record_words(k) == 2 && 2 * (k + 1) >= 24 && m >= 1 && m <= kHcHist;
+}
+
+extern "C" size_t mhb_count_hashed_workspace_bytes(uint64_t n, uint32_t k, int32_t m) {
+  (void)k;
+  return hc_layout(n, m).total;
+}
+
+extern "C" int mhb_count_solid_hashed(void *stream, uint32_t *recs_a, uint32_t *recs_b, uint64_t n, uint32_t k, int32_t m,
+                                      const uint64_t *hist_byte5, uint32_t *edges_out, uint8_t *aux_out,
+                                      uint64_t capacity_edges, uint64_t *mul_hist, uint64_t *n_solid_out, void *ws,
+                                      size_t ws_bytes) {
+  if (!mhb_count_hashed_supported(k, m)) return mhb_set_error(MHB_ERR_ARG, "hashed count needs 8-byte records (11 <= k <= 28) and 1 <= m <= %d", kHcHist);
+  if (!mul_hist || !n_solid_out || !ws) return mhb_set_error(MHB_ERR_ARG, "bad args");
+  if (n == 0) return MHB_OK;
+  if (n >= (1ull << 40)) return mhb_set_error(MHB_ERR_ARG, "too many records for one hashed count call");
+  const HcLayout L = hc_layout(n, m);
+  if (ws_bytes < L.total) return mhb_set_error(MHB_ERR_ARG, "hashed count workspace too small (%zu < %zu)", ws_bytes, L.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  // 1. group by the leading 24 key bits: stable passes on key bytes 5, 6, 7
+  const uint8_t bytes[3] = {5, 6, 7};
+  int in_b = 0;
+  if (int rc = mhb_sort_records_impl(st, recs_a, recs_b, n, 2, bytes, 3, hist_byte5, ws, L.sort_ws, &in_b, nullptr)) return rc;
+  const uint2 *recs = (const uint2 *)(in_b ? recs_b : recs_a);
+  char *w = (char *)ws;
+  u64 *bounds = (u64 *)(w + L.off_bounds);
+  u32 *bcnt = (u32 *)(w + L.off_bcnt);
+  u64 *slice_off = (u64 *)(w + L.off_soff);
+  u64 *bsum = (u64 *)(w + L.off_bsum);
+  u32 *misc = (u32 *)(w + L.off_misc);  // [0] ticket, [1] error flag, [2..3] number of slices (u64)
+  u32 *slice_count = (u32 *)(w + L.off_scount);
+  u64 *slice_dst = (u64 *)(w + L.off_sdst);
+  u64 *slice_base = (u64 *)(w + L.off_sbase);
+  u32 *slice_bucket = (u32 *)(w + L.off_sbucket);
+  u64 *list = (u64 *)(w + L.off_list);
+  u64 *n_slices_dev = (u64 *)(misc + 2);
+  CK(cudaMemsetAsync(misc, 0, 256, st));
+  CK(cudaMemsetAsync(slice_count, 0, L.max_slices * 4, st));
+  // 2. bucket boundaries, slices per bucket
+  k_bucket_bounds<<<(65537 + 255) / 256, 256, 0, st>>>(recs, n, bounds);
+  CK_LAUNCH();
+  k_slice_counts<<<65536 / 256, 256, 0, st>>>(bounds, kHcSliceRecords, bcnt);
+  CK_LAUNCH();
+  if (int rc = scan_counts(st, bcnt, 65536, slice_off, n_slices_dev, bsum)) return rc;
+  CK(cudaMemcpyAsync(slice_off + 65536, n_slices_dev, 8, cudaMemcpyDeviceToDevice, st));
+  // 3. per-slice hash aggregation
+  static int bps = 0;
+  const size_t smem = sizeof(HcShared);
+  if (!bps) {
+    CK(cudaFuncSetAttribute(k_hash_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_hash_count, kHcThreads, smem));
+    if (bps < 1) return mhb_set_error(MHB_ERR_CUDA, "hash-count kernel does not fit an SM (%zu B shared memory)", smem);
+    if (getenv("MHB_VERBOSE")) fprintf(stderr, "[mhb] hash count: %d threads, %zu B smem, %d CTA/SM\n", kHcThreads, smem, bps);
+  }
+  k_hash_count<<<sm_count() * bps, kHcThreads, smem, st>>>(recs, bounds, slice_off, n_slices_dev, kHcSliceRecords, m, misc, list,
+                                                          slice_count, slice_base, slice_bucket, mul_hist, misc + 1);
+  CK_LAUNCH();
+  // 4. offsets + edges (the scan runs over the allocated maximum; unused slice ids hold zero)
+  if (int rc = scan_counts(st, slice_count, L.max_slices, slice_dst, n_solid_out, bsum)) return rc;
+  k_hash_gather<<<sm_count() * 4, 256, 0, st>>>(list, n_slices_dev, slice_count, slice_dst, slice_base, slice_bucket,
+                                               words_per_edge(k), edges_out, aux_out, capacity_edges, misc + 1, n_solid_out);
+  CK_LAUNCH();
+  return MHB_OK;
+}

@@ -132,6 +132,69 @@ extern "C" int mhb_release(void) {
   return MHB_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The count stage on extracted records resident in d_a: either the LSD sort on every key byte followed by the
+// run-length count, or - 8-byte records, the default where available - two partition passes + per-bucket hash
+// aggregation (mhb_count_solid_hashed).  MHB_COUNT_MODE=sort forces the former.  Both leave the same edges / aux /
+// histogram; both clobber d_a and d_b.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct CountWork {
+  bool hashed;
+  size_t bytes;      // one work area: sort workspace + count scratch, or the hashed path's workspace
+  size_t ws_bytes;   // sort path: size of the leading sort workspace
+  int hist_byte;     // record byte whose histogram the extraction must deliver
+};
+CountWork count_work_plan(uint64_t n, uint32_t k, int32_t m) {
+  static const bool force_sort = getenv("MHB_COUNT_MODE") && !strcmp(getenv("MHB_COUNT_MODE"), "sort");
+  CountWork cw;
+  cw.hashed = !force_sort && mhb_count_hashed_supported(k, m);
+  if (cw.hashed) {
+    cw.bytes = mhb_count_hashed_workspace_bytes(n, k, m);
+    cw.ws_bytes = 0;
+    cw.hist_byte = 5;
+  } else {
+    uint8_t sb[72];
+    mhb_count_sort_bytes(k, sb);
+    cw.ws_bytes = Arena::pad(mhb_sort_workspace_bytes(n, count_record_words(k)));
+    cw.bytes = cw.ws_bytes + Arena::pad(mhb_count_solid_scratch_bytes(n));
+    cw.hist_byte = sb[0];
+  }
+  return cw;
+}
+int run_count_stage(cudaStream_t st, const CountWork &cw, uint32_t *d_a, uint32_t *d_b, uint64_t n, uint32_t k, int32_t m,
+                    const uint64_t *d_hist0, uint32_t *d_edges, uint8_t *d_aux, uint64_t cap_edges, uint64_t *d_mul_hist,
+                    uint64_t *d_nsolid, char *work, double *pass_ms, uint32_t *n_passes) {
+  const uint32_t WR = count_record_words(k);
+  if (cw.hashed) {
+    if (n_passes) *n_passes = n ? 2 : 0;
+    CKR(mhb_count_solid_hashed(st, d_a, d_b, n, k, m, d_hist0, d_edges, d_aux, cap_edges, d_mul_hist, d_nsolid, work, cw.bytes));
+    if (pass_ms && n) {
+      uint32_t np = 0, w = 0;
+      uint64_t nr = 0;
+      CKR(mhb_sort_pass_ms(0, pass_ms, 64, &np, &nr, &w));
+    }
+    return MHB_OK;
+  }
+  uint8_t sort_bytes[72];
+  const uint32_t n_sort = mhb_count_sort_bytes(k, sort_bytes);
+  if (n_passes) *n_passes = n ? n_sort : 0;
+  int in_b = 0;
+  CKR(mhb_sort_records_impl(st, d_a, d_b, n, WR, sort_bytes, n_sort, d_hist0, work, cw.ws_bytes, &in_b, pass_ms));
+  return mhb_count_solid(st, in_b ? d_b : d_a, n, k, m, d_edges, d_aux, cap_edges, d_mul_hist, d_nsolid, work + cw.ws_bytes,
+                         cw.bytes - cw.ws_bytes);
+}
+}  // namespace
+
+namespace {
+size_t round_bytes(uint64_t n, uint32_t WR, uint32_t WE, int32_t m, uint32_t k) {
+  const uint64_t cap_edges = n / (uint64_t)std::max(1, m) + 1;
+  return 2 * Arena::pad((size_t)n * WR * 4 + 16) + Arena::pad(count_work_plan(n, k, m).bytes) +
+         Arena::pad((size_t)cap_edges * WE * 4) + Arena::pad(cap_edges);
+}
+}  // namespace
+
 // ================================================================================================
 // count, out of core (A13): rounds over ranges of the leading record byte
 // ================================================================================================
@@ -140,11 +203,7 @@ uint64_t g_round_limit = 0;      // count records per round; 0 = derive from fre
 uint64_t g_s2s_round_limit = 0;  // seq2sdbg sort items per round; 0 = derive from free device memory
 
 // bytes of device memory one round of `n` records needs besides the resident read library
-size_t round_bytes(uint64_t n, uint32_t WR, uint32_t WE, int32_t m) {
-  const uint64_t cap_edges = n / (uint64_t)std::max(1, m) + 1;
-  return 2 * Arena::pad((size_t)n * WR * 4 + 16) + Arena::pad(mhb_sort_workspace_bytes(n, WR)) +
-         Arena::pad(mhb_count_solid_scratch_bytes(n)) + Arena::pad((size_t)cap_edges * WE * 4) + Arena::pad(cap_edges);
-}
+
 }  // namespace
 
 // Greedy cut of the 256 leading-byte values into contiguous ranges of at most max_records records each (pure host
@@ -287,14 +346,14 @@ static int count_host_rounds(const mhb_count_args *args, mhb_count_result *res, 
     uint64_t lo = 1, hi = n;  // largest round that fits (round_bytes is monotone)
     while (lo < hi) {
       const uint64_t mid = lo + (hi - lo + 1) / 2;
-      if (fixed + round_bytes(mid, WR, WE, m) <= avail) lo = mid;
+      if (fixed + round_bytes(mid, WR, WE, m, k) <= avail) lo = mid;
       else hi = mid - 1;
     }
     max_records = lo;
   }
   max_records = std::min<uint64_t>(std::max<uint64_t>(max_records, 1), std::max<uint64_t>(n, 1));
   const uint64_t cap_edges = max_records / (uint64_t)std::max(1, m) + 1;
-  CKR(g_arena.reserve(fixed + round_bytes(max_records, WR, WE, m)));
+  CKR(g_arena.reserve(fixed + round_bytes(max_records, WR, WE, m, k)));
 
   uint32_t *d_bin = g_arena.take<uint32_t>(bin_bytes / 4 + 4);
   uint64_t *d_per_read = g_arena.take<uint64_t>(n_reads + 2);
@@ -314,10 +373,8 @@ static int count_host_rounds(const mhb_count_args *args, mhb_count_result *res, 
   }
   uint32_t *d_a = g_arena.take<uint32_t>((size_t)max_records * WR + 4);
   uint32_t *d_b = g_arena.take<uint32_t>((size_t)max_records * WR + 4);
-  const size_t ws_bytes = mhb_sort_workspace_bytes(max_records, WR);
-  const size_t scratch_bytes = mhb_count_solid_scratch_bytes(max_records);
-  char *d_ws = g_arena.take<char>(ws_bytes);
-  char *d_scratch = g_arena.take<char>(scratch_bytes);
+  const CountWork cw = count_work_plan(max_records, k, m);
+  char *d_work = g_arena.take<char>(cw.bytes);
   uint32_t *d_edges = g_arena.take<uint32_t>((size_t)cap_edges * WE);
   uint8_t *d_aux = g_arena.take<uint8_t>(cap_edges);
 
@@ -378,15 +435,12 @@ static int count_host_rounds(const mhb_count_args *args, mhb_count_result *res, 
     CK(cudaStreamSynchronize(st));
     if (n_round > max_records) return mhb_set_error(MHB_ERR_NOMEM, "internal: round of %llu records exceeds its plan", (unsigned long long)n_round);
     if (n_round == 0) continue;
-    CKR(mhb_count_extract_range(st, &reads, k, rg.first, rg.second, 1, d_per_read, d_a, d_hist0, sort_bytes[0], nullptr));
+    CKR(mhb_count_extract_range(st, &reads, k, rg.first, rg.second, 1, d_per_read, d_a, d_hist0, cw.hist_byte, nullptr));
     res->t_extract_ms += t.stop();
-    // ---- sort + solid edges ----
+    // ---- sort / partition + solid edges ----
     t.start();
-    int in_b = 0;
-    CKR(mhb_sort_records_impl(st, d_a, d_b, n_round, WR, sort_bytes, n_sort, d_hist0, d_ws, ws_bytes, &in_b, nullptr));
-    res->t_sort_ms += t.stop();
-    t.start();
-    CKR(mhb_count_solid(st, in_b ? d_b : d_a, n_round, k, m, d_edges, d_aux, cap_edges, d_mul_hist, d_scalars, d_scratch, scratch_bytes));
+    CKR(run_count_stage(st, cw, d_a, d_b, n_round, k, m, d_hist0, d_edges, d_aux, cap_edges, d_mul_hist, d_scalars, d_work,
+                        nullptr, nullptr));
     uint64_t n_solid = 0;
     CK(cudaMemcpyAsync(&n_solid, d_scalars, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -503,10 +557,9 @@ extern "C" int mhb_count_host(const mhb_count_args *args, mhb_count_result *res)
   const uint64_t cap_edges = n / (uint64_t)std::max(1, m) + 1;
 
   const size_t bin_bytes = (args->bin_words * 4 + 15) & ~(size_t)15;
-  const size_t ws_bytes = mhb_sort_workspace_bytes(n, WR);
-  const size_t scratch_bytes = mhb_count_solid_scratch_bytes(n);
-  size_t need = Arena::pad(bin_bytes + 16) + 2 * Arena::pad((size_t)n * WR * 4 + 16) + Arena::pad(ws_bytes) +
-                Arena::pad(scratch_bytes) + Arena::pad((size_t)cap_edges * WE * 4) + Arena::pad(cap_edges) +
+  const CountWork cw = count_work_plan(n, k, m);
+  size_t need = Arena::pad(bin_bytes + 16) + 2 * Arena::pad((size_t)n * WR * 4 + 16) + Arena::pad(cw.bytes) +
+                Arena::pad((size_t)cap_edges * WE * 4) + Arena::pad(cap_edges) +
                 Arena::pad(65536 * 8) + Arena::pad(256 * 8) + 4096;
   if (!ix.fixed_len) need += 2 * Arena::pad((n_reads + 1) * 8);
   if (args->want_mercy) need += 2 * Arena::pad((size_t)(n_reads + 1) * 4);
@@ -526,8 +579,7 @@ extern "C" int mhb_count_host(const mhb_count_args *args, mhb_count_result *res)
   uint32_t *d_bin = g_arena.take<uint32_t>(bin_bytes / 4 + 4);
   uint32_t *d_a = g_arena.take<uint32_t>((size_t)n * WR + 4);
   uint32_t *d_b = g_arena.take<uint32_t>((size_t)n * WR + 4);
-  char *d_ws = g_arena.take<char>(ws_bytes);
-  char *d_scratch = g_arena.take<char>(scratch_bytes);
+  char *d_work = g_arena.take<char>(cw.bytes);
   uint32_t *d_edges = g_arena.take<uint32_t>((size_t)cap_edges * WE);
   uint8_t *d_aux = g_arena.take<uint8_t>(cap_edges);
   uint64_t *d_mul_hist = g_arena.take<uint64_t>(65536);
@@ -566,21 +618,15 @@ extern "C" int mhb_count_host(const mhb_count_args *args, mhb_count_result *res)
 
   // ---- extract ----
   t.start();
-  CKR(mhb_count_extract(st, &reads, k, d_a, n, d_hist0, sort_bytes[0]));
+  CKR(mhb_count_extract(st, &reads, k, d_a, n, d_hist0, cw.hist_byte));
   res->t_extract_ms = t.stop();
 
-  // ---- sort ----
+  // ---- sort (or partition) + count ----
   t.start();
-  int in_b = 0;
-  res->n_sort_passes = n ? n_sort : 0;
   res->n_rounds = 1;
-  CKR(mhb_sort_records_impl(st, d_a, d_b, n, WR, sort_bytes, n_sort, d_hist0, d_ws, ws_bytes, &in_b, res->sort_pass_ms));
-  res->t_sort_ms = t.stop();
-  const uint32_t *d_sorted = in_b ? d_b : d_a;
-
-  // ---- count ----
-  t.start();
-  CKR(mhb_count_solid(st, d_sorted, n, k, m, d_edges, d_aux, cap_edges, d_mul_hist, d_nsolid, d_scratch, scratch_bytes));
+  CKR(run_count_stage(st, cw, d_a, d_b, n, k, m, d_hist0, d_edges, d_aux, cap_edges, d_mul_hist, d_nsolid, d_work,
+                      res->sort_pass_ms, &res->n_sort_passes));
+  for (uint32_t p = 0; p < res->n_sort_passes; ++p) res->t_sort_ms += res->sort_pass_ms[p];
   uint64_t n_solid = 0;
   CK(cudaMemcpyAsync(&n_solid, d_nsolid, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -595,9 +641,9 @@ extern "C" int mhb_count_host(const mhb_count_args *args, mhb_count_result *res)
     uint64_t n_tip = 0;
     CKR(mhb_count_tip_edges(st, d_aux, n_solid, &n_tip));
     const size_t ts_bytes = mhb_tipset_bytes(n_tip, k);
-    // the sort workspace and the unused ping-pong buffer are free now: put the tip set there if it fits
+    // the ping-pong buffers are free now: put the tip set there if it fits
     char *d_tips = nullptr;
-    uint32_t *d_free = in_b ? d_a : d_b;
+    uint32_t *d_free = d_a;
     bool own = false;
     if (ts_bytes <= (size_t)n * WR * 4) d_tips = (char *)d_free;
     else {
@@ -946,8 +992,8 @@ extern "C" int mhb_build_host(const mhb_build_args *args, mhb_build_result *res)
   const int32_t m = args->m;
   const uint64_t cap_edges = n / (uint64_t)std::max(1, m) + 1;
   const size_t bin_bytes = (args->bin_words * 4 + 15) & ~(size_t)15;
-  const size_t c_ws = mhb_sort_workspace_bytes(n, WR), c_scr = mhb_count_solid_scratch_bytes(n);
-  const size_t count_work = 2 * Arena::pad((size_t)n * WR * 4 + 16) + Arena::pad(c_ws) + Arena::pad(c_scr);
+  const CountWork cw = count_work_plan(n, k, m);
+  const size_t count_work = 2 * Arena::pad((size_t)n * WR * 4 + 16) + Arena::pad(cw.bytes);
   // fixed part
   size_t fixed = Arena::pad(bin_bytes + 16) + Arena::pad((size_t)cap_edges * WE * 4) + Arena::pad(cap_edges) +
                  Arena::pad(65536 * 8) + 2 * Arena::pad(256 * 8) + Arena::pad(64) + Arena::pad((size_t)MHB_NUM_BUCKETS * 32) +
@@ -1020,9 +1066,8 @@ extern "C" int mhb_build_host(const mhb_build_args *args, mhb_build_result *res)
   uint32_t *c_a = (uint32_t *)work;
   uint32_t *c_b = (uint32_t *)(work + Arena::pad((size_t)n * WR * 4 + 16));
   char *c_wsp = work + 2 * Arena::pad((size_t)n * WR * 4 + 16);
-  char *c_scrp = c_wsp + Arena::pad(c_ws);
   if (!chunked) {
-    CKR(mhb_count_extract(st, &reads, k, c_a, n, d_hist0, cbytes[0]));
+    CKR(mhb_count_extract(st, &reads, k, c_a, n, d_hist0, cw.hist_byte));
   } else {
     static cudaStream_t copy_st = nullptr;
     static cudaEvent_t ev[64];
@@ -1050,12 +1095,10 @@ extern "C" int mhb_build_host(const mhb_build_args *args, mhb_build_result *res)
       piece.bin = d_bin + w0;
       piece.bin_words = w1 - w0;
       piece.n_reads = r1 - r0;
-      CKR(mhb_count_extract(st, &piece, k, c_a + (size_t)r0 * e_per_read * WR, (r1 - r0) * e_per_read, d_hist0, cbytes[0]));
+      CKR(mhb_count_extract(st, &piece, k, c_a + (size_t)r0 * e_per_read * WR, (r1 - r0) * e_per_read, d_hist0, cw.hist_byte));
     }
   }
-  int in_b = 0;
-  CKR(mhb_sort_records_impl(st, c_a, c_b, n, WR, cbytes, n_csort, d_hist0, c_wsp, c_ws, &in_b, nullptr));
-  CKR(mhb_count_solid(st, in_b ? c_b : c_a, n, k, m, d_edges, d_aux, cap_edges, d_mul_hist, d_nsolid, c_scrp, c_scr));
+  CKR(run_count_stage(st, cw, c_a, c_b, n, k, m, d_hist0, d_edges, d_aux, cap_edges, d_mul_hist, d_nsolid, c_wsp, nullptr, nullptr));
   uint64_t n_solid = 0;
   CK(cudaMemcpyAsync(&n_solid, d_nsolid, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));

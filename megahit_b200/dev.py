@@ -39,10 +39,18 @@ class CountPlan:
     """`count` (extract -> sort -> solid edges [-> mercy bookkeeping]) for a fixed-length read library
     resident on the device."""
 
-    def __init__(self, n_reads: int, read_len: int, k: int, m: int, device, want_mercy: bool = True):
+    def __init__(self, n_reads: int, read_len: int, k: int, m: int, device, want_mercy: bool = True, mode: str | None = None):
+        """mode: "sort" = LSD sort on every key byte + run-length count; "hashed" = two partition passes + per-bucket hash
+        aggregation (8-byte records, mhb_count_solid_hashed); None = $MHB_COUNT_MODE, else hashed where supported."""
+        import os
         L = lib.load()
         self.L, self.k, self.m, self.n_reads, self.read_len, self.device = L, k, m, n_reads, read_len, device
         self.want_mercy = want_mercy
+        mode = mode or os.environ.get("MHB_COUNT_MODE") or "auto"
+        ok = bool(L.mhb_count_hashed_supported(k, m))
+        if mode == "hashed" and not ok:
+            raise lib.MhbError(f"hashed count is not available for k={k}, m={m}")
+        self.hashed = ok and mode in ("hashed", "auto")
         self.n = n_reads * (read_len - k) if read_len >= k + 1 else 0
         self.WR, self.WE = lib.count_record_words(k), lib.words_per_edge(k)
         self.sort_bytes = lib.count_sort_bytes(k)
@@ -50,8 +58,12 @@ class CountPlan:
         i32 = dict(dtype=torch.int32, device=device)
         self.a = torch.empty(n * self.WR + 4, **i32)
         self.b = torch.empty(n * self.WR + 4, **i32)
-        self.ws = torch.empty(L.mhb_sort_workspace_bytes(n, self.WR), dtype=torch.uint8, device=device)
-        self.scratch = torch.empty(L.mhb_count_solid_scratch_bytes(n), dtype=torch.uint8, device=device)
+        if self.hashed:
+            self.ws = torch.empty(L.mhb_count_hashed_workspace_bytes(n, k, m), dtype=torch.uint8, device=device)
+            self.scratch = None
+        else:
+            self.ws = torch.empty(L.mhb_sort_workspace_bytes(n, self.WR), dtype=torch.uint8, device=device)
+            self.scratch = torch.empty(L.mhb_count_solid_scratch_bytes(n), dtype=torch.uint8, device=device)
         self.cap_edges = n // max(1, m) + 1
         self.edges = torch.empty(self.cap_edges * self.WE, **i32)
         self.aux = torch.empty(self.cap_edges, dtype=torch.uint8, device=device)
@@ -74,15 +86,22 @@ class CountPlan:
     def extract(self, bin_dev):
         self.hist0.zero_()
         lib._check(self.L.mhb_count_extract(_stream(), C.byref(self._reads(bin_dev)), self.k, _ptr(self.a), self.n,
-                                            _ptr(self.hist0), self.sort_bytes[0]))
+                                            _ptr(self.hist0), 5 if self.hashed else self.sort_bytes[0]))
 
     def sort(self):
+        if self.hashed:
+            return None  # the two partition passes run inside count()
         self.sorted = sort_records(self.a, self.b, self.n, self.WR, self.sort_bytes, self.hist0, self.ws)
         return self.sorted
 
     def count(self):
         self.mul_hist.zero_()
         self.n_solid_dev.zero_()
+        if self.hashed:
+            lib._check(self.L.mhb_count_solid_hashed(_stream(), _ptr(self.a), _ptr(self.b), self.n, self.k, self.m,
+                                                     _ptr(self.hist0), _ptr(self.edges), _ptr(self.aux), self.cap_edges,
+                                                     _ptr(self.mul_hist), _ptr(self.n_solid_dev), _ptr(self.ws), self.ws.numel()))
+            return
         lib._check(self.L.mhb_count_solid(_stream(), _ptr(self.sorted), self.n, self.k, self.m, _ptr(self.edges),
                                           _ptr(self.aux), self.cap_edges, _ptr(self.mul_hist), _ptr(self.n_solid_dev),
                                           _ptr(self.scratch), self.scratch.numel()))

@@ -134,6 +134,8 @@ class MultiGpuBuild:
         self.stride = 1 + (read_len + 15) // 16
         self.times = {}
         self.fused = self.world > 1 and not os.environ.get("MHB_MGPU_NCCL_A2A")
+        # count stage on the owned records: two partition passes + per-bucket hash aggregation where available
+        self.hashed = bool(self.L.mhb_count_hashed_supported(k, m)) and os.environ.get("MHB_COUNT_MODE", "auto") != "sort"
         self.peer = {}
         self._bufs = {}
         self._tok = torch.zeros(1, dtype=torch.int32, device=device)
@@ -342,9 +344,6 @@ class MultiGpuBuild:
         own, n_own, bounds, owner = self._partition_and_exchange(a, n, self.WR, top, hist, "c", max(n, 1))
         if timed:
             self._mark("exchange1")
-        srt = self._sort_raw(own, n_own, self.WR, self.cbytes, "c")
-        if timed:
-            self._mark("sort1")
         cap = n_own // max(1, m) + 1
         edges = self._buf("edges", cap * self.WE + 4, slack=1.15)
         aux = self._buf("aux", cap, torch.uint8, slack=1.15)
@@ -352,9 +351,20 @@ class MultiGpuBuild:
         mul_hist.zero_()
         nsol = self._buf("nsol", 8, torch.int64)[:8]
         nsol.zero_()
-        scratch = self._buf("c_scratch", L.mhb_count_solid_scratch_bytes(n_own), torch.uint8, slack=1.15)
-        lib._check(L.mhb_count_solid(_stream(), C.c_void_p(srt), n_own, k, m, _ptr(edges), _ptr(aux), cap, _ptr(mul_hist),
-                                     _ptr(nsol), _ptr(scratch), scratch.numel()))
+        if self.hashed:
+            if timed:
+                self._mark("sort1")  # the two partition passes run inside the hashed count call
+            tmp = self._buf("c_tmp", n_own * self.WR + 4, slack=1.15)
+            hws = self._buf("c_hws", L.mhb_count_hashed_workspace_bytes(max(n_own, 1), k, m), torch.uint8, slack=1.15)
+            lib._check(L.mhb_count_solid_hashed(_stream(), C.c_void_p(own), _ptr(tmp), n_own, k, m, None, _ptr(edges), _ptr(aux),
+                                                cap, _ptr(mul_hist), _ptr(nsol), _ptr(hws), hws.numel()))
+        else:
+            srt = self._sort_raw(own, n_own, self.WR, self.cbytes, "c")
+            if timed:
+                self._mark("sort1")
+            scratch = self._buf("c_scratch", L.mhb_count_solid_scratch_bytes(n_own), torch.uint8, slack=1.15)
+            lib._check(L.mhb_count_solid(_stream(), C.c_void_p(srt), n_own, k, m, _ptr(edges), _ptr(aux), cap, _ptr(mul_hist),
+                                         _ptr(nsol), _ptr(scratch), scratch.numel()))
         dist.all_reduce(mul_hist)  # edge_counter.h:44-52: `.counting` is a global histogram
         n_solid = int(self._to_host(nsol[:1])[0])
         if n_solid > cap:
@@ -575,7 +585,7 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric, clocks=None):
         # fused partition pass is not traced; with the NCCL fallback the partitions are, so search instead of counting)
         for back in range(4):
             pm, nrec, words = lib.sort_pass_ms(back)
-            if words == job.WR and nrec == res["n_records_owned"] and len(pm) == len(job.cbytes):
+            if words == job.WR and nrec == res["n_records_owned"] and len(pm) == (2 if job.hashed else len(job.cbytes)):
                 pass_ms.append(pm)
                 break
         else:

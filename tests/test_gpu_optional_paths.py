@@ -63,15 +63,12 @@ print("RESULT " + json.dumps({"edges": F.sha256(g["edges"].tobytes()), "n_solid"
 
 @pytest.mark.parametrize("name,k,m,gold", [c for c in golden_cases() if c.values[0] in ("syn150_k27", "synvar_k21_m3")])
 def test_rolling_extract_and_mark_match_default(name, k, m, gold):
-    """MHB_EXTRACT_ROLL=1 (rolling record builder in the extract and mercy-mark kernels): same edges, same candidate
-    reads as the default kernels and as the reference"""
+    """rolling record builder (MHB_EXTRACT_ROLL=1: extract and mercy-mark kernels; the mark kernel uses it by default) vs
+    the per-position kernels (MHB_EXTRACT_ROLL=0): same edges, same candidate reads, and those of the reference"""
     import json
     out = []
     for roll in (False, True):
-        env = dict(os.environ)
-        env.pop("MHB_EXTRACT_ROLL", None)
-        if roll:
-            env["MHB_EXTRACT_ROLL"] = "1"
+        env = dict(os.environ, MHB_EXTRACT_ROLL="1" if roll else "0")
         p = subprocess.run([sys.executable, "-c", _CHILD_ROLL, os.path.join(GOLDEN, name), str(k), str(m)], env=env,
                            capture_output=True, text=True, timeout=300)
         line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]

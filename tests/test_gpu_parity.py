@@ -287,7 +287,7 @@ def test_large_synthetic_properties():
     n_reads, L, k, m = 2_000_000, 150, 27, 2
     bin_dev = synth.synth_reads_torch(n_reads, L, 10_000_000, 0.01, 99, "cuda").reshape(-1)
     bin_dev = torch.cat([bin_dev, torch.zeros(8, dtype=torch.int32, device="cuda")])
-    plan = dev.CountPlan(n_reads, L, k, m, "cuda", want_mercy=True)
+    plan = dev.CountPlan(n_reads, L, k, m, "cuda", want_mercy=True, mode="sort")
     n_solid = plan.run(bin_dev)
     edges = plan.edges_host(n_solid)
     hist = plan.mul_hist.cpu().numpy()
@@ -314,11 +314,32 @@ def test_large_synthetic_properties():
     l = plan.last[:n_reads].cpu().numpy().view(np.uint32)
     both = (f != 0xFFFFFFFF) & (l != 0xFFFFFFFF)
     assert both.sum() > 0 and (f[f != 0xFFFFFFFF] <= L - k).all() and (l[l != 0xFFFFFFFF] <= L - k - 1).all()
+    # the partition + hash-aggregation count stage on the same library: identical edges, flags, histogram, mercy marks
+    aux = plan.aux[:n_solid].cpu().numpy().copy()
+    del plan
+    torch.cuda.empty_cache()
+    hp = dev.CountPlan(n_reads, L, k, m, "cuda", want_mercy=True, mode="hashed")
+    assert hp.run(bin_dev) == n_solid
+    assert (hp.edges_host(n_solid) == first).all() and (hp.aux[:n_solid].cpu().numpy() == aux).all()
+    assert (hp.mul_hist.cpu().numpy() == hist).all()
+    assert (hp.first[:n_reads].cpu().numpy().view(np.uint32) == f).all() and (hp.last[:n_reads].cpu().numpy().view(np.uint32) == l).all()
 
 
 # ------------------------------------------------------------------------------------------------
 # A11 through the host-level ABI, and the multi-GPU building blocks on one GPU
 # ------------------------------------------------------------------------------------------------
+def _bare_kmers(a, k, bare=False):
+    """sorted (k+1)-mers of mercy edges: `.edges`-format records (multiplicity 1 in the low 16 bits of the last word,
+    seq_to_sdbg.cpp:354) or, bare=True, the oracle's plain packed (k+1)-mers"""
+    a = np.ascontiguousarray(a, np.uint32).reshape(len(a), -1).copy()
+    wm = (k + 1 + 15) // 16
+    if not bare:
+        assert ((a[:, -1] & 0xFFFF) == 1).all()
+        a[:, -1] &= np.uint32(0xFFFF0000)
+        assert (a[:, wm:] == 0).all()
+    return sorted(map(bytes, np.ascontiguousarray(a[:, :wm])))
+
+
 @pytest.mark.parametrize("name,k,m,gold", [c for c in golden_cases() if c.values[0] in ("toy_k21", "syn150_k27", "synvar_k31_m1", "lowcov_k21")])
 def test_mercy_host_matches_oracle(name, k, m, gold):
     """mhb_mercy_host (what `seq2sdbg --need_mercy` calls): sorted `.edges` records + the `.cand` image -> the same
@@ -331,10 +352,7 @@ def test_mercy_host_matches_oracle(name, k, m, gold):
     got = lib.mercy_host(k, oc["edges"], np.frombuffer(oc["cand_bytes"], np.uint32))
     assert len(got) == len(exp)
     if len(exp):
-        key = lambda a: sorted(map(bytes, np.ascontiguousarray(a, np.uint32)))
-        exp = np.asarray(exp, np.uint32).reshape(len(exp), -1).copy()
-        exp[:, -1] |= 1  # the oracle returns the bare (k+1)-mers; the records carry multiplicity 1 (seq_to_sdbg.cpp:354)
-        assert key(got) == key(exp)
+        assert _bare_kmers(got, k) == _bare_kmers(exp, k, bare=True)
 
 
 def test_plan_partition_kernel_matches_host_planner():
@@ -435,7 +453,100 @@ def test_owner_answered_mercy_search_matches_single_segment(name, k, m, gold, n_
     lib._check(L.mhb_mercy_edges_write(None, C.byref(rd), C.c_void_p(d_ids.data_ptr()), n_cand, mx, k, C.c_void_p(out.data_ptr()),
                                        nm.value, nm.value, C.c_void_p(scratch.data_ptr()), scratch.numel()))
     got = out.cpu().numpy().view(np.uint32)[: nm.value * we].reshape(-1, we)
-    key = lambda a: sorted(map(bytes, np.ascontiguousarray(a, np.uint32)))
-    exp = exp.reshape(len(exp), -1).copy()
-    exp[:, -1] |= 1  # multiplicity 1 (seq_to_sdbg.cpp:354)
-    assert key(got) == key(exp)
+    assert _bare_kmers(got, k) == _bare_kmers(exp.reshape(len(exp), -1), k, bare=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# A4 + A5 by partition + per-bucket hash aggregation == sort + run-length count
+# ------------------------------------------------------------------------------------------------
+def _count_both_ways(recs: np.ndarray, k: int, m: int):
+    """recs: (n, 2) uint32 count records.  Returns ((edges, aux, hist, n_solid) sorted path, same for the hashed path)."""
+    torch = _torch()
+    import ctypes as C
+    from megahit_b200 import dev
+    L = lib.load()
+    n = len(recs)
+    we = lib.words_per_edge(k)
+    cap = n // max(1, m) + 1
+    out = []
+    for hashed in (False, True):
+        a = torch.from_numpy(np.concatenate([recs.reshape(-1), np.zeros(4, np.uint32)]).view(np.int32)).cuda()
+        b = torch.empty_like(a)
+        edges = torch.zeros(cap * we + 4, dtype=torch.int32, device="cuda")
+        aux = torch.zeros(cap + 4, dtype=torch.uint8, device="cuda")
+        hist = torch.zeros(65536, dtype=torch.int64, device="cuda")
+        ns = torch.zeros(8, dtype=torch.int64, device="cuda")
+        if hashed:
+            ws = torch.empty(L.mhb_count_hashed_workspace_bytes(n, k, m), dtype=torch.uint8, device="cuda")
+            lib._check(L.mhb_count_solid_hashed(None, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), n, k, m, None,
+                                                C.c_void_p(edges.data_ptr()), C.c_void_p(aux.data_ptr()), cap,
+                                                C.c_void_p(hist.data_ptr()), C.c_void_p(ns.data_ptr()), C.c_void_p(ws.data_ptr()),
+                                                ws.numel()))
+        else:
+            srt = dev.sort_records(a, b, n, 2, lib.count_sort_bytes(k))
+            sc = torch.empty(L.mhb_count_solid_scratch_bytes(n), dtype=torch.uint8, device="cuda")
+            lib._check(L.mhb_count_solid(None, C.c_void_p(srt.data_ptr()), n, k, m, C.c_void_p(edges.data_ptr()),
+                                         C.c_void_p(aux.data_ptr()), cap, C.c_void_p(hist.data_ptr()), C.c_void_p(ns.data_ptr()),
+                                         C.c_void_p(sc.data_ptr()), sc.numel()))
+        torch.cuda.synchronize()
+        n_solid = int(ns[0].item())
+        out.append((edges[: n_solid * we].cpu().numpy().copy(), aux[:n_solid].cpu().numpy().copy(), hist.cpu().numpy().copy(), n_solid))
+    return out
+
+
+@pytest.mark.parametrize("case", ["reads30x", "all_distinct", "one_bucket_many_keys", "one_key_huge", "few_keys_high_mult",
+                                  "k21_reads", "m1", "m5", "tiny"])
+def test_hashed_count_matches_sort_and_count(case):
+    """mhb_count_solid_hashed (2 partition passes + per-bucket hash aggregation) gives the edges, aux flags, multiplicity
+    histogram and solid count of the full sort + mhb_count_solid, on real extractions and on adversarial key sets: a bucket
+    with more distinct keys than the table holds (sub-range retries), one key repeated beyond the 16-bit tally fields
+    (clamping between chunks), multiplicities above the shared-memory histogram"""
+    torch = _torch()
+    import ctypes as C
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(case.encode()))
+    k, m = 27, 2
+
+    def from_reads(n_reads, kk, genome):
+        b = synth.synth_reads_torch(n_reads, 150, genome, 0.01, 5, "cuda").reshape(-1)
+        b = torch.cat([b, torch.zeros(8, dtype=torch.int32, device="cuda")])
+        n = n_reads * (150 - kk)
+        a = torch.empty(n * 2 + 4, dtype=torch.int32, device="cuda")
+        rd = lib.DevReads(b.data_ptr(), b.numel(), n_reads, 150, None, None)
+        lib._check(lib.load().mhb_count_extract(None, C.byref(rd), kk, C.c_void_p(a.data_ptr()), n, None, 0))
+        return a[: n * 2].cpu().numpy().view(np.uint32).reshape(n, 2)
+
+    def with_pn(keys):  # keys: uint64 with the low 8 bits free -> records with random prev/next (0..4 each)
+        pn = (rng.integers(0, 5, len(keys)) << 3 | rng.integers(0, 5, len(keys))).astype(np.uint64)
+        v = (keys & ~np.uint64(0xFF)) | pn
+        return np.stack([(v >> np.uint64(32)).astype(np.uint32), (v & np.uint64(0xFFFFFFFF)).astype(np.uint32)], axis=1)
+
+    if case == "reads30x":
+        recs = from_reads(150_000, 27, 750_000)
+    elif case == "k21_reads":
+        k = 21
+        recs = from_reads(60_000, 21, 300_000)
+    elif case == "m1":
+        m = 1
+        recs = from_reads(20_000, 27, 100_000)
+    elif case == "m5":
+        m = 5
+        recs = from_reads(60_000, 27, 200_000)
+    elif case == "all_distinct":
+        recs = with_pn(rng.integers(0, 2 ** 63, 400_000, dtype=np.uint64) << np.uint64(1))
+    elif case == "one_bucket_many_keys":  # 60 k distinct keys in ONE 16-bit bucket, each 1..3 times
+        base = rng.integers(0, 2 ** 40, 60_000, dtype=np.uint64) << np.uint64(8) | (np.uint64(0x1234) << np.uint64(48))
+        recs = with_pn(np.repeat(base, rng.integers(1, 4, len(base))))
+    elif case == "one_key_huge":  # one key 200 k times (> 65535: tally clamp) + noise in the same bucket
+        hot = np.full(200_000, (0x00FF << 48) | (0xABCDEF << 8), np.uint64)
+        noise = rng.integers(0, 2 ** 40, 5_000, dtype=np.uint64) << np.uint64(8) | (np.uint64(0x00FF) << np.uint64(48))
+        recs = with_pn(np.concatenate([hot, noise]))
+    elif case == "few_keys_high_mult":  # multiplicities 1000..3000: above the shared-memory histogram range
+        base = rng.integers(0, 2 ** 55, 300, dtype=np.uint64) << np.uint64(8)
+        recs = with_pn(np.repeat(base, rng.integers(1000, 3000, len(base))))
+    else:  # tiny
+        recs = with_pn(np.array([5 << 8, 5 << 8, 7 << 8], np.uint64))
+    recs = recs[rng.permutation(len(recs))]
+    (e0, a0, h0, n0), (e1, a1, h1, n1) = _count_both_ways(recs, k, m)
+    assert n0 == n1 and (n0 > 0 or case == "all_distinct")
+    assert (e0 == e1).all() and (a0 == a1).all() and (h0 == h1).all()
