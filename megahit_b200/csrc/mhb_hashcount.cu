@@ -31,17 +31,19 @@ using namespace mhb;
 
 namespace {
 
-constexpr int kHcThreads = 512;
-constexpr int kHcSlots = 4096;                 // hash slots per CTA (power of two)
-constexpr int kHcMaxSolid = 1024;              // solid keys per sub-range (sort buffer)
+constexpr int kHcThreads = 256;
+constexpr int kHcSlots = 2048;                 // hash slots per CTA (power of two)
+constexpr int kHcHashBits = 11;
+constexpr int kHcMaxSolid = 512;               // solid keys per sub-range (ordering buffers)
 constexpr int kHcHist = 1024;                  // multiplicities < kHcHist are histogrammed in shared memory
 constexpr u64 kHcEmpty = ~0ull;
-constexpr u32 kHcSolidFlag = 0x80000000u;
-constexpr int kHcBatch = 4;                    // records per thread in flight while streaming a bucket
+constexpr int kHcBatch = 4;                    // records per thread in flight while streaming a slice
 constexpr u32 kRemBits = 42;                   // record bits 47..6
+constexpr u32 kHcHotCount = 256;               // keys this frequent may wrap a byte tally: they get exact 32-bit tallies
+constexpr int kHcHotRound = 32;                // ... this many at a time
 
 __device__ __forceinline__ u64 rec_key64(const uint2 r) { return ((u64)r.x << 32) | r.y; }
-__device__ __forceinline__ u32 hc_hash(u64 r) { return (u32)((r * 0x9E3779B97F4A7C15ull) >> (64 - 12)); }
+__device__ __forceinline__ u32 hc_hash(u64 r) { return (u32)((r * 0x9E3779B97F4A7C15ull) >> (64 - kHcHashBits)); }
 
 // bounds[b] = first record whose 16-bit prefix is >= b (b = 0..65536); the records are sorted on that prefix
 __global__ void k_bucket_bounds(const uint2 *__restrict__ recs, u64 n, u64 *__restrict__ bounds) {
@@ -56,25 +58,28 @@ __global__ void k_bucket_bounds(const uint2 *__restrict__ recs, u64 n, u64 *__re
   bounds[b] = lo;
 }
 
-constexpr int kHcCells = 1024;                 // counting-sort cells that order a sub-range's solid keys
-constexpr int kHcMaxOcc = 2900;                // occupied slots per sub-range (load factor 0.7)
+constexpr int kHcCells = 2 * kHcThreads;       // counting-sort cells that order a sub-range's solid keys
+constexpr int kHcMaxOcc = 1450;                // occupied slots per sub-range (load factor 0.7)
 constexpr int kHcMaxProbes = 96;
 constexpr int kHcStack = 72;
 
 struct HcShared {
   u64 keys[kHcSlots];
-  u32 cnt[kHcSlots];
-  uint16_t rk[kHcSlots];       // rank of a solid slot inside its sub-range
+  u32 cnt[kHcSlots];           // occurrences
+  u32 pt[kHcSlots];            // prev tallies, one byte per base (exact while the key has < 256 occurrences)
+  u32 nt[kHcSlots];            // next tallies
   uint16_t occ[kHcSlots];      // dense list of the occupied slots (judged and cleared through it)
-  u32 tally[kHcMaxSolid][4];   // prev01, prev23, next01, next23 as 16-bit fields; re-used as u64 tmp[] while ordering
   u64 sorted[kHcMaxSolid];     // rem42 << 22 | cnt16 << 6 | aux
+  u64 tmp[kHcMaxSolid];
   u32 cell_base[kHcCells];
   u32 cell_cur[kHcCells];
   u32 cta_hist[kHcHist];
+  u32 wide[kHcHotRound][8];    // exact tallies of the hot keys of the current round
+  uint16_t hot_slot[kHcMaxSolid];
   u64 st_prefix[kHcStack];
   u32 st_bits[kHcStack];
   u32 warp_sum[kHcThreads / 32];
-  u32 n_occ, n_solid, overflow, bucket, out_cursor, sp;
+  u32 n_occ, n_solid, n_hot, overflow, bucket, out_cursor, sp;
 };
 
 __device__ __forceinline__ u32 lane_lt_mask() { return (1u << (threadIdx.x & 31)) - 1u; }
@@ -110,28 +115,18 @@ __device__ __forceinline__ u32 hc_find(const HcShared &s, u64 r) {
   return h;
 }
 
-// multiplicity histogram contribution (+1 / -1) of the occupied slots; the singletons and doubletons of a sub-range
-// would serialise on one shared-memory counter, so they are counted with ballots
-__device__ __forceinline__ void hc_hist_update(HcShared &s, u32 n_occ, u64 *mul_hist, bool add) {
-  for (u32 i0 = 0; i0 < n_occ; i0 += kHcThreads) {
-    const u32 i = i0 + threadIdx.x;
-    const bool on = i < n_occ;
-    const u32 c = on ? s.cnt[s.occ[i]] : 0u;
+// take the multiplicity histogram contribution of the occupied slots back (a sub-range that has to be split after
+// it was judged)
+__device__ __forceinline__ void hc_hist_undo(HcShared &s, u32 n_occ, u64 *mul_hist) {
+  for (u32 i = threadIdx.x; i < n_occ; i += kHcThreads) {
+    const u32 c = s.cnt[s.occ[i]];
     const u32 c16 = c > 65535u ? 65535u : c;
-    const u32 ones = __ballot_sync(0xffffffffu, on && c16 == 1u), twos = __ballot_sync(0xffffffffu, on && c16 == 2u);
-    const u32 d = add ? 1u : 0xFFFFFFFFu;
-    if (on && c16 > 2u) {
-      if (c16 < (u32)kHcHist) atomicAdd(&s.cta_hist[c16], d);
-      else atomicAdd((unsigned long long *)&mul_hist[c16], add ? 1ull : ~0ull);
-    }
-    if ((threadIdx.x & 31) == 0) {
-      if (ones) atomicAdd(&s.cta_hist[1], add ? (u32)__popc(ones) : 0u - (u32)__popc(ones));
-      if (twos) atomicAdd(&s.cta_hist[2], add ? (u32)__popc(twos) : 0u - (u32)__popc(twos));
-    }
+    if (c16 < (u32)kHcHist) atomicAdd(&s.cta_hist[c16], 0xFFFFFFFFu);
+    else atomicAdd((unsigned long long *)&mul_hist[c16], ~0ull);
   }
 }
 
-// exclusive scan of s.cell_base[0 .. kHcCells) in place (kHcCells = 2 * kHcThreads)
+// exclusive scan of s.cell_base[0 .. kHcCells) in place (kHcCells = 2 * kHcThreads); also primes cell_cur
 __device__ __forceinline__ void hc_scan_cells(HcShared &s) {
   const u32 t = threadIdx.x, lane = t & 31, w = t >> 5;
   const u32 a = s.cell_base[2 * t], b = s.cell_base[2 * t + 1];
@@ -161,6 +156,10 @@ __device__ __forceinline__ void hc_scan_cells(HcShared &s) {
   __syncthreads();
 }
 
+__device__ __forceinline__ bool hc_any_byte_ge(u32 w, u32 m) {
+  return (w & 0xFFu) >= m || ((w >> 8) & 0xFFu) >= m || ((w >> 16) & 0xFFu) >= m || (w >> 24) >= m;
+}
+
 // first index q in [p, hi] that may start a slice: q == lo, q == hi, or the 24-bit prefix changes between q-1 and q
 // (records with equal keys share their prefix, so they never straddle such a boundary).  Block-wide.
 __device__ __forceinline__ u64 hc_align(const uint2 *__restrict__ recs, u64 p, u64 lo, u64 hi, u32 *s_min) {
@@ -181,12 +180,15 @@ __device__ __forceinline__ u64 hc_align(const uint2 *__restrict__ recs, u64 p, u
 
 // Work unit = a SLICE of the prefix-sorted records: bucket b (16-bit prefix) is cut into ceil(n_b / T) slices whose
 // boundaries are moved forward to the next change of the 24-bit prefix, so that a slice is a contiguous, key-closed
-// range read exactly once per sweep with every lane busy.  slice_off[b] = first slice id of bucket b (exclusive scan of
-// the per-bucket slice counts).  list: slice s's solid entries go to list[a_s / m + s ...) with a_s the slice's first
-// record (a slice of n records holds at most n / m solid keys and floor is super-additive: the areas never overlap).
-__global__ void __launch_bounds__(kHcThreads, 2)
+// range read once with every lane busy.  slice_off[b] = first slice id of bucket b (exclusive scan of the per-bucket
+// slice counts).  list: slice s's solid entries go to list[a_s / m + s ...) with a_s the slice's first record (a slice
+// of n records holds at most n / m solid keys and floor is super-additive: the areas never overlap).
+// One sweep per slice: occurrence count and the 4 + 4 prev / next tallies (kmer_counter.cpp:279-295) of every key, the
+// tallies as byte fields; only keys with >= 256 occurrences ("hot": a byte could wrap) get a second sweep with exact
+// 32-bit tallies, 32 keys at a time.
+__global__ void __launch_bounds__(kHcThreads, 3)
     k_hash_count(const uint2 *__restrict__ recs, const u64 *__restrict__ bounds, const u64 *__restrict__ slice_off,
-                 const u64 *__restrict__ n_slices_dev, u32 slice_records, int m, u32 *ticket, u64 *__restrict__ list,
+                 const u64 *__restrict__ n_slices_dev, int m, u32 *ticket, u64 *__restrict__ list,
                  u32 *__restrict__ slice_count, u64 *__restrict__ slice_base, u32 *__restrict__ slice_bucket, u64 *mul_hist,
                  u32 *err_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -196,10 +198,13 @@ __global__ void __launch_bounds__(kHcThreads, 2)
   for (u32 i = tid; i < kHcSlots; i += kHcThreads) {
     s.keys[i] = kHcEmpty;
     s.cnt[i] = 0;
+    s.pt[i] = 0;
+    s.nt[i] = 0;
   }
   if (tid == 0) s.n_occ = 0;
   __syncthreads();
   const u64 n_slices = *n_slices_dev;
+  const u32 um = (u32)m;
   while (true) {
     if (tid == 0) {
       const u32 sl = atomicAdd(ticket, 1u);
@@ -229,191 +234,194 @@ __global__ void __launch_bounds__(kHcThreads, 2)
       slice_base[sl] = base;
       slice_bucket[sl] = b;
       s.out_cursor = 0;
+      s.st_prefix[0] = 0;
+      s.st_bits[0] = 0;
+      s.sp = 1;
     }
     if (hi <= lo) {  // a 24-bit group longer than a slice swallowed this one
       if (tid == 0) slice_count[sl] = 0;
       __syncthreads();
       continue;
     }
-    (void)slice_records;
-    const u32 top_bits = 0;
     __syncthreads();
-    for (u64 top = 0; top < (1ull << top_bits); ++top) {
+    while (s.sp > 0) {
+      // ---------------- one key sub-range: the records whose remainder starts with `prefix` (`bits` bits) -------
+      const u32 sp = s.sp - 1;
+      const u64 prefix = s.st_prefix[sp];
+      const u32 bits = s.st_bits[sp];
+      __syncthreads();
       if (tid == 0) {
-        s.st_prefix[0] = top;
-        s.st_bits[0] = top_bits;
-        s.sp = 1;
+        s.sp = sp;
+        s.n_solid = 0;
+        s.n_hot = 0;
+        s.overflow = 0;
       }
       __syncthreads();
-      while (s.sp > 0) {
-        // ---------------- one key sub-range: the records whose remainder starts with `prefix` (`bits` bits) -------
-        const u32 sp = s.sp - 1;
-        const u64 prefix = s.st_prefix[sp];
-        const u32 bits = s.st_bits[sp];
-        __syncthreads();
-        if (tid == 0) {
-          s.sp = sp;
-          s.n_solid = 0;
-          s.overflow = 0;
-        }
-        __syncthreads();
-        // ---- sweep 1: occurrence counts ----
-        for (u64 i0 = lo + tid; i0 < hi; i0 += (u64)kHcThreads * kHcBatch) {
-          uint2 v[kHcBatch];
+      // ---- the sweep: occurrence counts and byte tallies ----
+      for (u64 i0 = lo + tid; i0 < hi; i0 += (u64)kHcThreads * kHcBatch) {
+        uint2 v[kHcBatch];
 #pragma unroll
-          for (int j = 0; j < kHcBatch; ++j) {
-            const u64 i = i0 + (u64)j * kHcThreads;
-            v[j] = i < hi ? recs[i] : make_uint2(0, 0);
-          }
-#pragma unroll
-          for (int j = 0; j < kHcBatch; ++j) {
-            const u64 i = i0 + (u64)j * kHcThreads;
-            if (i >= hi) break;
-            const u64 r = (rec_key64(v[j]) >> 6) & ((1ull << kRemBits) - 1);
-            if (bits && (r >> (kRemBits - bits)) != prefix) continue;
-            const u32 h = hc_insert(s, r);
-            if (h == (u32)kHcSlots) s.overflow = 1;
-            else atomicAdd(&s.cnt[h], 1u);
-          }
-          if (s.overflow || s.n_occ > (u32)kHcMaxOcc) break;
+        for (int j = 0; j < kHcBatch; ++j) {
+          const u64 i = i0 + (u64)j * kHcThreads;
+          v[j] = i < hi ? recs[i] : make_uint2(0, 0);
         }
-        __syncthreads();
-        u32 n_occ = s.n_occ;
-        bool failed = s.overflow || n_occ > (u32)kHcMaxOcc;
-        if (n_occ > (u32)kHcSlots) n_occ = kHcSlots;
-        u32 ns = 0;
-        if (!failed) {
-          // ---- judge: multiplicity histogram, ranks for the keys that reached the solid threshold ----
-          hc_hist_update(s, n_occ, mul_hist, true);
-          for (u32 i0 = 0; i0 < n_occ; i0 += kHcThreads) {
-            const u32 i = i0 + tid;
-            const bool on = i < n_occ;
-            const u32 slot = on ? s.occ[i] : 0u;
-            const u32 c = on ? s.cnt[slot] : 0u;
-            const bool solid = on && (long long)c >= (long long)m;
-            const u32 sm_ = __ballot_sync(0xffffffffu, solid);
-            u32 wbase = 0;
-            if ((tid & 31) == 0 && sm_) wbase = atomicAdd(&s.n_solid, (u32)__popc(sm_));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (solid) {
-              const u32 rank = wbase + __popc(sm_ & lane_lt_mask());
-              if (rank < (u32)kHcMaxSolid) {
-                s.rk[slot] = (uint16_t)rank;
-                s.sorted[rank] = (s.keys[slot] << 22) | ((u64)(c > 65535u ? 65535u : c) << 6);
-                s.tally[rank][0] = s.tally[rank][1] = s.tally[rank][2] = s.tally[rank][3] = 0;
+#pragma unroll
+        for (int j = 0; j < kHcBatch; ++j) {
+          const u64 i = i0 + (u64)j * kHcThreads;
+          if (i >= hi) break;
+          const u64 key = rec_key64(v[j]);
+          const u64 r = (key >> 6) & ((1ull << kRemBits) - 1);
+          if (bits && (r >> (kRemBits - bits)) != prefix) continue;
+          const u32 h = hc_insert(s, r);
+          if (h == (u32)kHcSlots) {
+            s.overflow = 1;
+            continue;
+          }
+          atomicAdd(&s.cnt[h], 1u);
+          const u32 p = (u32)(key >> 3) & 7u, nx = (u32)key & 7u;
+          if (p < 4) atomicAdd(&s.pt[h], 1u << (8 * p));
+          if (nx < 4) atomicAdd(&s.nt[h], 1u << (8 * nx));
+        }
+        if (s.overflow || s.n_occ > (u32)kHcMaxOcc) break;
+      }
+      __syncthreads();
+      u32 n_occ = s.n_occ;
+      bool failed = s.overflow || n_occ > (u32)kHcMaxOcc;
+      if (n_occ > (u32)kHcSlots) n_occ = kHcSlots;
+      u32 ns = 0;
+      if (!failed) {
+        // ---- judge: multiplicity histogram; the keys that reached the solid threshold get a rank and their flags ----
+        for (u32 i0 = 0; i0 < n_occ; i0 += kHcThreads) {
+          const u32 i = i0 + tid;
+          const bool on = i < n_occ;
+          const u32 slot = on ? s.occ[i] : 0u;
+          const u32 c = on ? s.cnt[slot] : 0u;
+          const u32 c16 = c > 65535u ? 65535u : c;
+          const u32 ones = __ballot_sync(0xffffffffu, on && c16 == 1u), twos = __ballot_sync(0xffffffffu, on && c16 == 2u);
+          if (on && c16 > 2u) {
+            if (c16 < (u32)kHcHist) atomicAdd(&s.cta_hist[c16], 1u);
+            else atomicAdd((unsigned long long *)&mul_hist[c16], 1ull);
+          }
+          const bool solid = on && c >= um;
+          const u32 sm_ = __ballot_sync(0xffffffffu, solid);
+          u32 wbase = 0;
+          if ((tid & 31) == 0) {
+            if (ones) atomicAdd(&s.cta_hist[1], (u32)__popc(ones));
+            if (twos) atomicAdd(&s.cta_hist[2], (u32)__popc(twos));
+            if (sm_) wbase = atomicAdd(&s.n_solid, (u32)__popc(sm_));
+          }
+          wbase = __shfl_sync(0xffffffffu, wbase, 0);
+          if (solid) {
+            const u32 rank = wbase + __popc(sm_ & lane_lt_mask());
+            if (rank < (u32)kHcMaxSolid) {
+              u64 e = (s.keys[slot] << 22) | ((u64)c16 << 6);
+              if (c >= kHcHotCount) {  // byte tallies may have wrapped: exact tallies in a second sweep
+                const u32 hi_ = atomicAdd(&s.n_hot, 1u);
+                if (hi_ < (u32)kHcMaxSolid) s.hot_slot[hi_] = (uint16_t)slot;
+                s.pt[slot] = hi_;   // index among the hot keys
+                s.nt[slot] = rank;  // where its entry lives
+              } else {
+                e |= (hc_any_byte_ge(s.pt[slot], um) ? 0ull : 1ull) | (hc_any_byte_ge(s.nt[slot], um) ? 0ull : 2ull);
               }
+              s.sorted[rank] = e;
+            }
+          }
+        }
+        __syncthreads();
+        ns = s.n_solid;
+        if (ns > (u32)kHcMaxSolid) {  // too many solid keys for the ordering buffers: take the histogram back, split
+          hc_hist_undo(s, n_occ, mul_hist);
+          failed = true;
+        }
+      }
+      if (!failed && ns) {
+        const u32 n_hot = s.n_hot;
+        for (u32 h0 = 0; h0 < n_hot; h0 += kHcHotRound) {
+          // ---- exact prev / next tallies of up to 32 hot keys: one more sweep over the slice ----
+          for (u32 i = tid; i < (u32)kHcHotRound * 8; i += kHcThreads) s.wide[i >> 3][i & 7] = 0;
+          __syncthreads();
+          for (u64 i0 = lo + tid; i0 < hi; i0 += (u64)kHcThreads * kHcBatch) {
+            uint2 v[kHcBatch];
+#pragma unroll
+            for (int j = 0; j < kHcBatch; ++j) {
+              const u64 i = i0 + (u64)j * kHcThreads;
+              v[j] = i < hi ? recs[i] : make_uint2(0, 0);
+            }
+#pragma unroll
+            for (int j = 0; j < kHcBatch; ++j) {
+              const u64 i = i0 + (u64)j * kHcThreads;
+              if (i >= hi) break;
+              const u64 key = rec_key64(v[j]);
+              const u64 r = (key >> 6) & ((1ull << kRemBits) - 1);
+              if (bits && (r >> (kRemBits - bits)) != prefix) continue;
+              const u32 slot = hc_find(s, r);
+              const u32 c = s.cnt[slot];
+              if (c < kHcHotCount || c < um) continue;
+              const u32 hidx = s.pt[slot] - h0;
+              if (hidx >= (u32)kHcHotRound) continue;
+              const u32 p = (u32)(key >> 3) & 7u, nx = (u32)key & 7u;
+              if (p < 4) atomicAdd(&s.wide[hidx][p], 1u);
+              if (nx < 4) atomicAdd(&s.wide[hidx][4 + nx], 1u);
             }
           }
           __syncthreads();
-          ns = s.n_solid;
-          if (ns > (u32)kHcMaxSolid) {  // too many solid keys for the ordering buffers: take the histogram back, split
-            hc_hist_update(s, n_occ, mul_hist, false);
-            failed = true;
-          }
-        }
-        if (!failed && ns) {
-          // ---- sweep 2: prev / next tallies of the solid keys (16-bit fields; clamped to m between chunks of 32768
-          // records so that a field can never wrap, whatever the multiplicity) ----
-          const u64 chunk = 32768;
-          for (u64 c0 = lo; c0 < hi; c0 += chunk) {
-            const u64 c1 = c0 + chunk < hi ? c0 + chunk : hi;
-            for (u64 i0 = c0 + tid; i0 < c1; i0 += (u64)kHcThreads * kHcBatch) {
-              uint2 v[kHcBatch];
-#pragma unroll
-              for (int j = 0; j < kHcBatch; ++j) {
-                const u64 i = i0 + (u64)j * kHcThreads;
-                v[j] = i < c1 ? recs[i] : make_uint2(0, 0);
-              }
-#pragma unroll
-              for (int j = 0; j < kHcBatch; ++j) {
-                const u64 i = i0 + (u64)j * kHcThreads;
-                if (i >= c1) break;
-                const u64 key = rec_key64(v[j]);
-                const u64 r = (key >> 6) & ((1ull << kRemBits) - 1);
-                if (bits && (r >> (kRemBits - bits)) != prefix) continue;
-                const u32 slot = hc_find(s, r);
-                if ((long long)s.cnt[slot] < (long long)m) continue;
-                const u32 rank = s.rk[slot];
-                const u32 p = (u32)(key >> 3) & 7u, nx = (u32)key & 7u;
-                if (p < 4) atomicAdd(&s.tally[rank][p >> 1], 1u << (16 * (p & 1)));
-                if (nx < 4) atomicAdd(&s.tally[rank][2 + (nx >> 1)], 1u << (16 * (nx & 1)));
-              }
-            }
-            if (c1 < hi) {  // more chunks follow: clamp
-              __syncthreads();
-              for (u32 i = tid; i < ns * 4; i += kHcThreads) {
-                const u32 t = s.tally[i >> 2][i & 3];
-                u32 a = t & 0xFFFFu, bb = t >> 16;
-                a = a > (u32)m ? (u32)m : a;
-                bb = bb > (u32)m ? (u32)m : bb;
-                s.tally[i >> 2][i & 3] = a | (bb << 16);
-              }
-              __syncthreads();
-            }
-          }
-          __syncthreads();
-          // ---- aux flags ----
-          for (u32 i = tid; i < ns; i += kHcThreads) {
+          for (u32 i = tid; i < (u32)kHcHotRound && h0 + i < n_hot; i += kHcThreads) {
             bool has_in = false, has_out = false;
 #pragma unroll
-            for (int w = 0; w < 2; ++w) {
-              const u32 tp = s.tally[i][w], tn = s.tally[i][2 + w];
-              has_in = has_in || (tp & 0xFFFFu) >= (u32)m || (tp >> 16) >= (u32)m;
-              has_out = has_out || (tn & 0xFFFFu) >= (u32)m || (tn >> 16) >= (u32)m;
+            for (int c = 0; c < 4; ++c) {
+              has_in = has_in || s.wide[i][c] >= um;
+              has_out = has_out || s.wide[i][4 + c] >= um;
             }
-            s.sorted[i] |= (has_in ? 0ull : 1ull) | (has_out ? 0ull : 2ull);
-          }
-          for (u32 i = tid; i < (u32)kHcCells; i += kHcThreads) s.cell_base[i] = 0;
-          __syncthreads();
-          // ---- order the solid keys: counting sort on the next 10 key bits, ties ranked inside their cell ----
-          u64 *tmp = reinterpret_cast<u64 *>(&s.tally[0][0]);
-          const u32 cshift = 22 + (kRemBits - 10);  // entry bits 63..22 hold the remainder
-          for (u32 i = tid; i < ns; i += kHcThreads) atomicAdd(&s.cell_base[(u32)((s.sorted[i] << bits) >> cshift)], 1u);
-          __syncthreads();
-          hc_scan_cells(s);
-          for (u32 i = tid; i < ns; i += kHcThreads) {
-            const u64 e = s.sorted[i];
-            tmp[atomicAdd(&s.cell_cur[(u32)((e << bits) >> cshift)], 1u)] = e;
+            s.sorted[s.nt[s.hot_slot[h0 + i]]] |= (has_in ? 0ull : 1ull) | (has_out ? 0ull : 2ull);
           }
           __syncthreads();
-          const u32 at = s.out_cursor;
-          for (u32 i = tid; i < ns; i += kHcThreads) {
-            const u64 e = tmp[i];
-            const u32 c = (u32)((e << bits) >> cshift);
-            const u32 b0 = s.cell_base[c], b1 = c + 1 < (u32)kHcCells ? s.cell_base[c + 1] : ns;
-            u32 r = b0;
-            for (u32 j = b0; j < b1; ++j) r += tmp[j] < e ? 1u : 0u;
-            list[base + at + r] = e;
-          }
-          __syncthreads();
-          if (tid == 0) s.out_cursor = at + ns;
         }
-        // ---- clear the table through the dense list ----
-        for (u32 i = tid; i < n_occ; i += kHcThreads) {
-          const u32 slot = s.occ[i];
-          s.keys[slot] = kHcEmpty;
-          s.cnt[slot] = 0;
-        }
-        if (n_occ >= (u32)kHcSlots)  // the list itself overflowed: wipe everything
-          for (u32 i = tid; i < kHcSlots; i += kHcThreads) {
-            s.keys[i] = kHcEmpty;
-            s.cnt[i] = 0;
-          }
+        // ---- order the solid keys: counting sort on the next 9 key bits, ties ranked inside their cell ----
+        for (u32 i = tid; i < (u32)kHcCells; i += kHcThreads) s.cell_base[i] = 0;
         __syncthreads();
-        if (tid == 0) {
-          s.n_occ = 0;
-          if (failed) {  // split this sub-range in four (ascending order is kept: the smallest child is popped first)
-            if (bits + 2 > kRemBits || s.sp + 4 > (u32)kHcStack) atomicExch(err_flag, 1u);
-            else
-              for (int c = 3; c >= 0; --c) {
-                s.st_prefix[s.sp] = (prefix << 2) | (u64)c;
-                s.st_bits[s.sp] = bits + 2;
-                ++s.sp;
-              }
-          }
+        const u32 cshift = 22 + (kRemBits - 9);  // entry bits 63..22 hold the remainder; 512 cells
+        for (u32 i = tid; i < ns; i += kHcThreads) atomicAdd(&s.cell_base[(u32)((s.sorted[i] << bits) >> cshift)], 1u);
+        __syncthreads();
+        hc_scan_cells(s);
+        for (u32 i = tid; i < ns; i += kHcThreads) {
+          const u64 e = s.sorted[i];
+          s.tmp[atomicAdd(&s.cell_cur[(u32)((e << bits) >> cshift)], 1u)] = e;
         }
         __syncthreads();
+        const u32 at = s.out_cursor;
+        for (u32 i = tid; i < ns; i += kHcThreads) {
+          const u64 e = s.tmp[i];
+          const u32 c = (u32)((e << bits) >> cshift);
+          const u32 b0 = s.cell_base[c], b1 = c + 1 < (u32)kHcCells ? s.cell_base[c + 1] : ns;
+          u32 r = b0;
+          for (u32 j = b0; j < b1; ++j) r += s.tmp[j] < e ? 1u : 0u;
+          list[base + at + r] = e;
+        }
+        __syncthreads();
+        if (tid == 0) s.out_cursor = at + ns;
       }
+      // ---- clear the table through the dense list ----
+      for (u32 i = tid; i < n_occ; i += kHcThreads) {
+        const u32 slot = s.occ[i];
+        s.keys[slot] = kHcEmpty;
+        s.cnt[slot] = 0;
+        s.pt[slot] = 0;
+        s.nt[slot] = 0;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        s.n_occ = 0;
+        if (failed) {  // split this sub-range in four (ascending order is kept: the smallest child is popped first)
+          if (bits + 2 > kRemBits || s.sp + 4 > (u32)kHcStack) atomicExch(err_flag, 1u);
+          else
+            for (int c = 3; c >= 0; --c) {
+              s.st_prefix[s.sp] = (prefix << 2) | (u64)c;
+              s.st_bits[s.sp] = bits + 2;
+              ++s.sp;
+            }
+        }
+      }
+      __syncthreads();
     }
     // ---- the slice is complete ----
     if (tid == 0) slice_count[sl] = s.out_cursor;
@@ -472,7 +480,7 @@ int scan_counts(cudaStream_t st, const u32 *in, u64 n, u64 *out, u64 *total_dev,
   return MHB_OK;
 }
 
-constexpr u32 kHcSliceRecords = 6000;  // ~2200 distinct keys on 30x reads with 1 % errors (table limit 2900)
+constexpr u32 kHcSliceRecords = 3000;  // ~1100 distinct keys on 30x reads with 1 % errors (table limit 1450)
 
 struct HcLayout {
   size_t sort_ws, off_bounds, off_bcnt, off_soff, off_bsum, off_misc, off_scount, off_sdst, off_sbase, off_sbucket, off_list, total;
@@ -565,8 +573,8 @@ extern "C" int mhb_count_solid_hashed(void *stream, uint32_t *recs_a, uint32_t *
     if (bps < 1) return mhb_set_error(MHB_ERR_CUDA, "hash-count kernel does not fit an SM (%zu B shared memory)", smem);
     if (getenv("MHB_VERBOSE")) fprintf(stderr, "[mhb] hash count: %d threads, %zu B smem, %d CTA/SM\n", kHcThreads, smem, bps);
   }
-  k_hash_count<<<sm_count() * bps, kHcThreads, smem, st>>>(recs, bounds, slice_off, n_slices_dev, kHcSliceRecords, m, misc, list,
-                                                          slice_count, slice_base, slice_bucket, mul_hist, misc + 1);
+  k_hash_count<<<sm_count() * bps, kHcThreads, smem, st>>>(recs, bounds, slice_off, n_slices_dev, m, misc, list, slice_count,
+                                                          slice_base, slice_bucket, mul_hist, misc + 1);
   CK_LAUNCH();
   // 4. offsets + edges (the scan runs over the allocated maximum; unused slice ids hold zero)
   if (int rc = scan_counts(st, slice_count, L.max_slices, slice_dst, n_solid_out, bsum)) return rc;
