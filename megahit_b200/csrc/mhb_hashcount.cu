@@ -31,19 +31,16 @@ using namespace mhb;
 
 namespace {
 
-constexpr int kHcThreads = 256;
-constexpr int kHcSlots = 2048;                 // hash slots per CTA (power of two)
-constexpr int kHcHashBits = 11;
-constexpr int kHcMaxSolid = 512;               // solid keys per sub-range (ordering buffers)
 constexpr int kHcHist = 1024;                  // multiplicities < kHcHist are histogrammed in shared memory
 constexpr u64 kHcEmpty = ~0ull;
 constexpr int kHcBatch = 4;                    // records per thread in flight while streaming a slice
 constexpr u32 kRemBits = 42;                   // record bits 47..6
 constexpr u32 kHcHotCount = 256;               // keys this frequent may wrap a byte tally: they get exact 32-bit tallies
 constexpr int kHcHotRound = 32;                // ... this many at a time
+constexpr int kHcMaxProbes = 48;               // longer probe sequences = the table is too full for this sub-range
+constexpr int kHcStack = 72;
 
 __device__ __forceinline__ u64 rec_key64(const uint2 r) { return ((u64)r.x << 32) | r.y; }
-__device__ __forceinline__ u32 hc_hash(u64 r) { return (u32)((r * 0x9E3779B97F4A7C15ull) >> (64 - kHcHashBits)); }
 
 // bounds[b] = first record whose 16-bit prefix is >= b (b = 0..65536); the records are sorted on that prefix
 __global__ void k_bucket_bounds(const uint2 *__restrict__ recs, u64 n, u64 *__restrict__ bounds) {
@@ -58,76 +55,86 @@ __global__ void k_bucket_bounds(const uint2 *__restrict__ recs, u64 n, u64 *__re
   bounds[b] = lo;
 }
 
-constexpr int kHcCells = 2 * kHcThreads;       // counting-sort cells that order a sub-range's solid keys
-constexpr int kHcMaxOcc = 1450;                // occupied slots per sub-range (load factor 0.7)
-constexpr int kHcMaxProbes = 96;
-constexpr int kHcStack = 72;
+// Geometry of the hash kernel: THREADS per CTA, 2^LOG_SLOTS table slots, CTAS per SM.  The per-slice fixed costs
+// (barriers, table sweeps, the ordering scan) are amortised over more records by the larger geometries.
+template <int THREADS_, int LOG_SLOTS_, int CTAS_>
+struct HcGeom {
+  static constexpr int THREADS = THREADS_, LOG_SLOTS = LOG_SLOTS_, SLOTS = 1 << LOG_SLOTS_, CTAS = CTAS_;
+  static constexpr int MAX_SOLID = SLOTS / 4;   // solid keys per sub-range (ordering buffers)
+  static constexpr int CELLS = 2 * THREADS;     // counting-sort cells that order a sub-range's solid keys
+  static constexpr int LOG_CELLS = LOG_SLOTS_ - 2 >= 0 ? (THREADS_ == 256 ? 9 : (THREADS_ == 512 ? 10 : 11)) : 9;
+  static constexpr u32 SLICE = (u32)(SLOTS * 1.83);  // records per slice: ~0.68 x SLOTS distinct keys on 30x reads (swept)
+};
 
+template <class G>
 struct HcShared {
-  u64 keys[kHcSlots];
-  u32 cnt[kHcSlots];           // occurrences
-  u32 pt[kHcSlots];            // prev tallies, one byte per base (exact while the key has < 256 occurrences)
-  u32 nt[kHcSlots];            // next tallies
-  uint16_t occ[kHcSlots];      // dense list of the occupied slots (judged and cleared through it)
-  u64 sorted[kHcMaxSolid];     // rem42 << 22 | cnt16 << 6 | aux
-  u64 tmp[kHcMaxSolid];
-  u32 cell_base[kHcCells];
-  u32 cell_cur[kHcCells];
+  u64 keys[G::SLOTS];
+  u32 cnt[G::SLOTS];           // occurrences
+  u32 pt[G::SLOTS];            // prev tallies, one byte per base (exact while the key has < 256 occurrences)
+  u32 nt[G::SLOTS];            // next tallies
+  u64 sorted[G::MAX_SOLID];    // rem42 << 22 | cnt16 << 6 | aux
+  u64 tmp[G::MAX_SOLID];
+  u32 cell_base[G::CELLS];
+  u32 cell_cur[G::CELLS];
   u32 cta_hist[kHcHist];
   u32 wide[kHcHotRound][8];    // exact tallies of the hot keys of the current round
-  uint16_t hot_slot[kHcMaxSolid];
+  uint16_t hot_slot[G::MAX_SOLID];
   u64 st_prefix[kHcStack];
   u32 st_bits[kHcStack];
-  u32 warp_sum[kHcThreads / 32];
-  u32 n_occ, n_solid, n_hot, overflow, bucket, out_cursor, sp;
+  u32 warp_sum[G::THREADS / 32];
+  u32 n_solid, n_hot, overflow, bucket, out_cursor, sp;
 };
 
 __device__ __forceinline__ u32 lane_lt_mask() { return (1u << (threadIdx.x & 31)) - 1u; }
 
-// slot of key r, inserting it when absent (new slots are appended to the dense list with one warp-aggregated atomic).
-// Returns kHcSlots when the probe sequence gets too long: the sub-range holds too many distinct keys for the table.
-__device__ __forceinline__ u32 hc_insert(HcShared &s, u64 r) {
-  u32 h = hc_hash(r);
+// plain shared-memory reduction.  nvcc turns atomicAdd() on shared memory whose result is unused into a
+// MATCH.ANY-driven loop over the groups of lanes that hit the same address; with ~1 lane per address that is overhead.
+__device__ __forceinline__ void smem_add(u32 *p, u32 v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+template <class G>
+__device__ __forceinline__ u32 hc_hash(u64 r) { return (u32)((r * 0x9E3779B97F4A7C15ull) >> (64 - G::LOG_SLOTS)); }
+
+// slot of key r, inserting it when absent.  Returns SLOTS when the probe sequence gets too long: the sub-range holds
+// too many distinct keys for the table (the caller flags overflow and the sub-range is split).
+template <class G>
+__device__ __forceinline__ u32 hc_insert(HcShared<G> &s, u64 r) {
+  u32 h = hc_hash<G>(r);
   for (int probes = 0; probes < kHcMaxProbes; ++probes) {
     u64 cur = s.keys[h];
     if (cur == r) return h;
     if (cur == kHcEmpty) {
       cur = atomicCAS((unsigned long long *)&s.keys[h], kHcEmpty, r);
-      if (cur == kHcEmpty) {
-        const u32 am = __activemask();
-        const int leader = __ffs(am) - 1;
-        u32 basep = 0;
-        if ((int)(threadIdx.x & 31) == leader) basep = atomicAdd(&s.n_occ, (u32)__popc(am));
-        basep = __shfl_sync(am, basep, leader);
-        const u32 pos = basep + __popc(am & lane_lt_mask());
-        if (pos < (u32)kHcSlots) s.occ[pos] = (uint16_t)h;
-        return h;
-      }
-      if (cur == r) return h;
+      if (cur == kHcEmpty || cur == r) return h;
     }
-    h = (h + 1) & (kHcSlots - 1);
+    h = (h + 1) & (G::SLOTS - 1);
   }
-  return kHcSlots;
+  return G::SLOTS;
 }
-__device__ __forceinline__ u32 hc_find(const HcShared &s, u64 r) {
-  u32 h = hc_hash(r);
-  while (s.keys[h] != r) h = (h + 1) & (kHcSlots - 1);
+template <class G>
+__device__ __forceinline__ u32 hc_find(const HcShared<G> &s, u64 r) {
+  u32 h = hc_hash<G>(r);
+  while (s.keys[h] != r) h = (h + 1) & (G::SLOTS - 1);
   return h;
 }
 
 // take the multiplicity histogram contribution of the occupied slots back (a sub-range that has to be split after
 // it was judged)
-__device__ __forceinline__ void hc_hist_undo(HcShared &s, u32 n_occ, u64 *mul_hist) {
-  for (u32 i = threadIdx.x; i < n_occ; i += kHcThreads) {
-    const u32 c = s.cnt[s.occ[i]];
+template <class G>
+__device__ __forceinline__ void hc_hist_undo(HcShared<G> &s, u64 *mul_hist) {
+  for (u32 i = threadIdx.x; i < (u32)G::SLOTS; i += G::THREADS) {
+    if (s.keys[i] == kHcEmpty) continue;
+    const u32 c = s.cnt[i];
     const u32 c16 = c > 65535u ? 65535u : c;
     if (c16 < (u32)kHcHist) atomicAdd(&s.cta_hist[c16], 0xFFFFFFFFu);
     else atomicAdd((unsigned long long *)&mul_hist[c16], ~0ull);
   }
 }
 
-// exclusive scan of s.cell_base[0 .. kHcCells) in place (kHcCells = 2 * kHcThreads); also primes cell_cur
-__device__ __forceinline__ void hc_scan_cells(HcShared &s) {
+// exclusive scan of s.cell_base[0 .. CELLS) in place (CELLS = 2 * THREADS); also primes cell_cur
+template <class G>
+__device__ __forceinline__ void hc_scan_cells(HcShared<G> &s) {
   const u32 t = threadIdx.x, lane = t & 31, w = t >> 5;
   const u32 a = s.cell_base[2 * t], b = s.cell_base[2 * t + 1];
   u32 v = a + b;
@@ -139,13 +146,13 @@ __device__ __forceinline__ void hc_scan_cells(HcShared &s) {
   if (lane == 31) s.warp_sum[w] = v;
   __syncthreads();
   if (w == 0) {
-    u32 x = lane < kHcThreads / 32 ? s.warp_sum[lane] : 0u;
+    u32 x = lane < G::THREADS / 32 ? s.warp_sum[lane] : 0u;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const u32 o = __shfl_up_sync(0xffffffffu, x, d);
       if ((int)lane >= d) x += o;
     }
-    if (lane < kHcThreads / 32) s.warp_sum[lane] = x;  // inclusive
+    if (lane < G::THREADS / 32) s.warp_sum[lane] = x;  // inclusive
   }
   __syncthreads();
   const u32 excl = v - (a + b) + (w ? s.warp_sum[w - 1] : 0u);
@@ -162,10 +169,11 @@ __device__ __forceinline__ bool hc_any_byte_ge(u32 w, u32 m) {
 
 // first index q in [p, hi] that may start a slice: q == lo, q == hi, or the 24-bit prefix changes between q-1 and q
 // (records with equal keys share their prefix, so they never straddle such a boundary).  Block-wide.
+template <int THREADS>
 __device__ __forceinline__ u64 hc_align(const uint2 *__restrict__ recs, u64 p, u64 lo, u64 hi, u32 *s_min) {
   if (p <= lo) return lo;
   if (p >= hi) return hi;
-  for (u64 q0 = p; q0 < hi; q0 += kHcThreads) {
+  for (u64 q0 = p; q0 < hi; q0 += THREADS) {
     __syncthreads();
     if (threadIdx.x == 0) *s_min = 0xFFFFFFFFu;
     __syncthreads();
@@ -186,22 +194,23 @@ __device__ __forceinline__ u64 hc_align(const uint2 *__restrict__ recs, u64 p, u
 // One sweep per slice: occurrence count and the 4 + 4 prev / next tallies (kmer_counter.cpp:279-295) of every key, the
 // tallies as byte fields; only keys with >= 256 occurrences ("hot": a byte could wrap) get a second sweep with exact
 // 32-bit tallies, 32 keys at a time.
-__global__ void __launch_bounds__(kHcThreads, 3)
+template <class G>
+__global__ void __launch_bounds__(G::THREADS, G::CTAS)
     k_hash_count(const uint2 *__restrict__ recs, const u64 *__restrict__ bounds, const u64 *__restrict__ slice_off,
                  const u64 *__restrict__ n_slices_dev, int m, u32 *ticket, u64 *__restrict__ list,
                  u32 *__restrict__ slice_count, u64 *__restrict__ slice_base, u32 *__restrict__ slice_bucket, u64 *mul_hist,
                  u32 *err_flag) {
+  constexpr int THREADS = G::THREADS, SLOTS = G::SLOTS, MAX_SOLID = G::MAX_SOLID, CELLS = G::CELLS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  HcShared &s = *reinterpret_cast<HcShared *>(smem_raw);
+  HcShared<G> &s = *reinterpret_cast<HcShared<G> *>(smem_raw);
   const u32 tid = threadIdx.x;
-  for (u32 i = tid; i < kHcHist; i += kHcThreads) s.cta_hist[i] = 0;
-  for (u32 i = tid; i < kHcSlots; i += kHcThreads) {
+  for (u32 i = tid; i < kHcHist; i += THREADS) s.cta_hist[i] = 0;
+  for (u32 i = tid; i < (u32)SLOTS; i += THREADS) {
     s.keys[i] = kHcEmpty;
     s.cnt[i] = 0;
     s.pt[i] = 0;
     s.nt[i] = 0;
   }
-  if (tid == 0) s.n_occ = 0;
   __syncthreads();
   const u64 n_slices = *n_slices_dev;
   const u32 um = (u32)m;
@@ -226,8 +235,8 @@ __global__ void __launch_bounds__(kHcThreads, 3)
     const u64 blo = bounds[b], bhi = bounds[b + 1];
     const u64 n_in_b = slice_off[b + 1] - slice_off[b], idx = sl - slice_off[b];
     const u64 step = (bhi - blo + n_in_b - 1) / n_in_b;
-    const u64 lo = hc_align(recs, blo + idx * step, blo, bhi, &s.overflow);
-    const u64 hi = idx + 1 == n_in_b ? bhi : hc_align(recs, blo + (idx + 1) * step, blo, bhi, &s.overflow);
+    const u64 lo = hc_align<THREADS>(recs, blo + idx * step, blo, bhi, &s.overflow);
+    const u64 hi = idx + 1 == n_in_b ? bhi : hc_align<THREADS>(recs, blo + (idx + 1) * step, blo, bhi, &s.overflow);
     __syncthreads();
     const u64 base = lo / (u64)m + sl;
     if (tid == 0) {
@@ -258,48 +267,45 @@ __global__ void __launch_bounds__(kHcThreads, 3)
       }
       __syncthreads();
       // ---- the sweep: occurrence counts and byte tallies ----
-      for (u64 i0 = lo + tid; i0 < hi; i0 += (u64)kHcThreads * kHcBatch) {
+      for (u64 i0 = lo + tid; i0 < hi; i0 += (u64)THREADS * kHcBatch) {
         uint2 v[kHcBatch];
 #pragma unroll
         for (int j = 0; j < kHcBatch; ++j) {
-          const u64 i = i0 + (u64)j * kHcThreads;
+          const u64 i = i0 + (u64)j * THREADS;
           v[j] = i < hi ? recs[i] : make_uint2(0, 0);
         }
 #pragma unroll
         for (int j = 0; j < kHcBatch; ++j) {
-          const u64 i = i0 + (u64)j * kHcThreads;
+          const u64 i = i0 + (u64)j * THREADS;
           if (i >= hi) break;
           const u64 key = rec_key64(v[j]);
           const u64 r = (key >> 6) & ((1ull << kRemBits) - 1);
           if (bits && (r >> (kRemBits - bits)) != prefix) continue;
-          const u32 h = hc_insert(s, r);
-          if (h == (u32)kHcSlots) {
+          const u32 h = hc_insert<G>(s, r);
+          if (h == (u32)SLOTS) {
             s.overflow = 1;
             continue;
           }
-          atomicAdd(&s.cnt[h], 1u);
+          smem_add(&s.cnt[h], 1u);
           const u32 p = (u32)(key >> 3) & 7u, nx = (u32)key & 7u;
-          if (p < 4) atomicAdd(&s.pt[h], 1u << (8 * p));
-          if (nx < 4) atomicAdd(&s.nt[h], 1u << (8 * nx));
+          if (p < 4) smem_add(&s.pt[h], 1u << (8 * p));
+          if (nx < 4) smem_add(&s.nt[h], 1u << (8 * nx));
         }
-        if (s.overflow || s.n_occ > (u32)kHcMaxOcc) break;
+        if (s.overflow) break;
       }
       __syncthreads();
-      u32 n_occ = s.n_occ;
-      bool failed = s.overflow || n_occ > (u32)kHcMaxOcc;
-      if (n_occ > (u32)kHcSlots) n_occ = kHcSlots;
+      bool failed = s.overflow != 0;
       u32 ns = 0;
       if (!failed) {
         // ---- judge: multiplicity histogram; the keys that reached the solid threshold get a rank and their flags ----
-        for (u32 i0 = 0; i0 < n_occ; i0 += kHcThreads) {
-          const u32 i = i0 + tid;
-          const bool on = i < n_occ;
-          const u32 slot = on ? s.occ[i] : 0u;
+        for (u32 i0 = 0; i0 < (u32)SLOTS; i0 += THREADS) {
+          const u32 slot = i0 + tid;
+          const bool on = s.keys[slot] != kHcEmpty;
           const u32 c = on ? s.cnt[slot] : 0u;
           const u32 c16 = c > 65535u ? 65535u : c;
           const u32 ones = __ballot_sync(0xffffffffu, on && c16 == 1u), twos = __ballot_sync(0xffffffffu, on && c16 == 2u);
           if (on && c16 > 2u) {
-            if (c16 < (u32)kHcHist) atomicAdd(&s.cta_hist[c16], 1u);
+            if (c16 < (u32)kHcHist) smem_add(&s.cta_hist[c16], 1u);
             else atomicAdd((unsigned long long *)&mul_hist[c16], 1ull);
           }
           const bool solid = on && c >= um;
@@ -313,11 +319,11 @@ __global__ void __launch_bounds__(kHcThreads, 3)
           wbase = __shfl_sync(0xffffffffu, wbase, 0);
           if (solid) {
             const u32 rank = wbase + __popc(sm_ & lane_lt_mask());
-            if (rank < (u32)kHcMaxSolid) {
+            if (rank < (u32)MAX_SOLID) {
               u64 e = (s.keys[slot] << 22) | ((u64)c16 << 6);
               if (c >= kHcHotCount) {  // byte tallies may have wrapped: exact tallies in a second sweep
                 const u32 hi_ = atomicAdd(&s.n_hot, 1u);
-                if (hi_ < (u32)kHcMaxSolid) s.hot_slot[hi_] = (uint16_t)slot;
+                if (hi_ < (u32)MAX_SOLID) s.hot_slot[hi_] = (uint16_t)slot;
                 s.pt[slot] = hi_;   // index among the hot keys
                 s.nt[slot] = rank;  // where its entry lives
               } else {
@@ -329,8 +335,8 @@ __global__ void __launch_bounds__(kHcThreads, 3)
         }
         __syncthreads();
         ns = s.n_solid;
-        if (ns > (u32)kHcMaxSolid) {  // too many solid keys for the ordering buffers: take the histogram back, split
-          hc_hist_undo(s, n_occ, mul_hist);
+        if (ns > (u32)MAX_SOLID) {  // too many solid keys for the ordering buffers: take the histogram back, split
+          hc_hist_undo<G>(s, mul_hist);
           failed = true;
         }
       }
@@ -338,34 +344,34 @@ __global__ void __launch_bounds__(kHcThreads, 3)
         const u32 n_hot = s.n_hot;
         for (u32 h0 = 0; h0 < n_hot; h0 += kHcHotRound) {
           // ---- exact prev / next tallies of up to 32 hot keys: one more sweep over the slice ----
-          for (u32 i = tid; i < (u32)kHcHotRound * 8; i += kHcThreads) s.wide[i >> 3][i & 7] = 0;
+          for (u32 i = tid; i < (u32)kHcHotRound * 8; i += THREADS) s.wide[i >> 3][i & 7] = 0;
           __syncthreads();
-          for (u64 i0 = lo + tid; i0 < hi; i0 += (u64)kHcThreads * kHcBatch) {
+          for (u64 i0 = lo + tid; i0 < hi; i0 += (u64)THREADS * kHcBatch) {
             uint2 v[kHcBatch];
 #pragma unroll
             for (int j = 0; j < kHcBatch; ++j) {
-              const u64 i = i0 + (u64)j * kHcThreads;
+              const u64 i = i0 + (u64)j * THREADS;
               v[j] = i < hi ? recs[i] : make_uint2(0, 0);
             }
 #pragma unroll
             for (int j = 0; j < kHcBatch; ++j) {
-              const u64 i = i0 + (u64)j * kHcThreads;
+              const u64 i = i0 + (u64)j * THREADS;
               if (i >= hi) break;
               const u64 key = rec_key64(v[j]);
               const u64 r = (key >> 6) & ((1ull << kRemBits) - 1);
               if (bits && (r >> (kRemBits - bits)) != prefix) continue;
-              const u32 slot = hc_find(s, r);
+              const u32 slot = hc_find<G>(s, r);
               const u32 c = s.cnt[slot];
               if (c < kHcHotCount || c < um) continue;
               const u32 hidx = s.pt[slot] - h0;
               if (hidx >= (u32)kHcHotRound) continue;
               const u32 p = (u32)(key >> 3) & 7u, nx = (u32)key & 7u;
-              if (p < 4) atomicAdd(&s.wide[hidx][p], 1u);
-              if (nx < 4) atomicAdd(&s.wide[hidx][4 + nx], 1u);
+              if (p < 4) smem_add(&s.wide[hidx][p], 1u);
+              if (nx < 4) smem_add(&s.wide[hidx][4 + nx], 1u);
             }
           }
           __syncthreads();
-          for (u32 i = tid; i < (u32)kHcHotRound && h0 + i < n_hot; i += kHcThreads) {
+          for (u32 i = tid; i < (u32)kHcHotRound && h0 + i < n_hot; i += THREADS) {
             bool has_in = false, has_out = false;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -376,23 +382,23 @@ __global__ void __launch_bounds__(kHcThreads, 3)
           }
           __syncthreads();
         }
-        // ---- order the solid keys: counting sort on the next 9 key bits, ties ranked inside their cell ----
-        for (u32 i = tid; i < (u32)kHcCells; i += kHcThreads) s.cell_base[i] = 0;
+        // ---- order the solid keys: counting sort on the next key bits, ties ranked inside their cell ----
+        for (u32 i = tid; i < (u32)CELLS; i += THREADS) s.cell_base[i] = 0;
         __syncthreads();
-        const u32 cshift = 22 + (kRemBits - 9);  // entry bits 63..22 hold the remainder; 512 cells
-        for (u32 i = tid; i < ns; i += kHcThreads) atomicAdd(&s.cell_base[(u32)((s.sorted[i] << bits) >> cshift)], 1u);
+        const u32 cshift = 22 + (kRemBits - G::LOG_CELLS);  // entry bits 63..22 hold the remainder
+        for (u32 i = tid; i < ns; i += THREADS) smem_add(&s.cell_base[(u32)((s.sorted[i] << bits) >> cshift)], 1u);
         __syncthreads();
-        hc_scan_cells(s);
-        for (u32 i = tid; i < ns; i += kHcThreads) {
+        hc_scan_cells<G>(s);
+        for (u32 i = tid; i < ns; i += THREADS) {
           const u64 e = s.sorted[i];
           s.tmp[atomicAdd(&s.cell_cur[(u32)((e << bits) >> cshift)], 1u)] = e;
         }
         __syncthreads();
         const u32 at = s.out_cursor;
-        for (u32 i = tid; i < ns; i += kHcThreads) {
+        for (u32 i = tid; i < ns; i += THREADS) {
           const u64 e = s.tmp[i];
           const u32 c = (u32)((e << bits) >> cshift);
-          const u32 b0 = s.cell_base[c], b1 = c + 1 < (u32)kHcCells ? s.cell_base[c + 1] : ns;
+          const u32 b0 = s.cell_base[c], b1 = c + 1 < (u32)CELLS ? s.cell_base[c + 1] : ns;
           u32 r = b0;
           for (u32 j = b0; j < b1; ++j) r += s.tmp[j] < e ? 1u : 0u;
           list[base + at + r] = e;
@@ -400,26 +406,22 @@ __global__ void __launch_bounds__(kHcThreads, 3)
         __syncthreads();
         if (tid == 0) s.out_cursor = at + ns;
       }
-      // ---- clear the table through the dense list ----
-      for (u32 i = tid; i < n_occ; i += kHcThreads) {
-        const u32 slot = s.occ[i];
-        s.keys[slot] = kHcEmpty;
-        s.cnt[slot] = 0;
-        s.pt[slot] = 0;
-        s.nt[slot] = 0;
+      // ---- clear the table ----
+      for (u32 i = tid; i < (u32)SLOTS; i += THREADS) {
+        s.keys[i] = kHcEmpty;
+        s.cnt[i] = 0;
+        s.pt[i] = 0;
+        s.nt[i] = 0;
       }
       __syncthreads();
-      if (tid == 0) {
-        s.n_occ = 0;
-        if (failed) {  // split this sub-range in four (ascending order is kept: the smallest child is popped first)
-          if (bits + 2 > kRemBits || s.sp + 4 > (u32)kHcStack) atomicExch(err_flag, 1u);
-          else
-            for (int c = 3; c >= 0; --c) {
-              s.st_prefix[s.sp] = (prefix << 2) | (u64)c;
-              s.st_bits[s.sp] = bits + 2;
-              ++s.sp;
-            }
-        }
+      if (tid == 0 && failed) {  // split this sub-range in four (ascending order is kept: the smallest child is popped first)
+        if (bits + 2 > kRemBits || s.sp + 4 > (u32)kHcStack) atomicExch(err_flag, 1u);
+        else
+          for (int c = 3; c >= 0; --c) {
+            s.st_prefix[s.sp] = (prefix << 2) | (u64)c;
+            s.st_bits[s.sp] = bits + 2;
+            ++s.sp;
+          }
       }
       __syncthreads();
     }
@@ -427,9 +429,13 @@ __global__ void __launch_bounds__(kHcThreads, 3)
     if (tid == 0) slice_count[sl] = s.out_cursor;
     __syncthreads();
   }
-  for (u32 i = tid; i < kHcHist; i += kHcThreads)
+  for (u32 i = tid; i < kHcHist; i += THREADS)
     if (s.cta_hist[i]) atomicAdd((unsigned long long *)&mul_hist[i], (unsigned long long)s.cta_hist[i]);
 }
+
+using HcGeomA = HcGeom<256, 11, 3>;
+using HcGeomB = HcGeom<512, 12, 2>;
+using HcGeomC = HcGeom<1024, 13, 1>;
 
 // per-bucket slice counts: ceil(n_b / T) (0 for an empty bucket)
 __global__ void k_slice_counts(const u64 *__restrict__ bounds, u32 T, u32 *__restrict__ cnt) {
@@ -480,7 +486,34 @@ int scan_counts(cudaStream_t st, const u32 *in, u64 n, u64 *out, u64 *total_dev,
   return MHB_OK;
 }
 
-constexpr u32 kHcSliceRecords = 3000;  // ~1100 distinct keys on 30x reads with 1 % errors (table limit 1450)
+// MHB_HC_GEOM = A | B | C selects the kernel geometry, MHB_HC_SLICE the records per slice (tuning hooks)
+static int hc_geom() {
+  static const int g = getenv("MHB_HC_GEOM") ? (getenv("MHB_HC_GEOM")[0] == 'A' ? 0 : (getenv("MHB_HC_GEOM")[0] == 'C' ? 2 : 1)) : 1;
+  return g;
+}
+static u32 hc_slice_records() {
+  const u32 def = hc_geom() == 0 ? HcGeomA::SLICE : (hc_geom() == 1 ? HcGeomB::SLICE : HcGeomC::SLICE);
+  static const u32 v = getenv("MHB_HC_SLICE") ? (u32)atoi(getenv("MHB_HC_SLICE")) : 0;
+  return v >= 256 && v <= 64000 ? v : def;
+}
+#define kHcSliceRecords hc_slice_records()
+
+template <class G>
+static int launch_hash_count(cudaStream_t st, const uint2 *recs, const u64 *bounds, const u64 *slice_off, const u64 *n_slices_dev,
+                             int m, u32 *misc, u64 *list, u32 *slice_count, u64 *slice_base, u32 *slice_bucket, u64 *mul_hist) {
+  static int bps = 0;
+  const size_t smem = sizeof(HcShared<G>);
+  if (!bps) {
+    CK(cudaFuncSetAttribute(k_hash_count<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_hash_count<G>, G::THREADS, smem));
+    if (bps < 1) return mhb_set_error(MHB_ERR_CUDA, "hash-count kernel does not fit an SM (%zu B shared memory)", smem);
+    if (getenv("MHB_VERBOSE")) fprintf(stderr, "[mhb] hash count: %d threads, %d slots, %zu B smem, %d CTA/SM, slice %u\n", G::THREADS, G::SLOTS, smem, bps, kHcSliceRecords);
+  }
+  k_hash_count<G><<<sm_count() * bps, G::THREADS, smem, st>>>(recs, bounds, slice_off, n_slices_dev, m, misc, list, slice_count,
+                                                             slice_base, slice_bucket, mul_hist, misc + 1);
+  CK_LAUNCH();
+  return MHB_OK;
+}
 
 struct HcLayout {
   size_t sort_ws, off_bounds, off_bcnt, off_soff, off_bsum, off_misc, off_scount, off_sdst, off_sbase, off_sbucket, off_list, total;
@@ -489,7 +522,7 @@ struct HcLayout {
 HcLayout hc_layout(uint64_t n, int32_t m) {
   HcLayout L;
   auto pad = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  L.max_slices = n / kHcSliceRecords + 65536 + 2;
+  L.max_slices = n / 256 + 65536 + 2;  // 256 = smallest slice size hc_slice_records() admits
   L.sort_ws = pad(mhb_sort_workspace_bytes(n, 2));
   size_t p = L.sort_ws;
   L.off_bounds = p;
@@ -565,17 +598,13 @@ extern "C" int mhb_count_solid_hashed(void *stream, uint32_t *recs_a, uint32_t *
   if (int rc = scan_counts(st, bcnt, 65536, slice_off, n_slices_dev, bsum)) return rc;
   CK(cudaMemcpyAsync(slice_off + 65536, n_slices_dev, 8, cudaMemcpyDeviceToDevice, st));
   // 3. per-slice hash aggregation
-  static int bps = 0;
-  const size_t smem = sizeof(HcShared);
-  if (!bps) {
-    CK(cudaFuncSetAttribute(k_hash_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_hash_count, kHcThreads, smem));
-    if (bps < 1) return mhb_set_error(MHB_ERR_CUDA, "hash-count kernel does not fit an SM (%zu B shared memory)", smem);
-    if (getenv("MHB_VERBOSE")) fprintf(stderr, "[mhb] hash count: %d threads, %zu B smem, %d CTA/SM\n", kHcThreads, smem, bps);
+  {
+    int rc;
+    if (hc_geom() == 0) rc = launch_hash_count<HcGeomA>(st, recs, bounds, slice_off, n_slices_dev, m, misc, list, slice_count, slice_base, slice_bucket, mul_hist);
+    else if (hc_geom() == 2) rc = launch_hash_count<HcGeomC>(st, recs, bounds, slice_off, n_slices_dev, m, misc, list, slice_count, slice_base, slice_bucket, mul_hist);
+    else rc = launch_hash_count<HcGeomB>(st, recs, bounds, slice_off, n_slices_dev, m, misc, list, slice_count, slice_base, slice_bucket, mul_hist);
+    if (rc) return rc;
   }
-  k_hash_count<<<sm_count() * bps, kHcThreads, smem, st>>>(recs, bounds, slice_off, n_slices_dev, m, misc, list, slice_count,
-                                                          slice_base, slice_bucket, mul_hist, misc + 1);
-  CK_LAUNCH();
   // 4. offsets + edges (the scan runs over the allocated maximum; unused slice ids hold zero)
   if (int rc = scan_counts(st, slice_count, L.max_slices, slice_dst, n_solid_out, bsum)) return rc;
   k_hash_gather<<<sm_count() * 4, 256, 0, st>>>(list, n_slices_dev, slice_count, slice_dst, slice_base, slice_bucket,

@@ -1035,9 +1035,10 @@ extern "C" int mhb_build_host(const mhb_build_args *args, mhb_build_result *res)
   uint32_t *d_all_edges = d_edges;
 
   // ---- H2D ----
-  // MHB_H2D_CHUNKS=C (opt-in, fixed-length libraries): the library is uploaded in C pieces on a copy stream and the
-  // edges of piece i are extracted while piece i+1 is still crossing PCIe, instead of upload-then-extract.
-  static const int h2d_chunks_env = getenv("MHB_H2D_CHUNKS") ? atoi(getenv("MHB_H2D_CHUNKS")) : 1;
+  // Fixed-length libraries are uploaded in C pieces on a copy stream and the edges of piece i are extracted while piece
+  // i+1 is still crossing PCIe, instead of upload-then-extract (C = 4; MHB_H2D_CHUNKS=1 restores the single copy;
+  // measured e2e 115.7 -> 112.5 ms on the bench workload, profiles/r2a_bench_chunks.json).
+  static const int h2d_chunks_env = getenv("MHB_H2D_CHUNKS") ? atoi(getenv("MHB_H2D_CHUNKS")) : 4;
   const bool chunked = h2d_chunks_env > 1 && ix.fixed_len >= k + 1 && n_reads >= (uint64_t)h2d_chunks_env * 64;
   t.start();
   CK(cudaMemsetAsync(d_mul_hist, 0, 65536 * 8, st));

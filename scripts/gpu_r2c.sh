@@ -17,8 +17,8 @@ PY
 }
 echo "== bench hashed"
 MHB_VERBOSE=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --count-mode hashed --e2e-steps 0 > gpurun_out/bench_hashed.json 2> gpurun_out/bench_hashed.err; summ gpurun_out/bench_hashed.json; grep "mhb\]" gpurun_out/bench_hashed.err | sort | uniq | head
-echo "== bench sort"
+echo "== bench sort (skipped)"; if false; then
 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --count-mode sort --e2e-steps 0 > gpurun_out/bench_sortmode.json 2> gpurun_out/bench_sortmode.err; summ gpurun_out/bench_sortmode.json
-echo "== ncu of the hash-count kernel (2 M reads)"
+fi; echo "== ncu of the hash-count kernel (2 M reads)"
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:k_hash_count -c 1 -o gpurun_out/r2c_hash_count python bench.py --steps 1 --warmup 1 --no-cpu-baseline --count-mode hashed --e2e-steps 0 --reads 2000000 > gpurun_out/ncu_hc.log 2>&1; echo rc=$?
 ls -la gpurun_out/*.ncu-rep 2>/dev/null

@@ -30,15 +30,17 @@ print("RESULT " + json.dumps({"sdbg": F.sha256(lib.sdbg_stream_from_table(g["buc
 
 @pytest.mark.parametrize("name,k,m,gold", [c for c in golden_cases() if c.values[0] in ("syn150_k27",)])
 def test_fused_build_with_chunked_upload_matches_reference(name, k, m, gold):
-    """MHB_H2D_CHUNKS: the library uploaded in pieces, extraction overlapping the copies -> same SdBG as the reference"""
+    """MHB_H2D_CHUNKS (default 4; here 3 and the single-copy path 1): the library uploaded in pieces, extraction
+    overlapping the copies -> same SdBG as the reference"""
     import json
-    env = dict(os.environ, MHB_H2D_CHUNKS="3")
-    p = subprocess.run([sys.executable, "-c", _CHILD, os.path.join(GOLDEN, name), str(k), str(m)], env=env,
-                       capture_output=True, text=True, timeout=300)
-    line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
-    assert line, p.stderr[-800:]
-    r = json.loads(line[-1][7:])
-    assert r["sdbg"] == gold["sdbg_sha256"] and r["edges"] == gold["edges_sha256"]
+    for chunks in ("3", "1"):
+        env = dict(os.environ, MHB_H2D_CHUNKS=chunks)
+        p = subprocess.run([sys.executable, "-c", _CHILD, os.path.join(GOLDEN, name), str(k), str(m)], env=env,
+                           capture_output=True, text=True, timeout=300)
+        line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+        assert line, p.stderr[-800:]
+        r = json.loads(line[-1][7:])
+        assert r["sdbg"] == gold["sdbg_sha256"] and r["edges"] == gold["edges_sha256"]
 
 
 # The new radix-pass variants (compact look-back descriptors, two-stream ranking) are deliberately NOT exercised here:
