@@ -394,6 +394,8 @@ class MultiGpuBuild:
         if timed:
             self._mark("exchange2")
         srt2 = self._sort_raw(own2, n_own2, self.W2, self.sbytes, "s")
+        if timed:
+            self._mark("s2s_sort")
         wpt = (k + 15) // 16
         cap_b = n_own2 * (4 + 4 * wpt) + 16
         out_bytes = self._buf("sdbg", cap_b, torch.uint8, slack=1.1)
@@ -598,7 +600,7 @@ def bench(args, bin_dev, bin_words, rank, world, device, metric, clocks=None):
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=device)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     stage = {}
-    names = ["t0", "extract", "c_plan", "exchange1", "sort1", "count", "mercy", "s_plan", "exchange2", "s2s"]
+    names = ["t0", "extract", "c_plan", "exchange1", "sort1", "count", "mercy", "s_plan", "exchange2", "s2s_sort", "s2s"]
     for a, b in zip(names[:-1], names[1:]):
         t = torch.tensor([np.mean([x.elapsed_time(y) for x, y in zip(job.times[a], job.times[b])])], dtype=torch.float64,
                          device=device)
