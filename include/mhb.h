@@ -130,6 +130,11 @@ int mhb_partition_scatter(void *stream, const uint32_t *recs, uint64_t n, uint32
  * [16..31] records this rank sends to owner o, [32..32+world] bounds}.  world <= 16. */
 int mhb_plan_partition(void *stream, const uint64_t *hist_all_dev, uint32_t world, uint32_t rank, uint32_t record_bytes,
                        const uint64_t *peer_base_host, uint8_t *owner_lut_dev, uint64_t *bin_addr_dev, uint64_t *plan_dev);
+/* The solid edges with aux != 0 (the "tips" the mercy bookkeeping needs from every rank), compacted in no particular
+ * order: tips_out gets records of mhb_words_per_edge(k) words, tip_aux_out their flags, *cursor_dev (device uint64,
+ * caller-zeroed) ends at their number (entries beyond `capacity` are counted but not stored). */
+int mhb_compact_tip_edges(void *stream, const uint32_t *edges, const uint8_t *aux, uint64_t n_solid, uint32_t k,
+                          uint32_t *tips_out, uint8_t *tip_aux_out, uint64_t capacity, uint64_t *cursor_dev);
 /* cudaMalloc'ed buffers that can be shared between the per-GPU processes of one node (CUDA IPC) */
 int mhb_dev_malloc(void **ptr, size_t bytes);
 int mhb_dev_free(void *ptr);
@@ -426,6 +431,17 @@ typedef struct {
 
 int mhb_count_run(const mhb_count_opts *opts);
 int mhb_seq2sdbg_run(const mhb_seq2sdbg_opts *opts);
+
+/* `count` on n_gpus GPUs of this node (fixed-length read libraries; anything else, or n_gpus <= 1, runs mhb_count_run).
+ * One worker process per GPU is forked; each takes a contiguous block of the reads, the records meet on the rank that
+ * owns their leading byte (fused partition + exchange into CUDA-IPC peer buffers), every rank counts its
+ * bucket range, the mercy searches are answered by the owners of the searched prefixes, and - because the solid
+ * edges are already on the devices - the k_min SdBG is built in the same run.  Files: rank r writes P.edges.<r> and
+ * P.sdbg.<r>, rank 0 the merged P.edges.info (num_files = n_gpus, edge_io_meta.h:25-44), P.sdbg_info
+ * (sdbg_meta.cpp:44-61), P.cand, P.counting, and the marker P.sdbg_fused ("k need_mercy n_gpus") that lets a following
+ * `seq2sdbg --need_mercy --input_prefix P -o P` return at once instead of rebuilding the same graph.  The caller must not
+ * have initialised CUDA in this process (the workers are forked). */
+int mhb_count_run_multi(const mhb_count_opts *opts, int n_gpus);
 
 /* ---------------------------------------------------------------------------------------------
  * Self-test hooks (host): build ONE sort record with the same __host__ __device__ code the kernels

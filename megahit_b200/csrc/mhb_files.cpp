@@ -339,6 +339,22 @@ extern "C" int mhb_seq2sdbg_run(const mhb_seq2sdbg_opts *o) {
   const uint32_t k = o->k;
   const double t0 = now_s();
 
+  // A multi-GPU `count` (mhb_count_run_multi) has already built this very graph - same prefix, same k, mercy edges
+  // included - while the solid edges were on the devices, and left a marker: nothing to do.
+  if (!input.empty() && input == prefix && contig.empty() && addi.empty() && local.empty() && o->need_mercy) {
+    std::ifstream mk(prefix + ".sdbg_fused");
+    unsigned mk_k = 0, mk_mercy = 0, mk_files = 0;
+    if (mk && (mk >> mk_k >> mk_mercy >> mk_files) && mk_k == k && mk_mercy == 1) {
+      bool all = std::ifstream(prefix + ".sdbg_info").good();
+      for (unsigned i = 0; i < mk_files; ++i) all = all && std::ifstream(prefix + ".sdbg." + std::to_string(i)).good();
+      if (all) {
+        XINFO("SdBG for k = %u was built by the %u-GPU count stage; nothing to do\n", k, mk_files);
+        XINFO("seq2sdbg done. Time elapsed: %.4f\n", now_s() - t0);
+        return MHB_OK;
+      }
+    }
+  }
+
   HostSeqs seqs;
   if (!input.empty()) {  // seq_to_sdbg.cpp:424-434
     EdgeMeta meta;

@@ -143,16 +143,26 @@ MHB_HD void make_s2s_record(const u32 *s, u32 nwords, u32 L, u32 k, u32 strand, 
 // ------------------------------------------------------------------------------------------------
 template <int WR>
 __device__ __forceinline__ void ld_rec(const u32 *base, u64 idx, u32 (&r)[WR]) {
-  if constexpr (WR == 2) {
-    uint2 v = reinterpret_cast<const uint2 *>(base)[idx];
-    r[0] = v.x;
-    r[1] = v.y;
-  } else if constexpr (WR == 4) {
-    uint4 v = reinterpret_cast<const uint4 *>(base)[idx];
-    r[0] = v.x;
-    r[1] = v.y;
-    r[2] = v.z;
-    r[3] = v.w;
+  // records start at multiples of their own size in buffers that are at least 16-byte aligned: widths that are a
+  // multiple of 4 (2) words move as 128-bit (64-bit) pieces - one access per 16 (8) bytes instead of per word
+  if constexpr (WR % 4 == 0) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(base + idx * WR);
+#pragma unroll
+    for (int j = 0; j < WR / 4; ++j) {
+      const uint4 v = p[j];
+      r[4 * j] = v.x;
+      r[4 * j + 1] = v.y;
+      r[4 * j + 2] = v.z;
+      r[4 * j + 3] = v.w;
+    }
+  } else if constexpr (WR % 2 == 0) {
+    const uint2 *p = reinterpret_cast<const uint2 *>(base + idx * WR);
+#pragma unroll
+    for (int j = 0; j < WR / 2; ++j) {
+      const uint2 v = p[j];
+      r[2 * j] = v.x;
+      r[2 * j + 1] = v.y;
+    }
   } else {
     const u32 *p = base + idx * WR;
 #pragma unroll
@@ -161,10 +171,14 @@ __device__ __forceinline__ void ld_rec(const u32 *base, u64 idx, u32 (&r)[WR]) {
 }
 template <int WR>
 __device__ __forceinline__ void st_rec(u32 *base, u64 idx, const u32 (&r)[WR]) {
-  if constexpr (WR == 2) {
-    reinterpret_cast<uint2 *>(base)[idx] = make_uint2(r[0], r[1]);
-  } else if constexpr (WR == 4) {
-    reinterpret_cast<uint4 *>(base)[idx] = make_uint4(r[0], r[1], r[2], r[3]);
+  if constexpr (WR % 4 == 0) {
+    uint4 *p = reinterpret_cast<uint4 *>(base + idx * WR);
+#pragma unroll
+    for (int j = 0; j < WR / 4; ++j) p[j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+  } else if constexpr (WR % 2 == 0) {
+    uint2 *p = reinterpret_cast<uint2 *>(base + idx * WR);
+#pragma unroll
+    for (int j = 0; j < WR / 2; ++j) p[j] = make_uint2(r[2 * j], r[2 * j + 1]);
   } else {
     u32 *p = base + idx * WR;
 #pragma unroll

@@ -99,7 +99,7 @@ int main_count(int argc, char **argv) {
   RssRecorder rec;
   const std::vector<Opt> opts = {{"kmer_k", "k", false},          {"min_kmer_frequency", "m", false}, {"host_mem", "", false},
                                  {"num_cpu_threads", "", false},  {"read_lib_file", "", false},       {"output_prefix", "", false},
-                                 {"mem_flag", "", false}};
+                                 {"mem_flag", "", false},         {"gpus", "", false}};
   const char *usage = "Usage: sdbg_builder count --input_file fastx_file -o out";
   std::map<std::string, std::string> v;
   std::string err;
@@ -116,7 +116,9 @@ int main_count(int argc, char **argv) {
   o.output_prefix = out.c_str();
   if (lib.empty()) return fail_usage("No read library configuration file!", usage);
   if (o.host_mem == 0) return fail_usage("Please specify the host memory!", usage);
-  if (int rc = mhb_count_run(&o)) {
+  // --gpus N / MHB_GPUS=N (not an option of the reference, which the Python driver never passes): one worker per GPU
+  const int gpus = v.count("gpus") ? atoi(v["gpus"].c_str()) : (getenv("MHB_GPUS") ? atoi(getenv("MHB_GPUS")) : 1);
+  if (int rc = gpus > 1 ? mhb_count_run_multi(&o, gpus) : mhb_count_run(&o)) {
     fprintf(stderr, "FATAL megahit_b200: %s\n", mhb_last_error());
     (void)rc;
     exit(1);

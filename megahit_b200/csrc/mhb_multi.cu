@@ -107,6 +107,35 @@ extern "C" int mhb_plan_partition(void *stream, const uint64_t *hist_all_dev, ui
 }
 
 // ------------------------------------------------------------------------------------------------
+// tip edges (aux != 0) of a rank, compacted for the exchange (order is irrelevant: they go into a hash set)
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void k_compact_tips(const u32 *__restrict__ edges, const uint8_t *__restrict__ aux, u64 n, u32 we,
+                               u32 *__restrict__ tips, uint8_t *__restrict__ tip_aux, u64 capacity, unsigned long long *cursor) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const uint8_t a = aux[i];
+    if (!a) continue;
+    const u64 at = atomicAdd(cursor, 1ull);
+    if (at >= capacity) continue;
+    for (u32 w = 0; w < we; ++w) tips[at * we + w] = edges[i * we + w];
+    tip_aux[at] = a;
+  }
+}
+}  // namespace
+
+extern "C" int mhb_compact_tip_edges(void *stream, const uint32_t *edges, const uint8_t *aux, uint64_t n_solid, uint32_t k,
+                                     uint32_t *tips_out, uint8_t *tip_aux_out, uint64_t capacity, uint64_t *cursor_dev) {
+  if (n_solid == 0) return MHB_OK;
+  if (!edges || !aux || !tips_out || !tip_aux_out || !cursor_dev) return mhb_set_error(MHB_ERR_ARG, "null buffer");
+  u64 g = (n_solid + 255) / 256;
+  if (g > (u64)sm_count() * 16) g = (u64)sm_count() * 16;
+  k_compact_tips<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(edges, aux, n_solid, words_per_edge(k), tips_out, tip_aux_out,
+                                                              capacity, (unsigned long long *)cursor_dev);
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // mercy searches restricted to the owned bucket range
 // ------------------------------------------------------------------------------------------------
 namespace {

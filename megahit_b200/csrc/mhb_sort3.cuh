@@ -72,14 +72,17 @@ struct SortCfg3 {
 // the DRAM latency of the loads hides behind the look-back and the scatter.  asm volatile pins the loads there.
 template <int WR>
 __device__ __forceinline__ void ld_rec_pinned(const u32 *base, u64 idx, u32 (&r)[WR]) {
-  if constexpr (WR == 2) {
-    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "l"(base + idx * 2));
-  } else if constexpr (WR == 4) {
-    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "l"(base + idx * 4));
+  const u32 *p = base + idx * WR;
+  if constexpr (WR % 4 == 0) {
+#pragma unroll
+    for (int j = 0; j < WR; j += 4)
+      asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(r[j]), "=r"(r[j + 1]), "=r"(r[j + 2]), "=r"(r[j + 3])
+                   : "l"(p + j));
+  } else if constexpr (WR % 2 == 0) {
+#pragma unroll
+    for (int j = 0; j < WR; j += 2) asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r[j]), "=r"(r[j + 1]) : "l"(p + j));
   } else {
-    const u32 *p = base + idx * WR;
 #pragma unroll
     for (int j = 0; j < WR; ++j) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r[j]) : "l"(p + j));
   }
@@ -92,10 +95,13 @@ __device__ __forceinline__ void ld_rec_pinned(const u32 *base, u64 idx, u32 (&r)
 // written by them: s_recs/s_glob are complete before the barrier that precedes the scatter.
 template <int WR>
 __device__ __forceinline__ void st_global_rec(u64 addr, const u32 (&q)[WR]) {
-  if constexpr (WR == 2) {
-    asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(addr), "r"(q[0]), "r"(q[1]));
-  } else if constexpr (WR == 4) {
-    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]));
+  if constexpr (WR % 4 == 0) {
+#pragma unroll
+    for (int j = 0; j < WR; j += 4)
+      asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr + 4 * j), "r"(q[j]), "r"(q[j + 1]), "r"(q[j + 2]), "r"(q[j + 3]));
+  } else if constexpr (WR % 2 == 0) {
+#pragma unroll
+    for (int j = 0; j < WR; j += 2) asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(addr + 4 * j), "r"(q[j]), "r"(q[j + 1]));
   } else {
 #pragma unroll
     for (int j = 0; j < WR; ++j) asm volatile("st.global.u32 [%0], %1;" ::"l"(addr + 4 * j), "r"(q[j]));
@@ -116,10 +122,13 @@ __device__ __forceinline__ void red_shared_inc(u32 *p) {
 template <int WR>
 __device__ __forceinline__ void st_shared_rec(u32 *base, u32 idx, const u32 (&q)[WR]) {
   const u32 a = smem_u32(base) + idx * (WR * 4);
-  if constexpr (WR == 2) {
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(q[0]), "r"(q[1]));
-  } else if constexpr (WR == 4) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]));
+  if constexpr (WR % 4 == 0) {
+#pragma unroll
+    for (int j = 0; j < WR; j += 4)
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a + 4 * j), "r"(q[j]), "r"(q[j + 1]), "r"(q[j + 2]), "r"(q[j + 3]));
+  } else if constexpr (WR % 2 == 0) {
+#pragma unroll
+    for (int j = 0; j < WR; j += 2) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a + 4 * j), "r"(q[j]), "r"(q[j + 1]));
   } else {
 #pragma unroll
     for (int j = 0; j < WR; ++j) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a + 4 * j), "r"(q[j]));

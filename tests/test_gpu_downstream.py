@@ -155,3 +155,50 @@ def test_reference_python_driver_runs_on_our_core(tmp_path):
             log = open(out / "log").read()
             assert "megahit_b200" in log, "the driver's log does not show our core running count/seq2sdbg"
     assert finals["ours"] and finals["ours"] == finals["ref"]
+
+
+# ------------------------------------------------------------------------------------------------
+# several GPUs behind the CLI (C++ driver, one forked worker per GPU; needs >= 2 devices)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,k", [("syn150_k27", 27), ("syn150_klist", 59), ("lowcov_k21", 21), ("polya_k27", 27)])
+def test_cli_multi_gpu_count_matches_reference(name, k, tmp_path):
+    """`megahit_core count --gpus N` (mhb_count_run_multi): per-rank `.edges.<r>` / `.sdbg.<r>` + merged tables whose
+    canonical streams equal the reference's digests; the following `seq2sdbg --need_mercy` finds the graph already
+    built; the reference's `assemble` reads the N-file SdBG and gives the contigs of the reference-built graph"""
+    import json
+    n_dev = lib.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = min(n_dev, 4)
+    gold_all = json.load(open(os.path.join(GOLDEN, name, "golden.json")))
+    m, gold = gold_all["m"], gold_all["by_k"][str(k)]
+    libp = os.path.join(GOLDEN, name, "reads.lib")
+    p = str(tmp_path / "multi")
+    r = subprocess.run([OURS, "count", "-k", str(k), "-m", str(m), "--host_mem", "1e9", "--mem_flag", "1", "--output_prefix", p,
+                        "--num_cpu_threads", "4", "--read_lib_file", libp, "--gpus", str(n)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert f"{n} GPUs" in r.stderr
+    r2 = subprocess.run([OURS, "seq2sdbg", "--host_mem", "1e9", "--mem_flag", "1", "--output_prefix", p, "--num_cpu_threads", "4",
+                         "-k", str(k), "--kmer_from", "0", "--input_prefix", p, "--need_mercy"], capture_output=True, text=True)
+    assert r2.returncode == 0, r2.stderr[-3000:]
+    assert "nothing to do" in r2.stderr
+    d = _digests(p)
+    assert F.parse_edges_info(p).num_files == n and F.parse_sdbg_info(p).num_files == n
+    if gold["n_solid"]:
+        assert d["edges"] == gold["edges_sha256"]
+    assert d["cand"] == gold["cand_sha256"] and d["counting"] == gold["counting_sha256"]
+    assert d["sdbg"] == gold["sdbg_sha256"] and d["items"] == gold["sdbg_items"] and d["tips"] == gold["sdbg_tips"]
+    # without --need_mercy the marker does not apply: the ordinary single-GPU seq2sdbg reads the N edge files
+    q = str(tmp_path / "nomercy")
+    r3 = subprocess.run([OURS, "seq2sdbg", "--host_mem", "1e9", "--mem_flag", "1", "--output_prefix", q, "--num_cpu_threads", "4",
+                         "-k", str(k), "--kmer_from", "0", "--input_prefix", p], capture_output=True, text=True)
+    assert r3.returncode == 0 and "nothing to do" not in r3.stderr, r3.stderr[-2000:]
+    if os.path.exists(REF) and gold["sdbg_items"]:
+        rp = str(tmp_path / "ref")
+        _ref_build(REF, libp, rp, k, m, threads=4)
+        outs = []
+        for tag, pre in (("ref", rp), ("ours", p)):
+            cp = str(tmp_path / ("contigs_" + tag))
+            _run([REF, "assemble", "-s", pre, "-o", cp, "-t", "1"] + ASM)
+            outs.append(open(cp + ".contigs.fa", "rb").read())
+        assert outs[0] == outs[1]
