@@ -284,7 +284,9 @@ def ours(args):
     s2s_achieved = 2.0 * n_items * s2s.W * 4 / (float(spass.mean()) * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic(n_reads, k)
     roofline = {
-        "bound": "hbm", "kernel": f"k_radix_pass<{plan.WR}> (count records, {S} B)", "achieved": achieved, "peak": peak,
+        "bound": "hbm", "kernel": f"radix passes over the count records ({S} B): k_radix_pass3<{plan.WR}> (stable, look-back); "
+                                   "the first pass of a sort is k_part_unstable (no look-back) for 8/12-byte records",
+        "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": 2 * n_edges * S, "avg_launch_ms": avg_pass_ms,
         "per_pass_ms": [float(x) for x in cpass.mean(axis=0)],

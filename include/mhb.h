@@ -112,6 +112,12 @@ int mhb_sort_records(void *stream, uint32_t *a, uint32_t *b, uint64_t n, uint32_
                      const uint8_t *bytes, uint32_t n_bytes, const uint64_t *first_hist, void *ws,
                      size_t ws_bytes, int *result_in_b);
 
+/* The same sort for callers that do not care in which order records with ALL sorted bytes equal come out (the count and
+ * seq2sdbg stages: such records are tallied / reduced to their minimum multiplicity): the first pass may then be the
+ * unstable partition pass (no look-back chain, one shared-memory atomic per record instead of stable ranking). */
+int mhb_sort_records_relaxed(void *stream, uint32_t *a, uint32_t *b, uint64_t n, uint32_t words, const uint8_t *bytes,
+                             uint32_t n_bytes, const uint64_t *first_hist, void *ws, size_t ws_bytes, int *result_in_b);
+
 /* Fused partition + exchange for the multi-GPU path: ONE stable radix pass whose per-digit destinations are arbitrary
  * device byte addresses (bin_addr_dev[256], device memory) = where the first record of digit d coming from THIS call
  * goes.  The digit of a record is owner_of_byte_dev[record byte `byte`] (256-entry device table mapping the record's

@@ -326,7 +326,7 @@ void worker(const Job &J, Exchange &X) {
       const size_t sb = mhb_sort_workspace_bytes(std::max<uint64_t>(n_own, 1), WR), cb = mhb_count_solid_scratch_bytes(n_own);
       void *d_s = pool.get<char>(sb), *d_c = pool.get<char>(cb);
       int in_b = 0;
-      CKM(mhb_sort_records(nullptr, (uint32_t *)pc.mine, d_tmp, n_own, WR, cbytes, n_csort, nullptr, d_s, sb, &in_b));
+      CKM(mhb_sort_records_relaxed(nullptr, (uint32_t *)pc.mine, d_tmp, n_own, WR, cbytes, n_csort, nullptr, d_s, sb, &in_b));
       CKM(mhb_count_solid(nullptr, in_b ? d_tmp : (uint32_t *)pc.mine, n_own, k, m, d_edges, d_aux, cap, d_mul, d_ns, d_c, cb));
       CKC(cudaDeviceSynchronize());
       pool.drop(d_s);
@@ -506,7 +506,7 @@ void worker(const Job &J, Exchange &X) {
     const size_t sb = mhb_sort_workspace_bytes(std::max<uint64_t>(n_own2, 1), W2), eb = mhb_s2s_emit_scratch_bytes(n_own2, k);
     void *d_s = pool.get<char>(sb);
     int in_b = 0;
-    CKM(mhb_sort_records(nullptr, (uint32_t *)ps.mine, d_tmp, n_own2, W2, sbytes, n_ssort, nullptr, d_s, sb, &in_b));
+    CKM(mhb_sort_records_relaxed(nullptr, (uint32_t *)ps.mine, d_tmp, n_own2, W2, sbytes, n_ssort, nullptr, d_s, sb, &in_b));
     pool.drop(d_s);
     void *d_e = pool.get<char>(eb);
     const uint64_t cap_b = n_own2 * (4ull + 4ull * wpt) + 16;

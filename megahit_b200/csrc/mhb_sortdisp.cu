@@ -12,6 +12,7 @@
 #include "mhb_kernels.cuh"
 #include "mhb_sort.cuh"
 #include "mhb_sort3.cuh"
+#include "mhb_part.cuh"
 
 using namespace mhb;
 
@@ -83,7 +84,7 @@ static u64 sort_num_tiles(u64 n, u32 words) {
 #undef M
   return 0;
 }
-static constexpr size_t kSortHeadBytes = (size_t)(72 + 1) * 256 * 8 /*hist*/ + 256 * 8 /*bin_base*/ + 128 * 4;
+static constexpr size_t kSortHeadBytes = (size_t)(72 + 1) * 256 * 8 /*hist*/ + 256 * 8 /*bin_base*/ + 128 * 4 + 256 * 8 /*gcursor*/;
 // look-back storage for `tiles` tiles: 256 64-bit descriptors per tile + (compact-descriptor variants) one 16-byte
 // word per digit and group of four tiles behind them
 static size_t lb_bytes(u64 tiles) { return (size_t)tiles * 256 * 8 + (size_t)((tiles + 3) / 4) * 256 * 16; }
@@ -144,6 +145,37 @@ static int launch_radix_pass_cfg3(cudaStream_t st, const u32 *in, u64 n, int byt
   return MHB_OK;
 }
 
+// first pass of a sort whose caller does not need a deterministic order among fully equal keys (mhb_part.cuh)
+template <int WR>
+static int launch_part_unstable(cudaStream_t st, const u32 *in, u64 n, int byte_idx, const u64 *bin_base,
+                                unsigned long long *gcursor, u32 *tile_counter, u64 *next_hist, int next_byte,
+                                const uint8_t *lut) {
+  using C = PartCfg<WR>;
+  static int bps = 0;
+  if (!bps) {
+    CK(cudaFuncSetAttribute(k_part_unstable<WR, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CK(cudaFuncSetAttribute(k_part_unstable<WR, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CK(cudaFuncSetAttribute(k_part_unstable<WR, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_part_unstable<WR, false, true>, C::THREADS, C::SMEM));
+    if (bps < 1) return mhb_set_error(MHB_ERR_CUDA, "partition pass (WR=%d) does not fit an SM", WR);
+    if (getenv("MHB_VERBOSE")) fprintf(stderr, "[mhb] unstable partition pass WR=%d: %d threads x %d rec, %zu B smem, %d CTA/SM\n", WR, C::THREADS, C::IPT, C::SMEM, bps);
+  }
+  const u64 tiles = (n + C::TILE - 1) / C::TILE;
+  u64 grid = (u64)bps * sm_count();
+  if (grid > tiles) grid = tiles;
+  if (lut)
+    k_part_unstable<WR, true, false><<<(int)grid, C::THREADS, C::SMEM, st>>>(in, n, (u32)tiles, byte_idx, bin_base, gcursor,
+                                                                             tile_counter, nullptr, 0, lut);
+  else if (next_hist)
+    k_part_unstable<WR, false, true><<<(int)grid, C::THREADS, C::SMEM, st>>>(in, n, (u32)tiles, byte_idx, bin_base, gcursor,
+                                                                             tile_counter, next_hist, next_byte, nullptr);
+  else
+    k_part_unstable<WR, false, false><<<(int)grid, C::THREADS, C::SMEM, st>>>(in, n, (u32)tiles, byte_idx, bin_base, gcursor,
+                                                                              tile_counter, nullptr, 0, nullptr);
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
 template <int WR>
 static int launch_radix_pass(cudaStream_t st, const u32 *in, u64 n, int byte_idx, const u64 *bin_base,
                              u64 *lookback, u32 *tile_counter, u64 *next_hist, int next_byte, u32 epoch) {
@@ -191,9 +223,22 @@ SortTrace g_trace[4];
 uint64_t g_trace_seq = 0;
 }  // namespace
 
+// relaxed != 0: the first pass may be the unstable partition pass (mhb_part.cuh) - the order among records whose sorted
+// bytes are ALL equal is then unspecified; MHB_SORT_STABLE_FIRST=1 keeps the stable pass everywhere (A/B hook)
+int mhb_sort_records_ex(void *stream, uint32_t *a, uint32_t *b, uint64_t n, uint32_t words, const uint8_t *bytes,
+                        uint32_t n_bytes, const uint64_t *first_hist, void *ws, size_t ws_bytes, int *result_in_b,
+                        double *pass_ms_host, int relaxed);
 int mhb_sort_records_impl(void *stream, uint32_t *a, uint32_t *b, uint64_t n, uint32_t words, const uint8_t *bytes,
                           uint32_t n_bytes, const uint64_t *first_hist, void *ws, size_t ws_bytes, int *result_in_b,
                           double *pass_ms_host) {
+  // the library's own stages tally or minimise over records with equal sort keys: their order is irrelevant
+  return mhb_sort_records_ex(stream, a, b, n, words, bytes, n_bytes, first_hist, ws, ws_bytes, result_in_b, pass_ms_host, 1);
+}
+int mhb_sort_records_ex(void *stream, uint32_t *a, uint32_t *b, uint64_t n, uint32_t words, const uint8_t *bytes,
+                          uint32_t n_bytes, const uint64_t *first_hist, void *ws, size_t ws_bytes, int *result_in_b,
+                        double *pass_ms_host, int relaxed) {
+  static const bool stable_first = getenv("MHB_SORT_STABLE_FIRST") != nullptr;
+  if (stable_first) relaxed = 0;
   if (words < 1 || words > 17 || n_bytes > 72 || !result_in_b)
     return mhb_set_error(MHB_ERR_ARG, "bad sort geometry (words=%u n_bytes=%u)", words, n_bytes);
   *result_in_b = 0;
@@ -204,6 +249,7 @@ int mhb_sort_records_impl(void *stream, uint32_t *a, uint32_t *b, uint64_t n, ui
   u64 *hist = (u64 *)ws;                        // [n_bytes+1][256]
   u64 *bin_base = hist + (72 + 1) * 256;        // [256]
   u32 *tile_counter = (u32 *)(bin_base + 256);  // [128]
+  unsigned long long *gcursor = (unsigned long long *)(tile_counter + 128);  // [256]: unstable first pass
   u64 *lookback = (u64 *)((char *)ws + kSortHeadBytes);
   // only what this sort's tile geometry touches (the workspace itself is sized for the smallest tile of any variant)
   CK(cudaMemsetAsync(ws, 0, kSortHeadBytes + lb_bytes(sort_num_tiles(n, words)) + 256, st));
@@ -232,10 +278,14 @@ int mhb_sort_records_impl(void *stream, uint32_t *a, uint32_t *b, uint64_t n, ui
     u64 *next_hist = p + 1 < n_bytes ? hist + (u64)(p + 1) * 256 : nullptr;
     const int next_byte = p + 1 < n_bytes ? bytes[p + 1] : 0;
     int rc = MHB_ERR_ARG;
+    if (p == 0 && relaxed && words == 2) rc = launch_part_unstable<2>(st, in, n, bytes[p], bin_base, gcursor, tile_counter + p, next_hist, next_byte, nullptr);
+    else if (p == 0 && relaxed && words == 3) rc = launch_part_unstable<3>(st, in, n, bytes[p], bin_base, gcursor, tile_counter + p, next_hist, next_byte, nullptr);
+    else {
 #define M(WW) \
   if (words == WW) rc = launch_radix_pass<WW>(st, in, n, bytes[p], bin_base, lookback, tile_counter + p, next_hist, next_byte, p + 1);
-    MHB_FOR_WR(M)
+      MHB_FOR_WR(M)
 #undef M
+    }
     if (rc) return rc;
     CK(cudaEventRecord(tr.ev[p + 1], st));
     u32 *t = in;
@@ -297,7 +347,13 @@ extern "C" int mhb_partition_scatter(void *stream, const uint32_t *recs, uint64_
   u64 *lookback = (u64 *)((char *)ws + kSortHeadBytes);
   CK(cudaMemsetAsync(ws, 0, need, st));
   int rc = MHB_ERR_ARG;
-  if (owner_of_byte_dev) {
+  static const bool stable_first = getenv("MHB_SORT_STABLE_FIRST") != nullptr;
+  if (owner_of_byte_dev && !stable_first && (words == 2 || words == 3)) {
+    // the exchange has no earlier order to preserve: unstable pass (no look-back chain), 8- and 12-byte records
+    unsigned long long *gcursor = (unsigned long long *)(tile_counter + 128);
+    rc = words == 2 ? launch_part_unstable<2>(st, recs, n, byte, bin_addr_dev, gcursor, tile_counter, nullptr, 0, owner_of_byte_dev)
+                    : launch_part_unstable<3>(st, recs, n, byte, bin_addr_dev, gcursor, tile_counter, nullptr, 0, owner_of_byte_dev);
+  } else if (owner_of_byte_dev) {
 #define M(WW) \
   if (words == WW) rc = launch_partition_pass<WW>(st, recs, n, byte, bin_addr_dev, lookback, tile_counter, owner_of_byte_dev);
     MHB_FOR_WR(M)
@@ -356,6 +412,12 @@ extern "C" int mhb_sort_pass_ms(int back, double *pass_ms, uint32_t max_passes, 
 extern "C" int mhb_sort_records(void *stream, uint32_t *a, uint32_t *b, uint64_t n, uint32_t words,
                                 const uint8_t *bytes, uint32_t n_bytes, const uint64_t *first_hist, void *ws,
                                 size_t ws_bytes, int *result_in_b) {
-  return mhb_sort_records_impl(stream, a, b, n, words, bytes, n_bytes, first_hist, ws, ws_bytes, result_in_b, nullptr);
+  return mhb_sort_records_ex(stream, a, b, n, words, bytes, n_bytes, first_hist, ws, ws_bytes, result_in_b, nullptr, 0);
+}
+
+extern "C" int mhb_sort_records_relaxed(void *stream, uint32_t *a, uint32_t *b, uint64_t n, uint32_t words,
+                                        const uint8_t *bytes, uint32_t n_bytes, const uint64_t *first_hist, void *ws,
+                                        size_t ws_bytes, int *result_in_b) {
+  return mhb_sort_records_ex(stream, a, b, n, words, bytes, n_bytes, first_hist, ws, ws_bytes, result_in_b, nullptr, 1);
 }
 

@@ -21,17 +21,19 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def sort_records(a: torch.Tensor, b: torch.Tensor, n: int, words: int, sort_bytes, first_hist=None, ws=None):
+def sort_records(a: torch.Tensor, b: torch.Tensor, n: int, words: int, sort_bytes, first_hist=None, ws=None, relaxed=False):
     """LSD radix sort of n records (int32 tensors a, b of >= n*words elements).  Returns the tensor
-    holding the result."""
+    holding the result.  relaxed: the order among records with all sorted bytes equal may be arbitrary (what the count
+    and seq2sdbg stages need: mhb_sort_records_relaxed)."""
     L = lib.load()
     need = L.mhb_sort_workspace_bytes(n, words)
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, dtype=torch.uint8, device=a.device)
     bytes_arr = (C.c_uint8 * len(sort_bytes))(*sort_bytes)
     in_b = C.c_int(0)
-    lib._check(L.mhb_sort_records(_stream(), _ptr(a), _ptr(b), n, words, bytes_arr, len(sort_bytes), _ptr(first_hist),
-                                  _ptr(ws), ws.numel(), C.byref(in_b)))
+    fn = L.mhb_sort_records_relaxed if relaxed else L.mhb_sort_records
+    lib._check(fn(_stream(), _ptr(a), _ptr(b), n, words, bytes_arr, len(sort_bytes), _ptr(first_hist), _ptr(ws), ws.numel(),
+                  C.byref(in_b)))
     return b if in_b.value else a
 
 
@@ -91,7 +93,7 @@ class CountPlan:
     def sort(self):
         if self.hashed:
             return None  # the two partition passes run inside count()
-        self.sorted = sort_records(self.a, self.b, self.n, self.WR, self.sort_bytes, self.hist0, self.ws)
+        self.sorted = sort_records(self.a, self.b, self.n, self.WR, self.sort_bytes, self.hist0, self.ws, relaxed=True)
         return self.sorted
 
     def count(self):
@@ -183,7 +185,7 @@ class S2sPlan:
                                           self.sort_bytes[0]))
         if timed:
             ev[1].record()
-        srt = sort_records(self.a, self.b, self.n_items, self.W, self.sort_bytes, self.hist0, self.ws)
+        srt = sort_records(self.a, self.b, self.n_items, self.W, self.sort_bytes, self.hist0, self.ws, relaxed=True)
         if timed:
             ev[2].record()
         lib._check(self.L.mhb_s2s_emit(_stream(), _ptr(srt), self.n_items, self.k, _ptr(self.bytes), self.cap_bytes,

@@ -244,7 +244,7 @@ class MultiGpuBuild:
         ws = self._buf(tag + "_ws2", L.mhb_sort_workspace_bytes(max(n, 1), words), torch.uint8)
         arr = (C.c_uint8 * len(sort_bytes))(*sort_bytes)
         in_b = C.c_int(0)
-        lib._check(L.mhb_sort_records(_stream(), C.c_void_p(ptr_a), _ptr(tmp), n, words, arr, len(sort_bytes), None, _ptr(ws),
+        lib._check(L.mhb_sort_records_relaxed(_stream(), C.c_void_p(ptr_a), _ptr(tmp), n, words, arr, len(sort_bytes), None, _ptr(ws),
                                       ws.numel(), C.byref(in_b)))
         return tmp.data_ptr() if in_b.value else ptr_a
 

@@ -550,3 +550,33 @@ def test_hashed_count_matches_sort_and_count(case):
     (e0, a0, h0, n0), (e1, a1, h1, n1) = _count_both_ways(recs, k, m)
     assert n0 == n1 and (n0 > 0 or case == "all_distinct")
     assert (e0 == e1).all() and (a0 == a1).all() and (h0 == h1).all()
+
+
+@pytest.mark.parametrize("words,n", [(2, 1), (2, 6911), (2, 700_001), (3, 450_007), (2, 3_000_000)])
+def test_relaxed_sort_is_sorted_permutation(words, n):
+    """mhb_sort_records_relaxed (unstable first pass, mhb_part.cuh): ascending on the sorted bytes and a permutation of
+    the input - only the order among records with ALL sorted bytes equal may differ from the stable sort"""
+    torch = _torch()
+    from megahit_b200 import dev
+    rng = np.random.default_rng(words * 7 + n)
+    recs = rng.integers(0, 2 ** 32, size=(n, words), dtype=np.uint64).astype(np.uint32)
+    recs[:, 0] &= np.uint32(0x00FF0F0F)  # long runs of equal keys
+    sort_bytes = list(range(1, 4 * words)) if words == 2 else [2, 5, 6, 7, 8, 9, 10, 11]
+    a = torch.from_numpy(np.concatenate([recs.view(np.int32).reshape(-1), np.zeros(4, np.int32)])).cuda()
+    out = dev.sort_records(a, torch.empty_like(a), n, words, sort_bytes, relaxed=True)
+    got = out[: n * words].cpu().numpy().view(np.uint32).reshape(n, words)
+    exp = _np_lsd(recs, sort_bytes)
+
+    def key(x):  # the sorted bytes as one comparable integer per record
+        v = np.zeros(len(x), dtype=object)
+        for b in reversed(sort_bytes):
+            v = v * 256 + ((x[:, words - 1 - (b >> 2)] >> np.uint32(8 * (b & 3))) & 255).astype(object)
+        return v
+    if n <= 800_000:
+        assert (key(got) == key(exp)).all()
+    full = lambda x: np.sort(np.ascontiguousarray(x).view([("", x.dtype)] * words).reshape(-1))
+    assert (full(got) == full(recs)).all()
+    # digit-wise check that scales: every sorted byte column of got equals the stable result's
+    for b in sort_bytes:
+        col = lambda x: (x[:, words - 1 - (b >> 2)] >> np.uint32(8 * (b & 3))) & 255
+        assert (col(got) == col(exp)).all()
