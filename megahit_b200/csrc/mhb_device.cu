@@ -528,7 +528,7 @@ extern "C" int mhb_s2s_emit(void *stream, const uint32_t *sorted_records, uint64
     CK_LAUNCH();
     k_bucket_starts<<<64, 256, 0, st>>>(bucket_local, chunk_off, nc, bucket_start);
     CK_LAUNCH();
-    k_bucket_finalize<<<64, 256, 0, st>>>(bucket_start, totals, bucket_table);
+    k_bucket_finalize<<<1, 1024, 0, st>>>(bucket_start, totals, bucket_table);
     CK_LAUNCH();
     return MHB_OK;
   }
@@ -551,7 +551,7 @@ extern "C" int mhb_s2s_emit(void *stream, const uint32_t *sorted_records, uint64
   MHB_FOR_WR(M)
 #undef M
   CK_LAUNCH();
-  k_bucket_finalize<<<64, 256, 0, st>>>(bucket_start, totals, bucket_table);
+  k_bucket_finalize<<<1, 1024, 0, st>>>(bucket_start, totals, bucket_table);
   CK_LAUNCH();
   return MHB_OK;
 }

@@ -508,10 +508,7 @@ void worker(const Job &J, Exchange &X) {
     int in_b = 0;
     CKM(mhb_sort_records_relaxed(nullptr, (uint32_t *)ps.mine, d_tmp, n_own2, W2, sbytes, n_ssort, nullptr, d_s, sb, &in_b));
     pool.drop(d_s);
-    if (!in_b && n_own2) {  // keep the emit off the peer-mapped receive buffer (it re-reads records through L1)
-      CKC(cudaMemcpy(d_tmp, ps.mine, n_own2 * W2 * 4, cudaMemcpyDeviceToDevice));
-      in_b = 1;
-    }
+
     void *d_e = pool.get<char>(eb);
     const uint64_t cap_b = n_own2 * (4ull + 4ull * wpt) + 16;
     uint8_t *d_out = pool.get<uint8_t>(cap_b);

@@ -246,13 +246,7 @@ class MultiGpuBuild:
         in_b = C.c_int(0)
         lib._check(L.mhb_sort_records_relaxed(_stream(), C.c_void_p(ptr_a), _ptr(tmp), n, words, arr, len(sort_bytes), None, _ptr(ws),
                                       ws.numel(), C.byref(in_b)))
-        if in_b.value:
-            return tmp.data_ptr()
-        # an even number of passes leaves the result in the CUDA-IPC receive buffer.  That memory is mapped for the peers,
-        # and the kernels that follow (the seq2sdbg emit re-reads neighbouring records through L1) ran 2x slower on it
-        # than on ordinary device memory (8.2 -> 19 ms at 8 GPUs); one device-to-device copy (~1 ms) moves it out.
-        tmp[: n * words].copy_(torch.as_tensor(_RawView(ptr_a, n * words), device=self.device))
-        return tmp.data_ptr()
+        return tmp.data_ptr() if in_b.value else ptr_a
 
     # ------------------------------------------------------------------ mercy stage
     def _mercy(self, reads, bin_dev, edges, aux, n_solid, n_tip, owner):
