@@ -126,6 +126,13 @@ int mhb_sort_records_relaxed(void *stream, uint32_t *a, uint32_t *b, uint64_t n,
  * kernel and no separate all-to-all is needed.  ws as for mhb_sort_records. */
 int mhb_partition_scatter(void *stream, const uint32_t *recs, uint64_t n, uint32_t words, int byte,
                           const uint8_t *owner_of_byte_dev, const uint64_t *bin_addr_dev, void *ws, size_t ws_bytes);
+/* The same pass, additionally delivering - where the pass variant supports it (*hist_done = 1; 8- and 12-byte records) -
+ * one histogram of record byte `next_byte` per owner: owner_next_hist[o * 256 + v] (device uint64[16 * 256],
+ * caller-zeroed) += records sent to owner o whose byte next_byte is v.  Summed over the sending ranks it is the
+ * first-pass histogram of the owner's sort, which then need not sweep its records to count. */
+int mhb_partition_scatter_hist(void *stream, const uint32_t *recs, uint64_t n, uint32_t words, int byte,
+                               const uint8_t *owner_of_byte_dev, const uint64_t *bin_addr_dev, void *ws, size_t ws_bytes,
+                               int next_byte, uint64_t *owner_next_hist, int *hist_done);
 /* The bucket-range plan of one stage of the multi-GPU build, computed on the device from the all-gathered top-byte
  * histograms hist_all_dev[world][256] (so that nothing but a few counters has to visit the host between the histogram
  * exchange and the partition pass): rank r owns the leading-byte values [bounds[r], bounds[r+1]), cut where the

@@ -26,14 +26,18 @@ struct PartCfg {
   static constexpr int IPT = SortCfg3<WR, 0x080>::IPT;
   static constexpr int TILE = THREADS * IPT;
   static constexpr size_t SMEM = 256 * 8 /*s_base*/ + 4 * 256 * 4 /*s_cnt, s_off, s_cur, s_next*/ + 16 * 4 + (size_t)TILE * WR * 4;
+  static constexpr size_t SMEM_OWNER_HIST = SMEM + 16 * 256 * 4;  // + per-owner histograms of the next sort byte
 };
 
+// OWNER_LUT + HAS_NEXT: the digit is the owning rank (<= 16) and next_hist is [16][256]: one histogram of record byte
+// `next_byte` PER OWNER, so that the receiving rank gets the first-pass histogram of its sort for free.
 template <int WR, bool OWNER_LUT, bool HAS_NEXT>
 __global__ void __launch_bounds__(PartCfg<WR>::THREADS, 2)
     k_part_unstable(const u32 *__restrict__ in, u64 n, u32 num_tiles, int byte_idx,
                     const u64 *__restrict__ bin_addr /*byte address of each digit's first output record*/,
                     unsigned long long *gcursor /*[256], zeroed: records of each digit placed so far*/, u32 *tile_counter,
                     u64 *next_hist, int next_byte, const uint8_t *__restrict__ digit_lut) {
+  constexpr bool OWNER_HIST = OWNER_LUT && HAS_NEXT;
   using C = PartCfg<WR>;
   constexpr int THREADS = C::THREADS, IPT = C::IPT, TILE = C::TILE;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -44,6 +48,7 @@ __global__ void __launch_bounds__(PartCfg<WR>::THREADS, 2)
   u32 *s_next = s_cur + 256;
   u32 *s_misc = s_next + 256;  // 16
   u32 *s_recs = s_misc + 16;
+  u32 *s_onext = s_recs + (size_t)C::TILE * WR;  // OWNER_HIST: [16][256]
   __shared__ uint8_t s_lut[OWNER_LUT ? 256 : 1];
   const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 widx = (u32)(WR - 1 - (byte_idx >> 2)), bsel = (u32)(byte_idx & 3);
@@ -51,6 +56,9 @@ __global__ void __launch_bounds__(PartCfg<WR>::THREADS, 2)
   for (int i = tid; i < 256; i += THREADS) {
     s_cnt[i] = 0;
     s_next[i] = 0;
+  }
+  if constexpr (OWNER_HIST) {
+    for (int i = tid; i < 16 * 256; i += THREADS) s_onext[i] = 0;
   }
   if constexpr (OWNER_LUT) {
     for (int i = tid; i < 256; i += THREADS) s_lut[i] = digit_lut[i];
@@ -127,14 +135,18 @@ __global__ void __launch_bounds__(PartCfg<WR>::THREADS, 2)
         u32 dd = rec_digit<WR>(q, widx, bsel);
         if constexpr (OWNER_LUT) dd = s_lut[dd];
         st_global_rec<WR>(s_base[dd] + (u64)(p - s_off[dd]) * (WR * 4), q);
-        if constexpr (HAS_NEXT) red_shared_inc(&s_next[rec_digit<WR>(q, nwidx, nbsel)]);
+        if constexpr (OWNER_HIST) red_shared_inc(&s_onext[(dd & 15u) * 256 + rec_digit<WR>(q, nwidx, nbsel)]);
+        else if constexpr (HAS_NEXT) red_shared_inc(&s_next[rec_digit<WR>(q, nwidx, nbsel)]);
       }
     }
     for (int i = tid; i < 256; i += THREADS) s_cnt[i] = 0;
     __syncthreads();
     tile = next_tile;
   }
-  if constexpr (HAS_NEXT) {
+  if constexpr (OWNER_HIST) {
+    for (int i = tid; i < 16 * 256; i += THREADS)
+      if (s_onext[i]) atomicAdd((unsigned long long *)&next_hist[i], (unsigned long long)s_onext[i]);
+  } else if constexpr (HAS_NEXT) {
     for (int i = tid; i < 256; i += THREADS)
       if (s_next[i]) atomicAdd((unsigned long long *)&next_hist[i], (unsigned long long)s_next[i]);
   }

@@ -156,6 +156,7 @@ static int launch_part_unstable(cudaStream_t st, const u32 *in, u64 n, int byte_
     CK(cudaFuncSetAttribute(k_part_unstable<WR, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     CK(cudaFuncSetAttribute(k_part_unstable<WR, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     CK(cudaFuncSetAttribute(k_part_unstable<WR, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CK(cudaFuncSetAttribute(k_part_unstable<WR, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_OWNER_HIST));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_part_unstable<WR, false, true>, C::THREADS, C::SMEM));
     if (bps < 1) return mhb_set_error(MHB_ERR_CUDA, "partition pass (WR=%d) does not fit an SM", WR);
     if (getenv("MHB_VERBOSE")) fprintf(stderr, "[mhb] unstable partition pass WR=%d: %d threads x %d rec, %zu B smem, %d CTA/SM\n", WR, C::THREADS, C::IPT, C::SMEM, bps);
@@ -163,7 +164,10 @@ static int launch_part_unstable(cudaStream_t st, const u32 *in, u64 n, int byte_
   const u64 tiles = (n + C::TILE - 1) / C::TILE;
   u64 grid = (u64)bps * sm_count();
   if (grid > tiles) grid = tiles;
-  if (lut)
+  if (lut && next_hist)
+    k_part_unstable<WR, true, true><<<(int)grid, C::THREADS, C::SMEM_OWNER_HIST, st>>>(in, n, (u32)tiles, byte_idx, bin_base, gcursor,
+                                                                                       tile_counter, next_hist, next_byte, lut);
+  else if (lut)
     k_part_unstable<WR, true, false><<<(int)grid, C::THREADS, C::SMEM, st>>>(in, n, (u32)tiles, byte_idx, bin_base, gcursor,
                                                                              tile_counter, nullptr, 0, lut);
   else if (next_hist)
@@ -328,9 +332,26 @@ static int launch_partition_pass(cudaStream_t st, const u32 *in, u64 n, int byte
   return MHB_OK;
 }
 
+static int partition_scatter_impl(void *stream, const uint32_t *recs, uint64_t n, uint32_t words, int byte,
+                                  const uint8_t *owner_of_byte_dev, const uint64_t *bin_addr_dev, void *ws, size_t ws_bytes,
+                                  int next_byte, uint64_t *owner_next_hist, int *hist_done);
 extern "C" int mhb_partition_scatter(void *stream, const uint32_t *recs, uint64_t n, uint32_t words, int byte,
                                      const uint8_t *owner_of_byte_dev, const uint64_t *bin_addr_dev, void *ws,
                                      size_t ws_bytes) {
+  return partition_scatter_impl(stream, recs, n, words, byte, owner_of_byte_dev, bin_addr_dev, ws, ws_bytes, 0, nullptr, nullptr);
+}
+extern "C" int mhb_partition_scatter_hist(void *stream, const uint32_t *recs, uint64_t n, uint32_t words, int byte,
+                                          const uint8_t *owner_of_byte_dev, const uint64_t *bin_addr_dev, void *ws,
+                                          size_t ws_bytes, int next_byte, uint64_t *owner_next_hist, int *hist_done) {
+  if (!owner_of_byte_dev || !owner_next_hist || !hist_done || next_byte < 0 || next_byte >= (int)(4 * words))
+    return mhb_set_error(MHB_ERR_ARG, "bad owner-histogram arguments");
+  return partition_scatter_impl(stream, recs, n, words, byte, owner_of_byte_dev, bin_addr_dev, ws, ws_bytes, next_byte,
+                                owner_next_hist, hist_done);
+}
+static int partition_scatter_impl(void *stream, const uint32_t *recs, uint64_t n, uint32_t words, int byte,
+                                  const uint8_t *owner_of_byte_dev, const uint64_t *bin_addr_dev, void *ws, size_t ws_bytes,
+                                  int next_byte, uint64_t *owner_next_hist, int *hist_done) {
+  if (hist_done) *hist_done = 0;
   if (words < 1 || words > 17 || byte < 0 || byte >= (int)(4 * words)) return mhb_set_error(MHB_ERR_ARG, "bad geometry");
   if (n == 0) return MHB_OK;
   // the partition pass always runs the v2 kernel in geometry 0, whatever variant the sorts use
@@ -351,8 +372,9 @@ extern "C" int mhb_partition_scatter(void *stream, const uint32_t *recs, uint64_
   if (owner_of_byte_dev && !stable_first && (words == 2 || words == 3)) {
     // the exchange has no earlier order to preserve: unstable pass (no look-back chain), 8- and 12-byte records
     unsigned long long *gcursor = (unsigned long long *)(tile_counter + 128);
-    rc = words == 2 ? launch_part_unstable<2>(st, recs, n, byte, bin_addr_dev, gcursor, tile_counter, nullptr, 0, owner_of_byte_dev)
-                    : launch_part_unstable<3>(st, recs, n, byte, bin_addr_dev, gcursor, tile_counter, nullptr, 0, owner_of_byte_dev);
+    rc = words == 2 ? launch_part_unstable<2>(st, recs, n, byte, bin_addr_dev, gcursor, tile_counter, owner_next_hist, next_byte, owner_of_byte_dev)
+                    : launch_part_unstable<3>(st, recs, n, byte, bin_addr_dev, gcursor, tile_counter, owner_next_hist, next_byte, owner_of_byte_dev);
+    if (!rc && owner_next_hist && hist_done) *hist_done = 1;
   } else if (owner_of_byte_dev) {
 #define M(WW) \
   if (words == WW) rc = launch_partition_pass<WW>(st, recs, n, byte, bin_addr_dev, lookback, tile_counter, owner_of_byte_dev);

@@ -182,13 +182,17 @@ class MultiGpuBuild:
         pb = self.peer[tag] = PeerBuffers(int(need_bytes * 1.25) + 4096)
         return pb
 
-    def _partition_and_exchange(self, recs, n, words, top_byte, hist_dev, tag, expect_own):
+    def _partition_and_exchange(self, recs, n, words, top_byte, hist_dev, tag, expect_own, next_byte=None):
         """Move every record to the rank owning its leading byte.  Fused mode: ONE kernel does partition + exchange -
         the radix pass's scatter stores go straight into the owners' receive buffers over NVLink (CUDA IPC peer
         pointers).  Fallback (MHB_MGPU_NCCL_A2A=1): local pass, then one variable-size NCCL all-to-all.
+        next_byte: the byte the owner's sort visits first - where the exchange pass supports it, it also counts that byte
+        per owner, the ranks swap the 256-bin rows, and self._first_hist (device int64[256], else None) is the
+        first-pass histogram of the owned records: the owner's sort need not sweep them to count.
         Returns (pointer to the owned records, count, bounds[world+1] numpy, owner table numpy uint8[256])."""
         L, W = self.L, self.world
         rb = words * 4
+        self._first_hist = None
         hist_all = self._buf(tag + "_hist_all", W * 256, torch.int64)
         # the all-gather also orders the ranks: when it completes, every rank has finished the previous step's reads
         # of its receive buffer, so the scatter below may overwrite it
@@ -227,9 +231,22 @@ class MultiGpuBuild:
                                    output_split_sizes=[int(c) * words for c in recv_counts],
                                    input_split_sizes=[int(c) * words for c in send])
             return out.data_ptr(), n_own, bounds, owner
-        lib._check(L.mhb_partition_scatter(_stream(), _ptr(recs), n, words, top_byte, _ptr(lut_dev), _ptr(addr_dev), _ptr(ws),
-                                           ws.numel()))
-        self._stream_barrier()  # all ranks' scatter kernels have completed: my buffer is complete
+        self._first_hist = None
+        if next_byte is None:
+            lib._check(L.mhb_partition_scatter(_stream(), _ptr(recs), n, words, top_byte, _ptr(lut_dev), _ptr(addr_dev), _ptr(ws),
+                                               ws.numel()))
+            self._stream_barrier()  # all ranks' scatter kernels have completed: my buffer is complete
+            return pb.ptr, n_own, bounds, owner
+        oh = self._buf(tag + "_ohist", 16 * 256, torch.int64)[: 16 * 256]
+        oh.zero_()
+        done = C.c_int(0)
+        lib._check(L.mhb_partition_scatter_hist(_stream(), _ptr(recs), n, words, top_byte, _ptr(lut_dev), _ptr(addr_dev), _ptr(ws),
+                                                ws.numel(), next_byte, _ptr(oh), C.byref(done)))
+        # row o of my table goes to rank o; the all-to-all is also the barrier after the scatter
+        got = self._buf(tag + "_ohist_in", W * 256, torch.int64)[: W * 256]
+        dist.all_to_all_single(got, oh[: W * 256])
+        if done.value:
+            self._first_hist = got.view(W, 256).sum(0).contiguous()
         return pb.ptr, n_own, bounds, owner
 
     def close(self):
@@ -237,15 +254,15 @@ class MultiGpuBuild:
             pb.close()
         self.peer = {}
 
-    def _sort_raw(self, ptr_a, n, words, sort_bytes, tag):
+    def _sort_raw(self, ptr_a, n, words, sort_bytes, tag, first_hist=None):
         """LSD sort of n records at raw device pointer ptr_a; returns the pointer holding the result."""
         L = self.L
         tmp = self._buf(tag + "_tmp", n * words + 4, slack=1.15)
         ws = self._buf(tag + "_ws2", L.mhb_sort_workspace_bytes(max(n, 1), words), torch.uint8)
         arr = (C.c_uint8 * len(sort_bytes))(*sort_bytes)
         in_b = C.c_int(0)
-        lib._check(L.mhb_sort_records_relaxed(_stream(), C.c_void_p(ptr_a), _ptr(tmp), n, words, arr, len(sort_bytes), None, _ptr(ws),
-                                      ws.numel(), C.byref(in_b)))
+        lib._check(L.mhb_sort_records_relaxed(_stream(), C.c_void_p(ptr_a), _ptr(tmp), n, words, arr, len(sort_bytes),
+                                              _ptr(first_hist), _ptr(ws), ws.numel(), C.byref(in_b)))
         return tmp.data_ptr() if in_b.value else ptr_a
 
     # ------------------------------------------------------------------ mercy stage
@@ -341,7 +358,9 @@ class MultiGpuBuild:
         lib._check(L.mhb_count_extract(_stream(), C.byref(reads), k, _ptr(a), n, _ptr(hist), top))
         if timed:
             self._mark("extract")
-        own, n_own, bounds, owner = self._partition_and_exchange(a, n, self.WR, top, hist, "c", max(n, 1))
+        c_first = 5 if self.hashed else self.cbytes[0]  # the byte the owner's count stage sorts on first
+        own, n_own, bounds, owner = self._partition_and_exchange(a, n, self.WR, top, hist, "c", max(n, 1), next_byte=c_first)
+        c_hist = self._first_hist
         if timed:
             self._mark("exchange1")
         cap = n_own // max(1, m) + 1
@@ -356,10 +375,10 @@ class MultiGpuBuild:
                 self._mark("sort1")  # the two partition passes run inside the hashed count call
             tmp = self._buf("c_tmp", n_own * self.WR + 4, slack=1.15)
             hws = self._buf("c_hws", L.mhb_count_hashed_workspace_bytes(max(n_own, 1), k, m), torch.uint8, slack=1.15)
-            lib._check(L.mhb_count_solid_hashed(_stream(), C.c_void_p(own), _ptr(tmp), n_own, k, m, None, _ptr(edges), _ptr(aux),
+            lib._check(L.mhb_count_solid_hashed(_stream(), C.c_void_p(own), _ptr(tmp), n_own, k, m, _ptr(c_hist), _ptr(edges), _ptr(aux),
                                                 cap, _ptr(mul_hist), _ptr(nsol), _ptr(hws), hws.numel()))
         else:
-            srt = self._sort_raw(own, n_own, self.WR, self.cbytes, "c")
+            srt = self._sort_raw(own, n_own, self.WR, self.cbytes, "c", c_hist)
             if timed:
                 self._mark("sort1")
             scratch = self._buf("c_scratch", L.mhb_count_solid_scratch_bytes(n_own), torch.uint8, slack=1.15)
@@ -390,10 +409,12 @@ class MultiGpuBuild:
         hist2.zero_()
         top2 = self.sbytes[-1]
         lib._check(L.mhb_s2s_extract(_stream(), C.byref(seqs), k, _ptr(sa), n_items, _ptr(hist2), top2))
-        own2, n_own2, bounds2, _ = self._partition_and_exchange(sa, n_items, self.W2, top2, hist2, "s", max(n_items, 1))
+        own2, n_own2, bounds2, _ = self._partition_and_exchange(sa, n_items, self.W2, top2, hist2, "s", max(n_items, 1),
+                                                                 next_byte=self.sbytes[0])
+        s_hist = self._first_hist
         if timed:
             self._mark("exchange2")
-        srt2 = self._sort_raw(own2, n_own2, self.W2, self.sbytes, "s")
+        srt2 = self._sort_raw(own2, n_own2, self.W2, self.sbytes, "s", s_hist)
         if timed:
             self._mark("s2s_sort")
         wpt = (k + 15) // 16
