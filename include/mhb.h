@@ -94,6 +94,10 @@ typedef struct {
 int mhb_count_extract(void *stream, const mhb_dev_reads *reads, uint32_t k, uint32_t *records,
                       uint64_t n_edges, uint64_t *hist256, int hist_byte);
 
+/* *flag_dev (device uint64, caller-zeroed) becomes non-zero when a read of a library handed over as fixed-length
+ * (fixed_len > 0) has another length: the host-level calls look at a sample of the length words only and verify here. */
+int mhb_check_fixed_len(void *stream, const uint32_t *bin_dev, uint64_t n_reads, uint32_t fixed_len, uint64_t *flag_dev);
+
 /* A13 (base_engine.cpp:54-141, 254-281: Lv1 passes over bucket ranges): the same extraction restricted to the edges
  * whose 16-bit bucket id (first eight bases, kNumBuckets = 65536) lies in [lo, hi], for libraries whose records do
  * not fit in HBM at once.  Two calls per round: write = 0 fills per_read[0..n_reads] (device uint64) with the exclusive prefix of the

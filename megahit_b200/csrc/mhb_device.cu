@@ -129,6 +129,22 @@ static int grow_scratch(size_t bytes, void **out) {
 }
 static int scan64(cudaStream_t st, u64 *v, u64 n, u64 *total_dev, u64 *bsum);
 
+// every read of a library assumed fixed-length really has that length: *flag_dev (device uint64, caller-zeroed) != 0
+// when one does not (the host-level calls look at a sample of the length words only and verify here)
+static __global__ void k_check_fixed_len(const u32 *__restrict__ bin, u64 n_reads, u32 stride, u32 L, unsigned long long *flag) {
+  bool bad = false;
+  for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (u64)gridDim.x * blockDim.x) bad |= bin[r * stride] != L;
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1ull);
+}
+extern "C" int mhb_check_fixed_len(void *stream, const uint32_t *bin_dev, uint64_t n_reads, uint32_t fixed_len, uint64_t *flag_dev) {
+  if (n_reads == 0) return MHB_OK;
+  if (!bin_dev || !flag_dev || !fixed_len) return mhb_set_error(MHB_ERR_ARG, "bad arguments");
+  k_check_fixed_len<<<mhb_sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(bin_dev, n_reads, 1 + div_ceil(fixed_len, 16), fixed_len,
+                                                                     (unsigned long long *)flag_dev);
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // count: extract
 // ------------------------------------------------------------------------------------------------

@@ -86,7 +86,11 @@ struct BinIndex {
   uint64_t n_edges = 0;
 };
 
-int index_bin(const uint32_t *bin, uint64_t bin_words, uint64_t n_reads, uint32_t k, BinIndex *ix) {
+// sampled = true: a library whose size matches n_reads x (1 + ceil(L0/16)) is taken as fixed-length after looking at
+// ~2048 of its length words only; the caller must then verify ALL of them on the device (mhb_check_fixed_len) and come
+// back with sampled = false when that fails.  (The full host scan touches every cache line of the image: ~10 ms for
+// 10 M reads, all of it inside the end-to-end time of the fused build.)
+int index_bin(const uint32_t *bin, uint64_t bin_words, uint64_t n_reads, uint32_t k, BinIndex *ix, bool sampled = false) {
   ix->fixed_len = 0;
   ix->n_edges = 0;
   if (n_reads == 0) return MHB_OK;
@@ -94,7 +98,12 @@ int index_bin(const uint32_t *bin, uint64_t bin_words, uint64_t n_reads, uint32_
   const uint32_t L0 = bin[0];
   const uint64_t stride = 1 + div_ceil(L0, 16);
   bool fixed = L0 > 0 && bin_words == n_reads * stride;
-  if (fixed) {
+  if (fixed && sampled) {
+    const uint64_t step = std::max<uint64_t>(1, n_reads / 1024);
+    for (uint64_t r = 0; r < n_reads && fixed; r += step) fixed = bin[r * stride] == L0;
+    for (uint64_t r = 0; r < std::min<uint64_t>(n_reads, 1024) && fixed; ++r) fixed = bin[r * stride] == L0;
+    fixed = fixed && bin[(n_reads - 1) * stride] == L0;
+  } else if (fixed) {
     int bad = 0;
 #pragma omp parallel for reduction(| : bad) schedule(static)
     for (long long r = 0; r < (long long)n_reads; ++r) bad |= bin[(uint64_t)r * stride] != L0;
@@ -964,8 +973,12 @@ extern "C" int mhb_s2s_host(const mhb_s2s_args *args, mhb_s2s_result *res) {
 // ================================================================================================
 // fused k_min build: count -> mercy edges -> seq2sdbg, device resident
 // ================================================================================================
+static int build_host_impl(const mhb_build_args *args, mhb_build_result *res, bool full_index);
 extern "C" int mhb_build_host(const mhb_build_args *args, mhb_build_result *res) {
   if (!args || !res) return mhb_set_error(MHB_ERR_ARG, "null args");
+  return build_host_impl(args, res, false);
+}
+static int build_host_impl(const mhb_build_args *args, mhb_build_result *res, bool full_index) {
   memset(res, 0, sizeof(*res));
   const uint32_t k = args->k;
   if (k < 9 || k > MHB_MAX_K) return mhb_set_error(MHB_ERR_ARG, "kmer size must be >= 9 and <= 255");
@@ -976,7 +989,8 @@ extern "C" int mhb_build_host(const mhb_build_args *args, mhb_build_result *res)
   res->words_per_tip_label = WPT;
 
   BinIndex ix;
-  CKR(index_bin(args->bin, args->bin_words, args->n_reads, k, &ix));
+  CKR(index_bin(args->bin, args->bin_words, args->n_reads, k, &ix, !full_index));
+  const bool verify_fixed = !full_index && ix.fixed_len != 0;  // the device checks every length word (below)
   const uint64_t n = ix.n_edges, n_reads = args->n_reads;
   res->n_edge_records = n;
   uint32_t max_len = ix.fixed_len;
@@ -1099,10 +1113,13 @@ extern "C" int mhb_build_host(const mhb_build_args *args, mhb_build_result *res)
       CKR(mhb_count_extract(st, &piece, k, c_a + (size_t)r0 * e_per_read * WR, (r1 - r0) * e_per_read, d_hist0, cw.hist_byte));
     }
   }
+  if (verify_fixed) CKR(mhb_check_fixed_len(st, d_bin, n_reads, ix.fixed_len, d_nsolid + 1));
   CKR(run_count_stage(st, cw, c_a, c_b, n, k, m, d_hist0, d_edges, d_aux, cap_edges, d_mul_hist, d_nsolid, c_wsp, nullptr, nullptr));
-  uint64_t n_solid = 0;
-  CK(cudaMemcpyAsync(&n_solid, d_nsolid, 8, cudaMemcpyDeviceToHost, st));
+  uint64_t h_scal[2] = {0, 0};
+  CK(cudaMemcpyAsync(h_scal, d_nsolid, 16, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  if (verify_fixed && h_scal[1]) return build_host_impl(args, res, true);  // not fixed-length after all: indexed path
+  const uint64_t n_solid = h_scal[0];
   if (n_solid > cap_edges) return mhb_set_error(MHB_ERR_NOMEM, "internal: solid edges exceed capacity");
   res->n_solid = n_solid;
   res->t_count_ms = t.stop();

@@ -121,6 +121,29 @@ class CountPlan:
                                                need, n_tip.value, _ptr(self.first), _ptr(self.last)))
         return n_solid, n_tip.value
 
+    def mercy_edges(self, bin_dev: torch.Tensor, n_solid: int) -> int:
+        """A11 on the device (SeqToSdbg::GenMercyEdges): the candidate reads of the marks just computed, their mercy
+        (k+1)-mers appended behind the n_solid solid edges in self.edges.  Returns the number of mercy edges."""
+        L = self.L
+        if not hasattr(self, "cand"):
+            self.cand = torch.empty(self.n_reads + 1, dtype=torch.int64, device=self.device)
+            self.cand_scratch = torch.empty(L.mhb_mercy_candidates_scratch_bytes(self.n_reads), dtype=torch.uint8, device=self.device)
+            self.mercy_scratch = None
+        nc = C.c_uint64(0)
+        lib._check(L.mhb_mercy_candidates(_stream(), _ptr(self.first), _ptr(self.last), self.n_reads, _ptr(self.cand), C.byref(nc),
+                                          _ptr(self.cand_scratch), self.cand_scratch.numel()))
+        self.n_cand = nc.value
+        if not self.n_cand:
+            return 0
+        need = L.mhb_mercy_edges_scratch_bytes(self.n_cand, self.read_len)
+        if self.mercy_scratch is None or self.mercy_scratch.numel() < need:
+            self.mercy_scratch = torch.empty(int(need * 1.2), dtype=torch.uint8, device=self.device)
+        nm = C.c_uint64(0)
+        lib._check(L.mhb_mercy_edges(_stream(), C.byref(self._reads(bin_dev)), _ptr(self.cand), self.n_cand, self.read_len, self.k,
+                                     _ptr(self.edges), n_solid, C.c_void_p(self.edges.data_ptr() + n_solid * self.WE * 4),
+                                     self.cap_edges - n_solid, C.byref(nm), _ptr(self.mercy_scratch), self.mercy_scratch.numel()))
+        return nm.value
+
     def run(self, bin_dev: torch.Tensor, timed: bool = False):
         """One pass of the count stage over the resident library.  Returns n_solid (host int)."""
         if timed:

@@ -580,3 +580,28 @@ def test_relaxed_sort_is_sorted_permutation(words, n):
     for b in sort_bytes:
         col = lambda x: (x[:, words - 1 - (b >> 2)] >> np.uint32(8 * (b & 3))) & 255
         assert (col(got) == col(exp)).all()
+
+
+def test_fused_build_detects_a_rare_odd_length_read_on_the_device():
+    """mhb_build_host samples the length words of a library whose size matches a fixed length and lets the device verify
+    all of them (mhb_check_fixed_len); a single shorter read outside the sample must send the build through the indexed
+    path - same result as the oracle"""
+    OP, O = _oracle()
+    n_reads, L, k, m = 6000, 150, 27, 2
+    b = synth.synth_reads(n_reads, L, 30000, 0.01, seed=77).copy()
+    victim = 3333  # not in the first 1024, not a multiple of the sampling step
+    b[victim, 0] = 147  # same number of packed words, three bases shorter
+    b[victim, 1 + 9] &= np.uint32(0xFC000000)  # bases 144..146 stay, the tail is zero as buildlib leaves it
+    reads = O.unpack_bin(b.tobytes(), reverse=True)
+    oc = OP.oracle_count(reads, k, m)
+    g = lib.build_host(b.reshape(-1), n_reads, k, m, need_mercy=True, want_edges=True)
+    assert g["n_solid"] == oc["n_solid"] and (g["edges"] == oc["edges"]).all()
+    assert (g["cand_ids"] == oc["cand_ids"]).all()
+    seqs, mult = O.edges_as_seqs(oc["edges"], k)
+    cand = O.unpack_bin(oc["cand_bytes"], reverse=False)
+    me = O.gen_mercy(oc["edges"], cand, k)
+    if len(me):
+        seqs = O.Seqs.concat([seqs, O.Seqs.from_fixed(me, k + 1)])
+        mult = np.concatenate([mult, np.ones(len(me), np.uint16)])
+    os_ = O.seq2sdbg(seqs, mult, k)
+    assert g["bytes"] == os_["bytes"]

@@ -102,3 +102,17 @@ def test_two_rank_exchange_reproduces_oracle_edges():
     assert len(keys) == oc["n_solid"]
     assert (keys[:, :2] == (oc["edges"][:, :2] & np.array([0xFFFFFFFF, 0xFFFFFF00], np.uint32))).all()
     assert (np.minimum(mult, 65535) == (oc["edges"][:, 2] & 0xFFFF)).all()
+
+
+def test_reverse_rows_reproduces_the_reference_cand_file():
+    """multigpu._reverse_rows (the `.cand` writer of the partitioned build): candidate reads in the REVERSED orientation
+    KmerCounter holds them in (kmer_counter.cpp:387-401) - byte-identical to the `.cand` the reference wrote"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_pipeline as OP
+    from megahit_b200.multigpu import _reverse_rows
+    case = os.path.join(GOLDEN, "syn150_k27")
+    rows = np.fromfile(os.path.join(case, "reads.lib.bin"), np.uint32).reshape(3000, -1)
+    oc = OP.oracle_count(OP.load_reads(case), 27, 2)
+    got = _reverse_rows(rows[oc["cand_ids"]], 150).tobytes()
+    assert got == open(os.path.join(case, "cand.bin"), "rb").read() and len(got) > 0
+    assert _reverse_rows(rows[:0], 150).shape == (0, rows.shape[1])
