@@ -79,6 +79,14 @@ int mhbo_gen_mercy(const uint32_t *edges, uint64_t n_edges, uint32_t wpe, const 
 int mhbo_unpack_bin(const uint8_t *bin, uint64_t bin_bytes, int reverse, uint64_t *n_seqs,
                     uint64_t *n_words, uint32_t *words, uint64_t *word_off, uint32_t *len);
 
+/* main_read2sdbg (main_sdbg_build.cpp:88-156): read_to_sdbg_s1.cpp (only when m > 1) + the mercy step of
+ * Read2SdbgS2::Initialize (read_to_sdbg_s2.cpp:117-263, when need_mercy) + read_to_sdbg_s2.cpp, with kmsort's tie
+ * order reproduced (mhb_oracle_r2s.c).  counting[65536] = what stage 1 dumps to P.counting (all zero for m == 1).
+ * *is_solid_out (optional, malloc'ed, one bit per base of the package, bit i of byte i/8) = the solid-edge marker after
+ * the mercy step; *n_bases_out its size in bits. */
+int mhbo_read2sdbg(const mhbo_seqs *reads, uint32_t k, int32_t m, int need_mercy, mhbo_sdbg_out *out, int64_t *counting,
+                   uint64_t *n_mercy_out, uint8_t **is_solid_out, uint64_t *n_bases_out);
+
 void mhbo_free(void *p);
 
 #ifdef __cplusplus

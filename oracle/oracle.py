@@ -201,3 +201,33 @@ def edges_as_seqs(edges: np.ndarray, k: int):
     if rem:
         body[:, wm - 1] &= np.uint32((0xFFFFFFFF << (32 - 2 * rem)) & 0xFFFFFFFF)
     return Seqs.from_fixed(body, k + 1), mult
+
+
+def read2sdbg(reads: Seqs, k: int, m: int, need_mercy: bool, want_solid: bool = False):
+    """main_read2sdbg (main_sdbg_build.cpp:88-156) on the oracle: SdBG stream + what stage 1 writes to P.counting."""
+    L = lib()
+    L.mhbo_read2sdbg.restype = C.c_int
+    out = _SdbgOut()
+    s = reads.c()
+    counting = np.zeros(65536, np.int64)
+    nm, nb = C.c_uint64(), C.c_uint64()
+    solid = C.POINTER(C.c_uint8)()
+    rc = L.mhbo_read2sdbg(C.byref(s), C.c_uint32(k), C.c_int32(m), C.c_int(int(need_mercy)), C.byref(out),
+                          C.c_void_p(counting.ctypes.data), C.byref(nm), C.byref(solid) if want_solid else None,
+                          C.byref(nb))
+    assert rc == 0, rc
+    nbytes = out.bucket_byte_off[65536]
+    res = {
+        "n_records": out.n_records, "n_items": out.n_items, "words_per_tip_label": out.words_per_tip_label,
+        "bucket_items": np.array(out.bucket_items, np.uint64), "bucket_tips": np.array(out.bucket_tips, np.uint64),
+        "bucket_large_mul": np.array(out.bucket_large_mul, np.uint64),
+        "bucket_byte_off": np.array(out.bucket_byte_off, np.uint64),
+        "w_count": np.array(out.w_count, np.uint64), "ones_in_last": out.ones_in_last,
+        "bytes": bytes(np.ctypeslib.as_array(out.bytes, (max(nbytes, 1),))[:nbytes]),
+        "counting": counting, "n_mercy": nm.value, "n_bases": nb.value,
+    }
+    if want_solid:
+        res["is_solid"] = np.ctypeslib.as_array(solid, (nb.value // 8 + 2,)).copy()
+        L.mhbo_free(solid)
+    L.mhbo_sdbg_free(C.byref(out))
+    return res
