@@ -299,6 +299,14 @@ int mhb_s2s_emit(void *stream, const uint32_t *sorted_records, uint64_t n, uint3
                  uint64_t capacity_bytes, uint64_t *bucket_table, uint64_t *totals, void *scratch,
                  size_t scratch_bytes);
 
+/* The same emitter for the items of the 1-pass build (read2sdbg stage 2, read_to_sdbg_s2.cpp:521-614: identical
+ * group logic, multiplicity = run length, already folded into the records by the caller).  label_fmt = 1: tip labels
+ * carry the raw words of the reference's stage-2 record (flags nondollar<<3 | prev in the low 4 bits of word
+ * ceil((2k+4)/32)-1, read_to_sdbg_s2.cpp:483-485, :602-606) instead of the seq2sdbg record's; 0 = mhb_s2s_emit. */
+int mhb_s2s_emit_fmt(void *stream, const uint32_t *sorted_records, uint64_t n, uint32_t k, uint8_t *bytes_out,
+                     uint64_t capacity_bytes, uint64_t *bucket_table, uint64_t *totals, void *scratch,
+                     size_t scratch_bytes, int label_fmt);
+
 /* ---------------------------------------------------------------------------------------------
  * 2. Host level (buffers in host memory; device 0 unless mhb_set_device was called)
  * ------------------------------------------------------------------------------------------- */
@@ -407,6 +415,17 @@ typedef struct {
 
 int mhb_build_host(const mhb_build_args *args, mhb_build_result *res);
 
+/* The 1-pass k_min build (main_read2sdbg, main_sdbg_build.cpp:88-156; `megahit --kmin-1pass`, and the route the driver
+ * forces for --min-count 1, src/megahit:540-542): Read2SdbgS1 (read_to_sdbg_s1.cpp; only when m > 1) marks the solid
+ * (k+1)-mer occurrences and the mercy candidates - with kmlib::kmsort's order among equal keys reproduced, because
+ * stage 1 reads prev/next of a group's FIRST record for the whole group (:393-401) -, the mercy step of
+ * Read2SdbgS2::Initialize (read_to_sdbg_s2.cpp:117-263, need_mercy) adds the (k+1)-mers between tips, Read2SdbgS2
+ * builds the SdBG from the marked occurrences.  Same argument / result structs as mhb_build_host: want_edges is
+ * ignored (this route writes no edges); res->counting (malloc'ed, 65536) = what stage 1 dumps to P.counting (zero for
+ * m == 1), res->n_solid = distinct stage-2 items, t_count_ms / t_mercy_ms = bucket partition / kmsort emulation.
+ * Stage 1 handles k <= 237 (records of at most 17 words); larger k with m > 1 returns MHB_ERR_ARG. */
+int mhb_read2sdbg_host(const mhb_build_args *args, mhb_build_result *res);
+
 /* A11 from host buffers (SeqToSdbg::GenMercyEdges, seq_to_sdbg.cpp:171-357, as `seq2sdbg --need_mercy` runs it between
  * loading `.edges` / `.cand` and the sort): edges = n_edges sorted `.edges`-format records, cand_bin = the `.cand` image
  * (`.bin` record format, reads in the reversed orientation KmerCounter wrote them, kmer_counter.cpp:387-401).
@@ -446,8 +465,22 @@ typedef struct {
   int32_t mem_flag;
 } mhb_seq2sdbg_opts;
 
+/* main_read2sdbg options (main_sdbg_build.cpp:95-111): those of `count` plus --need_mercy */
+typedef struct {
+  uint32_t k;
+  int32_t m;
+  double host_mem;
+  int32_t num_cpu_threads;
+  const char *read_lib_file;
+  const char *output_prefix;
+  int32_t mem_flag;
+  int32_t need_mercy;
+} mhb_read2sdbg_opts;
+
 int mhb_count_run(const mhb_count_opts *opts);
 int mhb_seq2sdbg_run(const mhb_seq2sdbg_opts *opts);
+/* writes P.sdbg.0, P.sdbg_info, P.counting (m > 1) and the (empty) P.mercy_cand.<i> temp files of the reference */
+int mhb_read2sdbg_run(const mhb_read2sdbg_opts *opts);
 
 /* `count` on n_gpus GPUs of this node (fixed-length read libraries; anything else, or n_gpus <= 1, runs mhb_count_run).
  * One worker process per GPU is forked; each takes a contiguous block of the reads, the records meet on the rank that
@@ -470,6 +503,22 @@ int mhb_selftest_count_records_roll(const uint32_t *read_words, uint32_t nwords,
                                     uint64_t *rec4_out, uint32_t *strand4_out);
 int mhb_selftest_s2s_record(const uint32_t *seq_words, uint32_t nwords, uint32_t L, uint32_t k, uint32_t strand,
                             uint32_t offset, uint32_t mult, uint32_t *rec_out);
+
+/* read2sdbg building blocks on host arrays (same __host__ __device__ code as the kernels): stage-1 record e of a
+ * package-orientation read (rec_out: key words + 2), stage-2 item (seq2sdbg layout) + palindrome flag, kmsort of one
+ * bucket (records of nw + 2 words), stage-1 Lv2Postprocess over one sorted bucket of a fixed-length library, and the
+ * mercy step of one read.  Bit arrays: bit i of word i/32. */
+int mhb_selftest_r2s_s1_record(const uint32_t *pkg_words, uint32_t nwords, uint32_t L, uint32_t k, uint32_t e,
+                               uint64_t base_off, uint32_t *rec_out);
+int mhb_selftest_r2s_item(const uint32_t *pkg_words, uint32_t nwords, uint32_t L, uint32_t k, uint32_t i, uint32_t strand,
+                          uint32_t type, uint32_t *rec_out, uint32_t *palindrome_out);
+int mhb_selftest_kmsort(uint32_t *recs, uint64_t n, uint32_t nw);
+int mhb_selftest_r2s_s1_group(const uint32_t *recs, uint64_t n, uint32_t k, int32_t m, uint32_t fixed_len, uint64_t n_reads,
+                              int need_mercy, uint32_t *is_solid, uint32_t *no_in, uint32_t *no_out, uint32_t *any,
+                              int64_t *counting);
+int mhb_selftest_r2s_mercy_read(uint32_t fixed_len, uint64_t n_reads, uint64_t r, uint32_t k, const uint32_t *is_solid,
+                                const uint32_t *no_in, const uint32_t *no_out, const uint32_t *any, uint32_t *mercy,
+                                uint32_t *added_out);
 
 #ifdef __cplusplus
 }

@@ -494,6 +494,14 @@ extern "C" size_t mhb_s2s_emit_scratch_bytes(uint64_t n, uint32_t k) {
 extern "C" int mhb_s2s_emit(void *stream, const uint32_t *sorted_records, uint64_t n, uint32_t k, uint8_t *bytes_out,
                             uint64_t capacity_bytes, uint64_t *bucket_table, uint64_t *totals, void *scratch,
                             size_t scratch_bytes) {
+  return mhb_s2s_emit_fmt(stream, sorted_records, n, k, bytes_out, capacity_bytes, bucket_table, totals, scratch,
+                          scratch_bytes, 0);
+}
+
+extern "C" int mhb_s2s_emit_fmt(void *stream, const uint32_t *sorted_records, uint64_t n, uint32_t k, uint8_t *bytes_out,
+                                uint64_t capacity_bytes, uint64_t *bucket_table, uint64_t *totals, void *scratch,
+                                size_t scratch_bytes, int label_fmt) {
+  const u32 fmt = label_fmt ? 1u : 0u;
   if (k < 9 || k > MHB_MAX_K || !bucket_table || !totals) return mhb_set_error(MHB_ERR_ARG, "bad args");
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemsetAsync(totals, 0, 16 * 8, st));
@@ -531,7 +539,7 @@ extern "C" int mhb_s2s_emit(void *stream, const uint32_t *sorted_records, uint64
     u64 grid = (u64)sm_count() * bps;                                                                               \
     if (grid > (nc + kEmit2Warps - 1) / kEmit2Warps) grid = (nc + kEmit2Warps - 1) / kEmit2Warps;                   \
     k_s2s_judge<WW><<<(unsigned)grid, kEmit2Warps * 32, smem, st>>>(sorted_records, n, k, (u32)nc, tmp, chunk_tot,   \
-                                                                   bucket_local, totals);                          \
+                                                                   bucket_local, totals, fmt);                     \
   }
     MHB_FOR_WR(M)
 #undef M
@@ -563,7 +571,7 @@ extern "C" int mhb_s2s_emit(void *stream, const uint32_t *sorted_records, uint64
 #define M(WW)                                                                                                    \
   if (W == WW)                                                                                                   \
     k_s2s_write<WW><<<(unsigned)nblk, kEmitThreads, 0, st>>>(sorted_records, n, k, btot, bytes_out, capacity_bytes, \
-                                                            bucket_start, totals);
+                                                            bucket_start, totals, fmt);
   MHB_FOR_WR(M)
 #undef M
   CK_LAUNCH();

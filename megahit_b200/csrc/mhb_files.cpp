@@ -252,6 +252,36 @@ int read_contigs(const std::string &path, uint32_t min_len, uint32_t k_from, uin
   return MHB_OK;
 }
 
+// sdbg_writer.cpp:25-79 + sdbg_meta.cpp:44-61: one file, buckets in id order
+int write_sdbg_single(const std::string &prefix, uint32_t k, uint32_t words_per_tip_label, uint64_t n_items, uint64_t n_bytes,
+                      const uint8_t *bytes, const uint64_t *bucket_table) {
+  int rc = MHB_OK;
+  FILE *f = fopen((prefix + ".sdbg.0").c_str(), "wb");
+  if (!f) rc = mhb_set_error(MHB_ERR_IO, "cannot open %s.sdbg.0", prefix.c_str());
+  else {
+    if (n_bytes && fwrite(bytes, 1, n_bytes, f) != n_bytes) rc = mhb_set_error(MHB_ERR_IO, "write failed");
+    fclose(f);
+  }
+  if (!rc) {
+    FILE *g = fopen((prefix + ".sdbg_info").c_str(), "w");
+    if (!g) rc = mhb_set_error(MHB_ERR_IO, "cannot open %s.sdbg_info", prefix.c_str());
+    else {
+      fprintf(g, "k %u\nwords_per_tip_label %u\nnum_buckets %d\nnum_files %d\n", k, words_per_tip_label, MHB_NUM_BUCKETS,
+              n_items ? 1 : 0);
+      int empty = 0;
+      for (int b = 0; b < MHB_NUM_BUCKETS; ++b) {
+        const uint64_t *t = bucket_table + 4 * (size_t)b;
+        if (t[1]) fprintf(g, "%d 0 %llu %llu %llu %llu\n", b, (unsigned long long)t[0], (unsigned long long)t[1],
+                          (unsigned long long)t[2], (unsigned long long)t[3]);
+        else ++empty;
+      }
+      for (int i = 0; i < empty; ++i) fprintf(g, "18446744073709551615 18446744073709551615 0 0 0 0\n");
+      fclose(g);
+    }
+  }
+  return rc;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -412,31 +442,7 @@ extern "C" int mhb_seq2sdbg_run(const mhb_seq2sdbg_opts *o) {
   XINFO("GPU seq2sdbg: %llu sort items, extract %.2f ms, sort %.2f ms, emit %.2f ms\n", (unsigned long long)res->n_records,
         res->t_extract_ms, res->t_sort_ms, res->t_emit_ms);
 
-  // sdbg_writer.cpp:25-79 + sdbg_meta.cpp:44-61: one file, buckets in id order
-  int rc = MHB_OK;
-  FILE *f = fopen((prefix + ".sdbg.0").c_str(), "wb");
-  if (!f) rc = mhb_set_error(MHB_ERR_IO, "cannot open %s.sdbg.0", prefix.c_str());
-  else {
-    if (res->n_bytes && fwrite(res->bytes, 1, res->n_bytes, f) != res->n_bytes) rc = mhb_set_error(MHB_ERR_IO, "write failed");
-    fclose(f);
-  }
-  if (!rc) {
-    FILE *g = fopen((prefix + ".sdbg_info").c_str(), "w");
-    if (!g) rc = mhb_set_error(MHB_ERR_IO, "cannot open %s.sdbg_info", prefix.c_str());
-    else {
-      fprintf(g, "k %u\nwords_per_tip_label %u\nnum_buckets %d\nnum_files %d\n", k, res->words_per_tip_label, MHB_NUM_BUCKETS,
-              res->n_items ? 1 : 0);
-      int empty = 0;
-      for (int b = 0; b < MHB_NUM_BUCKETS; ++b) {
-        const uint64_t *t = res->bucket_table + 4 * (size_t)b;
-        if (t[1]) fprintf(g, "%d 0 %llu %llu %llu %llu\n", b, (unsigned long long)t[0], (unsigned long long)t[1],
-                          (unsigned long long)t[2], (unsigned long long)t[3]);
-        else ++empty;
-      }
-      for (int i = 0; i < empty; ++i) fprintf(g, "18446744073709551615 18446744073709551615 0 0 0 0\n");
-      fclose(g);
-    }
-  }
+  const int rc = write_sdbg_single(prefix, k, res->words_per_tip_label, res->n_items, res->n_bytes, res->bytes, res->bucket_table);
   XINFO("Number of $ A C G T A- C- G- T-:\n");
   XINFO("");
   for (int i = 0; i < 9; ++i) fprintf(stderr, "%llu ", (unsigned long long)res->w_count[i]);
@@ -446,5 +452,69 @@ extern "C" int mhb_seq2sdbg_run(const mhb_seq2sdbg_opts *o) {
   XINFO("Total number of $v edges: %llu\n", (unsigned long long)res->n_tips);
   XINFO("seq2sdbg done. Time elapsed: %.4f\n", now_s() - t0);
   mhb_free(res->bytes);
+  return rc;
+}
+
+// ================================================================================================
+// read2sdbg (main_read2sdbg, main_sdbg_build.cpp:88-156)
+// ================================================================================================
+extern "C" int mhb_read2sdbg_run(const mhb_read2sdbg_opts *o) {
+  if (!o || !o->read_lib_file || !o->read_lib_file[0]) return mhb_set_error(MHB_ERR_ARG, "No input file!");
+  if (o->host_mem == 0) return mhb_set_error(MHB_ERR_ARG, "Please specify the host memory!");
+  const std::string lib = o->read_lib_file, prefix = o->output_prefix ? o->output_prefix : "out";
+  const double t0 = now_s();
+  long long total_bases = 0, n_reads = 0;
+  {
+    std::ifstream is(lib + ".lib_info");
+    if (!(is >> total_bases >> n_reads)) return mhb_set_error(MHB_ERR_IO, "cannot read %s.lib_info", lib.c_str());
+  }
+  std::vector<uint32_t> bin;
+  if (!read_file(lib + ".bin", &bin)) return MHB_ERR_IO;
+  XINFO("%lld reads, %lld total bases; k = %u, m = %d, need_mercy = %d\n", n_reads, total_bases, o->k, o->m, o->need_mercy);
+  // the candidate files stage 1 hands to stage 2 inside the reference process (read_to_sdbg_s1.cpp:111-126: 1, 2, 4 .. 64
+  // files by read count); here the candidates never leave the device (three bit planes), the files are created empty so
+  // that whatever cleans up after the reference finds them
+  int n_mercy_files = 1;
+  while (n_mercy_files * 10485760LL < n_reads && n_mercy_files < 64) n_mercy_files <<= 1;
+  for (int i = 0; i < n_mercy_files; ++i) {
+    FILE *f = fopen((prefix + ".mercy_cand." + std::to_string(i)).c_str(), "wb");
+    if (!f) return mhb_set_error(MHB_ERR_IO, "cannot open %s.mercy_cand.%d", prefix.c_str(), i);
+    fclose(f);
+  }
+  mhb_build_args a;
+  memset(&a, 0, sizeof(a));
+  a.k = o->k;
+  a.m = o->m;
+  a.bin = bin.data();
+  a.bin_words = bin.size();
+  a.n_reads = (uint64_t)n_reads;
+  a.need_mercy = o->need_mercy;
+  mhb_build_result res;
+  if (int rc = mhb_read2sdbg_host(&a, &res)) return rc;
+  XINFO("GPU read2sdbg: %llu (k+1)-mer positions, bucket partition %.2f ms, kmsort %.2f ms, %llu mercy edges, %llu sort items, total %.2f ms\n",
+        (unsigned long long)res.n_edge_records, res.t_count_ms, res.t_mercy_ms, (unsigned long long)res.n_mercy,
+        (unsigned long long)res.n_sort_items, res.t_total_ms);
+  int rc = MHB_OK;
+  if (o->m > 1) {  // Read2SdbgS1::Lv0Postprocess, read_to_sdbg_s1.cpp:557-566
+    FILE *f = fopen((prefix + ".counting").c_str(), "w");
+    if (!f) rc = mhb_set_error(MHB_ERR_IO, "cannot open %s.counting", prefix.c_str());
+    else {
+      for (int i = 1; i <= MHB_MAX_MUL; ++i) fprintf(f, "%d %lld\n", i, (long long)res.counting[i]);
+      fclose(f);
+    }
+    if (o->need_mercy) XINFO("Number mercy: %llu\n", (unsigned long long)res.n_mercy);
+  }
+  if (!rc) rc = write_sdbg_single(prefix, o->k, res.words_per_tip_label, res.n_items, res.n_bytes, res.bytes, res.bucket_table);
+  XINFO("Number of $ A C G T A- C- G- T-:\n");
+  XINFO("");
+  for (int i = 0; i < 9; ++i) fprintf(stderr, "%llu ", (unsigned long long)res.w_count[i]);
+  fprintf(stderr, "\n");
+  XINFO("Total number of edges: %llu\n", (unsigned long long)res.n_items);
+  XINFO("Total number of ONEs: %llu\n", (unsigned long long)res.ones_in_last);
+  XINFO("Total number of $v edges: %llu\n", (unsigned long long)res.n_tips);
+  XINFO("read2sdbg done. Time elapsed: %.4f\n", now_s() - t0);
+  mhb_free(res.bytes);
+  mhb_free(res.bucket_table);
+  mhb_free(res.counting);
   return rc;
 }

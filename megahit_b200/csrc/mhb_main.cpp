@@ -164,6 +164,43 @@ int main_seq2sdbg(int argc, char **argv) {
   return 0;
 }
 
+int forward_to_reference(char **argv);
+
+// main_read2sdbg (main_sdbg_build.cpp:88-156)
+int main_read2sdbg(int argc, char **argv, char **full_argv) {
+  RssRecorder rec;
+  const std::vector<Opt> opts = {{"kmer_k", "k", false},         {"min_kmer_frequency", "m", false}, {"host_mem", "", false},
+                                 {"num_cpu_threads", "", false}, {"read_lib_file", "", false},       {"output_prefix", "", false},
+                                 {"mem_flag", "", false},        {"need_mercy", "", true}};
+  const char *usage = "Usage: sdbg_builder read2sdbg --read_lib_file fastx_file -o out";
+  std::map<std::string, std::string> v;
+  std::string err;
+  if (!parse(argc, argv, opts, &v, &err)) return fail_usage(err, usage);
+  mhb_read2sdbg_opts o;
+  memset(&o, 0, sizeof(o));
+  o.k = v.count("kmer_k") ? (uint32_t)atoi(v["kmer_k"].c_str()) : 21;  // read_to_sdbg.h:36-45 defaults
+  o.m = v.count("min_kmer_frequency") ? atoi(v["min_kmer_frequency"].c_str()) : 2;
+  o.host_mem = v.count("host_mem") ? atof(v["host_mem"].c_str()) : 0;
+  o.num_cpu_threads = v.count("num_cpu_threads") ? atoi(v["num_cpu_threads"].c_str()) : 0;
+  o.mem_flag = v.count("mem_flag") ? atoi(v["mem_flag"].c_str()) : 1;
+  o.need_mercy = v.count("need_mercy") ? 1 : 0;
+  const std::string lib = v["read_lib_file"], out = v.count("output_prefix") ? v["output_prefix"] : "out";
+  o.read_lib_file = lib.c_str();
+  o.output_prefix = out.c_str();
+  if (lib.empty()) return fail_usage("No input file!", usage);
+  if (o.host_mem == 0) return fail_usage("Please specify the host memory!", usage);
+  if (o.m > 1 && o.k > 237) {  // stage-1 records wider than the device sort handles: the reference's CPU path
+    fprintf(stderr, "megahit_b200: read2sdbg with k = %u and min count %d is forwarded to the reference\n", o.k, o.m);
+    return forward_to_reference(full_argv);
+  }
+  if (int rc = mhb_read2sdbg_run(&o)) {
+    fprintf(stderr, "FATAL megahit_b200: %s\n", mhb_last_error());
+    (void)rc;
+    exit(1);
+  }
+  return 0;
+}
+
 int forward_to_reference(char **argv) {
   std::string ref;
   if (const char *e = getenv("MHB_REFERENCE_CORE")) ref = e;
@@ -190,12 +227,13 @@ int forward_to_reference(char **argv) {
 
 int main(int argc, char **argv) {
   if (argc < 2) {
-    fprintf(stderr, "Usage: %s <sub_program> [sub options]\n    GPU sub-programs: count, seq2sdbg; everything else is forwarded to the reference megahit_core\n", argv[0]);
+    fprintf(stderr, "Usage: %s <sub_program> [sub options]\n    GPU sub-programs: count, seq2sdbg, read2sdbg; everything else is forwarded to the reference megahit_core\n", argv[0]);
     return 1;
   }
   const std::string cmd = argv[1];
   if (cmd == "count") return main_count(argc - 1, argv + 1);
   if (cmd == "seq2sdbg") return main_seq2sdbg(argc - 1, argv + 1);
+  if (cmd == "read2sdbg") return main_read2sdbg(argc - 1, argv + 1, argv);
   if (cmd == "checkcpu" || cmd == "checkpopcnt" || cmd == "checkbmi2") {
     printf("1\n");
     return 0;

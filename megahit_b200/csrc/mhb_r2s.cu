@@ -1,0 +1,532 @@
+// mhb_r2s.cu -- `read2sdbg` on the device: host-level entry point mhb_read2sdbg_host and the
+// self-test hooks of its building blocks.  Kernels: mhb_r2s.cuh.  Reference: main_sdbg_build.cpp:88-156,
+// sorting/read_to_sdbg_s1.cpp, sorting/read_to_sdbg_s2.cpp.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "mhb_common.cuh"
+#include "mhb_r2s.cuh"
+
+using namespace mhb;
+
+// three-phase scan of mhb_device.cu
+int scan32(cudaStream_t st, const uint32_t *in, uint64_t n, uint64_t *out, uint64_t *total_dev, uint64_t *bsum);
+#define MHB_FOR_RW(M) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12) M(13) M(14) M(15) M(16) M(17)
+
+namespace {
+
+struct DevBuf {  // cudaMalloc'ed scratch released on scope exit
+  void *p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  int alloc(size_t b, const char *what) {
+    release();
+    b = (b + 255) & ~(size_t)255;
+    if (b == 0) b = 256;
+    cudaError_t e = cudaMalloc(&p, b);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+      return mhb_set_error(MHB_ERR_NOMEM, "read2sdbg: cudaMalloc of %zu bytes for %s failed: %s", b, what,
+                           cudaGetErrorString(e));
+    }
+    bytes = b;
+    return MHB_OK;
+  }
+  template <class T>
+  T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+#define CKR(call)        \
+  do {                   \
+    int rc_ = (call);    \
+    if (rc_) return rc_; \
+  } while (0)
+
+unsigned grid_for(uint64_t n, unsigned threads, unsigned per_sm = 16) {
+  uint64_t g = (n + threads - 1) / threads;
+  const uint64_t cap = (uint64_t)sm_count() * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+// host index of the `.bin` image: package geometry of every read
+struct PkgIndex {
+  uint32_t fixed_len = 0, fixed_words = 0, max_len = 0;
+  uint64_t n_reads = 0, n_words = 0, n_bases = 0, n_s1 = 0, n_edges = 0;
+  std::vector<uint64_t> rec_off, word_off, base_off, s1_off, edge_off;
+  std::vector<uint32_t> len;
+};
+
+int index_pkg(const uint32_t *bin, uint64_t bin_words, uint64_t n_reads, uint32_t k, PkgIndex *ix) {
+  ix->n_reads = n_reads;
+  if (n_reads == 0) return MHB_OK;
+  if (bin_words == 0) return mhb_set_error(MHB_ERR_ARG, "empty .bin image for %llu reads", (unsigned long long)n_reads);
+  const uint32_t L0 = bin[0];
+  const uint64_t stride = 1 + div_ceil(L0, 16);
+  bool fixed = L0 > 0 && bin_words == n_reads * stride;
+  if (fixed) {
+    int bad = 0;
+#pragma omp parallel for reduction(| : bad) schedule(static)
+    for (long long r = 0; r < (long long)n_reads; ++r) bad |= bin[(uint64_t)r * stride] != L0;
+    fixed = !bad;
+  }
+  if (fixed) {
+    ix->fixed_len = ix->max_len = L0;
+    ix->fixed_words = div_ceil(L0, 16);
+    ix->n_words = n_reads * ix->fixed_words;
+    ix->n_bases = n_reads * (uint64_t)L0;
+    if (L0 >= k + 1) {
+      ix->n_s1 = n_reads * (uint64_t)(L0 - k + 4);
+      ix->n_edges = n_reads * (uint64_t)(L0 - k);
+    }
+    return MHB_OK;
+  }
+  ix->rec_off.resize(n_reads + 1);
+  ix->word_off.resize(n_reads + 1);
+  ix->base_off.resize(n_reads + 1);
+  ix->s1_off.resize(n_reads + 1);
+  ix->edge_off.resize(n_reads + 1);
+  ix->len.resize(n_reads);
+  uint64_t pos = 0, w = 0, b = 0, s1 = 0, e = 0;
+  for (uint64_t r = 0; r < n_reads; ++r) {
+    if (pos >= bin_words) return mhb_set_error(MHB_ERR_ARG, ".bin image truncated at read %llu", (unsigned long long)r);
+    const uint32_t L = bin[pos];
+    const uint32_t eff = L == 0 ? 1 : L;  // sequence_package.h:276-281
+    ix->rec_off[r] = pos;
+    ix->word_off[r] = w;
+    ix->base_off[r] = b;
+    ix->s1_off[r] = s1;
+    ix->edge_off[r] = e;
+    ix->len[r] = eff;
+    ix->max_len = std::max(ix->max_len, eff);
+    pos += 1 + div_ceil(L, 16);
+    w += div_ceil(eff, 16);
+    b += eff;
+    if (eff >= k + 1) {
+      s1 += eff - k + 4;
+      e += eff - k;
+    }
+  }
+  if (pos > bin_words) return mhb_set_error(MHB_ERR_ARG, ".bin image truncated");
+  ix->rec_off[n_reads] = pos;
+  ix->word_off[n_reads] = w;
+  ix->base_off[n_reads] = b;
+  ix->s1_off[n_reads] = s1;
+  ix->edge_off[n_reads] = e;
+  ix->n_words = w;
+  ix->n_bases = b;
+  ix->n_s1 = s1;
+  ix->n_edges = e;
+  return MHB_OK;
+}
+
+template <class T>
+int upload(DevBuf &d, const std::vector<T> &v, const char *what) {
+  CKR(d.alloc(v.size() * sizeof(T), what));
+  if (!v.empty()) CK(cudaMemcpy(d.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return MHB_OK;
+}
+
+// ---- stage 1 on the device: is_solid bits, mercy planes, multiplicity histogram ----
+int run_stage1(cudaStream_t st, const PkgView &pv, const PkgIndex &ix, uint32_t k, int32_t m, bool need_mercy, const S1Out &out,
+               unsigned long long *d_mul_hist, double *t_sort_ms, double *t_kmsort_ms) {
+  const uint32_t NW = r2s_s1_key_words(k), RW = NW + 2;
+  const uint64_t n = ix.n_s1;
+  if (n == 0) return MHB_OK;
+  if (RW > 17)
+    return mhb_set_error(MHB_ERR_ARG, "read2sdbg: stage 1 supports k <= 237 (record of %u words > 17)", RW);
+  if (n >= (1ull << 40)) return mhb_set_error(MHB_ERR_ARG, "read2sdbg: too many stage-1 records for one round");
+  DevBuf a, b, ws, bstart, segs0, segs1, counter;
+  const size_t rec_bytes = (size_t)n * RW * 4 + 16, ws_bytes = mhb_sort_workspace_bytes(n, RW);
+  CKR(a.alloc(rec_bytes, "stage-1 records"));
+  CKR(b.alloc(rec_bytes, "stage-1 records (sort buffer)"));
+  CKR(ws.alloc(ws_bytes, "sort workspace"));
+  CKR(bstart.alloc((MHB_NUM_BUCKETS + 1) * 8, "bucket bounds"));
+  const uint64_t seg_cap = n / (kKmInsertThreshold + 1) + 2;
+  CKR(segs0.alloc(seg_cap * sizeof(KmSeg), "kmsort ranges"));
+  CKR(segs1.alloc(seg_cap * sizeof(KmSeg), "kmsort ranges"));
+  CKR(counter.alloc(8, "counter"));
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventCreate(&e2);
+#define M(WW)                                                                                         \
+  if (NW == WW) k_r2s_s1_extract<WW><<<grid_for(n, 256), 256, 0, st>>>(pv, k, a.as<u32>(), n);
+  MHB_FOR_W(M)
+#undef M
+  CK_LAUNCH();
+  cudaEventRecord(e0, st);
+  // the reference's bucket input order: records of one 16-bit bucket in global read order = a STABLE sort on the two
+  // leading key bytes (base_engine.cpp:323-348 fills every bucket thread by thread, i.e. in read order)
+  const uint8_t bytes[2] = {(uint8_t)(4 * RW - 2), (uint8_t)(4 * RW - 1)};
+  int in_b = 0;
+  CKR(mhb_sort_records(st, a.as<u32>(), b.as<u32>(), n, RW, bytes, 2, nullptr, ws.p, ws_bytes, &in_b));
+  u32 *recs = in_b ? b.as<u32>() : a.as<u32>();
+  cudaEventRecord(e1, st);
+  k_r2s_bucket_bounds<<<(MHB_NUM_BUCKETS + 1 + 255) / 256, 256, 0, st>>>(recs, n, RW, bstart.as<u64>());
+  CK_LAUNCH();
+  // kmsort, level by level (kmsort.h:103-117 entry, :43-101 per range)
+  int kb = 4 * (int)NW - 2 - 1;
+  KmSeg *cur = segs0.as<KmSeg>(), *nxt = segs1.as<KmSeg>();
+  unsigned long long *d_cnt = counter.as<unsigned long long>();
+  CK(cudaMemsetAsync(d_cnt, 0, 8, st));
+#define M(WW)                                                                                                      \
+  if (RW == WW)                                                                                                    \
+    k_r2s_kmsort_level<WW><<<MHB_NUM_BUCKETS / 128, 128, 0, st>>>(recs, NW, kb, nullptr, bstart.as<u64>(),          \
+                                                                  MHB_NUM_BUCKETS, nxt, d_cnt, seg_cap);
+  MHB_FOR_RW(M)
+#undef M
+  CK_LAUNCH();
+  for (;;) {
+    unsigned long long n_next = 0;
+    CK(cudaMemcpyAsync(&n_next, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_next == 0 || kb == 0) break;
+    if (n_next > seg_cap) return mhb_set_error(MHB_ERR_CUDA, "read2sdbg: internal: kmsort range list overflow");
+    std::swap(cur, nxt);
+    --kb;
+    CK(cudaMemsetAsync(d_cnt, 0, 8, st));
+#define M(WW)                                                                                                         \
+  if (RW == WW)                                                                                                       \
+    k_r2s_kmsort_level<WW><<<(unsigned)((n_next + 127) / 128), 128, 0, st>>>(recs, NW, kb, cur, nullptr, n_next, nxt, \
+                                                                            d_cnt, seg_cap);
+    MHB_FOR_RW(M)
+#undef M
+    CK_LAUNCH();
+  }
+  cudaEventRecord(e2, st);
+#define M(WW)                                                                                                          \
+  if (RW == WW)                                                                                                        \
+    k_r2s_s1_post<WW><<<grid_for(n, 256, 32), 256, 0, st>>>(recs, n, NW, k, m, pv, out, need_mercy ? 1 : 0, d_mul_hist);
+  MHB_FOR_RW(M)
+#undef M
+  CK_LAUNCH();
+  CK(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  *t_sort_ms = ms;
+  cudaEventElapsedTime(&ms, e1, e2);
+  *t_kmsort_ms = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaEventDestroy(e2);
+  return MHB_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// main_read2sdbg (main_sdbg_build.cpp:88-156) from a host `.bin` image: SdBG item stream + bucket table out.
+// ------------------------------------------------------------------------------------------------
+extern "C" int mhb_read2sdbg_host(const mhb_build_args *args, mhb_build_result *res) {
+  if (!args || !res) return mhb_set_error(MHB_ERR_ARG, "null argument");
+  memset(res, 0, sizeof(*res));
+  const uint32_t k = args->k;
+  const int32_t m = args->m;
+  if (k < 9 || k > MHB_MAX_K || m < 1) return mhb_set_error(MHB_ERR_ARG, "read2sdbg: need 9 <= k <= 255 and m >= 1");
+  if (mhb_device_count() <= 0) return mhb_set_error(MHB_ERR_CUDA, "no CUDA device: libmhb has no CPU path");
+  cudaStream_t st = 0;
+  cudaEvent_t ev0, ev1;
+  cudaEventCreate(&ev0);
+  cudaEventCreate(&ev1);
+  cudaEventRecord(ev0, st);
+  PkgIndex ix;
+  CKR(index_pkg(args->bin, args->bin_words, args->n_reads, k, &ix));
+  const uint32_t W = s2s_record_words(k), WPT = words_per_tip_label(k);
+  res->words_per_tip_label = WPT;
+  res->n_edge_records = ix.n_edges;
+  res->bucket_table = (uint64_t *)calloc((size_t)MHB_NUM_BUCKETS * 4, 8);
+  res->counting = (int64_t *)calloc(65536, 8);
+  if (!res->bucket_table || !res->counting) return mhb_set_error(MHB_ERR_NOMEM, "host malloc failed");
+
+  // ---- the package: reversed reads on the device ----
+  DevBuf d_pkg, d_word_off, d_len, d_base_off, d_s1_off, d_edge_off;
+  PkgView pv;
+  memset(&pv, 0, sizeof(pv));
+  pv.n_reads = ix.n_reads;
+  pv.fixed_len = ix.fixed_len;
+  pv.fixed_words = ix.fixed_words;
+  CKR(d_pkg.alloc((size_t)ix.n_words * 4 + 64, "package"));
+  if (ix.n_reads) {
+    DevBuf d_bin, d_rec_off;
+    CKR(d_bin.alloc((size_t)args->bin_words * 4 + 64, ".bin image"));
+    CK(cudaMemcpyAsync(d_bin.p, args->bin, (size_t)args->bin_words * 4, cudaMemcpyHostToDevice, st));
+    if (!ix.fixed_len) {
+      CKR(upload(d_rec_off, ix.rec_off, "record offsets"));
+      CKR(upload(d_word_off, ix.word_off, "word offsets"));
+      CKR(upload(d_len, ix.len, "lengths"));
+      CKR(upload(d_base_off, ix.base_off, "base offsets"));
+      CKR(upload(d_s1_off, ix.s1_off, "stage-1 offsets"));
+      CKR(upload(d_edge_off, ix.edge_off, "edge offsets"));
+      pv.word_off = d_word_off.as<u64>();
+      pv.len = d_len.as<u32>();
+      pv.base_off = d_base_off.as<u64>();
+      pv.s1_off = d_s1_off.as<u64>();
+      pv.edge_off = d_edge_off.as<u64>();
+    }
+    if (ix.n_words) {
+      k_r2s_reverse<<<grid_for(ix.n_words, 256), 256, 0, st>>>(d_bin.as<u32>(), ix.n_reads, ix.fixed_len, d_rec_off.as<u64>(), pv,
+                                                                d_pkg.as<u32>(), ix.n_words);
+      CK_LAUNCH();
+    }
+    CK(cudaStreamSynchronize(st));  // d_bin / d_rec_off go out of scope
+  }
+  pv.words = d_pkg.as<u32>();
+
+  // ---- stage 1 (only when the threshold can reject anything, main_sdbg_build.cpp:141-147) ----
+  const uint64_t bit_words = ix.n_bases / 32 + 2;
+  DevBuf d_solid, d_planes, d_hist, d_cnt;
+  CKR(d_solid.alloc(bit_words * 4, "solid marker"));
+  CK(cudaMemsetAsync(d_solid.p, 0, bit_words * 4, st));
+  CKR(d_hist.alloc(65536 * 8, "multiplicity histogram"));
+  CK(cudaMemsetAsync(d_hist.p, 0, 65536 * 8, st));
+  CKR(d_cnt.alloc(64, "counters"));
+  CK(cudaMemsetAsync(d_cnt.p, 0, 64, st));
+  unsigned long long *d_counter = d_cnt.as<unsigned long long>();
+  const bool mercy = args->need_mercy && m > 1;
+  double t_sort = 0, t_km = 0;
+  if (m > 1 && ix.n_s1) {
+    S1Out so;
+    memset(&so, 0, sizeof(so));
+    so.is_solid = d_solid.as<u32>();
+    if (mercy) {
+      CKR(d_planes.alloc(bit_words * 4 * 4, "mercy candidate planes"));
+      CK(cudaMemsetAsync(d_planes.p, 0, bit_words * 4 * 4, st));
+      so.no_in = d_planes.as<u32>();
+      so.no_out = so.no_in + bit_words;
+      so.any = so.no_out + bit_words;
+    }
+    CKR(run_stage1(st, pv, ix, k, m, mercy, so, d_hist.as<unsigned long long>(), &t_sort, &t_km));
+    if (mercy) {  // Read2SdbgS2::Initialize, read_to_sdbg_s2.cpp:117-263
+      u32 *d_mercy = so.any + bit_words;
+      k_r2s_mercy<<<grid_for(ix.n_reads, 256), 256, 0, st>>>(pv, k, so, d_mercy, d_counter + 1);
+      CK_LAUNCH();
+      k_r2s_or_words<<<grid_for(bit_words, 256), 256, 0, st>>>(d_solid.as<u32>(), d_mercy, bit_words);
+      CK_LAUNCH();
+      unsigned long long nm = 0;
+      CK(cudaMemcpyAsync(&nm, d_counter + 1, 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      res->n_mercy = nm;
+    }
+    CK(cudaMemcpyAsync(res->counting, d_hist.p, 65536 * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    d_planes.release();
+  }
+  res->t_count_ms = t_sort;   // stable bucket partition of the stage-1 records
+  res->t_mercy_ms = t_km;     // kmsort emulation
+
+  // ---- stage 2 ----
+  uint64_t n_items = 0;
+  if (ix.n_edges) {
+    CK(cudaMemsetAsync(d_counter, 0, 8, st));
+#define M(WW)                                                                                                          \
+  if (W == WW)                                                                                                         \
+    k_r2s_s2_extract<WW, false><<<grid_for(ix.n_edges, 256), 256, 0, st>>>(pv, k, d_solid.as<u32>(), m == 1, ix.n_edges, \
+                                                                          nullptr, d_counter, 0);
+    MHB_FOR_WR(M)
+#undef M
+    CK_LAUNCH();
+    unsigned long long c = 0;
+    CK(cudaMemcpyAsync(&c, d_counter, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    n_items = c;
+  }
+  res->n_sort_items = n_items;
+  DevBuf d_table, d_totals;
+  CKR(d_table.alloc((size_t)MHB_NUM_BUCKETS * 32, "bucket table"));
+  CKR(d_totals.alloc(16 * 8, "totals"));
+  if (n_items == 0) {
+    res->bytes = args->sdbg_out ? args->sdbg_out : (uint8_t *)malloc(1);
+  } else {
+    DevBuf a, b, ws, heads, tile_heads, tile_off, bsum, scr, d_bytes;
+    const size_t rec_bytes = (size_t)n_items * W * 4 + 16, ws_bytes = mhb_sort_workspace_bytes(n_items, W);
+    CKR(a.alloc(rec_bytes, "stage-2 items"));
+    CKR(b.alloc(rec_bytes, "stage-2 items (sort buffer)"));
+    CKR(ws.alloc(ws_bytes, "sort workspace"));
+    CK(cudaMemsetAsync(d_counter, 0, 8, st));
+#define M(WW)                                                                                                          \
+  if (W == WW)                                                                                                         \
+    k_r2s_s2_extract<WW, true><<<grid_for(ix.n_edges, 256), 256, 0, st>>>(pv, k, d_solid.as<u32>(), m == 1, ix.n_edges,  \
+                                                                         a.as<u32>(), d_counter, n_items);
+    MHB_FOR_WR(M)
+#undef M
+    CK_LAUNCH();
+    uint8_t sbytes[80];
+    const uint32_t n_sb = mhb_s2s_sort_bytes(k, sbytes);
+    int in_b = 0;
+    CKR(mhb_sort_records_relaxed(st, a.as<u32>(), b.as<u32>(), n_items, W, sbytes, n_sb, nullptr, ws.p, ws_bytes, &in_b));
+    const u32 *sorted = in_b ? b.as<u32>() : a.as<u32>();
+    u32 *uniq = in_b ? a.as<u32>() : b.as<u32>();
+    // equal items -> one item carrying the run length (read_to_sdbg_s2.cpp:560-572)
+    const uint64_t n_tiles = (n_items + kDdTile - 1) / kDdTile;
+    CKR(tile_heads.alloc(n_tiles * 4, "tile counts"));
+    CKR(tile_off.alloc(n_tiles * 8, "tile offsets"));
+    CKR(bsum.alloc((n_tiles / 4096 + 4) * 8, "scan sums"));
+#define M(WW) \
+  if (W == WW) k_r2s_dd_count<WW><<<(unsigned)n_tiles, kDdThreads, 0, st>>>(sorted, n_items, tile_heads.as<u32>());
+    MHB_FOR_WR(M)
+#undef M
+    CK_LAUNCH();
+    CKR(scan32(st, tile_heads.as<u32>(), n_tiles, tile_off.as<u64>(), (uint64_t *)(d_counter + 2), bsum.as<u64>()));
+    unsigned long long n_u = 0;
+    CK(cudaMemcpyAsync(&n_u, d_counter + 2, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CKR(heads.alloc((size_t)n_u * 8, "run heads"));
+#define M(WW) \
+  if (W == WW) k_r2s_dd_heads<WW><<<(unsigned)n_tiles, kDdThreads, 0, st>>>(sorted, n_items, tile_off.as<u64>(), heads.as<u64>());
+    MHB_FOR_WR(M)
+#undef M
+    CK_LAUNCH();
+#define M(WW) \
+  if (W == WW) k_r2s_dd_build<WW><<<grid_for(n_u, 256), 256, 0, st>>>(sorted, n_items, heads.as<u64>(), n_u, uniq);
+    MHB_FOR_WR(M)
+#undef M
+    CK_LAUNCH();
+    const size_t scr_bytes = mhb_s2s_emit_scratch_bytes(n_u, k);
+    const uint64_t cap_bytes = (uint64_t)n_u * (4ull + 4ull * WPT) + 16;
+    CKR(scr.alloc(scr_bytes, "emit scratch"));
+    CKR(d_bytes.alloc(cap_bytes, "SdBG stream"));
+    CKR(mhb_s2s_emit_fmt(st, uniq, n_u, k, d_bytes.as<uint8_t>(), cap_bytes, d_table.as<u64>(), d_totals.as<u64>(), scr.p,
+                         scr_bytes, 1));
+    uint64_t totals[16];
+    CK(cudaMemcpyAsync(totals, d_totals.p, sizeof(totals), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    res->n_bytes = totals[0];
+    res->n_items = totals[1];
+    res->n_tips = totals[2];
+    res->n_large_mul = totals[3];
+    for (int i = 0; i < 9; ++i) res->w_count[i] = totals[4 + i];
+    res->ones_in_last = totals[13];
+    if (res->n_bytes > cap_bytes) return mhb_set_error(MHB_ERR_NOMEM, "internal: SdBG byte stream exceeds capacity");
+    if (args->sdbg_out && args->sdbg_out_capacity >= res->n_bytes) res->bytes = args->sdbg_out;
+    else res->bytes = (uint8_t *)malloc(std::max<size_t>(1, res->n_bytes));
+    if (!res->bytes) return mhb_set_error(MHB_ERR_NOMEM, "host malloc failed");
+    CK(cudaMemcpyAsync(res->bucket_table, d_table.p, (size_t)MHB_NUM_BUCKETS * 32, cudaMemcpyDeviceToHost, st));
+    if (res->n_bytes) CK(cudaMemcpyAsync(res->bytes, d_bytes.p, res->n_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    res->n_solid = n_u;  // distinct stage-2 items
+  }
+  cudaEventRecord(ev1, st);
+  cudaEventSynchronize(ev1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ev0, ev1);
+  res->t_total_ms = ms;
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  return MHB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Self-test hooks (host): the same __host__ __device__ code the kernels run, for the CPU-only tests (tests/test_r2s_cpu.py).
+// ------------------------------------------------------------------------------------------------
+extern "C" int mhb_selftest_r2s_s1_record(const uint32_t *pkg_words, uint32_t nwords, uint32_t L, uint32_t k, uint32_t e,
+                                          uint64_t base_off, uint32_t *rec_out) {
+  if (k < 9 || k > MHB_MAX_K || L < k + 1 || e >= L - k + 4) return mhb_set_error(MHB_ERR_ARG, "bad args");
+  const uint32_t NW = r2s_s1_key_words(k);
+  u32 p, want;
+  s1_emission(L, k, e, p, want);
+#define M(WW)                                                       \
+  if (NW == WW) {                                                   \
+    u32 rec[WW + 2];                                                \
+    make_s1_record<WW>(pkg_words, nwords, L, k, p, want, base_off, rec); \
+    memcpy(rec_out, rec, sizeof(rec));                              \
+  }
+  MHB_FOR_W(M)
+#undef M
+  return MHB_OK;
+}
+
+extern "C" int mhb_selftest_r2s_item(const uint32_t *pkg_words, uint32_t nwords, uint32_t L, uint32_t k, uint32_t i,
+                                     uint32_t strand, uint32_t type, uint32_t *rec_out, uint32_t *palindrome_out) {
+  if (k < 9 || k > MHB_MAX_K || i + k >= L || strand > 1 || type > 2) return mhb_set_error(MHB_ERR_ARG, "bad args");
+  const uint32_t W = s2s_record_words(k);
+#define M(WW)                                                              \
+  if (W == WW) {                                                           \
+    u32 rec[WW];                                                           \
+    make_r2s_item<WW>(pkg_words, nwords, k, i, strand, type, rec);         \
+    memcpy(rec_out, rec, sizeof(rec));                                     \
+    *palindrome_out = edge_is_palindrome<WW>(pkg_words, nwords, k, i) ? 1u : 0u; \
+  }
+  MHB_FOR_WR(M)
+#undef M
+  return MHB_OK;
+}
+
+// kmsort emulation of ONE bucket on the host, level by level exactly as the kernels do it (records of nw + 2 words)
+extern "C" int mhb_selftest_kmsort(uint32_t *recs, uint64_t n, uint32_t nw) {
+  const uint32_t RW = nw + 2;
+  if (nw < 1 || RW > 17 || n >= (1ull << 32)) return mhb_set_error(MHB_ERR_ARG, "bad args");
+  if (n <= 1) return MHB_OK;
+  std::vector<KmSeg> cur, nxt;
+  std::vector<u32> count(256), last(256);
+  int kb = 4 * (int)nw - 2 - 1;
+#define M(WW)                                                                                           \
+  if (RW == WW) {                                                                                       \
+    if (n <= (uint64_t)kKmInsertThreshold) {                                                            \
+      km_insertion<WW>(recs, (u32)n, nw);                                                               \
+      return MHB_OK;                                                                                    \
+    }                                                                                                   \
+    cur.push_back(KmSeg{0, n});                                                                         \
+    for (;;) {                                                                                          \
+      nxt.clear();                                                                                      \
+      for (const KmSeg &s : cur) {                                                                      \
+        u32 *a = recs + s.start * WW;                                                                   \
+        km_radix_range<WW>(a, (u32)s.len, nw, kb, count.data(), last.data());                           \
+        u32 b0 = 0;                                                                                     \
+        for (int i = 0; i < 256 && kb > 0; ++i) {                                                       \
+          const u32 c = count[i];                                                                       \
+          if (c > (u32)kKmInsertThreshold) nxt.push_back(KmSeg{s.start + b0, c});                       \
+          else if (c > 1) km_insertion<WW>(a + (u64)b0 * WW, c, nw);                                    \
+          b0 += c;                                                                                      \
+        }                                                                                               \
+      }                                                                                                 \
+      if (nxt.empty() || kb == 0) break;                                                                \
+      cur.swap(nxt);                                                                                    \
+      --kb;                                                                                             \
+    }                                                                                                   \
+  }
+  MHB_FOR_RW(M)
+#undef M
+  return MHB_OK;
+}
+
+// stage-1 Lv2Postprocess + the mercy step on host arrays (one sorted bucket / one read), same code as the kernels
+extern "C" int mhb_selftest_r2s_s1_group(const uint32_t *recs, uint64_t n, uint32_t k, int32_t m, uint32_t fixed_len,
+                                         uint64_t n_reads, int need_mercy, uint32_t *is_solid, uint32_t *no_in,
+                                         uint32_t *no_out, uint32_t *any, int64_t *counting) {
+  const uint32_t nw = r2s_s1_key_words(k), rw = nw + 2;
+  PkgView pv;
+  memset(&pv, 0, sizeof(pv));
+  pv.fixed_len = fixed_len;
+  pv.n_reads = n_reads;
+  S1Out o{is_solid, no_in, no_out, any};
+  for (u64 g = 0; g < n;) {
+    u32 hv[16], nh;
+    g = s1_group(recs, n, g, rw, nw, k, m, pv, o, need_mercy != 0, hv, nh);
+    for (u32 q = 0; q < nh; ++q) counting[hv[q] > MHB_MAX_MUL ? MHB_MAX_MUL : hv[q]]++;
+  }
+  return MHB_OK;
+}
+
+extern "C" int mhb_selftest_r2s_mercy_read(uint32_t fixed_len, uint64_t n_reads, uint64_t r, uint32_t k,
+                                           const uint32_t *is_solid, const uint32_t *no_in, const uint32_t *no_out,
+                                           const uint32_t *any, uint32_t *mercy, uint32_t *added_out) {
+  PkgView pv;
+  memset(&pv, 0, sizeof(pv));
+  pv.fixed_len = fixed_len;
+  pv.n_reads = n_reads;
+  S1Out o{const_cast<u32 *>(is_solid), const_cast<u32 *>(no_in), const_cast<u32 *>(no_out), const_cast<u32 *>(any)};
+  *added_out = r2s_mercy_read(pv, r, k, o, mercy);
+  return MHB_OK;
+}

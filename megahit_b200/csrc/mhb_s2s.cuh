@@ -214,6 +214,16 @@ __device__ __forceinline__ bool diff_km1(const u32 (&x)[W], const u32 (&y)[W], u
   return diff;
 }
 
+// Tip-label word q of a read2sdbg item (label_fmt = 1).  The items travel in the seq2sdbg layout (flags in the low 20
+// bits of word W-1); the reference's stage-2 record (read_to_sdbg_s2.cpp:483-485, W1 = ceil((2k+4)/32) words) keeps
+// nondollar<<3 | prev in the low 4 bits of word W1-1, and its tip label is the first ceil(k/16) raw words of THAT
+// record (:602-606).  A tip has nondollar = 0, so the 4 flag bits are b.
+__device__ __forceinline__ u32 r2s_label_word(u32 lw, u32 q, u32 W, u32 k, u32 b) {
+  if (q == W - 1) lw &= 0xFFF00000u;
+  if (q == div_ceil(2 * k + 4, 32) - 1) lw |= b;
+  return lw;
+}
+
 struct EmitAcc {
   u32 bytes, items, tips, large;
 };
@@ -222,7 +232,7 @@ struct EmitAcc {
 // sizes (WRITE=false) or writes (WRITE=true) its SdBG items (sdbg_writer.cpp:25-58).
 template <int W, bool WRITE>
 __device__ __forceinline__ void s2s_group(const u32 *__restrict__ recs, u64 n, u64 i, u32 k, EmitAcc &acc,
-                                          uint8_t *out, u32 *w_count, u32 &ones) {
+                                          uint8_t *out, u32 *w_count, u32 &ones, u32 fmt = 0) {
   const u32 WPT = words_per_tip_label(k);
   u32 r0[W], x[W];
   ld_rec<W>(recs, i, r0);
@@ -277,7 +287,8 @@ __device__ __forceinline__ void s2s_group(const u32 *__restrict__ recs, u64 n, u
         if (tip) {
           for (u32 q = 0; q < WPT; ++q) {
             u32 lw = pick<W>(cur, q);
-            if (q == (u32)W - 1) lw = (lw & 0xFFFF0000u) | best;  // label = raw words of the run's first sorted record
+            if (fmt) lw = r2s_label_word(lw, q, (u32)W, k, b);
+            else if (q == (u32)W - 1) lw = (lw & 0xFFFF0000u) | best;  // label = raw words of the run's first sorted record
             o[p++] = (uint16_t)(lw & 0xFFFFu);
             o[p++] = (uint16_t)(lw >> 16);
           }
@@ -336,7 +347,7 @@ template <int W>
 __global__ void __launch_bounds__(kEmitThreads)
     k_s2s_write(const u32 *__restrict__ recs, u64 n, u32 k, const u64 *btot /*scanned, 4 planes*/,
                 uint8_t *__restrict__ bytes_out, u64 capacity, u64 *bucket_start /*65536*4, init ~0*/,
-                u64 *totals /*16*/) {
+                u64 *totals /*16*/, u32 fmt) {
   __shared__ u32 s_scan[kEmitThreads / 32 + 1];
   __shared__ u32 s_w[9];
   if (threadIdx.x < 9) s_w[threadIdx.x] = 0;
@@ -381,7 +392,7 @@ __global__ void __launch_bounds__(kEmitThreads)
     }
     if (byte_off + acc.bytes <= capacity) {
       EmitAcc wacc = {0, 0, 0, 0};
-      s2s_group<W, true>(recs, n, i, k, wacc, bytes_out + byte_off, s_w, ones);
+      s2s_group<W, true>(recs, n, i, k, wacc, bytes_out + byte_off, s_w, ones, fmt);
     }
   }
   for (int d = 16; d; d >>= 1) ones += __shfl_xor_sync(0xffffffffu, ones, d);
@@ -473,7 +484,7 @@ struct StagedRecs {
 // walk the group starting at record i; returns its end.  WRITE: append item bytes at out + acc.bytes.
 template <int W, bool WRITE>
 __device__ __forceinline__ u64 s2s_group2(const StagedRecs<W> &sr, u64 n, u64 i, u32 k, EmitAcc &acc, uint8_t *out,
-                                          u32 *w_count, u32 &ones) {
+                                          u32 *w_count, u32 &ones, u32 fmt) {
   const u32 WPT = words_per_tip_label(k);
   u32 r0[W], x[W];
   sr.get(i, r0);
@@ -526,7 +537,8 @@ __device__ __forceinline__ u64 s2s_group2(const StagedRecs<W> &sr, u64 n, u64 i,
         if (tip) {
           for (u32 q = 0; q < WPT; ++q) {
             u32 lw = pick<W>(cur, q);
-            if (q == (u32)W - 1) lw = (lw & 0xFFFF0000u) | best;
+            if (fmt) lw = r2s_label_word(lw, q, (u32)W, k, b);
+            else if (q == (u32)W - 1) lw = (lw & 0xFFFF0000u) | best;  // label = raw words of the run's first sorted record
             o[p++] = (uint16_t)(lw & 0xFFFFu);
             o[p++] = (uint16_t)(lw >> 16);
           }
@@ -552,7 +564,7 @@ template <int W>
 __global__ void __launch_bounds__(kEmit2Warps * 32)
     k_s2s_judge(const u32 *__restrict__ recs, u64 n, u32 k, u32 n_chunks, uint8_t *__restrict__ tmp,
                 u32 *__restrict__ chunk_tot /*4 planes of n_chunks*/, u32 *__restrict__ bucket_local /*65536 x 5*/,
-                u64 *totals) {
+                u64 *totals, u32 fmt) {
   constexpr int IPL = emit2_ipl(W), CH = emit2_chunk(W);
   extern __shared__ __align__(16) u32 smem_e[];
   __shared__ u32 s_w[9];
@@ -599,7 +611,7 @@ __global__ void __launch_bounds__(kEmit2Warps * 32)
     // walk 1: sizes
     EmitAcc acc = {0, 0, 0, 0};
     u32 dummy = 0;
-    for (u64 t = first; t < hi_l;) t = s2s_group2<W, false>(sr, n, t, k, acc, nullptr, nullptr, dummy);
+    for (u64 t = first; t < hi_l;) t = s2s_group2<W, false>(sr, n, t, k, acc, nullptr, nullptr, dummy, fmt);
     // lane prefixes + chunk totals
     u32 inc[4] = {acc.bytes, acc.items, acc.tips, acc.large};
 #pragma unroll
@@ -635,7 +647,7 @@ __global__ void __launch_bounds__(kEmit2Warps * 32)
         bl[3] = pre[2] + wacc.tips;
         bl[4] = pre[3] + wacc.large;
       }
-      t = s2s_group2<W, true>(sr, n, t, k, wacc, out, s_w, ones);
+      t = s2s_group2<W, true>(sr, n, t, k, wacc, out, s_w, ones, fmt);
     }
   }
   for (int d = 16; d; d >>= 1) ones += __shfl_xor_sync(0xffffffffu, ones, d);

@@ -97,6 +97,12 @@ class Seq2SdbgOpts(C.Structure):
                 ("need_mercy", C.c_int32), ("mem_flag", C.c_int32)]
 
 
+class Read2SdbgOpts(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("m", C.c_int32), ("host_mem", C.c_double), ("num_cpu_threads", C.c_int32),
+                ("read_lib_file", C.c_char_p), ("output_prefix", C.c_char_p), ("mem_flag", C.c_int32),
+                ("need_mercy", C.c_int32)]
+
+
 # every symbol include/mhb.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
     "mhb_last_error", "mhb_version", "mhb_device_count", "mhb_launch_count", "mhb_count_record_words", "mhb_words_per_edge",
@@ -107,6 +113,8 @@ SYMBOLS = [
     "mhb_s2s_emit_scratch_bytes", "mhb_s2s_emit", "mhb_set_device", "mhb_count_host", "mhb_s2s_host", "mhb_build_host", "mhb_free",
     "mhb_mercy_candidates_scratch_bytes", "mhb_mercy_candidates", "mhb_mercy_edges_scratch_bytes", "mhb_mercy_edges", "mhb_mercy_edges_count", "mhb_mercy_edges_write", "mhb_mercy_edges_segs", "mhb_mercy_host", "mhb_mercy_planes_words", "mhb_mercy_probe_owned", "mhb_mercy_count_planes", "mhb_edge_lut_bytes", "mhb_edge_lut_build",
     "mhb_release", "mhb_count_run", "mhb_count_run_multi", "mhb_seq2sdbg_run", "mhb_selftest_count_record", "mhb_selftest_count_records_roll", "mhb_selftest_s2s_record",
+    "mhb_s2s_emit_fmt", "mhb_read2sdbg_host", "mhb_read2sdbg_run", "mhb_selftest_r2s_s1_record", "mhb_selftest_r2s_item",
+    "mhb_selftest_kmsort", "mhb_selftest_r2s_s1_group", "mhb_selftest_r2s_mercy_read",
 ]
 
 
@@ -203,6 +211,17 @@ def load():
                                                   C.c_void_p]
     L.mhb_selftest_s2s_record.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_uint32, C.c_void_p]
+    L.mhb_s2s_emit_fmt.argtypes = L.mhb_s2s_emit.argtypes + [C.c_int]
+    L.mhb_read2sdbg_host.argtypes = [C.POINTER(BuildArgs), C.POINTER(BuildResult)]
+    L.mhb_read2sdbg_run.argtypes = [C.POINTER(Read2SdbgOpts)]
+    L.mhb_selftest_r2s_s1_record.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]
+    L.mhb_selftest_r2s_item.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                        C.c_void_p, C.POINTER(C.c_uint32)]
+    L.mhb_selftest_kmsort.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
+    L.mhb_selftest_r2s_s1_group.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.c_uint32, C.c_uint64, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mhb_selftest_r2s_mercy_read.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
     _lib = L
     return L
 
@@ -402,6 +421,30 @@ def build_host(bin_words: np.ndarray, n_reads: int, k: int, m: int, need_mercy: 
     return out
 
 
+def read2sdbg_host(bin_words: np.ndarray, n_reads: int, k: int, m: int, need_mercy: bool = True) -> dict:
+    """The 1-pass build (`megahit_core read2sdbg`, main_sdbg_build.cpp:88-156): `.bin` image in, SdBG item stream out,
+    plus what stage 1 writes to P.counting."""
+    L = load()
+    bin_words = np.ascontiguousarray(bin_words, dtype=np.uint32).reshape(-1)
+    a = BuildArgs(k, m, bin_words.ctypes.data if len(bin_words) else None, len(bin_words), n_reads, int(need_mercy), 0, None, 0)
+    r = BuildResult()
+    _check(L.mhb_read2sdbg_host(C.byref(a), C.byref(r)))
+    out = {
+        "n_edge_records": r.n_edge_records, "n_distinct_items": r.n_solid, "n_mercy": r.n_mercy,
+        "n_sort_items": r.n_sort_items, "n_items": r.n_items, "n_tips": r.n_tips, "n_large_mul": r.n_large_mul,
+        "n_bytes": r.n_bytes, "words_per_tip_label": r.words_per_tip_label,
+        "bucket_table": np.ctypeslib.as_array(r.bucket_table, (NUM_BUCKETS * 4,)).reshape(NUM_BUCKETS, 4).copy(),
+        "w_count": np.array(r.w_count, np.uint64), "ones_in_last": r.ones_in_last,
+        "counting": np.ctypeslib.as_array(r.counting, (65536,)).copy(),
+        "bytes": bytes(np.ctypeslib.as_array(r.bytes, (max(r.n_bytes, 1),))[: r.n_bytes]),
+        "ms": {"total": r.t_total_ms, "bucket_partition": r.t_count_ms, "kmsort": r.t_mercy_ms},
+    }
+    L.mhb_free(r.bytes)
+    L.mhb_free(r.bucket_table)
+    L.mhb_free(r.counting)
+    return out
+
+
 def sdbg_stream_from_table(table: np.ndarray, data: bytes) -> bytes:
     """Canonical SdBG stream (formats.canonical_sdbg) from the {offset, items, tips, large} table."""
     chunks = []
@@ -432,6 +475,13 @@ def seq2sdbg_run(output_prefix: str, k: int, k_from: int = 0, input_prefix: str 
     _check(load().mhb_seq2sdbg_run(C.byref(o)))
 
 
+def read2sdbg_run(read_lib_file: str, output_prefix: str, k: int = 21, m: int = 2, need_mercy: bool = False,
+                  host_mem: float = 1e9, num_cpu_threads: int = 0, mem_flag: int = 1) -> None:
+    o = Read2SdbgOpts(k, m, host_mem, num_cpu_threads, read_lib_file.encode(), output_prefix.encode(), mem_flag,
+                      int(need_mercy))
+    _check(load().mhb_read2sdbg_run(C.byref(o)))
+
+
 # ------------------------------------------------------------------------------------------------
 # self-test hooks (host, one record at a time)
 # ------------------------------------------------------------------------------------------------
@@ -460,3 +510,31 @@ def selftest_s2s_record(seq_words: np.ndarray, L_: int, k: int, strand: int, off
     _check(load().mhb_selftest_s2s_record(seq_words.ctypes.data, len(seq_words), L_, k, strand, offset, mult,
                                           rec.ctypes.data))
     return rec
+
+
+def r2s_s1_key_words(k: int) -> int:
+    return (2 * (k - 1) + 6 + 31) // 32
+
+
+def selftest_r2s_s1_record(pkg_words: np.ndarray, L_: int, k: int, e: int, base_off: int = 0):
+    """stage-1 record number e (bucket input order) of a package-orientation read: key words + 2 payload words"""
+    pkg_words = np.ascontiguousarray(pkg_words, np.uint32)
+    rec = np.zeros(r2s_s1_key_words(k) + 2, np.uint32)
+    _check(load().mhb_selftest_r2s_s1_record(pkg_words.ctypes.data, len(pkg_words), L_, k, e, base_off, rec.ctypes.data))
+    return rec
+
+
+def selftest_r2s_item(pkg_words: np.ndarray, L_: int, k: int, i: int, strand: int, type_: int):
+    pkg_words = np.ascontiguousarray(pkg_words, np.uint32)
+    rec = np.zeros(s2s_record_words(k), np.uint32)
+    pal = C.c_uint32()
+    _check(load().mhb_selftest_r2s_item(pkg_words.ctypes.data, len(pkg_words), L_, k, i, strand, type_, rec.ctypes.data,
+                                        C.byref(pal)))
+    return rec, pal.value
+
+
+def selftest_kmsort(recs: np.ndarray, nw: int) -> np.ndarray:
+    """kmlib::kmsort's permutation of one bucket (records of nw + 2 words), emulated level by level as on the device"""
+    recs = np.ascontiguousarray(recs, np.uint32).copy()
+    _check(load().mhb_selftest_kmsort(recs.ctypes.data, len(recs), nw))
+    return recs

@@ -87,6 +87,12 @@ int mhbo_unpack_bin(const uint8_t *bin, uint64_t bin_bytes, int reverse, uint64_
 int mhbo_read2sdbg(const mhbo_seqs *reads, uint32_t k, int32_t m, int need_mercy, mhbo_sdbg_out *out, int64_t *counting,
                    uint64_t *n_mercy_out, uint8_t **is_solid_out, uint64_t *n_bases_out);
 
+/* pieces of the read2sdbg restatement, exported so that the CPU tests can check the device code's __host__ __device__
+ * building blocks one by one */
+unsigned mhbo_s1_read_records(const uint32_t *w, unsigned L, unsigned k, uint64_t base_off, uint32_t *out);
+void mhbo_kmsort(uint32_t *recs, int64_t n, unsigned nw, unsigned rw);
+void mhbo_s2_record(const uint32_t *w, unsigned k, unsigned i, unsigned strand, unsigned type, uint32_t *rec, int *palindrome);
+
 void mhbo_free(void *p);
 
 #ifdef __cplusplus

@@ -171,6 +171,43 @@ static void s1_record(const uint32_t *w, unsigned L, unsigned k, unsigned p, uns
   rec[nw + 1] = (uint32_t)info;
 }
 
+/* The stage-1 records of one read in the order the reference appends them to their buckets (Lv1FillOffsets
+ * :207-293: first (k-1)-mer on both strands, inner ones on the canonical strand, last one on both strands).
+ * out: (L - k + 4) records of ceil((2(k-1)+6)/32) + 2 words.  Returns their number (0 for L < k + 1). */
+unsigned mhbo_s1_read_records(const uint32_t *w, unsigned L, unsigned k, uint64_t base_off, uint32_t *out) {
+  const unsigned kk = k - 1, nw = div_ceil_u(2 * kk + 6, 32), rw = nw + 2;
+  unsigned n = 0;
+  if (L < k + 1) return 0;
+  for (unsigned p = 0; p + kk <= L; ++p) {
+    unsigned strands[2], ns = 0;
+    if (p == 0 || p + kk == L) { /* :239-245, :286-292 */
+      strands[ns++] = 0;
+      strands[ns++] = 1;
+    } else {
+      const int c = cmp_fwd_rc(w, p, kk);
+      if (c > 0) {
+        strands[ns++] = 1;
+      } else if (c < 0) {
+        strands[ns++] = 0;
+      } else { /* palindrome :263-279 */
+        const unsigned prev = sbase(w, p - 1), next = sbase(w, p + kk);
+        strands[ns++] = prev <= 3u - next ? 0 : 1;
+      }
+    }
+    for (unsigned s = 0; s < ns; ++s) s1_record(w, L, k, p, strands[s], ((base_off + p) << 1) | strands[s], nw, out + (size_t)(n++) * rw);
+  }
+  return n;
+}
+
+/* kmlib::kmsort on n records of rw words keyed on their first nw words (exported for the CPU tests of the device code) */
+void mhbo_kmsort(uint32_t *recs, int64_t n, unsigned nw, unsigned rw) {
+  const recfmt f = {nw, rw};
+  kms_sort(recs, n, &f);
+}
+
+/* stage-2 item in the reference's own layout (ceil((2k+4)/32) words) + whether the edge at i is a palindrome */
+void mhbo_s2_record(const uint32_t *w, unsigned k, unsigned i, unsigned strand, unsigned type, uint32_t *rec, int *palindrome);
+
 /* IsDiffKMinusOneMer (read_to_sdbg_s1.cpp:40-63) */
 static int diff_km1(const uint32_t *x, const uint32_t *y, unsigned k) {
   for (unsigned i = 0; i + 1 < k; ++i) {
@@ -280,7 +317,8 @@ static int stage1(const mhbo_seqs *reads, unsigned k, int m, const uint64_t *bas
   const unsigned kk = k - 1, nw = div_ceil_u(2 * kk + 6, 32), rw = nw + 2;
   uint64_t *bsize = (uint64_t *)calloc(MHBO_NUM_BUCKETS + 1, 8);
   if (!bsize) return -2;
-  uint32_t tmp[64 + 2];
+  uint32_t *read_recs = NULL;
+  unsigned read_cap = 0;
   uint32_t *recs = NULL;
   /* two sweeps in global read order: bucket sizes (Lv0CalcBucketSize :137-205), then the records in place
    * (Lv1FillOffsets :207-293 + Lv2ExtractSubString): a bucket holds its records in read order */
@@ -304,34 +342,27 @@ static int stage1(const mhbo_seqs *reads, unsigned k, int m, const uint64_t *bas
       const unsigned L = reads->len[r];
       if (L < k + 1) continue;
       const uint32_t *w = reads->words + reads->word_off[r];
-      for (unsigned p = 0; p + kk <= L; ++p) {
-        unsigned strands[2], ns = 0;
-        if (p == 0 || p + kk == L) { /* first and last (k-1)-mer: both strands (:239-245, :286-292) */
-          strands[ns++] = 0;
-          strands[ns++] = 1;
-        } else {
-          const int c = cmp_fwd_rc(w, p, kk);
-          if (c > 0) {
-            strands[ns++] = 1;
-          } else if (c < 0) {
-            strands[ns++] = 0;
-          } else { /* palindrome :263-279 */
-            const unsigned prev = sbase(w, p - 1), next = sbase(w, p + kk);
-            strands[ns++] = prev <= 3u - next ? 0 : 1;
-          }
+      if (L - k + 4 > read_cap) {
+        read_cap = 2 * (L - k + 4);
+        read_recs = (uint32_t *)realloc(read_recs, (size_t)read_cap * rw * 4);
+        if (!read_recs) {
+          rc = -2;
+          break;
         }
-        for (unsigned s = 0; s < ns; ++s) {
-          s1_record(w, L, k, p, strands[s], ((base_off[r] + p) << 1) | strands[s], nw, tmp);
-          const unsigned bucket = tmp[0] >> 16;
-          if (sweep == 0) {
-            bsize[bucket]++;
-          } else {
-            memcpy(recs + cursor[bucket]++ * rw, tmp, 4 * rw);
-          }
+      }
+      const unsigned ne = mhbo_s1_read_records(w, L, k, base_off[r], read_recs);
+      for (unsigned e = 0; e < ne; ++e) {
+        const uint32_t *t = read_recs + (size_t)e * rw;
+        const unsigned bucket = t[0] >> 16;
+        if (sweep == 0) {
+          bsize[bucket]++;
+        } else {
+          memcpy(recs + cursor[bucket]++ * rw, t, 4 * rw);
         }
       }
     }
   }
+  free(read_recs);
   if (rc == 0) {
     const recfmt f = {nw, rw};
     for (unsigned b = 0; b < MHBO_NUM_BUCKETS && rc == 0; ++b) {
@@ -423,6 +454,13 @@ static void s2_record(const uint32_t *w, unsigned k, unsigned i, unsigned strand
   }
   rec[W - 1] |= (uint32_t)(nc == k) << 3;
   rec[W - 1] |= prev;
+}
+
+void mhbo_s2_record(const uint32_t *w, unsigned k, unsigned i, unsigned strand, unsigned type, uint32_t *rec, int *palindrome) {
+  s2_record(w, k, i, strand, type, div_ceil_u(2 * k + 4, 32), rec);
+  int pal = 1;
+  for (unsigned j = 0; j <= k && pal; ++j) pal = sbase(w, i + j) == 3u - sbase(w, i + k - j);
+  *palindrome = pal;
 }
 
 static int cmp_words_r(const void *a, const void *b, void *arg) {
