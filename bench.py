@@ -242,7 +242,7 @@ def ours(args):
             e = torch.cuda.Event(enable_timing=True)
             e.record()
             mercy_ev.append(e)
-        s2s.run(plan.edges, None, ns + nm, plan.WE, timed=timed)
+        s2s.run(plan.edges, None, ns + nm, plan.WE, timed=timed, aux=plan.aux, n_aux=ns)
         return ns
 
     for _ in range(max(0, args.warmup - 1)):

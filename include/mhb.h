@@ -280,6 +280,17 @@ typedef struct {
 int mhb_s2s_extract(void *stream, const mhb_dev_seqs *seqs, uint32_t k, uint32_t *records, uint64_t n_items,
                     uint64_t *hist256, int hist_byte);
 
+/* A8/A9 for `.edges` records that still carry the count stage's flags (aux[e] bit0 = no incoming, bit1 = no outgoing,
+ * as mhb_count_solid writes them; edges n_with_aux .. n_edges-1, e.g. mercy edges appended behind the solid ones, have
+ * none): the offset-0 / offset-2 ("$") items that SeqToSdbg::Lv2Postprocess is certain to discard (seq_to_sdbg.cpp:
+ * 760-776: a solid edge enters / leaves the node - which is what has_in / has_out of kmer_counter.cpp:297-305 prove)
+ * are not generated, so the sort and the emitter see about a third of the 6 * n_edges items and produce the same bytes.
+ * Items are appended at records[*cursor_dev ...) (device uint64, caller-zeroed; ends at the item count, items beyond
+ * `capacity` are not stored) in no particular order; hist256 += histogram of record byte hist_byte. */
+int mhb_s2s_extract_edges_pruned(void *stream, const uint32_t *edges, const uint8_t *aux, uint64_t n_edges,
+                                 uint64_t n_with_aux, uint32_t k, uint32_t *records, uint64_t capacity,
+                                 uint64_t *cursor_dev, uint64_t *hist256, int hist_byte);
+
 /* A13 for seq2sdbg (base_engine.cpp:254-281): the sort items whose 16-bit bucket id (first eight bases) lies in
  * [lo, hi].  records == NULL: count only - hist256 (caller-zeroed) += histogram of record byte hist_byte over the
  * in-range items.  Otherwise the in-range records are appended (in no particular order) at records[*cursor_dev ...);

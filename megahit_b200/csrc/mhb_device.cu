@@ -423,6 +423,26 @@ extern "C" int mhb_s2s_extract(void *stream, const mhb_dev_seqs *seqs, uint32_t 
   return MHB_OK;
 }
 
+extern "C" int mhb_s2s_extract_edges_pruned(void *stream, const uint32_t *edges, const uint8_t *aux, uint64_t n_edges,
+                                            uint64_t n_with_aux, uint32_t k, uint32_t *records, uint64_t capacity,
+                                            uint64_t *cursor_dev, uint64_t *hist256, int hist_byte) {
+  if (!edges || (!aux && n_with_aux) || !records || !cursor_dev || k < 9 || k > MHB_MAX_K || n_with_aux > n_edges)
+    return mhb_set_error(MHB_ERR_ARG, "bad args");
+  if (n_edges == 0) return MHB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const u32 W = s2s_record_words(k), WE = words_per_edge(k);
+  u64 g = (n_edges + 255) / 256;
+  if (g > (u64)sm_count() * 32) g = (u64)sm_count() * 32;
+#define M(WW)                                                                                                        \
+  if (W == WW)                                                                                                       \
+    k_s2s_extract_edges_pruned<WW><<<(unsigned)g, 256, 0, st>>>(edges, aux, n_edges, n_with_aux, WE, k, records,       \
+                                                               (unsigned long long *)cursor_dev, capacity, hist256, hist_byte);
+  MHB_FOR_WR(M)
+#undef M
+  CK_LAUNCH();
+  return MHB_OK;
+}
+
 // A13 for seq2sdbg: the items whose leading record byte lies in [lo, hi].  records == NULL counts only (hist256 +=
 // histogram of record byte hist_byte over the in-range items); otherwise the in-range records are appended at
 // records[*cursor_dev ...) (cursor_dev: device uint64, caller-zeroed; ends at the number of in-range items even when

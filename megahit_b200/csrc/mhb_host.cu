@@ -1213,10 +1213,23 @@ static int build_host_impl(const mhb_build_args *args, mhb_build_result *res, bo
   seqs.n_seqs = n_seqs;
   seqs.fixed_len = k + 1;
   seqs.fixed_stride = WE;
-  CKR(mhb_s2s_extract(st, &seqs, k, s_a, n_items, d_hist1, sbytes[0]));
+  // the solid edges still have the count stage's in/out flags: the $-items the emitter would discard for certain are
+  // not generated (mhb_s2s_extract_edges_pruned; 2.02 instead of 6 items per edge on a 30x genome), same bytes out
+  static const bool no_prune = getenv("MHB_S2S_NO_PRUNE") != nullptr;
+  uint64_t n_sorted = n_items;
+  if (!no_prune) {
+    CK(cudaMemsetAsync(d_nsolid + 4, 0, 8, st));
+    CKR(mhb_s2s_extract_edges_pruned(st, d_all_edges, d_aux, n_seqs, n_solid, k, s_a, n_items, d_nsolid + 4, d_hist1, sbytes[0]));
+    CK(cudaMemcpyAsync(&n_sorted, d_nsolid + 4, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_sorted > n_items) return mhb_set_error(MHB_ERR_CUDA, "internal: pruned item count exceeds 6 per edge");
+    res->n_sort_items = n_sorted;
+  } else {
+    CKR(mhb_s2s_extract(st, &seqs, k, s_a, n_items, d_hist1, sbytes[0]));
+  }
   int s_in_b = 0;
-  CKR(mhb_sort_records_impl(st, s_a, s_b, n_items, W2, sbytes, n_ssort, d_hist1, s_wsp, s_ws, &s_in_b, nullptr));
-  CKR(mhb_s2s_emit(st, s_in_b ? s_b : s_a, n_items, k, d_bytes, cap_bytes, d_table, d_totals, s_scrp, s_scr));
+  CKR(mhb_sort_records_impl(st, s_a, s_b, n_sorted, W2, sbytes, n_ssort, d_hist1, s_wsp, s_ws, &s_in_b, nullptr));
+  CKR(mhb_s2s_emit(st, s_in_b ? s_b : s_a, n_sorted, k, d_bytes, cap_bytes, d_table, d_totals, s_scrp, s_scr));
   uint64_t totals[16];
   CK(cudaMemcpyAsync(totals, d_totals, sizeof(totals), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));

@@ -52,6 +52,40 @@ struct DevBuf {  // cudaMalloc'ed scratch released on scope exit
     if (rc_) return rc_; \
   } while (0)
 
+// phase marks on the stream: deltas include host-side gaps (allocations, synchronisations) between the marks
+struct PhaseTrace {
+  std::vector<std::pair<const char *, cudaEvent_t>> ev;
+  cudaStream_t st = 0;
+  void mark(const char *name) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.emplace_back(name, e);
+  }
+  // ms spent in the phases whose name starts with `prefix` (all when empty); call after a stream synchronise
+  double sum(const char *prefix) const {
+    double t = 0;
+    for (size_t i = 1; i < ev.size(); ++i)
+      if (strncmp(ev[i].first, prefix, strlen(prefix)) == 0) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
+        t += ms;
+      }
+    return t;
+  }
+  void report() const {
+    if (!getenv("MHB_R2S_TRACE")) return;
+    for (size_t i = 1; i < ev.size(); ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
+      fprintf(stderr, "[r2s] %-28s %9.3f ms\n", ev[i].first, ms);
+    }
+  }
+  ~PhaseTrace() {
+    for (auto &e : ev) cudaEventDestroy(e.second);
+  }
+};
+
 unsigned grid_for(uint64_t n, unsigned threads, unsigned per_sm = 16) {
   uint64_t g = (n + threads - 1) / threads;
   const uint64_t cap = (uint64_t)sm_count() * per_sm;
@@ -140,14 +174,14 @@ int upload(DevBuf &d, const std::vector<T> &v, const char *what) {
 
 // ---- stage 1 on the device: is_solid bits, mercy planes, multiplicity histogram ----
 int run_stage1(cudaStream_t st, const PkgView &pv, const PkgIndex &ix, uint32_t k, int32_t m, bool need_mercy, const S1Out &out,
-               unsigned long long *d_mul_hist, double *t_sort_ms, double *t_kmsort_ms) {
+               unsigned long long *d_mul_hist, PhaseTrace &tr) {
   const uint32_t NW = r2s_s1_key_words(k), RW = NW + 2;
   const uint64_t n = ix.n_s1;
   if (n == 0) return MHB_OK;
   if (RW > 17)
     return mhb_set_error(MHB_ERR_ARG, "read2sdbg: stage 1 supports k <= 237 (record of %u words > 17)", RW);
   if (n >= (1ull << 40)) return mhb_set_error(MHB_ERR_ARG, "read2sdbg: too many stage-1 records for one round");
-  DevBuf a, b, ws, bstart, segs0, segs1, counter;
+  DevBuf a, b, ws, bstart, segs0, segs1, counter, bnd;
   const size_t rec_bytes = (size_t)n * RW * 4 + 16, ws_bytes = mhb_sort_workspace_bytes(n, RW);
   CKR(a.alloc(rec_bytes, "stage-1 records"));
   CKR(b.alloc(rec_bytes, "stage-1 records (sort buffer)"));
@@ -157,23 +191,21 @@ int run_stage1(cudaStream_t st, const PkgView &pv, const PkgIndex &ix, uint32_t 
   CKR(segs0.alloc(seg_cap * sizeof(KmSeg), "kmsort ranges"));
   CKR(segs1.alloc(seg_cap * sizeof(KmSeg), "kmsort ranges"));
   CKR(counter.alloc(8, "counter"));
-  cudaEvent_t e0, e1, e2;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
-  cudaEventCreate(&e2);
+  CKR(bnd.alloc((n / 32 + 2) * 4, "range marks"));
+  CK(cudaMemsetAsync(bnd.p, 0, (n / 32 + 2) * 4, st));
 #define M(WW)                                                                                         \
   if (NW == WW) k_r2s_s1_extract<WW><<<grid_for(n, 256), 256, 0, st>>>(pv, k, a.as<u32>(), n);
   MHB_FOR_W(M)
 #undef M
   CK_LAUNCH();
-  cudaEventRecord(e0, st);
+  tr.mark("s1.extract");
   // the reference's bucket input order: records of one 16-bit bucket in global read order = a STABLE sort on the two
   // leading key bytes (base_engine.cpp:323-348 fills every bucket thread by thread, i.e. in read order)
   const uint8_t bytes[2] = {(uint8_t)(4 * RW - 2), (uint8_t)(4 * RW - 1)};
   int in_b = 0;
   CKR(mhb_sort_records(st, a.as<u32>(), b.as<u32>(), n, RW, bytes, 2, nullptr, ws.p, ws_bytes, &in_b));
   u32 *recs = in_b ? b.as<u32>() : a.as<u32>();
-  cudaEventRecord(e1, st);
+  tr.mark("s1.partition");
   k_r2s_bucket_bounds<<<(MHB_NUM_BUCKETS + 1 + 255) / 256, 256, 0, st>>>(recs, n, RW, bstart.as<u64>());
   CK_LAUNCH();
   // kmsort, level by level (kmsort.h:103-117 entry, :43-101 per range)
@@ -184,11 +216,16 @@ int run_stage1(cudaStream_t st, const PkgView &pv, const PkgIndex &ix, uint32_t 
 #define M(WW)                                                                                                      \
   if (RW == WW)                                                                                                    \
     k_r2s_kmsort_level<WW><<<MHB_NUM_BUCKETS / 128, 128, 0, st>>>(recs, NW, kb, nullptr, bstart.as<u64>(),          \
-                                                                  MHB_NUM_BUCKETS, nxt, d_cnt, seg_cap);
+                                                                  MHB_NUM_BUCKETS, nxt, d_cnt, seg_cap, bnd.as<u32>());
   MHB_FOR_RW(M)
 #undef M
   CK_LAUNCH();
+  static char level_names[72][24];
+  int level = 0;
   for (;;) {
+    snprintf(level_names[level], sizeof(level_names[level]), "s1.kmsort.L%d", level);
+    tr.mark(level_names[level]);
+    if (level < 71) ++level;
     unsigned long long n_next = 0;
     CK(cudaMemcpyAsync(&n_next, d_cnt, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -200,27 +237,25 @@ int run_stage1(cudaStream_t st, const PkgView &pv, const PkgIndex &ix, uint32_t 
 #define M(WW)                                                                                                         \
   if (RW == WW)                                                                                                       \
     k_r2s_kmsort_level<WW><<<(unsigned)((n_next + 127) / 128), 128, 0, st>>>(recs, NW, kb, cur, nullptr, n_next, nxt, \
-                                                                            d_cnt, seg_cap);
+                                                                            d_cnt, seg_cap, bnd.as<u32>());
     MHB_FOR_RW(M)
 #undef M
     CK_LAUNCH();
   }
-  cudaEventRecord(e2, st);
+#define M(WW) \
+  if (RW == WW) k_r2s_kmsort_finish<WW><<<grid_for(n, 256, 32), 256, 0, st>>>(recs, n, NW, bnd.as<u32>());
+  MHB_FOR_RW(M)
+#undef M
+  CK_LAUNCH();
+  tr.mark("s1.kmsort.finish");
 #define M(WW)                                                                                                          \
   if (RW == WW)                                                                                                        \
     k_r2s_s1_post<WW><<<grid_for(n, 256, 32), 256, 0, st>>>(recs, n, NW, k, m, pv, out, need_mercy ? 1 : 0, d_mul_hist);
   MHB_FOR_RW(M)
 #undef M
   CK_LAUNCH();
+  tr.mark("s1.post");
   CK(cudaStreamSynchronize(st));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, e0, e1);
-  *t_sort_ms = ms;
-  cudaEventElapsedTime(&ms, e1, e2);
-  *t_kmsort_ms = ms;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaEventDestroy(e2);
   return MHB_OK;
 }
 
@@ -237,10 +272,8 @@ extern "C" int mhb_read2sdbg_host(const mhb_build_args *args, mhb_build_result *
   if (k < 9 || k > MHB_MAX_K || m < 1) return mhb_set_error(MHB_ERR_ARG, "read2sdbg: need 9 <= k <= 255 and m >= 1");
   if (mhb_device_count() <= 0) return mhb_set_error(MHB_ERR_CUDA, "no CUDA device: libmhb has no CPU path");
   cudaStream_t st = 0;
-  cudaEvent_t ev0, ev1;
-  cudaEventCreate(&ev0);
-  cudaEventCreate(&ev1);
-  cudaEventRecord(ev0, st);
+  PhaseTrace tr;
+  tr.mark("start");
   PkgIndex ix;
   CKR(index_pkg(args->bin, args->bin_words, args->n_reads, k, &ix));
   const uint32_t W = s2s_record_words(k), WPT = words_per_tip_label(k);
@@ -283,6 +316,7 @@ extern "C" int mhb_read2sdbg_host(const mhb_build_args *args, mhb_build_result *
     CK(cudaStreamSynchronize(st));  // d_bin / d_rec_off go out of scope
   }
   pv.words = d_pkg.as<u32>();
+  tr.mark("h2d.upload+reverse");
 
   // ---- stage 1 (only when the threshold can reject anything, main_sdbg_build.cpp:141-147) ----
   const uint64_t bit_words = ix.n_bases / 32 + 2;
@@ -295,7 +329,6 @@ extern "C" int mhb_read2sdbg_host(const mhb_build_args *args, mhb_build_result *
   CK(cudaMemsetAsync(d_cnt.p, 0, 64, st));
   unsigned long long *d_counter = d_cnt.as<unsigned long long>();
   const bool mercy = args->need_mercy && m > 1;
-  double t_sort = 0, t_km = 0;
   if (m > 1 && ix.n_s1) {
     S1Out so;
     memset(&so, 0, sizeof(so));
@@ -307,7 +340,7 @@ extern "C" int mhb_read2sdbg_host(const mhb_build_args *args, mhb_build_result *
       so.no_out = so.no_in + bit_words;
       so.any = so.no_out + bit_words;
     }
-    CKR(run_stage1(st, pv, ix, k, m, mercy, so, d_hist.as<unsigned long long>(), &t_sort, &t_km));
+    CKR(run_stage1(st, pv, ix, k, m, mercy, so, d_hist.as<unsigned long long>(), tr));
     if (mercy) {  // Read2SdbgS2::Initialize, read_to_sdbg_s2.cpp:117-263
       u32 *d_mercy = so.any + bit_words;
       k_r2s_mercy<<<grid_for(ix.n_reads, 256), 256, 0, st>>>(pv, k, so, d_mercy, d_counter + 1);
@@ -318,13 +351,12 @@ extern "C" int mhb_read2sdbg_host(const mhb_build_args *args, mhb_build_result *
       CK(cudaMemcpyAsync(&nm, d_counter + 1, 8, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       res->n_mercy = nm;
+      tr.mark("s1.mercy");
     }
     CK(cudaMemcpyAsync(res->counting, d_hist.p, 65536 * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     d_planes.release();
   }
-  res->t_count_ms = t_sort;   // stable bucket partition of the stage-1 records
-  res->t_mercy_ms = t_km;     // kmsort emulation
 
   // ---- stage 2 ----
   uint64_t n_items = 0;
@@ -341,6 +373,7 @@ extern "C" int mhb_read2sdbg_host(const mhb_build_args *args, mhb_build_result *
     CK(cudaMemcpyAsync(&c, d_counter, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     n_items = c;
+    tr.mark("s2.count");
   }
   res->n_sort_items = n_items;
   DevBuf d_table, d_totals;
@@ -362,10 +395,12 @@ extern "C" int mhb_read2sdbg_host(const mhb_build_args *args, mhb_build_result *
     MHB_FOR_WR(M)
 #undef M
     CK_LAUNCH();
+    tr.mark("s2.extract");
     uint8_t sbytes[80];
     const uint32_t n_sb = mhb_s2s_sort_bytes(k, sbytes);
     int in_b = 0;
     CKR(mhb_sort_records_relaxed(st, a.as<u32>(), b.as<u32>(), n_items, W, sbytes, n_sb, nullptr, ws.p, ws_bytes, &in_b));
+    tr.mark("s2.sort");
     const u32 *sorted = in_b ? b.as<u32>() : a.as<u32>();
     u32 *uniq = in_b ? a.as<u32>() : b.as<u32>();
     // equal items -> one item carrying the run length (read_to_sdbg_s2.cpp:560-572)
@@ -393,6 +428,7 @@ extern "C" int mhb_read2sdbg_host(const mhb_build_args *args, mhb_build_result *
     MHB_FOR_WR(M)
 #undef M
     CK_LAUNCH();
+    tr.mark("s2.collapse");
     const size_t scr_bytes = mhb_s2s_emit_scratch_bytes(n_u, k);
     const uint64_t cap_bytes = (uint64_t)n_u * (4ull + 4ull * WPT) + 16;
     CKR(scr.alloc(scr_bytes, "emit scratch"));
@@ -402,6 +438,7 @@ extern "C" int mhb_read2sdbg_host(const mhb_build_args *args, mhb_build_result *
     uint64_t totals[16];
     CK(cudaMemcpyAsync(totals, d_totals.p, sizeof(totals), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    tr.mark("s2.emit");
     res->n_bytes = totals[0];
     res->n_items = totals[1];
     res->n_tips = totals[2];
@@ -415,15 +452,18 @@ extern "C" int mhb_read2sdbg_host(const mhb_build_args *args, mhb_build_result *
     CK(cudaMemcpyAsync(res->bucket_table, d_table.p, (size_t)MHB_NUM_BUCKETS * 32, cudaMemcpyDeviceToHost, st));
     if (res->n_bytes) CK(cudaMemcpyAsync(res->bytes, d_bytes.p, res->n_bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    tr.mark("d2h");
     res->n_solid = n_u;  // distinct stage-2 items
   }
-  cudaEventRecord(ev1, st);
-  cudaEventSynchronize(ev1);
-  float ms = 0;
-  cudaEventElapsedTime(&ms, ev0, ev1);
-  res->t_total_ms = ms;
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
+  tr.mark("release");
+  CK(cudaStreamSynchronize(st));
+  res->t_h2d_ms = tr.sum("h2d");
+  res->t_count_ms = tr.sum("s1.extract") + tr.sum("s1.partition");  // records + stable bucket partition
+  res->t_mercy_ms = tr.sum("s1.kmsort");                            // kmsort emulation (levels + finish)
+  res->t_s2s_ms = tr.sum("s2");
+  res->t_d2h_ms = tr.sum("d2h");
+  res->t_total_ms = tr.sum("");
+  tr.report();
   return MHB_OK;
 }
 
@@ -463,37 +503,38 @@ extern "C" int mhb_selftest_r2s_item(const uint32_t *pkg_words, uint32_t nwords,
   return MHB_OK;
 }
 
-// kmsort emulation of ONE bucket on the host, level by level exactly as the kernels do it (records of nw + 2 words)
+// kmsort emulation of ONE bucket on the host, exactly as the kernels do it (records of nw + 2 words): radix levels that
+// mark the range starts, then the insertion sorts of all marked small ranges
 extern "C" int mhb_selftest_kmsort(uint32_t *recs, uint64_t n, uint32_t nw) {
   const uint32_t RW = nw + 2;
   if (nw < 1 || RW > 17 || n >= (1ull << 32)) return mhb_set_error(MHB_ERR_ARG, "bad args");
   if (n <= 1) return MHB_OK;
   std::vector<KmSeg> cur, nxt;
-  std::vector<u32> count(256), last(256);
+  std::vector<u32> count(256), last(256), bnd(n / 32 + 2, 0u);
   int kb = 4 * (int)nw - 2 - 1;
+  bit_or(bnd.data(), 0);
 #define M(WW)                                                                                           \
   if (RW == WW) {                                                                                       \
-    if (n <= (uint64_t)kKmInsertThreshold) {                                                            \
-      km_insertion<WW>(recs, (u32)n, nw);                                                               \
-      return MHB_OK;                                                                                    \
-    }                                                                                                   \
-    cur.push_back(KmSeg{0, n});                                                                         \
-    for (;;) {                                                                                          \
+    if (n > (uint64_t)kKmInsertThreshold) cur.push_back(KmSeg{0, n});                                   \
+    while (!cur.empty()) {                                                                              \
       nxt.clear();                                                                                      \
       for (const KmSeg &s : cur) {                                                                      \
-        u32 *a = recs + s.start * WW;                                                                   \
-        km_radix_range<WW>(a, (u32)s.len, nw, kb, count.data(), last.data());                           \
+        km_radix_range<WW>(recs + s.start * WW, (u32)s.len, nw, kb, count.data(), last.data());         \
         u32 b0 = 0;                                                                                     \
-        for (int i = 0; i < 256 && kb > 0; ++i) {                                                       \
+        for (int i = 0; i < 256; ++i) {                                                                 \
           const u32 c = count[i];                                                                       \
-          if (c > (u32)kKmInsertThreshold) nxt.push_back(KmSeg{s.start + b0, c});                       \
-          else if (c > 1) km_insertion<WW>(a + (u64)b0 * WW, c, nw);                                    \
+          if (c) bit_or(bnd.data(), s.start + b0);                                                      \
+          if (c > (u32)kKmInsertThreshold && kb > 0) nxt.push_back(KmSeg{s.start + b0, c});             \
           b0 += c;                                                                                      \
         }                                                                                               \
       }                                                                                                 \
-      if (nxt.empty() || kb == 0) break;                                                                \
       cur.swap(nxt);                                                                                    \
       --kb;                                                                                             \
+    }                                                                                                   \
+    for (u64 i = 0; i < n; ++i) {                                                                       \
+      if (!bit_at(bnd.data(), i)) continue;                                                             \
+      const u32 len = km_small_range(bnd.data(), n, i, (u32)kKmInsertThreshold);                        \
+      if (len >= 2) km_insertion<WW>(recs + i * WW, len, nw);                                           \
     }                                                                                                   \
   }
   MHB_FOR_RW(M)

@@ -484,22 +484,24 @@ struct KmSeg {
 };
 
 // one kmsort level: thread t permutes range segs[t] on byte kb (level 0: the 65 536 buckets, radix_sort_entry
-// kmsort.h:103-117), sorts small children by insertion and queues the large ones for byte kb - 1
+// kmsort.h:103-117) and queues the children above the insertion-sort threshold for byte kb - 1.  Children of 2..64
+// records (and buckets that small) are NOT sorted here - 256 serial insertion sorts per thread were 80 % of the first
+// version's time -: every range start is marked in the bit array `bnd`, and k_r2s_kmsort_finish sorts all small ranges
+// of all levels afterwards, one thread per range (their order does not depend on anything outside the range).
 template <int RW>
 __global__ void __launch_bounds__(128) k_r2s_kmsort_level(u32 *__restrict__ recs, u32 nw, int kb, const KmSeg *__restrict__ segs,
                                                          const u64 *__restrict__ bstart, u64 n_segs, KmSeg *__restrict__ next,
-                                                         unsigned long long *__restrict__ n_next, u64 next_cap) {
+                                                         unsigned long long *__restrict__ n_next, u64 next_cap,
+                                                         u32 *__restrict__ bnd) {
   const u64 t = (u64)blockIdx.x * 128 + threadIdx.x;
   if (t >= n_segs) return;
   u64 start, len;
   if (bstart) {  // level 0
     start = bstart[t];
     len = bstart[t + 1] - start;
-    if (len <= 1) return;
-    if (len <= (u64)kKmInsertThreshold) {
-      km_insertion<RW>(recs + start * RW, (u32)len, nw);
-      return;
-    }
+    if (len == 0) return;
+    bit_or(bnd, start);
+    if (len <= (u64)kKmInsertThreshold) return;
   } else {
     start = segs[t].start;
     len = segs[t].len;
@@ -507,17 +509,35 @@ __global__ void __launch_bounds__(128) k_r2s_kmsort_level(u32 *__restrict__ recs
   u32 count[256], last[256];
   u32 *a = recs + start * RW;
   km_radix_range<RW>(a, (u32)len, nw, kb, count, last);
-  if (kb == 0) return;  // :84 / :93: no level below byte 0
   u32 b0 = 0;
   for (int i = 0; i < 256; ++i) {
     const u32 c = count[i];
-    if (c > (u32)kKmInsertThreshold) {
+    if (c) bit_or(bnd, start + b0);
+    if (c > (u32)kKmInsertThreshold && kb > 0) {  // :84 / :93: no level below byte 0
       const unsigned long long slot = atomicAdd(n_next, 1ull);
       if (slot < next_cap) next[slot] = KmSeg{start + b0, c};
-    } else if (c > 1) {
-      km_insertion<RW>(a + (u64)b0 * RW, c, nw);
     }
     b0 += c;
+  }
+}
+
+// length of the marked range starting at i if it has at most `lim` records, else 0 (bit n counts as a boundary)
+MHB_HD u32 km_small_range(const u32 *bnd, u64 n, u64 i, u32 lim) {
+  for (u32 d = 1; d <= lim; ++d) {
+    if (i + d >= n || bit_at(bnd, i + d)) return d;
+  }
+  return 0;
+}
+
+// the insertion sorts of every level (kmsort.h:88-99, :106-108): one thread per marked range of 2..64 records.  A
+// marked range of more than 64 records with no mark inside went through every radix level as a single bin: all its
+// keys are equal.
+template <int RW>
+__global__ void __launch_bounds__(256) k_r2s_kmsort_finish(u32 *__restrict__ recs, u64 n, u32 nw, const u32 *__restrict__ bnd) {
+  for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += (u64)gridDim.x * 256) {
+    if (!bit_at(bnd, i)) continue;
+    const u32 len = km_small_range(bnd, n, i, (u32)kKmInsertThreshold);
+    if (len >= 2) km_insertion<RW>(recs + i * RW, len, nw);
   }
 }
 

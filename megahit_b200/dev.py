@@ -6,6 +6,7 @@ only; all launches go to torch's current stream, so `torch.cuda.Event` timing se
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -190,14 +191,19 @@ class S2sPlan:
         self.table = torch.zeros(65536 * 4, dtype=torch.int64, device=device)
         self.totals = torch.zeros(16, dtype=torch.int64, device=device)
         self.hist0 = torch.zeros(256, dtype=torch.int64, device=device)
+        self.cursor = torch.zeros(1, dtype=torch.int64, device=device)
         self.events = []
 
     def run(self, words: torch.Tensor, mult: torch.Tensor | None = None, n_seqs: int | None = None, stride: int = 0,
-            timed: bool = False):
-        """words: packed sequences; with mult=None they are `.edges` records of `stride` words each."""
+            timed: bool = False, aux: torch.Tensor | None = None, n_aux: int = 0):
+        """words: packed sequences; with mult=None they are `.edges` records of `stride` words each.  aux (with
+        mult=None): the count stage's in/out flags of the first n_aux edges - the $-items the emitter is certain to
+        discard are then not generated (mhb_s2s_extract_edges_pruned)."""
         n_seqs = self.n_seqs if n_seqs is None else n_seqs
         assert n_seqs <= self.n_seqs
         self.n_items = n_seqs * 2 * (self.seq_len - self.k + 2)
+        if aux is not None and mult is None and not os.environ.get("MHB_S2S_NO_PRUNE"):
+            return self._run_pruned(words, n_seqs, aux, n_aux, timed)
         seqs = lib.DevSeqs(words.data_ptr(), words.numel(), n_seqs, self.seq_len, None, None, None,
                            mult.data_ptr() if mult is not None else None, stride)
         self.hist0.zero_()
@@ -206,6 +212,29 @@ class S2sPlan:
             ev[0].record()
         lib._check(self.L.mhb_s2s_extract(_stream(), C.byref(seqs), self.k, _ptr(self.a), self.n_items, _ptr(self.hist0),
                                           self.sort_bytes[0]))
+        if timed:
+            ev[1].record()
+        srt = sort_records(self.a, self.b, self.n_items, self.W, self.sort_bytes, self.hist0, self.ws, relaxed=True)
+        if timed:
+            ev[2].record()
+        lib._check(self.L.mhb_s2s_emit(_stream(), _ptr(srt), self.n_items, self.k, _ptr(self.bytes), self.cap_bytes,
+                                       _ptr(self.table), _ptr(self.totals), _ptr(self.scratch), self.scratch.numel()))
+        if timed:
+            ev[3].record()
+            self.events.append(ev)
+        return self.totals
+
+    def _run_pruned(self, edges: torch.Tensor, n_edges: int, aux: torch.Tensor, n_aux: int, timed: bool):
+        cap = self.n_items
+        self.hist0.zero_()
+        self.cursor.zero_()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timed else None
+        if timed:
+            ev[0].record()
+        lib._check(self.L.mhb_s2s_extract_edges_pruned(_stream(), _ptr(edges), _ptr(aux), n_edges, n_aux, self.k, _ptr(self.a),
+                                                       cap, _ptr(self.cursor), _ptr(self.hist0), self.sort_bytes[0]))
+        self.n_items = int(self.cursor.item())  # the one host read-back of the stage (launch geometry of the sort)
+        assert self.n_items <= cap
         if timed:
             ev[1].record()
         srt = sort_records(self.a, self.b, self.n_items, self.W, self.sort_bytes, self.hist0, self.ws, relaxed=True)

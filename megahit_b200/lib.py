@@ -113,7 +113,7 @@ SYMBOLS = [
     "mhb_s2s_emit_scratch_bytes", "mhb_s2s_emit", "mhb_set_device", "mhb_count_host", "mhb_s2s_host", "mhb_build_host", "mhb_free",
     "mhb_mercy_candidates_scratch_bytes", "mhb_mercy_candidates", "mhb_mercy_edges_scratch_bytes", "mhb_mercy_edges", "mhb_mercy_edges_count", "mhb_mercy_edges_write", "mhb_mercy_edges_segs", "mhb_mercy_host", "mhb_mercy_planes_words", "mhb_mercy_probe_owned", "mhb_mercy_count_planes", "mhb_edge_lut_bytes", "mhb_edge_lut_build",
     "mhb_release", "mhb_count_run", "mhb_count_run_multi", "mhb_seq2sdbg_run", "mhb_selftest_count_record", "mhb_selftest_count_records_roll", "mhb_selftest_s2s_record",
-    "mhb_s2s_emit_fmt", "mhb_read2sdbg_host", "mhb_read2sdbg_run", "mhb_selftest_r2s_s1_record", "mhb_selftest_r2s_item",
+    "mhb_s2s_extract_edges_pruned", "mhb_s2s_emit_fmt", "mhb_read2sdbg_host", "mhb_read2sdbg_run", "mhb_selftest_r2s_s1_record", "mhb_selftest_r2s_item",
     "mhb_selftest_kmsort", "mhb_selftest_r2s_s1_group", "mhb_selftest_r2s_mercy_read",
 ]
 
@@ -212,6 +212,8 @@ def load():
     L.mhb_selftest_s2s_record.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_uint32, C.c_void_p]
     L.mhb_s2s_emit_fmt.argtypes = L.mhb_s2s_emit.argtypes + [C.c_int]
+    L.mhb_s2s_extract_edges_pruned.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32,
+                                               C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
     L.mhb_read2sdbg_host.argtypes = [C.POINTER(BuildArgs), C.POINTER(BuildResult)]
     L.mhb_read2sdbg_run.argtypes = [C.POINTER(Read2SdbgOpts)]
     L.mhb_selftest_r2s_s1_record.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]
@@ -437,7 +439,8 @@ def read2sdbg_host(bin_words: np.ndarray, n_reads: int, k: int, m: int, need_mer
         "w_count": np.array(r.w_count, np.uint64), "ones_in_last": r.ones_in_last,
         "counting": np.ctypeslib.as_array(r.counting, (65536,)).copy(),
         "bytes": bytes(np.ctypeslib.as_array(r.bytes, (max(r.n_bytes, 1),))[: r.n_bytes]),
-        "ms": {"total": r.t_total_ms, "bucket_partition": r.t_count_ms, "kmsort": r.t_mercy_ms},
+        "ms": {"total": r.t_total_ms, "h2d": r.t_h2d_ms, "s1_records_partition": r.t_count_ms, "kmsort": r.t_mercy_ms,
+               "stage2": r.t_s2s_ms, "d2h": r.t_d2h_ms},
     }
     L.mhb_free(r.bytes)
     L.mhb_free(r.bucket_table)

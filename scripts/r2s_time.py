@@ -21,8 +21,10 @@ L, k = 150, 27
 b = synth.synth_reads(n_reads, L, 5 * n_reads, 0.01, seed=99)
 for m, mercy in ((2, True), (1, False)):
     lib.read2sdbg_host(b.reshape(-1), n_reads, k, m, mercy)  # warm-up (allocations, module load)
+    os.environ["MHB_R2S_TRACE"] = "1"  # per-phase times on stderr
     t0 = time.time()
     g = lib.read2sdbg_host(b.reshape(-1), n_reads, k, m, mercy)
+    del os.environ["MHB_R2S_TRACE"]
     wall = time.time() - t0
     line = {"what": "read2sdbg", "n_reads": n_reads, "k": k, "m": m, "mercy": mercy, "edge_positions": g["n_edge_records"],
             "sort_items": g["n_sort_items"], "distinct_items": g["n_distinct_items"], "sdbg_items": g["n_items"],
