@@ -21,6 +21,7 @@ the solid edges (all-gather) for the mercy-edge searches.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -408,7 +409,16 @@ class MultiGpuBuild:
         hist2 = self._buf("s_hist", 256, torch.int64)[:256]
         hist2.zero_()
         top2 = self.sbytes[-1]
-        lib._check(L.mhb_s2s_extract(_stream(), C.byref(seqs), k, _ptr(sa), n_items, _ptr(hist2), top2))
+        if os.environ.get("MHB_S2S_NO_PRUNE"):
+            lib._check(L.mhb_s2s_extract(_stream(), C.byref(seqs), k, _ptr(sa), n_items, _ptr(hist2), top2))
+        else:
+            # the owned solid edges still carry the count stage's in/out flags: $-items the emitter would discard for
+            # certain are neither generated nor exchanged (a third of the items; mhb_s2s_extract_edges_pruned)
+            cur = self._buf("s_cursor", 8, torch.int64)[:1]
+            cur.zero_()
+            lib._check(L.mhb_s2s_extract_edges_pruned(_stream(), _ptr(seq_edges), _ptr(aux), n_seqs, n_solid, k, _ptr(sa),
+                                                      n_items, _ptr(cur), _ptr(hist2), top2))
+            n_items = int(self._to_host(cur)[0])
         own2, n_own2, bounds2, _ = self._partition_and_exchange(sa, n_items, self.W2, top2, hist2, "s", max(n_items, 1),
                                                                  next_byte=self.sbytes[0])
         s_hist = self._first_hist
