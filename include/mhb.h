@@ -524,6 +524,8 @@ int mhb_selftest_r2s_s1_record(const uint32_t *pkg_words, uint32_t nwords, uint3
 int mhb_selftest_r2s_item(const uint32_t *pkg_words, uint32_t nwords, uint32_t L, uint32_t k, uint32_t i, uint32_t strand,
                           uint32_t type, uint32_t *rec_out, uint32_t *palindrome_out);
 int mhb_selftest_kmsort(uint32_t *recs, uint64_t n, uint32_t nw);
+/* the shared-memory form of the same sort (walk on tags, staged ranges of at most wcap records; 0 = device default), buckets above `cap` tags fall back to the in-place walk */
+int mhb_selftest_kmsort_smem(uint32_t *recs, uint64_t n, uint32_t nw, uint32_t cap, uint32_t wcap);
 int mhb_selftest_r2s_s1_group(const uint32_t *recs, uint64_t n, uint32_t k, int32_t m, uint32_t fixed_len, uint64_t n_reads,
                               int need_mercy, uint32_t *is_solid, uint32_t *no_in, uint32_t *no_out, uint32_t *any,
                               int64_t *counting);

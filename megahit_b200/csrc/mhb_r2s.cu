@@ -208,20 +208,49 @@ int run_stage1(cudaStream_t st, const PkgView &pv, const PkgIndex &ix, uint32_t 
   tr.mark("s1.partition");
   k_r2s_bucket_bounds<<<(MHB_NUM_BUCKETS + 1 + 255) / 256, 256, 0, st>>>(recs, n, RW, bstart.as<u64>());
   CK_LAUNCH();
-  // kmsort, level by level (kmsort.h:103-117 entry, :43-101 per range)
+  // kmsort (kmsort.h:103-117 entry, :43-101 per range), level by level
   int kb = 4 * (int)NW - 2 - 1;
   KmSeg *cur = segs0.as<KmSeg>(), *nxt = segs1.as<KmSeg>();
   unsigned long long *d_cnt = counter.as<unsigned long long>();
   CK(cudaMemsetAsync(d_cnt, 0, 8, st));
+  static const bool km_global = getenv("MHB_R2S_KMSORT_GLOBAL") != nullptr;  // the in-place form of every level (A/B)
+  static char level_names[72][24];
+  int level = 0;
+  DevBuf todo, src16;
+  u32 *d_todo = nullptr;
+  if (!km_global) {
+    // level 0 on shared-memory tags: bucket sizes decide the tag capacity of a CTA
+    std::vector<uint64_t> h_b(MHB_NUM_BUCKETS + 1);
+    CK(cudaMemcpyAsync(h_b.data(), bstart.p, h_b.size() * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint64_t max_bucket = 0;
+    for (int i = 0; i < MHB_NUM_BUCKETS; ++i) max_bucket = std::max(max_bucket, h_b[i + 1] - h_b[i]);
+    uint32_t cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(max_bucket, 1024), 65535);
+    cap = (cap + 1023) & ~1023u;
+    CKR(todo.alloc((n / 32 + 2) * 4, "unsorted-range marks"));
+    CK(cudaMemsetAsync(todo.p, 0, (n / 32 + 2) * 4, st));
+    CKR(src16.alloc((size_t)n * 2 + 64, "kmsort source indices"));
+    d_todo = todo.as<u32>();
+    u32 *other = in_b ? a.as<u32>() : b.as<u32>();
+#define M(WW)                                                                                                           \
+  if (RW == WW) {                                                                                                       \
+    CK(cudaFuncSetAttribute(k_r2s_km_bucket<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));               \
+    k_r2s_km_bucket<WW><<<MHB_NUM_BUCKETS, 128, cap, st>>>(recs, other, bstart.as<u64>(), NW, kb, cap,                   \
+                                                           src16.as<uint16_t>(), bnd.as<u32>(), d_todo, nxt, d_cnt, seg_cap); \
+  }
+    MHB_FOR_RW(M)
+#undef M
+    CK_LAUNCH();
+    recs = other;
+  } else {
 #define M(WW)                                                                                                      \
   if (RW == WW)                                                                                                    \
     k_r2s_kmsort_level<WW><<<MHB_NUM_BUCKETS / 128, 128, 0, st>>>(recs, NW, kb, nullptr, bstart.as<u64>(),          \
                                                                   MHB_NUM_BUCKETS, nxt, d_cnt, seg_cap, bnd.as<u32>());
-  MHB_FOR_RW(M)
+    MHB_FOR_RW(M)
 #undef M
-  CK_LAUNCH();
-  static char level_names[72][24];
-  int level = 0;
+    CK_LAUNCH();
+  }
   for (;;) {
     snprintf(level_names[level], sizeof(level_names[level]), "s1.kmsort.L%d", level);
     tr.mark(level_names[level]);
@@ -234,16 +263,34 @@ int run_stage1(cudaStream_t st, const PkgView &pv, const PkgIndex &ix, uint32_t 
     std::swap(cur, nxt);
     --kb;
     CK(cudaMemsetAsync(d_cnt, 0, 8, st));
+    if (!km_global) {
+#define M(WW)                                                                                                            \
+  if (RW == WW) {                                                                                                        \
+    const size_t smem = (size_t)kKmWarps * km_warp_smem<WW>();                                                           \
+    static bool attr = false;                                                                                            \
+    if (!attr) {                                                                                                         \
+      CK(cudaFuncSetAttribute(k_r2s_km_warp<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+      attr = true;                                                                                                       \
+    }                                                                                                                    \
+    uint64_t g = (n_next + kKmWarps - 1) / kKmWarps;                                                                     \
+    if (g > (uint64_t)sm_count() * 8) g = (uint64_t)sm_count() * 8;                                                      \
+    k_r2s_km_warp<WW><<<(unsigned)g, kKmWarps * 32, smem, st>>>(recs, NW, kb, cur, n_next, nxt, d_cnt, seg_cap,           \
+                                                              bnd.as<u32>(), d_todo);                                    \
+  }
+      MHB_FOR_RW(M)
+#undef M
+    } else {
 #define M(WW)                                                                                                         \
   if (RW == WW)                                                                                                       \
     k_r2s_kmsort_level<WW><<<(unsigned)((n_next + 127) / 128), 128, 0, st>>>(recs, NW, kb, cur, nullptr, n_next, nxt, \
                                                                             d_cnt, seg_cap, bnd.as<u32>());
-    MHB_FOR_RW(M)
+      MHB_FOR_RW(M)
 #undef M
+    }
     CK_LAUNCH();
   }
 #define M(WW) \
-  if (RW == WW) k_r2s_kmsort_finish<WW><<<grid_for(n, 256, 32), 256, 0, st>>>(recs, n, NW, bnd.as<u32>());
+  if (RW == WW) k_r2s_kmsort_finish<WW><<<grid_for(n, 256, 32), 256, 0, st>>>(recs, n, NW, bnd.as<u32>(), d_todo);
   MHB_FOR_RW(M)
 #undef M
   CK_LAUNCH();
@@ -536,6 +583,97 @@ extern "C" int mhb_selftest_kmsort(uint32_t *recs, uint64_t n, uint32_t nw) {
       const u32 len = km_small_range(bnd.data(), n, i, (u32)kKmInsertThreshold);                        \
       if (len >= 2) km_insertion<WW>(recs + i * WW, len, nw);                                           \
     }                                                                                                   \
+  }
+  MHB_FOR_RW(M)
+#undef M
+  return MHB_OK;
+}
+
+// The shared-memory form of the same sort, mirrored on the host with the same building blocks (km_walk_src on the tags,
+// km_insertion_idx on the index array of a staged range): level 0 gathers the bucket into a second buffer, later levels
+// stage ranges of at most `wcap` records (0 = km_wcap of the record width, as on the device), larger ones and buckets
+// above `cap` tags take the in-place walk; what is left unsorted is marked and finished by insertion.
+extern "C" int mhb_selftest_kmsort_smem(uint32_t *recs, uint64_t n, uint32_t nw, uint32_t cap, uint32_t wcap) {
+  const uint32_t RW = nw + 2;
+  if (nw < 1 || RW > 17 || n >= (1ull << 32)) return mhb_set_error(MHB_ERR_ARG, "bad args");
+  if (n <= 1) return MHB_OK;
+  std::vector<KmSeg> cur, nxt;
+  std::vector<u32> cnt(256), last(256), beg(256), bnd(n / 32 + 2, 0u), todo(n / 32 + 2, 0u);
+  std::vector<uint8_t> tags(n);
+  std::vector<uint16_t> src(n);
+  std::vector<u32> other((size_t)n * RW), staged;
+  int kb = 4 * (int)nw - 2 - 1;
+#define M(WW)                                                                                                         \
+  if (RW == WW) {                                                                                                     \
+    if (!wcap) wcap = km_wcap(WW);                                                                                    \
+    bit_or(bnd.data(), 0);                                                                                            \
+    auto children = [&](u64 start, bool sorted_small) {                                                               \
+      u32 acc = 0;                                                                                                    \
+      for (int i = 0; i < 256; ++i) {                                                                                 \
+        const u32 c = cnt[i];                                                                                         \
+        if (c) {                                                                                                      \
+          bit_or(bnd.data(), start + acc);                                                                            \
+          if (kb > 0) {                                                                                               \
+            if (c > (u32)kKmInsertThreshold) nxt.push_back(KmSeg{start + acc, c});                                    \
+            else if (c >= 2 && !sorted_small) bit_or(todo.data(), start + acc);                                       \
+          }                                                                                                           \
+        }                                                                                                             \
+        acc += c;                                                                                                     \
+      }                                                                                                               \
+    };                                                                                                                \
+    /* level 0 (k_r2s_km_bucket) */                                                                                   \
+    if (n <= (uint64_t)kKmInsertThreshold) {                                                                          \
+      bit_or(todo.data(), 0);                                                                                         \
+    } else if (n > cap || n > 65535) {                                                                                \
+      km_radix_range<WW>(recs, (u32)n, nw, kb, cnt.data(), last.data());                                              \
+      children(0, false);                                                                                             \
+    } else {                                                                                                          \
+      std::fill(cnt.begin(), cnt.end(), 0u);                                                                          \
+      for (u32 i = 0; i < n; ++i) ++cnt[tags[i] = (uint8_t)km_byte_mem(recs + (size_t)i * WW, nw, kb)];               \
+      for (u32 i = 0, acc = 0; i < 256; ++i) {                                                                        \
+        last[i] = acc;                                                                                                \
+        acc += cnt[i];                                                                                                \
+      }                                                                                                               \
+      km_walk_src<uint16_t>(tags.data(), (u32)n, cnt.data(), last.data(), src.data());                                \
+      for (u32 q = 0; q < n; ++q) memcpy(&other[(size_t)q * WW], recs + (size_t)src[q] * WW, 4 * WW);                 \
+      memcpy(recs, other.data(), (size_t)n * WW * 4);                                                                 \
+      children(0, false);                                                                                             \
+    }                                                                                                                 \
+    /* levels >= 1 (k_r2s_km_warp) */                                                                                 \
+    while (!nxt.empty() && kb > 0) {                                                                                  \
+      cur.swap(nxt);                                                                                                  \
+      nxt.clear();                                                                                                    \
+      --kb;                                                                                                           \
+      for (const KmSeg &sg : cur) {                                                                                   \
+        u32 *a = recs + sg.start * WW;                                                                                \
+        const u32 len = (u32)sg.len;                                                                                  \
+        if (len > wcap) {                                                                                             \
+          km_radix_range<WW>(a, len, nw, kb, cnt.data(), last.data());                                                \
+          children(sg.start, false);                                                                                  \
+          continue;                                                                                                   \
+        }                                                                                                             \
+        staged.assign(a, a + (size_t)len * WW);                                                                       \
+        std::fill(cnt.begin(), cnt.end(), 0u);                                                                        \
+        for (u32 i = 0; i < len; ++i) ++cnt[tags[i] = (uint8_t)km_byte_mem(&staged[(size_t)i * WW], nw, kb)];         \
+        for (u32 i = 0, acc = 0; i < 256; ++i) {                                                                      \
+          beg[i] = last[i] = acc;                                                                                     \
+          acc += cnt[i];                                                                                              \
+        }                                                                                                             \
+        km_walk_src<uint16_t>(tags.data(), len, cnt.data(), last.data(), src.data());                                 \
+        if (kb > 0)                                                                                                   \
+          for (int b = 0; b < 256; ++b)                                                                               \
+            if (cnt[b] >= 2 && cnt[b] <= (u32)kKmInsertThreshold)                                                     \
+              km_insertion_idx<uint16_t>(staged.data(), WW, src.data() + beg[b], cnt[b], nw);                         \
+        for (u32 q = 0; q < len; ++q) memcpy(a + (size_t)q * WW, &staged[(size_t)src[q] * WW], 4 * WW);               \
+        children(sg.start, true);                                                                                     \
+      }                                                                                                               \
+    }                                                                                                                 \
+    /* k_r2s_kmsort_finish */                                                                                         \
+    for (u64 i = 0; i < n; ++i) {                                                                                     \
+      if (!bit_at(todo.data(), i)) continue;                                                                          \
+      const u32 len = km_small_range(bnd.data(), n, i, (u32)kKmInsertThreshold);                                      \
+      if (len >= 2) km_insertion<WW>(recs + i * WW, len, nw);                                                         \
+    }                                                                                                                 \
   }
   MHB_FOR_RW(M)
 #undef M

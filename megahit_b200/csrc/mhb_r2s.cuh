@@ -270,6 +270,62 @@ MHB_HD void km_radix_range(u32 *a, u32 n, u32 nw, int kb, u32 *count, u32 *last)
   }
 }
 
+// The same permutation from the TAGS alone.  Positions at or behind a bin's cursor still hold their original record
+// (the walk only ever writes at a cursor and then advances it), so "the record displaced from slot q" is the record
+// that started at q: the walk needs nothing but tags[] and the 256 cursors, and yields src[q] = original index of the
+// record that ends in slot q.  cnt = bin sizes, last = bin starts on entry (cursors, clobbered).  With the tags in
+// shared memory a step costs two shared-memory round trips instead of a dependent global load + store.
+template <class IT>
+MHB_HD void km_walk_src(const uint8_t *tags, u32 n, const u32 *cnt, u32 *last, IT *src) {
+  u32 begin = 0;
+  int i = 0;
+  for (; i < 256; ++i) {
+    const u32 end = begin + cnt[i];
+    if (end == n) break;  // kmsort.h:66-69
+    while (last[i] != end) {
+      u32 p = last[i];
+      u32 t = tags[p];
+      while (t != (u32)i) {  // :75-79
+        const u32 q = last[t]++;
+        src[q] = (IT)p;
+        p = q;
+        t = tags[p];
+      }
+      src[last[i]] = (IT)p;
+      ++last[i];
+    }
+    begin = end;
+  }
+  if (i < 256)
+    for (u32 q = last[i]; q < n; ++q) src[q] = (IT)q;  // the last populated bin: what is left stays where it is
+}
+
+MHB_HD bool km_less_mem(const u32 *x, const u32 *y, u32 nw) {
+  for (u32 j = 0; j < nw; ++j)
+    if (x[j] != y[j]) return x[j] < y[j];
+  return false;
+}
+
+// insert_sort_core (kmsort.h:22-35) on an index array: slot j holds record staged[idx[j]]
+template <class IT>
+MHB_HD void km_insertion_idx(const u32 *staged, u32 rw, IT *idx, u32 c, u32 nw) {
+  for (u32 i = 1; i < c; ++i) {
+    const IT cur = idx[i];
+    if (km_less_mem(staged + (u32)cur * rw, staged + (u32)idx[i - 1] * rw, nw)) {
+      idx[i] = idx[i - 1];
+      u32 j = i - 1;
+      while (j > 0 && km_less_mem(staged + (u32)cur * rw, staged + (u32)idx[j - 1] * rw, nw)) {
+        idx[j] = idx[j - 1];
+        --j;
+      }
+      idx[j] = cur;
+    }
+  }
+}
+
+// records a warp stages in shared memory for one range (8 KB of records)
+__host__ __device__ constexpr u32 km_wcap(int rw) { return 2048u / (u32)rw; }
+
 // ------------------------------------------------------------------------------------------------
 // Stage 1, Lv2Postprocess (read_to_sdbg_s1.cpp:368-555) for the (k-1)-mer group starting at record g0.
 // ------------------------------------------------------------------------------------------------
@@ -383,10 +439,25 @@ MHB_HD u64 s1_group(const u32 *recs, u64 n, u64 g0, u32 rw, u32 nw, u32 k, int m
 // Read2SdbgS2::Initialize, the mercy step (read_to_sdbg_s2.cpp:172-254) for one read: every (k+1)-mer between a
 // "no out" k-mer and the next "no in" k-mer with no solid k-mer in between becomes solid.  Reads the stage-1 bits,
 // writes `mercy` (OR-ed into is_solid afterwards: has_solid_kmer must see the stage-1 state only).  Returns the number added.
+// any bit set in [lo, hi)?
+MHB_HD bool bits_any(const u32 *bits, u64 lo, u64 hi) {
+  if (lo >= hi) return false;
+  const u64 w0 = lo >> 5, w1 = (hi - 1) >> 5;
+  for (u64 w = w0; w <= w1; ++w) {
+    u32 v = bits[w];
+    if (w == w0) v &= 0xFFFFFFFFu << (lo & 31);
+    if (w == w1 && ((hi & 31) != 0)) v &= 0xFFFFFFFFu >> (32 - (hi & 31));
+    if (v) return true;
+  }
+  return false;
+}
+
 MHB_HD u32 r2s_mercy_read(const PkgView &pv, u64 r, u32 k, const S1Out &o, u32 *mercy) {
   const u32 L = pv.L(r);
   if (L < k + 1) return 0;
   const u64 b = pv.base(r);
+  // most reads have no tip at all: two word-level looks instead of a walk over every position
+  if (!bits_any(o.no_out, b, b + L) || !bits_any(o.no_in, b, b + L)) return 0;
   int first_0_out = -1, last_0_in = -1;
   bool any = false;
   for (u32 i = 0; i + k <= L; ++i) {
@@ -533,11 +604,184 @@ MHB_HD u32 km_small_range(const u32 *bnd, u64 n, u64 i, u32 lim) {
 // marked range of more than 64 records with no mark inside went through every radix level as a single bin: all its
 // keys are equal.
 template <int RW>
-__global__ void __launch_bounds__(256) k_r2s_kmsort_finish(u32 *__restrict__ recs, u64 n, u32 nw, const u32 *__restrict__ bnd) {
+__global__ void __launch_bounds__(256) k_r2s_kmsort_finish(u32 *__restrict__ recs, u64 n, u32 nw, const u32 *__restrict__ bnd,
+                                                          const u32 *__restrict__ todo) {
   for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += (u64)gridDim.x * 256) {
-    if (!bit_at(bnd, i)) continue;
+    if (!bit_at(todo ? todo : bnd, i)) continue;  // todo: only the small ranges nobody has sorted yet
     const u32 len = km_small_range(bnd, n, i, (u32)kKmInsertThreshold);
     if (len >= 2) km_insertion<RW>(recs + i * RW, len, nw);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kmsort on shared memory (the default path; k_r2s_kmsort_level above remains the in-place form used for ranges that do
+// not fit).  Level 0: one CTA per bucket - tags + histogram by all threads (the bucket is contiguous), the walk by
+// thread 0 on shared-memory tags (km_walk_src), the records gathered into the second buffer by all threads.  Levels
+// >= 1: one WARP per range of at most km_wcap(RW) records staged in shared memory: tags, walk, the insertion sorts of
+// the children of 2..64 records (one lane per child, on the index array), write-back in place.
+// `todo` marks the small ranges nobody has sorted yet (k_r2s_kmsort_finish), `bnd` every range start.
+// ------------------------------------------------------------------------------------------------
+template <int RW>
+__global__ void __launch_bounds__(128) k_r2s_km_bucket(const u32 *__restrict__ in, u32 *__restrict__ out, const u64 *__restrict__ bstart,
+                                                      u32 nw, int kb, u32 cap, uint16_t *__restrict__ src_g, u32 *__restrict__ bnd,
+                                                      u32 *__restrict__ todo, KmSeg *__restrict__ next,
+                                                      unsigned long long *__restrict__ n_next, u64 next_cap) {
+  extern __shared__ uint8_t s_tags[];
+  __shared__ u32 s_cnt[256], s_last[256], s_beg[256];
+  const u32 tid = threadIdx.x;
+  const u64 start = bstart[blockIdx.x];
+  const u64 len64 = bstart[blockIdx.x + 1] - start;
+  if (len64 == 0) return;
+  const u32 *a = in + start * RW;
+  u32 *o = out + start * RW;
+  if (tid == 0) bit_or(bnd, start);
+  if (len64 <= (u64)kKmInsertThreshold) {
+    for (u32 w = tid; w < (u32)len64 * RW; w += 128) o[w] = a[w];
+    if (tid == 0 && len64 >= 2) bit_or(todo, start);
+    return;
+  }
+  if (len64 > (u64)cap || len64 > 65535ull) {  // does not fit: the in-place walk on global memory, then the copy
+    if (tid == 0) km_radix_range<RW>(const_cast<u32 *>(a), (u32)len64, nw, kb, s_cnt, s_last);
+    __syncthreads();
+    for (u64 w = tid; w < len64 * RW; w += 128) o[w] = a[w];
+  } else {
+    const u32 len = (u32)len64;
+    for (u32 i = tid; i < 256; i += 128) s_cnt[i] = 0;
+    __syncthreads();
+    for (u32 i = tid; i < len; i += 128) {
+      const u32 t = km_byte_mem(a + (u64)i * RW, nw, kb);
+      s_tags[i] = (uint8_t)t;
+      atomicAdd(&s_cnt[t], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      u32 acc = 0;
+      for (int i = 0; i < 256; ++i) {
+        s_last[i] = acc;
+        acc += s_cnt[i];
+      }
+      km_walk_src<uint16_t>(s_tags, len, s_cnt, s_last, src_g + start);
+    }
+    __syncthreads();
+    const uint16_t *src = src_g + start;
+    for (u32 q = tid; q < len; q += 128) {
+      u32 r[RW];
+      ld_rec<RW>(a, src[q], r);
+      st_rec<RW>(o, q, r);
+    }
+  }
+  if (tid == 0) {
+    u32 acc = 0;
+    for (int i = 0; i < 256; ++i) {
+      s_beg[i] = acc;
+      acc += s_cnt[i];
+    }
+  }
+  __syncthreads();
+  for (u32 b = tid; b < 256; b += 128) {
+    const u32 c = s_cnt[b];
+    if (!c) continue;
+    bit_or(bnd, start + s_beg[b]);
+    if (kb == 0) continue;  // kmsort.h:84 / :93: no level below byte 0
+    if (c > (u32)kKmInsertThreshold) {
+      const unsigned long long slot = atomicAdd(n_next, 1ull);
+      if (slot < next_cap) next[slot] = KmSeg{start + s_beg[b], c};
+    } else if (c >= 2) {
+      bit_or(todo, start + s_beg[b]);
+    }
+  }
+}
+
+static constexpr int kKmWarps = 8;
+template <int RW>
+__host__ __device__ constexpr size_t km_warp_smem() {  // per warp: staged records, index array, tags, 3 x 256 counters
+  return (size_t)km_wcap(RW) * RW * 4 + (size_t)km_wcap(RW) * 2 + (size_t)((km_wcap(RW) + 3) & ~3u) + 3 * 256 * 4;
+}
+
+template <int RW>
+__global__ void __launch_bounds__(kKmWarps * 32) k_r2s_km_warp(u32 *__restrict__ recs, u32 nw, int kb, const KmSeg *__restrict__ segs,
+                                                              u64 n_segs, KmSeg *__restrict__ next,
+                                                              unsigned long long *__restrict__ n_next, u64 next_cap,
+                                                              u32 *__restrict__ bnd, u32 *__restrict__ todo) {
+  constexpr u32 WCAP = km_wcap(RW);
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+  uint8_t *base = s_raw + (size_t)warp * km_warp_smem<RW>();
+  u32 *staged = reinterpret_cast<u32 *>(base);
+  u32 *cnt = staged + (size_t)WCAP * RW;
+  u32 *last = cnt + 256;
+  u32 *beg = last + 256;
+  uint16_t *src = reinterpret_cast<uint16_t *>(beg + 256);
+  uint8_t *tags = reinterpret_cast<uint8_t *>(src + WCAP);
+  for (u64 sg = (u64)blockIdx.x * kKmWarps + warp; sg < n_segs; sg += (u64)gridDim.x * kKmWarps) {
+    const u64 start = segs[sg].start;
+    const u32 len = (u32)segs[sg].len;
+    u32 *a = recs + start * RW;
+    __syncwarp();
+    const bool fits = len <= WCAP;
+    if (!fits) {
+      if (lane == 0) km_radix_range<RW>(a, len, nw, kb, cnt, last);  // in place on global memory, counters in shared
+      __syncwarp();
+    } else {
+      for (u32 w = lane; w < len * RW; w += 32) staged[w] = a[w];
+      for (u32 i = lane; i < 256; i += 32) cnt[i] = 0;
+      __syncwarp();
+      for (u32 i = lane; i < len; i += 32) {
+        const u32 t = km_byte_mem(staged + i * RW, nw, kb);
+        tags[i] = (uint8_t)t;
+        atomicAdd(&cnt[t], 1u);
+      }
+      __syncwarp();
+    }
+    {  // bin starts: 8 bins per lane + warp scan
+      u32 c8[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        c8[j] = cnt[lane * 8 + j];
+        sum += c8[j];
+      }
+      u32 inc = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const u32 v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (u32)d) inc += v;
+      }
+      u32 acc = inc - sum;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        beg[lane * 8 + j] = acc;
+        if (fits) last[lane * 8 + j] = acc;
+        acc += c8[j];
+      }
+    }
+    __syncwarp();
+    if (fits) {
+      if (lane == 0) km_walk_src<uint16_t>(tags, len, cnt, last, src);
+      __syncwarp();
+      if (kb > 0) {  // the children of 2..64 records: insertion sort on their slice of the index array
+        for (u32 b = lane; b < 256; b += 32) {
+          const u32 c = cnt[b];
+          if (c >= 2 && c <= (u32)kKmInsertThreshold) km_insertion_idx<uint16_t>(staged, RW, src + beg[b], c, nw);
+        }
+      }
+      __syncwarp();
+      for (u32 w = lane; w < len * RW; w += 32) {
+        const u32 q = w / RW, j = w - q * RW;
+        a[w] = staged[(u32)src[q] * RW + j];
+      }
+    }
+    for (u32 b = lane; b < 256; b += 32) {
+      const u32 c = cnt[b];
+      if (!c) continue;
+      bit_or(bnd, start + beg[b]);
+      if (kb == 0) continue;
+      if (c > (u32)kKmInsertThreshold) {
+        const unsigned long long slot = atomicAdd(n_next, 1ull);
+        if (slot < next_cap) next[slot] = KmSeg{start + beg[b], c};
+      } else if (c >= 2 && !fits) {
+        bit_or(todo, start + beg[b]);
+      }
+    }
   }
 }
 

@@ -114,7 +114,7 @@ SYMBOLS = [
     "mhb_mercy_candidates_scratch_bytes", "mhb_mercy_candidates", "mhb_mercy_edges_scratch_bytes", "mhb_mercy_edges", "mhb_mercy_edges_count", "mhb_mercy_edges_write", "mhb_mercy_edges_segs", "mhb_mercy_host", "mhb_mercy_planes_words", "mhb_mercy_probe_owned", "mhb_mercy_count_planes", "mhb_edge_lut_bytes", "mhb_edge_lut_build",
     "mhb_release", "mhb_count_run", "mhb_count_run_multi", "mhb_seq2sdbg_run", "mhb_selftest_count_record", "mhb_selftest_count_records_roll", "mhb_selftest_s2s_record",
     "mhb_s2s_extract_edges_pruned", "mhb_s2s_emit_fmt", "mhb_read2sdbg_host", "mhb_read2sdbg_run", "mhb_selftest_r2s_s1_record", "mhb_selftest_r2s_item",
-    "mhb_selftest_kmsort", "mhb_selftest_r2s_s1_group", "mhb_selftest_r2s_mercy_read",
+    "mhb_selftest_kmsort", "mhb_selftest_kmsort_smem", "mhb_selftest_r2s_s1_group", "mhb_selftest_r2s_mercy_read",
 ]
 
 
@@ -220,6 +220,7 @@ def load():
     L.mhb_selftest_r2s_item.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                         C.c_void_p, C.POINTER(C.c_uint32)]
     L.mhb_selftest_kmsort.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
+    L.mhb_selftest_kmsort_smem.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
     L.mhb_selftest_r2s_s1_group.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.c_uint32, C.c_uint64, C.c_int,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mhb_selftest_r2s_mercy_read.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -536,8 +537,12 @@ def selftest_r2s_item(pkg_words: np.ndarray, L_: int, k: int, i: int, strand: in
     return rec, pal.value
 
 
-def selftest_kmsort(recs: np.ndarray, nw: int) -> np.ndarray:
-    """kmlib::kmsort's permutation of one bucket (records of nw + 2 words), emulated level by level as on the device"""
+def selftest_kmsort(recs: np.ndarray, nw: int, smem: bool = False, cap: int = 65535, wcap: int = 0) -> np.ndarray:
+    """kmlib::kmsort's permutation of one bucket (records of nw + 2 words), emulated level by level as on the device:
+    the in-place walk on the records, or (smem) the walk on tags + staged ranges the default kernels use"""
     recs = np.ascontiguousarray(recs, np.uint32).copy()
-    _check(load().mhb_selftest_kmsort(recs.ctypes.data, len(recs), nw))
+    if smem:
+        _check(load().mhb_selftest_kmsort_smem(recs.ctypes.data, len(recs), nw, cap, wcap))
+    else:
+        _check(load().mhb_selftest_kmsort(recs.ctypes.data, len(recs), nw))
     return recs

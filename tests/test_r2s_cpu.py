@@ -99,6 +99,9 @@ def test_kmsort_emulation_matches_oracle(n, nw, distinct):
     want = oracle_kmsort(recs, nw)
     got = lib.selftest_kmsort(recs, nw)
     assert (got == want).all()
+    # the shared-memory form: default staging, tiny staged ranges (deep ranges take the in-place walk), tiny tag capacity
+    for cap, wcap in ((65535, 0), (65535, 70), (100, 0)):
+        assert (lib.selftest_kmsort(recs, nw, smem=True, cap=cap, wcap=wcap) == want).all(), (cap, wcap)
     assert not (got[:, nw + 1] == np.sort(got[:, nw + 1])).all() or n <= 64 or distinct == 1  # it is not the stable order
 
 
