@@ -313,7 +313,7 @@ def ours(args):
         M_items, W2 = int(n_items), s2s.W
         alg = {
             "extract": n_edges * S + bin_words * 4,                      # records written + packed reads read
-            "sort": (2 if plan.hashed else len(plan.sort_bytes)) * 2 * n_edges * S,
+            "sort": int(cpass.shape[1]) * 2 * n_edges * S,                     # the passes this step really ran
             "count": n_edges * S + E * (WE * 4 + 1),                     # sorted records read + edges and flags written
             "mercy": bin_words * 4,                                      # reads re-scanned against the tip set
             "s2s_extract": E * WE * 4 + M_items * W2 * 4,
@@ -327,8 +327,8 @@ def ours(args):
     except Exception as e:  # pragma: no cover
         stage_roofline = {"error": str(e)}
 
-    count_mode = ("hashed: 2 radix passes on the leading key bytes (the 16-bit bucket id) + per-bucket hash aggregation in "
-                  "shared memory" if plan.hashed else "sort: LSD radix sort on all key bytes + run-length count")
+    count_mode = (f"hashed: {int(cpass.shape[1])} radix passes on the leading key bytes (first one unstable) + per-slice hash "
+                  "aggregation in shared memory" if plan.hashed else "sort: LSD radix sort on all key bytes + run-length count")
     # ---- e2e: host buffers through the C ABI (fused build), H2D/D2H copies inside the timed region ----
     host_bin = torch.empty(bin_words, dtype=torch.int32).pin_memory()
     host_bin.copy_(bin_dev[:bin_words])
@@ -370,7 +370,7 @@ def ours(args):
         "data": "synthetic",
         "config": {"workload": f"synthetic {n_reads}x{L}bp reads (30x, 1% subst.), k={k}, m={m}, 1xB200 single-GPU "
                                "sdbg_build: count (extract + partition/sort + solid count + mercy marks) + mercy-edge "
-                               "generation + seq2sdbg (extract+radix+emit) over solid + mercy edges",
+                               "generation + seq2sdbg (extract+radix+emit) over solid + mercy edges; the seq2sdbg extract skips the $-items the count stage's in/out flags prove the emitter would discard (same bytes out)",
                    "count_mode": count_mode, "host_affinity": args.affinity,
                    "n_edge_records": n_edges, "n_solid_edges": int(n_solid), "n_sdbg_sort_items": int(n_items),
                    "l2_note": "inputs (>= 4.9 GB per kernel) exceed the 126 MB L2, no explicit flush needed"},
