@@ -974,9 +974,137 @@ extern "C" int mhb_s2s_host(const mhb_s2s_args *args, mhb_s2s_result *res) {
 // fused k_min build: count -> mercy edges -> seq2sdbg, device resident
 // ================================================================================================
 static int build_host_impl(const mhb_build_args *args, mhb_build_result *res, bool full_index);
+
+// A13 for the fused build: when the records of the whole library do not fit next to it in HBM (or a round cap is set),
+// the same graph is built stage by stage through the host-level calls that already work in rounds - count (rounds over
+// bucket ranges) -> mercy edges -> seq2sdbg (rounds over bucket ranges) - with the solid edges passing through host
+// memory once, as they do between the reference's two sub-commands (base_engine.cpp:54-141 plans its passes the same
+// way: the output does not depend on where the boundaries fall).
+static int build_host_rounds(const mhb_build_args *args, mhb_build_result *res) {
+  memset(res, 0, sizeof(*res));
+  const uint32_t k = args->k, WE = words_per_edge(k), NWE = div_ceil(k + 1, 16);
+  mhb_count_args ca;
+  memset(&ca, 0, sizeof(ca));
+  ca.k = k;
+  ca.m = args->m;
+  ca.bin = args->bin;
+  ca.bin_words = args->bin_words;
+  ca.n_reads = args->n_reads;
+  ca.want_mercy = args->need_mercy;
+  std::vector<char> cbuf(sizeof(mhb_count_result));
+  mhb_count_result *cr = reinterpret_cast<mhb_count_result *>(cbuf.data());
+  CKR(mhb_count_host(&ca, cr));
+  struct Owned {  // the count result's buffers, unless handed on to the caller
+    mhb_count_result *r;
+    ~Owned() {
+      free(r->edges);
+      free(r->cand_ids);
+    }
+  } owned{cr};
+  res->n_edge_records = cr->n_edge_records;
+  res->n_solid = cr->n_solid;
+  res->n_cand = cr->n_cand;
+  res->words_per_edge = WE;
+  res->words_per_tip_label = words_per_tip_label(k);
+  res->t_count_ms = cr->t_total_ms;
+  uint32_t *mercy = nullptr;
+  uint64_t n_mercy = 0;
+  if (args->need_mercy && cr->n_cand) {  // the `.cand` image: candidate reads reversed (kmer_counter.cpp:387-401)
+    std::vector<uint32_t> cand;
+    uint64_t r = 0;
+    size_t pos = 0;
+    for (uint64_t c = 0; c < cr->n_cand; ++c) {
+      while (r < cr->cand_ids[c]) {
+        pos += 1 + div_ceil(args->bin[pos], 16);
+        ++r;
+      }
+      const uint32_t L = args->bin[pos], nw = div_ceil(L, 16);
+      const size_t at = cand.size();
+      cand.resize(at + 1 + nw, 0u);
+      cand[at] = L;
+      for (uint32_t i = 0; i < L; ++i) cand[at + 1 + (i >> 4)] |= base_at(&args->bin[pos + 1], L - 1 - i) << (30 - 2 * (i & 15));
+    }
+    uint64_t n_cr = 0;
+    CKR(mhb_mercy_host(k, cr->edges, cr->n_solid, cand.data(), cand.size(), &mercy, &n_mercy, &n_cr));
+  }
+  struct FreeMercy {
+    uint32_t *&p;
+    ~FreeMercy() { free(p); }
+  } fm{mercy};
+  res->n_mercy = n_mercy;
+  // the edge (k+1)-mers as seq2sdbg loads them (seq_to_sdbg.cpp:424-450)
+  const uint64_t n_seqs = cr->n_solid + n_mercy;
+  std::vector<uint32_t> words((size_t)n_seqs * NWE + 1, 0u), len(n_seqs, k + 1);
+  std::vector<uint64_t> word_off(n_seqs + 1);
+  std::vector<uint16_t> mult(n_seqs);
+  const uint32_t tail = (k + 1) % 16;
+  for (uint64_t i = 0; i < n_seqs; ++i) {
+    const uint32_t *e = i < cr->n_solid ? cr->edges + i * WE : mercy + (i - cr->n_solid) * WE;
+    for (uint32_t j = 0; j < NWE; ++j) words[i * NWE + j] = e[j];
+    if (tail) words[i * NWE + NWE - 1] &= top_mask(2 * tail);
+    word_off[i] = i * NWE;
+    mult[i] = (uint16_t)(e[WE - 1] & 0xFFFFu);
+  }
+  word_off[n_seqs] = n_seqs * NWE;
+  mhb_s2s_args sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.k = k;
+  sa.words = words.data();
+  sa.word_off = word_off.data();
+  sa.len = len.data();
+  sa.mult = mult.data();
+  sa.n_seqs = n_seqs;
+  std::vector<char> sbuf(sizeof(mhb_s2s_result));
+  mhb_s2s_result *sr = reinterpret_cast<mhb_s2s_result *>(sbuf.data());
+  CKR(mhb_s2s_host(&sa, sr));
+  res->n_sort_items = sr->n_records;
+  res->n_items = sr->n_items;
+  res->n_tips = sr->n_tips;
+  res->n_large_mul = sr->n_large_mul;
+  res->n_bytes = sr->n_bytes;
+  for (int i = 0; i < 9; ++i) res->w_count[i] = sr->w_count[i];
+  res->ones_in_last = sr->ones_in_last;
+  res->t_s2s_ms = sr->t_total_ms;
+  res->bucket_table = (uint64_t *)malloc((size_t)MHB_NUM_BUCKETS * 32);
+  if (!res->bucket_table) {
+    free(sr->bytes);
+    return mhb_set_error(MHB_ERR_NOMEM, "host malloc failed");
+  }
+  memcpy(res->bucket_table, sr->bucket_table, (size_t)MHB_NUM_BUCKETS * 32);
+  if (args->sdbg_out && args->sdbg_out_capacity >= sr->n_bytes) {
+    if (sr->n_bytes) memcpy(args->sdbg_out, sr->bytes, sr->n_bytes);
+    free(sr->bytes);
+    res->bytes = args->sdbg_out;
+  } else {
+    res->bytes = sr->bytes;
+  }
+  if (args->want_edges) {
+    res->counting = (int64_t *)malloc(65536 * 8);
+    if (!res->counting) return mhb_set_error(MHB_ERR_NOMEM, "host malloc failed");
+    memcpy(res->counting, cr->counting, 65536 * 8);
+    res->edges = cr->edges;
+    res->cand_ids = cr->cand_ids;
+    cr->edges = nullptr;
+    cr->cand_ids = nullptr;
+  }
+  res->t_total_ms = res->t_count_ms + res->t_s2s_ms;
+  return MHB_OK;
+}
+
 extern "C" int mhb_build_host(const mhb_build_args *args, mhb_build_result *res) {
   if (!args || !res) return mhb_set_error(MHB_ERR_ARG, "null args");
-  return build_host_impl(args, res, false);
+  if (g_round_limit || g_s2s_round_limit) return build_host_rounds(args, res);  // explicit caps (tests, small devices)
+  const int rc = build_host_impl(args, res, false);
+  if (rc == MHB_ERR_NOMEM) {  // everything resident does not fit: the staged build, whose stages plan their own rounds
+    mhb_free(res->bytes == args->sdbg_out ? nullptr : res->bytes);
+    mhb_free(res->bucket_table);
+    mhb_free(res->edges);
+    mhb_free(res->cand_ids);
+    mhb_free(res->counting);
+    mhb_release();
+    return build_host_rounds(args, res);
+  }
+  return rc;
 }
 static int build_host_impl(const mhb_build_args *args, mhb_build_result *res, bool full_index) {
   memset(res, 0, sizeof(*res));

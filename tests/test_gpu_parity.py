@@ -202,6 +202,34 @@ def test_fused_build_matches_reference(name, k, m, gold):
     assert F.sha256(lib.sdbg_stream_from_table(g["bucket_table"], g["bytes"])) == gold["sdbg_sha256"]
 
 
+@pytest.mark.parametrize("name,k", [("syn150_k27", 27), ("toy_k21", 21), ("lowcov_k21", 21), ("synvar_k21_m3", 21), ("syn150_klist", 59)])
+def test_fused_build_in_rounds_matches_reference(name, k):
+    """A13 for the fused build: with round caps set (or when the resident plan does not fit) mhb_build_host runs count ->
+    mercy edges -> seq2sdbg stage by stage, each in rounds over bucket ranges; same edges / `.cand` / SdBG bytes"""
+    gold_case = [c for c in golden_cases() if c.id == f"{name}-k{k}"][0]
+    m, gold = gold_case.values[2], gold_case.values[3]
+    case = os.path.join(GOLDEN, name)
+    bin_words = np.fromfile(os.path.join(case, "reads.lib.bin"), np.uint32)
+    _, n_reads = F.read_lib_info(os.path.join(case, "reads.lib"))
+    one = lib.build_host(bin_words, n_reads, k, m, need_mercy=True)
+    lib.set_round_limit(max(1, int(one["n_edge_records"]) // 4))
+    lib.set_s2s_round_limit(max(1, int(one["n_solid"] + one["n_mercy"]) * 6 // 4))
+    try:
+        try:
+            g = lib.build_host(bin_words, n_reads, k, m, need_mercy=True, want_edges=True)
+        except lib.MhbError as e:  # a single bucket above the cap is reported, never mis-sorted
+            assert "round" in str(e)
+            return
+    finally:
+        lib.set_round_limit(0)
+        lib.set_s2s_round_limit(0)
+    assert g["n_solid"] == gold["n_solid"] and g["n_mercy"] == one["n_mercy"]
+    if gold["n_solid"]:
+        assert F.sha256(g["edges"].tobytes()) == gold["edges_sha256"]
+    assert g["n_items"] == gold["sdbg_items"] and g["n_tips"] == gold["sdbg_tips"]
+    assert F.sha256(lib.sdbg_stream_from_table(g["bucket_table"], g["bytes"])) == gold["sdbg_sha256"]
+
+
 def test_fused_build_into_caller_buffer():
     case = os.path.join(GOLDEN, "syn150_k27")
     gold = [c for c in golden_cases() if c.id == "syn150_k27-k27"][0].values[3]
