@@ -229,7 +229,8 @@ def ours(args):
 
     plan = dev.CountPlan(n_reads, L, k, m, device, want_mercy=True, mode=args.count_mode)
     n_solid = plan.run(bin_dev)  # sizes the SdBG stage (also the first warm-up)
-    s2s = dev.S2sPlan(int(n_solid * 1.05) + 1024, k + 1, k, device)
+    n_mercy0 = plan.mercy_edges(bin_dev, n_solid)  # wide k: far more than a few per cent of the solid edges
+    s2s = dev.S2sPlan(int((n_solid + n_mercy0) * 1.05) + 1024, k + 1, k, device)
 
     mercy_ev = []
 
