@@ -483,96 +483,6 @@ static __global__ void __launch_bounds__(256)
 }
 
 
-// The same kernel with a FOLDED copy of the bit filter in shared memory in front of the global one.  The global filter
-// (32 bits per tip edge, ~2 MB on the bench workload) lives in L2, and one probe per (k+1)-mer - 1.23 G random 4-byte
-// L2 loads - is what the kernel waits for (97 % L2 hits, 6.5 ms).  A CTA ORs the filter down to 2^20 bits (128 KB; bit
-// b of the fold = OR of the global bits congruent to b), a probe looks there first and goes to L2 only when the folded
-// bit is set - a quarter of the probes with 0.3 M tip edges.  Same marks bit for bit (the fold can only add false
-// positives, which the global filter and the table then reject).
-static constexpr u32 kMercyFoldBits = 1u << 20;
-static __global__ void __launch_bounds__(1024)
-    k_mark_mercy_roll_fold(ReadsView rv, u32 k, const u32 *__restrict__ filter, u64 filter_words, const u32 *__restrict__ table,
-                           u64 cap, u32 *first_0_out, u32 *last_0_in) {
-  constexpr int W = 2;
-  extern __shared__ u32 s_fold[];
-  const u32 lane = lane_id();
-  const u32 K1 = k + 1;
-  const u32 fmask = (u32)(filter_words * 32 - 1);
-  const u32 swords = filter_words < (u64)(kMercyFoldBits / 32) ? (u32)filter_words : kMercyFoldBits / 32;
-  const u32 smask = swords * 32 - 1;
-  for (u32 i = threadIdx.x; i < swords; i += 1024) s_fold[i] = 0;
-  __syncthreads();
-  for (u64 i = threadIdx.x; i < filter_words; i += 1024) {
-    const u32 v = filter[i];
-    if (v) atomicOr(&s_fold[i & (swords - 1)], v);
-  }
-  __syncthreads();
-  for (u64 r = (u64)blockIdx.x * 32 + (threadIdx.x >> 5); r < rv.n_reads; r += (u64)gridDim.x * 32) {
-    const u32 *rec0 = rv.bin + rv.rec_start(r);
-    const u32 L = rec0[0];
-    const u32 *s = rec0 + 1;
-    const u32 nwords = div_ceil(L, 16);
-    u32 first = 0xFFFFFFFFu;
-    long long last = -1;
-    if (L >= K1) {
-      const u32 n_e = L - k;
-      for (u32 q0 = 0; q0 < n_e; q0 += 128) {
-        const u32 q = q0 + 4 * lane;
-        u32 key[4][W], strand[4] = {0, 0, 0, 0}, fw[4] = {0, 0, 0, 0}, h[4] = {0, 0, 0, 0};
-        bool live[4] = {false, false, false, false};
-        if (q < n_e) {
-          u64 rec[4];
-          make_count_records_roll<4>(s, nwords, L, k, q, rec, strand);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            live[u] = q + u < n_e;
-            key[u][0] = (u32)(rec[u] >> 32);
-            key[u][1] = (u32)rec[u] & ~63u;
-            if (live[u]) {
-              h[u] = hash_key<W>(key[u]);
-              const u32 hb = hash2(h[u]);
-              if ((s_fold[(hb & smask) >> 5] >> (hb & 31)) & 1u) fw[u] = filter[(hb & fmask) >> 5];
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (!live[u] || !((fw[u] >> (hash2(h[u]) & 31)) & 1u)) continue;
-          u64 slot = h[u] & (cap - 1);
-          u32 flags = 0;
-          while (true) {
-            const u32 *e = table + slot * (W + 1);
-            const u32 f = e[0];
-            if (f == 0) break;
-            if (e[1] == key[u][0] && e[2] == key[u][1]) {
-              flags = f;
-              break;
-            }
-            slot = (slot + 1) & (cap - 1);
-          }
-          if (flags) {
-            const u32 off = L - K1 - (q + u);
-            const bool to_last = ((flags & 1u) && strand[u] == 0) || ((flags & 2u) && strand[u] == 1);
-            const bool to_first = ((flags & 1u) && strand[u] == 1) || ((flags & 2u) && strand[u] == 0);
-            if (to_last) last = last > (long long)off ? last : (long long)off;
-            if (to_first) first = first < off + 1 ? first : off + 1;
-          }
-        }
-      }
-    }
-    for (int d = 16; d; d >>= 1) {
-      const u32 f2 = __shfl_xor_sync(0xffffffffu, first, d);
-      const long long l2 = __shfl_xor_sync(0xffffffffu, last, d);
-      first = first < f2 ? first : f2;
-      last = last > l2 ? last : l2;
-    }
-    if (lane == 0) {
-      first_0_out[r] = first;
-      last_0_in[r] = last < 0 ? 0xFFFFFFFFu : (u32)last;
-    }
-  }
-}
-
 }  // namespace mhb
 
 namespace mhb {

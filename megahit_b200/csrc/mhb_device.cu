@@ -357,19 +357,6 @@ extern "C" int mhb_count_mark_mercy(void *stream, const mhb_dev_reads *reads, ui
   // (profiles/r2a_bench_roll.json); MHB_EXTRACT_ROLL=0 selects the per-position kernel
   static const bool roll = !(getenv("MHB_EXTRACT_ROLL") && !strcmp(getenv("MHB_EXTRACT_ROLL"), "0"));
   if (roll && W == 2 && WR == 2 && k + 1 >= 17) {
-    // folded copy of the bit filter in shared memory in front of the L2-resident one (MHB_MERCY_FOLD=0: without)
-    static const bool fold = !(getenv("MHB_MERCY_FOLD") && !strcmp(getenv("MHB_MERCY_FOLD"), "0"));
-    if (fold && rv.n_reads >= 4096) {
-      const u64 sw = fwords < (u64)(kMercyFoldBits / 32) ? fwords : (u64)(kMercyFoldBits / 32);
-      static bool attr = false;
-      if (!attr) {
-        CK(cudaFuncSetAttribute(k_mark_mercy_roll_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMercyFoldBits / 8)));
-        attr = true;
-      }
-      k_mark_mercy_roll_fold<<<sm_count(), 1024, (size_t)sw * 4, st>>>(rv, k, filter, fwords, table, cap, first_0_out, last_0_in);
-      CK_LAUNCH();
-      return MHB_OK;
-    }
     k_mark_mercy_roll<<<grid, 256, 0, st>>>(rv, k, filter, fwords, table, cap, first_0_out, last_0_in);
     CK_LAUNCH();
     return MHB_OK;
