@@ -42,8 +42,16 @@ struct DevBuf {  // cudaMalloc'ed scratch released on scope exit
     bytes = b;
     return MHB_OK;
   }
+  // keep the allocation when it is already large enough (the two stages share their big buffers)
+  int ensure(size_t b, const char *what) { return bytes >= b ? MHB_OK : alloc(b, what); }
   template <class T>
   T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// the record / item ping-pong buffers and the sort workspace, shared by stage 1 and stage 2 (cudaMalloc + cudaFree of
+// 20-GB buffers between the stages cost ~0.2 s at 10 M reads)
+struct BigBufs {
+  DevBuf a, b, ws;
 };
 
 #define CKR(call)        \
@@ -174,18 +182,19 @@ int upload(DevBuf &d, const std::vector<T> &v, const char *what) {
 
 // ---- stage 1 on the device: is_solid bits, mercy planes, multiplicity histogram ----
 int run_stage1(cudaStream_t st, const PkgView &pv, const PkgIndex &ix, uint32_t k, int32_t m, bool need_mercy, const S1Out &out,
-               unsigned long long *d_mul_hist, PhaseTrace &tr) {
+               unsigned long long *d_mul_hist, PhaseTrace &tr, BigBufs &big, size_t min_rec_bytes, size_t min_ws_bytes) {
   const uint32_t NW = r2s_s1_key_words(k), RW = NW + 2;
   const uint64_t n = ix.n_s1;
   if (n == 0) return MHB_OK;
   if (RW > 17)
     return mhb_set_error(MHB_ERR_ARG, "read2sdbg: stage 1 supports k <= 237 (record of %u words > 17)", RW);
   if (n >= (1ull << 40)) return mhb_set_error(MHB_ERR_ARG, "read2sdbg: too many stage-1 records for one round");
-  DevBuf a, b, ws, bstart, segs0, segs1, counter, bnd;
+  DevBuf bstart, segs0, segs1, counter, bnd;
+  DevBuf &a = big.a, &b = big.b, &ws = big.ws;
   const size_t rec_bytes = (size_t)n * RW * 4 + 16, ws_bytes = mhb_sort_workspace_bytes(n, RW);
-  CKR(a.alloc(rec_bytes, "stage-1 records"));
-  CKR(b.alloc(rec_bytes, "stage-1 records (sort buffer)"));
-  CKR(ws.alloc(ws_bytes, "sort workspace"));
+  CKR(a.ensure(std::max(rec_bytes, min_rec_bytes), "records"));
+  CKR(b.ensure(std::max(rec_bytes, min_rec_bytes), "records (sort buffer)"));
+  CKR(ws.ensure(std::max(ws_bytes, min_ws_bytes), "sort workspace"));
   CKR(bstart.alloc((MHB_NUM_BUCKETS + 1) * 8, "bucket bounds"));
   const uint64_t seg_cap = n / (kKmInsertThreshold + 1) + 2;
   CKR(segs0.alloc(seg_cap * sizeof(KmSeg), "kmsort ranges"));
@@ -213,7 +222,7 @@ int run_stage1(cudaStream_t st, const PkgView &pv, const PkgIndex &ix, uint32_t 
   KmSeg *cur = segs0.as<KmSeg>(), *nxt = segs1.as<KmSeg>();
   unsigned long long *d_cnt = counter.as<unsigned long long>();
   CK(cudaMemsetAsync(d_cnt, 0, 8, st));
-  static const bool km_global = getenv("MHB_R2S_KMSORT_GLOBAL") != nullptr;  // the in-place form of every level (A/B)
+  const bool km_global = getenv("MHB_R2S_KMSORT_GLOBAL") != nullptr;  // the in-place form of every level (A/B, tests)
   static char level_names[72][24];
   int level = 0;
   DevBuf todo, src16;
@@ -227,6 +236,7 @@ int run_stage1(cudaStream_t st, const PkgView &pv, const PkgIndex &ix, uint32_t 
     for (int i = 0; i < MHB_NUM_BUCKETS; ++i) max_bucket = std::max(max_bucket, h_b[i + 1] - h_b[i]);
     uint32_t cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(max_bucket, 1024), 65535);
     cap = (cap + 1023) & ~1023u;
+    if (const char *e = getenv("MHB_R2S_KM_CAP")) cap = std::max(1024u, (uint32_t)atoi(e) & ~1023u);  // tests: force the fall-back
     CKR(todo.alloc((n / 32 + 2) * 4, "unsorted-range marks"));
     CK(cudaMemsetAsync(todo.p, 0, (n / 32 + 2) * 4, st));
     CKR(src16.alloc((size_t)n * 2 + 64, "kmsort source indices"));
@@ -376,6 +386,7 @@ extern "C" int mhb_read2sdbg_host(const mhb_build_args *args, mhb_build_result *
   CK(cudaMemsetAsync(d_cnt.p, 0, 64, st));
   unsigned long long *d_counter = d_cnt.as<unsigned long long>();
   const bool mercy = args->need_mercy && m > 1;
+  BigBufs big;
   if (m > 1 && ix.n_s1) {
     S1Out so;
     memset(&so, 0, sizeof(so));
@@ -387,7 +398,11 @@ extern "C" int mhb_read2sdbg_host(const mhb_build_args *args, mhb_build_result *
       so.no_out = so.no_in + bit_words;
       so.any = so.no_out + bit_words;
     }
-    CKR(run_stage1(st, pv, ix, k, m, mercy, so, d_hist.as<unsigned long long>(), tr));
+    // size the shared buffers for stage 2 as well: ~1.6 items per edge position on a 30x library, 2.2 to be safe
+    // (stage 2 reallocates when its count launch says more)
+    const uint64_t est_items = (uint64_t)(2.2 * (double)ix.n_edges) + 1024;
+    CKR(run_stage1(st, pv, ix, k, m, mercy, so, d_hist.as<unsigned long long>(), tr, big, (size_t)est_items * W * 4 + 16,
+                   mhb_sort_workspace_bytes(est_items, W)));
     if (mercy) {  // Read2SdbgS2::Initialize, read_to_sdbg_s2.cpp:117-263
       u32 *d_mercy = so.any + bit_words;
       k_r2s_mercy<<<grid_for(ix.n_reads, 256), 256, 0, st>>>(pv, k, so, d_mercy, d_counter + 1);
@@ -429,11 +444,12 @@ extern "C" int mhb_read2sdbg_host(const mhb_build_args *args, mhb_build_result *
   if (n_items == 0) {
     res->bytes = args->sdbg_out ? args->sdbg_out : (uint8_t *)malloc(1);
   } else {
-    DevBuf a, b, ws, heads, tile_heads, tile_off, bsum, scr, d_bytes;
+    DevBuf heads, tile_heads, tile_off, bsum, scr, d_bytes;
+    DevBuf &a = big.a, &b = big.b, &ws = big.ws;
     const size_t rec_bytes = (size_t)n_items * W * 4 + 16, ws_bytes = mhb_sort_workspace_bytes(n_items, W);
-    CKR(a.alloc(rec_bytes, "stage-2 items"));
-    CKR(b.alloc(rec_bytes, "stage-2 items (sort buffer)"));
-    CKR(ws.alloc(ws_bytes, "sort workspace"));
+    CKR(a.ensure(rec_bytes, "stage-2 items"));
+    CKR(b.ensure(rec_bytes, "stage-2 items (sort buffer)"));
+    CKR(ws.ensure(ws_bytes, "sort workspace"));
     CK(cudaMemsetAsync(d_counter, 0, 8, st));
 #define M(WW)                                                                                                          \
   if (W == WW)                                                                                                         \

@@ -55,6 +55,23 @@ def test_read2sdbg_host_matches_reference(gold):
     assert F.sha256(lib.sdbg_stream_from_table(g["bucket_table"], g["bytes"])) == gold["sdbg_sha256"]
 
 
+@pytest.mark.parametrize("env", [{"MHB_R2S_KMSORT_GLOBAL": "1"}, {"MHB_R2S_KM_CAP": "1024"}])
+@pytest.mark.parametrize("lib_name", ["synth:deep", "synth:mid", "golden/polya_k27"])
+def test_read2sdbg_kmsort_fallback_paths(lib_name, env):
+    """the in-place walk on global memory - as the whole sort (MHB_R2S_KMSORT_GLOBAL) and as the per-bucket fall-back of
+    the shared-memory form for buckets that exceed the tag capacity of a CTA (forced by a tiny capacity)"""
+    gold = [r for r in R2S["runs"] if r["lib"] == lib_name and r["k"] == 27 and r["m"] == 2 and r["mercy"] == 1][0]
+    data = r2s_reads(lib_name)
+    os.environ.update(env)
+    try:
+        g = lib.read2sdbg_host(np.frombuffer(data, np.uint32), n_reads_of(lib_name, data), 27, 2, True)
+    finally:
+        for k_ in env:
+            del os.environ[k_]
+    assert g["n_mercy"] == gold["n_mercy"] and F.sha256(O.counting_text(g["counting"])) == gold["counting_sha256"]
+    assert F.sha256(lib.sdbg_stream_from_table(g["bucket_table"], g["bytes"])) == gold["sdbg_sha256"]
+
+
 def test_read2sdbg_matches_oracle_tables():
     """bucket table / w counts / ones, which the digests do not cover"""
     data = r2s_reads("golden/syn150_k27")
