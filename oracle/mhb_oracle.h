@@ -87,6 +87,12 @@ int mhbo_unpack_bin(const uint8_t *bin, uint64_t bin_bytes, int reverse, uint64_
 int mhbo_read2sdbg(const mhbo_seqs *reads, uint32_t k, int32_t m, int need_mercy, mhbo_sdbg_out *out, int64_t *counting,
                    uint64_t *n_mercy_out, uint8_t **is_solid_out, uint64_t *n_bases_out);
 
+/* `megahit_core iterate` (main_iterate.cpp, iterate/contig_flank_index.h, iterate/kmer_collector.h): the iterative
+ * edges for k + step from contigs (flag-filtered, file orientation) and reads (file orientation); ascending unique
+ * `.edges` records with multiplicity 0 (mhb_oracle_iter.c).  *n_aligned_out = reads that produced at least one edge. */
+int mhbo_iterate(const mhbo_seqs *contigs, const mhbo_seqs *reads, uint32_t k, uint32_t step, uint32_t **edges_out,
+                 uint64_t *n_edges_out, uint64_t *n_aligned_out);
+
 /* pieces of the read2sdbg restatement, exported so that the CPU tests can check the device code's __host__ __device__
  * building blocks one by one */
 unsigned mhbo_s1_read_records(const uint32_t *w, unsigned L, unsigned k, uint64_t base_off, uint32_t *out);

@@ -231,3 +231,18 @@ def read2sdbg(reads: Seqs, k: int, m: int, need_mercy: bool, want_solid: bool = 
         L.mhbo_free(solid)
     L.mhbo_sdbg_free(C.byref(out))
     return res
+
+
+def iterate(contigs: Seqs, reads: Seqs, k: int, step: int):
+    """`megahit_core iterate` on the oracle: ascending unique `.edges` records (multiplicity 0) for k + step."""
+    L = lib()
+    L.mhbo_iterate.restype = C.c_int
+    ptr = C.POINTER(C.c_uint32)()
+    ne, na = C.c_uint64(), C.c_uint64()
+    cs, rs = contigs.c(), reads.c()
+    rc = L.mhbo_iterate(C.byref(cs), C.byref(rs), C.c_uint32(k), C.c_uint32(step), C.byref(ptr), C.byref(ne), C.byref(na))
+    assert rc == 0, rc
+    W = (2 * (k + step + 1) + 16 + 31) // 32
+    res = np.ctypeslib.as_array(ptr, (max(ne.value, 1) * W,))[: ne.value * W].reshape(-1, W).copy()
+    L.mhbo_free(ptr)
+    return res, na.value
