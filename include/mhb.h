@@ -437,6 +437,37 @@ int mhb_build_host(const mhb_build_args *args, mhb_build_result *res);
  * Stage 1 handles k <= 237 (records of at most 17 words); larger k with m > 1 returns MHB_ERR_ARG. */
 int mhb_read2sdbg_host(const mhb_build_args *args, mhb_build_result *res);
 
+/* `megahit_core iterate` (main_iterate.cpp:117-221, iterate/contig_flank_index.h:16-221,
+ * iterate/kmer_collector.h:37-79): the iterative edges for k + step - every (k+step+1)-mer of a read whose step+1
+ * consecutive (k+1)-mers are all covered by contig flanks or their matched extensions - as ascending, unique `.edges`
+ * records of mhb_words_per_edge(k + step) words with multiplicity 0 (the reference stores none: FlankInfo::mul is never
+ * filled in; it writes the same set in hash-table order).  contigs: word-aligned 2-bit sequences in FILE orientation,
+ * already filtered as AsyncContigReader does (contigs flagged kStandalone / kLoop discarded, async_sequence_reader.h:87);
+ * bin: the read library image (`.bin`, file orientation, async_sequence_reader.h:51).  step even, 2 .. 28
+ * (main_iterate.cpp:86); k + 1 <= 240 (flank records of at most 17 words).  res->edges: malloc'ed (mhb_free). */
+typedef struct {
+  uint32_t k, step;
+  const uint32_t *contig_words;
+  const uint64_t *contig_word_off; /* n_contigs + 1 */
+  const uint32_t *contig_len;      /* n_contigs */
+  uint64_t n_contigs;
+  const uint32_t *bin;
+  uint64_t bin_words;
+  uint64_t n_reads;
+} mhb_iterate_args;
+
+typedef struct {
+  uint64_t n_flanks;        /* distinct flank (k+1)-mers in the index */
+  uint64_t n_aligned_reads; /* reads that yielded at least one edge */
+  uint64_t n_candidates;    /* edges before the set semantics of KmerCollector */
+  uint64_t n_edges;
+  uint32_t words_per_edge;
+  uint32_t *edges;
+  double t_total_ms;
+} mhb_iterate_result;
+
+int mhb_iterate_host(const mhb_iterate_args *args, mhb_iterate_result *res);
+
 /* A11 from host buffers (SeqToSdbg::GenMercyEdges, seq_to_sdbg.cpp:171-357, as `seq2sdbg --need_mercy` runs it between
  * loading `.edges` / `.cand` and the sort): edges = n_edges sorted `.edges`-format records, cand_bin = the `.cand` image
  * (`.bin` record format, reads in the reversed orientation KmerCounter wrote them, kmer_counter.cpp:387-401).
@@ -488,8 +519,21 @@ typedef struct {
   int32_t need_mercy;
 } mhb_read2sdbg_opts;
 
+/* main_iterate options (main_iterate.cpp:57-72) */
+typedef struct {
+  const char *contig_file;
+  const char *bubble_file;
+  const char *read_file; /* the read library's `.bin` */
+  int32_t num_cpu_threads;
+  uint32_t k;
+  uint32_t step;
+  const char *output_prefix;
+} mhb_iterate_opts;
+
 int mhb_count_run(const mhb_count_opts *opts);
 int mhb_seq2sdbg_run(const mhb_seq2sdbg_opts *opts);
+/* writes P.edges.0 (ascending, unlike the reference's hash-table order) and P.edges.info (`is_sorted 0`, num_buckets 0) */
+int mhb_iterate_run(const mhb_iterate_opts *opts);
 /* writes P.sdbg.0, P.sdbg_info, P.counting (m > 1) and the (empty) P.mercy_cand.<i> temp files of the reference */
 int mhb_read2sdbg_run(const mhb_read2sdbg_opts *opts);
 
@@ -529,6 +573,8 @@ int mhb_selftest_kmsort_smem(uint32_t *recs, uint64_t n, uint32_t nw, uint32_t c
 int mhb_selftest_r2s_s1_group(const uint32_t *recs, uint64_t n, uint32_t k, int32_t m, uint32_t fixed_len, uint64_t n_reads,
                               int need_mercy, uint32_t *is_solid, uint32_t *no_in, uint32_t *no_out, uint32_t *any,
                               int64_t *counting);
+/* `iterate` with the device code's __host__ __device__ building blocks driven serially on the host (CPU tests only) */
+int mhb_selftest_iterate(const mhb_iterate_args *args, mhb_iterate_result *res);
 int mhb_selftest_r2s_mercy_read(uint32_t fixed_len, uint64_t n_reads, uint64_t r, uint32_t k, const uint32_t *is_solid,
                                 const uint32_t *no_in, const uint32_t *no_out, const uint32_t *any, uint32_t *mercy,
                                 uint32_t *added_out);

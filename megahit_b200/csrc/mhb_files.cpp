@@ -198,7 +198,7 @@ int write_edges(const std::string &prefix, uint32_t k, const uint32_t *edges, ui
 // contigs (contig_reader.h:52-119): FASTA with "flag=F multi=M len=N" comments
 // ------------------------------------------------------------------------------------------------
 int read_contigs(const std::string &path, uint32_t min_len, uint32_t k_from, uint32_t k_to, bool reverse,
-                 HostSeqs *out, int64_t *n_read) {
+                 HostSeqs *out, int64_t *n_read, unsigned discard_flag = 0) {
   *n_read = 0;
   FILE *f = fopen(path.c_str(), "rb");
   if (!f) return MHB_OK;  // the reference opens a missing file as an empty stream
@@ -223,6 +223,7 @@ int read_contigs(const std::string &path, uint32_t min_len, uint32_t k_from, uin
     const size_t sp = header.find_first_of(" \t");
     const std::string comment = sp == std::string::npos ? "" : header.substr(header.find_first_not_of(" \t", sp));
     const unsigned flag = comment.size() > 5 ? (unsigned)(comment[5] - '0') : 0u;
+    if (discard_flag & flag) return;  // contig_reader.h:66-69
     const double m = comment.size() > 13 ? atof(comment.c_str() + 13) : 0.0;
     const uint16_t mult = (uint16_t)(int32_t)(m + .5);
     if (extend_loop && (flag & 2u)) {  // contig_flag::kLoop, contig_reader.h:73-86
@@ -516,5 +517,70 @@ extern "C" int mhb_read2sdbg_run(const mhb_read2sdbg_opts *o) {
   mhb_free(res.bytes);
   mhb_free(res.bucket_table);
   mhb_free(res.counting);
+  return rc;
+}
+
+// ================================================================================================
+// iterate (main_iterate, main_iterate.cpp:196-221)
+// ================================================================================================
+extern "C" int mhb_iterate_run(const mhb_iterate_opts *o) {
+  auto S = [](const char *s) { return std::string(s ? s : ""); };
+  if (!o) return mhb_set_error(MHB_ERR_ARG, "null options");
+  const std::string contig = S(o->contig_file), bubble = S(o->bubble_file), reads = S(o->read_file), prefix = S(o->output_prefix);
+  if (contig.empty()) return mhb_set_error(MHB_ERR_ARG, "No contig file!");
+  if (bubble.empty()) return mhb_set_error(MHB_ERR_ARG, "No bubble file!");
+  if (reads.empty()) return mhb_set_error(MHB_ERR_ARG, "No reads file!");
+  if (o->k == 0) return mhb_set_error(MHB_ERR_ARG, "Invalid kmer size!");
+  if (o->step == 0 || o->step > 28 || (o->step & 1)) return mhb_set_error(MHB_ERR_ARG, "Invalid step size!");
+  if (prefix.empty()) return mhb_set_error(MHB_ERR_ARG, "No output prefix!");
+  const double t0 = now_s();
+  // the flank index reads contigs and bubbles in file orientation, without the standalone and loop ones
+  // (async_sequence_reader.h:82-101: SetDiscardFlag(kLoop | kStandalone), reverse = false)
+  HostSeqs seqs;
+  int64_t nr = 0;
+  if (int rc = read_contigs(contig, 0, 0, 0, false, &seqs, &nr, 3u)) return rc;
+  XINFO("Read %lld contigs\n", (long long)nr);
+  if (int rc = read_contigs(bubble, 0, 0, 0, false, &seqs, &nr, 3u)) return rc;
+  XINFO("Read %lld contigs\n", (long long)nr);
+  std::vector<uint32_t> bin;
+  if (!read_file(reads, &bin)) return MHB_ERR_IO;
+  uint64_t n_reads = 0;
+  for (size_t pos = 0; pos < bin.size(); ++n_reads) pos += 1 + div_ceil(bin[pos], 16);  // binary_reader.h:23-53
+  mhb_iterate_args a;
+  memset(&a, 0, sizeof(a));
+  a.k = o->k;
+  a.step = o->step;
+  if (seqs.words.empty()) seqs.words.push_back(0);
+  a.contig_words = seqs.words.data();
+  a.contig_word_off = seqs.word_off.data();
+  a.contig_len = seqs.len.data();
+  a.n_contigs = seqs.size();
+  a.bin = bin.data();
+  a.bin_words = bin.size();
+  a.n_reads = n_reads;
+  mhb_iterate_result res;
+  if (int rc = mhb_iterate_host(&a, &res)) return rc;
+  XINFO("Number of flank kmers: %llu\n", (unsigned long long)res.n_flanks);
+  XINFO("Total: %llu, aligned: %llu. Iterative edges: %llu\n", (unsigned long long)n_reads,
+        (unsigned long long)res.n_aligned_reads, (unsigned long long)res.n_edges);
+  int rc = MHB_OK;
+  FILE *f = fopen((prefix + ".edges.0").c_str(), "wb");
+  if (!f) rc = mhb_set_error(MHB_ERR_IO, "cannot open %s.edges.0 for writing", prefix.c_str());
+  else {
+    if (res.n_edges && fwrite(res.edges, 4 * (size_t)res.words_per_edge, res.n_edges, f) != res.n_edges)
+      rc = mhb_set_error(MHB_ERR_IO, "write to %s.edges.0 failed", prefix.c_str());
+    fclose(f);
+  }
+  if (!rc) {  // edge_writer.h:94-99 / edge_io_meta.h:25-44, unordered
+    FILE *g = fopen((prefix + ".edges.info").c_str(), "w");
+    if (!g) rc = mhb_set_error(MHB_ERR_IO, "cannot open %s.edges.info for writing", prefix.c_str());
+    else {
+      fprintf(g, "kmer_size %u\nwords_per_edge %u\nnum_files 1\nnum_buckets 0\nnum_edges %llu\nis_sorted 0\n", o->k + o->step,
+              res.words_per_edge, (unsigned long long)res.n_edges);
+      fclose(g);
+    }
+  }
+  XINFO("iterate done. Time elapsed: %.4f (GPU %.2f ms)\n", now_s() - t0, res.t_total_ms);
+  mhb_free(res.edges);
   return rc;
 }

@@ -166,6 +166,45 @@ int main_seq2sdbg(int argc, char **argv) {
 
 int forward_to_reference(char **argv);
 
+// main_iterate (main_iterate.cpp:57-112, 196-221)
+int main_iterate(int argc, char **argv, char **full_argv) {
+  RssRecorder rec;
+  const std::vector<Opt> opts = {{"contig_file", "c", false}, {"bubble_file", "b", false},     {"read_file", "r", false},
+                                 {"num_cpu_threads", "t", false}, {"kmer_k", "k", false},       {"step", "s", false},
+                                 {"output_prefix", "o", false}};
+  const char *usage = "Usage: megahit_core iterate [opt]\nopt with (*) are must";
+  std::map<std::string, std::string> v;
+  std::string err;
+  if (!parse(argc, argv, opts, &v, &err)) return fail_usage(err, usage);
+  mhb_iterate_opts o;
+  memset(&o, 0, sizeof(o));
+  const std::string c = v["contig_file"], b = v["bubble_file"], r = v["read_file"], out = v["output_prefix"];
+  o.contig_file = c.c_str();
+  o.bubble_file = b.c_str();
+  o.read_file = r.c_str();
+  o.output_prefix = out.c_str();
+  o.num_cpu_threads = v.count("num_cpu_threads") ? atoi(v["num_cpu_threads"].c_str()) : 0;
+  const int k = v.count("kmer_k") ? atoi(v["kmer_k"].c_str()) : 0, step = v.count("step") ? atoi(v["step"].c_str()) : 0;
+  if (c.empty()) return fail_usage("No contig file!", usage);
+  if (b.empty()) return fail_usage("No bubble file!", usage);
+  if (r.empty()) return fail_usage("No reads file!", usage);
+  if (k <= 0) return fail_usage("Invalid kmer size!", usage);
+  if (step <= 0 || step > 28 || step % 2 == 1) return fail_usage("Invalid step size!", usage);
+  if (out.empty()) return fail_usage("No output prefix!", usage);
+  o.k = (uint32_t)k;
+  o.step = (uint32_t)step;
+  if (k < 9 || k + 1 > 240 || r == "-") {  // outside the device path (17-word records; stdin): the reference's CPU path
+    fprintf(stderr, "megahit_b200: iterate with k = %d is forwarded to the reference\n", k);
+    return forward_to_reference(full_argv);
+  }
+  if (int rc = mhb_iterate_run(&o)) {
+    fprintf(stderr, "FATAL megahit_b200: %s\n", mhb_last_error());
+    (void)rc;
+    exit(1);
+  }
+  return 0;
+}
+
 // main_read2sdbg (main_sdbg_build.cpp:88-156)
 int main_read2sdbg(int argc, char **argv, char **full_argv) {
   RssRecorder rec;
@@ -227,13 +266,14 @@ int forward_to_reference(char **argv) {
 
 int main(int argc, char **argv) {
   if (argc < 2) {
-    fprintf(stderr, "Usage: %s <sub_program> [sub options]\n    GPU sub-programs: count, seq2sdbg, read2sdbg; everything else is forwarded to the reference megahit_core\n", argv[0]);
+    fprintf(stderr, "Usage: %s <sub_program> [sub options]\n    GPU sub-programs: count, seq2sdbg, read2sdbg, iterate; everything else is forwarded to the reference megahit_core\n", argv[0]);
     return 1;
   }
   const std::string cmd = argv[1];
   if (cmd == "count") return main_count(argc - 1, argv + 1);
   if (cmd == "seq2sdbg") return main_seq2sdbg(argc - 1, argv + 1);
   if (cmd == "read2sdbg") return main_read2sdbg(argc - 1, argv + 1, argv);
+  if (cmd == "iterate") return main_iterate(argc - 1, argv + 1, argv);
   if (cmd == "checkcpu" || cmd == "checkpopcnt" || cmd == "checkbmi2") {
     printf("1\n");
     return 0;

@@ -103,6 +103,22 @@ class Read2SdbgOpts(C.Structure):
                 ("need_mercy", C.c_int32)]
 
 
+class IterateArgs(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("step", C.c_uint32), ("contig_words", C.c_void_p), ("contig_word_off", C.c_void_p),
+                ("contig_len", C.c_void_p), ("n_contigs", C.c_uint64), ("bin", C.c_void_p), ("bin_words", C.c_uint64),
+                ("n_reads", C.c_uint64)]
+
+
+class IterateResult(C.Structure):
+    _fields_ = [("n_flanks", C.c_uint64), ("n_aligned_reads", C.c_uint64), ("n_candidates", C.c_uint64), ("n_edges", C.c_uint64),
+                ("words_per_edge", C.c_uint32), ("edges", C.POINTER(C.c_uint32)), ("t_total_ms", C.c_double)]
+
+
+class IterateOpts(C.Structure):
+    _fields_ = [("contig_file", C.c_char_p), ("bubble_file", C.c_char_p), ("read_file", C.c_char_p),
+                ("num_cpu_threads", C.c_int32), ("k", C.c_uint32), ("step", C.c_uint32), ("output_prefix", C.c_char_p)]
+
+
 # every symbol include/mhb.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
     "mhb_last_error", "mhb_version", "mhb_device_count", "mhb_launch_count", "mhb_count_record_words", "mhb_words_per_edge",
@@ -113,7 +129,7 @@ SYMBOLS = [
     "mhb_s2s_emit_scratch_bytes", "mhb_s2s_emit", "mhb_set_device", "mhb_count_host", "mhb_s2s_host", "mhb_build_host", "mhb_free",
     "mhb_mercy_candidates_scratch_bytes", "mhb_mercy_candidates", "mhb_mercy_edges_scratch_bytes", "mhb_mercy_edges", "mhb_mercy_edges_count", "mhb_mercy_edges_write", "mhb_mercy_edges_segs", "mhb_mercy_host", "mhb_mercy_planes_words", "mhb_mercy_probe_owned", "mhb_mercy_count_planes", "mhb_edge_lut_bytes", "mhb_edge_lut_build",
     "mhb_release", "mhb_count_run", "mhb_count_run_multi", "mhb_seq2sdbg_run", "mhb_selftest_count_record", "mhb_selftest_count_records_roll", "mhb_selftest_s2s_record",
-    "mhb_s2s_extract_edges_pruned", "mhb_s2s_emit_fmt", "mhb_read2sdbg_host", "mhb_read2sdbg_run", "mhb_selftest_r2s_s1_record", "mhb_selftest_r2s_item",
+    "mhb_iterate_host", "mhb_iterate_run", "mhb_selftest_iterate", "mhb_s2s_extract_edges_pruned", "mhb_s2s_emit_fmt", "mhb_read2sdbg_host", "mhb_read2sdbg_run", "mhb_selftest_r2s_s1_record", "mhb_selftest_r2s_item",
     "mhb_selftest_kmsort", "mhb_selftest_kmsort_smem", "mhb_selftest_r2s_s1_group", "mhb_selftest_r2s_mercy_read",
 ]
 
@@ -212,6 +228,9 @@ def load():
     L.mhb_selftest_s2s_record.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_uint32, C.c_void_p]
     L.mhb_s2s_emit_fmt.argtypes = L.mhb_s2s_emit.argtypes + [C.c_int]
+    L.mhb_iterate_host.argtypes = [C.POINTER(IterateArgs), C.POINTER(IterateResult)]
+    L.mhb_selftest_iterate.argtypes = [C.POINTER(IterateArgs), C.POINTER(IterateResult)]
+    L.mhb_iterate_run.argtypes = [C.POINTER(IterateOpts)]
     L.mhb_s2s_extract_edges_pruned.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32,
                                                C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
     L.mhb_read2sdbg_host.argtypes = [C.POINTER(BuildArgs), C.POINTER(BuildResult)]
@@ -477,6 +496,40 @@ def seq2sdbg_run(output_prefix: str, k: int, k_from: int = 0, input_prefix: str 
     o = Seq2SdbgOpts(host_mem, k, k_from, num_cpu_threads, contig.encode(), bubble.encode(), addi_contig.encode(),
                      local_contig.encode(), input_prefix.encode(), output_prefix.encode(), int(need_mercy), mem_flag)
     _check(load().mhb_seq2sdbg_run(C.byref(o)))
+
+
+def iterate_host(contig_words: np.ndarray, contig_word_off: np.ndarray, contig_len: np.ndarray, bin_words: np.ndarray,
+                 n_reads: int, k: int, step: int, selftest: bool = False) -> dict:
+    """`megahit_core iterate` (main_iterate.cpp): contigs (file orientation, flag-filtered) + read library in, the set of
+    iterative edges for k + step out (ascending `.edges` records, multiplicity 0).  selftest: the host mirror of the
+    device code (CPU tests), not a compute path."""
+    L = load()
+    cw = np.ascontiguousarray(contig_words, np.uint32)
+    if len(cw) == 0:
+        cw = np.zeros(1, np.uint32)
+    co = np.ascontiguousarray(contig_word_off, np.uint64)
+    cl = np.ascontiguousarray(contig_len, np.uint32)
+    n_contigs = len(cl)
+    if n_contigs == 0:
+        cl = np.zeros(1, np.uint32)
+    b = np.ascontiguousarray(bin_words, np.uint32).reshape(-1)
+    a = IterateArgs(k, step, cw.ctypes.data, co.ctypes.data, cl.ctypes.data, n_contigs, b.ctypes.data if len(b) else None,
+                    len(b), n_reads)
+    r = IterateResult()
+    _check((L.mhb_selftest_iterate if selftest else L.mhb_iterate_host)(C.byref(a), C.byref(r)))
+    W = r.words_per_edge
+    out = {"n_flanks": r.n_flanks, "n_aligned_reads": r.n_aligned_reads, "n_candidates": r.n_candidates, "n_edges": r.n_edges,
+           "edges": np.ctypeslib.as_array(r.edges, (max(r.n_edges, 1) * W,))[: r.n_edges * W].reshape(-1, W).copy(),
+           "ms": r.t_total_ms}
+    L.mhb_free(r.edges)
+    return out
+
+
+def iterate_run(contig_file: str, bubble_file: str, read_file: str, output_prefix: str, k: int, step: int,
+                num_cpu_threads: int = 0) -> None:
+    o = IterateOpts(contig_file.encode(), bubble_file.encode(), read_file.encode(), num_cpu_threads, k, step,
+                    output_prefix.encode())
+    _check(load().mhb_iterate_run(C.byref(o)))
 
 
 def read2sdbg_run(read_lib_file: str, output_prefix: str, k: int = 21, m: int = 2, need_mercy: bool = False,
