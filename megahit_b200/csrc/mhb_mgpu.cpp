@@ -480,7 +480,8 @@ void worker(const Job &J, Exchange &X) {
   X.barrier();
 
   // ---- SdBG stage over solid + mercy edges ----
-  const uint64_t n_seqs = n_solid + n_mercy, n_items = n_seqs * 6;
+  const uint64_t n_seqs = n_solid + n_mercy;
+  uint64_t n_items = n_seqs * 6;
   mhb_dev_seqs seqs;
   memset(&seqs, 0, sizeof(seqs));
   seqs.words = d_all_edges;
@@ -490,7 +491,18 @@ void worker(const Job &J, Exchange &X) {
   seqs.fixed_stride = WE;
   uint32_t *d_sa = pool.get<uint32_t>(n_items * W2 + 16);
   CKC(cudaMemset(d_hist, 0, 256 * 8));
-  CKM(mhb_s2s_extract(nullptr, &seqs, k, d_sa, n_items, d_hist, top2));
+  if (getenv("MHB_S2S_NO_PRUNE")) {
+    CKM(mhb_s2s_extract(nullptr, &seqs, k, d_sa, n_items, d_hist, top2));
+  } else {
+    // the owned solid edges still carry the count stage's in/out flags: the $-items the emitter is certain to discard are
+    // neither generated nor exchanged (mhb_s2s_extract_edges_pruned)
+    CKC(cudaMemset(d_ns + 4, 0, 8));
+    CKM(mhb_s2s_extract_edges_pruned(nullptr, d_all_edges, d_aux, n_seqs, n_solid, k, d_sa, n_items, d_ns + 4, d_hist, top2));
+    uint64_t kept = 0;
+    CKC(cudaMemcpy(&kept, d_ns + 4, 8, cudaMemcpyDeviceToHost));
+    if (kept > n_items) fail("internal: pruned item count exceeds 6 per edge");
+    n_items = kept;
+  }
   ws_bytes = mhb_sort_workspace_bytes(std::max<uint64_t>(n_items, 1), W2);
   d_ws = pool.get<char>(ws_bytes);
   PeerBuf ps;
