@@ -424,6 +424,9 @@ typedef struct {
   double t_total_ms, t_h2d_ms, t_count_ms, t_mercy_ms, t_s2s_ms, t_d2h_ms;
 } mhb_build_result;
 
+/* A13: when the resident plan does not fit in device memory (cudaMalloc fails), or a round cap is set with
+ * mhb_set_round_limit / mhb_set_s2s_round_limit, the same graph is built stage by stage - count in rounds over bucket
+ * ranges -> mercy edges -> seq2sdbg in rounds - with the solid edges passing through host memory once; same outputs. */
 int mhb_build_host(const mhb_build_args *args, mhb_build_result *res);
 
 /* The 1-pass k_min build (main_read2sdbg, main_sdbg_build.cpp:88-156; `megahit --kmin-1pass`, and the route the driver

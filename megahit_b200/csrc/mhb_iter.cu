@@ -108,9 +108,18 @@ extern "C" int mhb_iterate_host(const mhb_iterate_args *a, mhb_iterate_result *r
   if (mhb_device_count() <= 0) return mhb_set_error(MHB_ERR_CUDA, "no CUDA device: libmhb has no CPU path");
   res->words_per_edge = w2;
   cudaStream_t st = 0;
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
+  struct Events {
+    cudaEvent_t a, b;
+    Events() {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+    }
+    ~Events() {
+      cudaEventDestroy(a);
+      cudaEventDestroy(b);
+    }
+  } ev;
+  cudaEvent_t e0 = ev.a, e1 = ev.b;
   cudaEventRecord(e0, st);
   const int WCc = cap_class(std::max(wn, wk));
 
@@ -259,8 +268,6 @@ extern "C" int mhb_iterate_host(const mhb_iterate_args *a, mhb_iterate_result *r
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   res->t_total_ms = ms;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   return MHB_OK;
 }
 

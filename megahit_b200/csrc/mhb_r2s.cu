@@ -338,6 +338,20 @@ extern "C" int mhb_read2sdbg_host(const mhb_build_args *args, mhb_build_result *
   res->n_edge_records = ix.n_edges;
   res->bucket_table = (uint64_t *)calloc((size_t)MHB_NUM_BUCKETS * 4, 8);
   res->counting = (int64_t *)calloc(65536, 8);
+  struct ResGuard {  // a failing call hands nothing back
+    mhb_build_result *r;
+    const uint8_t *caller_buf;
+    bool ok = false;
+    ~ResGuard() {
+      if (ok) return;
+      free(r->bucket_table);
+      free(r->counting);
+      if (r->bytes != caller_buf) free(r->bytes);
+      r->bucket_table = nullptr;
+      r->counting = nullptr;
+      r->bytes = nullptr;
+    }
+  } guard{res, args->sdbg_out};
   if (!res->bucket_table || !res->counting) return mhb_set_error(MHB_ERR_NOMEM, "host malloc failed");
 
   // ---- the package: reversed reads on the device ----
@@ -527,6 +541,7 @@ extern "C" int mhb_read2sdbg_host(const mhb_build_args *args, mhb_build_result *
   res->t_d2h_ms = tr.sum("d2h");
   res->t_total_ms = tr.sum("");
   tr.report();
+  guard.ok = true;
   return MHB_OK;
 }
 
