@@ -129,7 +129,8 @@ def test_reference_assemble_consumes_our_sdbg(name, k, tmp_path):
 def test_reference_python_driver_runs_on_our_core(tmp_path):
     """src/megahit (the reference's driver, next to the reference binary as its build places it) with OUR megahit_core
     in its bin directory: checkcpu/kmax probes, count + seq2sdbg on the GPU for every k of the list (k_min from the read
-    library with mercy edges, k > k_min from contigs + iterate's unsorted edges), everything else forwarded."""
+    library with mercy edges, k > k_min from contigs + the iterative edges), `iterate` between the k's on the GPU as well
+    (since round 2), everything else forwarded; the final contigs must equal those of the reference core."""
     _need_ref()
     if not os.path.exists(DRIVER):
         pytest.fail("oracle/_ref/megahit (the reference's driver script) is missing: make -C oracle ref")
