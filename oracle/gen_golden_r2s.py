@@ -36,6 +36,7 @@ RUNS = [
     ("golden/polya_k27", 27, 2, 1), ("golden/polya_k27", 27, 1, 0), ("golden/tandem_k27", 27, 2, 1),
     ("golden/tandem_k27", 28, 2, 1), ("golden/lowcov_k21", 21, 2, 1), ("golden/empty_k21", 21, 2, 1),
     ("golden_kmax/syn300_k255", 255, 1, 0), ("golden_kmax/syn300_k255", 255, 2, 1), ("golden_kmax/syn300_k255", 199, 2, 1),
+    ("golden_kmax/syn300_k255", 237, 2, 1),  # the widest stage-1 record the device sort takes (17 words)
     # buckets far above kmsort's insertion-sort threshold (64): the American-flag permutation decides the tie order
     ("synth:deep", 27, 2, 1), ("synth:deep", 21, 3, 1), ("synth:wide", 27, 2, 1), ("synth:wide", 23, 1, 0),
     ("synth:mid", 27, 2, 1),
