@@ -1,7 +1,7 @@
 """GPU tests of read2sdbg (the 1-pass route: `megahit --kmin-1pass`, and what the driver runs for
 --min-count 1): the CUDA path through the C ABI against
 
-* the fixtures minted by the unmodified reference binary (tests/golden_r2s/r2s.json) - 27 runs: toy set, synthetic
+* the fixtures minted by the unmodified reference binary (tests/golden_r2s/r2s.json) - 28 runs: toy set, synthetic
   150 bp reads at k = 21 ... 141 and the reference's k = 255 / min-count 1 case, variable-length reads, poly-A,
   tandem repeats, end-overlapping reads (13 x more mercy than solid edges), and three seeded libraries whose buckets lie
   far above kmsort's insertion-sort threshold, where the reference's result depends on kmsort's order among tied
