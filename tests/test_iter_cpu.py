@@ -43,3 +43,37 @@ def test_host_mirror_duplicate_flanks_and_short_contigs():
     want, aligned = O.iterate(cs, O.unpack_bin(data, reverse=False), k, step)
     got = lib.iterate_host(cs.words, cs.word_off, cs.len, np.frombuffer(data, np.uint32), len(reads), k, step, selftest=True)
     assert len(want) > 0 and (got["edges"] == want).all() and got["n_aligned_reads"] == aligned
+
+
+@pytest.mark.parametrize("k,step,seed", [(15, 2, 1), (31, 28, 2), (47, 16, 3), (63, 2, 4), (99, 28, 5), (141, 28, 6), (211, 28, 7), (239, 4, 8)])
+def test_host_mirror_matches_oracle_on_random_contig_sets(k, step, seed):
+    """every register-width class of the kernels (2 / 4 / 8 / 17 words) up to the widest flank record (k + 1 = 240):
+    contigs = a repeat-rich genome cut at arbitrary places with k-base overlaps, reads of mixed lengths and strands"""
+    rng = np.random.default_rng(seed)
+    G = 6000
+    g = rng.integers(0, 4, G, dtype=np.uint8)
+    for rl in (k + 3, k + step // 2, 2 * k):
+        rep = rng.integers(0, 4, rl, dtype=np.uint8)
+        for p in rng.choice(G - rl, 3, replace=False):
+            g[p:p + rl] = rep
+    cuts = np.sort(rng.choice(np.arange(k + 2, G - k - 2), 14, replace=False))
+    bounds = [0] + list(cuts) + [G]
+    contigs = [g[max(0, a - k):b] for a, b in zip(bounds[:-1], bounds[1:])]
+    contigs += [3 - c[::-1] for c in contigs[::3]]                      # some given on the other strand
+    contigs += [g[100:100 + k + 1], g[300:300 + k]]                     # exactly k+1 bases; too short
+    rows = [F.pack_reads_fixed(c[None, :])[0][1:] for c in contigs]
+    off = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.uint64)
+    cs = O.Seqs(np.concatenate(rows), off, np.array([len(c) for c in contigs], np.uint32))
+    reads = []
+    for _ in range(300):
+        Lr = int(rng.integers(k, 3 * k + 2 * step + 40))
+        p = int(rng.integers(0, G - Lr))
+        r = g[p:p + Lr].copy()
+        e = rng.random(Lr) < 0.004
+        r[e] = (r[e] + 1) & 3
+        reads.append(3 - r[::-1] if rng.integers(0, 2) else r)
+    data = b"".join(F.pack_read(r).tobytes() for r in reads)
+    want, aligned = O.iterate(cs, O.unpack_bin(data, reverse=False), k, step)
+    got = lib.iterate_host(cs.words, cs.word_off, cs.len, np.frombuffer(data, np.uint32), len(reads), k, step, selftest=True)
+    assert len(want) > 0, "vacuous case"
+    assert got["n_edges"] == len(want) and (got["edges"] == want).all() and got["n_aligned_reads"] == aligned

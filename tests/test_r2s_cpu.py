@@ -8,6 +8,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
+from megahit_b200 import formats as F
 from megahit_b200 import lib, synth
 from oracle import oracle as O
 from test_oracle_r2s import R2S, r2s_reads
@@ -160,3 +161,19 @@ def test_stage1_and_mercy_on_host_match_oracle(case):
     bits = np.unpackbits(want["is_solid"], bitorder="little")[: n * Lr]
     got = np.unpackbits(solid.view(np.uint8), bitorder="little")[: n * Lr]
     assert (got == bits).all()
+
+
+@pytest.mark.parametrize("k", [9, 11, 15, 17, 23, 33, 45, 47, 49, 63, 65, 79, 95, 97, 111, 127, 129, 159, 191, 223, 237])
+def test_stage1_records_every_key_width(k):
+    """every instantiated key width (1 .. 15 words) of the stage-1 record builder against the oracle on random reads"""
+    rng = np.random.default_rng(k)
+    for Ln in (k + 1, k + 2, k + 17, 2 * k + 5):
+        b = rng.integers(0, 4, Ln, dtype=np.uint8)
+        if Ln > k + 3:
+            b[3:3 + (k - 1)] = np.concatenate([b[3:3 + (k - 1) // 2], (3 - b[3:3 + (k - 1) // 2][::-1])])[: k - 1]  # near-palindrome
+        reads = O.unpack_bin(F.pack_read(b).tobytes(), reverse=True)
+        want = oracle_s1_records(reads, 0, k, 12345)
+        w = reads.words[: int(reads.word_off[1])]
+        assert len(want) == Ln - k + 4
+        for e in range(len(want)):
+            assert (lib.selftest_r2s_s1_record(w, Ln, k, e, 12345) == want[e]).all(), (k, Ln, e)
